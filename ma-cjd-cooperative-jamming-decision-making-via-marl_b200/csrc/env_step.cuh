@@ -1,0 +1,272 @@
+// Fused batched environment step (K1 of SURVEY.md): one thread per episode.
+//
+// For every env the kernel evaluates what simulation/environment.py:221-477 does for its
+// single instance: action decode, jammer power bookkeeping and r_p, Friis jamming power
+// per jammer->radar link (core/jammer.py:56-98), radar-equation echo power per
+// radar-target pair (core/radar.py:35-60), SNR with / without suppression jamming,
+// Albersheim Pd (core/radar.py:67-82), Monte-Carlo detection and false-target draws,
+// r_d / r_j, termination -- and rewrites the static views (state, obs, avail-action
+// mask; environment.py:479-551).  Extensions: K > 1 targets, JSR in dB,
+// networked Pd.
+//
+// Numerics: float64, the reference's own number type (it decides `u <= pd` and the
+// catastrophically cancelling pd0 - pd1 of r_j), outputs rounded to float32 on store.
+// B200 has full-rate-class FP64 (64 lanes/SM); the kernel stays HBM-bound.
+//
+// Memory: scenario tables are struct-of-arrays [row][env] so a warp's table loads are
+// contiguous; per-env scalars out are [field][env]; the row-major views the agent
+// kernel consumes (state [env][S], obs [env][J][S], avail [env][J][A]) are staged in
+// shared memory and written back with coalesced 16-byte stores.
+#pragma once
+#include "macjd_common.cuh"
+
+namespace macjd {
+
+struct EnvKernelArgs {
+  macjd_env_tables tab;
+  macjd_env_io io;
+  int state_dim;      // S = R*(6+types) + 2J
+  int n_actions;      // A = 2R+1
+  int stage_ld;       // padded row length of the smem state stage (odd -> no bank conflicts)
+  int physics;        // 0: reset (views only, step_count <- 0), 1: full step
+};
+
+__device__ __forceinline__ double env_tab(const macjd_env_tables& t, int row, int env) {
+  return __ldg(t.data + (int64_t)row * t.row_stride + (int64_t)env * t.env_stride);
+}
+
+__device__ __forceinline__ double albersheim(const macjd_env_tables& t, double snr) {
+  // core/radar.py:67-82 (prfa, m folded into alb_a / alb_zoff / alb_den on the host)
+  const double s = snr > 0.0 ? snr : 0.0;
+  const double z = s + t.alb_zoff;
+  const double b = (10.0 * z - t.alb_a) / t.alb_den;
+  if (b > 700.0) return 1.0;
+  if (b < -700.0) return 0.0;
+  return 1.0 / (1.0 + exp(-b));
+}
+
+__global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
+  const macjd_env_tables& T = a.tab;
+  const macjd_env_io& io = a.io;
+  const int n = T.n_envs, J = T.n_jammers, R = T.n_radars, K = T.n_targets;
+  const int RK = R * K, S = a.state_dim, A = a.n_actions;
+  const int BS = blockDim.x, tid = threadIdx.x;
+  const int e0 = blockIdx.x * BS;
+  const int e = e0 + tid;
+  const bool live = e < n;
+  const int rbase = 0, jbase = 16 * R, tbase = 16 * R + 8 * J;
+
+  MACJD_DYNAMIC_SMEM(double, smem);
+  // per-thread scratch, [slot][thread] so that a warp touches consecutive banks
+  double* prjs = smem;                 // [R][BS] accumulated suppression power per radar
+  double* prod = smem + (size_t)R * BS;  // [R][BS] prod(1 - pd_f) over detected false targets
+  double* pnet = smem + (size_t)2 * R * BS;  // [K][BS] prod_r (1 - pd[r][k])
+  float* stage = reinterpret_cast<float*>(smem + (size_t)(2 * R + K) * BS);  // [BS][stage_ld]
+
+  if (live && a.physics) {
+    for (int r = 0; r < R; ++r) { prjs[r * BS + tid] = 0.0; prod[r * BS + tid] = 1.0; }
+    for (int k = 0; k < K; ++k) pnet[k * BS + tid] = 1.0;
+    const int step = io.step_count[e] + 1;  // environment.py:235
+    uint64_t supp_mask = 0, hit_mask = 0;
+    double r_p = 0.0;
+
+    // ---- jammer loop (environment.py:248-302)
+    for (int j = 0; j < J; ++j) {
+      const int jr = jbase + 8 * j;
+      const int Ti = io.act_d[(int64_t)e * J + j];
+      double P = (double)io.act_p[(int64_t)e * J + j];
+      P = P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
+      const double pmin = env_tab(T, jr + 6, e), pmax = env_tab(T, jr + 7, e);
+      const double range = pmax - pmin;
+      const double power = pmin + P * range;
+      const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
+      r_p += T.rp_max + (T.rp_min - T.rp_max) * norm;   // charged even when idle
+      if (io.jam_power) io.jam_power[(int64_t)j * n + e] = (float)power;
+      if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
+        const int tgt = (Ti + 1) / 2 - 1;
+        const int rr = rbase + 16 * tgt;
+        const double dx = env_tab(T, jr + 4, e) - env_tab(T, rr + 10, e);
+        const double dy = env_tab(T, jr + 5, e) - env_tab(T, rr + 11, e);
+        const double dist = sqrt(dx * dx + dy * dy);
+        if (dist > 1e-6) {
+          // core/jammer.py:73-98
+          const double dsq = fmax(1e-9, dist * dist);
+          const double den = dsq * env_tab(T, jr + 1, e) * env_tab(T, jr + 2, e) * fmax(1e-9, env_tab(T, jr + 3, e));
+          double prj = 0.0;
+          if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * env_tab(T, jr + 0, e) * env_tab(T, rr + 2, e)) / den);
+          if (Ti & 1) {  // suppression
+            prjs[tgt * BS + tid] += prj;
+            supp_mask |= (1ull << tgt);
+          } else {       // deception: false target (environment.py:408-437)
+            const double pn = env_tab(T, rr + 6, e);
+            double snr_f = pn > 1e-18 ? (env_tab(T, rr + 8, e) * prj) / pn : 0.0;
+            snr_f = fmax(0.0, snr_f);
+            const double pd_f = albersheim(T, snr_f);
+            const float u = io.noise ? io.noise[(int64_t)e * (RK + J) + RK + j]
+                                     : philox_uniform(io.seed, kStreamEnvNoise, (uint32_t)e, (uint32_t)step, (uint32_t)(RK + j));
+            if ((double)u <= pd_f) {
+              prod[tgt * BS + tid] *= (1.0 - fmin(pd_f, 0.999999));
+              hit_mask |= (1ull << tgt);
+            }
+          }
+        }
+      }
+    }
+
+    // ---- radar x target loop (environment.py:316-349, 359-366, 385-398)
+    const double four_pi3 = (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793);
+    double r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
+    for (int r = 0; r < R; ++r) {
+      const int rr = rbase + 16 * r;
+      const double pt = env_tab(T, rr + 0, e), gt = env_tab(T, rr + 1, e), gr = env_tab(T, rr + 2, e);
+      const double lam = env_tab(T, rr + 3, e), loss = env_tab(T, rr + 4, e), latm = env_tab(T, rr + 5, e);
+      const double pn = env_tab(T, rr + 6, e), Ga = env_tab(T, rr + 7, e), D = env_tab(T, rr + 8, e);
+      const double rx = env_tab(T, rr + 10, e), ry = env_tab(T, rr + 11, e);
+      const double jam = D * prjs[r * BS + tid];
+      const double den1 = jam + pn;
+      const double num0 = pt * gt * gr * (lam * lam);
+      bool tracked = false;
+      double red = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const int tr = tbase + 3 * k;
+        const double dx = rx - env_tab(T, tr + 0, e), dy = ry - env_tab(T, tr + 1, e);
+        const double d = fmax(sqrt(dx * dx + dy * dy), 1e-6);
+        const double num = num0 * env_tab(T, tr + 2, e);
+        const double d2 = d * d;
+        const double den = four_pi3 * (d2 * d2) * loss * latm;
+        const double ps = den > 1e-18 ? num / den : 0.0;
+        const double sig = Ga * ps;
+        const double snr0 = fmax(0.0, pn > 1e-18 ? sig / pn : 0.0);
+        const double snr1 = den1 > 1e-18 ? sig / den1 : 0.0;
+        const double pd = albersheim(T, snr1);
+        const int slot = r * K + k;
+        const float u = io.noise ? io.noise[(int64_t)e * (RK + J) + slot]
+                                 : philox_uniform(io.seed, kStreamEnvNoise, (uint32_t)e, (uint32_t)step, (uint32_t)slot);
+        const bool det = (double)u <= pd;
+        tracked |= det;
+        red += fmax(0.0, albersheim(T, snr0) - pd);
+        pnet[k * BS + tid] *= (1.0 - pd);
+        const int64_t o = (int64_t)slot * n + e;
+        if (io.pd) io.pd[o] = (float)pd;
+        if (io.detected) io.detected[o] = det ? 1 : 0;
+        if (io.snr0) io.snr0[o] = (float)snr0;
+        if (io.snr1) io.snr1[o] = (float)fmax(0.0, snr1);
+        if (io.jsr_db) io.jsr_db[o] = (float)(10.0 * log10(jam / sig));
+      }
+      if (io.tracking) io.tracking[(int64_t)r * n + e] = tracked ? 1 : 0;
+      if (tracked) {  // memoryless TRACK state (core/radar.py:90-117) -> r_d
+        const double pen = -env_tab(T, rr + 9, e);
+        r_d += fmin(fmax(pen, T.rd_min), T.rd_max);
+      }
+      if ((supp_mask >> r) & 1ull) r_j_supp += red;
+      if ((hit_mask >> r) & 1ull) r_j_dec += 1.0 - prod[r * BS + tid];
+    }
+    if (io.pd_net)
+      for (int k = 0; k < K; ++k) io.pd_net[(int64_t)k * n + e] = (float)(1.0 - pnet[k * BS + tid]);
+
+    const double r_j = r_j_supp + r_j_dec;
+    const double reward = r_d + r_p + r_j;                 // environment.py:457
+    const bool term = step >= T.episode_limit;             // environment.py:460
+    io.reward[e] = (float)reward;
+    if (io.reward64) io.reward64[e] = reward;
+    if (io.r_d) io.r_d[e] = (float)r_d;
+    if (io.r_p) io.r_p[e] = (float)r_p;
+    if (io.r_j) io.r_j[e] = (float)r_j;
+    if (io.terminated) io.terminated[e] = term ? 1 : 0;
+    io.step_count[e] = (term && io.auto_reset) ? 0 : step;
+  } else if (live && !a.physics) {
+    io.step_count[e] = 0;                                  // environment.py:203
+  }
+
+  // ---- static views (environment.py:479-551): stage one state row per thread
+  const bool want_views = (io.state != nullptr) || (io.obs != nullptr);
+  if (want_views) {
+    if (live) {
+      float* row = stage + (size_t)tid * a.stage_ld;
+      const int per = 6 + T.n_types;
+      for (int r = 0; r < R; ++r) {
+        const int rr = rbase + 16 * r, o = r * per;
+        row[o + 0] = (float)env_tab(T, rr + 0, e);          // pt
+        row[o + 1] = (float)env_tab(T, rr + 12, e);         // theta_m
+        row[o + 2] = (float)env_tab(T, rr + 14, e);         // t_s
+        const int ty = (int)env_tab(T, rr + 15, e);
+        for (int c = 0; c < T.n_types; ++c) row[o + 3 + c] = (c == ty) ? 1.0f : 0.0f;
+        row[o + 3 + T.n_types] = (float)env_tab(T, rr + 13, e);  // theta_a
+        row[o + 4 + T.n_types] = (float)env_tab(T, rr + 10, e);
+        row[o + 5 + T.n_types] = (float)env_tab(T, rr + 11, e);
+      }
+      for (int j = 0; j < J; ++j) {
+        row[R * per + 2 * j] = (float)env_tab(T, jbase + 8 * j + 4, e);
+        row[R * per + 2 * j + 1] = (float)env_tab(T, jbase + 8 * j + 5, e);
+      }
+    }
+    __syncthreads();
+    const int valid = min(BS, n - e0);
+    if ((S & 3) == 0 && (a.stage_ld & 3) == 0) {
+      // rows are 16-byte multiples: coalesced float4 stores
+      const int S4 = S >> 2, ld4 = a.stage_ld >> 2;
+      const float4* st4 = reinterpret_cast<const float4*>(stage);
+      if (io.state) {
+        float4* dst = reinterpret_cast<float4*>(io.state + (int64_t)e0 * S);
+        for (int v = tid; v < valid * S4; v += BS) { const int el = v / S4; dst[v] = st4[el * ld4 + (v - el * S4)]; }
+      }
+      if (io.obs) {
+        const int JS4 = J * S4;
+        float4* dst = reinterpret_cast<float4*>(io.obs + (int64_t)e0 * J * S);
+        for (int v = tid; v < valid * JS4; v += BS) { const int el = v / JS4; dst[v] = st4[el * ld4 + (v % S4)]; }
+      }
+    } else {
+      if (io.state) {
+        float* dst = io.state + (int64_t)e0 * S;
+        for (int v = tid; v < valid * S; v += BS) { const int el = v / S; dst[v] = stage[el * a.stage_ld + (v - el * S)]; }
+      }
+      if (io.obs) {
+        const int JS = J * S;
+        float* dst = io.obs + (int64_t)e0 * JS;
+        for (int v = tid; v < valid * JS; v += BS) { const int el = v / JS; dst[v] = stage[el * a.stage_ld + (v % S)]; }
+      }
+    }
+  }
+  if (io.avail) {  // all actions always available (environment.py:539-551)
+    const int valid = min(BS, n - e0);
+    const int64_t base = (int64_t)e0 * J * A;
+    const int total = valid * J * A;
+    for (int v = tid; v < total; v += BS) io.avail[base + v] = 1;
+  }
+}
+
+inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs) {
+  return (size_t)(2 * R + K) * bs * sizeof(double) + (size_t)bs * stage_ld * sizeof(float);
+}
+
+inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
+  if (!ctx || !tab || !io) return MACJD_ERR_INVALID_ARG;
+  if (tab->n_envs < 0 || tab->n_jammers < 1 || tab->n_radars < 1 || tab->n_targets < 1 || tab->n_types < 1)
+    return MACJD_ERR_INVALID_ARG;
+  if (tab->n_radars > 64) return MACJD_ERR_UNSUPPORTED;
+  if (!tab->data || !io->step_count) return MACJD_ERR_INVALID_ARG;
+  if (physics && (!io->act_d || !io->act_p || !io->reward)) return MACJD_ERR_INVALID_ARG;
+  if (tab->n_envs == 0) return MACJD_OK;
+  EnvKernelArgs a;
+  a.tab = *tab;
+  a.io = *io;
+  a.state_dim = tab->n_radars * (6 + tab->n_types) + 2 * tab->n_jammers;
+  a.n_actions = 2 * tab->n_radars + 1;
+  // stage rows: keep 16-byte multiples when S allows float4 stores (pad by 4 -> rows shift
+  // by 4 banks, conflict-free for the row-per-thread writes), else pad to odd.
+  a.stage_ld = (a.state_dim % 4 == 0) ? a.state_dim + 4 : (a.state_dim | 1);
+  a.physics = physics;
+  int bs = 128;
+  while (bs > 32 && env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs) > 96 * 1024) bs >>= 1;
+  const size_t smem = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs);
+  if (smem > 200 * 1024) return MACJD_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return MACJD_ERR_CUDA;
+  }
+  const int grid = (tab->n_envs + bs - 1) / bs;
+  MACJD_LAUNCH(env_step_kernel, grid, bs, smem, (cudaStream_t)ctx->stream, a);
+  return MACJD_OK;
+}
+
+}  // namespace macjd

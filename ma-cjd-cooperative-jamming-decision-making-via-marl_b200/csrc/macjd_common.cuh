@@ -1,0 +1,58 @@
+// Shared device helpers for the macjd kernels (sm_100a).
+#pragma once
+
+#ifdef MACJD_TEST_HOST_EMULATION
+// CPU test suite only: the same sources compiled by g++ against tests/emul/cuda_emul.h.
+#include "cuda_emul.h"
+#else
+#include <cuda_runtime.h>
+#define MACJD_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MACJD_DYNAMIC_SMEM(type, name)                             \
+  extern __shared__ __align__(16) unsigned char macjd_dyn_smem_[]; \
+  type* name = reinterpret_cast<type*>(macjd_dyn_smem_)
+#endif
+
+#include <stdint.h>
+
+#include "../../include/macjd.h"
+
+namespace macjd {
+
+constexpr int kWarp = 32;
+constexpr int kNumSMs = 148;  // B200
+
+// ---------------------------------------------------------------- Philox4x32-10
+// Counter-based RNG (Salmon et al. 2011).  Counter = (slot/4, step, index, stream),
+// key = 64-bit seed.  The oracle reproduces the same mapping (oracle/env_oracle.py).
+struct Philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+// uint32 -> uniform float in [0,1): top 24 bits, exact in fp32.
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+enum PhiloxStream : uint32_t { kStreamEnvNoise = 1, kStreamEpsilon = 2, kStreamRandomAction = 3, kStreamReplay = 4 };
+
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t stream, uint32_t index, uint32_t step,
+                                                uint32_t slot) {
+  const Philox4 r = philox4x32_10(slot >> 2, step, index, stream, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t q = slot & 3u;
+  return u01(q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w);
+}
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace macjd
