@@ -208,7 +208,258 @@ def gen_env():
               f"pd range [{arrs['pd'].min():.4f}, {arrs['pd'].max():.4f}], r_j max {arrs['r_j'].max():.4f}")
 
 
-GENERATORS = {"env": gen_env}
+# ------------------------------------------------------------------ networks
+def rl_args(**kw):
+    base = dict(n_agents=2, n_actions=5, state_shape=24, obs_shape=24, rnn_hidden_dim=128, actor_hidden_dim=128,
+                mixing_embed_dim=64, hyper_hidden_dim=128, epsilon_start=1.0, epsilon_finish=0.05,
+                epsilon_anneal_time=100000, gamma=0.99, lr=5e-6, grad_norm_clip=1.0, target_update_interval=200,
+                use_cuda=False, device="cpu", batch_size=32, buffer_size=16, episode_limit=100)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+NET_CONFIGS = {
+    "c1": dict(),
+    "small": dict(n_agents=3, n_actions=7, state_shape=39, obs_shape=39, rnn_hidden_dim=64, actor_hidden_dim=64,
+                  mixing_embed_dim=32, hyper_hidden_dim=64),
+}
+
+
+def realistic_obs(rng, shape):
+    """Half unit normal, half with the magnitudes the real state vector has (pt ~ 300, pos ~ 400)."""
+    x = rng.standard_normal(shape).astype(np.float32)
+    scale = np.where(rng.random(shape[-1]) < 0.5, 1.0, rng.choice([5.0, 50.0, 300.0], size=shape[-1])).astype(np.float32)
+    return x * scale
+
+
+def gen_agent():
+    import torch
+    from core.mac import BasicMAC
+    for name, kw in NET_CONFIGS.items():
+        args = rl_args(**kw)
+        torch.manual_seed(42 if name == "c1" else 7)
+        with quiet():
+            mac = BasicMAC(args.obs_shape, args)
+        sd = {k: v.detach().clone() for k, v in mac.agent.state_dict().items()}
+        rng = np.random.default_rng(100 if name == "c1" else 101)
+        B, Nn, O, A, H = (6 if name == "c1" else 5), args.n_agents, args.obs_shape, args.n_actions, args.rnn_hidden_dim
+        steps = 4
+        out = {f"sd.{k}": v.numpy() for k, v in sd.items()}
+        out["n_params"] = np.array(sum(v.numel() for v in sd.values()))
+        h0 = (rng.standard_normal((B * Nn, H)) * 0.5).astype(np.float32)
+        rec = {k: [] for k in ("obs", "avail", "u", "rand_actions", "t_env", "eps", "actions", "actions_test",
+                               "power", "power_test", "hidden", "q", "params")}
+        orig_rand_like, orig_multinomial = torch.rand_like, torch.multinomial
+        mac.hidden_states = torch.from_numpy(h0.copy())
+        for t in range(steps):
+            obs = realistic_obs(rng, (B, Nn, O))
+            avail = (rng.random((B, Nn, A)) < 0.7).astype(np.int64)
+            avail[..., 0] = np.where(avail.sum(-1) == 0, 1, avail[..., 0])
+            if t == 0:
+                avail[:] = 1
+            u = rng.random((B, Nn)).astype(np.float32)
+            t_env = int(rng.integers(0, 120000))
+            # a random *available* action per agent (what torch.multinomial would draw from)
+            ra = np.array([[rng.choice(np.flatnonzero(avail[b, n])) for n in range(Nn)] for b in range(B)], dtype=np.int64)
+            h_before = mac.hidden_states.clone()
+            torch.rand_like = lambda x, _u=u: torch.from_numpy(_u.copy())
+            torch.multinomial = lambda w, num_samples, _ra=ra: torch.from_numpy(_ra.reshape(-1, 1).copy())
+            try:
+                a_test, p_test = mac.select_actions(torch.from_numpy(obs), torch.from_numpy(avail), t_env, test_mode=True)
+                mac.hidden_states = h_before.clone()
+                a, p = mac.select_actions(torch.from_numpy(obs), torch.from_numpy(avail), t_env, test_mode=False)
+            finally:
+                torch.rand_like, torch.multinomial = orig_rand_like, orig_multinomial
+            # all-action Q and params through the reference agent directly
+            x = torch.from_numpy(obs).reshape(B * Nn, O)
+            h2 = mac.agent.forward(x, h_before)
+            params = mac.agent.actor_forward(x)
+            q = torch.stack([mac.agent.get_q_value_for_action(h2, torch.full((B * Nn, 1), ai, dtype=torch.long),
+                                                              params[:, ai:ai + 1]).squeeze(1) for ai in range(A)], 1)
+            assert torch.equal(h2.detach(), mac.hidden_states)
+            rec["obs"].append(obs); rec["avail"].append(avail); rec["u"].append(u); rec["rand_actions"].append(ra)
+            rec["t_env"].append(t_env); rec["eps"].append(mac.action_selector.epsilon)
+            rec["actions"].append(a.numpy()); rec["actions_test"].append(a_test.numpy())
+            rec["power"].append(p.detach().numpy()); rec["power_test"].append(p_test.detach().numpy())
+            rec["hidden"].append(mac.hidden_states.numpy().copy()); rec["q"].append(q.detach().numpy())
+            rec["params"].append(params.detach().numpy())
+        out.update({k: np.stack(v) for k, v in rec.items()})
+        out["h0"] = h0
+        out["args_json"] = np.array(json.dumps(vars(args)))
+        np.savez_compressed(os.path.join(HERE, f"agent_{name}.npz"), **out)
+        print(f"agent_{name}: params {int(out['n_params'])}, q range [{out['q'].min():.3f}, {out['q'].max():.3f}]")
+
+
+def gen_mixer():
+    import torch
+    from core.networks import QMixer
+    for name, kw in NET_CONFIGS.items():
+        args = rl_args(**kw)
+        torch.manual_seed(3 if name == "c1" else 4)
+        mixer = QMixer(args)
+        rng = np.random.default_rng(200)
+        Rr = 37
+        q = (rng.standard_normal((Rr, args.n_agents)) * 2).astype(np.float32)
+        s = realistic_obs(rng, (Rr, args.state_shape))
+        out = {f"sd.{k}": v.detach().numpy() for k, v in mixer.state_dict().items()}
+        out["n_params"] = np.array(sum(v.numel() for v in mixer.state_dict().values()))
+        qt = torch.from_numpy(q).requires_grad_(True)
+        y = mixer(qt.view(1, Rr, args.n_agents), torch.from_numpy(s).view(1, Rr, -1)).view(Rr)
+        # gradient of sum(y * w) w.r.t. everything: pins the backward pass
+        w = rng.standard_normal(Rr).astype(np.float32)
+        (y * torch.from_numpy(w)).sum().backward()
+        out.update(q=q, s=s, y=y.detach().numpy(), w=w, dq=qt.grad.numpy())
+        out.update({f"grad.{k}": v.grad.numpy() for k, v in mixer.named_parameters()})
+        out["args_json"] = np.array(json.dumps(vars(args)))
+        np.savez_compressed(os.path.join(HERE, f"mixer_{name}.npz"), **out)
+        print(f"mixer_{name}: params {int(out['n_params'])}, y range [{out['y'].min():.3f}, {out['y'].max():.3f}]")
+
+
+def synthetic_batch(rng, args, B, T, ragged):
+    """A sampled-batch dict in the reference's layout (utils/replay_buffer.py:153-214)."""
+    Nn, A, S, O, H = args.n_agents, args.n_actions, args.state_shape, args.obs_shape, args.rnn_hidden_dim
+    lens = np.full(B, T)
+    if ragged:
+        lens[1:] = rng.integers(2, T + 1, size=B - 1)
+        lens[0] = T
+    filled = (np.arange(T)[None, :] < lens[:, None])[..., None]
+    terminated = ~filled
+    for b in range(B):
+        if ragged and lens[b] < T:
+            terminated[b, lens[b] - 1, 0] = True
+    batch = {
+        "state": realistic_obs(rng, (B, T + 1, S)),
+        "obs": realistic_obs(rng, (B, T + 1, Nn, O)),
+        "actions_discrete": rng.integers(0, A, size=(B, T, Nn, 1)).astype(np.int32),
+        "actions_continuous": rng.random((B, T, Nn, 1)).astype(np.float32),
+        "avail_actions": np.ones((B, T + 1, Nn, A), dtype=np.int64),
+        "reward": rng.standard_normal((B, T, 1)).astype(np.float32),
+        "terminated": terminated,
+        "filled": filled,
+        "hidden_state": (rng.standard_normal((B, T + 1, Nn, H)) * 0.5).astype(np.float32),
+        "max_seq_len": int(lens.max()),
+    }
+    return batch
+
+
+LEARNER_CONFIGS = {
+    "c1": dict(net="c1", B=4, T=7, ragged=False, lr=5e-6, interval=2, steps=3),
+    "small_fastlr": dict(net="small", B=5, T=6, ragged=True, lr=1e-3, interval=2, steps=4),
+}
+
+
+def gen_learner():
+    import torch
+    from core.mac import BasicMAC
+    from core.qmix import QMixLearner
+    for name, c in LEARNER_CONFIGS.items():
+        args = rl_args(**NET_CONFIGS[c["net"]], lr=c["lr"], target_update_interval=c["interval"])
+        torch.manual_seed(42)
+        with quiet():
+            mac = BasicMAC(args.obs_shape, args)
+            learner = QMixLearner(mac, args)
+        rng = np.random.default_rng(300)
+        out = {f"agent0.{k}": v.detach().numpy().copy() for k, v in mac.agent.state_dict().items()}
+        out.update({f"mixer0.{k}": v.detach().numpy().copy() for k, v in learner.eval_qmix_net.state_dict().items()})
+        for step in range(c["steps"]):
+            batch = synthetic_batch(rng, args, c["B"], c["T"], c["ragged"])
+            stats = learner.train(batch, {})
+            for k, v in batch.items():
+                out[f"step{step}.batch.{k}"] = np.asarray(v)
+            out[f"step{step}.stats"] = np.array([stats["loss"], stats["grad_norm"], stats["eval_qtot_avg"], stats["target_qtot_avg"]])
+            for k, p_ in mac.agent.named_parameters():
+                out[f"step{step}.agent_has_grad.{k}"] = np.array(p_.grad is not None)
+                if p_.grad is not None:
+                    out[f"step{step}.agent_grad.{k}"] = p_.grad.numpy().copy()      # after clipping
+            for k, p_ in learner.eval_qmix_net.named_parameters():
+                out[f"step{step}.mixer_grad.{k}"] = p_.grad.numpy().copy()
+            # only the Q-head ever changes (SURVEY fact 8): store it, assert the rest is frozen
+            a0 = {k[len("agent0."):]: v for k, v in out.items() if k.startswith("agent0.")}
+            frozen = all(np.array_equal(a0[k], v.detach().numpy()) for k, v in mac.agent.state_dict().items()
+                         if not k.startswith("fc2_q_head"))
+            out[f"step{step}.agent_untrained_unchanged"] = np.array(frozen)
+            assert frozen
+            out.update({f"step{step}.agent.{k}": v.detach().numpy().copy() for k, v in mac.agent.state_dict().items()
+                        if k.startswith("fc2_q_head")})
+            out.update({f"step{step}.mixer.{k}": v.detach().numpy().copy() for k, v in learner.eval_qmix_net.state_dict().items()})
+            out.update({f"step{step}.tgt_agent.{k}": v.detach().numpy().copy()
+                        for k, v in learner.target_mac.agent.state_dict().items() if k.startswith("fc2_q_head")})
+            out.update({f"step{step}.tgt_mixer.{k}": v.detach().numpy().copy() for k, v in learner.target_qmix_net.state_dict().items()})
+            print(f"learner_{name} step {step}: {stats}")
+        out["args_json"] = np.array(json.dumps(vars(args)))
+        out["n_steps"] = np.array(c["steps"])
+        np.savez_compressed(os.path.join(HERE, f"learner_{name}.npz"), **out)
+
+
+def gen_replay():
+    from utils.replay_buffer import EpisodeReplayBuffer
+    args = rl_args(buffer_size=5, episode_limit=6, n_agents=2, n_actions=5, state_shape=8, obs_shape=8, rnn_hidden_dim=16)
+    with quiet():
+        buf = EpisodeReplayBuffer(args)
+    rng = np.random.default_rng(400)
+    T, Nn, A, S, H = 6, 2, 5, 8, 16
+    out = {"args_json": np.array(json.dumps(vars(args)))}
+    lens = [6, 6, 3, 6, 5, 6, 6]        # 7 episodes into a ring of 5 -> wraps
+    for i, L in enumerate(lens):
+        ep = {
+            "state": [rng.standard_normal((L + 1, S)).astype(np.float32)],
+            "obs": [rng.standard_normal((L + 1, Nn, S)).astype(np.float32)],
+            "actions_discrete": [rng.integers(0, A, size=(L, Nn, 1)).astype(np.int32)],
+            "actions_continuous": [rng.random((L, Nn, 1)).astype(np.float32)],
+            "avail_actions": [np.ones((L + 1, Nn, A), dtype=np.int64)],
+            "reward": [rng.standard_normal((L, 1)).astype(np.float32)],
+            "terminated": [np.arange(L)[:, None] == L - 1],
+            "hidden_state": [rng.standard_normal((L + 1, Nn, H)).astype(np.float32)],
+        }
+        for k, v in ep.items():
+            out[f"ep{i}.{k}"] = v[0]
+        buf.store_episode(ep)
+        out[f"after{i}.current_index"] = np.array(buf.current_index)
+        out[f"after{i}.current_size"] = np.array(buf.current_size)
+        if i in (2, 6):
+            idx = rng.permutation(buf.current_size)[:3]
+            orig = np.random.choice
+            np.random.choice = lambda n, k, replace=False, _idx=idx: _idx
+            try:
+                with quiet():
+                    b = buf.sample(3)
+            finally:
+                np.random.choice = orig
+            out[f"sample{i}.indices"] = idx
+            for k, v in b.items():
+                out[f"sample{i}.{k}"] = np.asarray(v)
+    out["n_eps"] = np.array(len(lens))
+    np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
+    print("replay: stored", len(lens), "episodes; final index/size", buf.current_index, buf.current_size)
+
+
+def gen_api():
+    """Public method signatures of the reference classes on the hot-path boundary."""
+    from simulation.environment import ElectromagneticEnvironment
+    from core.mac import BasicMAC
+    from core.networks import RNNAgent, QMixer
+    from core.qmix import QMixLearner
+    from utils.replay_buffer import EpisodeReplayBuffer
+    from utils.action_selectors import EpsilonGreedyActionSelector
+    from runners.episode_runner import EpisodeRunner, EpisodeBatch
+    api = {}
+    for cls in (ElectromagneticEnvironment, BasicMAC, RNNAgent, QMixer, QMixLearner, EpisodeReplayBuffer,
+                EpsilonGreedyActionSelector, EpisodeRunner, EpisodeBatch):
+        methods = {}
+        for mname, fn in inspect.getmembers(cls, predicate=inspect.isfunction):
+            if mname.startswith("_") and mname != "__init__":
+                continue
+            if fn.__qualname__.split(".")[0] != cls.__name__:
+                continue   # inherited from nn.Module
+            methods[mname] = [p_.name for p_ in inspect.signature(fn).parameters.values()]
+        api[cls.__name__] = methods
+    with open(os.path.join(HERE, "reference_api.json"), "w") as f:
+        json.dump(api, f, indent=1, sort_keys=True)
+    print("api:", {k: len(v) for k, v in api.items()})
+
+
+GENERATORS = {"env": gen_env, "agent": gen_agent, "mixer": gen_mixer, "learner": gen_learner,
+              "replay": gen_replay, "api": gen_api}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)

@@ -1,0 +1,101 @@
+"""The eager-PyTorch agent / mixer / learner oracle against fixtures produced by the
+unmodified reference modules (tests/golden/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import agent_oracle as AO
+from tests.helpers import GOLDEN
+
+
+def load(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    args = json.loads(str(g["args_json"]))
+    return g, args
+
+
+def sd_of(g, prefix="sd."):
+    return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("name", ["c1", "small"])
+def test_agent_and_selector(name):
+    g, args = load("agent_" + name)
+    sd = sd_of(g)
+    assert sum(v.numel() for v in sd.values()) == int(g["n_params"])
+    if name == "c1":
+        assert int(g["n_params"]) == 140038
+    h = torch.from_numpy(g["h0"])
+    for t in range(g["obs"].shape[0]):
+        obs, avail = torch.from_numpy(g["obs"][t]), torch.from_numpy(g["avail"][t])
+        eps = AO.epsilon_at(int(g["t_env"][t]), args["epsilon_start"], args["epsilon_finish"], args["epsilon_anneal_time"])
+        assert eps == pytest.approx(float(g["eps"][t]), rel=1e-12)
+        a, p, h2, q, params = AO.select_actions(sd, obs, avail, h, eps, False, torch.from_numpy(g["u"][t]),
+                                                torch.from_numpy(g["rand_actions"][t]))
+        at, pt, _, _, _ = AO.select_actions(sd, obs, avail, h, eps, True, torch.from_numpy(g["u"][t]),
+                                            torch.from_numpy(g["rand_actions"][t]))
+        np.testing.assert_array_equal(a.numpy(), g["actions"][t])
+        np.testing.assert_array_equal(at.numpy(), g["actions_test"][t])
+        np.testing.assert_allclose(p.numpy(), g["power"][t], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(pt.numpy(), g["power_test"][t], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(h2.numpy(), g["hidden"][t], rtol=1e-5, atol=1e-6)
+        qm = q.reshape(-1, q.shape[-1]).numpy()
+        fin = np.isfinite(qm)
+        np.testing.assert_allclose(qm[fin], g["q"][t][fin], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(params.numpy(), g["params"][t], rtol=1e-6, atol=1e-7)
+        h = torch.from_numpy(g["hidden"][t])
+
+
+@pytest.mark.parametrize("name", ["c1", "small"])
+def test_mixer_forward_and_gradients(name):
+    g, args = load("mixer_" + name)
+    msd = {k: v.clone().requires_grad_(True) for k, v in sd_of(g).items()}
+    if name == "c1":
+        assert int(g["n_params"]) == 34481
+    q = torch.from_numpy(g["q"]).requires_grad_(True)
+    y = AO.mixer_forward(msd, q, torch.from_numpy(g["s"]), args["n_agents"], args["mixing_embed_dim"])
+    np.testing.assert_allclose(y.detach().numpy(), g["y"], rtol=1e-5, atol=1e-6)
+    (y * torch.from_numpy(g["w"])).sum().backward()
+    np.testing.assert_allclose(q.grad.numpy(), g["dq"], rtol=1e-4, atol=1e-6)
+    for k, v in msd.items():
+        ref = g["grad." + k]
+        np.testing.assert_allclose(v.grad.numpy(), ref, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(ref).max()), err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["c1", "small_fastlr"])
+def test_learner_steps(name):
+    g, args = load("learner_" + name)
+    agent0, mixer0 = sd_of(g, "agent0."), sd_of(g, "mixer0.")
+    L = AO.LearnerOracle(agent0, mixer0, args["n_agents"], args["mixing_embed_dim"], args["gamma"], args["lr"],
+                         args["grad_norm_clip"], args["target_update_interval"])
+    for step in range(int(g["n_steps"])):
+        pre = f"step{step}."
+        batch = {}
+        for k in g.files:
+            if k.startswith(pre + "batch."):
+                v = g[k]
+                batch[k[len(pre + "batch."):]] = int(v) if v.ndim == 0 else torch.from_numpy(v)
+        stats, grads, aux = L.train(batch)
+        ref = g[pre + "stats"]
+        np.testing.assert_allclose([stats["loss"], stats["grad_norm"], stats["eval_qtot_avg"], stats["target_qtot_avg"]],
+                                   ref, rtol=2e-5)
+        coef = min(1.0, args["grad_norm_clip"] / (stats["grad_norm"] + 1e-6))
+        # the reference leaves *clipped* gradients in .grad; fc1 / rnn / actor never get one
+        for k in agent0:
+            has = bool(g[pre + "agent_has_grad." + k])
+            assert has == (k in AO.TRAINED_AGENT_KEYS), k
+        for name_, gr in grads.items():
+            kind, key = name_.split(".", 1)
+            ref_g = g[pre + ("agent_grad." if kind == "agent" else "mixer_grad.") + key]
+            np.testing.assert_allclose(gr.numpy() * coef, ref_g, rtol=2e-4, atol=2e-6 * max(1e-3, np.abs(ref_g).max()), err_msg=name_)
+        for k in AO.TRAINED_AGENT_KEYS:
+            w0 = agent0[k].numpy()
+            np.testing.assert_allclose(L.agent[k].numpy() - w0, g[pre + "agent." + k] - w0, rtol=2e-3, atol=args["lr"] * 2e-3 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+            np.testing.assert_allclose(L.tgt_agent[k].numpy(), g[pre + "tgt_agent." + k], rtol=1e-5, atol=1e-6)
+        for k in mixer0:
+            w0 = mixer0[k].numpy()
+            np.testing.assert_allclose(L.mixer[k].numpy() - w0, g[pre + "mixer." + k] - w0, rtol=2e-3, atol=args["lr"] * 2e-3 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+            np.testing.assert_allclose(L.tgt_mixer[k].numpy(), g[pre + "tgt_mixer." + k], rtol=1e-5, atol=1e-6)
