@@ -29,6 +29,12 @@ extern "C" {
 
 #define MACJD_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define MACJD_API __attribute__((visibility("default")))
+#else
+#define MACJD_API
+#endif
+
 enum macjd_status {
   MACJD_OK = 0,
   MACJD_ERR_INVALID_ARG = -1,  /* NULL / out-of-range argument                         */
@@ -43,11 +49,11 @@ typedef struct macjd_ctx {
   void* stream;      /* cudaStream_t (NULL = legacy default stream) */
 } macjd_ctx;
 
-const char* macjd_status_string(int status);
-const char* macjd_last_cuda_error(void);   /* thread-local text of the last CUDA failure */
-int macjd_abi_version(void);
+MACJD_API const char* macjd_status_string(int status);
+MACJD_API const char* macjd_last_cuda_error(void);   /* thread-local text of the last CUDA failure */
+MACJD_API int macjd_abi_version(void);
 /* sizeof() of every struct below, for binding self-checks: index = order of declaration */
-size_t macjd_abi_sizeof(int which);
+MACJD_API size_t macjd_abi_sizeof(int which);
 
 /* ===================================================================== environment
  * Replaces simulation/environment.py:29-573 (ElectromagneticEnvironment) together with
@@ -110,9 +116,81 @@ typedef struct macjd_env_io {
 } macjd_env_io;
 
 /* environment.py:221-477  step(actions) for all envs. */
-int macjd_env_step(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io);
+MACJD_API int macjd_env_step(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io);
 /* environment.py:208-219  reset(): zero step_count, write state / obs / avail. */
-int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io);
+MACJD_API int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io);
+
+/* ===================================================================== agent step
+ * Replaces core/mac.py:59-198 (BasicMAC.select_actions / forward / init_hidden),
+ * core/networks.py:16-180 (RNNAgent: fc1 -> GRUCell, actor MLP, MP-DQN Q-head evaluated
+ * for every discrete action), utils/action_selectors.py:15-63 (masked epsilon-greedy) and
+ * the time-unrolled use of the same network by core/qmix.py:217-280, as ONE fused kernel
+ * per launch (csrc/agent_act.cuh).
+ *
+ * Weights are read from a packed, K-major copy of the RNNAgent state_dict
+ * (core/networks.py: pack_agent_weights builds it; every matrix is stored transposed,
+ * [in][out] with `out` contiguous, K padded with zero rows to a multiple of 32):
+ */
+typedef struct macjd_agent_weights {
+  int32_t obs_dim;        /* O                                                         */
+  int32_t obs_pad;        /* O rounded up to a multiple of 32                          */
+  int32_t hidden;         /* H  = rnn_hidden_dim,   multiple of 64, <= 256             */
+  int32_t actor_hidden;   /* AH = actor_hidden_dim, multiple of 64, <= 256             */
+  int32_t n_actions;      /* A <= 64                                                   */
+  int32_t reserved;
+  const float* wa1t;      /* [obs_pad][AH]  actor.0.weight^T                           */
+  const float* ba1;       /* [AH]                                                      */
+  const float* wa2t;      /* [AH][AH]       actor.2.weight^T                           */
+  const float* ba2;       /* [AH]                                                      */
+  const float* wa3t;      /* [AH][A]        actor.4.weight^T                           */
+  const float* ba3;       /* [A]                                                       */
+  const float* wfc1t;     /* [obs_pad][H]   fc1.weight^T                               */
+  const float* bfc1;      /* [H]                                                       */
+  const float* wrzt;      /* [2H][2H] rows 0..H-1: rnn.weight_ih[0:2H]^T, rows H..2H-1:
+                             rnn.weight_hh[0:2H]^T; columns: r gate then z gate        */
+  const float* brz;       /* [2H]  (bias_ih + bias_hh)[0:2H]                           */
+  const float* wint;      /* [H][H] rnn.weight_ih[2H:3H]^T                             */
+  const float* bin;       /* [H]    rnn.bias_ih[2H:3H]                                 */
+  const float* whnt;      /* [H][H] rnn.weight_hh[2H:3H]^T                             */
+  const float* bhn;       /* [H]    rnn.bias_hh[2H:3H]                                 */
+  const float* wqt;       /* [H][H] fc2_q_head.0.weight[:, 0:H]^T                      */
+  const float* bq1;       /* [H]    fc2_q_head.0.bias                                  */
+  const float* w1a;       /* [A][H] fc2_q_head.0.weight[:, H+a]  (one-hot columns)     */
+  const float* w1p;       /* [H]    fc2_q_head.0.weight[:, H+A]  (parameter column)    */
+  const float* w2;        /* [H]    fc2_q_head.2.weight                                */
+  const float* bq2;       /* [1]    fc2_q_head.2.bias                                  */
+} macjd_agent_weights;
+
+typedef struct macjd_agent_io {
+  int32_t n_rows;             /* M = batch * n_agents                                   */
+  int32_t n_steps;            /* T timesteps unrolled inside this launch (acting: 1)    */
+  const float* obs;           /* [T][M][O]                                              */
+  float* hidden;              /* [M][H] recurrent state, updated in place; may be NULL  */
+  int32_t hidden_zero_init;   /* != 0: start from zeros (mac.py:189-198 init_hidden)    */
+  int32_t test_mode;          /* != 0: greedy only (action_selectors.py:59-61)          */
+  int32_t tile_rows;          /* rows per CTA: 0 = auto, or 32 / 64 (tuning knob)        */
+  int32_t reserved;
+  float* hidden_seq;          /* [T][M][H] h_t after every step, optional               */
+  float* q_all;               /* [T][M][A] Q(s, a, P_a) for every action, optional      */
+  float* params_all;          /* [T][M][A] actor outputs P_a, optional                  */
+  int32_t* greedy;            /* [T][M] argmax_a Q without availability mask, optional
+                                 (double-DQN action of qmix.py:143)                     */
+  const int32_t* sel_actions; /* [T][M] optional: actions to gather ...                 */
+  float* q_sel;               /* [T][M] ... Q(s, sel_actions) (qmix.py:147)             */
+  const uint8_t* avail;       /* [T][M][A] availability mask, NULL = all available      */
+  const float* u_eps;         /* [T][M] injected uniforms for the epsilon test, or NULL */
+  const int32_t* rand_actions;/* [T][M] injected random (available) actions, or NULL    */
+  float epsilon;              /* action_selectors.py:30-32, evaluated by the caller     */
+  uint32_t rng_step;          /* Philox step counter when draws are not injected        */
+  uint64_t seed;
+  int32_t* actions;           /* [T][M] chosen discrete action; NULL = no selection     */
+  float* power;               /* [T][M] P of the chosen action (mac.py:151-164)         */
+  float* q_chosen;            /* [T][M] Q of the chosen action, optional                */
+} macjd_agent_io;
+
+/* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);
+ * Q_a <- Qhead(h, a, P_a) for all a; masked epsilon-greedy / argmax / gathers. */
+MACJD_API int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io);
 
 #ifdef __cplusplus
 }

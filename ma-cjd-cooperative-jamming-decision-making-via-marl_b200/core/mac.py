@@ -1,0 +1,93 @@
+"""Multi-agent controller on the fused agent kernel (drop-in for core/mac.py:18-254).
+
+``select_actions`` is one kernel launch (csrc/agent_act.cuh): GRU step + actor + Q-head for
+every discrete action + availability mask + epsilon-greedy + gathers.  The random draws of
+the selector come from the kernel's Philox stream, or can be injected (``u_eps``,
+``rand_actions``) so that the reference and this path can be driven by identical sequences.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from .networks import RNNAgent
+from ..utils.action_selectors import EpsilonGreedyActionSelector
+
+
+class BasicMAC:
+    def __init__(self, input_shape, args, _lib=None):
+        self.n_agents = args.n_agents
+        self.args = args
+        self.input_shape = int(np.prod(input_shape)) if isinstance(input_shape, tuple) else input_shape
+        self._lib = _lib
+        self._build_agents(self.input_shape, args)
+        self.action_selector = EpsilonGreedyActionSelector(args)
+        self.hidden_states = None
+        self.seed = int(getattr(args, "seed", 0) or 0)
+        self._rng_step = 0
+        self.last_q_chosen = None
+
+    # ------------------------------------------------------------------ acting
+    def select_actions(self, obs_batch, avail_actions_batch, t_env, test_mode=False, *, u_eps=None, rand_actions=None):
+        """mac.py:59-166.  obs [B, N, obs], avail [B, N, A] -> (long [B, N, 1], float32 [B, N, 1]).
+        Updates ``self.hidden_states`` ([B*N, H]) in place."""
+        dev = self.device
+        B = obs_batch.shape[0]
+        M = B * self.n_agents
+        if self.hidden_states is None or self.hidden_states.shape[0] != M:
+            self.init_hidden(batch_size=B)
+        if self.hidden_states.device != dev:
+            self.hidden_states = self.hidden_states.to(dev)
+        eps = self.action_selector.anneal(t_env, test_mode)
+        obs = obs_batch.reshape(1, M, self.input_shape)
+        avail = avail_actions_batch.reshape(1, M, -1) if avail_actions_batch is not None else None
+        self._rng_step += 1
+        out = self.agent.run(obs, self.hidden_states, avail=avail, epsilon=eps, test_mode=test_mode,
+                             u_eps=u_eps, rand_actions=rand_actions, seed=self.seed, rng_step=self._rng_step,
+                             select=True)
+        self.last_q_chosen = out["q_chosen"][0]
+        actions = out["actions"][0].to(torch.int64).view(B, self.n_agents, 1)
+        power = out["power"][0].view(B, self.n_agents, 1)
+        return actions, power
+
+    def forward(self, agent_inputs_reshaped, hidden_states):
+        """mac.py:168-187 -> (h_out [M, H], continuous_params_all [M, A])."""
+        h = hidden_states.detach().to(dtype=torch.float32).contiguous().clone()
+        out = self.agent.run(agent_inputs_reshaped, h, want_params=True)
+        return out["hidden"], out["params_all"][0]
+
+    def init_hidden(self, batch_size):
+        """mac.py:189-198"""
+        self.hidden_states = torch.zeros(batch_size * self.n_agents, self.args.rnn_hidden_dim,
+                                         dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------ utilities
+    @property
+    def device(self):
+        return next(self.agent.parameters()).device
+
+    def parameters(self):
+        return self.agent.parameters()
+
+    def load_state(self, other_mac_state_dict):
+        self.agent.load_state_dict(other_mac_state_dict)
+
+    def state_dict(self):
+        return self.agent.state_dict()
+
+    def cuda(self):
+        self.agent.cuda()
+        if self.hidden_states is not None:
+            self.hidden_states = self.hidden_states.cuda()
+
+    def save_models(self, path):
+        os.makedirs(path, exist_ok=True)
+        torch.save(self.agent.state_dict(), f"{path}/agent.pth")
+
+    def load_models(self, path):
+        self.agent.load_state_dict(torch.load(f"{path}/agent.pth", map_location=self.device))
+
+    def _build_agents(self, input_shape, args):
+        self.agent = RNNAgent(input_shape, args, _lib=self._lib)

@@ -1,0 +1,229 @@
+"""Parameter containers of the MP-DQN agent and the QMix mixer, evaluated by CUDA kernels.
+
+Drop-in for ``core/networks.py`` of the reference: ``RNNAgent`` (:16-180) and ``QMixer``
+(:182-316) keep the reference's constructor signatures, sub-module layout and therefore
+its ``state_dict`` key names, shapes and -- because the layers are created in the same
+order -- its random initialisation under a given ``torch.manual_seed``.  Checkpoints
+(``agent.pth`` / ``qmix_net.pth``) load both ways.
+
+The forward passes do not run through ``torch.nn``: they call the fused kernels of
+libmacjd_b200.so on a packed K-major copy of the weights (``pack_agent_weights``), which is
+rebuilt whenever a parameter's version counter changes.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+
+
+def _ceil_to(x, m):
+    return (x + m - 1) // m * m
+
+
+class PackedAgentWeights:
+    """K-major packed copy of an RNNAgent's parameters (layout: include/macjd.h,
+    macjd_agent_weights).  One flat float32 buffer; every segment starts 16-byte aligned."""
+
+    FIELDS = ("wa1t", "ba1", "wa2t", "ba2", "wa3t", "ba3", "wfc1t", "bfc1", "wrzt", "brz", "wint", "bin",
+              "whnt", "bhn", "wqt", "bq1", "w1a", "w1p", "w2", "bq2")
+
+    def __init__(self, agent: "RNNAgent"):
+        self.O, self.H, self.AH, self.A = agent.input_shape, agent.rnn_hidden_dim, agent.actor_hidden_dim, agent.n_actions
+        self.Op = _ceil_to(self.O, 32)
+        if self.H % 64 or self.AH % 64 or self.H > 256 or self.AH > 256 or self.A > 64:
+            raise N.MacjdError(f"unsupported agent dims H={self.H} AH={self.AH} A={self.A} "
+                               "(kernels need H, AH multiples of 64 and <= 256, A <= 64)")
+        O, Op, H, AH, A = self.O, self.Op, self.H, self.AH, self.A
+        self.shapes = {"wa1t": (Op, AH), "ba1": (AH,), "wa2t": (AH, AH), "ba2": (AH,), "wa3t": (AH, A), "ba3": (A,),
+                       "wfc1t": (Op, H), "bfc1": (H,), "wrzt": (2 * H, 2 * H), "brz": (2 * H,), "wint": (H, H),
+                       "bin": (H,), "whnt": (H, H), "bhn": (H,), "wqt": (H, H), "bq1": (H,), "w1a": (A, H),
+                       "w1p": (H,), "w2": (H,), "bq2": (1,)}
+        self.offsets, off = {}, 0
+        for f in self.FIELDS:
+            self.offsets[f] = off
+            off += _ceil_to(int(np.prod(self.shapes[f])), 4)
+        self.size = off
+        self.buffer = None
+        self.versions = None
+
+    def view(self, f):
+        n = int(np.prod(self.shapes[f]))
+        return self.buffer[self.offsets[f]:self.offsets[f] + n].view(*self.shapes[f])
+
+    @torch.no_grad()
+    def refresh(self, agent, force=False):
+        """Re-pack if any parameter changed since the last pack (or moved device)."""
+        params = list(agent.parameters())
+        dev = params[0].device
+        versions = tuple((p._version, p.data_ptr()) for p in params)
+        if not force and self.buffer is not None and self.buffer.device == dev and versions == self.versions:
+            return self
+        if self.buffer is None or self.buffer.device != dev:
+            self.buffer = torch.zeros(self.size, dtype=torch.float32, device=dev)
+        O, H, A = self.O, self.H, self.A
+        sd = {k: v.detach().float() for k, v in agent.state_dict().items()}
+        self.view("wa1t")[:O].copy_(sd["actor.0.weight"].t())
+        self.view("ba1").copy_(sd["actor.0.bias"])
+        self.view("wa2t").copy_(sd["actor.2.weight"].t())
+        self.view("ba2").copy_(sd["actor.2.bias"])
+        self.view("wa3t").copy_(sd["actor.4.weight"].t())
+        self.view("ba3").copy_(sd["actor.4.bias"])
+        self.view("wfc1t")[:O].copy_(sd["fc1.weight"].t())
+        self.view("bfc1").copy_(sd["fc1.bias"])
+        wih, whh = sd["rnn.weight_ih"], sd["rnn.weight_hh"]          # [3H, H], gate blocks r, z, n
+        wrz = self.view("wrzt")
+        wrz[:H].copy_(wih[:2 * H].t())
+        wrz[H:].copy_(whh[:2 * H].t())
+        self.view("brz").copy_(sd["rnn.bias_ih"][:2 * H] + sd["rnn.bias_hh"][:2 * H])
+        self.view("wint").copy_(wih[2 * H:].t())
+        self.view("bin").copy_(sd["rnn.bias_ih"][2 * H:])
+        self.view("whnt").copy_(whh[2 * H:].t())
+        self.view("bhn").copy_(sd["rnn.bias_hh"][2 * H:])
+        w1 = sd["fc2_q_head.0.weight"]                               # [H, H + A + 1]
+        self.view("wqt").copy_(w1[:, :H].t())
+        self.view("bq1").copy_(sd["fc2_q_head.0.bias"])
+        self.view("w1a").copy_(w1[:, H:H + A].t())
+        self.view("w1p").copy_(w1[:, H + A])
+        self.view("w2").copy_(sd["fc2_q_head.2.weight"].reshape(-1))
+        self.view("bq2").copy_(sd["fc2_q_head.2.bias"])
+        self.versions = versions
+        return self
+
+    def cstruct(self):
+        base = self.buffer.data_ptr()
+        kw = {f: base + 4 * self.offsets[f] for f in self.FIELDS}
+        return N.AgentWeights(obs_dim=self.O, obs_pad=self.Op, hidden=self.H, actor_hidden=self.AH,
+                              n_actions=self.A, reserved=0, **kw)
+
+
+class RNNAgent(nn.Module):
+    """core/networks.py:16-180.  Sub-modules exist to own the parameters (names, shapes,
+    init); every forward goes through the fused CUDA kernel (csrc/agent_act.cuh)."""
+
+    def __init__(self, input_shape, args, _lib=None):
+        super().__init__()
+        self.args = args
+        self.n_actions = args.n_actions
+        self.input_shape = int(input_shape)
+        self.rnn_hidden_dim = args.rnn_hidden_dim
+        self.actor_hidden_dim = args.actor_hidden_dim
+        # creation order == reference order (networks.py:54-79) -> identical seeded init
+        self.actor = nn.Sequential(
+            nn.Linear(self.input_shape, self.actor_hidden_dim), nn.ReLU(),
+            nn.Linear(self.actor_hidden_dim, self.actor_hidden_dim), nn.ReLU(),
+            nn.Linear(self.actor_hidden_dim, self.n_actions), nn.Sigmoid())
+        self.fc1 = nn.Linear(self.input_shape, self.rnn_hidden_dim)
+        self.rnn = nn.GRUCell(self.rnn_hidden_dim, self.rnn_hidden_dim)
+        self.fc2_q_head = nn.Sequential(
+            nn.Linear(self.rnn_hidden_dim + self.n_actions + 1, self.rnn_hidden_dim), nn.ReLU(),
+            nn.Linear(self.rnn_hidden_dim, 1))
+        self._packed = PackedAgentWeights(self)
+        self._lib = _lib
+
+    # ---- native plumbing
+    def lib(self):
+        return self._lib if self._lib is not None else N.get_lib()
+
+    def packed(self, force=False):
+        return self._packed.refresh(self, force=force)
+
+    def _ctx(self):
+        dev = self.fc1.weight.device
+        if dev.type == "cuda":
+            return N.torch_ctx(dev)
+        if self._lib is None:
+            raise N.MacjdError("RNNAgent runs on CUDA only (no CPU fallback); call .cuda() first")
+        return N.Ctx(device=0, reserved=0, stream=None)
+
+    @torch.no_grad()
+    def run(self, obs, hidden=None, *, n_steps=1, zero_init=False, avail=None, epsilon=0.0, test_mode=True,
+            u_eps=None, rand_actions=None, seed=0, rng_step=0, select=False, want_q=False, want_params=False,
+            want_greedy=False, sel_actions=None, want_hidden_seq=False, tile_rows=0):
+        """One fused launch.  obs float32 [T, M, O] (or [M, O]); hidden float32 [M, H] updated in
+        place.  Returns a dict with the requested outputs."""
+        dev = self.fc1.weight.device
+        obs = obs.to(device=dev, dtype=torch.float32)
+        if obs.dim() == 2:
+            obs = obs.unsqueeze(0)
+        obs = obs.contiguous()
+        T, M, O = obs.shape
+        assert O == self.input_shape and T == n_steps
+        A, H = self.n_actions, self.rnn_hidden_dim
+        pk = self.packed()
+        out = {}
+        mk = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype, device=dev)
+        if hidden is None:
+            hidden = torch.zeros(M, H, dtype=torch.float32, device=dev)
+            zero_init = True
+        assert hidden.is_contiguous() and hidden.shape == (M, H) and hidden.dtype == torch.float32
+        out["hidden"] = hidden
+        if want_hidden_seq:
+            out["hidden_seq"] = mk(T, M, H)
+        if want_q:
+            out["q_all"] = mk(T, M, A)
+        if want_params:
+            out["params_all"] = mk(T, M, A)
+        if want_greedy:
+            out["greedy"] = mk(T, M, dtype=torch.int32)
+        if sel_actions is not None:
+            sel_actions = sel_actions.to(device=dev, dtype=torch.int32).contiguous()
+            out["q_sel"] = mk(T, M)
+        if select:
+            out["actions"] = mk(T, M, dtype=torch.int32)
+            out["power"] = mk(T, M)
+            out["q_chosen"] = mk(T, M)
+        if avail is not None:
+            avail = avail.to(device=dev).ne(0).to(torch.uint8).reshape(T, M, A).contiguous()
+        if u_eps is not None:
+            u_eps = u_eps.to(device=dev, dtype=torch.float32).reshape(T, M).contiguous()
+        if rand_actions is not None:
+            rand_actions = rand_actions.to(device=dev, dtype=torch.int32).reshape(T, M).contiguous()
+        p = N.ptr
+        io = N.AgentIO(
+            n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden),
+            hidden_zero_init=int(zero_init), test_mode=int(test_mode), tile_rows=int(tile_rows), reserved=0,
+            hidden_seq=p(out.get("hidden_seq")), q_all=p(out.get("q_all")), params_all=p(out.get("params_all")),
+            greedy=p(out.get("greedy")), sel_actions=p(sel_actions), q_sel=p(out.get("q_sel")),
+            avail=p(avail), u_eps=p(u_eps), rand_actions=p(rand_actions), epsilon=float(epsilon),
+            rng_step=int(rng_step) & 0xFFFFFFFF, seed=int(seed) & 0xFFFFFFFFFFFFFFFF,
+            actions=p(out.get("actions")), power=p(out.get("power")), q_chosen=p(out.get("q_chosen")))
+        self.lib().call("macjd_agent_forward", self._ctx(), pk.cstruct(), io)
+        return out
+
+    # ---- reference API
+    def init_hidden(self):
+        """networks.py:81-86"""
+        return self.fc1.weight.new(1, self.rnn_hidden_dim).zero_()
+
+    def forward(self, agent_inputs, h_in):
+        """networks.py:88-114 -> new hidden state [M, H] (h_in is not modified)."""
+        h = h_in.detach().to(dtype=torch.float32).contiguous().clone()
+        return self.run(agent_inputs, h)["hidden"]
+
+    def actor_forward(self, inputs):
+        """networks.py:116-129 -> P for every discrete action [M, A]."""
+        return self.run(inputs, None, want_params=True)["params_all"][0]
+
+
+class QMixer(nn.Module):
+    """core/networks.py:182-316 parameter container (LayerNorm + 4 hypernetworks).  The
+    forward / backward passes are the learner kernels (core/qmix.py of this package)."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.n_agents = args.n_agents
+        self.state_dim = int(np.prod(args.state_shape))
+        self.embed_dim = args.mixing_embed_dim
+        self.hyper_hidden_dim = args.hyper_hidden_dim
+        # creation order == reference order (networks.py:215-248)
+        self.state_norm = nn.LayerNorm(self.state_dim)
+        self.hyper_w_1 = nn.Sequential(nn.Linear(self.state_dim, self.hyper_hidden_dim), nn.ReLU(),
+                                       nn.Linear(self.hyper_hidden_dim, self.n_agents * self.embed_dim))
+        self.hyper_w_final = nn.Sequential(nn.Linear(self.state_dim, self.hyper_hidden_dim), nn.ReLU(),
+                                           nn.Linear(self.hyper_hidden_dim, self.embed_dim))
+        self.hyper_b_1 = nn.Linear(self.state_dim, self.embed_dim)
+        self.V = nn.Sequential(nn.Linear(self.state_dim, self.embed_dim), nn.ReLU(), nn.Linear(self.embed_dim, 1))

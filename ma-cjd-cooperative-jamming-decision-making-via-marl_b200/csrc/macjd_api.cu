@@ -3,6 +3,7 @@
 // codes.  No allocation, no synchronisation, no global mutable state.
 #include "macjd_common.cuh"
 #include "env_step.cuh"
+#include "agent_act.cuh"
 
 #include <stdio.h>
 #include <string.h>
@@ -56,6 +57,8 @@ size_t macjd_abi_sizeof(int which) {
     case 0: return sizeof(macjd_ctx);
     case 1: return sizeof(macjd_env_tables);
     case 2: return sizeof(macjd_env_io);
+    case 3: return sizeof(macjd_agent_weights);
+    case 4: return sizeof(macjd_agent_io);
     default: return 0;
   }
 }
@@ -70,6 +73,12 @@ int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab, const mac
   int st = enter(ctx);
   if (st != MACJD_OK) return st;
   return finish(ctx, macjd::env_launch(ctx, tab, io, /*physics=*/0));
+}
+
+int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  return finish(ctx, macjd::agent_launch(ctx, w, io));
 }
 
 }  // extern "C"

@@ -1,0 +1,157 @@
+"""Agent / controller parity checks shared by the host-emulation (CPU) and the GPU tests."""
+import json
+import os
+import types
+
+import numpy as np
+import torch
+
+from oracle import agent_oracle as AO
+from tests.helpers import GOLDEN
+
+Q_RTOL, Q_ATOL = 1e-5, 2e-6     # FP32 SIMT GEMMs vs eager torch: summation-order noise only
+
+
+def load_agent_golden(name):
+    g = np.load(os.path.join(GOLDEN, f"agent_{name}.npz"))
+    args = types.SimpleNamespace(**json.loads(str(g["args_json"])))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd.")}
+    return g, args, sd
+
+
+def make_mac(args, sd, device, lib=None):
+    from macjd_b200.core.mac import BasicMAC
+    mac = BasicMAC(args.obs_shape, args, _lib=lib)
+    mac.agent.load_state_dict(sd)
+    if device != "cpu":
+        mac.cuda()
+    return mac
+
+
+def argmax_margin(q):
+    """Gap between the best and the second best finite Q per row."""
+    s = np.sort(np.where(np.isfinite(q), q, -1e30), axis=-1)
+    return s[..., -1] - s[..., -2]
+
+
+def check_mac_against_golden(name, device, lib=None):
+    """select_actions driven by the reference's recorded inputs and injected selector draws:
+    actions bit-exact, hidden / power within FP32 tolerance."""
+    g, args, sd = load_agent_golden(name)
+    mac = make_mac(args, sd, device, lib)
+    assert sum(p.numel() for p in mac.parameters()) == int(g["n_params"])
+    dev = mac.device
+    steps, B, Nn, O = g["obs"].shape
+    mac.hidden_states = torch.from_numpy(g["h0"].copy()).to(dev)
+    for t in range(steps):
+        obs = torch.from_numpy(g["obs"][t]).to(dev)
+        avail = torch.from_numpy(g["avail"][t]).to(dev)
+        h_before = mac.hidden_states.clone()
+        kw = dict(u_eps=torch.from_numpy(g["u"][t]), rand_actions=torch.from_numpy(g["rand_actions"][t]))
+        a_test, p_test = mac.select_actions(obs, avail, int(g["t_env"][t]), test_mode=True, **kw)
+        mac.hidden_states.copy_(h_before)
+        a, p = mac.select_actions(obs, avail, int(g["t_env"][t]), test_mode=False, **kw)
+        assert a.dtype == torch.int64 and a.shape == (B, Nn, 1) and p.shape == (B, Nn, 1)
+        assert mac.action_selector.epsilon == float(g["eps"][t])
+        # the reference's own Q margins show which argmaxes are numerically decidable
+        qm = np.where(g["avail"][t].reshape(B * Nn, -1) != 0, g["q"][t], -np.inf)
+        decidable = (argmax_margin(qm) > 1e-5).reshape(B, Nn, 1)
+        assert decidable.mean() > 0.9
+        picked_random = (g["u"][t] < np.float32(g["eps"][t]))[..., None]
+        np.testing.assert_array_equal(a.cpu().numpy()[decidable | picked_random], g["actions"][t][decidable | picked_random])
+        np.testing.assert_array_equal(a_test.cpu().numpy()[decidable], g["actions_test"][t][decidable])
+        same = a.cpu().numpy() == g["actions"][t]
+        np.testing.assert_allclose(p.cpu().numpy()[same], g["power"][t][same], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(mac.hidden_states.cpu().numpy(), g["hidden"][t], rtol=1e-5, atol=2e-6)
+        # keep both sides on the reference trajectory
+        mac.hidden_states.copy_(torch.from_numpy(g["hidden"][t]))
+
+
+def check_agent_outputs_against_golden(name, device, lib=None):
+    """Q for every action, actor parameters and hidden state against the reference."""
+    g, args, sd = load_agent_golden(name)
+    mac = make_mac(args, sd, device, lib)
+    dev = mac.device
+    steps, B, Nn, O = g["obs"].shape
+    h = torch.from_numpy(g["h0"].copy()).to(dev)
+    for t in range(steps):
+        obs = torch.from_numpy(g["obs"][t]).reshape(B * Nn, O).to(dev)
+        out = mac.agent.run(obs, h, want_q=True, want_params=True, want_greedy=True)
+        np.testing.assert_allclose(out["q_all"][0].cpu().numpy(), g["q"][t], rtol=Q_RTOL, atol=Q_ATOL)
+        np.testing.assert_allclose(out["params_all"][0].cpu().numpy(), g["params"][t], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(h.cpu().numpy(), g["hidden"][t], rtol=1e-5, atol=2e-6)
+        dec = argmax_margin(g["q"][t]) > 1e-5
+        np.testing.assert_array_equal(out["greedy"][0].cpu().numpy()[dec], g["q"][t].argmax(-1)[dec])
+        h.copy_(torch.from_numpy(g["hidden"][t]))
+        # the reference-API methods
+        h_in = torch.from_numpy(g["h0"] if t == 0 else g["hidden"][t - 1]).to(dev)
+        h_out, params = mac.forward(obs, h_in)
+        np.testing.assert_allclose(h_out.cpu().numpy(), g["hidden"][t], rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(params.cpu().numpy(), g["params"][t], rtol=1e-5, atol=1e-6)
+
+
+def random_agent(seed, O, A, H, AH, Nn, device, lib=None):
+    from macjd_b200.core.mac import BasicMAC
+    args = types.SimpleNamespace(n_agents=Nn, n_actions=A, rnn_hidden_dim=H, actor_hidden_dim=AH, obs_shape=O,
+                                 epsilon_start=1.0, epsilon_finish=0.05, epsilon_anneal_time=1000, seed=seed)
+    torch.manual_seed(seed)
+    mac = BasicMAC(O, args, _lib=lib)
+    if device != "cpu":
+        mac.cuda()
+    return mac, args
+
+
+def check_unroll_against_oracle(device, lib=None, O=24, A=5, H=128, AH=128, Nn=2, B=19, T=5, seed=3, tile_rows=0):
+    """T-step unroll inside one launch (learner mode): all-action Q, unmasked argmax, gather of
+    given actions and hidden sequence against the eager oracle; ragged row count."""
+    mac, args = random_agent(seed, O, A, H, AH, Nn, device, lib)
+    dev = mac.device
+    rng = np.random.default_rng(seed)
+    M = B * Nn
+    obs = (rng.standard_normal((T, M, O)) * rng.choice([1.0, 30.0], size=O)).astype(np.float32)
+    sel = rng.integers(0, A, size=(T, M)).astype(np.int32)
+    sd = {k: v.detach().cpu() for k, v in mac.agent.state_dict().items()}
+    out = mac.agent.run(torch.from_numpy(obs).to(dev), None, n_steps=T, zero_init=True, want_q=True, want_greedy=True,
+                        sel_actions=torch.from_numpy(sel), want_hidden_seq=True, want_params=True, tile_rows=tile_rows)
+    h = torch.zeros(M, H)
+    for t in range(T):
+        x = torch.from_numpy(obs[t])
+        h = AO.agent_hidden(sd, x, h)
+        params = AO.actor_params(sd, x)
+        q = AO.q_all_actions(sd, h, params).numpy()
+        np.testing.assert_allclose(out["hidden_seq"][t].cpu().numpy(), h.numpy(), rtol=1e-5, atol=2e-6, err_msg=f"h t={t}")
+        np.testing.assert_allclose(out["q_all"][t].cpu().numpy(), q, rtol=Q_RTOL, atol=Q_ATOL, err_msg=f"q t={t}")
+        np.testing.assert_allclose(out["params_all"][t].cpu().numpy(), params.numpy(), rtol=1e-5, atol=1e-6)
+        dec = argmax_margin(q) > 1e-5
+        np.testing.assert_array_equal(out["greedy"][t].cpu().numpy()[dec], q.argmax(-1)[dec])
+        np.testing.assert_allclose(out["q_sel"][t].cpu().numpy(), q[np.arange(M), sel[t]], rtol=Q_RTOL, atol=Q_ATOL)
+    np.testing.assert_allclose(out["hidden"].cpu().numpy(), h.numpy(), rtol=1e-5, atol=2e-6)
+
+
+def check_device_rng_selection(device, lib=None):
+    """Without injected draws the kernel's Philox stream decides: reproduce it with the
+    oracle's Philox and check the epsilon test and the uniform-over-available draw."""
+    from oracle.env_oracle import philox4x32_10, u01_from_u32
+    mac, args = random_agent(11, 24, 5, 64, 64, 2, device, lib)
+    dev = mac.device
+    rng = np.random.default_rng(0)
+    B = 40
+    obs = torch.from_numpy(rng.standard_normal((B, 2, 24)).astype(np.float32)).to(dev)
+    avail = (rng.random((B, 2, 5)) < 0.6).astype(np.int64)
+    avail[..., 2] = 1
+    a_greedy, _ = mac.select_actions(obs, torch.from_numpy(avail).to(dev), 0, test_mode=True)
+    mac.init_hidden(B)
+    mac._rng_step = 0
+    a, _ = mac.select_actions(obs, torch.from_numpy(avail).to(dev), 500, test_mode=False)   # eps = 0.525
+    eps = np.float32(mac.action_selector.epsilon)
+    key = (args.seed & 0xFFFFFFFF, args.seed >> 32)
+    for m in range(B * 2):
+        u = u01_from_u32(philox4x32_10((0, 1, m, 2), key)[0])
+        if u < eps:
+            u2 = u01_from_u32(philox4x32_10((0, 1, m, 3), key)[0])
+            av = np.flatnonzero(avail.reshape(-1, 5)[m])
+            kth = min(len(av) - 1, int(np.float32(u2) * np.float32(len(av))))
+            assert int(a.reshape(-1)[m]) == av[kth], m
+        else:
+            assert int(a.reshape(-1)[m]) == int(a_greedy.reshape(-1)[m]), m
+    assert 0.3 < float((a != a_greedy).float().mean()) < 0.7

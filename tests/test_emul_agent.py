@@ -1,0 +1,29 @@
+"""Kernel logic of csrc/agent_act.cuh checked on the CPU through the host-emulation build
+(tests/emul): reference goldens + eager oracle.  GPU twin: tests/test_gpu_agent.py."""
+import pytest
+
+from tests import agent_checks as AC
+from tests.helpers import emul_lib
+
+
+@pytest.mark.parametrize("name", ["c1", "small"])
+def test_select_actions_vs_reference(name):
+    AC.check_mac_against_golden(name, "cpu", emul_lib())
+
+
+@pytest.mark.parametrize("name", ["c1", "small"])
+def test_q_params_hidden_vs_reference(name):
+    AC.check_agent_outputs_against_golden(name, "cpu", emul_lib())
+
+
+def test_unroll_vs_oracle_small():
+    AC.check_unroll_against_oracle("cpu", emul_lib(), O=39, A=7, H=64, AH=128, Nn=3, B=15, T=3)
+
+
+def test_unroll_vs_oracle_64_row_tiles():
+    # the 64-row CTA tile (RT=4) the large batches use, ragged: 2 tiles, the second partly empty
+    AC.check_unroll_against_oracle("cpu", emul_lib(), O=24, A=5, H=128, AH=64, Nn=2, B=35, T=2, tile_rows=64)
+
+
+def test_device_rng_selection():
+    AC.check_device_rng_selection("cpu", emul_lib())
