@@ -28,6 +28,20 @@ def make_mac(args, sd, device, lib=None):
     return mac
 
 
+def assert_as_accurate(actual, ref32, ref64, what, k=4.0, rtol=1e-5, atol=2e-6):
+    """FP32 results depend on summation order when the pre-activations are large (real
+    observations carry values of several hundred).  The bar: the kernel is within rtol of
+    the float64 truth, or no further from it than k x the eager-FP32 oracle's own worst
+    rounding error on the same input."""
+    ref64 = np.asarray(ref64, dtype=np.float64)
+    err_ref = np.abs(np.asarray(ref32, dtype=np.float64) - ref64).max()
+    err = np.abs(np.asarray(actual, dtype=np.float64) - ref64)
+    bound = np.maximum(rtol * np.abs(ref64) + atol, k * err_ref)
+    bad = err > bound
+    assert not bad.any(), (f"{what}: {bad.sum()} / {bad.size} elements off; max err {err.max():.3e}, "
+                           f"oracle-fp32 max err {err_ref:.3e}")
+
+
 def argmax_margin(q):
     """Gap between the best and the second best finite Q per row."""
     s = np.sort(np.where(np.isfinite(q), q, -1e30), axis=-1)
@@ -113,19 +127,25 @@ def check_unroll_against_oracle(device, lib=None, O=24, A=5, H=128, AH=128, Nn=2
     sd = {k: v.detach().cpu() for k, v in mac.agent.state_dict().items()}
     out = mac.agent.run(torch.from_numpy(obs).to(dev), None, n_steps=T, zero_init=True, want_q=True, want_greedy=True,
                         sel_actions=torch.from_numpy(sel), want_hidden_seq=True, want_params=True, tile_rows=tile_rows)
+    sd64 = AO.cast_sd(sd, torch.float64)
     h = torch.zeros(M, H)
+    h64 = torch.zeros(M, H, dtype=torch.float64)
     for t in range(T):
         x = torch.from_numpy(obs[t])
         h = AO.agent_hidden(sd, x, h)
         params = AO.actor_params(sd, x)
         q = AO.q_all_actions(sd, h, params).numpy()
-        np.testing.assert_allclose(out["hidden_seq"][t].cpu().numpy(), h.numpy(), rtol=1e-5, atol=2e-6, err_msg=f"h t={t}")
-        np.testing.assert_allclose(out["q_all"][t].cpu().numpy(), q, rtol=Q_RTOL, atol=Q_ATOL, err_msg=f"q t={t}")
-        np.testing.assert_allclose(out["params_all"][t].cpu().numpy(), params.numpy(), rtol=1e-5, atol=1e-6)
-        dec = argmax_margin(q) > 1e-5
-        np.testing.assert_array_equal(out["greedy"][t].cpu().numpy()[dec], q.argmax(-1)[dec])
-        np.testing.assert_allclose(out["q_sel"][t].cpu().numpy(), q[np.arange(M), sel[t]], rtol=Q_RTOL, atol=Q_ATOL)
-    np.testing.assert_allclose(out["hidden"].cpu().numpy(), h.numpy(), rtol=1e-5, atol=2e-6)
+        h64 = AO.agent_hidden(sd64, x.double(), h64)
+        params64 = AO.actor_params(sd64, x.double())
+        q64 = AO.q_all_actions(sd64, h64, params64).numpy()
+        assert_as_accurate(out["hidden_seq"][t].cpu().numpy(), h.numpy(), h64.numpy(), f"h t={t}")
+        assert_as_accurate(out["q_all"][t].cpu().numpy(), q, q64, f"q t={t}")
+        assert_as_accurate(out["params_all"][t].cpu().numpy(), params.numpy(), params64.numpy(), f"P t={t}", atol=1e-6)
+        dec = argmax_margin(q64) > 1e-4
+        assert dec.mean() > 0.9
+        np.testing.assert_array_equal(out["greedy"][t].cpu().numpy()[dec], q64.argmax(-1)[dec])
+        assert_as_accurate(out["q_sel"][t].cpu().numpy(), q[np.arange(M), sel[t]], q64[np.arange(M), sel[t]], f"q_sel t={t}")
+    assert_as_accurate(out["hidden"].cpu().numpy(), h.numpy(), h64.numpy(), "final hidden")
 
 
 def check_device_rng_selection(device, lib=None):
