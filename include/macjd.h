@@ -192,6 +192,116 @@ typedef struct macjd_agent_io {
  * Q_a <- Qhead(h, a, P_a) for all a; masked epsilon-greedy / argmax / gathers. */
 MACJD_API int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io);
 
+/* ===================================================================== replay ring
+ * Replaces the data movement of utils/replay_buffer.py:78-214 (store_episode / sample) and
+ * runners/episode_runner.py:187-277 (EpisodeBatch staging): index-driven episode copies
+ * between rollout buffers, ring slots and training batches, all in HBM.
+ */
+#define MACJD_MAX_COPY_KEYS 12
+typedef struct macjd_copy_desc {
+  const void* src;
+  void* dst;
+  int64_t src_ep_stride;   /* bytes between consecutive episodes on the source side      */
+  int64_t src_t_stride;    /* bytes between consecutive timesteps on the source side     */
+  int64_t dst_ep_stride;
+  int64_t dst_t_stride;
+  int32_t n_t;             /* timesteps to copy (T or T+1)                               */
+  int32_t inner_bytes;     /* contiguous bytes per timestep                              */
+  int32_t vec_bytes;       /* filled in by the library                                   */
+  int32_t reserved;
+} macjd_copy_desc;
+
+/* For b in [0, n_eps): slot = idx ? idx[b] : b.  index_on_src != 0: dst episode b <- src
+ * episode slot (sample);  index_on_src == 0: dst episode slot <- src episode b (store).
+ * descs_host is read on the host at call time. */
+MACJD_API int macjd_replay_copy(const macjd_ctx* ctx, const macjd_copy_desc* descs_host, int32_t n_keys,
+                                const int32_t* idx, int32_t n_eps, int32_t index_on_src);
+
+/* ===================================================================== learner
+ * Replaces core/qmix.py:76-215 (QMixLearner.train) below the time-unrolled agent passes
+ * (which are macjd_agent_forward with n_steps = T): QMixer forward / backward
+ * (core/networks.py:250-316), the Q-head on stored hidden states with its backward
+ * (core/networks.py:131-180, core/qmix.py:161-184), the double-DQN TD target and masked
+ * loss (core/qmix.py:155,191-194), gradient-norm clipping and Adam (core/qmix.py:197-200).
+ * Rows are time-major: r = t * batch + b.
+ */
+typedef struct macjd_mixer_dims {
+  int32_t n_rows;        /* R = batch * (T - 1)   */
+  int32_t state_dim;     /* S                     */
+  int32_t n_agents;      /* N                     */
+  int32_t embed_dim;     /* E = mixing_embed_dim  */
+  int32_t hyper_hidden;  /* HH = hyper_hidden_dim */
+  int32_t reserved;
+} macjd_mixer_dims;
+
+/* QMixer tensors in PyTorch layout ([out][in] row-major); the same struct addresses the
+ * weights and the gradient buffers. */
+typedef struct macjd_mixer_params {
+  float* ln_w;  float* ln_b;     /* state_norm.{weight,bias}      [S]               */
+  float* w1a_w; float* w1a_b;    /* hyper_w_1.0      [HH][S], [HH]                   */
+  float* w1b_w; float* w1b_b;    /* hyper_w_1.2      [N*E][HH], [N*E]                */
+  float* wfa_w; float* wfa_b;    /* hyper_w_final.0  [HH][S], [HH]                   */
+  float* wfb_w; float* wfb_b;    /* hyper_w_final.2  [E][HH], [E]                    */
+  float* b1_w;  float* b1_b;     /* hyper_b_1        [E][S], [E]                     */
+  float* va_w;  float* va_b;     /* V.0              [E][S], [E]                     */
+  float* vb_w;  float* vb_b;     /* V.2              [1][E], [1]                     */
+} macjd_mixer_params;
+
+MACJD_API size_t macjd_mixer_workspace_floats(const macjd_mixer_dims* dims);
+/* q [R][N], states [R][S] -> q_tot [R]; leaves the intermediates in `workspace`. */
+MACJD_API int macjd_mixer_forward(const macjd_ctx* ctx, const macjd_mixer_dims* dims, const macjd_mixer_params* w,
+                                  const float* q, const float* states, float* q_tot, float* workspace,
+                                  size_t workspace_floats);
+/* dq_tot [R] -> gradients of every QMixer tensor (overwritten) and dq [R][N] (may be NULL).
+ * Needs the workspace left by macjd_mixer_forward on the same inputs. */
+MACJD_API int macjd_mixer_backward(const macjd_ctx* ctx, const macjd_mixer_dims* dims, const macjd_mixer_params* w,
+                                   const float* q, const float* dq_tot, float* workspace, size_t workspace_floats,
+                                   const macjd_mixer_params* grads, float* dq);
+
+typedef struct macjd_qhead_dims {
+  int32_t n_rows;     /* batch * (T - 1) * n_agents */
+  int32_t hidden;     /* H                          */
+  int32_t n_actions;  /* A                          */
+  int32_t reserved;
+} macjd_qhead_dims;
+
+MACJD_API size_t macjd_qhead_scratch_floats(const macjd_qhead_dims* dims);
+/* q[r] = Qhead(hidden[r], a_d[r], a_c[r]) with the packed weights of macjd_agent_weights
+ * (wqt, bq1, w1a, w1p, w2, bq2); hid [R][H] keeps the ReLU activations for the backward. */
+MACJD_API int macjd_qhead_forward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
+                                  const float* hidden, const int32_t* a_d, const float* a_c, float* q, float* hid);
+/* dq [R] -> gradients in PyTorch layout: g_w1 [H][H+A+1], g_b1 [H], g_w2 [H], g_b2 [1].
+ * `hid` (from the forward) is consumed. */
+MACJD_API int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
+                                   const float* hidden, const int32_t* a_d, const float* a_c, float* hid,
+                                   const float* dq, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
+                                   float* scratch, size_t scratch_floats);
+
+MACJD_API size_t macjd_td_scratch_floats(int32_t n_rows);
+/* targets = reward + gamma (1 - terminated) tq_tot;  td = (q_tot - targets) mask;
+ * dq_tot = 2 td mask (NOT divided by sum(mask): macjd_clip_adam applies 1/sums[1]);
+ * sums[0..3] = { sum td^2, sum mask, sum q_tot, sum targets }. */
+MACJD_API int macjd_td_loss(const macjd_ctx* ctx, int32_t n_rows, const float* q_tot, const float* tq_tot,
+                            const float* reward, const uint8_t* terminated, const uint8_t* filled, float gamma,
+                            float* dq_tot, float* targets, float* sums, float* scratch, size_t scratch_floats);
+
+#define MACJD_MAX_OPT_TENSORS 32
+typedef struct macjd_opt_tensors {
+  int32_t count;
+  int32_t reserved;
+  float* param[MACJD_MAX_OPT_TENSORS];    /* parameter tensors, updated in place           */
+  int64_t numel[MACJD_MAX_OPT_TENSORS];   /* their sizes; gradients / moments are the flat
+                                             concatenation in the same order               */
+} macjd_opt_tensors;
+
+MACJD_API size_t macjd_opt_scratch_floats(void);
+/* norm = ||grad|| / sums[1];  coef = min(1, max_norm / (norm + 1e-6))  (clip_grad_norm_);
+ * Adam step `step` (1-based) on every tensor with g = grad * coef / sums[1].
+ * scal[0] = norm (pre-clip), scal[1] = coef / sums[1], scal[2] = loss = sums[0] / sums[1]. */
+MACJD_API int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, const float* grad, float* m,
+                              float* v, const float* sums, float max_norm, float lr, float beta1, float beta2,
+                              float eps, int64_t step, float* scal, float* scratch, size_t scratch_floats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,8 +56,44 @@ class AgentIO(C.Structure):
                 ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p)]
 
 
+class CopyDesc(C.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("src_ep_stride", c_int64), ("src_t_stride", c_int64),
+                ("dst_ep_stride", c_int64), ("dst_t_stride", c_int64), ("n_t", c_int32), ("inner_bytes", c_int32),
+                ("vec_bytes", c_int32), ("reserved", c_int32)]
+
+
+class MixerDims(C.Structure):
+    _fields_ = [("n_rows", c_int32), ("state_dim", c_int32), ("n_agents", c_int32), ("embed_dim", c_int32),
+                ("hyper_hidden", c_int32), ("reserved", c_int32)]
+
+
+MIXER_FIELDS = ("ln_w", "ln_b", "w1a_w", "w1a_b", "w1b_w", "w1b_b", "wfa_w", "wfa_b", "wfb_w", "wfb_b",
+                "b1_w", "b1_b", "va_w", "va_b", "vb_w", "vb_b")
+# state_dict key of every macjd_mixer_params field (core/networks.py QMixer)
+MIXER_KEYS = ("state_norm.weight", "state_norm.bias", "hyper_w_1.0.weight", "hyper_w_1.0.bias",
+              "hyper_w_1.2.weight", "hyper_w_1.2.bias", "hyper_w_final.0.weight", "hyper_w_final.0.bias",
+              "hyper_w_final.2.weight", "hyper_w_final.2.bias", "hyper_b_1.weight", "hyper_b_1.bias",
+              "V.0.weight", "V.0.bias", "V.2.weight", "V.2.bias")
+
+
+class MixerParams(C.Structure):
+    _fields_ = [(n, c_void_p) for n in MIXER_FIELDS]
+
+
+class QheadDims(C.Structure):
+    _fields_ = [("n_rows", c_int32), ("hidden", c_int32), ("n_actions", c_int32), ("reserved", c_int32)]
+
+
+MAX_OPT_TENSORS = 32
+
+
+class OptTensors(C.Structure):
+    _fields_ = [("count", c_int32), ("reserved", c_int32), ("param", c_void_p * MAX_OPT_TENSORS),
+                ("numel", c_int64 * MAX_OPT_TENSORS)]
+
+
 # order must match macjd_abi_sizeof() in csrc/macjd_api.cu
-ABI_STRUCTS = [Ctx, EnvTables, EnvIO, AgentWeights, AgentIO]
+ABI_STRUCTS = [Ctx, EnvTables, EnvIO, AgentWeights, AgentIO, CopyDesc, MixerDims, MixerParams, QheadDims, OptTensors]
 
 
 class MacjdError(RuntimeError):
@@ -96,6 +132,24 @@ class NativeLib:
             fn = getattr(L, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(a) for a in args]
+        P = C.POINTER
+        vp, sz, i32, i64, f32 = c_void_p, C.c_size_t, c_int32, c_int64, c_float
+        for name, restype, argtypes in (
+            ("macjd_replay_copy", C.c_int, [P(Ctx), P(CopyDesc), i32, vp, i32, i32]),
+            ("macjd_mixer_workspace_floats", sz, [P(MixerDims)]),
+            ("macjd_mixer_forward", C.c_int, [P(Ctx), P(MixerDims), P(MixerParams), vp, vp, vp, vp, sz]),
+            ("macjd_mixer_backward", C.c_int, [P(Ctx), P(MixerDims), P(MixerParams), vp, vp, vp, sz, P(MixerParams), vp]),
+            ("macjd_qhead_scratch_floats", sz, [P(QheadDims)]),
+            ("macjd_qhead_forward", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp]),
+            ("macjd_qhead_backward", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]),
+            ("macjd_td_scratch_floats", sz, [i32]),
+            ("macjd_td_loss", C.c_int, [P(Ctx), i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, sz]),
+            ("macjd_opt_scratch_floats", sz, []),
+            ("macjd_clip_adam", C.c_int, [P(Ctx), P(OptTensors), vp, vp, vp, vp, f32, f32, f32, f32, f32, i64, vp, vp, sz]),
+        ):
+            fn = getattr(L, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
         self._check_abi()
 
     SIGNATURES = {
@@ -112,6 +166,12 @@ class NativeLib:
             if got != C.sizeof(st):
                 raise MacjdError(f"ABI struct {st.__name__}: library says {got} bytes, binding has {C.sizeof(st)}")
 
+    def __deepcopy__(self, memo):
+        return self          # a loaded library is shared, never copied (target networks deepcopy the MAC)
+
+    def __reduce__(self):
+        return (NativeLib, (self.path,))
+
     def check(self, status):
         if status != 0:
             msg = self.lib.macjd_status_string(status).decode()
@@ -121,6 +181,21 @@ class NativeLib:
 
     def call(self, name, *structs):
         self.check(getattr(self.lib, name)(*[C.byref(s) for s in structs]))
+
+    def callv(self, name, *args):
+        """Entry points with scalar / raw-pointer arguments: structures are passed by
+        reference, tensors and arrays by address."""
+        conv = []
+        for a in args:
+            if isinstance(a, C.Structure):
+                conv.append(C.byref(a))
+            elif isinstance(a, C.Array):
+                conv.append(a)
+            elif a is None or isinstance(a, (int, float)):
+                conv.append(a)
+            else:
+                conv.append(ptr(a))
+        self.check(getattr(self.lib, name)(*conv))
 
 
 _lib = None

@@ -1,0 +1,293 @@
+"""QMix learner on CUDA kernels (drop-in for core/qmix.py:25-334).
+
+``train(batch, train_info)`` reproduces the reference step, quirks included (SURVEY facts
+8 and 9): the eval / target unrolls start from a zero hidden state and only feed the
+double-DQN argmax / gather (no availability mask, qmix.py:141-143); ``q_taken`` is computed
+from the *stored* hidden states, so only ``fc2_q_head`` and the eval mixer ever receive
+gradients; the loss is normalised by ``mask[:, :-1].sum()``; ``grad_norm`` is the pre-clip
+norm; Adam runs with torch's defaults; targets are hard-copied every
+``target_update_interval`` train steps.
+
+Kernel sequence per step (all stream-ordered, no host sync until the stats are read):
+  agent unroll (eval) -> agent unroll (target, gathers Q at the eval argmax)   csrc/agent_act.cuh
+  target mixer fwd -> Q-head fwd on stored h -> eval mixer fwd                 csrc/learner.cuh
+  TD target + masked loss -> mixer bwd -> Q-head bwd -> [NCCL all-reduce]      csrc/learner.cuh
+  grad-norm + clip + Adam (in place on the nn.Parameters)                      csrc/learner_kernels.cuh
+Data parallel: every rank trains on its own episodes; one flat FP32 bucket (gradients + the
+loss / mask sums) is all-reduced, then every rank applies the identical update.
+"""
+from __future__ import annotations
+
+import copy
+import os
+
+import numpy as np
+import torch
+import torch.optim as optim
+
+from .. import _native as N
+from .networks import QMixer
+
+TRAINED_AGENT_KEYS = ("fc2_q_head.0.weight", "fc2_q_head.0.bias", "fc2_q_head.2.weight", "fc2_q_head.2.bias")
+BETA1, BETA2, ADAM_EPS = 0.9, 0.999, 1e-8
+
+
+class QMixLearner:
+    def __init__(self, mac, args, _lib=None, process_group=None):
+        self.args = args
+        self.mac = mac
+        self.n_agents = args.n_agents
+        self.n_actions = args.n_actions
+        self.state_shape = args.state_shape
+        self.obs_shape = args.obs_shape
+        self._lib = _lib if _lib is not None else getattr(mac, "_lib", None)
+        self.process_group = process_group
+        use_cuda = bool(getattr(args, "use_cuda", True)) and torch.cuda.is_available()
+        self.device = torch.device(getattr(args, "device", "cuda") if use_cuda else "cpu")
+        self.eval_qmix_net = QMixer(args)
+        self.target_mac = copy.deepcopy(mac)
+        self.target_qmix_net = QMixer(args)
+        self.target_qmix_net.load_state_dict(self.eval_qmix_net.state_dict())
+        if use_cuda:
+            self.cuda()
+        elif self._lib is None:
+            raise N.MacjdError("QMixLearner runs on CUDA only (no CPU fallback)")
+        self.agent_params = list(self.mac.parameters())
+        self.qmix_params = list(self.eval_qmix_net.parameters())
+        self.params = self.agent_params + self.qmix_params
+        # kept for checkpoint-format compatibility (optimizer.pth); the update itself is a kernel
+        self.optimizer = optim.Adam(params=self.params, lr=args.lr)
+        self.last_target_update_step = 0
+        self.train_step = 0
+        self._opt_state = None
+        self._ws = {}
+        print(f"QMix Learner Initialized on device: {self.device}")
+
+    # ------------------------------------------------------------------ plumbing
+    def lib(self):
+        return self._lib if self._lib is not None else N.get_lib()
+
+    def _ctx(self):
+        if self.device.type == "cuda":
+            return N.torch_ctx(self.device)
+        return N.Ctx(device=0, reserved=0, stream=None)
+
+    def _trainable(self):
+        """(tensor, name) in flat-bucket order: the Q-head, then every mixer parameter."""
+        agent_sd = dict(self.mac.agent.named_parameters())
+        out = [(agent_sd[k], "agent." + k) for k in TRAINED_AGENT_KEYS]
+        out += [(p, "mixer." + k) for k, p in self.eval_qmix_net.named_parameters()]
+        return out
+
+    def _ensure_opt_state(self):
+        tr = self._trainable()
+        dev = tr[0][0].device
+        if self._opt_state is None or self._opt_state["grad"].device != dev:
+            sizes = [p.numel() for p, _ in tr]
+            total = sum(sizes)
+            z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+            old = self._opt_state
+            self._opt_state = {"sizes": sizes, "total": total, "grad": z(total + 4), "m": z(total), "v": z(total),
+                               "step": 0, "scal": z(4),
+                               "scratch": z(self.lib().lib.macjd_opt_scratch_floats())}
+            if old is not None:
+                self._opt_state["m"].copy_(old["m"]); self._opt_state["v"].copy_(old["v"]); self._opt_state["step"] = old["step"]
+        return self._opt_state
+
+    def _mixer_struct(self, net=None, flat=None, offset=0):
+        """macjd_mixer_params over a QMixer's parameters, or over views of a flat buffer."""
+        kw = {}
+        if net is not None:
+            sd = dict(net.named_parameters())
+            for f, k in zip(N.MIXER_FIELDS, N.MIXER_KEYS):
+                kw[f] = sd[k].data_ptr()
+        else:
+            names = [k for k, _ in self.eval_qmix_net.named_parameters()]
+            sizes = {k: p.numel() for k, p in self.eval_qmix_net.named_parameters()}
+            offs, o = {}, offset
+            for k in names:
+                offs[k] = o
+                o += sizes[k]
+            for f, k in zip(N.MIXER_FIELDS, N.MIXER_KEYS):
+                kw[f] = flat.data_ptr() + 4 * offs[k]
+        return N.MixerParams(**kw)
+
+    def _workspace(self, name, n_floats, dev):
+        t = self._ws.get(name)
+        if t is None or t.numel() < n_floats or t.device != dev:
+            t = torch.empty(max(int(n_floats), 4), dtype=torch.float32, device=dev)
+            self._ws[name] = t
+        return t
+
+    # ------------------------------------------------------------------ batch handling
+    def _time_major(self, batch):
+        """Reference-layout sampled batch (numpy / torch, [B, T(+1), ...]) or a time-major
+        batch from EpisodeReplayBuffer.sample(time_major=True) -> time-major device tensors."""
+        dev = self.device
+        T = int(batch["max_seq_len"])
+        tm = bool(batch.get("time_major", False))
+
+        def get(key, dtype, n_t):
+            x = batch[key]
+            x = torch.as_tensor(x) if not torch.is_tensor(x) else x
+            x = x.to(device=dev)
+            x = x[:n_t] if tm else x[:, :n_t].transpose(0, 1)
+            return x.to(dtype).contiguous()
+
+        B = (batch["state"].shape[1] if tm else batch["state"].shape[0])
+        return {
+            "T": T, "B": int(B),
+            "state": get("state", torch.float32, T), "obs": get("obs", torch.float32, T),
+            "hidden": get("hidden_state", torch.float32, max(T - 1, 0)),
+            "a_d": get("actions_discrete", torch.int32, max(T - 1, 0)),
+            "a_c": get("actions_continuous", torch.float32, max(T - 1, 0)),
+            "reward": get("reward", torch.float32, max(T - 1, 0)),
+            "terminated": get("terminated", torch.uint8, max(T - 1, 0)),
+            "filled": get("filled", torch.uint8, max(T - 1, 0)),
+        }
+
+    # ------------------------------------------------------------------ the train step
+    @torch.no_grad()
+    def train(self, batch, train_info=None, *, lazy_stats=False, return_debug=False):
+        """core/qmix.py:76-215.  Returns {loss, grad_norm, eval_qtot_avg, target_qtot_avg}."""
+        self.train_step += 1
+        L, ctx, dev = self.lib(), self._ctx(), self.device
+        tb = self._time_major(batch)
+        T, B, Nn, A = tb["T"], tb["B"], self.n_agents, self.n_actions
+        if T < 2:
+            raise ValueError("QMixLearner.train needs episodes of at least 2 steps")
+        M, R = B * Nn, B * (T - 1)
+        S = tb["state"].shape[-1]
+        H = self.args.rnn_hidden_dim
+        agent, tgt_agent = self.mac.agent, self.target_mac.agent
+        obs = tb["obs"].view(T, M, -1)
+
+        # 1-2. unrolls from a zero hidden state (qmix.py:129-147)
+        ev = agent.run(obs, None, n_steps=T, zero_init=True, want_greedy=True)
+        tg = tgt_agent.run(obs, None, n_steps=T, zero_init=True, sel_actions=ev["greedy"])
+        tq_taken = tg["q_sel"][1:].reshape(R, Nn)
+
+        # 3. target mixer (qmix.py:151)
+        dims = N.MixerDims(n_rows=R, state_dim=S, n_agents=Nn, embed_dim=self.args.mixing_embed_dim,
+                           hyper_hidden=self.args.hyper_hidden_dim, reserved=0)
+        ws_floats = L.lib.macjd_mixer_workspace_floats(dims)
+        ws = self._workspace("mixer", ws_floats, dev)
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        tq_tot, q_tot, dq_tot, targets = f32(R), f32(R), f32(R), f32(R)
+        states_next = tb["state"][1:T].reshape(R, S)
+        states_cur = tb["state"][0:T - 1].reshape(R, S)
+        L.callv("macjd_mixer_forward", ctx, dims, self._mixer_struct(self.target_qmix_net), tq_taken, states_next,
+                tq_tot, ws, ws_floats)
+
+        # 4. Q(s_t, a_t, P_t) from the stored hidden states (qmix.py:161-184)
+        qd = N.QheadDims(n_rows=R * Nn, hidden=H, n_actions=A, reserved=0)
+        pk = agent.packed().cstruct()
+        hidden = tb["hidden"].view(R * Nn, H)
+        a_d, a_c = tb["a_d"].view(-1), tb["a_c"].view(-1)
+        if int(a_d.numel()) and (int(a_d.min()) < 0 or int(a_d.max()) >= A):
+            raise IndexError(f"Action index out of bounds, n_actions: {A}")      # networks.py:157-158
+        q_taken = f32(R * Nn)
+        hid = self._workspace("qhead_hid", R * Nn * H, dev)
+        L.callv("macjd_qhead_forward", ctx, qd, pk, hidden, a_d, a_c, q_taken, hid)
+
+        # 5. eval mixer (qmix.py:187); leaves its intermediates in the workspace
+        eval_struct = self._mixer_struct(self.eval_qmix_net)
+        L.callv("macjd_mixer_forward", ctx, dims, eval_struct, q_taken, states_cur, q_tot, ws, ws_floats)
+
+        # 6. TD targets and masked loss sums (qmix.py:155,191-194)
+        opt = self._ensure_opt_state()
+        grad, total = opt["grad"], opt["total"]
+        sums = grad[total:total + 4]                       # rides in the all-reduce bucket
+        td_ws = self._workspace("td", L.lib.macjd_td_scratch_floats(R), dev)
+        L.callv("macjd_td_loss", ctx, R, q_tot, tq_tot, tb["reward"].view(-1), tb["terminated"].view(-1),
+                tb["filled"].view(-1), float(self.args.gamma), dq_tot, targets, sums, td_ws, td_ws.numel())
+
+        # 7-8. backward: mixer, then the Q-head (the only agent tensors with gradients)
+        qh = sum(opt["sizes"][:4])
+        dq = f32(R * Nn)
+        L.callv("macjd_mixer_backward", ctx, dims, eval_struct, q_taken, dq_tot, ws, ws_floats,
+                self._mixer_struct(flat=grad, offset=qh), dq)
+        o0, o1, o2, o3 = np.cumsum([0] + opt["sizes"][:3])
+        qs = self._workspace("qhead_scratch", L.lib.macjd_qhead_scratch_floats(qd), dev)
+        L.callv("macjd_qhead_backward", ctx, qd, pk, hidden, a_d, a_c, hid, dq,
+                grad[o0:], grad[o1:], grad[o2:], grad[o3:], qs, qs.numel())
+
+        # 9. data-parallel exchange: gradients + {sum td^2, sum mask, sum q_tot, sum targets}
+        world = 1
+        if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                              and getattr(self.args, "data_parallel", False)):
+            torch.distributed.all_reduce(grad, group=self.process_group)
+            world = torch.distributed.get_world_size(self.process_group)
+
+        # 10. clip + Adam on the Q-head and the mixer (qmix.py:197-200)
+        opt["step"] += 1
+        tr = self._trainable()
+        tensors = N.OptTensors(count=len(tr), reserved=0)
+        for i, (p, _) in enumerate(tr):
+            tensors.param[i] = p.data_ptr()
+            tensors.numel[i] = p.numel()
+        debug = None
+        if return_debug:
+            debug = {"grad": grad[:total].clone(), "names": [n for _, n in tr], "sizes": list(opt["sizes"]),
+                     "q_tot": q_tot.clone(), "targets": targets.clone(), "q_taken": q_taken.clone(),
+                     "tq_taken": tq_taken.clone(), "next_actions": ev["greedy"][1:].clone(), "sums": sums.clone()}
+        L.callv("macjd_clip_adam", ctx, tensors, grad, opt["m"], opt["v"], sums, float(self.args.grad_norm_clip),
+                float(self.args.lr), BETA1, BETA2, ADAM_EPS, int(opt["step"]), opt["scal"], opt["scratch"],
+                opt["scratch"].numel())
+        agent.packed(force=True)          # the Q-head changed under the packed copy
+
+        # 11. hard target sync (qmix.py:203-205)
+        if (self.train_step - self.last_target_update_step) >= self.args.target_update_interval:
+            self._update_targets()
+            self.last_target_update_step = self.train_step
+
+        # 12. stats (qmix.py:209-215)
+        rows_total = float(R * world)
+        stats_dev = torch.stack([opt["scal"][2], opt["scal"][0], sums[2] / rows_total, sums[3] / rows_total])
+        if lazy_stats:
+            stats = {"stats_tensor": stats_dev}
+        else:
+            s = stats_dev.tolist()
+            stats = {"loss": s[0], "grad_norm": s[1], "eval_qtot_avg": s[2], "target_qtot_avg": s[3]}
+        if return_debug:
+            stats["debug"] = debug
+        return stats
+
+    # ------------------------------------------------------------------ reference API
+    def _update_targets(self):
+        """qmix.py:282-290"""
+        self.target_mac.load_state(self.mac.state_dict())
+        self.target_qmix_net.load_state_dict(self.eval_qmix_net.state_dict())
+
+    def cuda(self):
+        self.mac.cuda()
+        self.target_mac.cuda()
+        self.eval_qmix_net.cuda()
+        self.target_qmix_net.cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def _export_optimizer_state(self):
+        """Fill the torch.optim.Adam object with the kernel's moments so optimizer.pth keeps
+        the reference's format (state only for the tensors that ever had a gradient)."""
+        if self._opt_state is None or self._opt_state["step"] == 0:
+            return
+        o, off = self._opt_state, 0
+        for (p, _), n in zip(self._trainable(), o["sizes"]):
+            self.optimizer.state[p] = {"step": torch.tensor(float(o["step"])),
+                                       "exp_avg": o["m"][off:off + n].view_as(p).clone(),
+                                       "exp_avg_sq": o["v"][off:off + n].view_as(p).clone()}
+            off += n
+
+    def save_models(self, path):
+        """qmix.py:300-315: agent.pth, qmix_net.pth, optimizer.pth"""
+        os.makedirs(path, exist_ok=True)
+        self.mac.save_models(path)
+        torch.save(self.eval_qmix_net.state_dict(), f"{path}/qmix_net.pth")
+        self._export_optimizer_state()
+        torch.save(self.optimizer.state_dict(), f"{path}/optimizer.pth")
+
+    def load_models(self, path):
+        """qmix.py:317-334 (the optimizer state is not restored, as in the reference)."""
+        self.mac.load_models(path)
+        self.eval_qmix_net.load_state_dict(torch.load(f"{path}/qmix_net.pth", map_location=lambda storage, loc: storage))
+        self._update_targets()

@@ -4,6 +4,8 @@
 #include "macjd_common.cuh"
 #include "env_step.cuh"
 #include "agent_act.cuh"
+#include "replay.cuh"
+#include "learner.cuh"
 
 #include <stdio.h>
 #include <string.h>
@@ -59,6 +61,11 @@ size_t macjd_abi_sizeof(int which) {
     case 2: return sizeof(macjd_env_io);
     case 3: return sizeof(macjd_agent_weights);
     case 4: return sizeof(macjd_agent_io);
+    case 5: return sizeof(macjd_copy_desc);
+    case 6: return sizeof(macjd_mixer_dims);
+    case 7: return sizeof(macjd_mixer_params);
+    case 8: return sizeof(macjd_qhead_dims);
+    case 9: return sizeof(macjd_opt_tensors);
     default: return 0;
   }
 }
@@ -79,6 +86,88 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   int st = enter(ctx);
   if (st != MACJD_OK) return st;
   return finish(ctx, macjd::agent_launch(ctx, w, io));
+}
+
+int macjd_replay_copy(const macjd_ctx* ctx, const macjd_copy_desc* descs_host, int32_t n_keys, const int32_t* idx,
+                      int32_t n_eps, int32_t index_on_src) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  return finish(ctx, macjd::replay_copy(ctx, descs_host, n_keys, idx, n_eps, index_on_src));
+}
+
+static bool mixer_dims_ok(const macjd_mixer_dims* d) {
+  return d && d->n_rows >= 0 && d->state_dim > 0 && d->n_agents > 0 && d->embed_dim > 0 && d->hyper_hidden > 0;
+}
+
+size_t macjd_mixer_workspace_floats(const macjd_mixer_dims* dims) {
+  if (!mixer_dims_ok(dims)) return 0;
+  return macjd::mixer_ws_layout(*dims, nullptr).total;
+}
+
+int macjd_mixer_forward(const macjd_ctx* ctx, const macjd_mixer_dims* dims, const macjd_mixer_params* w, const float* q,
+                        const float* states, float* q_tot, float* workspace, size_t workspace_floats) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!mixer_dims_ok(dims) || !w || !q || !states || !q_tot) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::mixer_forward((cudaStream_t)ctx->stream, *dims, *w, q, states, q_tot, workspace, workspace_floats));
+}
+
+int macjd_mixer_backward(const macjd_ctx* ctx, const macjd_mixer_dims* dims, const macjd_mixer_params* w, const float* q,
+                         const float* dq_tot, float* workspace, size_t workspace_floats, const macjd_mixer_params* grads,
+                         float* dq) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!mixer_dims_ok(dims) || !w || !q || !dq_tot || !grads) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::mixer_backward((cudaStream_t)ctx->stream, *dims, *w, q, dq_tot, workspace, workspace_floats, *grads, dq));
+}
+
+size_t macjd_qhead_scratch_floats(const macjd_qhead_dims* dims) {
+  if (!dims || dims->n_rows < 0 || dims->hidden < 1 || dims->n_actions < 1) return 0;
+  return macjd::qhead_scratch_floats(*dims);
+}
+
+int macjd_qhead_forward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
+                        const float* hidden, const int32_t* a_d, const float* a_c, float* q, float* hid) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!dims || !w || !hidden || !a_d || !a_c || !q || !hid || dims->n_rows < 0) return MACJD_ERR_INVALID_ARG;
+  if (dims->hidden != w->hidden || dims->n_actions != w->n_actions) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::qhead_forward((cudaStream_t)ctx->stream, *dims, *w, hidden, a_d, a_c, q, hid));
+}
+
+int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
+                         const float* hidden, const int32_t* a_d, const float* a_c, float* hid, const float* dq,
+                         float* g_w1, float* g_b1, float* g_w2, float* g_b2, float* scratch, size_t scratch_floats) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!dims || !w || !hidden || !a_d || !a_c || !hid || !dq || !g_w1 || !g_b1 || !g_w2 || !g_b2) return MACJD_ERR_INVALID_ARG;
+  if (dims->hidden != w->hidden || dims->n_actions != w->n_actions) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::qhead_backward((cudaStream_t)ctx->stream, *dims, *w, hidden, a_d, a_c, hid, dq, g_w1, g_b1,
+                                           g_w2, g_b2, scratch, scratch_floats));
+}
+
+size_t macjd_td_scratch_floats(int32_t n_rows) { return n_rows > 0 ? macjd::td_scratch_floats(n_rows) : 0; }
+
+int macjd_td_loss(const macjd_ctx* ctx, int32_t n_rows, const float* q_tot, const float* tq_tot, const float* reward,
+                  const uint8_t* terminated, const uint8_t* filled, float gamma, float* dq_tot, float* targets,
+                  float* sums, float* scratch, size_t scratch_floats) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!q_tot || !tq_tot || !reward || !terminated || !filled || !dq_tot || !sums) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::td_loss((cudaStream_t)ctx->stream, n_rows, q_tot, tq_tot, reward, terminated, filled, gamma,
+                                    dq_tot, targets, sums, scratch, scratch_floats));
+}
+
+size_t macjd_opt_scratch_floats(void) { return macjd::opt_scratch_floats(); }
+
+int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, const float* grad, float* m, float* v,
+                    const float* sums, float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
+                    float* scal, float* scratch, size_t scratch_floats) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!tensors || !grad || !m || !v || !sums || !scal) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::clip_adam((cudaStream_t)ctx->stream, *tensors, grad, m, v, sums, max_norm, lr, beta1, beta2,
+                                      eps, step, scal, scratch, scratch_floats));
 }
 
 }  // extern "C"

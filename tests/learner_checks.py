@@ -1,0 +1,177 @@
+"""Learner / mixer / replay parity checks shared by the host-emulation (CPU) and GPU tests."""
+import json
+import os
+import types
+
+import numpy as np
+import torch
+
+from oracle import agent_oracle as AO
+from tests.helpers import GOLDEN
+from macjd_b200 import _native as N
+
+
+def _load(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return g, types.SimpleNamespace(**json.loads(str(g["args_json"])))
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def _ctx(dev):
+    return N.torch_ctx(dev) if torch.device(dev).type == "cuda" else N.Ctx(device=0, reserved=0, stream=None)
+
+
+def check_mixer_against_golden(name, device, lib):
+    """QMixer forward and every parameter gradient against the reference module's autograd."""
+    from macjd_b200.core.networks import QMixer
+    g, args = _load("mixer_" + name)
+    net = QMixer(args)
+    net.load_state_dict(_sd(g, "sd."))
+    net.to(device)
+    assert sum(p.numel() for p in net.parameters()) == int(g["n_params"])
+    dev = torch.device(device)
+    q = torch.from_numpy(g["q"]).to(dev)
+    s = torch.from_numpy(g["s"]).to(dev)
+    R = q.shape[0]
+    dims = N.MixerDims(n_rows=R, state_dim=args.state_shape, n_agents=args.n_agents, embed_dim=args.mixing_embed_dim,
+                       hyper_hidden=args.hyper_hidden_dim, reserved=0)
+    wsf = lib.lib.macjd_mixer_workspace_floats(dims)
+    ws = torch.empty(wsf, dtype=torch.float32, device=dev)
+    sd = dict(net.named_parameters())
+    w = N.MixerParams(**{f: sd[k].data_ptr() for f, k in zip(N.MIXER_FIELDS, N.MIXER_KEYS)})
+    y = torch.empty(R, dtype=torch.float32, device=dev)
+    lib.callv("macjd_mixer_forward", _ctx(dev), dims, w, q, s, y, ws, wsf)
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], rtol=1e-5, atol=2e-6)
+    grads = {k: torch.full_like(p, 7.0) for k, p in sd.items()}      # poisoned: must be overwritten
+    gw = N.MixerParams(**{f: grads[k].data_ptr() for f, k in zip(N.MIXER_FIELDS, N.MIXER_KEYS)})
+    dq = torch.empty(R, args.n_agents, dtype=torch.float32, device=dev)
+    dy = torch.from_numpy(g["w"]).to(dev)
+    lib.callv("macjd_mixer_backward", _ctx(dev), dims, w, q, dy, ws, wsf, gw, dq)
+    np.testing.assert_allclose(dq.cpu().numpy(), g["dq"], rtol=1e-4, atol=1e-6)
+    for k in sd:
+        ref = g["grad." + k]
+        np.testing.assert_allclose(grads[k].cpu().numpy(), ref, rtol=2e-4, atol=2e-5 * max(1.0, np.abs(ref).max()), err_msg=k)
+
+
+def make_learner(args, agent_sd, mixer_sd, device, lib):
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.core.qmix import QMixLearner
+    args.use_cuda = torch.device(device).type == "cuda"
+    args.device = device
+    mac = BasicMAC(args.obs_shape, args, _lib=lib)
+    mac.agent.load_state_dict(agent_sd)
+    learner = QMixLearner(mac, args, _lib=lib)
+    learner.eval_qmix_net.load_state_dict(mixer_sd)
+    learner._update_targets()
+    return learner
+
+
+def check_learner_against_golden(name, device, lib):
+    """Whole train steps against the unmodified reference learner: stats, (clipped) gradients
+    of every trained tensor, post-Adam weights, target sync; untrained tensors stay frozen."""
+    g, args = _load("learner_" + name)
+    agent0, mixer0 = _sd(g, "agent0."), _sd(g, "mixer0.")
+    L = make_learner(args, agent0, mixer0, device, lib)
+    for step in range(int(g["n_steps"])):
+        pre = f"step{step}."
+        batch = {}
+        for k in g.files:
+            if k.startswith(pre + "batch."):
+                v = g[k]
+                batch[k[len(pre + "batch."):]] = int(v) if v.ndim == 0 else v
+        stats = L.train(batch, {}, return_debug=True)
+        dbg = stats.pop("debug")
+        ref = g[pre + "stats"]
+        np.testing.assert_allclose([stats["loss"], stats["grad_norm"], stats["eval_qtot_avg"], stats["target_qtot_avg"]],
+                                   ref, rtol=5e-5, err_msg=f"stats step {step}")
+        coef = min(1.0, args.grad_norm_clip / (stats["grad_norm"] + 1e-6))
+        scale = coef / float(dbg["sums"][1])
+        off = 0
+        for nm, n in zip(dbg["names"], dbg["sizes"]):
+            kind, key = nm.split(".", 1)
+            ref_g = g[pre + ("agent_grad." if kind == "agent" else "mixer_grad.") + key]
+            mine = dbg["grad"][off:off + n].cpu().numpy().reshape(ref_g.shape) * scale
+            np.testing.assert_allclose(mine, ref_g, rtol=5e-4, atol=5e-6 * max(1e-3, np.abs(ref_g).max()), err_msg=f"{nm} step {step}")
+            off += n
+        sd_now = {k: v.detach().cpu().numpy() for k, v in L.mac.agent.state_dict().items()}
+        for k in agent0:
+            if k in AO.TRAINED_AGENT_KEYS:
+                w0 = agent0[k].numpy()
+                np.testing.assert_allclose(sd_now[k] - w0, g[pre + "agent." + k] - w0, rtol=5e-3,
+                                           atol=args.lr * 5e-3 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+            else:
+                np.testing.assert_array_equal(sd_now[k], agent0[k].numpy(), err_msg=f"{k} must stay frozen")
+        tgt_now = L.target_mac.agent.state_dict()
+        for k in AO.TRAINED_AGENT_KEYS:
+            np.testing.assert_allclose(tgt_now[k].cpu().numpy(), g[pre + "tgt_agent." + k], rtol=1e-5, atol=1e-6)
+        mix_now = L.eval_qmix_net.state_dict()
+        tmix_now = L.target_qmix_net.state_dict()
+        for k in mixer0:
+            w0 = mixer0[k].numpy()
+            np.testing.assert_allclose(mix_now[k].cpu().numpy() - w0, g[pre + "mixer." + k] - w0, rtol=5e-3,
+                                       atol=args.lr * 5e-3 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+            np.testing.assert_allclose(tmix_now[k].cpu().numpy(), g[pre + "tgt_mixer." + k], rtol=1e-5, atol=1e-6)
+    return L
+
+
+def check_replay_against_golden(device, lib):
+    """store_episode / sample against the reference ring buffer: ring index arithmetic, padding
+    rules, trimming to the longest sampled episode, dtypes of the returned dict."""
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    g, args = _load("replay")
+    buf = EpisodeReplayBuffer(args, device=device, _lib=lib)
+    keys = ("state", "obs", "actions_discrete", "actions_continuous", "avail_actions", "reward", "terminated", "hidden_state")
+    for i in range(int(g["n_eps"])):
+        buf.store_episode({k: [g[f"ep{i}.{k}"]] for k in keys})
+        assert buf.current_index == int(g[f"after{i}.current_index"])
+        assert buf.current_size == int(g[f"after{i}.current_size"]) == len(buf)
+        if f"sample{i}.indices" in g.files:
+            out = buf.gather(g[f"sample{i}.indices"])
+            assert out["max_seq_len"] == int(g[f"sample{i}.max_seq_len"])
+            for k in keys + ("filled",):
+                ref = g[f"sample{i}.{k}"]
+                mine = out[k].cpu().numpy()
+                assert mine.shape == ref.shape, k
+                np.testing.assert_array_equal(mine.astype(ref.dtype), ref, err_msg=k)
+    # the public sample(): reference dtypes for masks / avail, no replacement
+    np.random.seed(0)
+    s = buf.sample(4)
+    assert s["terminated"].dtype == torch.bool and s["filled"].dtype == torch.bool and s["avail_actions"].dtype == torch.int64
+    assert s["state"].shape[0] == 4
+    np.random.seed(0)
+    s2 = buf.sample(4, time_major=True)
+    assert torch.equal(s2["state"].transpose(0, 1), s["state"])
+    assert buf.sample(0) is None
+    return buf
+
+
+def check_rollout_store_roundtrip(device, lib, n=7, seed=0):
+    """store_rollout (time-major device buffers of many episodes) -> gather returns them."""
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    args = types.SimpleNamespace(buffer_size=10, episode_limit=5, n_actions=5, n_agents=2, state_shape=8, obs_shape=8,
+                                 rnn_hidden_dim=64, use_cuda=True, device=device)
+    buf = EpisodeReplayBuffer(args, device=device, _lib=lib)
+    gen = torch.Generator().manual_seed(seed)
+    T, Nn = 5, 2
+    def mk(n_eps):
+        return {"state": torch.randn(T + 1, n_eps, 8, generator=gen), "obs": torch.randn(T + 1, n_eps, Nn, 8, generator=gen),
+                "actions_discrete": torch.randint(0, 5, (T, n_eps, Nn, 1), generator=gen, dtype=torch.int32),
+                "actions_continuous": torch.rand(T, n_eps, Nn, 1, generator=gen),
+                "avail_actions": torch.randint(0, 2, (T + 1, n_eps, Nn, 5), generator=gen, dtype=torch.uint8),
+                "reward": torch.randn(T, n_eps, 1, generator=gen),
+                "terminated": torch.randint(0, 2, (T, n_eps, 1), generator=gen, dtype=torch.uint8),
+                "hidden_state": torch.randn(T + 1, n_eps, Nn, 64, generator=gen)}
+    first, second = mk(n), mk(n)
+    buf.store_rollout({k: v.to(device) for k, v in first.items()})
+    assert (buf.current_index, buf.current_size) == (7, 7)
+    buf.store_rollout({k: v.to(device) for k, v in second.items()})          # wraps: slots 7,8,9,0,1,2,3
+    assert (buf.current_index, buf.current_size) == (4, 10)
+    out = buf.gather(np.array([8, 0, 4, 6]))
+    src = [(second, 1), (second, 3), (first, 4), (first, 6)]
+    for k in first:
+        for b, (tr, e) in enumerate(src):
+            assert torch.equal(out[k][b].cpu(), tr[k][:, e]), (k, b)
+    assert bool(out["filled"].all())

@@ -1,0 +1,24 @@
+"""Learner, mixer and replay kernels checked on the CPU through the host-emulation build
+(tests/emul) against the reference goldens.  GPU twin: tests/test_gpu_learner.py."""
+import pytest
+
+from tests import learner_checks as LC
+from tests.helpers import emul_lib
+
+
+@pytest.mark.parametrize("name", ["c1", "small"])
+def test_mixer_forward_backward(name):
+    LC.check_mixer_against_golden(name, "cpu", emul_lib())
+
+
+@pytest.mark.parametrize("name", ["c1", "small_fastlr"])
+def test_learner_train_steps(name):
+    LC.check_learner_against_golden(name, "cpu", emul_lib())
+
+
+def test_replay_store_sample():
+    LC.check_replay_against_golden("cpu", emul_lib())
+
+
+def test_replay_rollout_roundtrip():
+    LC.check_rollout_store_roundtrip("cpu", emul_lib())
