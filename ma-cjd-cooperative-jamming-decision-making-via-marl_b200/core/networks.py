@@ -141,11 +141,12 @@ class RNNAgent(nn.Module):
     @torch.no_grad()
     def run(self, obs, hidden=None, *, n_steps=1, zero_init=False, avail=None, epsilon=0.0, test_mode=True,
             u_eps=None, rand_actions=None, seed=0, rng_step=0, select=False, want_q=False, want_params=False,
-            want_greedy=False, sel_actions=None, want_hidden_seq=False, tile_rows=0):
+            want_greedy=False, sel_actions=None, want_hidden_seq=False, tile_rows=0, out=None):
         """One fused launch.  obs float32 [T, M, O] (or [M, O]); hidden float32 [M, H] updated in
         place.  Returns a dict with the requested outputs."""
         dev = self.fc1.weight.device
-        obs = obs.to(device=dev, dtype=torch.float32)
+        if obs.device != dev or obs.dtype != torch.float32:
+            obs = obs.to(device=dev, dtype=torch.float32)
         if obs.dim() == 2:
             obs = obs.unsqueeze(0)
         obs = obs.contiguous()
@@ -153,30 +154,40 @@ class RNNAgent(nn.Module):
         assert O == self.input_shape and T == n_steps
         A, H = self.n_actions, self.rnn_hidden_dim
         pk = self.packed()
+        given = out or {}     # caller-provided output buffers (e.g. slices of a trajectory)
         out = {}
-        mk = lambda *shape, dtype=torch.float32: torch.empty(*shape, dtype=dtype, device=dev)
+
+        def mk(*shape, dtype=torch.float32, name=None):
+            t = given.get(name)
+            if t is not None:
+                assert t.is_contiguous() and t.dtype == dtype and t.numel() == int(np.prod(shape)), name
+                return t
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
         if hidden is None:
             hidden = torch.zeros(M, H, dtype=torch.float32, device=dev)
             zero_init = True
         assert hidden.is_contiguous() and hidden.shape == (M, H) and hidden.dtype == torch.float32
         out["hidden"] = hidden
         if want_hidden_seq:
-            out["hidden_seq"] = mk(T, M, H)
+            out["hidden_seq"] = mk(T, M, H, name="hidden_seq")
         if want_q:
-            out["q_all"] = mk(T, M, A)
+            out["q_all"] = mk(T, M, A, name="q_all")
         if want_params:
-            out["params_all"] = mk(T, M, A)
+            out["params_all"] = mk(T, M, A, name="params_all")
         if want_greedy:
-            out["greedy"] = mk(T, M, dtype=torch.int32)
+            out["greedy"] = mk(T, M, dtype=torch.int32, name="greedy")
         if sel_actions is not None:
             sel_actions = sel_actions.to(device=dev, dtype=torch.int32).contiguous()
-            out["q_sel"] = mk(T, M)
+            out["q_sel"] = mk(T, M, name="q_sel")
         if select:
-            out["actions"] = mk(T, M, dtype=torch.int32)
-            out["power"] = mk(T, M)
-            out["q_chosen"] = mk(T, M)
+            out["actions"] = mk(T, M, dtype=torch.int32, name="actions")
+            out["power"] = mk(T, M, name="power")
+            out["q_chosen"] = mk(T, M, name="q_chosen")
         if avail is not None:
-            avail = avail.to(device=dev).ne(0).to(torch.uint8).reshape(T, M, A).contiguous()
+            if avail.dtype != torch.uint8 or avail.device != dev:
+                avail = avail.to(device=dev).ne(0).to(torch.uint8)
+            avail = avail.reshape(T, M, A).contiguous()
         if u_eps is not None:
             u_eps = u_eps.to(device=dev, dtype=torch.float32).reshape(T, M).contiguous()
         if rand_actions is not None:

@@ -1,0 +1,207 @@
+"""Episode rollouts (drop-in for runners/episode_runner.py).
+
+``EpisodeRunner`` follows the reference protocol one environment at a time (it works with
+the single-instance shim of the environment and stores one host-staged episode per call,
+episode_runner.py:27-181).  ``BatchedEpisodeRunner`` is the device-resident version: all
+``n_envs`` episodes advance together, the agent and step kernels write straight into
+time-major trajectory buffers in HBM and the finished episodes go to the replay ring with
+one copy kernel -- no host round trip inside an episode.
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+import torch
+
+
+class EpisodeBatch:
+    """Host staging of one episode (episode_runner.py:187-277): zero-initialised arrays with
+    T (+1) slots; `update_last` only writes if the episode ended early (reference fact 9)."""
+
+    T_PLUS_1 = ("state", "obs", "avail_actions", "hidden_state")
+
+    def __init__(self, args, max_seq_length, n_agents, obs_shape):
+        self.args = args
+        self.max_seq_length = max_seq_length
+        self.n_agents = n_agents
+        self.obs_shape = obs_shape
+        self.scheme = self._get_scheme(args)
+        self.data = {}
+        self.t = 0
+
+    def _get_scheme(self, args):
+        info = args.env_info
+        return {"state": ((info["state_shape"],), None, np.float32),
+                "obs": ((self.obs_shape,), "agents", np.float32),
+                "actions_discrete": ((1,), "agents", np.int32),
+                "actions_continuous": ((1,), "agents", np.float32),
+                "avail_actions": ((info["n_actions"],), "agents", np.int64),
+                "reward": ((1,), None, np.float32),
+                "terminated": ((1,), None, np.bool_),
+                "hidden_state": ((args.rnn_hidden_dim,), "agents", np.float32)}
+
+    def _init_data(self):
+        self.data = {}
+        for key, (shape, group, dtype) in self.scheme.items():
+            n_t = self.max_seq_length + 1 if key in self.T_PLUS_1 else self.max_seq_length
+            full = (n_t, self.n_agents) + shape if group == "agents" else (n_t,) + shape
+            self.data[key] = np.zeros(full, dtype=dtype)
+        self.t = 0
+
+    def push(self, transition_data):
+        if self.t == 0:
+            self._init_data()
+        if self.t < self.max_seq_length:
+            for key, value in transition_data.items():
+                if key in self.data:
+                    self.data[key][self.t] = value
+            self.t += 1
+        else:
+            print("Warning: Episode length exceeded max_seq_length. Data not stored.")
+
+    def update_last(self, last_data):
+        if self.t < self.max_seq_length:
+            for key, value in last_data.items():
+                if key in self.data:
+                    self.data[key][self.t] = value
+
+    def get_batch_data(self):
+        out = {}
+        for key in self.scheme:
+            n = self.t + 1 if key in self.T_PLUS_1 else self.t
+            out[key] = [self.data[key][:n]]
+        return out
+
+
+class EpisodeRunner:
+    """One episode per ``run`` through the reference-facing API (episode_runner.py:5-184)."""
+
+    def __init__(self, env, mac, buffer, args):
+        self.env, self.mac, self.buffer, self.args = env, mac, buffer, args
+        info = self.env.get_env_info()
+        self.episode_limit = info["episode_limit"]
+        self.n_agents = info["n_agents"]
+        self.t = 0
+        self.t_env = 0
+        self.new_batch = partial(EpisodeBatch, self.args, self.episode_limit, self.n_agents, info["obs_shape"])
+        self.device = mac.device if hasattr(mac, "device") else torch.device("cpu")
+
+    def run(self, test_mode=False):
+        batch = self.new_batch()
+        self.mac.init_hidden(batch_size=1)
+        self.env.reset()
+        state = self.env.get_state()
+        obs_list = self.env.get_obs()
+        terminated, step, episode_return = False, 0, 0
+        log = {"r": [], "r_d": [], "r_p": [], "r_j": [], "a_d": [], "a_c": []}
+        info = {}
+        while not terminated:
+            avail_list = self.env.get_avail_actions()
+            obs_t = torch.as_tensor(np.array(obs_list), dtype=torch.float32).unsqueeze(0).to(self.device)
+            avail_t = torch.as_tensor(np.array(avail_list), dtype=torch.long).unsqueeze(0).to(self.device)
+            a_t, p_t = self.mac.select_actions(obs_t, avail_t, self.t_env, test_mode=test_mode)
+            hidden = self.mac.hidden_states.detach().cpu().reshape(self.n_agents, -1).numpy()
+            a_d = a_t.detach().squeeze(0).cpu().numpy()
+            a_c = p_t.detach().squeeze(0).cpu().numpy()
+            next_obs, reward, terminated, info = self.env.step([(d[0], c[0]) for d, c in zip(a_d, a_c)])
+            log["r"].append(reward); log["r_d"].append(info.get("r_d", 0)); log["r_p"].append(info.get("r_p", 0))
+            log["r_j"].append(info.get("r_j", 0)); log["a_d"].append(a_d); log["a_c"].append(a_c)
+            episode_return += reward
+            batch.push({"state": np.array(state), "obs": np.array(obs_list), "actions_discrete": a_d,
+                        "actions_continuous": a_c, "avail_actions": np.array(avail_list),
+                        "reward": np.array([reward]), "terminated": np.array([terminated]), "hidden_state": hidden})
+            state = self.env.get_state()
+            obs_list = next_obs
+            step += 1
+            self.t_env += 1
+            if terminated or step >= self.episode_limit:
+                batch.update_last({"state": np.array(self.env.get_state()), "obs": np.array(next_obs),
+                                   "avail_actions": np.array(self.env.get_avail_actions())})
+                break
+        if not test_mode:
+            self.buffer.store_episode(batch.get_batch_data())
+        a_d_all = np.array(log["a_d"]) if log["a_d"] else np.empty((0, self.n_agents, 1))
+        a_c_all = np.array(log["a_c"]) if log["a_c"] else np.empty((0, self.n_agents, 1))
+        counts = np.bincount(a_d_all.flatten().astype(int), minlength=self.args.n_actions)[:self.args.n_actions] \
+            if a_d_all.size else np.zeros(self.args.n_actions)
+        run_info = {"episode_length": step, "episode_return": episode_return,
+                    "avg_step_reward": np.mean(log["r"]) if log["r"] else 0,
+                    "avg_r_d": np.mean(log["r_d"]) if log["r_d"] else 0,
+                    "avg_r_p": np.mean(log["r_p"]) if log["r_p"] else 0,
+                    "avg_r_j": np.mean(log["r_j"]) if log["r_j"] else 0,
+                    "avg_power_overall": float(np.mean(a_c_all)) if a_c_all.size else 0.0,
+                    "action_distribution": counts / max(1, counts.sum())}
+        if "individual_rewards" in info:
+            run_info["individual_rewards_final"] = info["individual_rewards"]
+        return run_info
+
+    def close_env(self):
+        self.env.close()
+
+
+class BatchedEpisodeRunner:
+    """All ``n_envs`` episodes of a batched environment advance together on the device.
+
+    Per timestep: one fused agent kernel (reads obs / avail of slot t, writes actions, powers
+    and h_t into slot t) and one fused env-step kernel (reads them, writes reward / terminated
+    into slot t and state / obs / avail into slot t+1).  ``run`` returns the same ``run_info``
+    keys as the reference runner, averaged over the batch, and stores the episodes in the
+    replay ring (``store_rollout``)."""
+
+    def __init__(self, env, mac, buffer, args):
+        assert env.batched, "BatchedEpisodeRunner needs ElectromagneticEnvironment(n_envs=...)"
+        self.env, self.mac, self.buffer, self.args = env, mac, buffer, args
+        info = env.get_env_info()
+        self.episode_limit, self.n_agents = info["episode_limit"], info["n_agents"]
+        self.n_envs = env.n_envs
+        self.t_env = 0
+        dev = env.device
+        n, T, Nn, S, A, H = self.n_envs, self.episode_limit, self.n_agents, info["state_shape"], info["n_actions"], args.rnn_hidden_dim
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        self.traj = {"state": z((T + 1, n, S), torch.float32), "obs": z((T + 1, n, Nn, S), torch.float32),
+                     "actions_discrete": z((T, n, Nn, 1), torch.int32), "actions_continuous": z((T, n, Nn, 1), torch.float32),
+                     "avail_actions": z((T + 1, n, Nn, A), torch.uint8), "reward": z((T, n, 1), torch.float32),
+                     "terminated": z((T, n, 1), torch.uint8), "hidden_state": z((T + 1, n, Nn, H), torch.float32)}
+        self.r_parts = z((3, T, n), torch.float32)
+
+    def step(self, t, test_mode=False, noise=None, u_eps=None, rand_actions=None):
+        """Timestep t of the current episodes: agent act + env step, both into the trajectory."""
+        tr, mac, env = self.traj, self.mac, self.env
+        n, Nn = self.n_envs, self.n_agents
+        eps = mac.action_selector.anneal(self.t_env, test_mode)
+        mac._rng_step += 1
+        mac.agent.run(tr["obs"][t].view(1, n * Nn, -1), mac.hidden_states, avail=tr["avail_actions"][t],
+                      epsilon=eps, test_mode=test_mode, u_eps=u_eps, rand_actions=rand_actions, seed=mac.seed,
+                      rng_step=mac._rng_step, select=True, want_hidden_seq=True,
+                      out={"actions": tr["actions_discrete"][t], "power": tr["actions_continuous"][t],
+                           "hidden_seq": tr["hidden_state"][t]})
+        env.step_device(tr["actions_discrete"][t], tr["actions_continuous"][t], noise,
+                        out={"reward": tr["reward"][t], "terminated": tr["terminated"][t],
+                             "r_d": self.r_parts[0, t], "r_p": self.r_parts[1, t], "r_j": self.r_parts[2, t],
+                             "state": tr["state"][t + 1], "obs": tr["obs"][t + 1], "avail": tr["avail_actions"][t + 1]})
+        self.t_env += 1
+
+    def reset(self):
+        tr = self.traj
+        self.mac.init_hidden(batch_size=self.n_envs)
+        self.env._reset_device(out={"state": tr["state"][0], "obs": tr["obs"][0], "avail": tr["avail_actions"][0]})
+
+    def run(self, test_mode=False, store=True):
+        self.reset()
+        for t in range(self.episode_limit):
+            self.step(t, test_mode=test_mode)
+        if store and not test_mode and self.buffer is not None:
+            self.buffer.store_rollout(self.traj)
+        tr = self.traj
+        a = tr["actions_discrete"].view(-1).long()
+        counts = torch.bincount(a, minlength=self.args.n_actions)[:self.args.n_actions].float()
+        stats = torch.stack([tr["reward"].sum(0).mean(), tr["reward"].mean(), self.r_parts[0].mean(),
+                             self.r_parts[1].mean(), self.r_parts[2].mean(), tr["actions_continuous"].mean()]).tolist()
+        return {"episode_length": self.episode_limit, "episode_return": stats[0], "avg_step_reward": stats[1],
+                "avg_r_d": stats[2], "avg_r_p": stats[3], "avg_r_j": stats[4], "avg_power_overall": stats[5],
+                "action_distribution": (counts / counts.sum().clamp(min=1)).cpu().numpy(),
+                "n_episodes": self.n_envs}
+
+    def close_env(self):
+        self.env.close()

@@ -120,9 +120,9 @@ class ElectromagneticEnvironment:
             return N.torch_ctx(self.device)
         return N.Ctx(device=0, reserved=0, stream=None)
 
-    def _io(self, act_d=None, act_p=None, noise=None):
+    def _io(self, act_d=None, act_p=None, noise=None, out=None):
         p = N.ptr
-        return N.EnvIO(
+        io = N.EnvIO(
             act_d=p(act_d), act_p=p(act_p), noise=p(noise), seed=self.seed,
             auto_reset=int(self.auto_reset), reserved=0, step_count=p(self.step_count),
             reward=p(self.reward), r_d=p(self.r_d), r_p=p(self.r_p), r_j=p(self.r_j),
@@ -130,15 +130,22 @@ class ElectromagneticEnvironment:
             pd=p(self.pd), detected=p(self.detected), tracking=p(self.tracking),
             snr0=p(self.snr0), snr1=p(self.snr1), jsr_db=p(self.jsr_db), pd_net=p(self.pd_net),
             jam_power=p(self.jam_power), state=p(self.state), obs=p(self.obs), avail=p(self.avail))
+        if out:
+            # redirect selected outputs (e.g. into the slices of a rollout trajectory);
+            # a value of None drops an optional output
+            for k, v in out.items():
+                setattr(io, k, p(v))
+        return io
 
-    def _reset_device(self):
-        self._lib.call("macjd_env_reset", self._ctx(), self._ctab, self._io())
+    def _reset_device(self, out=None):
+        self._lib.call("macjd_env_reset", self._ctx(), self._ctab, self._io(out=out))
 
-    def step_device(self, act_d, act_p, noise=None):
+    def step_device(self, act_d, act_p, noise=None, out=None):
         """Enqueue one step for all envs.  act_d int32 [n,J], act_p float32 [n,J] and
         optional noise float32 [n, R*K+J] must be contiguous tensors on the env device.
-        Results land in the persistent output buffers (self.reward, self.obs, ...)."""
-        self._lib.call("macjd_env_step", self._ctx(), self._ctab, self._io(act_d, act_p, noise))
+        Results land in the persistent output buffers (self.reward, self.obs, ...) unless
+        ``out`` redirects them ({EnvIO field: tensor})."""
+        self._lib.call("macjd_env_step", self._ctx(), self._ctab, self._io(act_d, act_p, noise, out))
 
     # ------------------------------------------------------------------ reference API
     def reset(self):

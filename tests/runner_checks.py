@@ -1,0 +1,130 @@
+"""Runner checks shared by the host-emulation (CPU) and GPU tests."""
+import os
+import tempfile
+import types
+
+import numpy as np
+import torch
+import yaml
+
+from oracle.env_oracle import EnvOracle
+from oracle import agent_oracle as AO
+
+
+def rl_args(device, **kw):
+    base = dict(n_agents=2, n_actions=5, state_shape=24, obs_shape=24, rnn_hidden_dim=64, actor_hidden_dim=64,
+                mixing_embed_dim=32, hyper_hidden_dim=64, epsilon_start=1.0, epsilon_finish=0.05,
+                epsilon_anneal_time=50, gamma=0.99, lr=1e-3, grad_norm_clip=1.0, target_update_interval=2,
+                use_cuda=torch.device(device).type == "cuda", device=device, batch_size=4, buffer_size=16,
+                episode_limit=6, seed=3)
+    base.update(kw)
+    a = types.SimpleNamespace(**base)
+    a.env_info = {"state_shape": a.state_shape, "obs_shape": a.obs_shape, "n_actions": a.n_actions,
+                  "n_agents": a.n_agents, "episode_limit": a.episode_limit}
+    return a
+
+
+def check_batched_rollout_against_oracles(device, lib, n_envs=9):
+    """A full batched rollout with injected env noise and selector draws, replayed step by step
+    through the NumPy env oracle and the eager agent oracle: actions, rewards, stored hidden
+    states and the replay contents must agree."""
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import hetero_spec
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
+    args = rl_args(device)
+    spec = hetero_spec(n_envs, seed=9, active=True, episode_limit=args.episode_limit)
+    env = ElectromagneticEnvironment(args, spec=spec, device=device, _lib=lib)
+    torch.manual_seed(1)
+    mac = BasicMAC(24, args, _lib=lib)
+    if args.use_cuda:
+        mac.cuda()
+    buf = EpisodeReplayBuffer(args, device=device, _lib=lib)
+    runner = BatchedEpisodeRunner(env, mac, buf, args)
+    ora = EnvOracle(spec)
+    sd = {k: v.detach().cpu() for k, v in mac.agent.state_dict().items()}
+    rng = np.random.default_rng(2)
+    T, Nn = args.episode_limit, 2
+    runner.reset()
+    ora.reset()
+    h = torch.zeros(n_envs * Nn, args.rnn_hidden_dim)
+    dev = env.device
+    for t in range(T):
+        noise = rng.random((n_envs, 4)).astype(np.float32)
+        u = rng.random((n_envs, Nn)).astype(np.float32)
+        ra = rng.integers(0, 5, size=(n_envs, Nn))
+        eps = AO.epsilon_at(runner.t_env, 1.0, 0.05, 50)
+        runner.step(t, noise=torch.from_numpy(noise).to(dev), u_eps=torch.from_numpy(u), rand_actions=torch.from_numpy(ra))
+        obs = torch.from_numpy(ora.get_obs())
+        a, p, h, q, _ = AO.select_actions(sd, obs, torch.ones(n_envs, Nn, 5, dtype=torch.long), h, np.float32(eps), False,
+                                          torch.from_numpy(u), torch.from_numpy(ra))
+        mine_a = runner.traj["actions_discrete"][t].cpu().numpy()
+        srt = np.sort(q.numpy(), axis=-1)
+        decidable = ((srt[..., -1] - srt[..., -2]) > 1e-5)[..., None] | (u < np.float32(eps))[..., None]
+        assert decidable.all(), "test inputs should have decidable argmaxes"
+        np.testing.assert_array_equal(mine_a, a.numpy())
+        np.testing.assert_allclose(runner.traj["actions_continuous"][t].cpu().numpy(), p.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(runner.traj["hidden_state"][t].cpu().numpy().reshape(n_envs * Nn, -1), h.numpy(), rtol=1e-4, atol=1e-5)
+        o = ora.step(mine_a.reshape(n_envs, Nn), runner.traj["actions_continuous"][t].cpu().numpy().reshape(n_envs, Nn), noise)
+        np.testing.assert_allclose(runner.traj["reward"][t].cpu().numpy()[:, 0], o["reward"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_array_equal(runner.traj["terminated"][t].cpu().numpy()[:, 0].astype(bool), o["terminated"])
+        h = runner.traj["hidden_state"][t].cpu().reshape(n_envs * Nn, -1).clone()    # stay on the kernel's trajectory
+    buf.store_rollout(runner.traj)
+    got = buf.gather(np.arange(n_envs))
+    for k in ("state", "obs", "reward", "hidden_state", "actions_discrete"):
+        assert torch.equal(got[k].transpose(0, 1), runner.traj[k]), k
+    assert got["max_seq_len"] == T
+    return runner, buf, args
+
+
+def check_training_loop_smoke(device, lib):
+    """act -> store -> sample -> train -> target update on the batched path; finite stats,
+    the Q-head moves, everything else of the agent stays frozen."""
+    from macjd_b200.core.qmix import QMixLearner
+    runner, buf, args = check_batched_rollout_against_oracles(device, lib, n_envs=6)
+    learner = QMixLearner(runner.mac, args, _lib=lib)
+    before = {k: v.detach().cpu().clone() for k, v in runner.mac.agent.state_dict().items()}
+    info = runner.run()
+    assert info["episode_length"] == args.episode_limit and np.isfinite(info["episode_return"])
+    assert abs(info["action_distribution"].sum() - 1) < 1e-6
+    np.random.seed(0)
+    for it in range(3):
+        stats = learner.train(buf.sample(args.batch_size, time_major=(it % 2 == 0)), {})
+        assert all(np.isfinite(v) for v in stats.values()), stats
+    after = runner.mac.agent.state_dict()
+    for k in before:
+        changed = not torch.equal(before[k], after[k].cpu())
+        assert changed == k.startswith("fc2_q_head"), k
+    assert learner.last_target_update_step == 2
+
+
+def check_reference_protocol_runner(device, lib):
+    """EpisodeRunner (one env, host staging) against the shim environment: stored episode has
+    the reference's shapes / dtypes and the zero last slot."""
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import default_config_dict
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    from macjd_b200.runners.episode_runner import EpisodeRunner
+    args = rl_args(device, episode_limit=5)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "simulation_config.yaml")
+        with open(path, "w") as f:
+            yaml.safe_dump(default_config_dict(), f)
+        env = ElectromagneticEnvironment(args, sim_config_path=path, device=device, _lib=lib)
+    mac = BasicMAC(24, args, _lib=lib)
+    if args.use_cuda:
+        mac.cuda()
+    buf = EpisodeReplayBuffer(args, device=device, _lib=lib)
+    runner = EpisodeRunner(env, mac, buf, args)
+    info = runner.run()
+    assert info["episode_length"] == 5 and runner.t_env == 5 and len(buf) == 1
+    assert set(info) >= {"episode_length", "episode_return", "avg_step_reward", "avg_r_d", "avg_r_p", "avg_r_j",
+                         "avg_power_overall", "action_distribution"}
+    ep = buf.gather(np.array([0]))
+    assert ep["max_seq_len"] == 5
+    assert float(ep["state"][0, 5].abs().sum()) == 0.0 and float(ep["hidden_state"][0, 5].abs().sum()) == 0.0
+    assert float(ep["state"][0, 4].abs().sum()) > 0 and bool(ep["filled"].all())
+    assert not bool(ep["terminated"][0, :4].any()) and bool(ep["terminated"][0, 4].all())
+    runner.close_env()

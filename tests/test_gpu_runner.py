@@ -1,0 +1,18 @@
+"""Runners + training loop on the GPU."""
+import pytest
+
+from tests import runner_checks as RC
+
+pytestmark = pytest.mark.gpu
+
+
+def test_batched_rollout_vs_oracles():
+    RC.check_batched_rollout_against_oracles("cuda", None, n_envs=300)
+
+
+def test_training_loop_smoke():
+    RC.check_training_loop_smoke("cuda", None)
+
+
+def test_reference_protocol_runner():
+    RC.check_reference_protocol_runner("cuda", None)
