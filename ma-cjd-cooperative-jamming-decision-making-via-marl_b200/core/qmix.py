@@ -87,7 +87,7 @@ class QMixLearner:
             total = sum(sizes)
             z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
             old = self._opt_state
-            self._opt_state = {"sizes": sizes, "total": total, "grad": z(total + 4), "m": z(total), "v": z(total),
+            self._opt_state = {"sizes": sizes, "total": total, "grad": z(total + 8), "m": z(total), "v": z(total),
                                "step": 0, "scal": z(4),
                                "scratch": z(self.lib().lib.macjd_opt_scratch_floats())}
             if old is not None:
@@ -197,7 +197,8 @@ class QMixLearner:
         # 6. TD targets and masked loss sums (qmix.py:155,191-194)
         opt = self._ensure_opt_state()
         grad, total = opt["grad"], opt["total"]
-        sums = grad[total:total + 4]                       # rides in the all-reduce bucket
+        sums = grad[total:total + 8]                       # rides in the all-reduce bucket
+        sums[4:].fill_(float(R))                           # local row count (ragged shards)
         td_ws = self._workspace("td", L.lib.macjd_td_scratch_floats(R), dev)
         L.callv("macjd_td_loss", ctx, R, q_tot, tq_tot, tb["reward"].view(-1), tb["terminated"].view(-1),
                 tb["filled"].view(-1), float(self.args.gamma), dq_tot, targets, sums, td_ws, td_ws.numel())
@@ -213,11 +214,9 @@ class QMixLearner:
                 grad[o0:], grad[o1:], grad[o2:], grad[o3:], qs, qs.numel())
 
         # 9. data-parallel exchange: gradients + {sum td^2, sum mask, sum q_tot, sum targets}
-        world = 1
         if self.process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                               and getattr(self.args, "data_parallel", False)):
             torch.distributed.all_reduce(grad, group=self.process_group)
-            world = torch.distributed.get_world_size(self.process_group)
 
         # 10. clip + Adam on the Q-head and the mixer (qmix.py:197-200)
         opt["step"] += 1
@@ -242,8 +241,7 @@ class QMixLearner:
             self.last_target_update_step = self.train_step
 
         # 12. stats (qmix.py:209-215)
-        rows_total = float(R * world)
-        stats_dev = torch.stack([opt["scal"][2], opt["scal"][0], sums[2] / rows_total, sums[3] / rows_total])
+        stats_dev = torch.stack([opt["scal"][2], opt["scal"][0], sums[2] / sums[4], sums[3] / sums[4]])
         if lazy_stats:
             stats = {"stats_tensor": stats_dev}
         else:

@@ -33,7 +33,7 @@ def check_batched_rollout_against_oracles(device, lib, n_envs=9):
     from macjd_b200.core.mac import BasicMAC
     from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
     from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
-    args = rl_args(device)
+    args = rl_args(device, buffer_size=max(16, 2 * n_envs))
     spec = hetero_spec(n_envs, seed=9, active=True, episode_limit=args.episode_limit)
     env = ElectromagneticEnvironment(args, spec=spec, device=device, _lib=lib)
     torch.manual_seed(1)
