@@ -179,6 +179,8 @@ def main():
 
     import torch
     import torch.distributed as dist
+    real_stdout = sys.stdout
+    sys.stdout = sys.stderr                     # library chatter must not pollute the one JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -248,11 +250,11 @@ def main():
             runner.reset()
             t_cur[0] = 0
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(W):
         rollout_step(i)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     dt = timed_steps(rollout_step, K, pre=pre_step)
     barrier()
     dt = reduce_max(dt)
@@ -371,7 +373,7 @@ def main():
                            "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
                 "e2e": e2e, "gpu_launches": 2 * K, "roofline": roofline, "roofline_env": roofline_env,
                 "learner": learner_rec, "clocks": clocks, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
