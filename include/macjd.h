@@ -168,7 +168,7 @@ typedef struct macjd_agent_io {
   float* hidden;              /* [M][H] recurrent state, updated in place; may be NULL  */
   int32_t hidden_zero_init;   /* != 0: start from zeros (mac.py:189-198 init_hidden)    */
   int32_t test_mode;          /* != 0: greedy only (action_selectors.py:59-61)          */
-  int32_t tile_rows;          /* rows per CTA: 0 = auto, or 32 / 64 (tuning knob)        */
+  int32_t tile_rows;          /* rows per CTA: 0 = auto, or 8/16/32/64 (tuning knob)     */
   int32_t reserved;
   float* hidden_seq;          /* [T][M][H] h_t after every step, optional               */
   float* q_all;               /* [T][M][A] Q(s, a, P_a) for every action, optional      */

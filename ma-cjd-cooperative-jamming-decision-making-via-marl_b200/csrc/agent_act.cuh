@@ -435,28 +435,39 @@ inline int agent_launch(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
       !w->w1p || !w->w2 || !w->bq2 || !w->ba1 || !w->ba2 || !w->ba3 || !w->bfc1 || !w->brz || !w->bin || !w->bhn || !w->bq1)
     return MACJD_ERR_INVALID_ARG;
   if (io->actions && !io->test_mode && !(io->epsilon >= 0.f)) return MACJD_ERR_INVALID_ARG;
-  if (io->tile_rows != 0 && io->tile_rows != 32 && io->tile_rows != 64) return MACJD_ERR_INVALID_ARG;
+  if (io->tile_rows != 0 && io->tile_rows != 8 && io->tile_rows != 16 && io->tile_rows != 32 && io->tile_rows != 64)
+    return MACJD_ERR_INVALID_ARG;
   if (io->n_rows == 0) return MACJD_OK;
   AgentArgs a;
   a.w = *w;
   a.io = *io;
   const size_t limit = 200 * 1024;
-  // 64-row tiles (256 threads) when they fit in shared memory and still give most SMs a CTA
-  bool big = agent_smem_bytes(*w, 64) <= limit && io->n_rows >= 64 * kNumSMs / 2;
-  if (io->tile_rows == 64) { if (agent_smem_bytes(*w, 64) > limit) return MACJD_ERR_UNSUPPORTED; big = true; }
-  if (io->tile_rows == 32) big = false;
-  if (big) {
-    const size_t smem = agent_smem_bytes(*w, 64);
-    auto k = agent_forward_kernel<256>;
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MACJD_ERR_CUDA;
-    MACJD_LAUNCH(k, (io->n_rows + 63) / 64, 256, smem, (cudaStream_t)ctx->stream, a);
-  } else {
-    const size_t smem = agent_smem_bytes(*w, 32);
-    if (smem > limit) return MACJD_ERR_UNSUPPORTED;
-    auto k = agent_forward_kernel<128>;
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MACJD_ERR_CUDA;
-    MACJD_LAUNCH(k, (io->n_rows + 31) / 32, 128, smem, (cudaStream_t)ctx->stream, a);
+  // Rows per CTA: 64 (256 threads) when that still gives most SMs a CTA, else 32.  The time of
+  // one step of one CTA does not depend on the tile height (every thread always owns a 4x4
+  // tile and walks the same chunk sequence), so smaller tiles (16 / 8 rows, selectable with
+  // tile_rows) only help by occupying more SMs.
+  int tm = io->tile_rows;
+  if (tm == 0) tm = io->n_rows >= 64 * kNumSMs / 2 ? 64 : 32;
+  while (tm > 8 && agent_smem_bytes(*w, tm) > limit) tm >>= 1;
+  const size_t smem = agent_smem_bytes(*w, tm);
+  if (smem > limit) return MACJD_ERR_UNSUPPORTED;
+  if (io->tile_rows != 0 && tm != io->tile_rows) return MACJD_ERR_UNSUPPORTED;
+  const int grid = (io->n_rows + tm - 1) / tm;
+  cudaStream_t st = (cudaStream_t)ctx->stream;
+#define MACJD_AGENT_LAUNCH(NT)                                                                                       \
+  {                                                                                                                  \
+    auto k = agent_forward_kernel<NT>;                                                                               \
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)              \
+      return MACJD_ERR_CUDA;                                                                                         \
+    MACJD_LAUNCH(k, grid, NT, smem, st, a);                                                                          \
   }
+  switch (tm) {
+    case 64: MACJD_AGENT_LAUNCH(256) break;
+    case 32: MACJD_AGENT_LAUNCH(128) break;
+    case 16: MACJD_AGENT_LAUNCH(64) break;
+    default: MACJD_AGENT_LAUNCH(32) break;
+  }
+#undef MACJD_AGENT_LAUNCH
   return MACJD_OK;
 }
 

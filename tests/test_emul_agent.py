@@ -25,5 +25,10 @@ def test_unroll_vs_oracle_64_row_tiles():
     AC.check_unroll_against_oracle("cpu", emul_lib(), O=24, A=5, H=128, AH=64, Nn=2, B=35, T=2, tile_rows=64)
 
 
+@pytest.mark.parametrize("tile", [8, 16])
+def test_unroll_vs_oracle_small_tiles(tile):
+    AC.check_unroll_against_oracle("cpu", emul_lib(), O=24, A=5, H=64, AH=64, Nn=2, B=13, T=2, tile_rows=tile)
+
+
 def test_device_rng_selection():
     AC.check_device_rng_selection("cpu", emul_lib())

@@ -24,6 +24,8 @@ def test_q_params_hidden_vs_reference(name):
     dict(O=24, A=5, H=256, AH=128, Nn=2, B=100, T=3),                 # C4 dims (H=256)
     dict(O=176, A=33, H=128, AH=128, Nn=8, B=37, T=2),                # C3 dims
     dict(O=39, A=7, H=64, AH=192, Nn=3, B=50, T=3),
+    dict(O=24, A=5, H=128, AH=128, Nn=2, B=32, T=4, tile_rows=8),
+    dict(O=24, A=5, H=128, AH=128, Nn=2, B=32, T=4, tile_rows=16),
 ])
 def test_unroll_vs_oracle(cfg):
     AC.check_unroll_against_oracle("cuda", **cfg)
@@ -44,7 +46,7 @@ def test_full_size_properties():
     avail = (torch.rand(1, M, 5, device="cuda", generator=g) < 0.6)
     avail[..., 4] = True
     outs = []
-    for tile in (32, 64, 32):
+    for tile in (32, 64, 16):
         h = h0.clone()
         outs.append(mac.agent.run(obs, h, avail=avail, select=True, test_mode=True, want_q=True, tile_rows=tile))
     for k in ("q_all", "actions", "power", "hidden"):
