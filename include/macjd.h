@@ -302,6 +302,14 @@ MACJD_API int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* ten
                               float* v, const float* sums, float max_norm, float lr, float beta1, float beta2,
                               float eps, int64_t step, float* scal, float* scratch, size_t scratch_floats);
 
+/* ===================================================================== tensor-core self-test
+ * D[M][N] = A[M][K] B[N][K]^T on the tcgen05 TF32 pipe with the 3xTF32 operand split
+ * (csrc/tc05.cuh).  M in {64, 128}, N multiple of 16 <= 256, K multiple of 8.  Exercises the
+ * shared-memory descriptors, TMEM allocation, tcgen05.mma / commit / ld used by the agent
+ * kernel's tensor-core path. */
+MACJD_API int macjd_tc_gemm_selftest(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A,
+                                     const float* B, float* D);
+
 #ifdef __cplusplus
 }
 #endif

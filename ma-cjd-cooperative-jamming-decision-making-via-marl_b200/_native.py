@@ -145,6 +145,7 @@ class NativeLib:
             ("macjd_td_scratch_floats", sz, [i32]),
             ("macjd_td_loss", C.c_int, [P(Ctx), i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, sz]),
             ("macjd_opt_scratch_floats", sz, []),
+            ("macjd_tc_gemm_selftest", C.c_int, [P(Ctx), i32, i32, i32, vp, vp, vp]),
             ("macjd_clip_adam", C.c_int, [P(Ctx), P(OptTensors), vp, vp, vp, vp, f32, f32, f32, f32, f32, i64, vp, vp, sz]),
         ):
             fn = getattr(L, name)

@@ -6,6 +6,7 @@
 #include "agent_act.cuh"
 #include "replay.cuh"
 #include "learner.cuh"
+#include "tc05.cuh"
 
 #include <stdio.h>
 #include <string.h>
@@ -168,6 +169,18 @@ int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, cons
   if (!tensors || !grad || !m || !v || !sums || !scal) return MACJD_ERR_INVALID_ARG;
   return finish(ctx, macjd::clip_adam((cudaStream_t)ctx->stream, *tensors, grad, m, v, sums, max_norm, lr, beta1, beta2,
                                       eps, step, scal, scratch, scratch_floats));
+}
+
+int macjd_tc_gemm_selftest(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
+                           float* D) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+#ifdef MACJD_TEST_HOST_EMULATION
+  (void)M; (void)N; (void)K; (void)A; (void)B; (void)D;
+  return MACJD_ERR_UNSUPPORTED;   // tensor cores cannot be emulated on the host
+#else
+  return finish(ctx, macjd::tc::tc_gemm_selftest(ctx, M, N, K, A, B, D));
+#endif
 }
 
 }  // extern "C"
