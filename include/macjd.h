@@ -159,6 +159,10 @@ typedef struct macjd_agent_weights {
   const float* w1p;       /* [H]    fc2_q_head.0.weight[:, H+A]  (parameter column)    */
   const float* w2;        /* [H]    fc2_q_head.2.weight                                */
   const float* bq2;       /* [1]    fc2_q_head.2.bias                                  */
+  const float* tc_chunks; /* optional: the dense layers again, packed for the tcgen05 path
+                             (csrc/agent_act_tc.cuh): 128 x 16 weight chunks in consumption order,
+                             UMMA K-major layout, TF32 hi part then lo part (16 KB per chunk);
+                             NULL = FP32 SIMT kernel only                              */
 } macjd_agent_weights;
 
 typedef struct macjd_agent_io {
@@ -169,7 +173,8 @@ typedef struct macjd_agent_io {
   int32_t hidden_zero_init;   /* != 0: start from zeros (mac.py:189-198 init_hidden)    */
   int32_t test_mode;          /* != 0: greedy only (action_selectors.py:59-61)          */
   int32_t tile_rows;          /* rows per CTA: 0 = auto, or 8/16/32/64 (tuning knob)     */
-  int32_t reserved;
+  int32_t path;               /* 0 = auto (tensor cores when tc_chunks is given and the dims
+                                 allow), 1 = FP32 SIMT, 2 = tcgen05 3xTF32 (error if unsupported) */
   float* hidden_seq;          /* [T][M][H] h_t after every step, optional               */
   float* q_all;               /* [T][M][A] Q(s, a, P_a) for every action, optional      */
   float* params_all;          /* [T][M][A] actor outputs P_a, optional                  */

@@ -44,12 +44,12 @@ class AgentWeights(C.Structure):
     _fields_ = [("obs_dim", c_int32), ("obs_pad", c_int32), ("hidden", c_int32), ("actor_hidden", c_int32),
                 ("n_actions", c_int32), ("reserved", c_int32)] + [
         (n, c_void_p) for n in ("wa1t", "ba1", "wa2t", "ba2", "wa3t", "ba3", "wfc1t", "bfc1", "wrzt", "brz",
-                                "wint", "bin", "whnt", "bhn", "wqt", "bq1", "w1a", "w1p", "w2", "bq2")]
+                                "wint", "bin", "whnt", "bhn", "wqt", "bq1", "w1a", "w1p", "w2", "bq2", "tc_chunks")]
 
 
 class AgentIO(C.Structure):
     _fields_ = [("n_rows", c_int32), ("n_steps", c_int32), ("obs", c_void_p), ("hidden", c_void_p),
-                ("hidden_zero_init", c_int32), ("test_mode", c_int32), ("tile_rows", c_int32), ("reserved", c_int32),
+                ("hidden_zero_init", c_int32), ("test_mode", c_int32), ("tile_rows", c_int32), ("path", c_int32),
                 ("hidden_seq", c_void_p), ("q_all", c_void_p), ("params_all", c_void_p), ("greedy", c_void_p),
                 ("sel_actions", c_void_p), ("q_sel", c_void_p), ("avail", c_void_p), ("u_eps", c_void_p),
                 ("rand_actions", c_void_p), ("epsilon", c_float), ("rng_step", C.c_uint32), ("seed", c_uint64),

@@ -48,6 +48,9 @@ class PackedAgentWeights:
         self.size = off
         self.buffer = None
         self.versions = None
+        # tensor-core copy (csrc/agent_act_tc.cuh): reference width only
+        self.tc_ok = (self.H == 128 and self.AH == 128)
+        self.tc_buffer = None
 
     def view(self, f):
         n = int(np.prod(self.shapes[f]))
@@ -89,14 +92,49 @@ class PackedAgentWeights:
         self.view("w1p").copy_(w1[:, H + A])
         self.view("w2").copy_(sd["fc2_q_head.2.weight"].reshape(-1))
         self.view("bq2").copy_(sd["fc2_q_head.2.bias"])
+        if self.tc_ok and dev.type == "cuda":
+            self._pack_tc(sd)
         self.versions = versions
         return self
+
+    @staticmethod
+    def _umma_chunks(w, kc=16):
+        """[128, K] (out, in) -> [K / kc] chunks in the K-major no-swizzle UMMA layout
+        (8 x 16-byte core matrices: n/8, k/4, n%8, k%4), each followed by nothing (hi / lo are
+        interleaved by the caller)."""
+        n, K = w.shape
+        x = w.reshape(n // 8, 8, K // kc, kc // 4, 4)          # n/8, n%8, chunk, k/4, k%4
+        return x.permute(2, 0, 3, 1, 4).contiguous().reshape(K // kc, n * kc)
+
+    def _pack_tc(self, sd):
+        """Weight chunks in the order agent_forward_tc_kernel consumes them; TF32 hi part
+        (low 13 mantissa bits cleared) followed by the lo remainder, per chunk."""
+        O, Op, H, A = self.O, self.Op, self.H, self.A
+        dev = sd["fc1.weight"].device
+        pad = lambda w: torch.cat([w, torch.zeros(w.shape[0], Op - O, device=dev)], dim=1)
+        wih, whh = sd["rnn.weight_ih"], sd["rnn.weight_hh"]
+        ca1, cfc1 = self._umma_chunks(pad(sd["actor.0.weight"])), self._umma_chunks(pad(sd["fc1.weight"]))
+        seq = []
+        for i in range(Op // 16):
+            seq += [ca1[i:i + 1], cfc1[i:i + 1]]
+        seq.append(self._umma_chunks(sd["actor.2.weight"]))
+        for g in range(2):                                      # r, z: W_i{g} on xf then W_h{g} on h
+            seq.append(self._umma_chunks(wih[g * H:(g + 1) * H]))
+            seq.append(self._umma_chunks(whh[g * H:(g + 1) * H]))
+        seq.append(self._umma_chunks(wih[2 * H:]))              # W_in on xf
+        seq.append(self._umma_chunks(whh[2 * H:]))              # W_hn on h
+        seq.append(self._umma_chunks(sd["fc2_q_head.0.weight"][:, :H]))
+        full = torch.cat(seq, dim=0).contiguous()               # [n_chunks, 128 * 16]
+        hi = (full.view(torch.int32) & -8192).view(torch.float32)
+        lo = full - hi
+        self.tc_buffer = torch.stack([hi, lo], dim=1).contiguous()   # [n_chunks, 2, 2048]
 
     def cstruct(self):
         base = self.buffer.data_ptr()
         kw = {f: base + 4 * self.offsets[f] for f in self.FIELDS}
+        tc = self.tc_buffer.data_ptr() if self.tc_buffer is not None else None
         return N.AgentWeights(obs_dim=self.O, obs_pad=self.Op, hidden=self.H, actor_hidden=self.AH,
-                              n_actions=self.A, reserved=0, **kw)
+                              n_actions=self.A, reserved=0, tc_chunks=tc, **kw)
 
 
 class RNNAgent(nn.Module):
@@ -122,6 +160,8 @@ class RNNAgent(nn.Module):
             nn.Linear(self.rnn_hidden_dim, 1))
         self._packed = PackedAgentWeights(self)
         self._lib = _lib
+        # kernel path: 0 = auto (tcgen05 3xTF32 when the dims allow), 1 = FP32 SIMT, 2 = tcgen05 only
+        self.path = int(getattr(args, "agent_kernel_path", 0))
 
     # ---- native plumbing
     def lib(self):
@@ -141,7 +181,7 @@ class RNNAgent(nn.Module):
     @torch.no_grad()
     def run(self, obs, hidden=None, *, n_steps=1, zero_init=False, avail=None, epsilon=0.0, test_mode=True,
             u_eps=None, rand_actions=None, seed=0, rng_step=0, select=False, want_q=False, want_params=False,
-            want_greedy=False, sel_actions=None, want_hidden_seq=False, tile_rows=0, out=None):
+            want_greedy=False, sel_actions=None, want_hidden_seq=False, tile_rows=0, out=None, path=None):
         """One fused launch.  obs float32 [T, M, O] (or [M, O]); hidden float32 [M, H] updated in
         place.  Returns a dict with the requested outputs."""
         dev = self.fc1.weight.device
@@ -195,7 +235,7 @@ class RNNAgent(nn.Module):
         p = N.ptr
         io = N.AgentIO(
             n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden),
-            hidden_zero_init=int(zero_init), test_mode=int(test_mode), tile_rows=int(tile_rows), reserved=0,
+            hidden_zero_init=int(zero_init), test_mode=int(test_mode), tile_rows=int(tile_rows), path=int(self.path if path is None else path),
             hidden_seq=p(out.get("hidden_seq")), q_all=p(out.get("q_all")), params_all=p(out.get("params_all")),
             greedy=p(out.get("greedy")), sel_actions=p(sel_actions), q_sel=p(out.get("q_sel")),
             avail=p(avail), u_eps=p(u_eps), rand_actions=p(rand_actions), epsilon=float(epsilon),

@@ -4,6 +4,7 @@
 #include "macjd_common.cuh"
 #include "env_step.cuh"
 #include "agent_act.cuh"
+#include "agent_act_tc.cuh"
 #include "replay.cuh"
 #include "learner.cuh"
 #include "tc05.cuh"
@@ -86,6 +87,19 @@ int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab, const mac
 int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io) {
   int st = enter(ctx);
   if (st != MACJD_OK) return st;
+  if (!w || !io) return MACJD_ERR_INVALID_ARG;
+  if (io->path < 0 || io->path > 2) return MACJD_ERR_INVALID_ARG;
+#ifndef MACJD_TEST_HOST_EMULATION
+  if (io->path != 1 && macjd::tc::agent_tc_supported(*w)) {
+    if (io->n_rows < 0 || io->n_steps < 1 || !io->obs) return MACJD_ERR_INVALID_ARG;
+    if (io->n_rows == 0) return MACJD_OK;
+    macjd::AgentArgs a;
+    a.w = *w;
+    a.io = *io;
+    return finish(ctx, macjd::tc::agent_tc_launch(ctx, a));
+  }
+#endif
+  if (io->path == 2) return MACJD_ERR_UNSUPPORTED;
   return finish(ctx, macjd::agent_launch(ctx, w, io));
 }
 

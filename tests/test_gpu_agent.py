@@ -48,10 +48,38 @@ def test_full_size_properties():
     outs = []
     for tile in (32, 64, 16):
         h = h0.clone()
-        outs.append(mac.agent.run(obs, h, avail=avail, select=True, test_mode=True, want_q=True, tile_rows=tile))
+        outs.append(mac.agent.run(obs, h, avail=avail, select=True, test_mode=True, want_q=True, tile_rows=tile, path=1))
     for k in ("q_all", "actions", "power", "hidden"):
         assert torch.equal(outs[0][k], outs[1][k]) and torch.equal(outs[0][k], outs[2][k]), k
     chosen = outs[0]["actions"][0].long()
     assert bool(avail[0].gather(1, chosen[:, None]).all())
     q = outs[0]["q_all"][0].masked_fill(~avail[0], -float("inf"))
     assert torch.equal(q.argmax(1), chosen)
+
+
+@pytest.mark.parametrize("M,T", [(8192, 1), (100, 3), (64, 5)])
+def test_tensor_core_path_matches_simt_path(M, T):
+    """tcgen05 3xTF32 kernel against the FP32 SIMT kernel on the same inputs: Q, P, hidden within
+    FP32 rounding noise; chosen actions identical wherever the SIMT Q margin is decidable."""
+    mac, args = AC.random_agent(7, 24, 5, 128, 128, 2, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    obs = torch.randn(T, M, 24, device="cuda", generator=g) * 5
+    h0 = torch.randn(M, 128, device="cuda", generator=g) * 0.5
+    avail = torch.rand(T, M, 5, device="cuda", generator=g) < 0.7
+    avail[..., 0] = True
+    res = {}
+    for path in (1, 2):
+        h = h0.clone()
+        res[path] = mac.agent.run(obs, h, n_steps=T, avail=avail, select=True, test_mode=True, want_q=True,
+                                  want_params=True, want_greedy=True, want_hidden_seq=True, path=path)
+    a, b = res[1], res[2]
+    torch.testing.assert_close(b["params_all"], a["params_all"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(b["hidden_seq"], a["hidden_seq"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(b["q_all"], a["q_all"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(b["hidden"], a["hidden"], rtol=1e-4, atol=2e-5)
+    q = a["q_all"].masked_fill(~avail, -float("inf"))
+    top2 = q.topk(2, dim=-1).values
+    decidable = (top2[..., 0] - top2[..., 1]) > 1e-4
+    assert decidable.float().mean() > 0.9
+    assert torch.equal(a["actions"][decidable], b["actions"][decidable])
+    torch.testing.assert_close(b["power"][decidable], a["power"][decidable], rtol=1e-5, atol=1e-6)
