@@ -160,8 +160,9 @@ class RNNAgent(nn.Module):
             nn.Linear(self.rnn_hidden_dim, 1))
         self._packed = PackedAgentWeights(self)
         self._lib = _lib
-        # kernel path: 0 = auto (tcgen05 3xTF32 when the dims allow), 1 = FP32 SIMT, 2 = tcgen05 only
-        self.path = int(getattr(args, "agent_kernel_path", 0))
+        # kernel path: 1 = FP32 SIMT (default: the parity-exact path), 2 = tcgen05 3xTF32 (needs
+        # hidden = actor_hidden = 128), 0 = let the library pick the tensor-core path when it can
+        self.path = int(getattr(args, "agent_kernel_path", 1))
 
     # ---- native plumbing
     def lib(self):

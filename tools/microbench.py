@@ -71,14 +71,14 @@ def bench_agent(out):
         flop = 2 * (Op * AH + AH * AH + AH * A + Op * H + 6 * H * H + H * H) + A * H * 5
         obs = torch.randn(T, M, O, device="cuda")
         h = torch.zeros(M, H, device="cuda")
-        for tile in (32, 64):
+        for tile, path in ((32, 1), (64, 1), (0, 2)):
             try:
-                fn = lambda: mac.agent.run(obs, h, n_steps=T, select=True, test_mode=True, tile_rows=tile)
+                fn = lambda: mac.agent.run(obs, h, n_steps=T, select=True, test_mode=True, tile_rows=tile, path=path)
                 med, best = timeit(fn, iters=8, warmup=2)
-            except Exception as e:  # tile does not fit
-                print(c["tag"], tile, "skipped:", e)
+            except Exception as e:  # tile does not fit / path unsupported
+                print(c["tag"], tile, path, "skipped:", e)
                 continue
-            rec = dict(kernel="agent_forward", tag=c["tag"], M=M, T=T, tile=tile, us=med * 1e6, us_best=best * 1e6,
+            rec = dict(kernel="agent_forward", tag=c["tag"], M=M, T=T, tile=tile, path={1: "simt", 2: "tcgen05"}[path], us=med * 1e6, us_best=best * 1e6,
                        agent_steps_per_s=M * T / med, tflops=M * T * flop / med / 1e12, flop_per_row=flop)
             out.append(rec)
             print(json.dumps(rec), flush=True)
