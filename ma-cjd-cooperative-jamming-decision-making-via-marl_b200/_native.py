@@ -11,7 +11,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmacjd_b200.so")
+LIB_PATH = os.environ.get("MACJD_LIB_PATH", os.path.join(_HERE, "csrc", "libmacjd_b200.so"))   # override: profiling builds
 
 c_void_p, c_int32, c_int64, c_uint64, c_double, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_float
 

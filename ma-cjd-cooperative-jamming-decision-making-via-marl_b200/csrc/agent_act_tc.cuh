@@ -12,10 +12,13 @@
 //              actor head / the per-action Q tail entirely in registers, and writes the next
 //              layer's A operand (hi and lo TF32 parts) to shared memory in UMMA layout.
 //   warp 4     lane 0 streams the packed weight chunks (128 x 16, hi + lo = 16 KB) from L2 with
-//              1-D bulk async copies into a 4-stage ring and issues the tcgen05.mma's; mbarriers
-//              carry weights-landed / stage-free / accumulator-ready / operand-ready events.
-// TMEM (512 columns): actor.0 -> [0,128), fc1 -> [128,256), actor.2 -> [256,384);
-// GRU r | z | W_in xf | W_hn h -> [0,512); Q-head pre-activation -> [0,128).
+//              1-D bulk async copies into a 4-stage ring.
+//   warp 5     lane 0 issues the tcgen05.mma's (every 128-wide layer as two N = 64 halves, the
+//              second on TMEM lanes +16, so both half-warps of an epilogue warp own half a row).
+//   mbarriers carry weights-landed / stage-free / accumulator-ready / operand-ready events.
+// Measured on B200 (tools/tc_mma_rate.py): one M x N x 8 TF32 SS MMA costs ~52 / 69 / 133 cycles
+// for N = 64 / 128 / 256 regardless of M in {64, 128}; a single thread that both waits on
+// barriers and issues copies needs ~800 cycles per chunk, hence the separate stream warp.
 #pragma once
 #include "agent_act.cuh"
 #include "tc05.cuh"
@@ -30,7 +33,11 @@ constexpr int kTcKc = 16;            // k per weight chunk
 constexpr int kTcStages = 4;
 constexpr int kTcChunkFloats = 2 * kTcH * kTcKc;          // hi + lo
 constexpr int kTcChunkBytes = kTcChunkFloats * 4;         // 16 KB
-constexpr int kTcThreads = 160;
+constexpr int kTcThreads = 192;       // 4 epilogue warps + weight-stream warp + MMA warp
+#ifndef MACJD_TC_PIECES
+#define MACJD_TC_PIECES 4
+#endif
+constexpr int kTcPieces = MACJD_TC_PIECES;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
@@ -55,15 +62,43 @@ __device__ __forceinline__ void store_split4(float* hi, float* lo, int r, int k,
   *reinterpret_cast<float4*>(lo + off) = l;
 }
 
+// Optional phase timestamps of CTA 0 (compile with -DMACJD_TC_PROFILE; tools/tc_phase_profile.py)
+#ifdef MACJD_TC_PROFILE
+__device__ unsigned long long g_tc_prof[64];
+#define TC_STAMP(slot) do { if (blockIdx.x == 0 && t == 1) g_tc_prof[slot] = clock64(); } while (0)
+#else
+#define TC_STAMP(slot) do { } while (0)
+#endif
+
+// Small per-layer vectors, staged once per CTA, packed so that one 16-byte shared-memory load
+// (a warp-wide broadcast) brings everything an epilogue needs for one hidden unit.
+struct TcConst {
+  float4 gate_b[kTcH];      // (b_r, b_z, b_in, b_hn) per hidden unit
+  float4 q_c[kTcH];         // (fc2_q_head.0.bias, W1[:, H+A], fc2_q_head.2.weight, 0) per unit
+  float ba1[kTcH], ba2[kTcH], bfc1[kTcH];
+  float4 wa3t[kTcH * 2];    // [unit][8 actions]  actor.4.weight^T, zero padded
+  float4 w1a[kTcH * 2];     // [unit][8 actions]  fc2_q_head.0.weight[:, H + a]
+  float ba3[8];
+};
+
 struct TcSmem {
   float xhi[kTcRows * 32], xlo[kTcRows * 32];           // observation chunk (32 k)
   float b0hi[kTcRows * kTcH], b0lo[kTcRows * kTcH];     // a1 -> xf
   float hhi[kTcRows * kTcH], hlo[kTcRows * kTcH];       // h -> h'
   float wst[kTcStages][kTcChunkFloats];                 // weight ring
+  TcConst c;
   uint64_t w_full[kTcStages], w_empty[kTcStages];
   uint64_t x_full, x_empty, d_ready, a_ready;
   uint32_t tmem_base;
 };
+
+// TMEM columns.  Every 128-wide accumulator is issued as two N = 64 MMAs: output units 0-63 on
+// the lower 16 lanes of each 32-lane quarter, units 64-127 on the upper 16 lanes (lane offset
+// 16), same columns -- so both half-warps of an epilogue warp own half a row each.
+constexpr uint32_t kColA1 = 0, kColFc1 = 64, kColA2 = 128;          // actor.0, fc1, actor.2
+constexpr uint32_t kColR = 0, kColZ = 64, kColIn = 128, kColHn = 192;   // GRU
+constexpr uint32_t kColQ = 0;
+constexpr uint32_t kTmemCols = 256;
 
 __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const AgentArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
@@ -81,53 +116,75 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
   const int nxc = Op / 32;
   const int chunks_per_step = 4 * nxc + 8 + 48 + 8;
 
-  if (warp == 4) tmem_alloc(&S.tmem_base, 512);
+  if (warp == 5) tmem_alloc(&S.tmem_base, kTmemCols);
   if (tid == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
     mbar_init(&S.x_full, 128); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 128);
     fence_mbar_init();
   }
+  // stage the small vectors
+  for (int i = tid; i < H; i += kTcThreads) {
+    S.c.gate_b[i] = make_float4(W.brz[i], W.brz[H + i], W.bin[i], W.bhn[i]);
+    S.c.q_c[i] = make_float4(W.bq1[i], W.w1p[i], W.w2[i], 0.f);
+    S.c.ba1[i] = W.ba1[i]; S.c.ba2[i] = W.ba2[i]; S.c.bfc1[i] = W.bfc1[i];
+    float w3[8], wq[8];
+    for (int j = 0; j < 8; ++j) {
+      w3[j] = j < A ? W.wa3t[(size_t)i * A + j] : 0.f;
+      wq[j] = j < A ? W.w1a[(size_t)j * H + i] : 0.f;
+    }
+    S.c.wa3t[2 * i] = make_float4(w3[0], w3[1], w3[2], w3[3]);
+    S.c.wa3t[2 * i + 1] = make_float4(w3[4], w3[5], w3[6], w3[7]);
+    S.c.w1a[2 * i] = make_float4(wq[0], wq[1], wq[2], wq[3]);
+    S.c.w1a[2 * i + 1] = make_float4(wq[4], wq[5], wq[6], wq[7]);
+  }
+  if (tid < 8) S.c.ba3[tid] = tid < A ? W.ba3[tid] : 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = S.tmem_base;
 
   if (warp == 4) {
-    // =========================================================== weight stream + MMA issue
+    // =========================================================== weight stream (bulk async copies)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kTcRows, H);
       const char* wsrc = reinterpret_cast<const char*>(W.tc_chunks);
       const long long total_chunks = (long long)chunks_per_step * T;
-      long long next_load = 0, cur = 0;
-      uint32_t full_par = 0, empty_par = 0;       // bit s = parity to wait for on stage s
+      uint32_t empty_par = 0;                     // bit s = parity to wait for on stage s
+      for (long long L = 0; L < total_chunks; ++L) {
+        const int s = (int)(L % kTcStages);
+        if (L >= kTcStages) { mbar_wait(&S.w_empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
+        mbar_expect_tx(&S.w_full[s], kTcChunkBytes);
+        bulk_g2s(S.wst[s], wsrc + (size_t)(L % chunks_per_step) * kTcChunkBytes, kTcChunkBytes, &S.w_full[s]);
+      }
+    }
+  } else if (warp == 5) {
+    // =========================================================== MMA issue
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kTcRows, 64);
+      long long cur = 0;
+      uint32_t full_par = 0;
       uint32_t x_full_par = 0, a_ready_par = 0;
-      auto pump = [&]() {                         // keep up to kTcStages chunks in flight
-        while (next_load < total_chunks && next_load < cur + kTcStages) {
-          const int s = (int)(next_load % kTcStages);
-          if (next_load >= kTcStages) { mbar_wait(&S.w_empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
-          mbar_expect_tx(&S.w_full[s], kTcChunkBytes);
-          bulk_g2s(S.wst[s], wsrc + (size_t)(next_load % chunks_per_step) * kTcChunkBytes, kTcChunkBytes, &S.w_full[s]);
-          ++next_load;
-        }
-      };
-      // one chunk: 2 k-steps x 3 split products into TMEM column `dcol`
+      // one chunk (16 k): 2 k-steps x 2 unit halves x 3 split products into TMEM column `dcol`
       auto mma_chunk = [&](const float* ahi, const float* alo, uint32_t a_sbo, uint32_t a_koff_bytes, uint32_t dcol,
                            bool first) {
-        pump();
         const int s = (int)(cur % kTcStages);
         mbar_wait(&S.w_full[s], (full_par >> s) & 1u);
         full_par ^= 1u << s;
         fence_after_sync();
         const uint64_t dah = umma_smem_desc(smem_u32(ahi) + a_koff_bytes, 128, a_sbo);
         const uint64_t dal = umma_smem_desc(smem_u32(alo) + a_koff_bytes, 128, a_sbo);
-        const uint64_t dbh = umma_smem_desc(smem_u32(S.wst[s]), 128, kTcKc * 32);
-        const uint64_t dbl = umma_smem_desc(smem_u32(S.wst[s]) + kTcH * kTcKc * 4, 128, kTcKc * 32);
+        const uint32_t wbase = smem_u32(S.wst[s]);
 #pragma unroll
-        for (int ks = 0; ks < kTcKc / 8; ++ks) {
-          const uint64_t adv = (uint64_t)((ks * 256) >> 4);
-          mma_tf32_ss(tmem + dcol, dah + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
-          mma_tf32_ss(tmem + dcol, dal + adv, dbh + adv, idesc, 1u);
-          mma_tf32_ss(tmem + dcol, dah + adv, dbl + adv, idesc, 1u);
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t dbh = umma_smem_desc(wbase + half * 4096, 128, kTcKc * 32);
+          const uint64_t dbl = umma_smem_desc(wbase + kTcH * kTcKc * 4 + half * 4096, 128, kTcKc * 32);
+          const uint32_t d = tmem + ((uint32_t)(half * 16) << 16) + dcol;
+#pragma unroll
+          for (int ks = 0; ks < kTcKc / 8; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 256) >> 4);
+            mma_tf32_ss(d, dah + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
+            mma_tf32_ss(d, dal + adv, dbh + adv, idesc, 1u);
+            mma_tf32_ss(d, dah + adv, dbl + adv, idesc, 1u);
+          }
         }
         mma_commit(&S.w_empty[s]);
         ++cur;
@@ -136,44 +193,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
         // actor.0 and fc1 share the observation operand
         for (int xc = 0; xc < nxc; ++xc) {
           mbar_wait(&S.x_full, x_full_par); x_full_par ^= 1u;
+          TC_STAMP(32);
           for (int hf = 0; hf < 2; ++hf) {
-            mma_chunk(S.xhi, S.xlo, 32 * 32, hf * 512, 0, xc == 0 && hf == 0);
-            mma_chunk(S.xhi, S.xlo, 32 * 32, hf * 512, 128, xc == 0 && hf == 0);
+            mma_chunk(S.xhi, S.xlo, 32 * 32, hf * 512, kColA1, xc == 0 && hf == 0);
+            mma_chunk(S.xhi, S.xlo, 32 * 32, hf * 512, kColFc1, xc == 0 && hf == 0);
           }
           mma_commit(&S.x_empty);
         }
         mma_commit(&S.d_ready);
+        TC_STAMP(33);
         // actor.2 on a1
         mbar_wait(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
-        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, 256, kc == 0);
+        TC_STAMP(34);
+        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, kColA2, kc == 0);
         mma_commit(&S.d_ready);
+        TC_STAMP(35);
         // GRU on xf (B0) and h
         mbar_wait(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
+        TC_STAMP(36);
         for (int g = 0; g < 2; ++g) {
-          for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, g * 128, kc == 0);
-          for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, g * 128, false);
+          for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, g == 0 ? kColR : kColZ, kc == 0);
+          for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, g == 0 ? kColR : kColZ, false);
         }
-        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, 256, kc == 0);
-        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, 384, kc == 0);
+        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, kColIn, kc == 0);
+        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, kColHn, kc == 0);
         mma_commit(&S.d_ready);
+        TC_STAMP(37);
         // Q-head on h'
         mbar_wait(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
-        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, 0, kc == 0);
+        TC_STAMP(38);
+        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, kColQ, kc == 0);
         mma_commit(&S.d_ready);
+        TC_STAMP(39);
       }
     }
   } else {
     // =========================================================== epilogue warps
-    const int r = warp * 16 + lane;                  // row within the tile (lanes < 16)
-    const bool has_row = lane < 16;
-    const bool live = has_row && r < valid;
+    const int half = lane >> 4;                      // which 64 output units of the row
+    const int r = warp * 16 + (lane & 15);           // row within the tile
+    const int ub = half * 64;                        // first unit owned by this thread
+    const bool live = r < valid;
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lane quarter
     uint32_t d_par = 0, x_empty_par = 0;
 
-    // recurrent state -> hi / lo operand tiles
-    if (has_row) {
+    // recurrent state -> hi / lo operand tiles (each thread: its half of the row)
+    {
       const bool have = io.hidden && !io.hidden_zero_init && live;
-      for (int k = 0; k < H; k += 4) {
+      for (int k = ub; k < ub + 64; k += 4) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (have) {
           const float4 x = *reinterpret_cast<const float4*>(io.hidden + (size_t)(row0 + r) * H + k);
@@ -185,117 +251,134 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
 
     for (int t = 0; t < T; ++t) {
       const size_t tM = (size_t)t * M;
-      // ---- observation chunks
+#ifdef MACJD_TC_PROFILE
+#define EP_STAMP(slot) do { if (tid == 0) TC_STAMP(slot); } while (0)
+#else
+#define EP_STAMP(slot) do { } while (0)
+#endif
+      EP_STAMP(0);
+      // ---- observation chunks (32 k): 16 k per half-warp thread
       for (int xc = 0; xc < nxc; ++xc) {
         if (t > 0 || xc > 0) { mbar_wait(&S.x_empty, x_empty_par); x_empty_par ^= 1u; }
-        if (has_row) {
-          const float* obs = io.obs + (tM + row0 + r) * O;
-          for (int k = 0; k < 32; k += 4) {
-            float v[4];
+        const float* obs = io.obs + (tM + row0 + r) * O;
+        for (int k = half * 16; k < half * 16 + 16; k += 4) {
+          float v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { const int kk = xc * 32 + k + j; v[j] = (live && kk < O) ? __ldg(obs + kk) : 0.f; }
-            store_split4(S.xhi, S.xlo, r, k, 32, v);
-          }
+          for (int j = 0; j < 4; ++j) { const int kk = xc * 32 + k + j; v[j] = (live && kk < O) ? __ldg(obs + kk) : 0.f; }
+          store_split4(S.xhi, S.xlo, r, k, 32, v);
         }
         fence_async_smem();
         fence_before_sync();
         mbar_arrive(&S.x_full);
       }
 
+      EP_STAMP(1);
       // ---- E1: a1 = relu(D1 + b) -> B0
       mbar_wait(&S.d_ready, d_par); d_par ^= 1u;
       fence_after_sync();
-      for (int c0 = 0; c0 < H; c0 += 8) {
-        float v[8];
-        tmem_ld8(tl + (uint32_t)c0, v);
-        if (has_row) {
+      EP_STAMP(2);
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16_nowait(tl + kColA1 + (uint32_t)c0, v);
+        tmem_ld_wait();
+        reg_fence(v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
           float o[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[j] + __ldg(W.ba1 + c0 + j), 0.f);
-          store_split4(S.b0hi, S.b0lo, r, c0, H, o);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 + j] + __ldg(W.ba1 + c0 + 4 + j), 0.f);
-          store_split4(S.b0hi, S.b0lo, r, c0 + 4, H, o);
+          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * q + j] + S.c.ba1[ub + c0 + 4 * q + j], 0.f);
+          store_split4(S.b0hi, S.b0lo, r, ub + c0 + 4 * q, H, o);
         }
       }
       fence_async_smem();
       fence_before_sync();
       mbar_arrive(&S.a_ready);
 
+      EP_STAMP(3);
       // ---- E2: actor head P = sigmoid(relu(D2 + b) W_a3 + b3);  E3: xf = relu(D3 + b) -> B0
       mbar_wait(&S.d_ready, d_par); d_par ^= 1u;
       fence_after_sync();
-      for (int a0 = 0; a0 < A; a0 += 8) {
+      EP_STAMP(4);
+      {
         float acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = (a0 + j < A) ? __ldg(W.ba3 + a0 + j) : 0.f;
-        for (int c0 = 0; c0 < H; c0 += 8) {
-          float v[8];
-          tmem_ld8(tl + 256u + (uint32_t)c0, v);
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+          tmem_ld16_nowait(tl + kColA2 + (uint32_t)c0, v);
+          tmem_ld_wait();
+          reg_fence(v);
 #pragma unroll
-          for (int n = 0; n < 8; ++n) {
-            const float a2 = fmaxf(v[n] + __ldg(W.ba2 + c0 + n), 0.f);
-            const float* w3 = W.wa3t + (size_t)(c0 + n) * A + a0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (a0 + j < A) acc[j] = fmaf(a2, __ldg(w3 + j), acc[j]);
+          for (int n = 0; n < 16; ++n) {
+            const int u = ub + c0 + n;
+            const float a2 = fmaxf(v[n] + S.c.ba2[u], 0.f);
+            const float4 wl = S.c.wa3t[2 * u], wh = S.c.wa3t[2 * u + 1];
+            acc[0] = fmaf(a2, wl.x, acc[0]); acc[1] = fmaf(a2, wl.y, acc[1]);
+            acc[2] = fmaf(a2, wl.z, acc[2]); acc[3] = fmaf(a2, wl.w, acc[3]);
+            acc[4] = fmaf(a2, wh.x, acc[4]); acc[5] = fmaf(a2, wh.y, acc[5]);
+            acc[6] = fmaf(a2, wh.z, acc[6]); acc[7] = fmaf(a2, wh.w, acc[7]);
           }
         }
-        if (has_row)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (a0 + j < A) Ps[(a0 + j) * kTcRows + r] = sigmoid_f(acc[j]);
+        for (int j = 0; j < 8; ++j) {
+          const float tot = acc[j] + __shfl_xor_sync(0xffffffffu, acc[j], 16);
+          if (half == 0 && j < A) Ps[j * kTcRows + r] = sigmoid_fast(tot + S.c.ba3[j]);
+        }
       }
-      for (int c0 = 0; c0 < H; c0 += 8) {
-        float v[8];
-        tmem_ld8(tl + 128u + (uint32_t)c0, v);
-        if (has_row) {
+      EP_STAMP(5);
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16_nowait(tl + kColFc1 + (uint32_t)c0, v);
+        tmem_ld_wait();
+        reg_fence(v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
           float o[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[j] + __ldg(W.bfc1 + c0 + j), 0.f);
-          store_split4(S.b0hi, S.b0lo, r, c0, H, o);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 + j] + __ldg(W.bfc1 + c0 + 4 + j), 0.f);
-          store_split4(S.b0hi, S.b0lo, r, c0 + 4, H, o);
+          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * q + j] + S.c.bfc1[ub + c0 + 4 * q + j], 0.f);
+          store_split4(S.b0hi, S.b0lo, r, ub + c0 + 4 * q, H, o);
         }
       }
       fence_async_smem();
       fence_before_sync();
       mbar_arrive(&S.a_ready);
 
+      EP_STAMP(6);
       // ---- E4: GRU gates -> h' (in place over h), global hidden outputs
       mbar_wait(&S.d_ready, d_par); d_par ^= 1u;
       fence_after_sync();
-      for (int c0 = 0; c0 < H; c0 += 8) {
+      EP_STAMP(7);
+      for (int c0 = 0; c0 < 64; c0 += 8) {
         float vr[8], vz[8], vi[8], vh[8];
-        tmem_ld8(tl + (uint32_t)c0, vr);
-        tmem_ld8(tl + 128u + (uint32_t)c0, vz);
-        tmem_ld8(tl + 256u + (uint32_t)c0, vi);
-        tmem_ld8(tl + 384u + (uint32_t)c0, vh);
-        if (has_row) {
+        tmem_ld8_nowait(tl + kColR + (uint32_t)c0, vr);
+        tmem_ld8_nowait(tl + kColZ + (uint32_t)c0, vz);
+        tmem_ld8_nowait(tl + kColIn + (uint32_t)c0, vi);
+        tmem_ld8_nowait(tl + kColHn + (uint32_t)c0, vh);
+        tmem_ld_wait();
+        reg_fence(vr); reg_fence(vz); reg_fence(vi); reg_fence(vh);
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int c = c0 + 4 * q;
-            const uint32_t off = umma_off_bytes(r, c, H) >> 2;
-            const float4 hh = *reinterpret_cast<const float4*>(S.hhi + off);
-            const float4 hl = *reinterpret_cast<const float4*>(S.hlo + off);
-            const float hold[4] = {hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w};
-            float o[4];
+        for (int q = 0; q < 2; ++q) {
+          const int c = ub + c0 + 4 * q;
+          const uint32_t off = umma_off_bytes(r, c, H) >> 2;
+          const float4 hh = *reinterpret_cast<const float4*>(S.hhi + off);
+          const float4 hl = *reinterpret_cast<const float4*>(S.hlo + off);
+          const float hold[4] = {hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w};
+          float o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int u = c + j, jj = 4 * q + j;
-              const float rg = sigmoid_f(vr[jj] + __ldg(W.brz + u));
-              const float zg = sigmoid_f(vz[jj] + __ldg(W.brz + H + u));
-              const float n = tanhf(vi[jj] + __ldg(W.bin + u) + rg * (vh[jj] + __ldg(W.bhn + u)));
-              o[j] = (1.0f - zg) * n + zg * hold[j];
-            }
-            store_split4(S.hhi, S.hlo, r, c, H, o);
-            if (live) {
-              const float4 v4 = make_float4(o[0], o[1], o[2], o[3]);
-              const size_t offg = (size_t)(row0 + r) * H + c;
-              if (io.hidden_seq) *reinterpret_cast<float4*>(io.hidden_seq + tM * H + offg) = v4;
-              if (io.hidden && t == T - 1) *reinterpret_cast<float4*>(io.hidden + offg) = v4;
-            }
+          for (int j = 0; j < 4; ++j) {
+            const int u = c + j, jj = 4 * q + j;
+            const float4 gb = S.c.gate_b[u];
+            const float rg = sigmoid_fast(vr[jj] + gb.x);
+            const float zg = sigmoid_fast(vz[jj] + gb.y);
+            const float n = tanh_fast(vi[jj] + gb.z + rg * (vh[jj] + gb.w));
+            o[j] = (1.0f - zg) * n + zg * hold[j];
+          }
+          store_split4(S.hhi, S.hlo, r, c, H, o);
+          if (live) {
+            const float4 v4 = make_float4(o[0], o[1], o[2], o[3]);
+            const size_t offg = (size_t)(row0 + r) * H + c;
+            if (io.hidden_seq) *reinterpret_cast<float4*>(io.hidden_seq + tM * H + offg) = v4;
+            if (io.hidden && t == T - 1) *reinterpret_cast<float4*>(io.hidden + offg) = v4;
           }
         }
       }
@@ -303,35 +386,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
       fence_before_sync();
       mbar_arrive(&S.a_ready);
 
+      EP_STAMP(8);
       // ---- E5: Q tail, outputs, selection
       mbar_wait(&S.d_ready, d_par); d_par ^= 1u;
       fence_after_sync();
+      EP_STAMP(9);
       const float bq2 = __ldg(W.bq2);
-      for (int a0 = 0; a0 < A; a0 += 8) {
+      {
         float acc[8], pa[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[j] = bq2; pa[j] = (has_row && a0 + j < A) ? Ps[(a0 + j) * kTcRows + r] : 0.f; }
-        for (int c0 = 0; c0 < H; c0 += 8) {
-          float v[8];
-          tmem_ld8(tl + (uint32_t)c0, v);
+        for (int j = 0; j < 8; ++j) { acc[j] = 0.f; pa[j] = (j < A) ? Ps[j * kTcRows + r] : 0.f; }
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+          tmem_ld16_nowait(tl + kColQ + (uint32_t)c0, v);
+          tmem_ld_wait();
+          reg_fence(v);
 #pragma unroll
-          for (int n = 0; n < 8; ++n) {
-            const int u = c0 + n;
-            const float pre = v[n] + __ldg(W.bq1 + u);
-            const float w1p = __ldg(W.w1p + u), w2 = __ldg(W.w2 + u);
+          for (int n = 0; n < 16; ++n) {
+            const int u = ub + c0 + n;
+            const float4 qc = S.c.q_c[u];
+            const float4 wl = S.c.w1a[2 * u], wh = S.c.w1a[2 * u + 1];
+            const float pre = v[n] + qc.x;
+            const float wa[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (a0 + j < A)
-                acc[j] = fmaf(w2, fmaxf(pre + __ldg(W.w1a + (size_t)(a0 + j) * H + u) + pa[j] * w1p, 0.f), acc[j]);
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(qc.z, fmaxf(fmaf(pa[j], qc.y, pre + wa[j]), 0.f), acc[j]);
           }
         }
-        if (has_row)
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (a0 + j < A) Qs[(a0 + j) * kTcRows + r] = acc[j];
+        for (int j = 0; j < 8; ++j) {
+          const float tot = acc[j] + __shfl_xor_sync(0xffffffffu, acc[j], 16);
+          if (half == 0 && j < A) Qs[j * kTcRows + r] = tot + bq2;
+        }
       }
       fence_before_sync();          // TMEM reads of this step are complete before the next x_full arrival
-      if (live) {
+      __syncwarp();                 // Qs / Ps of the row were written by the lower half-warp
+      if (half == 0 && live) {
         const size_t m = tM + row0 + r;
         const uint8_t* av = io.avail ? io.avail + m * A : nullptr;
         float best = -INFINITY, bestm = -INFINITY;
@@ -380,11 +469,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
           if (io.q_chosen) io.q_chosen[m] = Qs[chosen * kTcRows + r];
         }
       }
+      __syncwarp();
+      EP_STAMP(10);
     }
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == 5) tmem_dealloc(tmem, kTmemCols);
 }
 
 inline size_t agent_tc_smem_bytes(const macjd_agent_weights& w) {
@@ -393,6 +484,7 @@ inline size_t agent_tc_smem_bytes(const macjd_agent_weights& w) {
 
 inline bool agent_tc_supported(const macjd_agent_weights& w) {
   return w.tc_chunks != nullptr && w.hidden == kTcH && w.actor_hidden == kTcH && w.obs_pad % 32 == 0 &&
+         w.n_actions <= 8 &&
          agent_tc_smem_bytes(w) <= 227 * 1024;
 }
 
@@ -403,6 +495,16 @@ inline int agent_tc_launch(const macjd_ctx* ctx, const AgentArgs& a) {
   const int grid = (a.io.n_rows + kTcRows - 1) / kTcRows;
   agent_forward_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)ctx->stream>>>(a);
   return MACJD_OK;
+}
+
+inline int tc_profile_read(unsigned long long* out_host, int n) {
+#ifdef MACJD_TC_PROFILE
+  if (n > 64) n = 64;
+  return cudaMemcpyFromSymbol(out_host, g_tc_prof, sizeof(unsigned long long) * n) == cudaSuccess ? MACJD_OK : MACJD_ERR_CUDA;
+#else
+  for (int i = 0; i < n; ++i) out_host[i] = 0;
+  return MACJD_OK;
+#endif
 }
 
 }  // namespace tc

@@ -22,11 +22,15 @@ def newest_source_mtime():
     return m
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
+    global LIB
+    if out:
+        LIB = out
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest_source_mtime():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(HERE, s) for s in SOURCES] + ["-o", LIB]
+    extra = os.environ.get("NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + [os.path.join(HERE, s) for s in SOURCES] + ["-o", LIB]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
@@ -39,4 +43,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    outs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose=True, out=outs[0] if outs else None))

@@ -197,4 +197,28 @@ int macjd_tc_gemm_selftest(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K
 #endif
 }
 
+// Debug aid (not part of the documented ABI): phase timestamps of the tcgen05 agent kernel when
+// the library was compiled with -DMACJD_TC_PROFILE; zeros otherwise.
+__attribute__((visibility("default"))) int macjd_debug_tc_profile(unsigned long long* out_host, int n) {
+#ifdef MACJD_TEST_HOST_EMULATION
+  for (int i = 0; i < n; ++i) out_host[i] = 0;
+  return MACJD_OK;
+#else
+  return macjd::tc::tc_profile_read(out_host, n);
+#endif
+}
+
+// Debug aid: tcgen05.mma issue / completion rate (cycles) for n back-to-back M x N x 8 TF32 MMAs.
+__attribute__((visibility("default"))) int macjd_debug_tc_mma_rate(const macjd_ctx* ctx, int M, int N, int n,
+                                                                  unsigned long long* out_dev) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+#ifdef MACJD_TEST_HOST_EMULATION
+  (void)M; (void)N; (void)n; (void)out_dev;
+  return MACJD_ERR_UNSUPPORTED;
+#else
+  return finish(ctx, macjd::tc::tc_mma_rate(ctx, M, N, n, out_dev));
+#endif
+}
+
 }  // extern "C"

@@ -115,6 +115,41 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 16 consecutive columns, no wait (pair with tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// After tmem_ld_wait(): pins the uses of asynchronously loaded registers behind the wait
+// (volatile asm statements keep their order; this one redefines v).
+template <int N>
+__device__ __forceinline__ void reg_fence(float (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]));
+}
+
+// fast transcendental forms (MUFU ex2 / rcp): |error| ~1e-6 absolute on sigmoid / tanh
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
 // ---------------------------------------------------------------------------------------
 // Self-test: D[M][N] = A[M][K] B[N][K]^T with the 3xTF32 split (one CTA, 128 threads).
 // Exercises every primitive above; tests/test_gpu_tc05.py checks it against float64.
@@ -193,6 +228,47 @@ inline int tc_gemm_selftest(const macjd_ctx* ctx, int M, int N, int K, const flo
     return MACJD_ERR_CUDA;
   TcTestArgs a{A, B, D, M, N, K};
   tc_gemm_selftest_kernel<<<1, 128, smem, (cudaStream_t)ctx->stream>>>(a);
+  return MACJD_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Micro-benchmark: issue `n` back-to-back tcgen05.mma (kind::tf32, SS) of shape M x N x 8 on
+// garbage operands; out[0] = cycles to issue them, out[1] = cycles until the commit fires.
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int M, int N, int n, unsigned long long* out) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < 40 * 1024 / 4; i += 128) reinterpret_cast<float*>(tc_smem)[i] = 0.001f * (float)(i & 255);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_tf32(M, N);
+    const uint64_t da = umma_smem_desc(smem_u32(tc_smem), 128, 16 * 32);
+    const uint64_t db = umma_smem_desc(smem_u32(tc_smem) + 16384, 128, 16 * 32);
+    const unsigned long long t0 = clock64();
+    for (int i = 0; i < n; ++i) mma_tf32_ss(tmem_base + (uint32_t)((i & 1) * 256), da + (uint64_t)((i & 1) * 16), db, idesc, 1u);
+    mma_commit(&bar);
+    const unsigned long long t1 = clock64();
+    mbar_wait(&bar, 0);
+    const unsigned long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+inline int tc_mma_rate(const macjd_ctx* ctx, int M, int N, int n, unsigned long long* out_dev) {
+  if (cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+    return MACJD_ERR_CUDA;
+  tc_mma_rate_kernel<<<1, 128, 64 * 1024, (cudaStream_t)ctx->stream>>>(M, N, n, out_dev);
   return MACJD_OK;
 }
 

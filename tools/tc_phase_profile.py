@@ -1,0 +1,27 @@
+"""Phase timestamps (SM clock cycles) of one tcgen05 agent CTA; needs a -DMACJD_TC_PROFILE build:
+   NVCC_EXTRA=-DMACJD_TC_PROFILE python <pkg>/csrc/build.py --force"""
+import ctypes, sys
+import torch
+sys.path.insert(0, ".")
+from tests.agent_checks import random_agent
+from macjd_b200 import _native as N
+mac, _ = random_agent(0, 24, 5, 128, 128, 2, "cuda")
+M, T = int(sys.argv[1]) if len(sys.argv) > 1 else 64, 3
+obs = torch.randn(T, M, 24, device="cuda")
+h = torch.zeros(M, 128, device="cuda")
+for _ in range(3):
+    mac.agent.run(obs, h, n_steps=T, select=True, test_mode=True, path=2)
+torch.cuda.synchronize()
+buf = (ctypes.c_ulonglong * 64)()
+N.get_lib().lib.macjd_debug_tc_profile(buf, 64)
+v = list(buf)
+names = {0: "step start", 1: "X written", 2: "D13 ready", 3: "E1 done", 4: "D2 ready", 5: "E2 done", 6: "E3 done", 7: "D4 ready",
+         8: "E4 done", 9: "D5 ready", 10: "E5+select done"}
+t0 = v[0]
+print("epilogue warp 0 (cycles since step start):")
+for k in range(11):
+    print(f"  {names[k]:>16}: {v[k] - t0:8d}" + (f"  (+{v[k] - v[k-1]})" if k else ""))
+inames = {32: "x_full seen", 33: "G1/G3 issued", 34: "a_ready#1", 35: "G2 issued", 36: "a_ready#2", 37: "G4 issued", 38: "a_ready#3", 39: "G5 issued"}
+print("issuer:")
+for k in range(32, 40):
+    print(f"  {inames[k]:>16}: {v[k] - t0:8d}" + (f"  (+{v[k] - v[k-1]})" if k > 32 else ""))
