@@ -282,6 +282,11 @@ MACJD_API int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims*
                                    const float* dq, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
                                    float* scratch, size_t scratch_floats);
 
+/* out[i] = q_all[i][idx[i]] for i < n: the target network's Q at the eval network's greedy
+ * action (core/qmix.py:147 torch.gather). */
+MACJD_API int macjd_gather_q(const macjd_ctx* ctx, int32_t n, int32_t n_actions, const float* q_all,
+                             const int32_t* idx, float* out);
+
 MACJD_API size_t macjd_td_scratch_floats(int32_t n_rows);
 /* targets = reward + gamma (1 - terminated) tq_tot;  td = (q_tot - targets) mask;
  * dq_tot = 2 td mask (NOT divided by sum(mask): macjd_clip_adam applies 1/sums[1]);

@@ -142,6 +142,7 @@ class NativeLib:
             ("macjd_qhead_scratch_floats", sz, [P(QheadDims)]),
             ("macjd_qhead_forward", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp]),
             ("macjd_qhead_backward", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]),
+            ("macjd_gather_q", C.c_int, [P(Ctx), i32, i32, vp, vp, vp]),
             ("macjd_td_scratch_floats", sz, [i32]),
             ("macjd_td_loss", C.c_int, [P(Ctx), i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, sz]),
             ("macjd_opt_scratch_floats", sz, []),

@@ -61,6 +61,7 @@ class QMixLearner:
         self.train_step = 0
         self._opt_state = None
         self._ws = {}
+        self._side_stream = None
         print(f"QMix Learner Initialized on device: {self.device}")
 
     # ------------------------------------------------------------------ plumbing
@@ -162,17 +163,32 @@ class QMixLearner:
         agent, tgt_agent = self.mac.agent, self.target_mac.agent
         obs = tb["obs"].view(T, M, -1)
 
-        # 1-2. unrolls from a zero hidden state (qmix.py:129-147)
-        ev = agent.run(obs, None, n_steps=T, zero_init=True, want_greedy=True)
-        tg = tgt_agent.run(obs, None, n_steps=T, zero_init=True, sel_actions=ev["greedy"])
-        tq_taken = tg["q_sel"][1:].reshape(R, Nn)
+        # 1-2. unrolls from a zero hidden state (qmix.py:129-147).  The two networks are
+        # independent until the double-DQN gather, so the target unroll runs on a side stream
+        # next to the eval unroll (each occupies only a few SMs at training batch sizes).
+        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        if dev.type == "cuda":
+            cur = torch.cuda.current_stream(dev)
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=dev)
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                tg = tgt_agent.run(obs, None, n_steps=T, zero_init=True, want_q=True)
+            ev = agent.run(obs, None, n_steps=T, zero_init=True, want_greedy=True)
+            cur.wait_stream(side)
+            tg["q_all"].record_stream(cur)
+        else:
+            tg = tgt_agent.run(obs, None, n_steps=T, zero_init=True, want_q=True)
+            ev = agent.run(obs, None, n_steps=T, zero_init=True, want_greedy=True)
+        tq_taken = f32(R, Nn)
+        L.callv("macjd_gather_q", ctx, R * Nn, A, tg["q_all"][1:], ev["greedy"][1:], tq_taken)
 
         # 3. target mixer (qmix.py:151)
         dims = N.MixerDims(n_rows=R, state_dim=S, n_agents=Nn, embed_dim=self.args.mixing_embed_dim,
                            hyper_hidden=self.args.hyper_hidden_dim, reserved=0)
         ws_floats = L.lib.macjd_mixer_workspace_floats(dims)
         ws = self._workspace("mixer", ws_floats, dev)
-        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         tq_tot, q_tot, dq_tot, targets = f32(R), f32(R), f32(R), f32(R)
         states_next = tb["state"][1:T].reshape(R, S)
         states_cur = tb["state"][0:T - 1].reshape(R, S)

@@ -144,6 +144,17 @@ __global__ void __launch_bounds__(256) qhead_tail_bwd_kernel(float* __restrict__
   for (int c = lane; c <= A; c += 32) xaug[(size_t)row * (A + 1) + c] = c == A ? par[row] : (c == a ? 1.f : 0.f);
 }
 
+// ---------------------------------------------------------------- double-DQN gather (qmix.py:147)
+// out[i] = q_all[i][idx[i]]   (i over rows x timesteps, q_all [.., A])
+__global__ void __launch_bounds__(256) gather_q_kernel(const float* __restrict__ q_all, const int* __restrict__ idx,
+                                                       int n, int A, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int a = idx[i];
+  a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+  out[i] = q_all[(size_t)i * A + a];
+}
+
 // ---------------------------------------------------------------- column reductions
 // part[chunk][c] = sum over the chunk's rows of X[r][c] (* Y[r][c]);  then a fixed-order
 // second pass.  Used for bias gradients and LayerNorm dgamma / dbeta.

@@ -161,6 +161,16 @@ int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, con
                                            g_w2, g_b2, scratch, scratch_floats));
 }
 
+int macjd_gather_q(const macjd_ctx* ctx, int32_t n, int32_t n_actions, const float* q_all, const int32_t* idx, float* out) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (n < 0 || n_actions < 1 || !q_all || !idx || !out) return MACJD_ERR_INVALID_ARG;
+  if (n == 0) return MACJD_OK;
+  MACJD_LAUNCH(macjd::gather_q_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)ctx->stream, q_all,
+               (const int*)idx, (int)n, (int)n_actions, out);
+  return finish(ctx, MACJD_OK);
+}
+
 size_t macjd_td_scratch_floats(int32_t n_rows) { return n_rows > 0 ? macjd::td_scratch_floats(n_rows) : 0; }
 
 int macjd_td_loss(const macjd_ctx* ctx, int32_t n_rows, const float* q_tot, const float* tq_tot, const float* reward,

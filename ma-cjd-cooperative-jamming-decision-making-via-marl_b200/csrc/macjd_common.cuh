@@ -53,6 +53,15 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint32_t stream, 
   return u01(q == 0 ? r.x : q == 1 ? r.y : q == 2 ? r.z : r.w);
 }
 
+// Fire-and-forget request that pulls a line into L2 (no register, no scoreboard entry).
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef MACJD_TEST_HOST_EMULATION
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace macjd
