@@ -13,7 +13,10 @@ if which == "agent":
     obs = torch.randn(1, M, 24, device="cuda")
     h = torch.zeros(M, 128, device="cuda")
     for _ in range(4):
-        mac.agent.run(obs, h, select=True, test_mode=True, tile_rows=int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+        if len(sys.argv) > 2 and sys.argv[2] == "tc":
+            mac.agent.run(obs, h, select=True, test_mode=True, path=2)
+        else:
+            mac.agent.run(obs, h, select=True, test_mode=True, tile_rows=int(sys.argv[2]) if len(sys.argv) > 2 else 0, path=1)
 elif which == "env":
     from macjd_b200.simulation.environment import ElectromagneticEnvironment
     from macjd_b200.simulation.scenario import default_spec
