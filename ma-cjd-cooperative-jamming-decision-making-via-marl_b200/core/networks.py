@@ -51,6 +51,16 @@ class PackedAgentWeights:
         # tensor-core copy (csrc/agent_act_tc.cuh): reference width only
         self.tc_ok = (self.H == 128 and self.AH == 128)
         self.tc_buffer = None
+        self._cstruct = None
+        self._cstruct_for = None
+
+    def __deepcopy__(self, memo):
+        # target networks deep-copy the agent: the copy re-packs from its own parameters
+        new = PackedAgentWeights.__new__(PackedAgentWeights)
+        new.__dict__.update({k: v for k, v in self.__dict__.items()
+                             if k not in ("buffer", "tc_buffer", "versions", "_cstruct", "_cstruct_for")})
+        new.buffer = new.tc_buffer = new.versions = new._cstruct = new._cstruct_for = None
+        return new
 
     def view(self, f):
         n = int(np.prod(self.shapes[f]))
@@ -130,6 +140,13 @@ class PackedAgentWeights:
         self.tc_buffer = torch.stack([hi, lo], dim=1).contiguous()   # [n_chunks, 2, 2048]
 
     def cstruct(self):
+        if self._cstruct is not None and self._cstruct_for == (self.buffer.data_ptr(), id(self.tc_buffer)):
+            return self._cstruct
+        self._cstruct = self._make_cstruct()
+        self._cstruct_for = (self.buffer.data_ptr(), id(self.tc_buffer))
+        return self._cstruct
+
+    def _make_cstruct(self):
         base = self.buffer.data_ptr()
         kw = {f: base + 4 * self.offsets[f] for f in self.FIELDS}
         tc = self.tc_buffer.data_ptr() if self.tc_buffer is not None else None

@@ -165,12 +165,44 @@ class BatchedEpisodeRunner:
                      "terminated": z((T, n, 1), torch.uint8), "hidden_state": z((T + 1, n, Nn, H), torch.float32)}
         self.r_parts = z((3, T, n), torch.float32)
 
+    def _build_step_structs(self):
+        """All pointers of a timestep are fixed (persistent trajectory buffers), so the C structs
+        of its two launches are built once; per step only epsilon / rng_step / test_mode change.
+        Keeps the host cost of a step at two ctypes calls (the rollout stays GPU-bound)."""
+        from .. import _native as N
+        tr, mac, env = self.traj, self.mac, self.env
+        n, Nn = self.n_envs, self.n_agents
+        p = N.ptr
+        self._agent_io, self._env_io = [], []
+        for t in range(self.episode_limit):
+            self._agent_io.append(N.AgentIO(
+                n_rows=n * Nn, n_steps=1, obs=p(tr["obs"][t]), hidden=p(mac.hidden_states), hidden_zero_init=0,
+                test_mode=0, tile_rows=0, path=mac.agent.path, hidden_seq=p(tr["hidden_state"][t]),
+                avail=p(tr["avail_actions"][t]), epsilon=0.0, rng_step=0, seed=mac.seed & 0xFFFFFFFFFFFFFFFF,
+                actions=p(tr["actions_discrete"][t]), power=p(tr["actions_continuous"][t])))
+            self._env_io.append(env._io(tr["actions_discrete"][t], tr["actions_continuous"][t], None, out={
+                "reward": tr["reward"][t], "terminated": tr["terminated"][t], "r_d": self.r_parts[0, t],
+                "r_p": self.r_parts[1, t], "r_j": self.r_parts[2, t], "state": tr["state"][t + 1],
+                "obs": tr["obs"][t + 1], "avail": tr["avail_actions"][t + 1]}))
+        self._structs_for = (mac.hidden_states.data_ptr(), mac.agent.path)
+
     def step(self, t, test_mode=False, noise=None, u_eps=None, rand_actions=None):
         """Timestep t of the current episodes: agent act + env step, both into the trajectory."""
         tr, mac, env = self.traj, self.mac, self.env
         n, Nn = self.n_envs, self.n_agents
         eps = mac.action_selector.anneal(self.t_env, test_mode)
         mac._rng_step += 1
+        if noise is None and u_eps is None and rand_actions is None:
+            # fast path: cached structs
+            if getattr(self, "_structs_for", None) != (mac.hidden_states.data_ptr(), mac.agent.path):
+                self._build_step_structs()
+            aio = self._agent_io[t]
+            aio.epsilon, aio.rng_step, aio.test_mode = float(eps), mac._rng_step & 0xFFFFFFFF, int(test_mode)
+            lib, ctx = mac.agent.lib(), mac.agent._ctx()
+            lib.call("macjd_agent_forward", ctx, mac.agent.packed().cstruct(), aio)
+            lib.call("macjd_env_step", ctx, env._ctab, self._env_io[t])
+            self.t_env += 1
+            return
         mac.agent.run(tr["obs"][t].view(1, n * Nn, -1), mac.hidden_states, avail=tr["avail_actions"][t],
                       epsilon=eps, test_mode=test_mode, u_eps=u_eps, rand_actions=rand_actions, seed=mac.seed,
                       rng_step=mac._rng_step, select=True, want_hidden_seq=True,

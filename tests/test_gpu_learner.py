@@ -68,3 +68,38 @@ def test_learner_full_size_vs_oracle():
     ref, _, _ = ora.train({k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in batch.items()})
     for k in ("loss", "grad_norm", "eval_qtot_avg", "target_qtot_avg"):
         np.testing.assert_allclose(stats[0][k], ref[k], rtol=2e-4, atol=1e-5, err_msg=k)
+
+
+def test_learner_stress_dims_vs_oracle():
+    """BASELINE config 4 dims (H = 256, E = 128) at a small batch: one step against the eager oracle."""
+    from oracle import agent_oracle as AO
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.core.qmix import QMixLearner
+    args = types.SimpleNamespace(n_agents=2, n_actions=5, state_shape=24, obs_shape=24, rnn_hidden_dim=256,
+                                 actor_hidden_dim=128, mixing_embed_dim=128, hyper_hidden_dim=128, epsilon_start=1.0,
+                                 epsilon_finish=0.05, epsilon_anneal_time=1000, gamma=0.99, lr=1e-4, grad_norm_clip=1.0,
+                                 target_update_interval=200, use_cuda=True, device="cuda", seed=0)
+    B, T, Nn, A, S, H = 12, 9, 2, 5, 24, 256
+    rng = np.random.default_rng(5)
+    batch = {"state": rng.standard_normal((B, T + 1, S)).astype(np.float32),
+             "obs": rng.standard_normal((B, T + 1, Nn, S)).astype(np.float32),
+             "actions_discrete": rng.integers(0, A, size=(B, T, Nn, 1)).astype(np.int32),
+             "actions_continuous": rng.random((B, T, Nn, 1)).astype(np.float32),
+             "avail_actions": np.ones((B, T + 1, Nn, A), dtype=np.int64),
+             "reward": rng.standard_normal((B, T, 1)).astype(np.float32),
+             "terminated": np.zeros((B, T, 1), dtype=bool), "filled": np.ones((B, T, 1), dtype=bool),
+             "hidden_state": (rng.standard_normal((B, T + 1, Nn, H)) * 0.5).astype(np.float32), "max_seq_len": T}
+    torch.manual_seed(1)
+    mac = BasicMAC(S, args)
+    L = QMixLearner(mac, args)
+    agent_sd = {k: v.detach().cpu().clone() for k, v in mac.agent.state_dict().items()}
+    mixer_sd = {k: v.detach().cpu().clone() for k, v in L.eval_qmix_net.state_dict().items()}
+    stats = L.train(batch, {})
+    ora = AO.LearnerOracle(agent_sd, mixer_sd, Nn, 128, 0.99, 1e-4, 1.0, 200)
+    ref, _, _ = ora.train({k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v) for k, v in batch.items()})
+    for k in ("loss", "grad_norm", "eval_qtot_avg", "target_qtot_avg"):
+        np.testing.assert_allclose(stats[k], ref[k], rtol=2e-4, atol=1e-5, err_msg=k)
+    for k in AO.TRAINED_AGENT_KEYS:
+        w0 = agent_sd[k].numpy()
+        np.testing.assert_allclose(mac.agent.state_dict()[k].cpu().numpy() - w0, ora.agent[k].numpy() - w0,
+                                   rtol=1e-2, atol=1e-4 * 1e-2 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
