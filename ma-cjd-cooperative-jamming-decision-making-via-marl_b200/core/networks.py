@@ -103,7 +103,9 @@ class PackedAgentWeights:
         self.view("w2").copy_(sd["fc2_q_head.2.weight"].reshape(-1))
         self.view("bq2").copy_(sd["fc2_q_head.2.bias"])
         if self.tc_ok and dev.type == "cuda":
-            self._pack_tc(sd)
+            kc = int(agent.lib().lib.macjd_agent_tc_chunk_k())
+            if kc > 0:
+                self._pack_tc(sd, kc)
         self.versions = versions
         return self
 
@@ -116,25 +118,26 @@ class PackedAgentWeights:
         x = w.reshape(n // 8, 8, K // kc, kc // 4, 4)          # n/8, n%8, chunk, k/4, k%4
         return x.permute(2, 0, 3, 1, 4).contiguous().reshape(K // kc, n * kc)
 
-    def _pack_tc(self, sd):
+    def _pack_tc(self, sd, kc=16):
         """Weight chunks in the order agent_forward_tc_kernel consumes them; TF32 hi part
         (low 13 mantissa bits cleared) followed by the lo remainder, per chunk."""
         O, Op, H, A = self.O, self.Op, self.H, self.A
         dev = sd["fc1.weight"].device
         pad = lambda w: torch.cat([w, torch.zeros(w.shape[0], Op - O, device=dev)], dim=1)
         wih, whh = sd["rnn.weight_ih"], sd["rnn.weight_hh"]
-        ca1, cfc1 = self._umma_chunks(pad(sd["actor.0.weight"])), self._umma_chunks(pad(sd["fc1.weight"]))
+        uc = lambda w: self._umma_chunks(w, kc)
+        ca1, cfc1 = uc(pad(sd["actor.0.weight"])), uc(pad(sd["fc1.weight"]))
         seq = []
-        for i in range(Op // 16):
+        for i in range(Op // kc):
             seq += [ca1[i:i + 1], cfc1[i:i + 1]]
-        seq.append(self._umma_chunks(sd["actor.2.weight"]))
+        seq.append(uc(sd["actor.2.weight"]))
         for g in range(2):                                      # r, z: W_i{g} on xf then W_h{g} on h
-            seq.append(self._umma_chunks(wih[g * H:(g + 1) * H]))
-            seq.append(self._umma_chunks(whh[g * H:(g + 1) * H]))
-        seq.append(self._umma_chunks(wih[2 * H:]))              # W_in on xf
-        seq.append(self._umma_chunks(whh[2 * H:]))              # W_hn on h
-        seq.append(self._umma_chunks(sd["fc2_q_head.0.weight"][:, :H]))
-        full = torch.cat(seq, dim=0).contiguous()               # [n_chunks, 128 * 16]
+            seq.append(uc(wih[g * H:(g + 1) * H]))
+            seq.append(uc(whh[g * H:(g + 1) * H]))
+        seq.append(uc(wih[2 * H:]))                             # W_in on xf
+        seq.append(uc(whh[2 * H:]))                             # W_hn on h
+        seq.append(uc(sd["fc2_q_head.0.weight"][:, :H]))
+        full = torch.cat(seq, dim=0).contiguous()               # [n_chunks, 128 * kc]
         hi = (full.view(torch.int32) & -8192).view(torch.float32)
         lo = full - hi
         self.tc_buffer = torch.stack([hi, lo], dim=1).contiguous()   # [n_chunks, 2, 2048]

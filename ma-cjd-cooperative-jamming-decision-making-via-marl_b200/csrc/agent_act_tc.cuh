@@ -29,8 +29,14 @@ namespace tc {
 
 constexpr int kTcRows = 64;
 constexpr int kTcH = 128;            // hidden width this kernel is specialised for
-constexpr int kTcKc = 16;            // k per weight chunk
-constexpr int kTcStages = 4;
+#ifndef MACJD_TC_KC
+#define MACJD_TC_KC 32
+#endif
+constexpr int kTcKc = MACJD_TC_KC;   // k per weight chunk (16 or 32); the ring always holds 64 KB
+constexpr int kTcStages = 64 / kTcKc;
+constexpr int kTcChunksPerH = kTcH / kTcKc;               // chunks of a K = 128 layer
+constexpr int kTcChunksPerX = 32 / kTcKc;                 // chunks per 32-wide observation block
+constexpr uint32_t kTcAStep = kTcKc * 32;                 // A-tile byte offset between chunks
 constexpr int kTcChunkFloats = 2 * kTcH * kTcKc;          // hi + lo
 constexpr int kTcChunkBytes = kTcChunkFloats * 4;         // 16 KB
 constexpr int kTcThreads = 192;       // 4 epilogue warps + weight-stream warp + MMA warp
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
   float* Ps = reinterpret_cast<float*>(tc_raw + sizeof(TcSmem));     // [A][64]
   float* Qs = Ps + (size_t)A * kTcRows;                               // [A][64]
   const int nxc = Op / 32;
-  const int chunks_per_step = 4 * nxc + 8 + 48 + 8;
+  const int chunks_per_step = 2 * kTcChunksPerX * nxc + 8 * kTcChunksPerH;
 
   if (warp == 5) tmem_alloc(&S.tmem_base, kTmemCols);
   if (tid == 0) {
@@ -175,8 +181,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
         const uint32_t wbase = smem_u32(S.wst[s]);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const uint64_t dbh = umma_smem_desc(wbase + half * 4096, 128, kTcKc * 32);
-          const uint64_t dbl = umma_smem_desc(wbase + kTcH * kTcKc * 4 + half * 4096, 128, kTcKc * 32);
+          const uint64_t dbh = umma_smem_desc(wbase + half * (8 * kTcKc * 32), 128, kTcKc * 32);   // units 64.. = 8 row groups down
+          const uint64_t dbl = umma_smem_desc(wbase + kTcH * kTcKc * 4 + half * (8 * kTcKc * 32), 128, kTcKc * 32);
           const uint32_t d = tmem + ((uint32_t)(half * 16) << 16) + dcol;
 #pragma unroll
           for (int ks = 0; ks < kTcKc / 8; ++ks) {
@@ -194,9 +200,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
         for (int xc = 0; xc < nxc; ++xc) {
           mbar_wait(&S.x_full, x_full_par); x_full_par ^= 1u;
           TC_STAMP(32);
-          for (int hf = 0; hf < 2; ++hf) {
-            mma_chunk(S.xhi, S.xlo, 32 * 32, hf * 512, kColA1, xc == 0 && hf == 0);
-            mma_chunk(S.xhi, S.xlo, 32 * 32, hf * 512, kColFc1, xc == 0 && hf == 0);
+          for (int hf = 0; hf < kTcChunksPerX; ++hf) {
+            mma_chunk(S.xhi, S.xlo, 32 * 32, hf * kTcAStep, kColA1, xc == 0 && hf == 0);
+            mma_chunk(S.xhi, S.xlo, 32 * 32, hf * kTcAStep, kColFc1, xc == 0 && hf == 0);
           }
           mma_commit(&S.x_empty);
         }
@@ -205,24 +211,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
         // actor.2 on a1
         mbar_wait(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
         TC_STAMP(34);
-        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, kColA2, kc == 0);
+        for (int kc = 0; kc < kTcChunksPerH; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * kTcAStep, kColA2, kc == 0);
         mma_commit(&S.d_ready);
         TC_STAMP(35);
         // GRU on xf (B0) and h
         mbar_wait(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
         TC_STAMP(36);
         for (int g = 0; g < 2; ++g) {
-          for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, g == 0 ? kColR : kColZ, kc == 0);
-          for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, g == 0 ? kColR : kColZ, false);
+          for (int kc = 0; kc < kTcChunksPerH; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * kTcAStep, g == 0 ? kColR : kColZ, kc == 0);
+          for (int kc = 0; kc < kTcChunksPerH; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * kTcAStep, g == 0 ? kColR : kColZ, false);
         }
-        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * 512, kColIn, kc == 0);
-        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, kColHn, kc == 0);
+        for (int kc = 0; kc < kTcChunksPerH; ++kc) mma_chunk(S.b0hi, S.b0lo, H * 32, kc * kTcAStep, kColIn, kc == 0);
+        for (int kc = 0; kc < kTcChunksPerH; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * kTcAStep, kColHn, kc == 0);
         mma_commit(&S.d_ready);
         TC_STAMP(37);
         // Q-head on h'
         mbar_wait(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
         TC_STAMP(38);
-        for (int kc = 0; kc < 8; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * 512, kColQ, kc == 0);
+        for (int kc = 0; kc < kTcChunksPerH; ++kc) mma_chunk(S.hhi, S.hlo, H * 32, kc * kTcAStep, kColQ, kc == 0);
         mma_commit(&S.d_ready);
         TC_STAMP(39);
       }
@@ -477,6 +483,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
   __syncthreads();
   if (warp == 5) tmem_dealloc(tmem, kTmemCols);
 }
+
+inline int agent_tc_chunk_k() { return kTcKc; }
 
 inline size_t agent_tc_smem_bytes(const macjd_agent_weights& w) {
   return sizeof(TcSmem) + sizeof(float) * 2 * (size_t)w.n_actions * kTcRows + 1024;

@@ -207,6 +207,15 @@ int macjd_tc_gemm_selftest(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K
 #endif
 }
 
+// k-extent of one packed weight chunk the tcgen05 agent kernel was built for (0: no tensor-core path).
+__attribute__((visibility("default"))) int macjd_agent_tc_chunk_k(void) {
+#ifdef MACJD_TEST_HOST_EMULATION
+  return 0;
+#else
+  return macjd::tc::agent_tc_chunk_k();
+#endif
+}
+
 // Debug aid (not part of the documented ABI): phase timestamps of the tcgen05 agent kernel when
 // the library was compiled with -DMACJD_TC_PROFILE; zeros otherwise.
 __attribute__((visibility("default"))) int macjd_debug_tc_profile(unsigned long long* out_host, int n) {
