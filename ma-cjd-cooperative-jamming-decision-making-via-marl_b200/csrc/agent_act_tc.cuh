@@ -6,19 +6,24 @@
 // (profiles/r1a_agent_r1a.summary.csv): the dense layers move to tcgen05.mma, everything
 // else stays FP32 SIMT.
 //
-// One CTA = 64 agent rows, 5 warps:
-//   warps 0-3  epilogue: thread (w, l < 16) owns row 16 w + l = TMEM lane 32 w + l.  It reads its
-//              accumulator row with tcgen05.ld, applies bias / ReLU / the GRU gate algebra / the
-//              actor head / the per-action Q tail entirely in registers, and writes the next
-//              layer's A operand (hi and lo TF32 parts) to shared memory in UMMA layout.
-//   warp 4     lane 0 streams the packed weight chunks (128 x 16, hi + lo = 16 KB) from L2 with
-//              1-D bulk async copies into a 4-stage ring.
-//   warp 5     lane 0 issues the tcgen05.mma's (every 128-wide layer as two N = 64 halves, the
-//              second on TMEM lanes +16, so both half-warps of an epilogue warp own half a row).
+// One CTA = 64 agent rows, 6 warps:
+//   warps 0-3  epilogue.  Accumulators are M = 64 tiles in TMEM (row i of quarter w on lane
+//              32 w + i, i < 16); the warps read them with tcgen05.ld.16x256b, which spreads the 16
+//              valid lanes over all 32 threads like an m16n8 accumulator fragment (thread t: rows
+//              t/4 and t/4 + 8, column pairs 2 (t%4) of every 8-column group).  Bias / ReLU / GRU gate
+//              algebra / actor head / per-action Q tail run in registers (row sums finish with two
+//              shuffles over the 4 threads of a row); the next layer's A operand is written to
+//              shared memory as TF32 hi + lo tiles in UMMA K-major layout.
+//   warp 4     lane 0 streams the packed weight chunks (128 x 32, hi + lo = 32 KB) from L2 with
+//              1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) into a 2-stage ring.
+//   warp 5     lane 0 issues the tcgen05.mma's: M = 64, N = 128, K = 8, kind::tf32, three split
+//              products per k-step, accumulators in 512 TMEM columns.
 //   mbarriers carry weights-landed / stage-free / accumulator-ready / operand-ready events.
 // Measured on B200 (tools/tc_mma_rate.py): one M x N x 8 TF32 SS MMA costs ~52 / 69 / 133 cycles
 // for N = 64 / 128 / 256 regardless of M in {64, 128}; a single thread that both waits on
 // barriers and issues copies needs ~800 cycles per chunk, hence the separate stream warp.
+// One CTA-step takes ~32 us alone and ~48 us with 128 CTAs resident (1.09 MB of weight chunks
+// per CTA-step from L2: 2.9 TB/s aggregate).
 #pragma once
 #include "agent_act.cuh"
 #include "tc05.cuh"
@@ -98,13 +103,24 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
-// TMEM columns.  Every 128-wide accumulator is issued as two N = 64 MMAs: output units 0-63 on
-// the lower 16 lanes of each 32-lane quarter, units 64-127 on the upper 16 lanes (lane offset
-// 16), same columns -- so both half-warps of an epilogue warp own half a row each.
-constexpr uint32_t kColA1 = 0, kColFc1 = 64, kColA2 = 128;          // actor.0, fc1, actor.2
-constexpr uint32_t kColR = 0, kColZ = 64, kColIn = 128, kColHn = 192;   // GRU
+// TMEM columns (M = 64 accumulators: row i of warp-quarter w on lane 32 w + i, i < 16).  The
+// epilogue warps read them with tcgen05.ld.16x256b, which spreads the 16 valid lanes over all
+// 32 threads like an m16n8 accumulator fragment: thread t owns rows g and g + 8 (g = t / 4)
+// and, in every 8-column group, columns 2 (t % 4) and 2 (t % 4) + 1.
+constexpr uint32_t kColA1 = 0, kColFc1 = 128, kColA2 = 256;             // actor.0, fc1, actor.2
+constexpr uint32_t kColR = 0, kColZ = 128, kColIn = 256, kColHn = 384;   // GRU
 constexpr uint32_t kColQ = 0;
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = 512;
+
+// write 2 consecutive k of one row (hi and lo parts) into a UMMA-layout operand tile
+__device__ __forceinline__ void store_split2(float* hi, float* lo, int r, int k, int K, float v0, float v1) {
+  const uint32_t off = umma_off_bytes(r, k, K) >> 2;
+  float2 h, l;
+  h.x = tf32_hi(v0); h.y = tf32_hi(v1);
+  l.x = v0 - h.x; l.y = v1 - h.y;
+  *reinterpret_cast<float2*>(hi + off) = h;
+  *reinterpret_cast<float2*>(lo + off) = l;
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const AgentArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
@@ -165,11 +181,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
   } else if (warp == 5) {
     // =========================================================== MMA issue
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kTcRows, 64);
+      const uint32_t idesc = umma_idesc_tf32(kTcRows, kTcH);
       long long cur = 0;
       uint32_t full_par = 0;
       uint32_t x_full_par = 0, a_ready_par = 0;
-      // one chunk (16 k): 2 k-steps x 2 unit halves x 3 split products into TMEM column `dcol`
+      // one chunk: kTcKc / 8 k-steps x 3 split products (M = 64, N = 128) into TMEM column `dcol`
       auto mma_chunk = [&](const float* ahi, const float* alo, uint32_t a_sbo, uint32_t a_koff_bytes, uint32_t dcol,
                            bool first) {
         const int s = (int)(cur % kTcStages);
@@ -179,18 +195,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
         const uint64_t dah = umma_smem_desc(smem_u32(ahi) + a_koff_bytes, 128, a_sbo);
         const uint64_t dal = umma_smem_desc(smem_u32(alo) + a_koff_bytes, 128, a_sbo);
         const uint32_t wbase = smem_u32(S.wst[s]);
+        const uint64_t dbh = umma_smem_desc(wbase, 128, kTcKc * 32);
+        const uint64_t dbl = umma_smem_desc(wbase + kTcH * kTcKc * 4, 128, kTcKc * 32);
+        const uint32_t d = tmem + dcol;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint64_t dbh = umma_smem_desc(wbase + half * (8 * kTcKc * 32), 128, kTcKc * 32);   // units 64.. = 8 row groups down
-          const uint64_t dbl = umma_smem_desc(wbase + kTcH * kTcKc * 4 + half * (8 * kTcKc * 32), 128, kTcKc * 32);
-          const uint32_t d = tmem + ((uint32_t)(half * 16) << 16) + dcol;
-#pragma unroll
-          for (int ks = 0; ks < kTcKc / 8; ++ks) {
-            const uint64_t adv = (uint64_t)((ks * 256) >> 4);
-            mma_tf32_ss(d, dah + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
-            mma_tf32_ss(d, dal + adv, dbh + adv, idesc, 1u);
-            mma_tf32_ss(d, dah + adv, dbl + adv, idesc, 1u);
-          }
+        for (int ks = 0; ks < kTcKc / 8; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * 256) >> 4);
+          mma_tf32_ss(d, dah + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
+          mma_tf32_ss(d, dal + adv, dbh + adv, idesc, 1u);
+          mma_tf32_ss(d, dah + adv, dbl + adv, idesc, 1u);
         }
         mma_commit(&S.w_empty[s]);
         ++cur;
@@ -240,6 +253,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
     const int ub = half * 64;                        // first unit owned by this thread
     const bool live = r < valid;
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lane quarter
+    const int fr = warp * 16 + (lane >> 2);          // fragment rows of this thread: fr and fr + 8
+    const int fq = lane & 3;                         // fragment column pair within every 8-column group
     uint32_t d_par = 0, x_empty_par = 0;
 
     // recurrent state -> hi / lo operand tiles (each thread: its half of the row)
@@ -283,17 +298,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
       mbar_wait(&S.d_ready, d_par); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(2);
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int cb = 0; cb < 4; ++cb) {
         float v[16];
-        tmem_ld16_nowait(tl + kColA1 + (uint32_t)c0, v);
+        tmem_ld_16x256b_x4_nowait(tl + kColA1 + (uint32_t)(32 * cb), v);
         tmem_ld_wait();
         reg_fence(v);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float o[4];
+        for (int i = 0; i < 4; ++i) {
+          const int c = 32 * cb + 8 * i + 2 * fq;
+          const float2 b = *reinterpret_cast<const float2*>(&S.c.ba1[c]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * q + j] + S.c.ba1[ub + c0 + 4 * q + j], 0.f);
-          store_split4(S.b0hi, S.b0lo, r, ub + c0 + 4 * q, H, o);
+          for (int hr = 0; hr < 2; ++hr)
+            store_split2(S.b0hi, S.b0lo, fr + 8 * hr, c, H, fmaxf(v[4 * i + 2 * hr] + b.x, 0.f),
+                         fmaxf(v[4 * i + 2 * hr + 1] + b.y, 0.f));
         }
       }
       fence_async_smem();
@@ -306,43 +323,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
       fence_after_sync();
       EP_STAMP(4);
       {
-        float acc[8];
+        float acc[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[hr][j] = 0.f;
+        for (int cb = 0; cb < 4; ++cb) {
           float v[16];
-          tmem_ld16_nowait(tl + kColA2 + (uint32_t)c0, v);
+          tmem_ld_16x256b_x4_nowait(tl + kColA2 + (uint32_t)(32 * cb), v);
           tmem_ld_wait();
           reg_fence(v);
 #pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            const int u = ub + c0 + n;
-            const float a2 = fmaxf(v[n] + S.c.ba2[u], 0.f);
-            const float4 wl = S.c.wa3t[2 * u], wh = S.c.wa3t[2 * u + 1];
-            acc[0] = fmaf(a2, wl.x, acc[0]); acc[1] = fmaf(a2, wl.y, acc[1]);
-            acc[2] = fmaf(a2, wl.z, acc[2]); acc[3] = fmaf(a2, wl.w, acc[3]);
-            acc[4] = fmaf(a2, wh.x, acc[4]); acc[5] = fmaf(a2, wh.y, acc[5]);
-            acc[6] = fmaf(a2, wh.z, acc[6]); acc[7] = fmaf(a2, wh.w, acc[7]);
-          }
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int u = 32 * cb + 8 * i + 2 * fq + e;
+              const float b = S.c.ba2[u];
+              const float4 wl = S.c.wa3t[2 * u], wh = S.c.wa3t[2 * u + 1];
+              const float w[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
+#pragma unroll
+              for (int hr = 0; hr < 2; ++hr) {
+                const float a2 = fmaxf(v[4 * i + 2 * hr + e] + b, 0.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[hr][j] = fmaf(a2, w[j], acc[hr][j]);
+              }
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float tot = acc[j] + __shfl_xor_sync(0xffffffffu, acc[j], 16);
-          if (half == 0 && j < A) Ps[j * kTcRows + r] = sigmoid_fast(tot + S.c.ba3[j]);
-        }
+        for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float tot = acc[hr][j];
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            if (fq == 0 && j < A) Ps[j * kTcRows + fr + 8 * hr] = sigmoid_fast(tot + S.c.ba3[j]);
+          }
       }
       EP_STAMP(5);
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int cb = 0; cb < 4; ++cb) {
         float v[16];
-        tmem_ld16_nowait(tl + kColFc1 + (uint32_t)c0, v);
+        tmem_ld_16x256b_x4_nowait(tl + kColFc1 + (uint32_t)(32 * cb), v);
         tmem_ld_wait();
         reg_fence(v);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float o[4];
+        for (int i = 0; i < 4; ++i) {
+          const int c = 32 * cb + 8 * i + 2 * fq;
+          const float2 b = *reinterpret_cast<const float2*>(&S.c.bfc1[c]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * q + j] + S.c.bfc1[ub + c0 + 4 * q + j], 0.f);
-          store_split4(S.b0hi, S.b0lo, r, ub + c0 + 4 * q, H, o);
+          for (int hr = 0; hr < 2; ++hr)
+            store_split2(S.b0hi, S.b0lo, fr + 8 * hr, c, H, fmaxf(v[4 * i + 2 * hr] + b.x, 0.f),
+                         fmaxf(v[4 * i + 2 * hr + 1] + b.y, 0.f));
         }
       }
       fence_async_smem();
@@ -354,37 +384,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
       mbar_wait(&S.d_ready, d_par); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(7);
-      for (int c0 = 0; c0 < 64; c0 += 8) {
+      for (int c0 = 0; c0 < H; c0 += 16) {
         float vr[8], vz[8], vi[8], vh[8];
-        tmem_ld8_nowait(tl + kColR + (uint32_t)c0, vr);
-        tmem_ld8_nowait(tl + kColZ + (uint32_t)c0, vz);
-        tmem_ld8_nowait(tl + kColIn + (uint32_t)c0, vi);
-        tmem_ld8_nowait(tl + kColHn + (uint32_t)c0, vh);
+        tmem_ld_16x256b_x2_nowait(tl + kColR + (uint32_t)c0, vr);
+        tmem_ld_16x256b_x2_nowait(tl + kColZ + (uint32_t)c0, vz);
+        tmem_ld_16x256b_x2_nowait(tl + kColIn + (uint32_t)c0, vi);
+        tmem_ld_16x256b_x2_nowait(tl + kColHn + (uint32_t)c0, vh);
         tmem_ld_wait();
         reg_fence(vr); reg_fence(vz); reg_fence(vi); reg_fence(vh);
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int c = ub + c0 + 4 * q;
-          const uint32_t off = umma_off_bytes(r, c, H) >> 2;
-          const float4 hh = *reinterpret_cast<const float4*>(S.hhi + off);
-          const float4 hl = *reinterpret_cast<const float4*>(S.hlo + off);
-          const float hold[4] = {hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w};
-          float o[4];
+        for (int i = 0; i < 2; ++i) {
+          const int c = c0 + 8 * i + 2 * fq;
+          const float4 gb0 = S.c.gate_b[c], gb1 = S.c.gate_b[c + 1];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int u = c + j, jj = 4 * q + j;
-            const float4 gb = S.c.gate_b[u];
-            const float rg = sigmoid_fast(vr[jj] + gb.x);
-            const float zg = sigmoid_fast(vz[jj] + gb.y);
-            const float n = tanh_fast(vi[jj] + gb.z + rg * (vh[jj] + gb.w));
-            o[j] = (1.0f - zg) * n + zg * hold[j];
-          }
-          store_split4(S.hhi, S.hlo, r, c, H, o);
-          if (live) {
-            const float4 v4 = make_float4(o[0], o[1], o[2], o[3]);
-            const size_t offg = (size_t)(row0 + r) * H + c;
-            if (io.hidden_seq) *reinterpret_cast<float4*>(io.hidden_seq + tM * H + offg) = v4;
-            if (io.hidden && t == T - 1) *reinterpret_cast<float4*>(io.hidden + offg) = v4;
+          for (int hr = 0; hr < 2; ++hr) {
+            const int r = fr + 8 * hr;
+            const uint32_t off = umma_off_bytes(r, c, H) >> 2;
+            const float2 hh = *reinterpret_cast<const float2*>(S.hhi + off);
+            const float2 hl = *reinterpret_cast<const float2*>(S.hlo + off);
+            const int jj = 4 * i + 2 * hr;
+            const float rg0 = sigmoid_fast(vr[jj] + gb0.x), rg1 = sigmoid_fast(vr[jj + 1] + gb1.x);
+            const float zg0 = sigmoid_fast(vz[jj] + gb0.y), zg1 = sigmoid_fast(vz[jj + 1] + gb1.y);
+            const float n0 = tanh_fast(vi[jj] + gb0.z + rg0 * (vh[jj] + gb0.w));
+            const float n1 = tanh_fast(vi[jj + 1] + gb1.z + rg1 * (vh[jj + 1] + gb1.w));
+            const float o0 = (1.0f - zg0) * n0 + zg0 * (hh.x + hl.x);
+            const float o1 = (1.0f - zg1) * n1 + zg1 * (hh.y + hl.y);
+            store_split2(S.hhi, S.hlo, r, c, H, o0, o1);
+            if (r < valid) {
+              const float2 v2 = make_float2(o0, o1);
+              const size_t offg = (size_t)(row0 + r) * H + c;
+              if (io.hidden_seq) *reinterpret_cast<float2*>(io.hidden_seq + tM * H + offg) = v2;
+              if (io.hidden && t == T - 1) *reinterpret_cast<float2*>(io.hidden + offg) = v2;
+            }
           }
         }
       }
@@ -399,33 +430,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
       EP_STAMP(9);
       const float bq2 = __ldg(W.bq2);
       {
-        float acc[8], pa[8];
+        float acc[2][8], pa[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[j] = 0.f; pa[j] = (j < A) ? Ps[j * kTcRows + r] : 0.f; }
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[hr][j] = 0.f; pa[hr][j] = (j < A) ? Ps[j * kTcRows + fr + 8 * hr] : 0.f; }
+        for (int cb = 0; cb < 4; ++cb) {
           float v[16];
-          tmem_ld16_nowait(tl + kColQ + (uint32_t)c0, v);
+          tmem_ld_16x256b_x4_nowait(tl + kColQ + (uint32_t)(32 * cb), v);
           tmem_ld_wait();
           reg_fence(v);
 #pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            const int u = ub + c0 + n;
-            const float4 qc = S.c.q_c[u];
-            const float4 wl = S.c.w1a[2 * u], wh = S.c.w1a[2 * u + 1];
-            const float pre = v[n] + qc.x;
-            const float wa[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(qc.z, fmaxf(fmaf(pa[j], qc.y, pre + wa[j]), 0.f), acc[j]);
+            for (int e = 0; e < 2; ++e) {
+              const int u = 32 * cb + 8 * i + 2 * fq + e;
+              const float4 qc = S.c.q_c[u];
+              const float4 wl = S.c.w1a[2 * u], wh = S.c.w1a[2 * u + 1];
+              const float wa[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
+#pragma unroll
+              for (int hr = 0; hr < 2; ++hr) {
+                const float pre = v[4 * i + 2 * hr + e] + qc.x;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  acc[hr][j] = fmaf(qc.z, fmaxf(fmaf(pa[hr][j], qc.y, pre + wa[j]), 0.f), acc[hr][j]);
+              }
+            }
+        }
+#pragma unroll
+        for (int hr = 0; hr < 2; ++hr)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float tot = acc[hr][j];
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            if (fq == 0 && j < A) Qs[j * kTcRows + fr + 8 * hr] = tot + bq2;
           }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float tot = acc[j] + __shfl_xor_sync(0xffffffffu, acc[j], 16);
-          if (half == 0 && j < A) Qs[j * kTcRows + r] = tot + bq2;
-        }
       }
       fence_before_sync();          // TMEM reads of this step are complete before the next x_full arrival
-      __syncwarp();                 // Qs / Ps of the row were written by the lower half-warp
+      __syncwarp();                 // Qs / Ps of a row were written by the lane with fq == 0 that owns it
       if (half == 0 && live) {
         const size_t m = tM + row0 + r;
         const uint8_t* av = io.avail ? io.avail + m * A : nullptr;

@@ -203,7 +203,8 @@ int macjd_tc_gemm_selftest(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K
   (void)M; (void)N; (void)K; (void)A; (void)B; (void)D;
   return MACJD_ERR_UNSUPPORTED;   // tensor cores cannot be emulated on the host
 #else
-  return finish(ctx, macjd::tc::tc_gemm_selftest(ctx, M, N, K, A, B, D));
+  // N's bit 30 selects the fragment-layout TMEM read (tcgen05.ld.16x256b) in the epilogue
+  return finish(ctx, macjd::tc::tc_gemm_selftest(ctx, M, N & 0xFFFF, K, A, B, D, (N >> 30) & 1));
 #endif
 }
 

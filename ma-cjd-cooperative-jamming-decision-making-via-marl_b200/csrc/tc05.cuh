@@ -146,6 +146,33 @@ __device__ __forceinline__ void reg_fence(float (&v)[N]) {
   for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]));
 }
 
+// 16 lanes x 256 bit x2: 16 consecutive columns of the 16 lanes starting at the warp's lane base,
+// spread over all 32 threads like an m16n8 accumulator fragment: for column group i (8 columns),
+// thread t holds v[4i+0..1] = (lane t/4, columns 8i + 2 (t%4) + {0,1}) and
+// v[4i+2..3] = (lane t/4 + 8, same columns).
+__device__ __forceinline__ void tmem_ld_16x256b_x2_nowait(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// x4: 32 consecutive columns, 16 registers (column group i = v[4i..4i+3])
+__device__ __forceinline__ void tmem_ld_16x256b_x4_nowait(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // fast transcendental forms (MUFU ex2 / rcp): |error| ~1e-6 absolute on sigmoid / tanh
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
@@ -156,6 +183,7 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2
 struct TcTestArgs {
   const float* A; const float* B; float* D;
   int M, N, K;
+  int ld_shape;    // 0: tcgen05.ld.32x32b (thread = lane), 1: tcgen05.ld.16x256b (fragment layout, M = 64)
 };
 
 __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const TcTestArgs a) {
@@ -205,6 +233,23 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const TcTestAr
   mbar_wait(&bar, 0);
   fence_after_sync();
 
+  if (a.ld_shape == 1) {
+    // fragment-layout read of the 16 valid lanes of this warp's quarter (M = 64 accumulators)
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[8];
+      tmem_ld_16x256b_x2_nowait(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      reg_fence(v);
+      for (int i = 0; i < 2; ++i)
+        for (int hr = 0; hr < 2; ++hr)
+          for (int j = 0; j < 2; ++j)
+            a.D[(size_t)(warp * 16 + (lane >> 2) + 8 * hr) * N + c0 + 8 * i + 2 * (lane & 3) + j] = v[4 * i + 2 * hr + j];
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    return;
+  }
   // epilogue: warp w owns TMEM lanes 32w..32w+31
   const int row = (M == 128) ? tid : (warp * 16 + lane);
   const bool has_row = (M == 128) || (lane < 16);
@@ -219,14 +264,16 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_selftest_kernel(const TcTestAr
   if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-inline int tc_gemm_selftest(const macjd_ctx* ctx, int M, int N, int K, const float* A, const float* B, float* D) {
+inline int tc_gemm_selftest(const macjd_ctx* ctx, int M, int N, int K, const float* A, const float* B, float* D,
+                            int ld_shape = 0) {
   if (!ctx || !A || !B || !D) return MACJD_ERR_INVALID_ARG;
   if ((M != 64 && M != 128) || N < 16 || N > 256 || N % 16 || K < 8 || K % 8) return MACJD_ERR_UNSUPPORTED;
   const size_t smem = (size_t)2 * (M + N) * K * sizeof(float);
   if (smem > 200 * 1024) return MACJD_ERR_UNSUPPORTED;
   if (cudaFuncSetAttribute(tc_gemm_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return MACJD_ERR_CUDA;
-  TcTestArgs a{A, B, D, M, N, K};
+  if (ld_shape == 1 && M != 64) return MACJD_ERR_UNSUPPORTED;
+  TcTestArgs a{A, B, D, M, N, K, ld_shape};
   tc_gemm_selftest_kernel<<<1, 128, smem, (cudaStream_t)ctx->stream>>>(a);
   return MACJD_OK;
 }
