@@ -28,6 +28,7 @@ class BasicMAC:
         self.seed = int(getattr(args, "seed", 0) or 0)
         self._rng_step = 0
         self.last_q_chosen = None
+        self._sel_cache = None
 
     # ------------------------------------------------------------------ acting
     def select_actions(self, obs_batch, avail_actions_batch, t_env, test_mode=False, *, u_eps=None, rand_actions=None):
@@ -41,6 +42,12 @@ class BasicMAC:
         if self.hidden_states.device != dev:
             self.hidden_states = self.hidden_states.to(dev)
         eps = self.action_selector.anneal(t_env, test_mode)
+        self._rng_step += 1
+        fast = self._select_fast(obs_batch, avail_actions_batch, B, M, eps, test_mode) \
+            if (u_eps is None and rand_actions is None) else None
+        if fast is not None:
+            return fast
+        self._rng_step -= 1
         obs = obs_batch.reshape(1, M, self.input_shape)
         avail = avail_actions_batch.reshape(1, M, -1) if avail_actions_batch is not None else None
         self._rng_step += 1
@@ -51,6 +58,32 @@ class BasicMAC:
         actions = out["actions"][0].to(torch.int64).view(B, self.n_agents, 1)
         power = out["power"][0].view(B, self.n_agents, 1)
         return actions, power
+
+    def _select_fast(self, obs, avail, B, M, eps, test_mode):
+        """Steady-state path: when the caller keeps handing in the same device buffers (a rollout
+        loop does), the launch struct and the output tensors are cached and a call costs one ctypes
+        invocation.  Falls back (returns None) for anything unusual."""
+        from .. import _native as N
+        if not (torch.is_tensor(obs) and torch.is_tensor(avail) and obs.device == self.device and avail.device == self.device
+                and obs.dtype == torch.float32 and avail.dtype == torch.uint8 and obs.is_contiguous() and avail.is_contiguous()):
+            return None
+        key = (M, obs.data_ptr(), avail.data_ptr(), self.hidden_states.data_ptr(), self.agent.path)
+        c = self._sel_cache
+        if c is None or c["key"] != key:
+            dev = self.device
+            out = {"actions": torch.empty(M, dtype=torch.int32, device=dev), "power": torch.empty(M, dtype=torch.float32, device=dev),
+                   "q_chosen": torch.empty(M, dtype=torch.float32, device=dev)}
+            io = N.AgentIO(n_rows=M, n_steps=1, obs=obs.data_ptr(), hidden=self.hidden_states.data_ptr(), hidden_zero_init=0,
+                           test_mode=0, tile_rows=0, path=self.agent.path, avail=avail.data_ptr(), epsilon=0.0, rng_step=0,
+                           seed=self.seed & 0xFFFFFFFFFFFFFFFF, actions=out["actions"].data_ptr(),
+                           power=out["power"].data_ptr(), q_chosen=out["q_chosen"].data_ptr())
+            c = self._sel_cache = {"key": key, "io": io, "out": out, "keep": (obs, avail)}
+        io = c["io"]
+        io.epsilon, io.rng_step, io.test_mode = float(eps), self._rng_step & 0xFFFFFFFF, int(test_mode)
+        self.agent.lib().call("macjd_agent_forward", self.agent._ctx(), self.agent.packed().cstruct(), io)
+        out = c["out"]
+        self.last_q_chosen = out["q_chosen"]
+        return out["actions"].to(torch.int64).view(B, self.n_agents, 1), out["power"].clone().view(B, self.n_agents, 1)
 
     def forward(self, agent_inputs_reshaped, hidden_states):
         """mac.py:168-187 -> (h_out [M, H], continuous_params_all [M, A])."""

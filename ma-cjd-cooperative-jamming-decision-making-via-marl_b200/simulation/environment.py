@@ -202,13 +202,26 @@ class ElectromagneticEnvironment:
         return self.get_obs(), reward, bool(self.terminated[0].item()), info
 
     def _jammer_action_details(self, act_d):
-        """The `jammer_actions` debugging list of environment.py:288-295 (shim mode only)."""
+        """The `jammer_actions` debugging list of environment.py:288-295 (shim mode only):
+        one entry per action that actually radiated at a radar (valid index, power > 0,
+        distance > 1e-6), with the received jamming power of core/jammer.py:73-98 (host arithmetic
+        on the float64 scenario tables; not on the hot path)."""
         out = []
+        tab = self.tables.data[:, 0]
+        R, J = self.num_radars, self.num_jammers
         power = self.jam_power[:, 0].double().cpu().numpy()
         for i, T in enumerate(act_d):
-            if 1 <= T <= 2 * self.num_radars and power[i] > 0:
-                out.append({"jammer_idx": i, "target_idx": int((T + 1) // 2 - 1), "type": int(T % 2),
-                            "power": float(power[i])})
+            if not (1 <= T <= 2 * R and power[i] > 0):
+                continue
+            tgt = int((T + 1) // 2 - 1)
+            jr, rr = 16 * R + 8 * i, 16 * tgt
+            dist = float(np.hypot(tab[jr + 4] - tab[rr + 10], tab[jr + 5] - tab[rr + 11]))
+            if dist <= 1e-6:
+                continue
+            den = max(1e-9, dist ** 2) * tab[jr + 1] * tab[jr + 2] * max(1e-9, tab[jr + 3])
+            prj = 0.0 if den <= 1e-18 else max(0.0, max(0.0, power[i]) * tab[jr + 0] * tab[rr + 2] / den)
+            out.append({"jammer_idx": i, "target_idx": tgt, "type": int(T % 2), "power": float(power[i]),
+                        "received_power": float(prj)})
         return out
 
     def get_state(self):

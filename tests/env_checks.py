@@ -117,6 +117,9 @@ def check_shim_types(make_single_env):
         assert set(info) == {"radar_pds", "radar_states", "snr_no_jamming", "snr_with_jamming", "r_d", "r_p", "r_j", "jammer_actions"}
         assert [s_["is_tracking"] for s_ in info["radar_states"]] == [True, False]
         _, reward, _, info = env.step([(4, .3), (4, .9)], noise=[.2, .05, .5, .5])
+        ja = info["jammer_actions"]
+        assert [a["jammer_idx"] for a in ja] == [0, 1] and all(a["type"] == 0 and a["target_idx"] == 1 for a in ja)
+        assert all(set(a) == {"jammer_idx", "target_idx", "type", "power", "received_power"} for a in ja)
         np.testing.assert_allclose(reward, -0.3280000000009998, rtol=1e-7)
         np.testing.assert_allclose(info["r_j"], 0.999999999999, rtol=1e-6)
         _, reward, _, _ = env.step([(1, 0.0), (2, 1e-9)], noise=[.2, .2, .9, 0.0])

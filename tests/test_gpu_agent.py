@@ -83,3 +83,27 @@ def test_tensor_core_path_matches_simt_path(M, T):
     assert decidable.float().mean() > 0.9
     assert torch.equal(a["actions"][decidable], b["actions"][decidable])
     torch.testing.assert_close(b["power"][decidable], a["power"][decidable], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["c1"])
+def test_tensor_core_path_vs_reference_golden(name):
+    """The tcgen05 path against the reference's recorded outputs, with its stated looser bound:
+    realistic observation magnitudes (hundreds) put pre-activations near 30-100, where the 3xTF32
+    split (2^-21 per product) shows; actions must still agree wherever the reference's own Q margin
+    exceeds 1e-3."""
+    g, args, sd = AC.load_agent_golden(name)
+    args.agent_kernel_path = 2
+    mac = AC.make_mac(args, sd, "cuda")
+    steps, B, Nn, O = g["obs"].shape
+    mac.hidden_states = torch.from_numpy(g["h0"].copy()).cuda()
+    for t in range(steps):
+        obs, avail = torch.from_numpy(g["obs"][t]).cuda(), torch.from_numpy(g["avail"][t]).cuda()
+        a_test, p_test = mac.select_actions(obs, avail, int(g["t_env"][t]), test_mode=True)
+        np.testing.assert_allclose(mac.hidden_states.cpu().numpy(), g["hidden"][t], rtol=2e-4, atol=2e-4)
+        qm = np.where(g["avail"][t].reshape(B * Nn, -1) != 0, g["q"][t], -np.inf)
+        decidable = (AC.argmax_margin(qm) > 1e-3).reshape(B, Nn, 1)
+        assert decidable.mean() > 0.7
+        np.testing.assert_array_equal(a_test.cpu().numpy()[decidable], g["actions_test"][t][decidable])
+        same = a_test.cpu().numpy() == g["actions_test"][t]
+        np.testing.assert_allclose(p_test.cpu().numpy()[same], g["power_test"][t][same], rtol=2e-4, atol=2e-5)
+        mac.hidden_states.copy_(torch.from_numpy(g["hidden"][t]))
