@@ -290,15 +290,16 @@ def main():
                                                   out=agent_out, path=1), kn) / kn
     bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
     tf32_peak = bf16_peak / 2.0
-    tr = traffic.get("agent_forward_tc_kernel") or {}
-    roofline = {"kernel": "agent_forward_tc_kernel", "bound": "tensor", "achieved": M * fpr / dt_agent / 1e12,
+    tr = traffic.get("agent_forward_tc2_kernel") or traffic.get("agent_forward_tc_kernel") or {}
+    roofline = {"kernel": "agent_forward_tc2_kernel", "bound": "tensor", "achieved": M * fpr / dt_agent / 1e12,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": M * fpr / dt_agent / 1e12 / tf32_peak,
                 "traffic": tr.get("dram_bytes_per_launch"), "flop_per_agent_step": fpr, "us_per_launch": dt_agent * 1e6,
                 "executed_tensor_tflops": 3 * M * fpr / dt_agent / 1e12,
                 "peak_source": ("TF32 dense = MEASURED_PEAKS.json bf16_tflops / 2 (of measured)" if "bf16_tflops" in peaks
                                 else "TF32 dense = fallback 1590 / 2 (of fallback)"),
                 "note": "achieved counts algorithmic FLOPs once; the 3xTF32 split executes 3x that on the tensor pipe. "
-                        "64-row tiles issue M=64,N=64,K=8 MMAs (~52 cycles each, tools/tc_mma_rate.py): issue-bound, not at the roofline",
+                        "CTA pairs issue M=128,N=128,K=8 cta_group::2 MMAs: ~52 cycles each from one issuing thread against 32 at the pipe's peak "
+                        "(tools/tc_mma_rate.py), and MMA phases alternate with epilogue phases: issue- and dependency-bound, not at the roofline",
                 "simt_kernel": {"kernel": "agent_forward_kernel<256>", "bound": "fp32", "us_per_launch": dt_simt * 1e6,
                                 "achieved": M * fpr / dt_simt / 1e12, "peak": fp32_peak,
                                 "frac": M * fpr / dt_simt / 1e12 / fp32_peak,
@@ -310,34 +311,26 @@ def main():
                     "us_per_launch": dt_env * 1e6,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
 
-    # ---- e2e: the reference-facing host API (numpy in pinned memory in, numpy out) per step
-    obs_h = torch.empty(n_envs, N_AGENTS, OBS, dtype=torch.float32).pin_memory()
-    avail_h = torch.empty(n_envs, N_AGENTS, N_ACTIONS, dtype=torch.uint8).pin_memory()
-    act_h = torch.empty(n_envs, N_AGENTS, dtype=torch.int32).pin_memory()
-    pow_h = torch.empty(n_envs, N_AGENTS, dtype=torch.float32).pin_memory()
-    rew_h = torch.empty(n_envs, dtype=torch.float32).pin_memory()
-    term_h = torch.empty(n_envs, dtype=torch.uint8).pin_memory()
-    obs_h.copy_(env.get_obs()); avail_h.copy_(env.get_avail_actions())
-    obs_d = torch.empty_like(obs_h, device=device); avail_d = torch.empty_like(avail_h, device=device)
-    act_d = torch.empty_like(act_h, device=device); pow_d = torch.empty_like(pow_h, device=device)
+    # ---- e2e: the reference-facing host API (host buffers in, host buffers out) per step: what the
+    # reference's runner loop does -- mac.select_actions(obs) -> env.step(actions) -- through the two
+    # host-buffer C-ABI calls (copies inside the call, stream drained on return)
+    hb = env.host_buffers()                                    # pinned: act_d, act_p, reward, terminated, obs
+    avail_h = torch.ones(n_envs, N_AGENTS, N_ACTIONS, dtype=torch.uint8).pin_memory()
+    env.reset()
+    hb["obs"].copy_(env.get_obs())
     mac.init_hidden(n_envs)
     t_env = [0]
 
     def host_step():
-        obs_d.copy_(obs_h, non_blocking=True)                 # H2D: this step's observations + masks
-        avail_d.copy_(avail_h, non_blocking=True)
-        a, p = mac.select_actions(obs_d, avail_d, t_env[0])
-        act_h.copy_(a.view(n_envs, N_AGENTS), non_blocking=True)     # D2H: actions for the host-side runner
-        pow_h.copy_(p.view(n_envs, N_AGENTS), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        act_d.copy_(act_h, non_blocking=True)                 # H2D: env.step(actions) takes host actions
-        pow_d.copy_(pow_h, non_blocking=True)
-        env.step_device(act_d, pow_d)
-        obs_h.copy_(env.obs, non_blocking=True)               # D2H: next obs, reward, terminated
-        rew_h.copy_(env.reward, non_blocking=True)
-        term_h.copy_(env.terminated, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # H2D obs + avail, fused agent step, D2H actions + power (written straight into the env's action buffers)
+        mac.select_actions_host(hb["obs"], avail_h, t_env[0], actions_out=hb["act_d"], power_out=hb["act_p"])
+        # H2D actions + power, fused env step, D2H reward + terminated + next obs
+        env.step_host(hb)
         t_env[0] += 1
+        if t_env[0] % T == 0:
+            env.reset()
+            hb["obs"].copy_(env.get_obs())
+            mac.init_hidden(n_envs)
 
     for _ in range(W):
         host_step()
@@ -347,11 +340,12 @@ def main():
         host_step()
     torch.cuda.synchronize()
     dt_e2e = reduce_max(time.perf_counter() - t0)
-    h2d = obs_h.numel() * 4 + avail_h.numel() + act_h.numel() * 4 + pow_h.numel() * 4
-    d2h = act_h.numel() * 4 + pow_h.numel() * 4 + obs_h.numel() * 4 + rew_h.numel() * 4 + term_h.numel()
+    h2d = hb["obs"].numel() * 4 + avail_h.numel() + hb["act_d"].numel() * 4 + hb["act_p"].numel() * 4
+    d2h = hb["act_d"].numel() * 4 + hb["act_p"].numel() * 4 + hb["obs"].numel() * 4 + hb["reward"].numel() * 4 + hb["terminated"].numel()
     e2e = {"value": world * M * K / dt_e2e, "unit": "env-agent steps/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": dt_e2e / K * 1e3,
-           "api": "BasicMAC.select_actions + ElectromagneticEnvironment.step_device with pinned host buffers"}
+           "api": "BasicMAC.select_actions_host + ElectromagneticEnvironment.step_host (C-ABI macjd_agent_act_host + "
+                  "macjd_env_step_host): pinned host buffers in and out, two stream drains per step"}
 
     # ---- learner: sample + train (B=32 episodes x T=100), all-reduce of the gradient bucket when N > 1
     np.random.seed(1 + rank)

@@ -120,6 +120,24 @@ MACJD_API int macjd_env_step(const macjd_ctx* ctx, const macjd_env_tables* tab, 
 /* environment.py:208-219  reset(): zero step_count, write state / obs / avail. */
 MACJD_API int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io);
 
+/* Host-buffer form of step(): what the reference's Python loop hands over and gets back
+ * (environment.py:221 `actions` list in; environment.py:462-477 reward, terminated and the next
+ * observations out).  `io` names DEVICE staging buffers exactly as for macjd_env_step (act_d,
+ * act_p, reward, terminated, obs ... must be set); the call copies the host actions in on
+ * ctx->stream, launches the step, copies the requested outputs back and returns after the
+ * stream has drained.  Host pointers may be pageable or pinned (pinned: truly asynchronous
+ * copies); NULL outputs are skipped. */
+typedef struct macjd_env_host {
+  const int32_t* act_d;     /* host [n_envs][J]                                       */
+  const float* act_p;       /* host [n_envs][J]                                       */
+  float* reward;            /* host [n_envs], optional                                */
+  uint8_t* terminated;      /* host [n_envs], optional                                */
+  float* obs;               /* host [n_envs][J][S], optional                          */
+  float* state;             /* host [n_envs][S], optional                             */
+} macjd_env_host;
+MACJD_API int macjd_env_step_host(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io,
+                                  const macjd_env_host* host);
+
 /* ===================================================================== agent step
  * Replaces core/mac.py:59-198 (BasicMAC.select_actions / forward / init_hidden),
  * core/networks.py:16-180 (RNNAgent: fc1 -> GRUCell, actor MLP, MP-DQN Q-head evaluated
@@ -174,7 +192,10 @@ typedef struct macjd_agent_io {
   int32_t test_mode;          /* != 0: greedy only (action_selectors.py:59-61)          */
   int32_t tile_rows;          /* rows per CTA: 0 = auto, or 8/16/32/64 (tuning knob)     */
   int32_t path;               /* 0 = auto (tensor cores when tc_chunks is given and the dims
-                                 allow), 1 = FP32 SIMT, 2 = tcgen05 3xTF32 (error if unsupported) */
+                                 allow), 1 = FP32 SIMT, 2 = tcgen05 3xTF32 with one CTA per 64 rows,
+                                 3 = tcgen05 3xTF32 with CTA pairs (cta_group::2, 128 rows per
+                                 pair); 2 and 3 return MACJD_ERR_UNSUPPORTED if the dims do
+                                 not fit */
   float* hidden_seq;          /* [T][M][H] h_t after every step, optional               */
   float* q_all;               /* [T][M][A] Q(s, a, P_a) for every action, optional      */
   float* params_all;          /* [T][M][A] actor outputs P_a, optional                  */
@@ -196,6 +217,22 @@ typedef struct macjd_agent_io {
 /* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);
  * Q_a <- Qhead(h, a, P_a) for all a; masked epsilon-greedy / argmax / gathers. */
 MACJD_API int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io);
+
+/* Host-buffer form of BasicMAC.select_actions (core/mac.py:59-187: numpy observations and
+ * availability masks in, chosen discrete actions and their power levels out).  `io` is a
+ * single-step (n_steps = 1) macjd_agent_io whose obs / avail / actions / power name DEVICE
+ * staging buffers; the call copies host obs (and avail) in on ctx->stream, launches the
+ * fused step, copies actions / power (and q_chosen when both sides give it) back and returns
+ * after the stream has drained.  The recurrent state stays on the device (io->hidden). */
+typedef struct macjd_act_host {
+  const float* obs;         /* host [M][O]                                            */
+  const uint8_t* avail;     /* host [M][A], optional (NULL: io->avail is used as is)  */
+  int32_t* actions;         /* host [M]                                               */
+  float* power;             /* host [M]                                               */
+  float* q_chosen;          /* host [M], optional                                     */
+} macjd_act_host;
+MACJD_API int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io,
+                                   const macjd_act_host* host);
 
 /* ===================================================================== replay ring
  * Replaces the data movement of utils/replay_buffer.py:78-214 (store_episode / sample) and

@@ -56,6 +56,15 @@ class AgentIO(C.Structure):
                 ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p)]
 
 
+class ActHost(C.Structure):
+    _fields_ = [("obs", c_void_p), ("avail", c_void_p), ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p)]
+
+
+class EnvHost(C.Structure):
+    _fields_ = [("act_d", c_void_p), ("act_p", c_void_p), ("reward", c_void_p), ("terminated", c_void_p),
+                ("obs", c_void_p), ("state", c_void_p)]
+
+
 class CopyDesc(C.Structure):
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("src_ep_stride", c_int64), ("src_t_stride", c_int64),
                 ("dst_ep_stride", c_int64), ("dst_t_stride", c_int64), ("n_t", c_int32), ("inner_bytes", c_int32),
@@ -93,7 +102,8 @@ class OptTensors(C.Structure):
 
 
 # order must match macjd_abi_sizeof() in csrc/macjd_api.cu
-ABI_STRUCTS = [Ctx, EnvTables, EnvIO, AgentWeights, AgentIO, CopyDesc, MixerDims, MixerParams, QheadDims, OptTensors]
+ABI_STRUCTS = [Ctx, EnvTables, EnvIO, AgentWeights, AgentIO, CopyDesc, MixerDims, MixerParams, QheadDims, OptTensors,
+               ActHost, EnvHost]
 
 
 class MacjdError(RuntimeError):
@@ -158,6 +168,8 @@ class NativeLib:
         "macjd_env_step": (Ctx, EnvTables, EnvIO),
         "macjd_env_reset": (Ctx, EnvTables, EnvIO),
         "macjd_agent_forward": (Ctx, AgentWeights, AgentIO),
+        "macjd_agent_act_host": (Ctx, AgentWeights, AgentIO, ActHost),
+        "macjd_env_step_host": (Ctx, EnvTables, EnvIO, EnvHost),
     }
 
     def _check_abi(self):

@@ -7,6 +7,7 @@ the selector come from the kernel's Philox stream, or can be injected (``u_eps``
 """
 from __future__ import annotations
 
+import copy
 import os
 
 import numpy as np
@@ -29,6 +30,15 @@ class BasicMAC:
         self._rng_step = 0
         self.last_q_chosen = None
         self._sel_cache = None
+        self._host_cache = None
+
+    def __deepcopy__(self, memo):
+        # launch-struct caches hold raw addresses of this controller's buffers: never copied
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, None if k in ("_sel_cache", "_host_cache") else copy.deepcopy(v, memo))
+        return new
 
     # ------------------------------------------------------------------ acting
     def select_actions(self, obs_batch, avail_actions_batch, t_env, test_mode=False, *, u_eps=None, rand_actions=None):
@@ -84,6 +94,48 @@ class BasicMAC:
         out = c["out"]
         self.last_q_chosen = out["q_chosen"]
         return out["actions"].to(torch.int64).view(B, self.n_agents, 1), out["power"].clone().view(B, self.n_agents, 1)
+
+    def select_actions_host(self, obs, avail, t_env, test_mode=False, *, actions_out=None, power_out=None):
+        """mac.py:59-166 for callers that live on the host, as the reference's runner does: ``obs``
+        float32 [B, N, obs] and ``avail`` uint8 [B, N, A] are contiguous CPU tensors / numpy arrays
+        (page-locked memory makes the copies asynchronous); returns the chosen discrete actions int32
+        [B, N] and power float32 [B, N] in host memory (``actions_out`` / ``power_out`` when given).
+        One C call: copies in, fused step, copies out, stream drained on return
+        (include/macjd.h: macjd_agent_act_host).  The recurrent state stays on the device."""
+        from .. import _native as N
+        B = obs.shape[0]
+        M = B * self.n_agents
+        dev = self.device
+        if self.hidden_states is None or self.hidden_states.shape[0] != M:
+            self.init_hidden(batch_size=B)
+        if self.hidden_states.device != dev:
+            self.hidden_states = self.hidden_states.to(dev)
+        key = (M, N.ptr(obs), N.ptr(avail), N.ptr(actions_out), N.ptr(power_out), self.hidden_states.data_ptr(), self.agent.path)
+        c = self._host_cache
+        if c is None or c["key"] != key:
+            A = self.args.n_actions
+            pin = dev.type == "cuda"
+            if actions_out is None:
+                actions_out = torch.zeros(B, self.n_agents, dtype=torch.int32, pin_memory=pin)
+            if power_out is None:
+                power_out = torch.zeros(B, self.n_agents, dtype=torch.float32, pin_memory=pin)
+            st = {"obs": torch.empty(M, self.input_shape, dtype=torch.float32, device=dev),
+                  "avail": torch.ones(M, A, dtype=torch.uint8, device=dev),
+                  "actions": torch.empty(M, dtype=torch.int32, device=dev), "power": torch.empty(M, dtype=torch.float32, device=dev),
+                  "q_chosen": torch.empty(M, dtype=torch.float32, device=dev)}
+            io = N.AgentIO(n_rows=M, n_steps=1, obs=st["obs"].data_ptr(), hidden=self.hidden_states.data_ptr(), hidden_zero_init=0,
+                           test_mode=0, tile_rows=0, path=self.agent.path, avail=st["avail"].data_ptr(), epsilon=0.0, rng_step=0,
+                           seed=self.seed & 0xFFFFFFFFFFFFFFFF, actions=st["actions"].data_ptr(),
+                           power=st["power"].data_ptr(), q_chosen=st["q_chosen"].data_ptr())
+            hs = N.ActHost(obs=N.ptr(obs), avail=N.ptr(avail), actions=N.ptr(actions_out), power=N.ptr(power_out), q_chosen=None)
+            c = self._host_cache = {"key": key, "io": io, "host": hs, "stage": st, "keep": (obs, avail, actions_out, power_out)}
+        eps = self.action_selector.anneal(t_env, test_mode)
+        self._rng_step += 1
+        io = c["io"]
+        io.epsilon, io.rng_step, io.test_mode = float(eps), self._rng_step & 0xFFFFFFFF, int(test_mode)
+        self.agent.lib().call("macjd_agent_act_host", self.agent._ctx(), self.agent.packed().cstruct(), io, c["host"])
+        self.last_q_chosen = c["stage"]["q_chosen"]
+        return c["keep"][2], c["keep"][3]
 
     def forward(self, agent_inputs_reshaped, hidden_states):
         """mac.py:168-187 -> (h_out [M, H], continuous_params_all [M, A])."""

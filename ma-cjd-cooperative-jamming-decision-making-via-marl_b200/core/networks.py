@@ -180,8 +180,9 @@ class RNNAgent(nn.Module):
             nn.Linear(self.rnn_hidden_dim, 1))
         self._packed = PackedAgentWeights(self)
         self._lib = _lib
-        # kernel path: 1 = FP32 SIMT (default: the parity-exact path), 2 = tcgen05 3xTF32 (needs
-        # hidden = actor_hidden = 128), 0 = let the library pick the tensor-core path when it can
+        # kernel path: 1 = FP32 SIMT (default: the parity-exact path), 2 / 3 = tcgen05 3xTF32 with one
+        # CTA per 64 rows / with CTA pairs (needs hidden = actor_hidden = 128), 0 = let the library
+        # pick a tensor-core kernel when it can
         self.path = int(getattr(args, "agent_kernel_path", 1))
 
     # ---- native plumbing

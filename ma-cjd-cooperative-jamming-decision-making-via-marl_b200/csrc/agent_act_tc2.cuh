@@ -1,0 +1,607 @@
+// Fused agent step on tcgen05 with CTA pairs (cta_group::2): 128 agent rows per 2-CTA cluster.
+//
+// Same computation as agent_forward_tc_kernel (agent_act_tc.cuh); what changes is how the
+// tensor cores are driven.  Measurements on the B200 (tools/tc_mma_rate.py) show that one
+// tcgen05.mma costs the same cycles for M = 64 and M = 128, so a CTA that owns 64 rows wastes
+// half the pipe -- but 128 rows of TF32 hi + lo operand tiles do not fit one SM's shared
+// memory.  A CTA pair solves both: each CTA keeps its own 64 rows of operands and only HALF of
+// every weight chunk (the B operand of a 2-SM MMA is split across the pair), the leader CTA
+// issues one M = 128, N = 128 tcgen05.mma.cta_group::2 per k-step and split product for both,
+// and the weight bytes streamed from L2 per row halve.
+//
+// Per CTA (rank r of the pair): warps 0-3 epilogue, warp 4 weight stream (its half of each
+// chunk), warp 5 = MMA issuer (leader) or stage relay (peer: tells the leader when the peer's
+// half has landed).  Accumulators: 2-SM M = 128 layout -- this CTA's row i on TMEM lane i for
+// output units 0-63 and on lane 64 + i for units 64-127 (same columns) -- so epilogue warp w
+// owns rows 32 (w & 1) .. +31 and units 64 (w >> 1) .. +63 with plain 32x32b loads; row sums
+// (actor head, Q tail) are combined across the two unit halves through shared memory.
+// Cross-CTA events use cluster-scope mbarrier arrives (mapa) and multicast tcgen05.commit.
+#pragma once
+#include "agent_act_tc.cuh"
+
+#ifndef MACJD_TEST_HOST_EMULATION
+namespace macjd {
+namespace tc {
+
+constexpr int kT2Stages = 2;
+constexpr int kT2HalfBytes = kTcH * kTcKc * 4 / 2;        // this CTA's 64 weight rows of one hi (or lo) chunk
+constexpr int kT2SubBytes = 2 * kT2HalfBytes;              // hi half + lo half of one chunk
+constexpr int kT2StageBytes = 2 * kT2SubBytes;             // a stage holds two consecutive chunks: one barrier round trip per 64 k
+constexpr int kT2Threads = 192;
+constexpr uint32_t kT2ColA1 = 0, kT2ColFc1 = 64, kT2ColA2 = 128;
+constexpr uint32_t kT2ColR = 0, kT2ColZ = 64, kT2ColIn = 128, kT2ColHn = 192, kT2ColQ = 0;
+constexpr uint32_t kT2TmemCols = 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 raddr;\n\t"
+      "mapa.shared::cluster.u32 raddr, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [raddr];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// bounded wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void mma_tf32_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of this thread -> the mbarrier at this offset in both CTAs
+__device__ __forceinline__ void mma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b16 mask;\n\t"
+      "mov.b16 mask, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mask;\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+// One ring stage of the issuer's schedule: which activation tile, where its two sub-chunks accumulate,
+// and which hand-shakes surround it.
+struct T2Stage {
+  uint32_t ahi, alo, sbo, koff0, koff1, d0, d1;
+  uint8_t first0, first1;
+  uint8_t pre;      // 1: wait for the observation block, 2: wait for the epilogue's activation tile
+  uint8_t post;     // bit 0: release the observation block, bit 1: accumulators ready for the epilogue
+};
+
+struct T2Smem {
+  float b0hi[kTcRows * kTcH], b0lo[kTcRows * kTcH];        // observation block (first 8 KB) -> a1 -> xf
+  float hhi[kTcRows * kTcH], hlo[kTcRows * kTcH];            // h -> h'
+  unsigned char wst[kT2Stages][kT2StageBytes];
+  TcConst c;
+  float red[2][8][kTcRows];                 // partial row sums of the two unit halves
+  T2Stage stage_tab[24];                    // nxc + 16 stages per step (obs_dim <= 256)
+  uint64_t w_full[kT2Stages], w_empty[kT2Stages];
+  uint64_t x_full, x_empty, d_ready, a_ready;
+  uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent_forward_tc2_kernel(const AgentArgs a) {
+  extern __shared__ __align__(1024) unsigned char tc_raw[];
+  T2Smem& S = *reinterpret_cast<T2Smem*>(tc_raw);
+  const macjd_agent_weights& W = a.w;
+  const macjd_agent_io& io = a.io;
+  const int O = W.obs_dim, Op = W.obs_pad, A = W.n_actions;
+  constexpr int H = kTcH;
+  const int M = io.n_rows, T = io.n_steps;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  TC_CTA_STAMP(0);
+  TC_STAMP_ONCE(20);
+  const int row0 = blockIdx.x * kTcRows;
+  const int valid = max(0, min(kTcRows, M - row0));
+  float* Ps = reinterpret_cast<float*>(tc_raw + sizeof(T2Smem));     // [A][64]
+  float* Qs = Ps + (size_t)A * kTcRows;
+  const int nxc = Op / 32;
+  const int chunks_per_step = 2 * kTcChunksPerX * nxc + 8 * kTcChunksPerH;
+  const int supers_per_step = chunks_per_step / 2;
+  float* const xhi = S.b0hi;   // the observation block lives in b0 until E1 overwrites it with a1
+  float* const xlo = S.b0lo;
+
+  warm_weights_l2(W.tc_chunks, chunks_per_step, kT2Threads);
+
+  if (tid == 0) {
+    // the leader's "full" needs its own copy armed and the peer's "my half has landed" relay
+    for (int s = 0; s < kT2Stages; ++s) { mbar_init(&S.w_full[s], rank == 0 ? 2 : 1); mbar_init(&S.w_empty[s], 1); }
+    mbar_init(&S.x_full, 256); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 256);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < H; i += kT2Threads) {
+    S.c.gate_b[i] = make_float4(W.brz[i], W.brz[H + i], W.bin[i], W.bhn[i]);
+    S.c.q_c[i] = make_float4(W.bq1[i], W.w1p[i], W.w2[i], 0.f);
+    S.c.ba1[i] = W.ba1[i]; S.c.ba2[i] = W.ba2[i]; S.c.bfc1[i] = W.bfc1[i];
+    float w3[8], wq[8];
+    for (int j = 0; j < 8; ++j) {
+      w3[j] = j < A ? W.wa3t[(size_t)i * A + j] : 0.f;
+      wq[j] = j < A ? W.w1a[(size_t)j * H + i] : 0.f;
+    }
+    S.c.wa3t[2 * i] = make_float4(w3[0], w3[1], w3[2], w3[3]);
+    S.c.wa3t[2 * i + 1] = make_float4(w3[4], w3[5], w3[6], w3[7]);
+    S.c.w1a[2 * i] = make_float4(wq[0], wq[1], wq[2], wq[3]);
+    S.c.w1a[2 * i + 1] = make_float4(wq[4], wq[5], wq[6], wq[7]);
+  }
+  if (tid < 8) S.c.ba3[tid] = tid < A ? W.ba3[tid] : 0.f;
+  __syncthreads();
+  TC_STAMP_ONCE(21);
+  cluster_sync_all();                         // both CTAs' barriers exist before any remote arrive
+  TC_STAMP_ONCE(22);
+  if (warp == 5) tmem_alloc_2sm(&S.tmem_base, kT2TmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+  TC_STAMP_ONCE(23);
+
+  if (warp == 4) {
+    // =========================================================== weight stream: this CTA's half of every chunk
+    if (lane == 0) {
+      const char* wsrc = reinterpret_cast<const char*>(W.tc_chunks);
+      uint32_t empty_par = 0;
+      int s = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int L = 0; L < supers_per_step; ++L) {
+          if (t > 0 || L >= kT2Stages) { mbar_wait_cluster(&S.w_empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
+          const char* src = wsrc + (size_t)L * 2 * kTcChunkBytes + (size_t)rank * kT2HalfBytes;
+          mbar_expect_tx(&S.w_full[s], kT2StageBytes);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            bulk_g2s(S.wst[s] + sub * kT2SubBytes, src + sub * kTcChunkBytes, kT2HalfBytes, &S.w_full[s]);               // hi
+            bulk_g2s(S.wst[s] + sub * kT2SubBytes + kT2HalfBytes, src + sub * kTcChunkBytes + kTcChunkBytes / 2,
+                     kT2HalfBytes, &S.w_full[s]);                                                                       // lo
+          }
+          s ^= 1;
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && rank != 0) {
+      // =========================================================== peer: relay "my half has landed"
+      const long long total = (long long)supers_per_step * T;
+      uint32_t full_par = 0;
+      int s = 0;
+      for (long long L = 0; L < total; ++L) {
+        mbar_wait(&S.w_full[s], (full_par >> s) & 1u);
+        full_par ^= 1u << s;
+        mbar_arrive_cluster(&S.w_full[s], 0);
+        s ^= 1;
+      }
+    } else if (lane == 0) {
+      // =========================================================== leader: MMA issue for the pair
+      // One compact loop over a table of stages (a stage = two consecutive 32-k weight chunks against
+      // one activation tile).  Straight-line code for the 408 MMAs of a step would be ~100 KB of
+      // instructions executed once per step: after an L2 flush the issuer then runs at instruction-fetch
+      // speed (measured: +23 us per cold step).
+      const uint32_t idesc = umma_idesc_tf32(2 * kTcRows, H);
+      const uint32_t bh = smem_u32(S.b0hi), bl = smem_u32(S.b0lo), hh = smem_u32(S.hhi), hl = smem_u32(S.hlo);
+      const uint32_t w0 = smem_u32(S.wst[0]);
+      for (int L = 0; L < supers_per_step; ++L) {
+        T2Stage e;
+        if (L < nxc) {                       // [actor.0 | fc1] chunk pair of observation block L
+          e.ahi = bh; e.alo = bl; e.sbo = 32 * 32; e.koff0 = e.koff1 = 0;
+          e.d0 = kT2ColA1; e.d1 = kT2ColFc1; e.first0 = e.first1 = (L == 0);
+          e.pre = 1; e.post = 1 | (L == nxc - 1 ? 2 : 0);
+        } else {                             // K = 128 layers: 4 chunks = 2 stages each
+          const int j = (L - nxc) >> 1, hf = (L - nxc) & 1;
+          //                 actor.2   W_ir      W_hr     W_iz      W_hz     W_in       W_hn       q.0[:, :H]
+          const uint32_t dcol[8] = {kT2ColA2, kT2ColR, kT2ColR, kT2ColZ, kT2ColZ, kT2ColIn, kT2ColHn, kT2ColQ};
+          const bool use_h = (0xD4u >> j) & 1u;        // layers 2, 4, 6, 7 read h
+          const bool first = (0xEBu >> j) & 1u;        // layers 2 and 4 accumulate onto the W_i* product
+          e.ahi = use_h ? hh : bh; e.alo = use_h ? hl : bl; e.sbo = H * 32;
+          e.koff0 = (2 * hf) * kTcAStep; e.koff1 = (2 * hf + 1) * kTcAStep;
+          e.d0 = e.d1 = dcol[j]; e.first0 = first && hf == 0; e.first1 = 0;
+          e.pre = (hf == 0 && (j == 0 || j == 1 || j == 7)) ? 2 : 0;
+          e.post = (hf == 1 && (j == 0 || j == 6 || j == 7)) ? 2 : 0;
+        }
+        S.stage_tab[L] = e;
+      }
+      uint32_t full_par = 0, x_full_par = 0, a_ready_par = 0;
+      int s = 0;
+      for (int t = 0; t < T; ++t) {
+#ifdef MACJD_TC_PROFILE
+        int stamp = 33;
+#endif
+        for (int L = 0; L < supers_per_step; ++L) {
+          const T2Stage e = S.stage_tab[L];
+          if (e.pre == 1) { mbar_wait_cluster(&S.x_full, x_full_par); x_full_par ^= 1u; TC_STAMP(32); }
+          if (e.pre == 2) {
+            mbar_wait_cluster(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
+#ifdef MACJD_TC_PROFILE
+            TC_STAMP(stamp); ++stamp;
+#endif
+          }
+          mbar_wait_cluster(&S.w_full[s], (full_par >> s) & 1u);
+          full_par ^= 1u << s;
+          fence_after_sync();
+          const uint32_t wbase = w0 + (uint32_t)s * kT2StageBytes;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const uint32_t koff = sub ? e.koff1 : e.koff0;
+            const uint64_t dah = umma_smem_desc(e.ahi + koff, 128, e.sbo);
+            const uint64_t dal = umma_smem_desc(e.alo + koff, 128, e.sbo);
+            const uint64_t dbh = umma_smem_desc(wbase + sub * kT2SubBytes, 128, kTcKc * 32);
+            const uint64_t dbl = umma_smem_desc(wbase + sub * kT2SubBytes + kT2HalfBytes, 128, kTcKc * 32);
+            const uint32_t d = tmem + (sub ? e.d1 : e.d0);
+            const uint32_t first = sub ? e.first1 : e.first0;
+#pragma unroll
+            for (int ks = 0; ks < kTcKc / 8; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * 256) >> 4);
+              mma_tf32_ss_2sm(d, dah + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
+              mma_tf32_ss_2sm(d, dal + adv, dbh + adv, idesc, 1u);
+              mma_tf32_ss_2sm(d, dah + adv, dbl + adv, idesc, 1u);
+            }
+          }
+          mma_commit_2sm(&S.w_empty[s]);
+          if (e.post & 1u) mma_commit_2sm(&S.x_empty);
+          if (e.post & 2u) {
+            mma_commit_2sm(&S.d_ready);
+#ifdef MACJD_TC_PROFILE
+            TC_STAMP(stamp); ++stamp;
+#endif
+          }
+          s ^= 1;
+        }
+      }
+    }
+  } else {
+    // =========================================================== epilogue warps
+    const int half = warp >> 1;                      // which 64 output units of the row
+    const int r = (warp & 1) * 32 + lane;            // row within this CTA's tile
+    const int ub = half * 64;
+    const bool live = r < valid;
+    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t d_par = 0, x_empty_par = 0;
+
+    {
+      const bool have = io.hidden && !io.hidden_zero_init && live;
+      for (int k = ub; k < ub + 64; k += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (have) {
+          const float4 x = *reinterpret_cast<const float4*>(io.hidden + (size_t)(row0 + r) * H + k);
+          v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        }
+        store_split4(S.hhi, S.hlo, r, k, H, v);
+      }
+    }
+
+    for (int t = 0; t < T; ++t) {
+      const size_t tM = (size_t)t * M;
+      EP_STAMP(0);
+      for (int xc = 0; xc < nxc; ++xc) {
+        if (t > 0 || xc > 0) { mbar_wait_cluster(&S.x_empty, x_empty_par); x_empty_par ^= 1u; }
+        const float* obs = io.obs + (tM + row0 + r) * O;
+        for (int k = half * 16; k < half * 16 + 16; k += 4) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const int kk = xc * 32 + k + j; v[j] = (live && kk < O) ? __ldg(obs + kk) : 0.f; }
+          store_split4(xhi, xlo, r, k, 32, v);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        mbar_arrive_cluster(&S.x_full, 0);
+      }
+
+      // ---- E1: a1 = relu(D1 + b) -> B0
+      EP_STAMP(1);
+      mbar_wait_cluster(&S.d_ready, d_par); d_par ^= 1u;
+      fence_after_sync();
+      EP_STAMP(2);
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16_nowait(tl + kT2ColA1 + (uint32_t)c0, v);
+        tmem_ld_wait();
+        reg_fence(v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * q + j] + S.c.ba1[ub + c0 + 4 * q + j], 0.f);
+          store_split4(S.b0hi, S.b0lo, r, ub + c0 + 4 * q, H, o);
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      mbar_arrive_cluster(&S.a_ready, 0);
+      EP_STAMP(3);
+
+      // ---- E2: actor head;  E3: xf = relu(D3 + b) -> B0
+      mbar_wait_cluster(&S.d_ready, d_par); d_par ^= 1u;
+      fence_after_sync();
+      EP_STAMP(4);
+      {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+          tmem_ld16_nowait(tl + kT2ColA2 + (uint32_t)c0, v);
+          tmem_ld_wait();
+          reg_fence(v);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            const int u = ub + c0 + n;
+            const float a2 = fmaxf(v[n] + S.c.ba2[u], 0.f);
+            const float4 wl = S.c.wa3t[2 * u], wh = S.c.wa3t[2 * u + 1];
+            acc[0] = fmaf(a2, wl.x, acc[0]); acc[1] = fmaf(a2, wl.y, acc[1]);
+            acc[2] = fmaf(a2, wl.z, acc[2]); acc[3] = fmaf(a2, wl.w, acc[3]);
+            acc[4] = fmaf(a2, wh.x, acc[4]); acc[5] = fmaf(a2, wh.y, acc[5]);
+            acc[6] = fmaf(a2, wh.z, acc[6]); acc[7] = fmaf(a2, wh.w, acc[7]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) S.red[half][j][r] = acc[j];
+        epi_bar_sync();
+        if (half == 0)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < A) Ps[j * kTcRows + r] = sigmoid_fast(S.red[0][j][r] + S.red[1][j][r] + S.c.ba3[j]);
+      }
+      EP_STAMP(5);
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16_nowait(tl + kT2ColFc1 + (uint32_t)c0, v);
+        tmem_ld_wait();
+        reg_fence(v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * q + j] + S.c.bfc1[ub + c0 + 4 * q + j], 0.f);
+          store_split4(S.b0hi, S.b0lo, r, ub + c0 + 4 * q, H, o);
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      mbar_arrive_cluster(&S.a_ready, 0);
+      EP_STAMP(6);
+
+      // ---- E4: GRU gates -> h' (in place over h), global hidden outputs
+      mbar_wait_cluster(&S.d_ready, d_par); d_par ^= 1u;
+      fence_after_sync();
+      EP_STAMP(7);
+      for (int c0 = 0; c0 < 64; c0 += 8) {
+        float vr[8], vz[8], vi[8], vh[8];
+        tmem_ld8_nowait(tl + kT2ColR + (uint32_t)c0, vr);
+        tmem_ld8_nowait(tl + kT2ColZ + (uint32_t)c0, vz);
+        tmem_ld8_nowait(tl + kT2ColIn + (uint32_t)c0, vi);
+        tmem_ld8_nowait(tl + kT2ColHn + (uint32_t)c0, vh);
+        tmem_ld_wait();
+        reg_fence(vr); reg_fence(vz); reg_fence(vi); reg_fence(vh);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c = ub + c0 + 4 * q;
+          const uint32_t off = umma_off_bytes(r, c, H) >> 2;
+          const float4 hh = *reinterpret_cast<const float4*>(S.hhi + off);
+          const float4 hl = *reinterpret_cast<const float4*>(S.hlo + off);
+          const float hold[4] = {hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w};
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int u = c + j, jj = 4 * q + j;
+            const float4 gb = S.c.gate_b[u];
+            const float rg = sigmoid_fast(vr[jj] + gb.x);
+            const float zg = sigmoid_fast(vz[jj] + gb.y);
+            const float n = tanh_fast(vi[jj] + gb.z + rg * (vh[jj] + gb.w));
+            o[j] = (1.0f - zg) * n + zg * hold[j];
+          }
+          store_split4(S.hhi, S.hlo, r, c, H, o);
+          if (live) {
+            const float4 v4 = make_float4(o[0], o[1], o[2], o[3]);
+            const size_t offg = (size_t)(row0 + r) * H + c;
+            if (io.hidden_seq) *reinterpret_cast<float4*>(io.hidden_seq + tM * H + offg) = v4;
+            if (io.hidden && t == T - 1) *reinterpret_cast<float4*>(io.hidden + offg) = v4;
+          }
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      mbar_arrive_cluster(&S.a_ready, 0);
+      EP_STAMP(8);
+
+      // ---- E5: Q tail, outputs, selection
+      mbar_wait_cluster(&S.d_ready, d_par); d_par ^= 1u;
+      fence_after_sync();
+      EP_STAMP(9);
+      const float bq2 = __ldg(W.bq2);
+      {
+        float acc[8], pa[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j] = 0.f; pa[j] = (j < A) ? Ps[j * kTcRows + r] : 0.f; }
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          float v[16];
+          tmem_ld16_nowait(tl + kT2ColQ + (uint32_t)c0, v);
+          tmem_ld_wait();
+          reg_fence(v);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            const int u = ub + c0 + n;
+            const float4 qc = S.c.q_c[u];
+            const float4 wl = S.c.w1a[2 * u], wh = S.c.w1a[2 * u + 1];
+            const float pre = v[n] + qc.x;
+            const float wa[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(qc.z, fmaxf(fmaf(pa[j], qc.y, pre + wa[j]), 0.f), acc[j]);
+          }
+        }
+        epi_bar_sync();                 // every thread has read its Ps before red is reused
+#pragma unroll
+        for (int j = 0; j < 8; ++j) S.red[half][j][r] = acc[j];
+        epi_bar_sync();
+        if (half == 0)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < A) Qs[j * kTcRows + r] = S.red[0][j][r] + S.red[1][j][r] + bq2;
+      }
+      fence_before_sync();
+      if (half == 0 && live) {
+        const size_t m = tM + row0 + r;
+        const uint8_t* av = io.avail ? io.avail + m * A : nullptr;
+        float best = -INFINITY, bestm = -INFINITY;
+        int bi = 0, bim = 0, n_avail = 0;
+        for (int act = 0; act < A; ++act) {
+          const float q = Qs[act * kTcRows + r];
+          const float p = Ps[act * kTcRows + r];
+          if (io.q_all) io.q_all[m * A + act] = q;
+          if (io.params_all) io.params_all[m * A + act] = p;
+          if (q > best) { best = q; bi = act; }
+          const bool ok = av ? (av[act] != 0) : true;
+          n_avail += ok ? 1 : 0;
+          const float qm = ok ? q : -INFINITY;
+          if (qm > bestm) { bestm = qm; bim = act; }
+        }
+        if (io.greedy) io.greedy[m] = bi;
+        if (io.sel_actions && io.q_sel) {
+          int s = io.sel_actions[m];
+          s = s < 0 ? 0 : (s >= A ? A - 1 : s);
+          io.q_sel[m] = Qs[s * kTcRows + r];
+        }
+        if (io.actions) {
+          int chosen = bim;
+          if (!io.test_mode) {
+            const uint32_t row_id = (uint32_t)(row0 + r);
+            const float u = io.u_eps ? io.u_eps[m] : philox_uniform(io.seed, kStreamEpsilon, row_id, io.rng_step + t, 0);
+            if (u < io.epsilon) {
+              if (io.rand_actions) {
+                chosen = io.rand_actions[m];
+              } else {
+                const float u2 = philox_uniform(io.seed, kStreamRandomAction, row_id, io.rng_step + t, 0);
+                const int navl = n_avail > 0 ? n_avail : A;
+                int kth = (int)(u2 * (float)navl);
+                kth = kth >= navl ? navl - 1 : kth;
+                chosen = 0;
+                for (int act = 0, seen = 0; act < A; ++act) {
+                  const bool ok = (n_avail == 0) || !av || av[act] != 0;
+                  if (ok) { if (seen == kth) { chosen = act; break; } ++seen; }
+                }
+              }
+              chosen = chosen < 0 ? 0 : (chosen >= A ? A - 1 : chosen);
+            }
+          }
+          io.actions[m] = chosen;
+          if (io.power) io.power[m] = Ps[chosen * kTcRows + r];
+          if (io.q_chosen) io.q_chosen[m] = Qs[chosen * kTcRows + r];
+        }
+      }
+      epi_bar_sync();                   // Ps / Qs / red are free for the next step
+      EP_STAMP(10);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  TC_STAMP_ONCE(24);
+  cluster_sync_all();                   // the leader's MMAs read the peer's shared memory until here
+  if (warp == 5) tmem_dealloc_2sm(tmem, kT2TmemCols);
+  TC_STAMP_ONCE(25);
+  TC_CTA_STAMP(1);
+}
+
+inline size_t agent_tc2_smem_bytes(const macjd_agent_weights& w) {
+  return sizeof(T2Smem) + sizeof(float) * 2 * (size_t)w.n_actions * kTcRows + 1024;
+}
+
+inline bool agent_tc2_supported(const macjd_agent_weights& w) {
+  return agent_tc_supported(w) && kTcKc == 32 && kTcChunksPerX == 1 && w.obs_pad <= 256 && agent_tc2_smem_bytes(w) <= 227 * 1024;
+}
+
+inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
+  const size_t smem = agent_tc2_smem_bytes(a.w);
+  if (cudaFuncSetAttribute(agent_forward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return MACJD_ERR_CUDA;
+  const int pairs = (a.io.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
+  agent_forward_tc2_kernel<<<2 * pairs, kT2Threads, smem, (cudaStream_t)ctx->stream>>>(a);
+  return MACJD_OK;
+}
+
+// Micro-benchmark: like tc_mma_rate_kernel, for tcgen05.mma.cta_group::2 issued by the leader of a CTA pair.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tc2_mma_rate_kernel(int M, int N, int n, unsigned long long* out) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < 40 * 1024 / 4; i += 128) reinterpret_cast<float*>(tc_smem)[i] = 0.001f * (float)(i & 255);
+  fence_async_smem();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_alloc_2sm(&tmem_base_s, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid == 0 && rank == 0) {
+    const uint32_t idesc = umma_idesc_tf32(M, N);
+    const uint64_t da = umma_smem_desc(smem_u32(tc_smem), 128, 16 * 32);
+    const uint64_t db = umma_smem_desc(smem_u32(tc_smem) + 16384, 128, 16 * 32);
+    const unsigned long long t0 = clock64();
+    for (int i = 0; i < n; ++i) mma_tf32_ss_2sm(tmem_base + (uint32_t)((i & 1) * 256), da + (uint64_t)((i & 1) * 16), db, idesc, 1u);
+    mma_commit_2sm(&bar);
+    const unsigned long long t1 = clock64();
+    mbar_wait_cluster(&bar, 0);
+    const unsigned long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  } else if (tid == 0) {
+    mbar_wait_cluster(&bar, 0);
+  }
+  fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+inline int tc2_mma_rate(const macjd_ctx* ctx, int M, int N, int n, unsigned long long* out_dev) {
+  if (cudaFuncSetAttribute(tc2_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+    return MACJD_ERR_CUDA;
+  tc2_mma_rate_kernel<<<2, 128, 64 * 1024, (cudaStream_t)ctx->stream>>>(M, N, n, out_dev);
+  return MACJD_OK;
+}
+
+}  // namespace tc
+}  // namespace macjd
+#endif  // !MACJD_TEST_HOST_EMULATION

@@ -5,6 +5,7 @@
 #include "env_step.cuh"
 #include "agent_act.cuh"
 #include "agent_act_tc.cuh"
+#include "agent_act_tc2.cuh"
 #include "replay.cuh"
 #include "learner.cuh"
 #include "tc05.cuh"
@@ -68,6 +69,8 @@ size_t macjd_abi_sizeof(int which) {
     case 7: return sizeof(macjd_mixer_params);
     case 8: return sizeof(macjd_qhead_dims);
     case 9: return sizeof(macjd_opt_tensors);
+    case 10: return sizeof(macjd_act_host);
+    case 11: return sizeof(macjd_env_host);
     default: return 0;
   }
 }
@@ -88,7 +91,7 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   int st = enter(ctx);
   if (st != MACJD_OK) return st;
   if (!w || !io) return MACJD_ERR_INVALID_ARG;
-  if (io->path < 0 || io->path > 2) return MACJD_ERR_INVALID_ARG;
+  if (io->path < 0 || io->path > 3) return MACJD_ERR_INVALID_ARG;
 #ifndef MACJD_TEST_HOST_EMULATION
   if (io->path != 1 && macjd::tc::agent_tc_supported(*w)) {
     if (io->n_rows < 0 || io->n_steps < 1 || !io->obs) return MACJD_ERR_INVALID_ARG;
@@ -96,11 +99,87 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
     macjd::AgentArgs a;
     a.w = *w;
     a.io = *io;
+    // path 2: one CTA per 64 rows; path 3: CTA pairs (cta_group::2), 128 rows per pair;
+    // path 0 picks the pair kernel as soon as there is more than one 64-row tile
+    const bool pair_ok = macjd::tc::agent_tc2_supported(*w);
+    if (io->path == 3 && !pair_ok) return MACJD_ERR_UNSUPPORTED;
+    if (io->path == 3 || (io->path == 0 && pair_ok && io->n_rows > macjd::tc::kTcRows))
+      return finish(ctx, macjd::tc::agent_tc2_launch(ctx, a));
     return finish(ctx, macjd::tc::agent_tc_launch(ctx, a));
   }
 #endif
-  if (io->path == 2) return MACJD_ERR_UNSUPPORTED;
+  if (io->path >= 2) return MACJD_ERR_UNSUPPORTED;
   return finish(ctx, macjd::agent_launch(ctx, w, io));
+}
+
+namespace {
+// copies on the launch stream; `what` only labels the error string
+int copy_async(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, const macjd_ctx* ctx) {
+  if (bytes == 0) return MACJD_OK;
+  const cudaError_t err = cudaMemcpyAsync(dst, src, bytes, kind, (cudaStream_t)ctx->stream);
+  if (err != cudaSuccess) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s", cudaGetErrorString(err));
+    return MACJD_ERR_CUDA;
+  }
+  return MACJD_OK;
+}
+int drain(const macjd_ctx* ctx) {
+  const cudaError_t err = cudaStreamSynchronize((cudaStream_t)ctx->stream);
+  if (err != cudaSuccess) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s", cudaGetErrorString(err));
+    return MACJD_ERR_CUDA;
+  }
+  return MACJD_OK;
+}
+}  // namespace
+
+int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io,
+                         const macjd_act_host* host) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!w || !io || !host) return MACJD_ERR_INVALID_ARG;
+  if (io->n_steps != 1 || io->n_rows < 0) return MACJD_ERR_INVALID_ARG;
+  if (!host->obs || !host->actions || !host->power || !io->obs || !io->actions || !io->power) return MACJD_ERR_INVALID_ARG;
+  if (host->avail && !io->avail) return MACJD_ERR_INVALID_ARG;
+  const size_t M = (size_t)io->n_rows;
+  if (M == 0) return MACJD_OK;
+  st = copy_async(const_cast<float*>(io->obs), host->obs, M * w->obs_dim * sizeof(float), cudaMemcpyHostToDevice, ctx);
+  if (st == MACJD_OK && host->avail)
+    st = copy_async(const_cast<uint8_t*>(io->avail), host->avail, M * w->n_actions, cudaMemcpyHostToDevice, ctx);
+  if (st != MACJD_OK) return st;
+  st = macjd_agent_forward(ctx, w, io);
+  if (st != MACJD_OK) return st;
+  st = copy_async(host->actions, io->actions, M * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK) st = copy_async(host->power, io->power, M * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && host->q_chosen && io->q_chosen)
+    st = copy_async(host->q_chosen, io->q_chosen, M * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (st != MACJD_OK) return st;
+  return drain(ctx);
+}
+
+int macjd_env_step_host(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io,
+                        const macjd_env_host* host) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!tab || !io || !host) return MACJD_ERR_INVALID_ARG;
+  if (!host->act_d || !host->act_p || !io->act_d || !io->act_p) return MACJD_ERR_INVALID_ARG;
+  if ((host->reward && !io->reward) || (host->terminated && !io->terminated) || (host->obs && !io->obs) ||
+      (host->state && !io->state))
+    return MACJD_ERR_INVALID_ARG;
+  if (tab->n_envs <= 0) return tab->n_envs == 0 ? MACJD_OK : MACJD_ERR_INVALID_ARG;
+  const size_t n = (size_t)tab->n_envs, J = (size_t)tab->n_jammers;
+  const size_t S = (size_t)tab->n_radars * (6 + tab->n_types) + 2 * J;
+  st = copy_async(const_cast<int32_t*>(io->act_d), host->act_d, n * J * sizeof(int32_t), cudaMemcpyHostToDevice, ctx);
+  if (st == MACJD_OK) st = copy_async(const_cast<float*>(io->act_p), host->act_p, n * J * sizeof(float), cudaMemcpyHostToDevice, ctx);
+  if (st != MACJD_OK) return st;
+  st = macjd_env_step(ctx, tab, io);
+  if (st != MACJD_OK) return st;
+  if (host->reward) st = copy_async(host->reward, io->reward, n * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && host->terminated) st = copy_async(host->terminated, io->terminated, n, cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && host->obs) st = copy_async(host->obs, io->obs, n * J * S * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && host->state) st = copy_async(host->state, io->state, n * S * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (st != MACJD_OK) return st;
+  return drain(ctx);
 }
 
 int macjd_replay_copy(const macjd_ctx* ctx, const macjd_copy_desc* descs_host, int32_t n_keys, const int32_t* idx,
@@ -238,6 +317,31 @@ __attribute__((visibility("default"))) int macjd_debug_tc_mma_rate(const macjd_c
   return MACJD_ERR_UNSUPPORTED;
 #else
   return finish(ctx, macjd::tc::tc_mma_rate(ctx, M, N, n, out_dev));
+#endif
+}
+
+__attribute__((visibility("default"))) int macjd_debug_tc_mma_rate_multi(const macjd_ctx* ctx, int M, int N, int n, int issuers,
+                                                                        unsigned long long* out_dev) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+#ifdef MACJD_TEST_HOST_EMULATION
+  (void)M; (void)N; (void)n; (void)issuers; (void)out_dev;
+  return MACJD_ERR_UNSUPPORTED;
+#else
+  return finish(ctx, macjd::tc::tc_mma_rate_multi(ctx, M, N, n, issuers, out_dev));
+#endif
+}
+
+// Same, for tcgen05.mma.cta_group::2 issued by the leader of a 2-CTA cluster (M = pair rows: 128 or 256).
+__attribute__((visibility("default"))) int macjd_debug_tc2_mma_rate(const macjd_ctx* ctx, int M, int N, int n,
+                                                                   unsigned long long* out_dev) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+#ifdef MACJD_TEST_HOST_EMULATION
+  (void)M; (void)N; (void)n; (void)out_dev;
+  return MACJD_ERR_UNSUPPORTED;
+#else
+  return finish(ctx, macjd::tc::tc2_mma_rate(ctx, M, N, n, out_dev));
 #endif
 }
 

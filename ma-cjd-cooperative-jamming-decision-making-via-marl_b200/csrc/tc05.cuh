@@ -312,6 +312,48 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int M, int N, int n
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// Same with `issuers` (1..4) threads of different warps issuing n MMAs each into separate accumulators:
+// out[0] = cycles until every issuer's commit has fired (tells whether the ~50-cycle floor per MMA
+// belongs to the issuing thread or to the tensor pipe).
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_multi_kernel(int M, int N, int n, int issuers, unsigned long long* out) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) { for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1); fence_mbar_init(); }
+  for (int i = tid; i < 40 * 1024 / 4; i += 128) reinterpret_cast<float*>(tc_smem)[i] = 0.001f * (float)(i & 255);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const unsigned long long t0 = clock64();
+  if ((tid & 31) == 0 && warp < issuers) {
+    const uint32_t idesc = umma_idesc_tf32(M, N);
+    const uint64_t da = umma_smem_desc(smem_u32(tc_smem), 128, 16 * 32);
+    const uint64_t db = umma_smem_desc(smem_u32(tc_smem) + 16384, 128, 16 * 32);
+    for (int i = 0; i < n; ++i) mma_tf32_ss(tmem_base + (uint32_t)(warp * 128), da + (uint64_t)((i & 1) * 16), db, idesc, 1u);
+    mma_commit(&bar[warp]);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < issuers; ++i) mbar_wait(&bar[i], 0);
+    out[0] = clock64() - t0;
+    out[1] = out[0];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+inline int tc_mma_rate_multi(const macjd_ctx* ctx, int M, int N, int n, int issuers, unsigned long long* out_dev) {
+  if (issuers < 1 || issuers > 4 || N > 128) return MACJD_ERR_INVALID_ARG;
+  if (cudaFuncSetAttribute(tc_mma_rate_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+    return MACJD_ERR_CUDA;
+  tc_mma_rate_multi_kernel<<<1, 128, 64 * 1024, (cudaStream_t)ctx->stream>>>(M, N, n, issuers, out_dev);
+  return MACJD_OK;
+}
+
 inline int tc_mma_rate(const macjd_ctx* ctx, int M, int N, int n, unsigned long long* out_dev) {
   if (cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
     return MACJD_ERR_CUDA;

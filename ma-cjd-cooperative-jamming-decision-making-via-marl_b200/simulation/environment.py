@@ -147,6 +147,34 @@ class ElectromagneticEnvironment:
         ``out`` redirects them ({EnvIO field: tensor})."""
         self._lib.call("macjd_env_step", self._ctx(), self._ctab, self._io(act_d, act_p, noise, out))
 
+    def host_buffers(self, pinned=True):
+        """Host arrays for ``step_host`` (page-locked unless ``pinned=False``): the discrete / continuous
+        actions going in and reward, terminated, next observations coming out, as CPU tensors."""
+        n, J, S = self.n_envs, self.num_jammers, self.state_dim
+        pin = bool(pinned) and self.device.type == "cuda"
+        mk = lambda shape, dt: torch.zeros(shape, dtype=dt, pin_memory=pin)
+        return {"act_d": mk((n, J), torch.int32), "act_p": mk((n, J), torch.float32), "reward": mk((n,), torch.float32),
+                "terminated": mk((n,), torch.uint8), "obs": mk((n, J, S), torch.float32)}
+
+    def step_host(self, host):
+        """environment.py:221-477 for callers that live on the host, as the reference's runner does:
+        ``host`` maps act_d / act_p (in) and any of reward / terminated / obs / state (out) to contiguous
+        CPU tensors or numpy arrays (see ``host_buffers``).  One C call: copies in, fused step, copies
+        out, stream drained on return (include/macjd.h: macjd_env_step_host)."""
+        key = tuple((k, N.ptr(v)) for k, v in sorted(host.items()))
+        c = getattr(self, "_host_cache", None)
+        if c is None or c["key"] != key:
+            n, J = self.n_envs, self.num_jammers
+            if not hasattr(self, "_act_d_dev"):
+                self._act_d_dev = torch.zeros(n, J, dtype=torch.int32, device=self.device)
+                self._act_p_dev = torch.zeros(n, J, dtype=torch.float32, device=self.device)
+            unknown = set(host) - {"act_d", "act_p", "reward", "terminated", "obs", "state"}
+            if unknown or "act_d" not in host or "act_p" not in host:
+                raise ValueError(f"step_host: need act_d and act_p, unknown keys {sorted(unknown)}")
+            hs = N.EnvHost(**{k: N.ptr(v) for k, v in host.items()})
+            c = self._host_cache = {"key": key, "host": hs, "io": self._io(self._act_d_dev, self._act_p_dev), "keep": dict(host)}
+        self._lib.call("macjd_env_step_host", self._ctx(), self._ctab, c["io"], c["host"])
+
     # ------------------------------------------------------------------ reference API
     def reset(self):
         """environment.py:208-219."""

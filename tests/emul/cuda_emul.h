@@ -58,7 +58,7 @@ typedef int cudaError_t;
 typedef void* cudaStream_t;
 enum { cudaSuccess = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
-enum cudaMemcpyKind { cudaMemcpyDeviceToDevice = 3 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }

@@ -4,6 +4,7 @@ import tempfile
 import types
 
 import numpy as np
+import pytest
 import torch
 import yaml
 
@@ -128,3 +129,44 @@ def check_reference_protocol_runner(device, lib):
     assert float(ep["state"][0, 4].abs().sum()) > 0 and bool(ep["filled"].all())
     assert not bool(ep["terminated"][0, :4].any()) and bool(ep["terminated"][0, 4].all())
     runner.close_env()
+
+
+def check_host_buffer_api(device, lib, n_envs=7, steps=5):
+    """The host-buffer entry points (macjd_agent_act_host / macjd_env_step_host: numpy in, numpy out,
+    copies inside the call) against the device-resident API on twin envs / controllers driven greedily:
+    identical actions, power, rewards, terminated flags and observations at every step."""
+    import copy
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import hetero_spec
+    from macjd_b200.core.mac import BasicMAC
+    args = rl_args(device)
+    spec = hetero_spec(n_envs, seed=4, active=True, episode_limit=steps - 1)
+    envs = [ElectromagneticEnvironment(args, spec=spec, device=device, seed=11, _lib=lib) for _ in range(2)]
+    torch.manual_seed(5)
+    mac_a = BasicMAC(24, args, _lib=lib)
+    if args.use_cuda:
+        mac_a.cuda()
+    mac_a.select_actions(envs[0].get_obs(), envs[0].get_avail_actions(), 0, test_mode=True)   # fills the launch caches
+    mac_b = copy.deepcopy(mac_a)                  # a controller with live caches must stay copyable
+    for m in (mac_a, mac_b):
+        m.init_hidden(n_envs)
+        m._rng_step = 0
+    env_d, env_h = envs
+    hb = env_h.host_buffers()
+    obs_h = env_h.get_obs().cpu().contiguous()
+    avail_h = env_h.get_avail_actions().cpu().contiguous()
+    for t in range(steps):
+        a_d, p_d = mac_a.select_actions(env_d.get_obs(), env_d.get_avail_actions(), t, test_mode=(t % 2 == 0))
+        a_h, p_h = mac_b.select_actions_host(obs_h, avail_h, t, test_mode=(t % 2 == 0),
+                                             actions_out=hb["act_d"], power_out=hb["act_p"])
+        assert a_h is hb["act_d"] and p_h is hb["act_p"]
+        np.testing.assert_array_equal(a_h.numpy(), a_d.cpu().numpy()[..., 0])
+        np.testing.assert_array_equal(p_h.numpy(), p_d.cpu().numpy()[..., 0])
+        obs_d, rew_d, term_d, _ = env_d.step((a_d[..., 0], p_d[..., 0]))
+        env_h.step_host(hb)
+        np.testing.assert_array_equal(hb["reward"].numpy(), rew_d.cpu().numpy())
+        np.testing.assert_array_equal(hb["terminated"].numpy().astype(bool), term_d.cpu().numpy())
+        np.testing.assert_array_equal(hb["obs"].numpy(), obs_d.cpu().numpy())
+        obs_h = hb["obs"]
+    with pytest.raises(ValueError):
+        env_h.step_host({"act_d": hb["act_d"]})

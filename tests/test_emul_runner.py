@@ -13,3 +13,7 @@ def test_training_loop_smoke():
 
 def test_reference_protocol_runner():
     RC.check_reference_protocol_runner("cpu", emul_lib())
+
+
+def test_host_buffer_api():
+    RC.check_host_buffer_api("cpu", emul_lib())

@@ -16,3 +16,7 @@ def test_training_loop_smoke():
 
 def test_reference_protocol_runner():
     RC.check_reference_protocol_runner("cuda", None)
+
+
+def test_host_buffer_api():
+    RC.check_host_buffer_api("cuda", None, n_envs=300)
