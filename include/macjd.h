@@ -125,8 +125,10 @@ MACJD_API int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab,
  * observations out).  `io` names DEVICE staging buffers exactly as for macjd_env_step (act_d,
  * act_p, reward, terminated, obs ... must be set); the call copies the host actions in on
  * ctx->stream, launches the step, copies the requested outputs back and returns after the
- * stream has drained.  Host pointers may be pageable or pinned (pinned: truly asynchronous
- * copies); NULL outputs are skipped. */
+ * stream has drained.  Host pointers may be pageable or page-locked; page-locked buffers are
+ * handed to the kernel in place when that is faster than a copy-engine transfer (outputs up to
+ * 8 MB, inputs up to 256 KB; csrc/macjd_api.cu: direct_host_limit), so the io staging buffers
+ * may go unused.  NULL outputs are skipped. */
 typedef struct macjd_env_host {
   const int32_t* act_d;     /* host [n_envs][J]                                       */
   const float* act_p;       /* host [n_envs][J]                                       */
@@ -223,7 +225,8 @@ MACJD_API int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weight
  * single-step (n_steps = 1) macjd_agent_io whose obs / avail / actions / power name DEVICE
  * staging buffers; the call copies host obs (and avail) in on ctx->stream, launches the
  * fused step, copies actions / power (and q_chosen when both sides give it) back and returns
- * after the stream has drained.  The recurrent state stays on the device (io->hidden). */
+ * after the stream has drained (small page-locked buffers are read / written in place by the
+ * kernel, see macjd_env_step_host).  The recurrent state stays on the device (io->hidden). */
 typedef struct macjd_act_host {
   const float* obs;         /* host [M][O]                                            */
   const uint8_t* avail;     /* host [M][A], optional (NULL: io->avail is used as is)  */

@@ -11,6 +11,7 @@
 #include "tc05.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -131,6 +132,38 @@ int drain(const macjd_ctx* ctx) {
   }
   return MACJD_OK;
 }
+
+// Host buffers in page-locked memory can be handed to the kernels as they are (the SMs read / write them
+// over PCIe: no separate copy operation and none of its launch latency).  Measured on B200 / PCIe 5
+// (tools/e2e_host.py, 4096 envs): kernel WRITES to host memory beat a copy-engine transfer even at 786 KB
+// (env step + D2H 62 -> 50 us); kernel READS win only for small buffers (786 KB of observations read in
+// place cost the agent step +10 us, its first phase waits for them).  Larger buffers and pageable memory
+// go through the copy engines.  MACJD_DIRECT_HOST_READ_BYTES / _WRITE_BYTES override the limits (0 = never).
+size_t direct_host_limit(bool write) {
+  static const size_t lim[2] = {
+      [] { const char* e = getenv("MACJD_DIRECT_HOST_READ_BYTES"); return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)256 << 10; }(),
+      [] { const char* e = getenv("MACJD_DIRECT_HOST_WRITE_BYTES"); return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)8 << 20; }()};
+  return lim[write ? 1 : 0];
+}
+extern "C++" {
+template <typename T>
+T* device_alias(T* host_ptr, size_t bytes, bool write) {
+#ifdef MACJD_TEST_HOST_EMULATION
+  (void)bytes; (void)write;
+  return host_ptr;                     // emulation: "device" memory is host memory
+#else
+  if (!host_ptr || bytes > direct_host_limit(write)) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+  return reinterpret_cast<T*>(attr.devicePointer);
+#endif
+}
+}  // extern "C++"
+
 }  // namespace
 
 int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io,
@@ -143,15 +176,26 @@ int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, con
   if (host->avail && !io->avail) return MACJD_ERR_INVALID_ARG;
   const size_t M = (size_t)io->n_rows;
   if (M == 0) return MACJD_OK;
-  st = copy_async(const_cast<float*>(io->obs), host->obs, M * w->obs_dim * sizeof(float), cudaMemcpyHostToDevice, ctx);
-  if (st == MACJD_OK && host->avail)
-    st = copy_async(const_cast<uint8_t*>(io->avail), host->avail, M * w->n_actions, cudaMemcpyHostToDevice, ctx);
+  macjd_agent_io k = *io;
+  const size_t obs_bytes = M * w->obs_dim * sizeof(float), avail_bytes = M * w->n_actions;
+  if (const float* d = device_alias(host->obs, obs_bytes, false)) k.obs = d;
+  else st = copy_async(const_cast<float*>(io->obs), host->obs, obs_bytes, cudaMemcpyHostToDevice, ctx);
+  if (st == MACJD_OK && host->avail) {
+    if (const uint8_t* d = device_alias(host->avail, avail_bytes, false)) k.avail = d;
+    else st = copy_async(const_cast<uint8_t*>(io->avail), host->avail, avail_bytes, cudaMemcpyHostToDevice, ctx);
+  }
   if (st != MACJD_OK) return st;
-  st = macjd_agent_forward(ctx, w, io);
+  int32_t* d_act = device_alias(host->actions, M * sizeof(int32_t), true);
+  float* d_pow = device_alias(host->power, M * sizeof(float), true);
+  float* d_q = (host->q_chosen && io->q_chosen) ? device_alias(host->q_chosen, M * sizeof(float), true) : nullptr;
+  if (d_act) k.actions = d_act;
+  if (d_pow) k.power = d_pow;
+  if (d_q) k.q_chosen = d_q;
+  st = macjd_agent_forward(ctx, w, &k);
   if (st != MACJD_OK) return st;
-  st = copy_async(host->actions, io->actions, M * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx);
-  if (st == MACJD_OK) st = copy_async(host->power, io->power, M * sizeof(float), cudaMemcpyDeviceToHost, ctx);
-  if (st == MACJD_OK && host->q_chosen && io->q_chosen)
+  if (!d_act) st = copy_async(host->actions, io->actions, M * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && !d_pow) st = copy_async(host->power, io->power, M * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && !d_q && host->q_chosen && io->q_chosen)
     st = copy_async(host->q_chosen, io->q_chosen, M * sizeof(float), cudaMemcpyDeviceToHost, ctx);
   if (st != MACJD_OK) return st;
   return drain(ctx);
@@ -169,15 +213,28 @@ int macjd_env_step_host(const macjd_ctx* ctx, const macjd_env_tables* tab, const
   if (tab->n_envs <= 0) return tab->n_envs == 0 ? MACJD_OK : MACJD_ERR_INVALID_ARG;
   const size_t n = (size_t)tab->n_envs, J = (size_t)tab->n_jammers;
   const size_t S = (size_t)tab->n_radars * (6 + tab->n_types) + 2 * J;
-  st = copy_async(const_cast<int32_t*>(io->act_d), host->act_d, n * J * sizeof(int32_t), cudaMemcpyHostToDevice, ctx);
-  if (st == MACJD_OK) st = copy_async(const_cast<float*>(io->act_p), host->act_p, n * J * sizeof(float), cudaMemcpyHostToDevice, ctx);
+  macjd_env_io k = *io;
+  if (const int32_t* d = device_alias(host->act_d, n * J * sizeof(int32_t), false)) k.act_d = d;
+  else st = copy_async(const_cast<int32_t*>(io->act_d), host->act_d, n * J * sizeof(int32_t), cudaMemcpyHostToDevice, ctx);
+  if (st == MACJD_OK) {
+    if (const float* d = device_alias(host->act_p, n * J * sizeof(float), false)) k.act_p = d;
+    else st = copy_async(const_cast<float*>(io->act_p), host->act_p, n * J * sizeof(float), cudaMemcpyHostToDevice, ctx);
+  }
   if (st != MACJD_OK) return st;
-  st = macjd_env_step(ctx, tab, io);
+  float* d_rew = device_alias(host->reward, n * sizeof(float), true);
+  uint8_t* d_term = device_alias(host->terminated, n, true);
+  float* d_obs = device_alias(host->obs, n * J * S * sizeof(float), true);
+  float* d_state = device_alias(host->state, n * S * sizeof(float), true);
+  if (d_rew) k.reward = d_rew;
+  if (d_term) k.terminated = d_term;
+  if (d_obs) k.obs = d_obs;
+  if (d_state) k.state = d_state;
+  st = macjd_env_step(ctx, tab, &k);
   if (st != MACJD_OK) return st;
-  if (host->reward) st = copy_async(host->reward, io->reward, n * sizeof(float), cudaMemcpyDeviceToHost, ctx);
-  if (st == MACJD_OK && host->terminated) st = copy_async(host->terminated, io->terminated, n, cudaMemcpyDeviceToHost, ctx);
-  if (st == MACJD_OK && host->obs) st = copy_async(host->obs, io->obs, n * J * S * sizeof(float), cudaMemcpyDeviceToHost, ctx);
-  if (st == MACJD_OK && host->state) st = copy_async(host->state, io->state, n * S * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (host->reward && !d_rew) st = copy_async(host->reward, io->reward, n * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && host->terminated && !d_term) st = copy_async(host->terminated, io->terminated, n, cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && host->obs && !d_obs) st = copy_async(host->obs, io->obs, n * J * S * sizeof(float), cudaMemcpyDeviceToHost, ctx);
+  if (st == MACJD_OK && host->state && !d_state) st = copy_async(host->state, io->state, n * S * sizeof(float), cudaMemcpyDeviceToHost, ctx);
   if (st != MACJD_OK) return st;
   return drain(ctx);
 }

@@ -131,7 +131,7 @@ def check_reference_protocol_runner(device, lib):
     runner.close_env()
 
 
-def check_host_buffer_api(device, lib, n_envs=7, steps=5):
+def check_host_buffer_api(device, lib, n_envs=7, steps=5, pinned=True):
     """The host-buffer entry points (macjd_agent_act_host / macjd_env_step_host: numpy in, numpy out,
     copies inside the call) against the device-resident API on twin envs / controllers driven greedily:
     identical actions, power, rewards, terminated flags and observations at every step."""
@@ -152,7 +152,7 @@ def check_host_buffer_api(device, lib, n_envs=7, steps=5):
         m.init_hidden(n_envs)
         m._rng_step = 0
     env_d, env_h = envs
-    hb = env_h.host_buffers()
+    hb = env_h.host_buffers(pinned=pinned)   # pinned + small: kernels work on host memory directly; else copy engines
     obs_h = env_h.get_obs().cpu().contiguous()
     avail_h = env_h.get_avail_actions().cpu().contiguous()
     for t in range(steps):

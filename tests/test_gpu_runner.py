@@ -18,5 +18,6 @@ def test_reference_protocol_runner():
     RC.check_reference_protocol_runner("cuda", None)
 
 
-def test_host_buffer_api():
-    RC.check_host_buffer_api("cuda", None, n_envs=300)
+@pytest.mark.parametrize("n_envs,pinned", [(300, True), (300, False), (6000, True)])
+def test_host_buffer_api(n_envs, pinned):
+    RC.check_host_buffer_api("cuda", None, n_envs=n_envs, pinned=pinned)
