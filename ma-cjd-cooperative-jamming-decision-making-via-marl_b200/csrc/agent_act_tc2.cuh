@@ -27,7 +27,12 @@ constexpr int kT2Stages = 2;
 constexpr int kT2HalfBytes = kTcH * kTcKc * 4 / 2;        // this CTA's 64 weight rows of one hi (or lo) chunk
 constexpr int kT2SubBytes = 2 * kT2HalfBytes;              // hi half + lo half of one chunk
 constexpr int kT2StageBytes = 2 * kT2SubBytes;             // a stage holds two consecutive chunks: one barrier round trip per 64 k
-constexpr int kT2Threads = 192;
+constexpr int kT2ColSplit = 2;                             // epilogue warps per TMEM lane quarter (each takes 64 / split units)
+constexpr int kT2EpiWarps = 4 * kT2ColSplit;
+constexpr int kT2EpiThreads = 32 * kT2EpiWarps;
+constexpr int kT2Threads = kT2EpiThreads + 64;             // + weight-stream warp + MMA / relay warp
+constexpr int kT2Upt = 64 / kT2ColSplit;                   // output units per epilogue thread
+constexpr int kT2Parts = 2 * kT2ColSplit;                  // threads that share one row
 constexpr uint32_t kT2ColA1 = 0, kT2ColFc1 = 64, kT2ColA2 = 128;
 constexpr uint32_t kT2ColR = 0, kT2ColZ = 64, kT2ColIn = 128, kT2ColHn = 192, kT2ColQ = 0;
 constexpr uint32_t kT2TmemCols = 256;
@@ -99,24 +104,21 @@ __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t n
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;\n" ::"n"(kT2EpiThreads) : "memory"); }
 
-// One ring stage of the issuer's schedule: which activation tile, where its two sub-chunks accumulate,
-// and which hand-shakes surround it.
-struct T2Stage {
-  uint32_t ahi, alo, sbo, koff0, koff1, d0, d1;
-  uint8_t first0, first1;
-  uint8_t pre;      // 1: wait for the observation block, 2: wait for the epilogue's activation tile
-  uint8_t post;     // bit 0: release the observation block, bit 1: accumulators ready for the epilogue
-};
+// Epilogue-side wait: one warp polls the mbarrier, the others park on a named barrier (a parked warp
+// takes no issue slots).
+__device__ __forceinline__ void epi_wait(uint64_t* bar, uint32_t parity, int warp) {
+  if (warp == 0) mbar_wait_cluster(bar, parity);
+  epi_bar_sync();
+}
 
 struct T2Smem {
   float b0hi[kTcRows * kTcH], b0lo[kTcRows * kTcH];        // observation block (first 8 KB) -> a1 -> xf
   float hhi[kTcRows * kTcH], hlo[kTcRows * kTcH];            // h -> h'
   unsigned char wst[kT2Stages][kT2StageBytes];
   TcConst c;
-  float red[2][8][kTcRows];                 // partial row sums of the two unit halves
-  T2Stage stage_tab[24];                    // nxc + 16 stages per step (obs_dim <= 256)
+  float red[kT2Parts][8][kTcRows];          // partial row sums of the threads that share a row
   uint64_t w_full[kT2Stages], w_empty[kT2Stages];
   uint64_t x_full, x_empty, d_ready, a_ready;
   uint32_t tmem_base;
@@ -149,7 +151,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   if (tid == 0) {
     // the leader's "full" needs its own copy armed and the peer's "my half has landed" relay
     for (int s = 0; s < kT2Stages; ++s) { mbar_init(&S.w_full[s], rank == 0 ? 2 : 1); mbar_init(&S.w_empty[s], 1); }
-    mbar_init(&S.x_full, 256); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 256);
+    mbar_init(&S.x_full, 2 * kT2EpiThreads); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 2 * kT2EpiThreads);
     fence_mbar_init();
   }
   for (int i = tid; i < H; i += kT2Threads) {
@@ -171,14 +173,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   TC_STAMP_ONCE(21);
   cluster_sync_all();                         // both CTAs' barriers exist before any remote arrive
   TC_STAMP_ONCE(22);
-  if (warp == 5) tmem_alloc_2sm(&S.tmem_base, kT2TmemCols);
+  if (warp == kT2EpiWarps + 1) tmem_alloc_2sm(&S.tmem_base, kT2TmemCols);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = S.tmem_base;
   TC_STAMP_ONCE(23);
 
-  if (warp == 4) {
+  if (warp == kT2EpiWarps) {
     // =========================================================== weight stream: this CTA's half of every chunk
     if (lane == 0) {
       const char* wsrc = reinterpret_cast<const char*>(W.tc_chunks);
@@ -199,7 +201,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kT2EpiWarps + 1) {
     if (lane == 0 && rank != 0) {
       // =========================================================== peer: relay "my half has landed"
       const long long total = (long long)supers_per_step * T;
@@ -211,35 +213,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         mbar_arrive_cluster(&S.w_full[s], 0);
         s ^= 1;
       }
-    } else if (lane == 0) {
+    } else if (rank == 0) {
       // =========================================================== leader: MMA issue for the pair
-      // One compact loop over a table of stages (a stage = two consecutive 32-k weight chunks against
-      // one activation tile).  Straight-line code for the 408 MMAs of a step would be ~100 KB of
-      // instructions executed once per step: after an L2 flush the issuer then runs at instruction-fetch
-      // speed (measured: +23 us per cold step).
+      // The WHOLE warp runs this loop and one elected lane issues: every MMA operand is then a
+      // warp-uniform value held in uniform registers.  Issued from inside `if (lane == 0)` each
+      // tcgen05.mma was wrapped in an ELECT / 5x R2UR / branch sequence (60 cycles per MMA).
+      // The schedule is a compact loop over stages (a stage = two consecutive 32-k weight chunks
+      // against one activation tile) with the per-stage parameters computed from the stage index:
+      // straight-line code for the 408 MMAs of a step is ~100 KB of instructions executed once per
+      // step, and after an L2 flush the issuer then runs at instruction-fetch speed (+23 us).
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc = umma_idesc_tf32(2 * kTcRows, H);
       const uint32_t bh = smem_u32(S.b0hi), bl = smem_u32(S.b0lo), hh = smem_u32(S.hhi), hl = smem_u32(S.hlo);
       const uint32_t w0 = smem_u32(S.wst[0]);
-      for (int L = 0; L < supers_per_step; ++L) {
-        T2Stage e;
-        if (L < nxc) {                       // [actor.0 | fc1] chunk pair of observation block L
-          e.ahi = bh; e.alo = bl; e.sbo = 32 * 32; e.koff0 = e.koff1 = 0;
-          e.d0 = kT2ColA1; e.d1 = kT2ColFc1; e.first0 = e.first1 = (L == 0);
-          e.pre = 1; e.post = 1 | (L == nxc - 1 ? 2 : 0);
-        } else {                             // K = 128 layers: 4 chunks = 2 stages each
-          const int j = (L - nxc) >> 1, hf = (L - nxc) & 1;
-          //                 actor.2   W_ir      W_hr     W_iz      W_hz     W_in       W_hn       q.0[:, :H]
-          const uint32_t dcol[8] = {kT2ColA2, kT2ColR, kT2ColR, kT2ColZ, kT2ColZ, kT2ColIn, kT2ColHn, kT2ColQ};
-          const bool use_h = (0xD4u >> j) & 1u;        // layers 2, 4, 6, 7 read h
-          const bool first = (0xEBu >> j) & 1u;        // layers 2 and 4 accumulate onto the W_i* product
-          e.ahi = use_h ? hh : bh; e.alo = use_h ? hl : bl; e.sbo = H * 32;
-          e.koff0 = (2 * hf) * kTcAStep; e.koff1 = (2 * hf + 1) * kTcAStep;
-          e.d0 = e.d1 = dcol[j]; e.first0 = first && hf == 0; e.first1 = 0;
-          e.pre = (hf == 0 && (j == 0 || j == 1 || j == 7)) ? 2 : 0;
-          e.post = (hf == 1 && (j == 0 || j == 6 || j == 7)) ? 2 : 0;
-        }
-        S.stage_tab[L] = e;
-      }
       uint32_t full_par = 0, x_full_par = 0, a_ready_par = 0;
       int s = 0;
       for (int t = 0; t < T; ++t) {
@@ -247,59 +233,81 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         int stamp = 33;
 #endif
         for (int L = 0; L < supers_per_step; ++L) {
-          const T2Stage e = S.stage_tab[L];
-          if (e.pre == 1) { mbar_wait_cluster(&S.x_full, x_full_par); x_full_par ^= 1u; TC_STAMP(32); }
-          if (e.pre == 2) {
+          uint32_t ahi, alo, sbo, koff0, koff1, d0, d1, first0, first1, pre, post;
+          if (L < nxc) {                       // [actor.0 | fc1] chunk pair of observation block L
+            ahi = bh; alo = bl; sbo = 32 * 32; koff0 = koff1 = 0;
+            d0 = kT2ColA1; d1 = kT2ColFc1; first0 = first1 = (L == 0);
+            pre = 1; post = 1u | (L == nxc - 1 ? 2u : 0u);
+          } else {                             // K = 128 layers: 4 chunks = 2 stages each
+            //  j:  0 actor.2 (b0)  1 W_ir (b0)  2 W_hr (h)  3 W_iz (b0)  4 W_hz (h)  5 W_in (b0)  6 W_hn (h)  7 q.0[:, :H] (h)
+            const uint32_t j = (uint32_t)(L - nxc) >> 1, hf = (uint32_t)(L - nxc) & 1u;
+            const bool use_h = (0xD4u >> j) & 1u;          // layers 2, 4, 6, 7 read h
+            ahi = use_h ? hh : bh; alo = use_h ? hl : bl; sbo = H * 32;
+            koff0 = (2 * hf) * kTcAStep; koff1 = (2 * hf + 1) * kTcAStep;
+            d0 = d1 = 64u * ((0x03211002u >> (4 * j)) & 0xFu);   // accumulator column / 64 per layer
+            first0 = ((0xEBu >> j) & 1u) & (hf == 0 ? 1u : 0u);  // layers 2 and 4 accumulate onto the W_i* product
+            first1 = 0;
+            pre = (hf == 0 && ((0x83u >> j) & 1u)) ? 2u : 0u;    // actor.2, W_ir, q.0 wait for the epilogue's tile
+            post = (hf == 1 && ((0xC1u >> j) & 1u)) ? 2u : 0u;   // after actor.2, W_hn, q.0 the epilogue may read
+          }
+          if (pre == 1) { mbar_wait_cluster(&S.x_full, x_full_par); x_full_par ^= 1u; if (lane == 0) TC_STAMP(32); }
+          if (pre == 2) {
             mbar_wait_cluster(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
 #ifdef MACJD_TC_PROFILE
-            TC_STAMP(stamp); ++stamp;
+            if (lane == 0) TC_STAMP(stamp);
+            ++stamp;
 #endif
           }
           mbar_wait_cluster(&S.w_full[s], (full_par >> s) & 1u);
           full_par ^= 1u << s;
           fence_after_sync();
           const uint32_t wbase = w0 + (uint32_t)s * kT2StageBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {
-            const uint32_t koff = sub ? e.koff1 : e.koff0;
-            const uint64_t dah = umma_smem_desc(e.ahi + koff, 128, e.sbo);
-            const uint64_t dal = umma_smem_desc(e.alo + koff, 128, e.sbo);
-            const uint64_t dbh = umma_smem_desc(wbase + sub * kT2SubBytes, 128, kTcKc * 32);
-            const uint64_t dbl = umma_smem_desc(wbase + sub * kT2SubBytes + kT2HalfBytes, 128, kTcKc * 32);
-            const uint32_t d = tmem + (sub ? e.d1 : e.d0);
-            const uint32_t first = sub ? e.first1 : e.first0;
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint32_t koff = sub ? koff1 : koff0;
+              const uint64_t dah = umma_smem_desc(ahi + koff, 128, sbo);
+              const uint64_t dal = umma_smem_desc(alo + koff, 128, sbo);
+              const uint64_t dbh = umma_smem_desc(wbase + sub * kT2SubBytes, 128, kTcKc * 32);
+              const uint64_t dbl = umma_smem_desc(wbase + sub * kT2SubBytes + kT2HalfBytes, 128, kTcKc * 32);
+              const uint32_t d = tmem_u + (sub ? d1 : d0);
+              const uint32_t first = sub ? first1 : first0;
 #pragma unroll
-            for (int ks = 0; ks < kTcKc / 8; ++ks) {
-              const uint64_t adv = (uint64_t)((ks * 256) >> 4);
-              mma_tf32_ss_2sm(d, dah + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
-              mma_tf32_ss_2sm(d, dal + adv, dbh + adv, idesc, 1u);
-              mma_tf32_ss_2sm(d, dah + adv, dbl + adv, idesc, 1u);
+              for (int ks = 0; ks < kTcKc / 8; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * 256) >> 4);
+                mma_tf32_ss_2sm(d, dah + adv, dbh + adv, idesc, (first && ks == 0) ? 0u : 1u);
+                mma_tf32_ss_2sm(d, dal + adv, dbh + adv, idesc, 1u);
+                mma_tf32_ss_2sm(d, dah + adv, dbl + adv, idesc, 1u);
+              }
             }
+            mma_commit_2sm(&S.w_empty[s]);
+            if (post & 1u) mma_commit_2sm(&S.x_empty);
+            if (post & 2u) mma_commit_2sm(&S.d_ready);
           }
-          mma_commit_2sm(&S.w_empty[s]);
-          if (e.post & 1u) mma_commit_2sm(&S.x_empty);
-          if (e.post & 2u) {
-            mma_commit_2sm(&S.d_ready);
+          __syncwarp();
 #ifdef MACJD_TC_PROFILE
-            TC_STAMP(stamp); ++stamp;
+          if (post & 2u) { if (lane == 0) TC_STAMP(stamp); ++stamp; }
 #endif
-          }
           s ^= 1;
         }
       }
     }
   } else {
     // =========================================================== epilogue warps
-    const int half = warp >> 1;                      // which 64 output units of the row
-    const int r = (warp & 1) * 32 + lane;            // row within this CTA's tile
-    const int ub = half * 64;
+    // warp -> TMEM lane quarter q = warp % 4 (a hardware rule) = (row block, 64-unit half of the 2-SM
+    // accumulator layout); warps q and q + 4 split that quarter's 64 columns
+    const int q4 = warp & 3, ch = warp >> 2;
+    const int half = q4 >> 1;
+    const int r = (q4 & 1) * 32 + lane;              // row within this CTA's tile
+    const int ub = half * 64 + ch * kT2Upt;          // first output unit of this thread
+    const int part = half * kT2ColSplit + ch;        // which of the row's kT2Parts threads
     const bool live = r < valid;
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * kT2Upt);
     uint32_t d_par = 0, x_empty_par = 0;
 
     {
       const bool have = io.hidden && !io.hidden_zero_init && live;
-      for (int k = ub; k < ub + 64; k += 4) {
+      for (int k = ub; k < ub + kT2Upt; k += 4) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (have) {
           const float4 x = *reinterpret_cast<const float4*>(io.hidden + (size_t)(row0 + r) * H + k);
@@ -313,9 +321,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       const size_t tM = (size_t)t * M;
       EP_STAMP(0);
       for (int xc = 0; xc < nxc; ++xc) {
-        if (t > 0 || xc > 0) { mbar_wait_cluster(&S.x_empty, x_empty_par); x_empty_par ^= 1u; }
+        if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
         const float* obs = io.obs + (tM + row0 + r) * O;
-        for (int k = half * 16; k < half * 16 + 16; k += 4) {
+        for (int k = part * (32 / kT2Parts); k < (part + 1) * (32 / kT2Parts); k += 4) {
           float v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) { const int kk = xc * 32 + k + j; v[j] = (live && kk < O) ? __ldg(obs + kk) : 0.f; }
@@ -328,10 +336,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 
       // ---- E1: a1 = relu(D1 + b) -> B0
       EP_STAMP(1);
-      mbar_wait_cluster(&S.d_ready, d_par); d_par ^= 1u;
+      epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(2);
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
         float v[16];
         tmem_ld16_nowait(tl + kT2ColA1 + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -350,14 +358,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       EP_STAMP(3);
 
       // ---- E2: actor head;  E3: xf = relu(D3 + b) -> B0
-      mbar_wait_cluster(&S.d_ready, d_par); d_par ^= 1u;
+      epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(4);
       {
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
           float v[16];
           tmem_ld16_nowait(tl + kT2ColA2 + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -374,15 +382,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) S.red[half][j][r] = acc[j];
+        for (int j = 0; j < 8; ++j) S.red[part][j][r] = acc[j];
         epi_bar_sync();
-        if (half == 0)
+        if (part == 0)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (j < A) Ps[j * kTcRows + r] = sigmoid_fast(S.red[0][j][r] + S.red[1][j][r] + S.c.ba3[j]);
+            if (j < A) {
+              float sum = S.c.ba3[j];
+#pragma unroll
+              for (int pp = 0; pp < kT2Parts; ++pp) sum += S.red[pp][j][r];
+              Ps[j * kTcRows + r] = sigmoid_fast(sum);
+            }
       }
       EP_STAMP(5);
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
         float v[16];
         tmem_ld16_nowait(tl + kT2ColFc1 + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -401,10 +414,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       EP_STAMP(6);
 
       // ---- E4: GRU gates -> h' (in place over h), global hidden outputs
-      mbar_wait_cluster(&S.d_ready, d_par); d_par ^= 1u;
+      epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(7);
-      for (int c0 = 0; c0 < 64; c0 += 8) {
+      for (int c0 = 0; c0 < kT2Upt; c0 += 8) {
         float vr[8], vz[8], vi[8], vh[8];
         tmem_ld8_nowait(tl + kT2ColR + (uint32_t)c0, vr);
         tmem_ld8_nowait(tl + kT2ColZ + (uint32_t)c0, vz);
@@ -444,7 +457,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       EP_STAMP(8);
 
       // ---- E5: Q tail, outputs, selection
-      mbar_wait_cluster(&S.d_ready, d_par); d_par ^= 1u;
+      epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(9);
       const float bq2 = __ldg(W.bq2);
@@ -452,7 +465,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         float acc[8], pa[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc[j] = 0.f; pa[j] = (j < A) ? Ps[j * kTcRows + r] : 0.f; }
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
           float v[16];
           tmem_ld16_nowait(tl + kT2ColQ + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -470,15 +483,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         }
         epi_bar_sync();                 // every thread has read its Ps before red is reused
 #pragma unroll
-        for (int j = 0; j < 8; ++j) S.red[half][j][r] = acc[j];
+        for (int j = 0; j < 8; ++j) S.red[part][j][r] = acc[j];
         epi_bar_sync();
-        if (half == 0)
+        if (part == 0)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (j < A) Qs[j * kTcRows + r] = S.red[0][j][r] + S.red[1][j][r] + bq2;
+            if (j < A) {
+              float sum = bq2;
+#pragma unroll
+              for (int pp = 0; pp < kT2Parts; ++pp) sum += S.red[pp][j][r];
+              Qs[j * kTcRows + r] = sum;
+            }
       }
       fence_before_sync();
-      if (half == 0 && live) {
+      if (part == 0 && live) {
         const size_t m = tM + row0 + r;
         const uint8_t* av = io.avail ? io.avail + m * A : nullptr;
         float best = -INFINITY, bestm = -INFINITY;
@@ -535,7 +553,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   __syncthreads();
   TC_STAMP_ONCE(24);
   cluster_sync_all();                   // the leader's MMAs read the peer's shared memory until here
-  if (warp == 5) tmem_dealloc_2sm(tmem, kT2TmemCols);
+  if (warp == kT2EpiWarps + 1) tmem_dealloc_2sm(tmem, kT2TmemCols);
   TC_STAMP_ONCE(25);
   TC_CTA_STAMP(1);
 }
@@ -545,7 +563,7 @@ inline size_t agent_tc2_smem_bytes(const macjd_agent_weights& w) {
 }
 
 inline bool agent_tc2_supported(const macjd_agent_weights& w) {
-  return agent_tc_supported(w) && kTcKc == 32 && kTcChunksPerX == 1 && w.obs_pad <= 256 && agent_tc2_smem_bytes(w) <= 227 * 1024;
+  return agent_tc_supported(w) && kTcKc == 32 && kTcChunksPerX == 1 && agent_tc2_smem_bytes(w) <= 227 * 1024;
 }
 
 inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
@@ -574,18 +592,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tc2_mma_rate
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  if (tid == 0 && rank == 0) {
+  if (warp == 0 && rank == 0) {
+    // whole warp converged, one elected lane issues: operands stay in uniform registers (issued from
+    // inside `if (tid == 0)` every MMA is wrapped in an ELECT / R2UR sequence that costs ~50 cycles)
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t idesc = umma_idesc_tf32(M, N);
     const uint64_t da = umma_smem_desc(smem_u32(tc_smem), 128, 16 * 32);
     const uint64_t db = umma_smem_desc(smem_u32(tc_smem) + 16384, 128, 16 * 32);
     const unsigned long long t0 = clock64();
-    for (int i = 0; i < n; ++i) mma_tf32_ss_2sm(tmem_base + (uint32_t)((i & 1) * 256), da + (uint64_t)((i & 1) * 16), db, idesc, 1u);
-    mma_commit_2sm(&bar);
+    for (int i = 0; i < n; ++i) {
+      const uint32_t d = tb + (uint32_t)((i & 1) * 256);
+      const uint64_t a = da + (uint64_t)((i & 1) * 16);
+      if (elect_one()) mma_tf32_ss_2sm(d, a, db, idesc, 1u);
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit_2sm(&bar);
+    __syncwarp();
     const unsigned long long t1 = clock64();
     mbar_wait_cluster(&bar, 0);
     const unsigned long long t2 = clock64();
-    out[0] = t1 - t0;
-    out[1] = t2 - t0;
+    if (tid == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
   } else if (tid == 0) {
     mbar_wait_cluster(&bar, 0);
   }

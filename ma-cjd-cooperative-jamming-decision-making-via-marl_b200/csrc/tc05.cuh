@@ -46,6 +46,18 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
@@ -294,18 +306,29 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(int M, int N, int n
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  if (tid == 0) {
+  if (warp == 0) {
+    // whole warp converged, one elected lane issues: operands stay in uniform registers (issued from
+    // inside `if (tid == 0)` every MMA is wrapped in an ELECT / R2UR sequence that costs ~50 cycles)
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t idesc = umma_idesc_tf32(M, N);
     const uint64_t da = umma_smem_desc(smem_u32(tc_smem), 128, 16 * 32);
     const uint64_t db = umma_smem_desc(smem_u32(tc_smem) + 16384, 128, 16 * 32);
     const unsigned long long t0 = clock64();
-    for (int i = 0; i < n; ++i) mma_tf32_ss(tmem_base + (uint32_t)((i & 1) * 256), da + (uint64_t)((i & 1) * 16), db, idesc, 1u);
-    mma_commit(&bar);
+    for (int i = 0; i < n; ++i) {
+      const uint32_t d = tb + (uint32_t)((i & 1) * 256);
+      const uint64_t a = da + (uint64_t)((i & 1) * 16);
+      if (elect_one()) mma_tf32_ss(d, a, db, idesc, 1u);
+      __syncwarp();
+    }
+    if (elect_one()) mma_commit(&bar);
+    __syncwarp();
     const unsigned long long t1 = clock64();
     mbar_wait(&bar, 0);
     const unsigned long long t2 = clock64();
-    out[0] = t1 - t0;
-    out[1] = t2 - t0;
+    if (tid == 0) {
+      out[0] = t1 - t0;
+      out[1] = t2 - t0;
+    }
   }
   fence_before_sync();
   __syncthreads();

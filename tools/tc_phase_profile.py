@@ -40,3 +40,4 @@ ext = [v[65 + 2 * b] for b in range(n_cta)]
 e0 = min(ent)
 print(f"{n_cta} CTAs: entry spread {max(ent) - e0} ns; exit min/median/max {min(ext) - e0} / {sorted(ext)[n_cta // 2] - e0} / {max(ext) - e0} ns;"
       f" per-CTA duration min/max {min(x - e for x, e in zip(ext, ent))} / {max(x - e for x, e in zip(ext, ent))} ns")
+
