@@ -30,10 +30,13 @@ struct EnvKernelArgs {
   int stage_ld;       // padded row length of the smem state stage (odd -> no bank conflicts)
   int physics;        // 0: reset (views only, step_count <- 0), 1: full step
   int prefetch;       // issue L2 prefetches for the env's table column first (small batches)
+  uint32_t magic_s4;  // ceil(2^32 / (S/4)), ceil(2^32 / (J*S/4)): exact v / d for the view write-back loops
+  uint32_t magic_js4;
 };
 
-__device__ __forceinline__ double env_tab(const macjd_env_tables& t, int row, int env) {
-  return __ldg(t.data + (int64_t)row * t.row_stride + (int64_t)env * t.env_stride);
+// element `row` of one env's table column (col = data + env * env_stride; row stride fits 32 bits)
+__device__ __forceinline__ double env_tab(const double* col, int row_stride, int row) {
+  return __ldg(col + (int64_t)row * row_stride);
 }
 
 __device__ __forceinline__ double albersheim(const macjd_env_tables& t, double snr) {
@@ -67,10 +70,11 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
   // The physics below walks the scenario tables with data-dependent, serial lookups.  Request
   // this env's whole table column (and its action / noise rows) up front so that the chain runs
   // against L2 instead of DRAM; a warp's requests cover contiguous 256-byte row segments.
+  const double* col = T.data + (int64_t)(live ? e : 0) * T.env_stride;   // this env's table column
+  const int rs = (int)T.row_stride;
   if (live && a.prefetch) {
-    const double* col = T.data + (int64_t)e * T.env_stride;
     const int n_rows = 16 * R + 8 * J + 3 * K;
-    for (int row = 0; row < n_rows; ++row) prefetch_l2(col + (int64_t)row * T.row_stride);
+    for (int row = 0; row < n_rows; ++row) prefetch_l2(col + (int64_t)row * rs);
     if (a.physics) {
       prefetch_l2(io.act_d + (int64_t)e * J);
       prefetch_l2(io.act_p + (int64_t)e * J);
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
       const int Ti = io.act_d[(int64_t)e * J + j];
       double P = (double)io.act_p[(int64_t)e * J + j];
       P = P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
-      const double pmin = env_tab(T, jr + 6, e), pmax = env_tab(T, jr + 7, e);
+      const double pmin = env_tab(col, rs, jr + 6), pmax = env_tab(col, rs, jr + 7);
       const double range = pmax - pmin;
       const double power = pmin + P * range;
       const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
@@ -100,21 +104,21 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
       if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
         const int tgt = (Ti + 1) / 2 - 1;
         const int rr = rbase + 16 * tgt;
-        const double dx = env_tab(T, jr + 4, e) - env_tab(T, rr + 10, e);
-        const double dy = env_tab(T, jr + 5, e) - env_tab(T, rr + 11, e);
+        const double dx = env_tab(col, rs, jr + 4) - env_tab(col, rs, rr + 10);
+        const double dy = env_tab(col, rs, jr + 5) - env_tab(col, rs, rr + 11);
         const double dist = sqrt(dx * dx + dy * dy);
         if (dist > 1e-6) {
           // core/jammer.py:73-98
           const double dsq = fmax(1e-9, dist * dist);
-          const double den = dsq * env_tab(T, jr + 1, e) * env_tab(T, jr + 2, e) * fmax(1e-9, env_tab(T, jr + 3, e));
+          const double den = dsq * env_tab(col, rs, jr + 1) * env_tab(col, rs, jr + 2) * fmax(1e-9, env_tab(col, rs, jr + 3));
           double prj = 0.0;
-          if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * env_tab(T, jr + 0, e) * env_tab(T, rr + 2, e)) / den);
+          if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * env_tab(col, rs, jr + 0) * env_tab(col, rs, rr + 2)) / den);
           if (Ti & 1) {  // suppression
             prjs[tgt * BS + tid] += prj;
             supp_mask |= (1ull << tgt);
           } else {       // deception: false target (environment.py:408-437)
-            const double pn = env_tab(T, rr + 6, e);
-            double snr_f = pn > 1e-18 ? (env_tab(T, rr + 8, e) * prj) / pn : 0.0;
+            const double pn = env_tab(col, rs, rr + 6);
+            double snr_f = pn > 1e-18 ? (env_tab(col, rs, rr + 8) * prj) / pn : 0.0;
             snr_f = fmax(0.0, snr_f);
             const double pd_f = albersheim(T, snr_f);
             const float u = io.noise ? io.noise[(int64_t)e * (RK + J) + RK + j]
@@ -133,10 +137,10 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
     double r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
     for (int r = 0; r < R; ++r) {
       const int rr = rbase + 16 * r;
-      const double pt = env_tab(T, rr + 0, e), gt = env_tab(T, rr + 1, e), gr = env_tab(T, rr + 2, e);
-      const double lam = env_tab(T, rr + 3, e), loss = env_tab(T, rr + 4, e), latm = env_tab(T, rr + 5, e);
-      const double pn = env_tab(T, rr + 6, e), Ga = env_tab(T, rr + 7, e), D = env_tab(T, rr + 8, e);
-      const double rx = env_tab(T, rr + 10, e), ry = env_tab(T, rr + 11, e);
+      const double pt = env_tab(col, rs, rr + 0), gt = env_tab(col, rs, rr + 1), gr = env_tab(col, rs, rr + 2);
+      const double lam = env_tab(col, rs, rr + 3), loss = env_tab(col, rs, rr + 4), latm = env_tab(col, rs, rr + 5);
+      const double pn = env_tab(col, rs, rr + 6), Ga = env_tab(col, rs, rr + 7), D = env_tab(col, rs, rr + 8);
+      const double rx = env_tab(col, rs, rr + 10), ry = env_tab(col, rs, rr + 11);
       const double jam = D * prjs[r * BS + tid];
       const double den1 = jam + pn;
       const double num0 = pt * gt * gr * (lam * lam);
@@ -144,9 +148,9 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
       double red = 0.0;
       for (int k = 0; k < K; ++k) {
         const int tr = tbase + 3 * k;
-        const double dx = rx - env_tab(T, tr + 0, e), dy = ry - env_tab(T, tr + 1, e);
+        const double dx = rx - env_tab(col, rs, tr + 0), dy = ry - env_tab(col, rs, tr + 1);
         const double d = fmax(sqrt(dx * dx + dy * dy), 1e-6);
-        const double num = num0 * env_tab(T, tr + 2, e);
+        const double num = num0 * env_tab(col, rs, tr + 2);
         const double d2 = d * d;
         const double den = four_pi3 * (d2 * d2) * loss * latm;
         const double ps = den > 1e-18 ? num / den : 0.0;
@@ -167,11 +171,11 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
         if (io.detected) io.detected[o] = det ? 1 : 0;
         if (io.snr0) io.snr0[o] = (float)snr0;
         if (io.snr1) io.snr1[o] = (float)fmax(0.0, snr1);
-        if (io.jsr_db) io.jsr_db[o] = (float)(10.0 * log10(jam / sig));
+        if (io.jsr_db) io.jsr_db[o] = 10.0f * log10f((float)(jam / sig));   // float32 output of an extension: float log
       }
       if (io.tracking) io.tracking[(int64_t)r * n + e] = tracked ? 1 : 0;
       if (tracked) {  // memoryless TRACK state (core/radar.py:90-117) -> r_d
-        const double pen = -env_tab(T, rr + 9, e);
+        const double pen = -env_tab(col, rs, rr + 9);
         r_d += fmin(fmax(pen, T.rd_min), T.rd_max);
       }
       if ((supp_mask >> r) & 1ull) r_j_supp += red;
@@ -202,18 +206,18 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
       const int per = 6 + T.n_types;
       for (int r = 0; r < R; ++r) {
         const int rr = rbase + 16 * r, o = r * per;
-        row[o + 0] = (float)env_tab(T, rr + 0, e);          // pt
-        row[o + 1] = (float)env_tab(T, rr + 12, e);         // theta_m
-        row[o + 2] = (float)env_tab(T, rr + 14, e);         // t_s
-        const int ty = (int)env_tab(T, rr + 15, e);
+        row[o + 0] = (float)env_tab(col, rs, rr + 0);          // pt
+        row[o + 1] = (float)env_tab(col, rs, rr + 12);         // theta_m
+        row[o + 2] = (float)env_tab(col, rs, rr + 14);         // t_s
+        const int ty = (int)env_tab(col, rs, rr + 15);
         for (int c = 0; c < T.n_types; ++c) row[o + 3 + c] = (c == ty) ? 1.0f : 0.0f;
-        row[o + 3 + T.n_types] = (float)env_tab(T, rr + 13, e);  // theta_a
-        row[o + 4 + T.n_types] = (float)env_tab(T, rr + 10, e);
-        row[o + 5 + T.n_types] = (float)env_tab(T, rr + 11, e);
+        row[o + 3 + T.n_types] = (float)env_tab(col, rs, rr + 13);  // theta_a
+        row[o + 4 + T.n_types] = (float)env_tab(col, rs, rr + 10);
+        row[o + 5 + T.n_types] = (float)env_tab(col, rs, rr + 11);
       }
       for (int j = 0; j < J; ++j) {
-        row[R * per + 2 * j] = (float)env_tab(T, jbase + 8 * j + 4, e);
-        row[R * per + 2 * j + 1] = (float)env_tab(T, jbase + 8 * j + 5, e);
+        row[R * per + 2 * j] = (float)env_tab(col, rs, jbase + 8 * j + 4);
+        row[R * per + 2 * j + 1] = (float)env_tab(col, rs, jbase + 8 * j + 5);
       }
     }
     __syncthreads();
@@ -224,12 +228,16 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
       const float4* st4 = reinterpret_cast<const float4*>(stage);
       if (io.state) {
         float4* dst = reinterpret_cast<float4*>(io.state + (int64_t)e0 * S);
-        for (int v = tid; v < valid * S4; v += BS) { const int el = v / S4; dst[v] = st4[el * ld4 + (v - el * S4)]; }
+        for (int v = tid; v < valid * S4; v += BS) { const int el = a.magic_s4 ? (int)__umulhi((uint32_t)v, a.magic_s4) : v / S4; dst[v] = st4[el * ld4 + (v - el * S4)]; }
       }
       if (io.obs) {
         const int JS4 = J * S4;
         float4* dst = reinterpret_cast<float4*>(io.obs + (int64_t)e0 * J * S);
-        for (int v = tid; v < valid * JS4; v += BS) { const int el = v / JS4; dst[v] = st4[el * ld4 + (v % S4)]; }
+        for (int v = tid; v < valid * JS4; v += BS) {
+          const int el = a.magic_js4 ? (int)__umulhi((uint32_t)v, a.magic_js4) : v / JS4;
+          const int w = v - el * JS4;                                    // position inside the env's J rows
+          dst[v] = st4[el * ld4 + (w - (a.magic_s4 ? (int)__umulhi((uint32_t)w, a.magic_s4) : w / S4) * S4)];
+        }
       }
     } else {
       if (io.state) {
@@ -259,7 +267,7 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   if (!ctx || !tab || !io) return MACJD_ERR_INVALID_ARG;
   if (tab->n_envs < 0 || tab->n_jammers < 1 || tab->n_radars < 1 || tab->n_targets < 1 || tab->n_types < 1)
     return MACJD_ERR_INVALID_ARG;
-  if (tab->n_radars > 64) return MACJD_ERR_UNSUPPORTED;
+  if (tab->n_radars > 64 || tab->row_stride > 0x7fffffffll || tab->row_stride < 0) return MACJD_ERR_UNSUPPORTED;
   if (!tab->data || !io->step_count) return MACJD_ERR_INVALID_ARG;
   if (physics && (!io->act_d || !io->act_p || !io->reward)) return MACJD_ERR_INVALID_ARG;
   if (tab->n_envs == 0) return MACJD_OK;
@@ -272,6 +280,13 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   // by 4 banks, conflict-free for the row-per-thread writes), else pad to odd.
   a.stage_ld = (a.state_dim % 4 == 0) ? a.state_dim + 4 : (a.state_dim | 1);
   a.physics = physics;
+  // v / d == umulhi(v, ceil(2^32 / d)) whenever v * d < 2^32 (v < 128 * J * S/4 here); 0 = divide
+  {
+    const uint64_t s4 = (uint64_t)a.state_dim / 4, js4 = (uint64_t)tab->n_jammers * s4;
+    const bool ok = s4 >= 2 && 128ull * js4 * js4 < 0x100000000ull;
+    a.magic_s4 = ok ? (uint32_t)((0x100000000ull + s4 - 1) / s4) : 0;
+    a.magic_js4 = ok ? (uint32_t)((0x100000000ull + js4 - 1) / js4) : 0;
+  }
   // latency-bound regime only: with many resident blocks per SM the loads already overlap
   a.prefetch = tab->env_stride != 0 && tab->n_envs <= 16384;   // measured: +15 % at 4096 envs, -6 % at 65536
   int bs = 128;

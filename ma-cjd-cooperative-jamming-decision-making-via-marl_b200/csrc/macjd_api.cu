@@ -101,10 +101,12 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
     a.w = *w;
     a.io = *io;
     // path 2: one CTA per 64 rows; path 3: CTA pairs (cta_group::2), 128 rows per pair;
-    // path 0 picks the pair kernel as soon as there is more than one 64-row tile
+    // path 0 picks the pair kernel whenever it fits -- even for <= 64 rows (a pair MMA of M = 128,
+    // N = 128 takes 37 cycles against 68 for the single-CTA M = 64 one, and each CTA streams half
+    // the weights: 22 vs 33 us per step on the learner's 64-row unroll, tools/tc_small_m.py)
     const bool pair_ok = macjd::tc::agent_tc2_supported(*w);
     if (io->path == 3 && !pair_ok) return MACJD_ERR_UNSUPPORTED;
-    if (io->path == 3 || (io->path == 0 && pair_ok && io->n_rows > macjd::tc::kTcRows))
+    if (io->path == 3 || (io->path == 0 && pair_ok))
       return finish(ctx, macjd::tc::agent_tc2_launch(ctx, a));
     return finish(ctx, macjd::tc::agent_tc_launch(ctx, a));
   }
