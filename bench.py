@@ -101,6 +101,11 @@ def cpu_baseline_run(steps, warmup, n_envs=N_ENVS):
     (vectorised over envs) + eager-PyTorch agent act (all torch threads).  One step = the
     bench workload's step (n_envs envs x n_agents agents)."""
     import torch
+    # torchrun exports OMP_NUM_THREADS=1; the baseline is meant to use every host core it can
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     from macjd_b200.simulation.scenario import default_spec
     from oracle.env_oracle import EnvOracle
     from oracle import agent_oracle as AO
