@@ -148,6 +148,25 @@ def cpu_baseline_run(steps, warmup, n_envs=N_ENVS):
                       f"host has {os.cpu_count()} cores"}
 
 
+def cpu_learner_run(mac, learner, buf, steps):
+    """The oracle port of QMixLearner.train (eager PyTorch autograd, all host threads) on a batch drawn from
+    the same replay ring: the CPU figure beside the learner's train-samples/s."""
+    import torch
+    from oracle import agent_oracle as AO
+    agent_sd = {k: v.detach().cpu().clone() for k, v in mac.agent.state_dict().items()}
+    mixer_sd = {k: v.detach().cpu().clone() for k, v in learner.eval_qmix_net.state_dict().items()}
+    ora = AO.LearnerOracle(agent_sd, mixer_sd, N_AGENTS, 64, 0.99, 5e-6, 1.0, 200)
+    batch = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in buf.sample(LEARNER_B).items()}
+    ora.train(batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ora.train(batch)
+    dt = (time.perf_counter() - t0) / steps
+    return {"train_episodes_per_sec": LEARNER_B / dt, "train_transitions_per_sec": LEARNER_B * (LEARNER_T - 1) / dt,
+            "ms_per_train_step": dt * 1e3, "cores": int(torch.get_num_threads()), "kind": "port",
+            "sample": f"{steps} train steps of B = {LEARNER_B} x T = {LEARNER_T} through oracle/agent_oracle.py LearnerOracle"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -371,10 +390,21 @@ def main():
                    "includes": "replay sample (gather kernel) + 2 unrolls + mixers + TD + backward + clip/Adam"
                                + (" + NCCL all-reduce" if world > 1 else "")}
 
+    # 2 N F_agent (two unrolls) + 3 N F_qhead (q_taken fwd + bwd) + 4 F_mixer per transition
+    f_agent, f_qhead, f_mixer = 415_744, 34_560, 68_288
+    flop_tr = 2 * N_AGENTS * f_agent + 3 * N_AGENTS * f_qhead + 4 * f_mixer
+    l_tflops = LEARNER_B * (LEARNER_T - 1) * flop_tr / dt_l / 1e12
+    learner_rec["roofline"] = {
+        "bound": "tensor", "achieved": l_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": l_tflops / tf32_peak,
+        "flop_per_transition": flop_tr,
+        "note": "B = 32 episodes is 64 agent rows: both 100-step unrolls run on one CTA pair each, so the step is bound by "
+                "the serial depth (2 T dependent GRU steps, SURVEY 8d), not by throughput"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_run(args.cpu_steps, 3)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["learner"] = cpu_learner_run(mac, learner, buf, 2)
 
     if rank == 0:
         line = {"metric": "env_agent_steps_per_sec", "value": value, "unit": "env-agent steps/s", "n_gpus": world,

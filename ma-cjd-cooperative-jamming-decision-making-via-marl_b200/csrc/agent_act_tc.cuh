@@ -196,14 +196,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
   }
   // stage the small vectors
   for (int i = tid; i < H; i += kTcThreads) {
-    S.c.gate_b[i] = make_float4(W.brz[i], W.brz[H + i], W.bin[i], W.bhn[i]);
-    S.c.q_c[i] = make_float4(W.bq1[i], W.w1p[i], W.w2[i], 0.f);
-    S.c.ba1[i] = W.ba1[i]; S.c.ba2[i] = W.ba2[i]; S.c.bfc1[i] = W.bfc1[i];
+    // all loads first (read-only path), then the stores: interleaved, every load waited for the
+    // previous shared-memory store (possible aliasing) -- ten serial DRAM round trips after an L2 flush
+    const float g0 = __ldg(W.brz + i), g1 = __ldg(W.brz + H + i), g2 = __ldg(W.bin + i), g3 = __ldg(W.bhn + i);
+    const float q0 = __ldg(W.bq1 + i), q1 = __ldg(W.w1p + i), q2 = __ldg(W.w2 + i);
+    const float b1 = __ldg(W.ba1 + i), b2 = __ldg(W.ba2 + i), b3 = __ldg(W.bfc1 + i);
     float w3[8], wq[8];
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
-      w3[j] = j < A ? W.wa3t[(size_t)i * A + j] : 0.f;
-      wq[j] = j < A ? W.w1a[(size_t)j * H + i] : 0.f;
+      w3[j] = j < A ? __ldg(W.wa3t + (size_t)i * A + j) : 0.f;
+      wq[j] = j < A ? __ldg(W.w1a + (size_t)j * H + i) : 0.f;
     }
+    S.c.gate_b[i] = make_float4(g0, g1, g2, g3);
+    S.c.q_c[i] = make_float4(q0, q1, q2, 0.f);
+    S.c.ba1[i] = b1; S.c.ba2[i] = b2; S.c.bfc1[i] = b3;
     S.c.wa3t[2 * i] = make_float4(w3[0], w3[1], w3[2], w3[3]);
     S.c.wa3t[2 * i + 1] = make_float4(w3[4], w3[5], w3[6], w3[7]);
     S.c.w1a[2 * i] = make_float4(wq[0], wq[1], wq[2], wq[3]);

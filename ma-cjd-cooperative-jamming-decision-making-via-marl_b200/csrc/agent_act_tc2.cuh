@@ -33,9 +33,19 @@ constexpr int kT2EpiThreads = 32 * kT2EpiWarps;
 constexpr int kT2Threads = kT2EpiThreads + 64;             // + weight-stream warp + MMA / relay warp
 constexpr int kT2Upt = 64 / kT2ColSplit;                   // output units per epilogue thread
 constexpr int kT2Parts = 2 * kT2ColSplit;                  // threads that share one row
+// Accumulator columns (2-SM layout: 64 columns per 128-unit accumulator).  All seven layer
+// accumulators of a step are live at once -- the recurrent products are issued before the
+// actor's second layer and the actor head is evaluated while the input products run -- so none
+// of them share columns; only Q reuses actor.0's.
 constexpr uint32_t kT2ColA1 = 0, kT2ColFc1 = 64, kT2ColA2 = 128;
-constexpr uint32_t kT2ColR = 0, kT2ColZ = 64, kT2ColIn = 128, kT2ColHn = 192, kT2ColQ = 0;
-constexpr uint32_t kT2TmemCols = 256;
+constexpr uint32_t kT2ColR = 192, kT2ColZ = 256, kT2ColIn = 320, kT2ColHn = 384, kT2ColQ = 0;
+constexpr uint32_t kT2TmemCols = 512;
+// Issue order of the eight K = 128 layers of a step, and where each sits in the packed weights
+// (order there: 0 actor.2, 1 W_ir, 2 W_hr, 3 W_iz, 4 W_hz, 5 W_in, 6 W_hn, 7 q.0[:, :H]):
+//   slot: 0 W_hr  1 W_hz  2 W_hn  3 actor.2  4 W_ir  5 W_iz  6 W_in  7 q.0
+// The three recurrent products need nothing from this step's epilogues, so they run while the
+// epilogue warps turn actor.0 into a1; the input products come after xf is written.
+constexpr uint32_t kT2LayerSrc = 0x75310642u;    // nibble s = packed index of slot s
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -146,6 +156,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   float* const xhi = S.b0hi;   // the observation block lives in b0 until E1 overwrites it with a1
   float* const xlo = S.b0lo;
 
+  // Epilogue threads request their slice of the incoming hidden state and of the first observation
+  // block right away, so those (cold) loads overlap the constant staging, the cluster barrier and
+  // the TMEM allocation instead of following them.
+  float4 h_in[kT2Upt / 4];
+  float x_in[32 / kT2Parts];
+  if (warp < kT2EpiWarps) {
+    const int q4 = warp & 3, ch = warp >> 2, half = q4 >> 1;
+    const int r = (q4 & 1) * 32 + lane, ub = half * 64 + ch * kT2Upt, part = half * kT2ColSplit + ch;
+    const bool live = r < valid;
+    const bool have = io.hidden && !io.hidden_zero_init && live;
+#pragma unroll
+    for (int i = 0; i < kT2Upt / 4; ++i)
+      h_in[i] = have ? __ldg(reinterpret_cast<const float4*>(io.hidden + (size_t)(row0 + r) * H + ub) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 32 / kT2Parts; ++j) {
+      const int kk = part * (32 / kT2Parts) + j;
+      x_in[j] = (live && kk < O) ? __ldg(io.obs + (size_t)(row0 + r) * O + kk) : 0.f;
+    }
+  }
+
   warm_weights_l2(W.tc_chunks, chunks_per_step, kT2Threads);
 
   if (tid == 0) {
@@ -155,14 +185,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
     fence_mbar_init();
   }
   for (int i = tid; i < H; i += kT2Threads) {
-    S.c.gate_b[i] = make_float4(W.brz[i], W.brz[H + i], W.bin[i], W.bhn[i]);
-    S.c.q_c[i] = make_float4(W.bq1[i], W.w1p[i], W.w2[i], 0.f);
-    S.c.ba1[i] = W.ba1[i]; S.c.ba2[i] = W.ba2[i]; S.c.bfc1[i] = W.bfc1[i];
+    // all loads first (read-only path), then the stores: interleaved, every load waited for the
+    // previous shared-memory store (possible aliasing) -- ten serial DRAM round trips after an L2 flush
+    const float g0 = __ldg(W.brz + i), g1 = __ldg(W.brz + H + i), g2 = __ldg(W.bin + i), g3 = __ldg(W.bhn + i);
+    const float q0 = __ldg(W.bq1 + i), q1 = __ldg(W.w1p + i), q2 = __ldg(W.w2 + i);
+    const float b1 = __ldg(W.ba1 + i), b2 = __ldg(W.ba2 + i), b3 = __ldg(W.bfc1 + i);
     float w3[8], wq[8];
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
-      w3[j] = j < A ? W.wa3t[(size_t)i * A + j] : 0.f;
-      wq[j] = j < A ? W.w1a[(size_t)j * H + i] : 0.f;
+      w3[j] = j < A ? __ldg(W.wa3t + (size_t)i * A + j) : 0.f;
+      wq[j] = j < A ? __ldg(W.w1a + (size_t)j * H + i) : 0.f;
     }
+    S.c.gate_b[i] = make_float4(g0, g1, g2, g3);
+    S.c.q_c[i] = make_float4(q0, q1, q2, 0.f);
+    S.c.ba1[i] = b1; S.c.ba2[i] = b2; S.c.bfc1[i] = b3;
     S.c.wa3t[2 * i] = make_float4(w3[0], w3[1], w3[2], w3[3]);
     S.c.wa3t[2 * i + 1] = make_float4(w3[4], w3[5], w3[6], w3[7]);
     S.c.w1a[2 * i] = make_float4(wq[0], wq[1], wq[2], wq[3]);
@@ -189,7 +225,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       for (int t = 0; t < T; ++t) {
         for (int L = 0; L < supers_per_step; ++L) {
           if (t > 0 || L >= kT2Stages) { mbar_wait_cluster(&S.w_empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
-          const char* src = wsrc + (size_t)L * 2 * kTcChunkBytes + (size_t)rank * kT2HalfBytes;
+          // stages follow the issue order; the packed buffer keeps the single-CTA kernel's layer order
+          const int Lsrc = L < nxc ? L : nxc + 2 * (int)((kT2LayerSrc >> (4 * ((L - nxc) >> 1))) & 0xFu) + ((L - nxc) & 1);
+          const char* src = wsrc + (size_t)Lsrc * 2 * kTcChunkBytes + (size_t)rank * kT2HalfBytes;
           mbar_expect_tx(&S.w_full[s], kT2StageBytes);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
@@ -239,16 +277,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
             d0 = kT2ColA1; d1 = kT2ColFc1; first0 = first1 = (L == 0);
             pre = 1; post = 1u | (L == nxc - 1 ? 2u : 0u);
           } else {                             // K = 128 layers: 4 chunks = 2 stages each
-            //  j:  0 actor.2 (b0)  1 W_ir (b0)  2 W_hr (h)  3 W_iz (b0)  4 W_hz (h)  5 W_in (b0)  6 W_hn (h)  7 q.0[:, :H] (h)
+            //  slot j:  0 W_hr (h)  1 W_hz (h)  2 W_hn (h)  3 actor.2 (b0)  4 W_ir (b0)  5 W_iz (b0)  6 W_in (b0)  7 q.0 (h)
             const uint32_t j = (uint32_t)(L - nxc) >> 1, hf = (uint32_t)(L - nxc) & 1u;
-            const bool use_h = (0xD4u >> j) & 1u;          // layers 2, 4, 6, 7 read h
+            const bool use_h = (0x87u >> j) & 1u;          // slots 0, 1, 2, 7 read h
             ahi = use_h ? hh : bh; alo = use_h ? hl : bl; sbo = H * 32;
             koff0 = (2 * hf) * kTcAStep; koff1 = (2 * hf + 1) * kTcAStep;
-            d0 = d1 = 64u * ((0x03211002u >> (4 * j)) & 0xFu);   // accumulator column / 64 per layer
-            first0 = ((0xEBu >> j) & 1u) & (hf == 0 ? 1u : 0u);  // layers 2 and 4 accumulate onto the W_i* product
+            // accumulator column / 64 per slot: R 3, Z 4, Hn 6, A2 2, R 3, Z 4, In 5, Q 0
+            d0 = d1 = 64u * ((0x05432643u >> (4 * j)) & 0xFu);
+            first0 = ((0xCFu >> j) & 1u) & (hf == 0 ? 1u : 0u);  // W_ir, W_iz accumulate onto the recurrent product
             first1 = 0;
-            pre = (hf == 0 && ((0x83u >> j) & 1u)) ? 2u : 0u;    // actor.2, W_ir, q.0 wait for the epilogue's tile
-            post = (hf == 1 && ((0xC1u >> j) & 1u)) ? 2u : 0u;   // after actor.2, W_hn, q.0 the epilogue may read
+            pre = (hf == 0 && ((0x98u >> j) & 1u)) ? 2u : 0u;    // actor.2 (a1), W_ir (xf), q.0 (h') wait for the epilogue's tile
+            post = (hf == 1 && ((0xC8u >> j) & 1u)) ? 2u : 0u;   // after actor.2, W_in, q.0 the epilogue may read
           }
           if (pre == 1) { mbar_wait_cluster(&S.x_full, x_full_par); x_full_par ^= 1u; if (lane == 0) TC_STAMP(32); }
           if (pre == 2) {
@@ -305,16 +344,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
     const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * kT2Upt);
     uint32_t d_par = 0, x_empty_par = 0;
 
-    {
-      const bool have = io.hidden && !io.hidden_zero_init && live;
-      for (int k = ub; k < ub + kT2Upt; k += 4) {
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (have) {
-          const float4 x = *reinterpret_cast<const float4*>(io.hidden + (size_t)(row0 + r) * H + k);
-          v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-        }
-        store_split4(S.hhi, S.hlo, r, k, H, v);
-      }
+#pragma unroll
+    for (int i = 0; i < kT2Upt / 4; ++i) {
+      const float v[4] = {h_in[i].x, h_in[i].y, h_in[i].z, h_in[i].w};
+      store_split4(S.hhi, S.hlo, r, ub + 4 * i, H, v);
     }
 
     for (int t = 0; t < T; ++t) {
@@ -323,10 +356,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       for (int xc = 0; xc < nxc; ++xc) {
         if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
         const float* obs = io.obs + (tM + row0 + r) * O;
-        for (int k = part * (32 / kT2Parts); k < (part + 1) * (32 / kT2Parts); k += 4) {
+        const bool pre = (t == 0 && xc == 0);      // already in registers (requested at kernel entry)
+#pragma unroll
+        for (int g = 0; g < 32 / kT2Parts / 4; ++g) {
+          const int k = part * (32 / kT2Parts) + 4 * g;
           float v[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) { const int kk = xc * 32 + k + j; v[j] = (live && kk < O) ? __ldg(obs + kk) : 0.f; }
+          for (int j = 0; j < 4; ++j) {
+            const int kk = xc * 32 + k + j;
+            v[j] = pre ? x_in[4 * g + j] : ((live && kk < O) ? __ldg(obs + kk) : 0.f);
+          }
           store_split4(xhi, xlo, r, k, 32, v);
         }
         fence_async_smem();
@@ -357,10 +396,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       mbar_arrive_cluster(&S.a_ready, 0);
       EP_STAMP(3);
 
-      // ---- E2: actor head;  E3: xf = relu(D3 + b) -> B0
+      // ---- E3: xf = relu(D3 + b) -> B0 (releases the input products), then E2: actor head while they run
       epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(4);
+      for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
+        float v[16];
+        tmem_ld16_nowait(tl + kT2ColFc1 + (uint32_t)c0, v);
+        tmem_ld_wait();
+        reg_fence(v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * q + j] + S.c.bfc1[ub + c0 + 4 * q + j], 0.f);
+          store_split4(S.b0hi, S.b0lo, r, ub + c0 + 4 * q, H, o);
+        }
+      }
+      fence_async_smem();
+      fence_before_sync();
+      mbar_arrive_cluster(&S.a_ready, 0);
+      EP_STAMP(5);
       {
         float acc[8];
 #pragma unroll
@@ -394,23 +450,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
               Ps[j * kTcRows + r] = sigmoid_fast(sum);
             }
       }
-      EP_STAMP(5);
-      for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
-        float v[16];
-        tmem_ld16_nowait(tl + kT2ColFc1 + (uint32_t)c0, v);
-        tmem_ld_wait();
-        reg_fence(v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = fmaxf(v[4 * q + j] + S.c.bfc1[ub + c0 + 4 * q + j], 0.f);
-          store_split4(S.b0hi, S.b0lo, r, ub + c0 + 4 * q, H, o);
-        }
-      }
-      fence_async_smem();
-      fence_before_sync();
-      mbar_arrive_cluster(&S.a_ready, 0);
       EP_STAMP(6);
 
       // ---- E4: GRU gates -> h' (in place over h), global hidden outputs
