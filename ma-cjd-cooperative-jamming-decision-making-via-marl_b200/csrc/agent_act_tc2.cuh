@@ -353,6 +353,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
     for (int t = 0; t < T; ++t) {
       const size_t tM = (size_t)t * M;
       EP_STAMP(0);
+      // this step's availability mask, requested now and used in E5 (a cold load at the end of the
+      // step would sit on the critical path)
+      uint8_t av_in[8];
+#pragma unroll
+      for (int act = 0; act < 8; ++act)
+        av_in[act] = (part == 0 && live && io.avail && act < A) ? __ldg(io.avail + (tM + row0 + r) * A + act) : (uint8_t)1;
       for (int xc = 0; xc < nxc; ++xc) {
         if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
         const float* obs = io.obs + (tM + row0 + r) * O;
@@ -537,7 +543,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       fence_before_sync();
       if (part == 0 && live) {
         const size_t m = tM + row0 + r;
-        const uint8_t* av = io.avail ? io.avail + m * A : nullptr;
+        uint32_t av_mask = 0;
+#pragma unroll
+        for (int act = 0; act < 8; ++act) av_mask |= (av_in[act] != 0 ? 1u : 0u) << act;
         float best = -INFINITY, bestm = -INFINITY;
         int bi = 0, bim = 0, n_avail = 0;
         for (int act = 0; act < A; ++act) {
@@ -546,7 +554,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           if (io.q_all) io.q_all[m * A + act] = q;
           if (io.params_all) io.params_all[m * A + act] = p;
           if (q > best) { best = q; bi = act; }
-          const bool ok = av ? (av[act] != 0) : true;
+          const bool ok = (av_mask >> act) & 1u;
           n_avail += ok ? 1 : 0;
           const float qm = ok ? q : -INFINITY;
           if (qm > bestm) { bestm = qm; bim = act; }
@@ -572,7 +580,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
                 kth = kth >= navl ? navl - 1 : kth;
                 chosen = 0;
                 for (int act = 0, seen = 0; act < A; ++act) {
-                  const bool ok = (n_avail == 0) || !av || av[act] != 0;
+                  const bool ok = (n_avail == 0) || ((av_mask >> act) & 1u);
                   if (ok) { if (seen == kth) { chosen = act; break; } ++seen; }
                 }
               }
