@@ -329,8 +329,9 @@ def main():
                 "peak_source": ("TF32 dense = MEASURED_PEAKS.json bf16_tflops / 2 (of measured)" if "bf16_tflops" in peaks
                                 else "TF32 dense = fallback 1590 / 2 (of fallback)"),
                 "note": "achieved counts algorithmic FLOPs once; the 3xTF32 split executes 3x that on the tensor pipe. "
-                        "CTA pairs issue M=128,N=128,K=8 cta_group::2 MMAs: ~52 cycles each from one issuing thread against 32 at the pipe's peak "
-                        "(tools/tc_mma_rate.py), and MMA phases alternate with epilogue phases: issue- and dependency-bound, not at the roofline",
+                        "CTA pairs issue M=128,N=128,K=8 cta_group::2 MMAs; inside the MMA phases they run at ~53 cycles each against the "
+                        "pipe's 36.8 (refill latency of the 2-stage weight ring, tools/tc_mma_rate.py), and the MMA phases alternate "
+                        "with epilogue phases along the layer dependency chain: latency-bound at 64 rows per SM, not at the roofline",
                 "simt_kernel": {"kernel": "agent_forward_kernel<256>", "bound": "fp32", "us_per_launch": dt_simt * 1e6,
                                 "achieved": M * fpr / dt_simt / 1e12, "peak": fp32_peak,
                                 "frac": M * fpr / dt_simt / 1e12 / fp32_peak,

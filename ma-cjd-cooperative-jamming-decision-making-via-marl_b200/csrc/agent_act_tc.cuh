@@ -45,10 +45,6 @@ constexpr uint32_t kTcAStep = kTcKc * 32;                 // A-tile byte offset 
 constexpr int kTcChunkFloats = 2 * kTcH * kTcKc;          // hi + lo
 constexpr int kTcChunkBytes = kTcChunkFloats * 4;         // 16 KB
 constexpr int kTcThreads = 192;       // 4 epilogue warps + weight-stream warp + MMA warp
-#ifndef MACJD_TC_PIECES
-#define MACJD_TC_PIECES 4
-#endif
-constexpr int kTcPieces = MACJD_TC_PIECES;
 
 __device__ float g_tc_sink;
 

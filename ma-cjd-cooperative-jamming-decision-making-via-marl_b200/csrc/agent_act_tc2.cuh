@@ -9,13 +9,19 @@
 // issues one M = 128, N = 128 tcgen05.mma.cta_group::2 per k-step and split product for both,
 // and the weight bytes streamed from L2 per row halve.
 //
-// Per CTA (rank r of the pair): warps 0-3 epilogue, warp 4 weight stream (its half of each
-// chunk), warp 5 = MMA issuer (leader) or stage relay (peer: tells the leader when the peer's
+// Per CTA (rank r of the pair): warps 0-7 epilogue, warp 8 weight stream (its half of each
+// chunk), warp 9 = MMA issuer (leader: the whole warp runs the stage loop so that every operand is
+// warp-uniform, one elected lane issues) or stage relay (peer: tells the leader when the peer's
 // half has landed).  Accumulators: 2-SM M = 128 layout -- this CTA's row i on TMEM lane i for
 // output units 0-63 and on lane 64 + i for units 64-127 (same columns) -- so epilogue warp w
-// owns rows 32 (w & 1) .. +31 and units 64 (w >> 1) .. +63 with plain 32x32b loads; row sums
-// (actor head, Q tail) are combined across the two unit halves through shared memory.
+// (TMEM lane quarter w % 4) owns rows 32 (w & 1) .. +31, the 64-unit half (w >> 1) & 1 and, of
+// that half, units 32 (w >> 2) .. +31, with plain 32x32b loads; row sums (actor head, Q tail)
+// are combined across the four threads of a row through shared memory.
 // Cross-CTA events use cluster-scope mbarrier arrives (mapa) and multicast tcgen05.commit.
+//
+// Order inside a step (all seven accumulators live in separate TMEM columns):
+//   issuer:   [actor.0 | fc1] x  ->  W_hr h, W_hz h, W_hn h  ->  actor.2 a1  ->  W_ir xf, W_iz xf, W_in xf  ->  q.0 h'
+//   epilogue: x tile -> E1 (a1) .............. -> E3 (xf), E2 (actor head P) ....... -> E4 (gates, h') -> E5 (Q, selection)
 #pragma once
 #include "agent_act_tc.cuh"
 
