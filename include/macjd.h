@@ -214,11 +214,22 @@ typedef struct macjd_agent_io {
   int32_t* actions;           /* [T][M] chosen discrete action; NULL = no selection     */
   float* power;               /* [T][M] P of the chosen action (mac.py:151-164)         */
   float* q_chosen;            /* [T][M] Q of the chosen action, optional                */
+  int32_t part;               /* 0 = the whole step (default); the CTA-pair kernel also runs the two
+                                 halves of a step separately, for time-unrolled use where only
+                                 the recurrence is sequential (core/qmix.py:217-280):
+                                 1 = recurrence only: h <- GRU(relu(fc1 obs_t), h) for T steps,
+                                     writes hidden / hidden_seq, nothing else;
+                                 2 = heads only (n_steps = 1): `hidden` is the post-GRU state of
+                                     every row (read, not updated); actor, Q-head, selection.
+                                 Other kernels return MACJD_ERR_UNSUPPORTED for part != 0.   */
+  int32_t reserved2;
 } macjd_agent_io;
 
 /* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);
  * Q_a <- Qhead(h, a, P_a) for all a; masked epsilon-greedy / argmax / gathers. */
 MACJD_API int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io);
+/* 1 if the CTA-pair tensor-core kernel (io->path 3 / auto, io->part 1 and 2) can run these weights. */
+MACJD_API int macjd_agent_pair_supported(const macjd_agent_weights* w);
 
 /* Host-buffer form of BasicMAC.select_actions (core/mac.py:59-187: numpy observations and
  * availability masks in, chosen discrete actions and their power levels out).  `io` is a

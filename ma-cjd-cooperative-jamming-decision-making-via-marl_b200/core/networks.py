@@ -203,8 +203,9 @@ class RNNAgent(nn.Module):
     @torch.no_grad()
     def run(self, obs, hidden=None, *, n_steps=1, zero_init=False, avail=None, epsilon=0.0, test_mode=True,
             u_eps=None, rand_actions=None, seed=0, rng_step=0, select=False, want_q=False, want_params=False,
-            want_greedy=False, sel_actions=None, want_hidden_seq=False, tile_rows=0, out=None, path=None):
-        """One fused launch.  obs float32 [T, M, O] (or [M, O]); hidden float32 [M, H] updated in
+            want_greedy=False, sel_actions=None, want_hidden_seq=False, tile_rows=0, out=None, path=None,
+            split_unroll=True):
+        """One fused launch (two for a time-unrolled call on the CTA-pair kernel, see below).  obs float32 [T, M, O] (or [M, O]); hidden float32 [M, H] updated in
         place.  Returns a dict with the requested outputs."""
         dev = self.fc1.weight.device
         if obs.device != dev or obs.dtype != torch.float32:
@@ -255,16 +256,42 @@ class RNNAgent(nn.Module):
         if rand_actions is not None:
             rand_actions = rand_actions.to(device=dev, dtype=torch.int32).reshape(T, M).contiguous()
         p = N.ptr
-        io = N.AgentIO(
-            n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden),
-            hidden_zero_init=int(zero_init), test_mode=int(test_mode), tile_rows=int(tile_rows), path=int(self.path if path is None else path),
-            hidden_seq=p(out.get("hidden_seq")), q_all=p(out.get("q_all")), params_all=p(out.get("params_all")),
-            greedy=p(out.get("greedy")), sel_actions=p(sel_actions), q_sel=p(out.get("q_sel")),
-            avail=p(avail), u_eps=p(u_eps), rand_actions=p(rand_actions), epsilon=float(epsilon),
-            rng_step=int(rng_step) & 0xFFFFFFFF, seed=int(seed) & 0xFFFFFFFFFFFFFFFF,
-            actions=p(out.get("actions")), power=p(out.get("power")), q_chosen=p(out.get("q_chosen")))
+        path = int(self.path if path is None else path)
+        common = dict(test_mode=int(test_mode), tile_rows=int(tile_rows), path=path, epsilon=float(epsilon),
+                      rng_step=int(rng_step) & 0xFFFFFFFF, seed=int(seed) & 0xFFFFFFFFFFFFFFFF, reserved2=0)
+        heads = dict(q_all=p(out.get("q_all")), params_all=p(out.get("params_all")), greedy=p(out.get("greedy")),
+                     sel_actions=p(sel_actions), q_sel=p(out.get("q_sel")), avail=p(avail), u_eps=p(u_eps),
+                     rand_actions=p(rand_actions), actions=p(out.get("actions")), power=p(out.get("power")),
+                     q_chosen=p(out.get("q_chosen")))
+        wants_heads = want_q or want_params or want_greedy or sel_actions is not None or select
+        if split_unroll and T > 1 and path in (0, 3) and (not select or test_mode) and self._pair_kernel_ok(pk):
+            # Time-unrolled use (core/qmix.py:217-280): only h_t -> h_t+1 is sequential.  The CTA-pair
+            # kernel runs the recurrence alone for the T steps (6 of the 8 layer products, 2 of the 5
+            # epilogues per step), then actor + Q-head + arg-max for all T x M rows in one parallel
+            # launch on the stored hidden states -- bit-identical to the fused per-step order.
+            hs = out.get("hidden_seq")
+            if hs is None:
+                hs = torch.empty(T, M, H, dtype=torch.float32, device=dev)
+            io = N.AgentIO(n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden), hidden_zero_init=int(zero_init),
+                           hidden_seq=p(hs), part=1, **common)
+            self.lib().call("macjd_agent_forward", self._ctx(), pk.cstruct(), io)
+            if wants_heads:
+                io = N.AgentIO(n_rows=T * M, n_steps=1, obs=p(obs), hidden=p(hs), hidden_zero_init=0, part=2,
+                               **common, **heads)
+                self.lib().call("macjd_agent_forward", self._ctx(), pk.cstruct(), io)
+            return out
+        io = N.AgentIO(n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden), hidden_zero_init=int(zero_init),
+                       hidden_seq=p(out.get("hidden_seq")), part=0, **common, **heads)
         self.lib().call("macjd_agent_forward", self._ctx(), pk.cstruct(), io)
         return out
+
+    def _pair_kernel_ok(self, pk):
+        ok = getattr(pk, "_pair_ok", None)
+        if ok is None:
+            fn = self.lib().lib.macjd_agent_pair_supported
+            fn.restype = N.C.c_int
+            ok = pk._pair_ok = bool(fn(N.C.byref(pk.cstruct())))
+        return ok
 
     # ---- reference API
     def init_hidden(self):

@@ -162,46 +162,49 @@ class QMixLearner:
         H = self.args.rnn_hidden_dim
         agent, tgt_agent = self.mac.agent, self.target_mac.agent
         obs = tb["obs"].view(T, M, -1)
+        # networks.py:157-158 raises on an action index outside [0, A).  Checked here, before the long
+        # unrolls are queued: the read-back then only waits for the batch preparation (checked later it
+        # would block the host until both unrolls finish and serialise the rest of the step behind them).
+        if int(tb["a_d"].numel()):
+            lo_hi = torch.stack([tb["a_d"].min(), tb["a_d"].max()]).tolist()
+            if lo_hi[0] < 0 or lo_hi[1] >= A:
+                raise IndexError(f"Action index out of bounds, n_actions: {A}")
 
-        # 1-2. unrolls from a zero hidden state (qmix.py:129-147).  The two networks are
-        # independent until the double-DQN gather, so the target unroll runs on a side stream
-        # next to the eval unroll (each occupies only a few SMs at training batch sizes).
+        # 1-2. unrolls from a zero hidden state (qmix.py:129-147).  The two networks are independent
+        # until the double-DQN gather, and neither feeds steps 4-5 (Q of the taken actions from the
+        # STORED hidden states, eval mixer), so both unrolls go to side streams -- each occupies one
+        # CTA pair -- and the main stream computes 4-5 underneath them.
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         if dev.type == "cuda":
             cur = torch.cuda.current_stream(dev)
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream(device=dev)
-            side = self._side_stream
+                self._side_stream2 = torch.cuda.Stream(device=dev)
+            side, side2 = self._side_stream, self._side_stream2
             side.wait_stream(cur)
+            side2.wait_stream(cur)
             with torch.cuda.stream(side):
                 tg = tgt_agent.run(obs, None, n_steps=T, zero_init=True, want_q=True)
-            ev = agent.run(obs, None, n_steps=T, zero_init=True, want_greedy=True)
-            cur.wait_stream(side)
-            tg["q_all"].record_stream(cur)
+            with torch.cuda.stream(side2):
+                ev = agent.run(obs, None, n_steps=T, zero_init=True, want_greedy=True)
         else:
             tg = tgt_agent.run(obs, None, n_steps=T, zero_init=True, want_q=True)
             ev = agent.run(obs, None, n_steps=T, zero_init=True, want_greedy=True)
-        tq_taken = f32(R, Nn)
-        L.callv("macjd_gather_q", ctx, R * Nn, A, tg["q_all"][1:], ev["greedy"][1:], tq_taken)
 
-        # 3. target mixer (qmix.py:151)
         dims = N.MixerDims(n_rows=R, state_dim=S, n_agents=Nn, embed_dim=self.args.mixing_embed_dim,
                            hyper_hidden=self.args.hyper_hidden_dim, reserved=0)
         ws_floats = L.lib.macjd_mixer_workspace_floats(dims)
-        ws = self._workspace("mixer", ws_floats, dev)
+        ws = self._workspace("mixer", ws_floats, dev)              # eval mixer: intermediates kept for the backward
+        ws_tgt = self._workspace("mixer_tgt", ws_floats, dev)
         tq_tot, q_tot, dq_tot, targets = f32(R), f32(R), f32(R), f32(R)
         states_next = tb["state"][1:T].reshape(R, S)
         states_cur = tb["state"][0:T - 1].reshape(R, S)
-        L.callv("macjd_mixer_forward", ctx, dims, self._mixer_struct(self.target_qmix_net), tq_taken, states_next,
-                tq_tot, ws, ws_floats)
 
         # 4. Q(s_t, a_t, P_t) from the stored hidden states (qmix.py:161-184)
         qd = N.QheadDims(n_rows=R * Nn, hidden=H, n_actions=A, reserved=0)
         pk = agent.packed().cstruct()
         hidden = tb["hidden"].view(R * Nn, H)
         a_d, a_c = tb["a_d"].view(-1), tb["a_c"].view(-1)
-        if int(a_d.numel()) and (int(a_d.min()) < 0 or int(a_d.max()) >= A):
-            raise IndexError(f"Action index out of bounds, n_actions: {A}")      # networks.py:157-158
         q_taken = f32(R * Nn)
         hid = self._workspace("qhead_hid", R * Nn * H, dev)
         L.callv("macjd_qhead_forward", ctx, qd, pk, hidden, a_d, a_c, q_taken, hid)
@@ -209,6 +212,17 @@ class QMixLearner:
         # 5. eval mixer (qmix.py:187); leaves its intermediates in the workspace
         eval_struct = self._mixer_struct(self.eval_qmix_net)
         L.callv("macjd_mixer_forward", ctx, dims, eval_struct, q_taken, states_cur, q_tot, ws, ws_floats)
+
+        # 3. double-DQN gather and target mixer (qmix.py:143-151): first use of the unrolls
+        if dev.type == "cuda":
+            cur.wait_stream(side)
+            cur.wait_stream(side2)
+            tg["q_all"].record_stream(cur)
+            ev["greedy"].record_stream(cur)
+        tq_taken = f32(R, Nn)
+        L.callv("macjd_gather_q", ctx, R * Nn, A, tg["q_all"][1:], ev["greedy"][1:], tq_taken)
+        L.callv("macjd_mixer_forward", ctx, dims, self._mixer_struct(self.target_qmix_net), tq_taken, states_next,
+                tq_tot, ws_tgt, ws_floats)
 
         # 6. TD targets and masked loss sums (qmix.py:155,191-194)
         opt = self._ensure_opt_state()

@@ -52,6 +52,11 @@ constexpr uint32_t kT2TmemCols = 512;
 // The three recurrent products need nothing from this step's epilogues, so they run while the
 // epilogue warps turn actor.0 into a1; the input products come after xf is written.
 constexpr uint32_t kT2LayerSrc = 0x75310642u;    // nibble s = packed index of slot s
+// io.part selects which slots a launch runs, in this order (nibble i = i-th slot):
+//   0 whole step: 0..7;  1 recurrence only: the six GRU products;  2 heads only: q.0 (on the given
+//   hidden state), then actor.2 -- one accumulator hand-over fewer, each gated by the epilogue.
+__device__ __forceinline__ uint32_t t2_slot_seq(int part) { return part == 1 ? 0x00654210u : part == 2 ? 0x00000037u : 0x76543210u; }
+__device__ __forceinline__ int t2_slot_count(int part) { return part == 1 ? 6 : part == 2 ? 2 : 8; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -158,7 +163,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   float* Qs = Ps + (size_t)A * kTcRows;
   const int nxc = Op / 32;
   const int chunks_per_step = 2 * kTcChunksPerX * nxc + 8 * kTcChunksPerH;
-  const int supers_per_step = chunks_per_step / 2;
+  const int mode = io.part;            // 0 whole step, 1 recurrence only, 2 heads only
+  const uint32_t slot_seq = t2_slot_seq(mode);
+  const int supers_per_step = nxc + 2 * t2_slot_count(mode);     // ring stages this launch runs per step
   float* const xhi = S.b0hi;   // the observation block lives in b0 until E1 overwrites it with a1
   float* const xlo = S.b0lo;
 
@@ -232,7 +239,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         for (int L = 0; L < supers_per_step; ++L) {
           if (t > 0 || L >= kT2Stages) { mbar_wait_cluster(&S.w_empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
           // stages follow the issue order; the packed buffer keeps the single-CTA kernel's layer order
-          const int Lsrc = L < nxc ? L : nxc + 2 * (int)((kT2LayerSrc >> (4 * ((L - nxc) >> 1))) & 0xFu) + ((L - nxc) & 1);
+          const int slot = L < nxc ? 0 : (int)((slot_seq >> (4 * ((L - nxc) >> 1))) & 0xFu);
+          const int Lsrc = L < nxc ? L : nxc + 2 * (int)((kT2LayerSrc >> (4 * slot)) & 0xFu) + ((L - nxc) & 1);
           const char* src = wsrc + (size_t)Lsrc * 2 * kTcChunkBytes + (size_t)rank * kT2HalfBytes;
           mbar_expect_tx(&S.w_full[s], kT2StageBytes);
 #pragma unroll
@@ -284,16 +292,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
             pre = 1; post = 1u | (L == nxc - 1 ? 2u : 0u);
           } else {                             // K = 128 layers: 4 chunks = 2 stages each
             //  slot j:  0 W_hr (h)  1 W_hz (h)  2 W_hn (h)  3 actor.2 (b0)  4 W_ir (b0)  5 W_iz (b0)  6 W_in (b0)  7 q.0 (h)
-            const uint32_t j = (uint32_t)(L - nxc) >> 1, hf = (uint32_t)(L - nxc) & 1u;
+            const uint32_t j = (slot_seq >> (4 * ((uint32_t)(L - nxc) >> 1))) & 0xFu, hf = (uint32_t)(L - nxc) & 1u;
             const bool use_h = (0x87u >> j) & 1u;          // slots 0, 1, 2, 7 read h
             ahi = use_h ? hh : bh; alo = use_h ? hl : bl; sbo = H * 32;
             koff0 = (2 * hf) * kTcAStep; koff1 = (2 * hf + 1) * kTcAStep;
             // accumulator column / 64 per slot: R 3, Z 4, Hn 6, A2 2, R 3, Z 4, In 5, Q 0
-            d0 = d1 = 64u * ((0x05432643u >> (4 * j)) & 0xFu);
+            // (heads only: q.0 is issued before actor.0's accumulator has been read, so it takes W_hn's columns)
+            d0 = d1 = 64u * (((mode == 2 ? 0x65432643u : 0x05432643u) >> (4 * j)) & 0xFu);
             first0 = ((0xCFu >> j) & 1u) & (hf == 0 ? 1u : 0u);  // W_ir, W_iz accumulate onto the recurrent product
             first1 = 0;
-            pre = (hf == 0 && ((0x98u >> j) & 1u)) ? 2u : 0u;    // actor.2 (a1), W_ir (xf), q.0 (h') wait for the epilogue's tile
-            post = (hf == 1 && ((0xC8u >> j) & 1u)) ? 2u : 0u;   // after actor.2, W_in, q.0 the epilogue may read
+            // whole step: actor.2 (a1), W_ir (xf), q.0 (h') wait for the epilogue's tile; after actor.2, W_in,
+            // q.0 the epilogue may read.  Heads only: q.0 reads the given hidden state (no wait, no hand-over
+            // of its own: actor.2's commit covers it).
+            const uint32_t pre_m = mode == 2 ? 0x08u : 0x98u, post_m = mode == 2 ? 0x08u : 0xC8u;
+            pre = (hf == 0 && ((pre_m >> j) & 1u)) ? 2u : 0u;
+            post = (hf == 1 && ((post_m >> j) & 1u)) ? 2u : 0u;
           }
           if (pre == 1) { mbar_wait_cluster(&S.x_full, x_full_par); x_full_par ^= 1u; if (lane == 0) TC_STAMP(32); }
           if (pre == 2) {
@@ -385,6 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         mbar_arrive_cluster(&S.x_full, 0);
       }
 
+      if (mode != 1) {                // (recurrence-only launches have no actor)
       // ---- E1: a1 = relu(D1 + b) -> B0
       EP_STAMP(1);
       epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
@@ -407,11 +421,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       fence_before_sync();
       mbar_arrive_cluster(&S.a_ready, 0);
       EP_STAMP(3);
+      }
 
-      // ---- E3: xf = relu(D3 + b) -> B0 (releases the input products), then E2: actor head while they run
+      // ---- E3: xf = relu(D3 + b) -> B0 (releases the input products), then E2: actor head while they run.
+      // This wait is for actor.2 (whole step, heads only) or for the observation products (recurrence only).
       epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(4);
+      if (mode != 2) {
       for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
         float v[16];
         tmem_ld16_nowait(tl + kT2ColFc1 + (uint32_t)c0, v);
@@ -428,7 +445,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       fence_async_smem();
       fence_before_sync();
       mbar_arrive_cluster(&S.a_ready, 0);
+      }
       EP_STAMP(5);
+      if (mode != 1)
       {
         float acc[8];
 #pragma unroll
@@ -464,6 +483,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       }
       EP_STAMP(6);
 
+      if (mode != 2) {
       // ---- E4: GRU gates -> h' (in place over h), global hidden outputs
       epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
@@ -504,11 +524,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       }
       fence_async_smem();
       fence_before_sync();
-      mbar_arrive_cluster(&S.a_ready, 0);
+      if (mode == 0) mbar_arrive_cluster(&S.a_ready, 0);     // (recurrence only: the next step's x_full covers h')
+      }
       EP_STAMP(8);
 
+      if (mode != 1) {
       // ---- E5: Q tail, outputs, selection
-      epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
+      if (mode == 0) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }   // heads only: q.0 finished with actor.2
+      else epi_bar_sync();                                                  // ... but P (written by E2's last stage) must be visible
       fence_after_sync();
       EP_STAMP(9);
       const float bq2 = __ldg(W.bq2);
@@ -518,7 +541,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         for (int j = 0; j < 8; ++j) { acc[j] = 0.f; pa[j] = (j < A) ? Ps[j * kTcRows + r] : 0.f; }
         for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
           float v[16];
-          tmem_ld16_nowait(tl + kT2ColQ + (uint32_t)c0, v);
+          tmem_ld16_nowait(tl + (mode == 2 ? kT2ColHn : kT2ColQ) + (uint32_t)c0, v);
           tmem_ld_wait();
           reg_fence(v);
 #pragma unroll
@@ -597,6 +620,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           if (io.power) io.power[m] = Ps[chosen * kTcRows + r];
           if (io.q_chosen) io.q_chosen[m] = Qs[chosen * kTcRows + r];
         }
+      }
       }
       epi_bar_sync();                   // Ps / Qs / red are free for the next step
       EP_STAMP(10);

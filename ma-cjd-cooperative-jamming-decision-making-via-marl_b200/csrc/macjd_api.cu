@@ -92,7 +92,8 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   int st = enter(ctx);
   if (st != MACJD_OK) return st;
   if (!w || !io) return MACJD_ERR_INVALID_ARG;
-  if (io->path < 0 || io->path > 3) return MACJD_ERR_INVALID_ARG;
+  if (io->path < 0 || io->path > 3 || io->part < 0 || io->part > 2) return MACJD_ERR_INVALID_ARG;
+  if (io->part == 2 && (io->n_steps != 1 || !io->hidden)) return MACJD_ERR_INVALID_ARG;
 #ifndef MACJD_TEST_HOST_EMULATION
   if (io->path != 1 && macjd::tc::agent_tc_supported(*w)) {
     if (io->n_rows < 0 || io->n_steps < 1 || !io->obs) return MACJD_ERR_INVALID_ARG;
@@ -105,14 +106,24 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
     // N = 128 takes 37 cycles against 68 for the single-CTA M = 64 one, and each CTA streams half
     // the weights: 22 vs 33 us per step on the learner's 64-row unroll, tools/tc_small_m.py)
     const bool pair_ok = macjd::tc::agent_tc2_supported(*w);
-    if (io->path == 3 && !pair_ok) return MACJD_ERR_UNSUPPORTED;
+    if ((io->path == 3 || io->part != 0) && !pair_ok) return MACJD_ERR_UNSUPPORTED;
+    if (io->part != 0 && io->path == 2) return MACJD_ERR_UNSUPPORTED;
     if (io->path == 3 || (io->path == 0 && pair_ok))
       return finish(ctx, macjd::tc::agent_tc2_launch(ctx, a));
     return finish(ctx, macjd::tc::agent_tc_launch(ctx, a));
   }
 #endif
-  if (io->path >= 2) return MACJD_ERR_UNSUPPORTED;
+  if (io->path >= 2 || io->part != 0) return MACJD_ERR_UNSUPPORTED;
   return finish(ctx, macjd::agent_launch(ctx, w, io));
+}
+
+int macjd_agent_pair_supported(const macjd_agent_weights* w) {
+#ifndef MACJD_TEST_HOST_EMULATION
+  return (w && macjd::tc::agent_tc2_supported(*w)) ? 1 : 0;
+#else
+  (void)w;
+  return 0;
+#endif
 }
 
 namespace {

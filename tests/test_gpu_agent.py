@@ -109,3 +109,29 @@ def test_tensor_core_path_vs_reference_golden(name, tc_path):
         same = a_test.cpu().numpy() == g["actions_test"][t]
         np.testing.assert_allclose(p_test.cpu().numpy()[same], g["power_test"][t][same], rtol=2e-4, atol=2e-5)
         mac.hidden_states.copy_(torch.from_numpy(g["hidden"][t]))
+
+
+@pytest.mark.parametrize("M,T", [(64, 7), (200, 4)])
+def test_split_unroll_is_bit_identical_to_fused_unroll(M, T):
+    """Time-unrolled calls on the CTA-pair kernel run the recurrence alone (io.part = 1) and then actor +
+    Q-head for all T x M rows in one launch (io.part = 2): every output must equal the fused per-step
+    kernel's bit for bit (same operands, same accumulation order)."""
+    mac, args = AC.random_agent(11, 24, 5, 128, 128, 2, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    obs = torch.randn(T, M, 24, device="cuda", generator=g) * 3
+    h0 = torch.randn(M, 128, device="cuda", generator=g) * 0.5
+    avail = torch.rand(T, M, 5, device="cuda", generator=g) < 0.7
+    avail[..., 0] = True
+    sel = torch.randint(0, 5, (T, M), device="cuda", generator=g, dtype=torch.int32)
+    res = []
+    for split in (False, True):
+        h = h0.clone()
+        res.append(mac.agent.run(obs, h, n_steps=T, avail=avail, select=True, test_mode=True, want_q=True, want_params=True,
+                                 want_greedy=True, want_hidden_seq=True, sel_actions=sel, path=3, split_unroll=split))
+    a, b = res
+    for k in ("hidden", "hidden_seq", "q_all", "params_all", "greedy", "q_sel", "actions", "power", "q_chosen"):
+        assert torch.equal(a[k], b[k]), k
+    # recurrence only (no head outputs requested): hidden states alone
+    h = h0.clone()
+    c = mac.agent.run(obs, h, n_steps=T, want_hidden_seq=True, path=3)
+    assert torch.equal(c["hidden_seq"], a["hidden_seq"]) and torch.equal(c["hidden"], a["hidden"])
