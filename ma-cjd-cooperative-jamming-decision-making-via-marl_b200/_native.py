@@ -229,6 +229,9 @@ def get_lib() -> NativeLib:
 def torch_ctx(device=None):
     """macjd_ctx for torch's current stream on ``device``."""
     import torch
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    return Ctx(device=idx, reserved=0, stream=torch.cuda.current_stream(idx).cuda_stream)
+    idx = getattr(device, "index", None) if device is not None and not isinstance(device, (str, int)) else None
+    if idx is None:
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)      # same handle, without building a Stream object
+    return Ctx(device=idx, reserved=0, stream=raw(idx) if raw is not None else torch.cuda.current_stream(idx).cuda_stream)

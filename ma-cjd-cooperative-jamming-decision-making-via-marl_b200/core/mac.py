@@ -151,7 +151,7 @@ class BasicMAC:
     # ------------------------------------------------------------------ utilities
     @property
     def device(self):
-        return next(self.agent.parameters()).device
+        return self.agent.fc1.weight.device
 
     def parameters(self):
         return self.agent.parameters()

@@ -58,7 +58,7 @@ class PackedAgentWeights:
         # target networks deep-copy the agent: the copy re-packs from its own parameters
         new = PackedAgentWeights.__new__(PackedAgentWeights)
         new.__dict__.update({k: v for k, v in self.__dict__.items()
-                             if k not in ("buffer", "tc_buffer", "versions", "_cstruct", "_cstruct_for")})
+                             if k not in ("buffer", "tc_buffer", "versions", "_cstruct", "_cstruct_for", "_slots")})
         new.buffer = new.tc_buffer = new.versions = new._cstruct = new._cstruct_for = None
         return new
 
@@ -69,9 +69,14 @@ class PackedAgentWeights:
     @torch.no_grad()
     def refresh(self, agent, force=False):
         """Re-pack if any parameter changed since the last pack (or moved device)."""
-        params = list(agent.parameters())
+        # (module, name) slots are collected once: walking agent.parameters() costs ~25 us per call, and this
+        # check runs on every act; looking the Parameters up through their modules still sees replaced ones
+        slots = self.__dict__.get("_slots")
+        if slots is None or force:
+            slots = self._slots = [(m, k) for m in agent.modules() for k in m._parameters if m._parameters[k] is not None]
+        params = [m._parameters[k] for m, k in slots]
         dev = params[0].device
-        versions = tuple((p._version, p.data_ptr()) for p in params)
+        versions = tuple([(p._version, p.data_ptr()) for p in params])
         if not force and self.buffer is not None and self.buffer.device == dev and versions == self.versions:
             return self
         if self.buffer is None or self.buffer.device != dev:

@@ -645,8 +645,14 @@ inline bool agent_tc2_supported(const macjd_agent_weights& w) {
 
 inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
   const size_t smem = agent_tc2_smem_bytes(a.w);
-  if (cudaFuncSetAttribute(agent_forward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-    return MACJD_ERR_CUDA;
+  // the opt-in is per device and sticky: ask once per device and size (an act call is latency-critical)
+  static size_t opted[64] = {};
+  const int dev = ctx->device & 63;
+  if (smem > opted[dev]) {
+    if (cudaFuncSetAttribute(agent_forward_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return MACJD_ERR_CUDA;
+    opted[dev] = smem;
+  }
   const int pairs = (a.io.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
   agent_forward_tc2_kernel<<<2 * pairs, kT2Threads, smem, (cudaStream_t)ctx->stream>>>(a);
   return MACJD_OK;

@@ -161,7 +161,7 @@ class ElectromagneticEnvironment:
         ``host`` maps act_d / act_p (in) and any of reward / terminated / obs / state (out) to contiguous
         CPU tensors or numpy arrays (see ``host_buffers``).  One C call: copies in, fused step, copies
         out, stream drained on return (include/macjd.h: macjd_env_step_host)."""
-        key = tuple((k, N.ptr(v)) for k, v in sorted(host.items()))
+        key = (tuple(host), tuple([v.data_ptr() if hasattr(v, "data_ptr") else N.ptr(v) for v in host.values()]))
         c = getattr(self, "_host_cache", None)
         if c is None or c["key"] != key:
             n, J = self.n_envs, self.num_jammers
