@@ -30,6 +30,9 @@ struct EnvKernelArgs {
   int stage_ld;       // padded row length of the smem state stage (odd -> no bank conflicts)
   int physics;        // 0: reset (views only, step_count <- 0), 1: full step
   int prefetch;       // issue L2 prefetches for the env's table column first (small batches)
+  int split_views;    // small batches: a second set of warps writes the static views while the first runs
+                      // the physics (the block is launched with 2 x the env count; one dependent chain
+                      // instead of two in sequence)
   uint32_t magic_s4;  // ceil(2^32 / (S/4)), ceil(2^32 / (J*S/4)): exact v / d for the view write-back loops
   uint32_t magic_js4;
 };
@@ -49,12 +52,20 @@ __device__ __forceinline__ double albersheim(const macjd_env_tables& t, double s
   return 1.0 / (1.0 + exp(-b));
 }
 
-__global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
+// kSplit: the block has 2 BS threads, the first BS run the physics and the second BS write the static
+// views of the same envs (two concurrent dependent chains; small batches only, see env_launch).
+template <bool kSplit>
+__global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvKernelArgs a) {
   const macjd_env_tables& T = a.tab;
   const macjd_env_io& io = a.io;
   const int n = T.n_envs, J = T.n_jammers, R = T.n_radars, K = T.n_targets;
   const int RK = R * K, S = a.state_dim, A = a.n_actions;
-  const int BS = blockDim.x, tid = threadIdx.x;
+  // BS envs per block; with split_views the block has 2 BS threads: the first BS run the physics,
+  // the second BS write the views of the same envs
+  const int BS = kSplit ? (int)blockDim.x / 2 : (int)blockDim.x;
+  const bool do_phys = !kSplit || (int)threadIdx.x < BS;
+  const bool do_views = !kSplit || (int)threadIdx.x >= BS;
+  const int tid = (int)threadIdx.x - ((kSplit && (int)threadIdx.x >= BS) ? BS : 0);
   const int e0 = blockIdx.x * BS;
   const int e = e0 + tid;
   const bool live = e < n;
@@ -72,7 +83,7 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
   // against L2 instead of DRAM; a warp's requests cover contiguous 256-byte row segments.
   const double* col = T.data + (int64_t)(live ? e : 0) * T.env_stride;   // this env's table column
   const int rs = (int)T.row_stride;
-  if (live && a.prefetch) {
+  if (live && a.prefetch && do_phys) {
     const int n_rows = 16 * R + 8 * J + 3 * K;
     for (int row = 0; row < n_rows; ++row) prefetch_l2(col + (int64_t)row * rs);
     if (a.physics) {
@@ -82,7 +93,7 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
     }
   }
 
-  if (live && a.physics) {
+  if (live && a.physics && do_phys) {
     for (int r = 0; r < R; ++r) { prjs[r * BS + tid] = 0.0; prod[r * BS + tid] = 1.0; }
     for (int k = 0; k < K; ++k) pnet[k * BS + tid] = 1.0;
     const int step = io.step_count[e] + 1;  // environment.py:235
@@ -194,13 +205,13 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
     if (io.r_j) io.r_j[e] = (float)r_j;
     if (io.terminated) io.terminated[e] = term ? 1 : 0;
     io.step_count[e] = (term && io.auto_reset) ? 0 : step;
-  } else if (live && !a.physics) {
+  } else if (live && !a.physics && do_phys) {
     io.step_count[e] = 0;                                  // environment.py:203
   }
 
   // ---- static views (environment.py:479-551): stage one state row per thread
   const bool want_views = (io.state != nullptr) || (io.obs != nullptr);
-  if (want_views) {
+  if (want_views && do_views) {
     if (live) {
       float* row = stage + (size_t)tid * a.stage_ld;
       const int per = 6 + T.n_types;
@@ -220,7 +231,12 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
         row[R * per + 2 * j + 1] = (float)env_tab(col, rs, jbase + 8 * j + 5);
       }
     }
+#ifndef MACJD_TEST_HOST_EMULATION
+    if (kSplit) asm volatile("bar.sync 1, %0;\n" ::"r"(BS) : "memory");   // the view warps only
+    else __syncthreads();
+#else
     __syncthreads();
+#endif
     const int valid = min(BS, n - e0);
     if ((S & 3) == 0 && (a.stage_ld & 3) == 0) {
       // rows are 16-byte multiples: coalesced float4 stores
@@ -251,7 +267,7 @@ __global__ void __launch_bounds__(128) env_step_kernel(const EnvKernelArgs a) {
       }
     }
   }
-  if (io.avail) {  // all actions always available (environment.py:539-551)
+  if (io.avail && do_views) {  // all actions always available (environment.py:539-551)
     const int valid = min(BS, n - e0);
     const int64_t base = (int64_t)e0 * J * A;
     const int total = valid * J * A;
@@ -294,11 +310,21 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   const size_t smem = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs);
   if (smem > 200 * 1024) return MACJD_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return MACJD_ERR_CUDA;
   }
   const int grid = (tab->n_envs + bs - 1) / bs;
-  MACJD_LAUNCH(env_step_kernel, grid, bs, smem, (cudaStream_t)ctx->stream, a);
+#ifndef MACJD_TEST_HOST_EMULATION
+  // latency-bound regime: physics and views as two concurrent chains (measured at 4 096 envs: 22.5 -> 18.4 us)
+  a.split_views = physics && tab->n_envs <= 16384 && bs <= 128 && smem <= 48 * 1024 && (io->state || io->obs || io->avail);
+  if (a.split_views) {
+    env_step_kernel<true><<<grid, 2 * bs, smem, (cudaStream_t)ctx->stream>>>(a);
+    return MACJD_OK;
+  }
+#else
+  a.split_views = 0;
+#endif
+  MACJD_LAUNCH(env_step_kernel<false>, grid, bs, smem, (cudaStream_t)ctx->stream, a);
   return MACJD_OK;
 }
 
