@@ -52,20 +52,27 @@ __device__ __forceinline__ double albersheim(const macjd_env_tables& t, double s
   return 1.0 / (1.0 + exp(-b));
 }
 
-// kSplit: the block has 2 BS threads, the first BS run the physics and the second BS write the static
-// views of the same envs (two concurrent dependent chains; small batches only, see env_launch).
-template <bool kSplit>
-__global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvKernelArgs a) {
+// kMode 0: one thread per env does everything.  Small batches are one long dependent FP64 chain per
+// thread (the time for 32 envs equals the time for 4 096), so they split it over concurrent warp sets:
+// kMode 1: the block has 2 BS threads -- set 0 runs the physics, set 1 writes the static views of the
+//          same envs;
+// kMode 2: 3 BS threads -- sets 0 and 1 both run the (short) jammer loop, then take the even / odd
+//          radars; set 0 adds the per-radar terms up in radar order (so every sum has the sequential
+//          kernel's order and value); set 2 writes the views.
+template <int kMode>
+__global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env_step_kernel(const EnvKernelArgs a) {
   const macjd_env_tables& T = a.tab;
   const macjd_env_io& io = a.io;
   const int n = T.n_envs, J = T.n_jammers, R = T.n_radars, K = T.n_targets;
   const int RK = R * K, S = a.state_dim, A = a.n_actions;
-  // BS envs per block; with split_views the block has 2 BS threads: the first BS run the physics,
-  // the second BS write the views of the same envs
-  const int BS = kSplit ? (int)blockDim.x / 2 : (int)blockDim.x;
-  const bool do_phys = !kSplit || (int)threadIdx.x < BS;
-  const bool do_views = !kSplit || (int)threadIdx.x >= BS;
-  const int tid = (int)threadIdx.x - ((kSplit && (int)threadIdx.x >= BS) ? BS : 0);
+  constexpr int NW = kMode == 2 ? 2 : 1;                     // physics workers per env
+  constexpr int kSets = kMode == 0 ? 1 : NW + 1;
+  const int BS = (int)blockDim.x / kSets;                    // envs per block
+  const int set_id = kMode == 0 ? 0 : (int)threadIdx.x / BS;
+  const bool do_phys = kMode == 0 || set_id < NW;
+  const bool do_views = kMode == 0 || set_id == NW;
+  const int wk = (kMode == 2 && do_phys) ? set_id : 0;       // which physics worker
+  const int tid = (int)threadIdx.x - set_id * BS;
   const int e0 = blockIdx.x * BS;
   const int e = e0 + tid;
   const bool live = e < n;
@@ -73,10 +80,13 @@ __global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvK
 
   MACJD_DYNAMIC_SMEM(double, smem);
   // per-thread scratch, [slot][thread] so that a warp touches consecutive banks
-  double* prjs = smem;                 // [R][BS] accumulated suppression power per radar
-  double* prod = smem + (size_t)R * BS;  // [R][BS] prod(1 - pd_f) over detected false targets
-  double* pnet = smem + (size_t)2 * R * BS;  // [K][BS] prod_r (1 - pd[r][k])
-  float* stage = reinterpret_cast<float*>(smem + (size_t)(2 * R + K) * BS);  // [BS][stage_ld]
+  double* prjs = smem + (size_t)wk * 2 * R * BS;     // [R][BS] accumulated suppression power per radar (per worker)
+  double* prod = prjs + (size_t)R * BS;              // [R][BS] prod(1 - pd_f) over detected false targets
+  double* pnet = smem + (size_t)NW * 2 * R * BS;     // [K][BS] prod_r (1 - pd[r][k])
+  float* stage = reinterpret_cast<float*>(smem + (size_t)(NW * 2 * R + K) * BS);  // [BS][stage_ld]
+  // kMode 2: per-radar terms handed to worker 0: [3][R][BS] (r_d, r_j suppression, r_j deception), [RK][BS] pd
+  double* rad = smem + (size_t)(NW * 2 * R + K) * BS + ((size_t)BS * a.stage_ld + 1) / 2;
+  double* pdv = rad + (size_t)3 * R * BS;
 
   // The physics below walks the scenario tables with data-dependent, serial lookups.  Request
   // this env's whole table column (and its action / noise rows) up front so that the chain runs
@@ -93,12 +103,15 @@ __global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvK
     }
   }
 
-  if (live && a.physics && do_phys) {
+  const bool phys = live && a.physics && do_phys;
+  int step = 0;
+  double r_p = 0.0, r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
+  if (phys) {
     for (int r = 0; r < R; ++r) { prjs[r * BS + tid] = 0.0; prod[r * BS + tid] = 1.0; }
-    for (int k = 0; k < K; ++k) pnet[k * BS + tid] = 1.0;
-    const int step = io.step_count[e] + 1;  // environment.py:235
+    if (wk == 0)
+      for (int k = 0; k < K; ++k) pnet[k * BS + tid] = 1.0;
+    step = io.step_count[e] + 1;  // environment.py:235
     uint64_t supp_mask = 0, hit_mask = 0;
-    double r_p = 0.0;
 
     // ---- jammer loop (environment.py:248-302)
     for (int j = 0; j < J; ++j) {
@@ -111,7 +124,7 @@ __global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvK
       const double power = pmin + P * range;
       const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
       r_p += T.rp_max + (T.rp_min - T.rp_max) * norm;   // charged even when idle
-      if (io.jam_power) io.jam_power[(int64_t)j * n + e] = (float)power;
+      if (io.jam_power && wk == 0) io.jam_power[(int64_t)j * n + e] = (float)power;
       if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
         const int tgt = (Ti + 1) / 2 - 1;
         const int rr = rbase + 16 * tgt;
@@ -145,8 +158,7 @@ __global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvK
 
     // ---- radar x target loop (environment.py:316-349, 359-366, 385-398)
     const double four_pi3 = (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793);
-    double r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
-    for (int r = 0; r < R; ++r) {
+    for (int r = wk; r < R; r += NW) {
       const int rr = rbase + 16 * r;
       const double pt = env_tab(col, rs, rr + 0), gt = env_tab(col, rs, rr + 1), gr = env_tab(col, rs, rr + 2);
       const double lam = env_tab(col, rs, rr + 3), loss = env_tab(col, rs, rr + 4), latm = env_tab(col, rs, rr + 5);
@@ -176,7 +188,8 @@ __global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvK
         tracked |= det;
         // P_d without jamming only matters for radars hit by suppression this step (r_j)
         if ((supp_mask >> r) & 1ull) red += fmax(0.0, albersheim(T, snr0) - pd);
-        pnet[k * BS + tid] *= (1.0 - pd);
+        if (kMode == 2) pdv[slot * BS + tid] = pd;
+        else pnet[k * BS + tid] *= (1.0 - pd);
         const int64_t o = (int64_t)slot * n + e;
         if (io.pd) io.pd[o] = (float)pd;
         if (io.detected) io.detected[o] = det ? 1 : 0;
@@ -185,12 +198,32 @@ __global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvK
         if (io.jsr_db) io.jsr_db[o] = 10.0f * log10f((float)(jam / sig));   // float32 output of an extension: float log
       }
       if (io.tracking) io.tracking[(int64_t)r * n + e] = tracked ? 1 : 0;
-      if (tracked) {  // memoryless TRACK state (core/radar.py:90-117) -> r_d
-        const double pen = -env_tab(col, rs, rr + 9);
-        r_d += fmin(fmax(pen, T.rd_min), T.rd_max);
+      // memoryless TRACK state (core/radar.py:90-117) -> r_d; suppression / deception terms of r_j
+      const double rd_term = tracked ? fmin(fmax(-env_tab(col, rs, rr + 9), T.rd_min), T.rd_max) : 0.0;
+      const bool supp = (supp_mask >> r) & 1ull, hit = (hit_mask >> r) & 1ull;
+      if (kMode == 2) {
+        rad[(0 * R + r) * BS + tid] = rd_term;
+        rad[(1 * R + r) * BS + tid] = supp ? red : 0.0;
+        rad[(2 * R + r) * BS + tid] = hit ? 1.0 - prod[r * BS + tid] : 0.0;
+      } else {
+        if (tracked) r_d += rd_term;
+        if (supp) r_j_supp += red;
+        if (hit) r_j_dec += 1.0 - prod[r * BS + tid];
       }
-      if ((supp_mask >> r) & 1ull) r_j_supp += red;
-      if ((hit_mask >> r) & 1ull) r_j_dec += 1.0 - prod[r * BS + tid];
+    }
+  }
+#ifndef MACJD_TEST_HOST_EMULATION
+  if (kMode == 2 && a.physics && do_phys) asm volatile("bar.sync 2, %0;\n" ::"r"(2 * BS) : "memory");   // both physics sets
+#endif
+  if (phys && wk == 0) {
+    if (kMode == 2) {
+      // the sequential kernel's sums, in its order (a term that kernel skips is an exact + 0.0 here)
+      for (int r = 0; r < R; ++r) {
+        r_d += rad[(0 * R + r) * BS + tid];
+        r_j_supp += rad[(1 * R + r) * BS + tid];
+        r_j_dec += rad[(2 * R + r) * BS + tid];
+        for (int k = 0; k < K; ++k) pnet[k * BS + tid] *= (1.0 - pdv[(r * K + k) * BS + tid]);
+      }
     }
     if (io.pd_net)
       for (int k = 0; k < K; ++k) io.pd_net[(int64_t)k * n + e] = (float)(1.0 - pnet[k * BS + tid]);
@@ -232,7 +265,7 @@ __global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvK
       }
     }
 #ifndef MACJD_TEST_HOST_EMULATION
-    if (kSplit) asm volatile("bar.sync 1, %0;\n" ::"r"(BS) : "memory");   // the view warps only
+    if (kMode != 0) asm volatile("bar.sync 1, %0;\n" ::"r"(BS) : "memory");   // the view warps only
     else __syncthreads();
 #else
     __syncthreads();
@@ -275,8 +308,9 @@ __global__ void __launch_bounds__(kSplit ? 256 : 128) env_step_kernel(const EnvK
   }
 }
 
-inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs) {
-  return (size_t)(2 * R + K) * bs * sizeof(double) + (size_t)bs * stage_ld * sizeof(float);
+inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1) {
+  return (size_t)(workers * 2 * R + K) * bs * sizeof(double) + (((size_t)bs * stage_ld + 1) / 2) * sizeof(double) +
+         (workers > 1 ? (size_t)(3 * R + R * K) * bs * sizeof(double) : 0);
 }
 
 inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
@@ -310,21 +344,24 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   const size_t smem = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs);
   if (smem > 200 * 1024) return MACJD_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(env_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return MACJD_ERR_CUDA;
   }
   const int grid = (tab->n_envs + bs - 1) / bs;
 #ifndef MACJD_TEST_HOST_EMULATION
-  // latency-bound regime: physics and views as two concurrent chains (measured at 4 096 envs: 22.5 -> 18.4 us)
-  a.split_views = physics && tab->n_envs <= 16384 && bs <= 128 && smem <= 48 * 1024 && (io->state || io->obs || io->avail);
+  // latency-bound regime: physics and views as concurrent chains (measured at 4 096 envs: 22.5 -> 18.4 us),
+  // and the radar loop over two workers
+  a.split_views = physics && tab->n_envs <= 16384 && bs == 128 && smem <= 48 * 1024 && (io->state || io->obs || io->avail);
   if (a.split_views) {
-    env_step_kernel<true><<<grid, 2 * bs, smem, (cudaStream_t)ctx->stream>>>(a);
+    const size_t smem2 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 2);
+    if (tab->n_radars >= 2 && smem2 <= 48 * 1024) env_step_kernel<2><<<grid, 3 * bs, smem2, (cudaStream_t)ctx->stream>>>(a);
+    else env_step_kernel<1><<<grid, 2 * bs, smem, (cudaStream_t)ctx->stream>>>(a);
     return MACJD_OK;
   }
 #else
   a.split_views = 0;
 #endif
-  MACJD_LAUNCH(env_step_kernel<false>, grid, bs, smem, (cudaStream_t)ctx->stream, a);
+  MACJD_LAUNCH(env_step_kernel<0>, grid, bs, smem, (cudaStream_t)ctx->stream, a);
   return MACJD_OK;
 }
 
