@@ -197,6 +197,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
     mbar_init(&S.x_full, 2 * kT2EpiThreads); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 2 * kT2EpiThreads);
     fence_mbar_init();
   }
+  // tensor memory for the pair (needs nothing from the rest of the prologue: runs under the constant staging)
+  if (warp == kT2EpiWarps + 1) tmem_alloc_2sm(&S.tmem_base, kT2TmemCols);
   for (int i = tid; i < H; i += kT2Threads) {
     // all loads first (read-only path), then the stores: interleaved, every load waited for the
     // previous shared-memory store (possible aliasing) -- ten serial DRAM round trips after an L2 flush
@@ -218,14 +220,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
     S.c.w1a[2 * i + 1] = make_float4(wq[4], wq[5], wq[6], wq[7]);
   }
   if (tid < 8) S.c.ba3[tid] = tid < A ? W.ba3[tid] : 0.f;
-  __syncthreads();
   TC_STAMP_ONCE(21);
-  cluster_sync_all();                         // both CTAs' barriers exist before any remote arrive
-  TC_STAMP_ONCE(22);
-  if (warp == kT2EpiWarps + 1) tmem_alloc_2sm(&S.tmem_base, kT2TmemCols);
+  // one cluster-wide barrier ends the prologue: both CTAs' mbarriers exist before any remote arrive, the
+  // staged constants and the TMEM base address are visible to every warp
   fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();
   fence_after_sync();
+  TC_STAMP_ONCE(22);
   const uint32_t tmem = S.tmem_base;
   TC_STAMP_ONCE(23);
 
