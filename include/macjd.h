@@ -221,8 +221,16 @@ typedef struct macjd_agent_io {
                                      writes hidden / hidden_seq, nothing else;
                                  2 = heads only (n_steps = 1): `hidden` is the post-GRU state of
                                      every row (read, not updated); actor, Q-head, selection.
+                                 3 = input pre-pass (n_steps = 1, rows = all T x M): the three GRU
+                                     input products W_ir xf, W_iz xf, W_in xf (xf = relu(fc1 obs),
+                                     no biases) -> gate_x;
+                                 4 = recurrence on gate_x: per step only W_h* h and the gates
+                                     (obs is not read); writes hidden / hidden_seq.  1 and 3+4
+                                     differ by FP32 rounding (x and h products are summed in the
+                                     epilogue instead of in the accumulator).
                                  Other kernels return MACJD_ERR_UNSUPPORTED for part != 0.   */
   int32_t reserved2;
+  float* gate_x;              /* [T][M][3][H] part 3 output / part 4 input, else unused  */
 } macjd_agent_io;
 
 /* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);

@@ -53,7 +53,8 @@ class AgentIO(C.Structure):
                 ("hidden_seq", c_void_p), ("q_all", c_void_p), ("params_all", c_void_p), ("greedy", c_void_p),
                 ("sel_actions", c_void_p), ("q_sel", c_void_p), ("avail", c_void_p), ("u_eps", c_void_p),
                 ("rand_actions", c_void_p), ("epsilon", c_float), ("rng_step", C.c_uint32), ("seed", c_uint64),
-                ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p), ("part", c_int32), ("reserved2", c_int32)]
+                ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p), ("part", c_int32), ("reserved2", c_int32),
+                ("gate_x", c_void_p)]
 
 
 class ActHost(C.Structure):

@@ -270,20 +270,27 @@ class RNNAgent(nn.Module):
                      q_chosen=p(out.get("q_chosen")))
         wants_heads = want_q or want_params or want_greedy or sel_actions is not None or select
         if split_unroll and T > 1 and path in (0, 3) and (not select or test_mode) and self._pair_kernel_ok(pk):
-            # Time-unrolled use (core/qmix.py:217-280): only h_t -> h_t+1 is sequential.  The CTA-pair
-            # kernel runs the recurrence alone for the T steps (6 of the 8 layer products, 2 of the 5
-            # epilogues per step), then actor + Q-head + arg-max for all T x M rows in one parallel
-            # launch on the stored hidden states -- bit-identical to the fused per-step order.
+            # Time-unrolled use (core/qmix.py:217-280): only h_t -> h_t+1 is sequential.  On the CTA-pair
+            # kernel the call becomes three launches: (3) the GRU input products W_i* relu(fc1 obs) for all
+            # T x M rows at once, (4) the recurrence proper -- per step only W_h* h and the gates --, (2) actor +
+            # Q-head + arg-max for all T x M rows on the stored hidden states.  split_unroll="exact" keeps the
+            # input products inside the per-step launch (part 1) and is bit-identical to the fused step; the
+            # default differs from it by FP32 rounding (x and h products summed in the epilogue).
             hs = out.get("hidden_seq")
             if hs is None:
                 hs = torch.empty(T, M, H, dtype=torch.float32, device=dev)
-            io = N.AgentIO(n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden), hidden_zero_init=int(zero_init),
-                           hidden_seq=p(hs), part=1, **common)
-            self.lib().call("macjd_agent_forward", self._ctx(), pk.cstruct(), io)
+            call = lambda io: self.lib().call("macjd_agent_forward", self._ctx(), pk.cstruct(), io)
+            if split_unroll == "exact":
+                call(N.AgentIO(n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden), hidden_zero_init=int(zero_init),
+                               hidden_seq=p(hs), part=1, **common))
+            else:
+                gx = torch.empty(T * M, 3 * H, dtype=torch.float32, device=dev)
+                call(N.AgentIO(n_rows=T * M, n_steps=1, obs=p(obs), hidden_zero_init=1, gate_x=p(gx), part=3, **common))
+                call(N.AgentIO(n_rows=M, n_steps=T, hidden=p(hidden), hidden_zero_init=int(zero_init), hidden_seq=p(hs),
+                               gate_x=p(gx), part=4, **common))
             if wants_heads:
-                io = N.AgentIO(n_rows=T * M, n_steps=1, obs=p(obs), hidden=p(hs), hidden_zero_init=0, part=2,
-                               **common, **heads)
-                self.lib().call("macjd_agent_forward", self._ctx(), pk.cstruct(), io)
+                call(N.AgentIO(n_rows=T * M, n_steps=1, obs=p(obs), hidden=p(hs), hidden_zero_init=0, part=2,
+                               **common, **heads))
             return out
         io = N.AgentIO(n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden), hidden_zero_init=int(zero_init),
                        hidden_seq=p(out.get("hidden_seq")), part=0, **common, **heads)

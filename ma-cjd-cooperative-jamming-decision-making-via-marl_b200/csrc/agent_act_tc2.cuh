@@ -55,8 +55,12 @@ constexpr uint32_t kT2LayerSrc = 0x75310642u;    // nibble s = packed index of s
 // io.part selects which slots a launch runs, in this order (nibble i = i-th slot):
 //   0 whole step: 0..7;  1 recurrence only: the six GRU products;  2 heads only: q.0 (on the given
 //   hidden state), then actor.2 -- one accumulator hand-over fewer, each gated by the epilogue.
-__device__ __forceinline__ uint32_t t2_slot_seq(int part) { return part == 1 ? 0x00654210u : part == 2 ? 0x00000037u : 0x76543210u; }
-__device__ __forceinline__ int t2_slot_count(int part) { return part == 1 ? 6 : part == 2 ? 2 : 8; }
+//   3 input pre-pass: the three input products (each overwrites its accumulator);  4 recurrence on the
+//   pre-computed input products: the three recurrent products, no observation stage.
+__device__ __forceinline__ uint32_t t2_slot_seq(int part) {
+  return part == 1 ? 0x00654210u : part == 2 ? 0x00000037u : part == 3 ? 0x00000654u : part == 4 ? 0x00000210u : 0x76543210u;
+}
+__device__ __forceinline__ int t2_slot_count(int part) { return part == 1 ? 6 : part == 2 ? 2 : (part == 3 || part == 4) ? 3 : 8; }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -163,9 +167,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   float* Qs = Ps + (size_t)A * kTcRows;
   const int nxc = Op / 32;
   const int chunks_per_step = 2 * kTcChunksPerX * nxc + 8 * kTcChunksPerH;
-  const int mode = io.part;            // 0 whole step, 1 recurrence only, 2 heads only
+  const int mode = io.part;            // 0 whole step, 1 recurrence only, 2 heads only, 3 input pre-pass, 4 recurrence on gate_x
   const uint32_t slot_seq = t2_slot_seq(mode);
-  const int supers_per_step = nxc + 2 * t2_slot_count(mode);     // ring stages this launch runs per step
+  const int nx = mode == 4 ? 0 : nxc;                            // observation stages per step
+  const int supers_per_step = nx + 2 * t2_slot_count(mode);      // ring stages this launch runs per step
   float* const xhi = S.b0hi;   // the observation block lives in b0 until E1 overwrites it with a1
   float* const xlo = S.b0lo;
 
@@ -185,7 +190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #pragma unroll
     for (int j = 0; j < 32 / kT2Parts; ++j) {
       const int kk = part * (32 / kT2Parts) + j;
-      x_in[j] = (live && kk < O) ? __ldg(io.obs + (size_t)(row0 + r) * O + kk) : 0.f;
+      x_in[j] = (live && kk < O && mode != 4) ? __ldg(io.obs + (size_t)(row0 + r) * O + kk) : 0.f;
     }
   }
 
@@ -240,8 +245,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         for (int L = 0; L < supers_per_step; ++L) {
           if (t > 0 || L >= kT2Stages) { mbar_wait_cluster(&S.w_empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
           // stages follow the issue order; the packed buffer keeps the single-CTA kernel's layer order
-          const int slot = L < nxc ? 0 : (int)((slot_seq >> (4 * ((L - nxc) >> 1))) & 0xFu);
-          const int Lsrc = L < nxc ? L : nxc + 2 * (int)((kT2LayerSrc >> (4 * slot)) & 0xFu) + ((L - nxc) & 1);
+          const int slot = L < nx ? 0 : (int)((slot_seq >> (4 * ((L - nx) >> 1))) & 0xFu);
+          const int Lsrc = L < nx ? L : nxc + 2 * (int)((kT2LayerSrc >> (4 * slot)) & 0xFu) + ((L - nx) & 1);
           const char* src = wsrc + (size_t)Lsrc * 2 * kTcChunkBytes + (size_t)rank * kT2HalfBytes;
           mbar_expect_tx(&S.w_full[s], kT2StageBytes);
 #pragma unroll
@@ -287,25 +292,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #endif
         for (int L = 0; L < supers_per_step; ++L) {
           uint32_t ahi, alo, sbo, koff0, koff1, d0, d1, first0, first1, pre, post;
-          if (L < nxc) {                       // [actor.0 | fc1] chunk pair of observation block L
+          if (L < nx) {                        // [actor.0 | fc1] chunk pair of observation block L
             ahi = bh; alo = bl; sbo = 32 * 32; koff0 = koff1 = 0;
             d0 = kT2ColA1; d1 = kT2ColFc1; first0 = first1 = (L == 0);
-            pre = 1; post = 1u | (L == nxc - 1 ? 2u : 0u);
+            pre = 1; post = 1u | (L == nx - 1 ? 2u : 0u);
           } else {                             // K = 128 layers: 4 chunks = 2 stages each
             //  slot j:  0 W_hr (h)  1 W_hz (h)  2 W_hn (h)  3 actor.2 (b0)  4 W_ir (b0)  5 W_iz (b0)  6 W_in (b0)  7 q.0 (h)
-            const uint32_t j = (slot_seq >> (4 * ((uint32_t)(L - nxc) >> 1))) & 0xFu, hf = (uint32_t)(L - nxc) & 1u;
+            const uint32_t j = (slot_seq >> (4 * ((uint32_t)(L - nx) >> 1))) & 0xFu, hf = (uint32_t)(L - nx) & 1u;
             const bool use_h = (0x87u >> j) & 1u;          // slots 0, 1, 2, 7 read h
             ahi = use_h ? hh : bh; alo = use_h ? hl : bl; sbo = H * 32;
             koff0 = (2 * hf) * kTcAStep; koff1 = (2 * hf + 1) * kTcAStep;
             // accumulator column / 64 per slot: R 3, Z 4, Hn 6, A2 2, R 3, Z 4, In 5, Q 0
             // (heads only: q.0 is issued before actor.0's accumulator has been read, so it takes W_hn's columns)
             d0 = d1 = 64u * (((mode == 2 ? 0x65432643u : 0x05432643u) >> (4 * j)) & 0xFu);
-            first0 = ((0xCFu >> j) & 1u) & (hf == 0 ? 1u : 0u);  // W_ir, W_iz accumulate onto the recurrent product
+            // W_ir, W_iz accumulate onto the recurrent product (pre-pass: they stand alone)
+            first0 = (((mode == 3 ? 0xFFu : 0xCFu) >> j) & 1u) & (hf == 0 ? 1u : 0u);
             first1 = 0;
             // whole step: actor.2 (a1), W_ir (xf), q.0 (h') wait for the epilogue's tile; after actor.2, W_in,
             // q.0 the epilogue may read.  Heads only: q.0 reads the given hidden state (no wait, no hand-over
             // of its own: actor.2's commit covers it).
-            const uint32_t pre_m = mode == 2 ? 0x08u : 0x98u, post_m = mode == 2 ? 0x08u : 0xC8u;
+            // Recurrence on gate_x: W_hr waits for h' of the previous step, W_hn's commit hands over.
+            const uint32_t pre_m = mode == 2 ? 0x08u : mode == 4 ? 0x01u : 0x98u;
+            const uint32_t post_m = mode == 2 ? 0x08u : mode == 4 ? 0x04u : 0xC8u;
             pre = (hf == 0 && ((pre_m >> j) & 1u)) ? 2u : 0u;
             post = (hf == 1 && ((post_m >> j) & 1u)) ? 2u : 0u;
           }
@@ -369,6 +377,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       const float v[4] = {h_in[i].x, h_in[i].y, h_in[i].z, h_in[i].w};
       store_split4(S.hhi, S.hlo, r, ub + 4 * i, H, v);
     }
+    if (mode == 4) {                    // no observation stage announces the hidden tile: say so directly
+      fence_async_smem();
+      fence_before_sync();
+      mbar_arrive_cluster(&S.a_ready, 0);
+    }
 
     for (int t = 0; t < T; ++t) {
       const size_t tM = (size_t)t * M;
@@ -379,7 +392,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #pragma unroll
       for (int act = 0; act < 8; ++act)
         av_in[act] = (part == 0 && live && io.avail && act < A) ? __ldg(io.avail + (tM + row0 + r) * A + act) : (uint8_t)1;
-      for (int xc = 0; xc < nxc; ++xc) {
+      for (int xc = 0; xc < nx; ++xc) {
         if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
         const float* obs = io.obs + (tM + row0 + r) * O;
         const bool pre = (t == 0 && xc == 0);      // already in registers (requested at kernel entry)
@@ -399,7 +412,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         mbar_arrive_cluster(&S.x_full, 0);
       }
 
-      if (mode != 1) {                // (recurrence-only launches have no actor)
+      if (mode == 0 || mode == 2) {   // (recurrence / pre-pass launches have no actor)
       // ---- E1: a1 = relu(D1 + b) -> B0
       EP_STAMP(1);
       epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
@@ -426,10 +439,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 
       // ---- E3: xf = relu(D3 + b) -> B0 (releases the input products), then E2: actor head while they run.
       // This wait is for actor.2 (whole step, heads only) or for the observation products (recurrence only).
-      epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
+      if (mode != 4) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }
       fence_after_sync();
       EP_STAMP(4);
-      if (mode != 2) {
+      if (mode != 2 && mode != 4) {
       for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
         float v[16];
         tmem_ld16_nowait(tl + kT2ColFc1 + (uint32_t)c0, v);
@@ -448,7 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       mbar_arrive_cluster(&S.a_ready, 0);
       }
       EP_STAMP(5);
-      if (mode != 1)
+      if (mode == 0 || mode == 2)
       {
         float acc[8];
 #pragma unroll
@@ -484,8 +497,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       }
       EP_STAMP(6);
 
-      if (mode != 2) {
+      if (mode == 3) {
+      // ---- pre-pass: the three input products of every row -> gate_x [row][3][H]
+      epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
+      fence_after_sync();
+      for (int c0 = 0; c0 < kT2Upt; c0 += 8) {
+        float vr[8], vz[8], vi[8];
+        tmem_ld8_nowait(tl + kT2ColR + (uint32_t)c0, vr);
+        tmem_ld8_nowait(tl + kT2ColZ + (uint32_t)c0, vz);
+        tmem_ld8_nowait(tl + kT2ColIn + (uint32_t)c0, vi);
+        tmem_ld_wait();
+        reg_fence(vr); reg_fence(vz); reg_fence(vi);
+        if (live) {
+          float4* g = reinterpret_cast<float4*>(io.gate_x + (size_t)(row0 + r) * 3 * H + ub + c0);
+          g[0] = make_float4(vr[0], vr[1], vr[2], vr[3]); g[1] = make_float4(vr[4], vr[5], vr[6], vr[7]);
+          g[H / 4] = make_float4(vz[0], vz[1], vz[2], vz[3]); g[H / 4 + 1] = make_float4(vz[4], vz[5], vz[6], vz[7]);
+          g[2 * H / 4] = make_float4(vi[0], vi[1], vi[2], vi[3]); g[2 * H / 4 + 1] = make_float4(vi[4], vi[5], vi[6], vi[7]);
+        }
+      }
+      fence_before_sync();
+      } else if (mode != 2) {
       // ---- E4: GRU gates -> h' (in place over h), global hidden outputs
+      // mode 4: the input products come from gate_x (software-pipelined: the next 8 units' values are
+      // requested while the current ones are used; the first request goes out before the wait)
+      const float4* gx = reinterpret_cast<const float4*>(io.gate_x + (tM + row0 + r) * 3 * H + ub);
+      float4 gq[6];
+      if (mode == 4) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) gq[i] = live ? __ldg(gx + (i >> 1) * (H / 4) + (i & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(7);
@@ -493,10 +533,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         float vr[8], vz[8], vi[8], vh[8];
         tmem_ld8_nowait(tl + kT2ColR + (uint32_t)c0, vr);
         tmem_ld8_nowait(tl + kT2ColZ + (uint32_t)c0, vz);
-        tmem_ld8_nowait(tl + kT2ColIn + (uint32_t)c0, vi);
+        if (mode != 4) tmem_ld8_nowait(tl + kT2ColIn + (uint32_t)c0, vi);
         tmem_ld8_nowait(tl + kT2ColHn + (uint32_t)c0, vh);
         tmem_ld_wait();
-        reg_fence(vr); reg_fence(vz); reg_fence(vi); reg_fence(vh);
+        reg_fence(vr); reg_fence(vz); reg_fence(vh);
+        if (mode != 4) {
+          reg_fence(vi);
+        } else {
+          const float gr_[8] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w};
+          const float gz_[8] = {gq[2].x, gq[2].y, gq[2].z, gq[2].w, gq[3].x, gq[3].y, gq[3].z, gq[3].w};
+          const float gn_[8] = {gq[4].x, gq[4].y, gq[4].z, gq[4].w, gq[5].x, gq[5].y, gq[5].z, gq[5].w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { vr[i] += gr_[i]; vz[i] += gz_[i]; vi[i] = gn_[i]; }
+          if (c0 + 8 < kT2Upt) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+              gq[i] = live ? __ldg(gx + (i >> 1) * (H / 4) + (c0 + 8) / 4 + (i & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int c = ub + c0 + 4 * q;
@@ -525,11 +579,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       }
       fence_async_smem();
       fence_before_sync();
-      if (mode == 0) mbar_arrive_cluster(&S.a_ready, 0);     // (recurrence only: the next step's x_full covers h')
+      if (mode == 0 || mode == 4) mbar_arrive_cluster(&S.a_ready, 0);     // (mode 1: the next step's x_full covers h')
       }
       EP_STAMP(8);
 
-      if (mode != 1) {
+      if (mode == 0 || mode == 2) {
       // ---- E5: Q tail, outputs, selection
       if (mode == 0) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }   // heads only: q.0 finished with actor.2
       else epi_bar_sync();                                                  // ... but P (written by E2's last stage) must be visible

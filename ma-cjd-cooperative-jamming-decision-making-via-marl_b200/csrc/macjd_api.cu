@@ -92,11 +92,13 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   int st = enter(ctx);
   if (st != MACJD_OK) return st;
   if (!w || !io) return MACJD_ERR_INVALID_ARG;
-  if (io->path < 0 || io->path > 3 || io->part < 0 || io->part > 2) return MACJD_ERR_INVALID_ARG;
+  if (io->path < 0 || io->path > 3 || io->part < 0 || io->part > 4) return MACJD_ERR_INVALID_ARG;
   if (io->part == 2 && (io->n_steps != 1 || !io->hidden)) return MACJD_ERR_INVALID_ARG;
+  if (io->part == 3 && (io->n_steps != 1 || !io->gate_x)) return MACJD_ERR_INVALID_ARG;
+  if (io->part == 4 && !io->gate_x) return MACJD_ERR_INVALID_ARG;
 #ifndef MACJD_TEST_HOST_EMULATION
   if (io->path != 1 && macjd::tc::agent_tc_supported(*w)) {
-    if (io->n_rows < 0 || io->n_steps < 1 || !io->obs) return MACJD_ERR_INVALID_ARG;
+    if (io->n_rows < 0 || io->n_steps < 1 || (!io->obs && io->part != 4)) return MACJD_ERR_INVALID_ARG;
     if (io->n_rows == 0) return MACJD_OK;
     macjd::AgentArgs a;
     a.w = *w;

@@ -124,7 +124,7 @@ def test_split_unroll_is_bit_identical_to_fused_unroll(M, T):
     avail[..., 0] = True
     sel = torch.randint(0, 5, (T, M), device="cuda", generator=g, dtype=torch.int32)
     res = []
-    for split in (False, True):
+    for split in (False, "exact"):
         h = h0.clone()
         res.append(mac.agent.run(obs, h, n_steps=T, avail=avail, select=True, test_mode=True, want_q=True, want_params=True,
                                  want_greedy=True, want_hidden_seq=True, sel_actions=sel, path=3, split_unroll=split))
@@ -133,5 +133,15 @@ def test_split_unroll_is_bit_identical_to_fused_unroll(M, T):
         assert torch.equal(a[k], b[k]), k
     # recurrence only (no head outputs requested): hidden states alone
     h = h0.clone()
-    c = mac.agent.run(obs, h, n_steps=T, want_hidden_seq=True, path=3)
+    c = mac.agent.run(obs, h, n_steps=T, want_hidden_seq=True, path=3, split_unroll="exact")
     assert torch.equal(c["hidden_seq"], a["hidden_seq"]) and torch.equal(c["hidden"], a["hidden"])
+    # default time-unrolled form: input products in a pre-pass (parts 3 + 4 + 2): same values up to FP32 rounding
+    h = h0.clone()
+    d = mac.agent.run(obs, h, n_steps=T, avail=avail, select=True, test_mode=True, want_q=True, want_params=True,
+                      want_greedy=True, want_hidden_seq=True, sel_actions=sel, path=3)
+    for k in ("hidden", "hidden_seq", "q_all", "params_all", "q_sel"):
+        torch.testing.assert_close(d[k], a[k], rtol=1e-5, atol=2e-6, msg=k)
+    q = a["q_all"].masked_fill(~avail, -float("inf"))
+    top2 = q.topk(2, dim=-1).values
+    decidable = (top2[..., 0] - top2[..., 1]) > 1e-5
+    assert torch.equal(d["actions"][decidable], a["actions"][decidable])
