@@ -24,6 +24,9 @@
 //   epilogue: x tile -> E1 (a1) .............. -> E3 (xf), E2 (actor head P) ....... -> E4 (gates, h') -> E5 (Q, selection)
 #pragma once
 #include "agent_act_tc.cuh"
+#ifndef MACJD_TEST_HOST_EMULATION
+#include <cuda.h>            // CUtensorMap (type and enums only; the encoder is fetched through the runtime)
+#endif
 
 #ifndef MACJD_TEST_HOST_EMULATION
 namespace macjd {
@@ -138,6 +141,28 @@ __device__ __forceinline__ void epi_wait(uint64_t* bar, uint32_t parity, int war
   epi_bar_sync();
 }
 
+// Kernel parameters: the launch arguments plus a TMA descriptor of the packed weight chunks, seen as
+// [bytes / 128][32 floats] so that one box of 64 rows is one contiguous 8 KB half-chunk.
+struct T2Args {
+  AgentArgs a;
+  alignas(64) CUtensorMap wmap;
+};
+
+// 8 KB half-chunk -> this CTA's shared memory; the bytes are counted on the LEADER's mbarrier
+// (cta_group::2 form: the mbarrier may live in the peer CTA), so the MMA issuer waits on one barrier
+// for both halves of a stage and no thread has to relay "the peer's half has landed".
+__device__ __forceinline__ void tma_half_chunk_2sm(void* smem_dst, const CUtensorMap* map, int row128, uint64_t* bar,
+                                                   uint32_t leader_rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rbar;\n\t"
+      "mapa.shared::cluster.u32 rbar, %2, %5;\n\t"
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [rbar];\n\t"
+      "}\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(0), "r"(row128), "r"(leader_rank)
+      : "memory");
+}
+
 struct T2Smem {
   float b0hi[kTcRows * kTcH], b0lo[kTcRows * kTcH];        // observation block (first 8 KB) -> a1 -> xf
   float hhi[kTcRows * kTcH], hlo[kTcRows * kTcH];            // h -> h'
@@ -149,9 +174,10 @@ struct T2Smem {
   uint32_t tmem_base;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent_forward_tc2_kernel(const AgentArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   T2Smem& S = *reinterpret_cast<T2Smem*>(tc_raw);
+  const AgentArgs& a = p.a;
   const macjd_agent_weights& W = a.w;
   const macjd_agent_io& io = a.io;
   const int O = W.obs_dim, Op = W.obs_pad, A = W.n_actions;
@@ -197,8 +223,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   warm_weights_l2(W.tc_chunks, chunks_per_step, kT2Threads);
 
   if (tid == 0) {
-    // the leader's "full" needs its own copy armed and the peer's "my half has landed" relay
-    for (int s = 0; s < kT2Stages; ++s) { mbar_init(&S.w_full[s], rank == 0 ? 2 : 1); mbar_init(&S.w_empty[s], 1); }
+    // "full" lives in the leader: armed by its stream thread for both CTAs' bytes of a stage
+    for (int s = 0; s < kT2Stages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
     mbar_init(&S.x_full, 2 * kT2EpiThreads); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 2 * kT2EpiThreads);
     fence_mbar_init();
   }
@@ -238,7 +264,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   if (warp == kT2EpiWarps) {
     // =========================================================== weight stream: this CTA's half of every chunk
     if (lane == 0) {
-      const char* wsrc = reinterpret_cast<const char*>(W.tc_chunks);
       uint32_t empty_par = 0;
       int s = 0;
       for (int t = 0; t < T; ++t) {
@@ -247,30 +272,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           // stages follow the issue order; the packed buffer keeps the single-CTA kernel's layer order
           const int slot = L < nx ? 0 : (int)((slot_seq >> (4 * ((L - nx) >> 1))) & 0xFu);
           const int Lsrc = L < nx ? L : nxc + 2 * (int)((kT2LayerSrc >> (4 * slot)) & 0xFu) + ((L - nx) & 1);
-          const char* src = wsrc + (size_t)Lsrc * 2 * kTcChunkBytes + (size_t)rank * kT2HalfBytes;
-          mbar_expect_tx(&S.w_full[s], kT2StageBytes);
+          // 128-byte row index of this CTA's half of the stage's first chunk
+          const int row = (int)(((size_t)Lsrc * 2 * kTcChunkBytes + (size_t)rank * kT2HalfBytes) / 128);
+          if (rank == 0) mbar_expect_tx(&S.w_full[s], 2 * kT2StageBytes);       // both CTAs' halves
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
-            bulk_g2s(S.wst[s] + sub * kT2SubBytes, src + sub * kTcChunkBytes, kT2HalfBytes, &S.w_full[s]);               // hi
-            bulk_g2s(S.wst[s] + sub * kT2SubBytes + kT2HalfBytes, src + sub * kTcChunkBytes + kTcChunkBytes / 2,
-                     kT2HalfBytes, &S.w_full[s]);                                                                       // lo
+            tma_half_chunk_2sm(S.wst[s] + sub * kT2SubBytes, &p.wmap, row + sub * (kTcChunkBytes / 128), &S.w_full[s], 0);                        // hi
+            tma_half_chunk_2sm(S.wst[s] + sub * kT2SubBytes + kT2HalfBytes, &p.wmap, row + sub * (kTcChunkBytes / 128) + kTcChunkBytes / 256,
+                               &S.w_full[s], 0);                                                                                                      // lo
           }
           s ^= 1;
         }
       }
     }
   } else if (warp == kT2EpiWarps + 1) {
-    if (lane == 0 && rank != 0) {
-      // =========================================================== peer: relay "my half has landed"
-      const long long total = (long long)supers_per_step * T;
-      uint32_t full_par = 0;
-      int s = 0;
-      for (long long L = 0; L < total; ++L) {
-        mbar_wait(&S.w_full[s], (full_par >> s) & 1u);
-        full_par ^= 1u << s;
-        mbar_arrive_cluster(&S.w_full[s], 0);
-        s ^= 1;
-      }
+    if (rank != 0) {
+      // the peer's MMA warp has nothing to do: its loads report to the leader's barriers by themselves
     } else if (rank == 0) {
       // =========================================================== leader: MMA issue for the pair
       // The WHOLE warp runs this loop and one elected lane issues: every MMA operand is then a
@@ -708,8 +725,31 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
       return MACJD_ERR_CUDA;
     opted[dev] = smem;
   }
+  // TMA descriptor of the chunk buffer (a pure host-side encode; the driver entry point is looked up once)
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return MACJD_ERR_CUDA;
+  T2Args p;
+  p.a = a;
+  const size_t chunk_bytes = (size_t)(2 * kTcChunksPerX * (a.w.obs_pad / 32) + 8 * kTcChunksPerH) * kTcChunkBytes;
+  const cuuint64_t gdim[2] = {32, chunk_bytes / 128};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {32, kT2HalfBytes / 128};
+  const cuuint32_t estride[2] = {1, 1};
+  if (encode(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.w.tc_chunks), gdim, gstride, box, estride,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return MACJD_ERR_CUDA;
   const int pairs = (a.io.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
-  agent_forward_tc2_kernel<<<2 * pairs, kT2Threads, smem, (cudaStream_t)ctx->stream>>>(a);
+  agent_forward_tc2_kernel<<<2 * pairs, kT2Threads, smem, (cudaStream_t)ctx->stream>>>(p);
   return MACJD_OK;
 }
 
