@@ -425,6 +425,9 @@ def main():
                            "rnn_hidden": HID, "l2": "flushed between timed steps (256 MiB write)",
                            "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
                 "e2e": e2e, "gpu_launches": 2 * K, "roofline": roofline, "roofline_env": roofline_env,
+                # the metric for the env step alone and the agent act alone (same launches, timed apart)
+                "env_only": {"value": world * M / dt_env, "unit": "env-agent steps/s", "us_per_launch": dt_env * 1e6},
+                "act_only": {"value": world * M / dt_agent, "unit": "env-agent steps/s", "us_per_launch": dt_agent * 1e6},
                 "learner": learner_rec, "clocks": clocks, "cpu_baseline": cpu}
         print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
