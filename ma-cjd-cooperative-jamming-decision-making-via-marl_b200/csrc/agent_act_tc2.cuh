@@ -260,6 +260,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   TC_STAMP_ONCE(22);
   const uint32_t tmem = S.tmem_base;
   TC_STAMP_ONCE(23);
+  // the next kernel of the stream may be scheduled now if it asked for an early start (the env step does:
+  // its launch latency and table loads then overlap this kernel; it waits before reading the actions)
+  grid_launch_dependents();
 
   if (warp == kT2EpiWarps) {
     // =========================================================== weight stream: this CTA's half of every chunk

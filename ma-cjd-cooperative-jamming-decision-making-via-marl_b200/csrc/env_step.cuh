@@ -106,6 +106,10 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
   const bool phys = live && a.physics && do_phys;
   int step = 0;
   double r_p = 0.0, r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
+  // Everything above reads the scenario tables only.  From here on the kernel reads the actions and
+  // writes outputs: wait for the preceding kernel of the stream (normally the agent step that chose
+  // the actions) -- a no-op unless this launch was allowed to start early (env_launch).
+  if (do_phys) grid_dependency_wait();
   if (phys) {
     for (int r = 0; r < R; ++r) { prjs[r * BS + tid] = 0.0; prod[r * BS + tid] = 1.0; }
     if (wk == 0)
@@ -270,6 +274,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
 #else
     __syncthreads();
 #endif
+    if (kMode != 0) grid_dependency_wait();      // view warps: staged from the tables, nothing written yet
     const int valid = min(BS, n - e0);
     if ((S & 3) == 0 && (a.stage_ld & 3) == 0) {
       // rows are 16-byte multiples: coalesced float4 stores
@@ -300,6 +305,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
       }
     }
   }
+  if (kMode != 0 && do_views && !want_views) grid_dependency_wait();
   if (io.avail && do_views) {  // all actions always available (environment.py:539-551)
     const int valid = min(BS, n - e0);
     const int64_t base = (int64_t)e0 * J * A;
@@ -354,9 +360,22 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   a.split_views = physics && tab->n_envs <= 16384 && bs == 128 && smem <= 48 * 1024 && (io->state || io->obs || io->avail);
   if (a.split_views) {
     const size_t smem2 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 2);
-    if (tab->n_radars >= 2 && smem2 <= 48 * 1024) env_step_kernel<2><<<grid, 3 * bs, smem2, (cudaStream_t)ctx->stream>>>(a);
-    else env_step_kernel<1><<<grid, 2 * bs, smem, (cudaStream_t)ctx->stream>>>(a);
-    return MACJD_OK;
+    // allowed to start while the preceding kernel (the agent step) drains: launch latency, table loads and
+    // view staging overlap its tail; the kernel waits (grid_dependency_wait) before the first dependent access
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(grid); cfg.stream = (cudaStream_t)ctx->stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t err;
+    if (tab->n_radars >= 2 && smem2 <= 48 * 1024) {
+      cfg.blockDim = dim3(3 * bs); cfg.dynamicSmemBytes = smem2;
+      err = cudaLaunchKernelEx(&cfg, env_step_kernel<2>, a);
+    } else {
+      cfg.blockDim = dim3(2 * bs); cfg.dynamicSmemBytes = smem;
+      err = cudaLaunchKernelEx(&cfg, env_step_kernel<1>, a);
+    }
+    return err == cudaSuccess ? MACJD_OK : MACJD_ERR_CUDA;
   }
 #else
   a.split_views = 0;

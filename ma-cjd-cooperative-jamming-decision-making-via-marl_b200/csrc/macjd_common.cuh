@@ -62,6 +62,22 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
+// Programmatic dependent launch (stream order kept, launch latency and independent prologue work
+// overlapped): a kernel launched with the programmatic-serialization attribute may start while its
+// predecessor still runs; it must call grid_dependency_wait() before touching anything the
+// predecessor reads or writes.  A predecessor opts in with grid_launch_dependents(); without that
+// (or without the launch attribute) both calls are no-ops and the launch is an ordinary one.
+__device__ __forceinline__ void grid_dependency_wait() {
+#ifndef MACJD_TEST_HOST_EMULATION
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void grid_launch_dependents() {
+#ifndef MACJD_TEST_HOST_EMULATION
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 }  // namespace macjd
