@@ -96,6 +96,7 @@ __device__ __forceinline__ float reduce16(float v) {
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) agent_forward_kernel(const AgentArgs a) {
+  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   constexpr int TM = NT / 4;           // 16 column lanes x (NT/16) row groups x 4 rows
   const macjd_agent_weights& W = a.w;
   const macjd_agent_io& io = a.io;

@@ -6,8 +6,24 @@
 #include "cuda_emul.h"
 #else
 #include <cuda_runtime.h>
+// Every kernel launched through MACJD_LAUNCH starts with grid_dependency_wait() (below), so it may be
+// launched as a programmatic dependent of its predecessor in the stream: its blocks are scheduled while
+// the predecessor drains, the launch latency of the learner's ~60 short kernels overlaps, and stream
+// order is still what the kernel observes.
+namespace macjd {
+template <typename... KArgs, typename... Args>
+inline void launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+}  // namespace macjd
 #define MACJD_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+  ::macjd::launch_dependent(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)
 #define MACJD_DYNAMIC_SMEM(type, name)                             \
   extern __shared__ __align__(16) unsigned char macjd_dyn_smem_[]; \
   type* name = reinterpret_cast<type*>(macjd_dyn_smem_)
