@@ -129,6 +129,12 @@ MACJD_API int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab,
  * handed to the kernel in place when that is faster than a copy-engine transfer (outputs up to
  * 8 MB, inputs up to 256 KB; csrc/macjd_api.cu: direct_host_limit), so the io staging buffers
  * may go unused.  NULL outputs are skipped. */
+/* flags of the host-buffer structs.  MACJD_HOST_PINNED: the caller vouches that every host pointer in
+ * the struct is page-locked memory of the unified address space (cudaHostAlloc / torch pin_memory), so
+ * the library uses them as device addresses without asking the driver about each one on every call
+ * (about 1 us per pointer).  Without the flag each pointer is queried; pageable memory is copied. */
+#define MACJD_HOST_PINNED 1u
+
 typedef struct macjd_env_host {
   const int32_t* act_d;     /* host [n_envs][J]                                       */
   const float* act_p;       /* host [n_envs][J]                                       */
@@ -136,6 +142,8 @@ typedef struct macjd_env_host {
   uint8_t* terminated;      /* host [n_envs], optional                                */
   float* obs;               /* host [n_envs][J][S], optional                          */
   float* state;             /* host [n_envs][S], optional                             */
+  uint32_t flags;           /* MACJD_HOST_PINNED: see below                           */
+  uint32_t reserved;
 } macjd_env_host;
 MACJD_API int macjd_env_step_host(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io,
                                   const macjd_env_host* host);
@@ -252,6 +260,8 @@ typedef struct macjd_act_host {
   int32_t* actions;         /* host [M]                                               */
   float* power;             /* host [M]                                               */
   float* q_chosen;          /* host [M], optional                                     */
+  uint32_t flags;           /* MACJD_HOST_PINNED                                      */
+  uint32_t reserved;
 } macjd_act_host;
 MACJD_API int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io,
                                    const macjd_act_host* host);

@@ -57,13 +57,17 @@ class AgentIO(C.Structure):
                 ("gate_x", c_void_p)]
 
 
+HOST_PINNED = 1       # include/macjd.h: MACJD_HOST_PINNED
+
+
 class ActHost(C.Structure):
-    _fields_ = [("obs", c_void_p), ("avail", c_void_p), ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p)]
+    _fields_ = [("obs", c_void_p), ("avail", c_void_p), ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class EnvHost(C.Structure):
     _fields_ = [("act_d", c_void_p), ("act_p", c_void_p), ("reward", c_void_p), ("terminated", c_void_p),
-                ("obs", c_void_p), ("state", c_void_p)]
+                ("obs", c_void_p), ("state", c_void_p), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class CopyDesc(C.Structure):

@@ -103,16 +103,17 @@ class BasicMAC:
         One C call: copies in, fused step, copies out, stream drained on return
         (include/macjd.h: macjd_agent_act_host).  The recurrent state stays on the device."""
         from .. import _native as N
-        B = obs.shape[0]
-        M = B * self.n_agents
-        dev = self.device
-        if self.hidden_states is None or self.hidden_states.shape[0] != M:
-            self.init_hidden(batch_size=B)
-        if self.hidden_states.device != dev:
-            self.hidden_states = self.hidden_states.to(dev)
-        key = (M, N.ptr(obs), N.ptr(avail), N.ptr(actions_out), N.ptr(power_out), self.hidden_states.data_ptr(), self.agent.path)
+        # steady state: the caller hands in the same buffer objects every step -> identity checks only
         c = self._host_cache
-        if c is None or c["key"] != key:
+        if not (c is not None and c["keep"][0] is obs and c["keep"][1] is avail and (actions_out is None or c["keep"][2] is actions_out)
+                and (power_out is None or c["keep"][3] is power_out) and c["hid"] is self.hidden_states and c["path"] == self.agent.path):
+            B = obs.shape[0]
+            M = B * self.n_agents
+            dev = self.device
+            if self.hidden_states is None or self.hidden_states.shape[0] != M:
+                self.init_hidden(batch_size=B)
+            if self.hidden_states.device != dev:
+                self.hidden_states = self.hidden_states.to(dev)
             A = self.args.n_actions
             pin = dev.type == "cuda"
             if actions_out is None:
@@ -127,8 +128,11 @@ class BasicMAC:
                            test_mode=0, tile_rows=0, path=self.agent.path, avail=st["avail"].data_ptr(), epsilon=0.0, rng_step=0,
                            seed=self.seed & 0xFFFFFFFFFFFFFFFF, actions=st["actions"].data_ptr(),
                            power=st["power"].data_ptr(), q_chosen=st["q_chosen"].data_ptr())
-            hs = N.ActHost(obs=N.ptr(obs), avail=N.ptr(avail), actions=N.ptr(actions_out), power=N.ptr(power_out), q_chosen=None)
-            c = self._host_cache = {"key": key, "io": io, "host": hs, "stage": st, "keep": (obs, avail, actions_out, power_out)}
+            pinned = dev.type == "cuda" and all(torch.is_tensor(v) and v.is_pinned() for v in (obs, avail, actions_out, power_out))
+            hs = N.ActHost(obs=N.ptr(obs), avail=N.ptr(avail), actions=N.ptr(actions_out), power=N.ptr(power_out), q_chosen=None,
+                           flags=N.HOST_PINNED if pinned else 0)
+            c = self._host_cache = {"io": io, "host": hs, "stage": st, "keep": (obs, avail, actions_out, power_out),
+                                    "hid": self.hidden_states, "path": self.agent.path}
         eps = self.action_selector.anneal(t_env, test_mode)
         self._rng_step += 1
         io = c["io"]

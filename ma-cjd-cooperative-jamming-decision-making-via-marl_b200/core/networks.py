@@ -66,9 +66,26 @@ class PackedAgentWeights:
         n = int(np.prod(self.shapes[f]))
         return self.buffer[self.offsets[f]:self.offsets[f] + n].view(*self.shapes[f])
 
-    @torch.no_grad()
     def refresh(self, agent, force=False):
         """Re-pack if any parameter changed since the last pack (or moved device)."""
+        # the per-act fast path: no context manager, no tensor ops
+        slots = self.__dict__.get("_slots")
+        if slots is not None and not force and self.buffer is not None:
+            v = self.versions
+            i = 0
+            for m, k in slots:
+                p_ = m._parameters[k]
+                if p_._version != v[i][0]:
+                    break
+                i += 1
+            else:
+                p0 = slots[0][0]._parameters[slots[0][1]]
+                if p0.data_ptr() == v[0][1] and p0.device == self.buffer.device:
+                    return self
+        with torch.no_grad():
+            return self._repack(agent, force)
+
+    def _repack(self, agent, force):
         # (module, name) slots are collected once: walking agent.parameters() costs ~25 us per call, and this
         # check runs on every act; looking the Parameters up through their modules still sees replaced ones
         slots = self.__dict__.get("_slots")

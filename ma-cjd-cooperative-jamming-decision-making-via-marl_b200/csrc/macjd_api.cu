@@ -162,12 +162,13 @@ size_t direct_host_limit(bool write) {
 }
 extern "C++" {
 template <typename T>
-T* device_alias(T* host_ptr, size_t bytes, bool write) {
+T* device_alias(T* host_ptr, size_t bytes, bool write, uint32_t flags) {
 #ifdef MACJD_TEST_HOST_EMULATION
-  (void)bytes; (void)write;
+  (void)bytes; (void)write; (void)flags;
   return host_ptr;                     // emulation: "device" memory is host memory
 #else
   if (!host_ptr || bytes > direct_host_limit(write)) return nullptr;
+  if (flags & MACJD_HOST_PINNED) return host_ptr;      // caller-vouched: unified addressing, device alias == host pointer
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, host_ptr) != cudaSuccess) {
     cudaGetLastError();
@@ -193,16 +194,16 @@ int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, con
   if (M == 0) return MACJD_OK;
   macjd_agent_io k = *io;
   const size_t obs_bytes = M * w->obs_dim * sizeof(float), avail_bytes = M * w->n_actions;
-  if (const float* d = device_alias(host->obs, obs_bytes, false)) k.obs = d;
+  if (const float* d = device_alias(host->obs, obs_bytes, false, host->flags)) k.obs = d;
   else st = copy_async(const_cast<float*>(io->obs), host->obs, obs_bytes, cudaMemcpyHostToDevice, ctx);
   if (st == MACJD_OK && host->avail) {
-    if (const uint8_t* d = device_alias(host->avail, avail_bytes, false)) k.avail = d;
+    if (const uint8_t* d = device_alias(host->avail, avail_bytes, false, host->flags)) k.avail = d;
     else st = copy_async(const_cast<uint8_t*>(io->avail), host->avail, avail_bytes, cudaMemcpyHostToDevice, ctx);
   }
   if (st != MACJD_OK) return st;
-  int32_t* d_act = device_alias(host->actions, M * sizeof(int32_t), true);
-  float* d_pow = device_alias(host->power, M * sizeof(float), true);
-  float* d_q = (host->q_chosen && io->q_chosen) ? device_alias(host->q_chosen, M * sizeof(float), true) : nullptr;
+  int32_t* d_act = device_alias(host->actions, M * sizeof(int32_t), true, host->flags);
+  float* d_pow = device_alias(host->power, M * sizeof(float), true, host->flags);
+  float* d_q = (host->q_chosen && io->q_chosen) ? device_alias(host->q_chosen, M * sizeof(float), true, host->flags) : nullptr;
   if (d_act) k.actions = d_act;
   if (d_pow) k.power = d_pow;
   if (d_q) k.q_chosen = d_q;
@@ -229,17 +230,17 @@ int macjd_env_step_host(const macjd_ctx* ctx, const macjd_env_tables* tab, const
   const size_t n = (size_t)tab->n_envs, J = (size_t)tab->n_jammers;
   const size_t S = (size_t)tab->n_radars * (6 + tab->n_types) + 2 * J;
   macjd_env_io k = *io;
-  if (const int32_t* d = device_alias(host->act_d, n * J * sizeof(int32_t), false)) k.act_d = d;
+  if (const int32_t* d = device_alias(host->act_d, n * J * sizeof(int32_t), false, host->flags)) k.act_d = d;
   else st = copy_async(const_cast<int32_t*>(io->act_d), host->act_d, n * J * sizeof(int32_t), cudaMemcpyHostToDevice, ctx);
   if (st == MACJD_OK) {
-    if (const float* d = device_alias(host->act_p, n * J * sizeof(float), false)) k.act_p = d;
+    if (const float* d = device_alias(host->act_p, n * J * sizeof(float), false, host->flags)) k.act_p = d;
     else st = copy_async(const_cast<float*>(io->act_p), host->act_p, n * J * sizeof(float), cudaMemcpyHostToDevice, ctx);
   }
   if (st != MACJD_OK) return st;
-  float* d_rew = device_alias(host->reward, n * sizeof(float), true);
-  uint8_t* d_term = device_alias(host->terminated, n, true);
-  float* d_obs = device_alias(host->obs, n * J * S * sizeof(float), true);
-  float* d_state = device_alias(host->state, n * S * sizeof(float), true);
+  float* d_rew = device_alias(host->reward, n * sizeof(float), true, host->flags);
+  uint8_t* d_term = device_alias(host->terminated, n, true, host->flags);
+  float* d_obs = device_alias(host->obs, n * J * S * sizeof(float), true, host->flags);
+  float* d_state = device_alias(host->state, n * S * sizeof(float), true, host->flags);
   if (d_rew) k.reward = d_rew;
   if (d_term) k.terminated = d_term;
   if (d_obs) k.obs = d_obs;

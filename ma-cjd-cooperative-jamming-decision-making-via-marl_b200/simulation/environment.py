@@ -171,7 +171,8 @@ class ElectromagneticEnvironment:
             unknown = set(host) - {"act_d", "act_p", "reward", "terminated", "obs", "state"}
             if unknown or "act_d" not in host or "act_p" not in host:
                 raise ValueError(f"step_host: need act_d and act_p, unknown keys {sorted(unknown)}")
-            hs = N.EnvHost(**{k: N.ptr(v) for k, v in host.items()})
+            pinned = all(torch.is_tensor(v) and v.is_pinned() for v in host.values()) and self.device.type == "cuda"
+            hs = N.EnvHost(flags=N.HOST_PINNED if pinned else 0, **{k: N.ptr(v) for k, v in host.items()})
             c = self._host_cache = {"key": key, "host": hs, "io": self._io(self._act_d_dev, self._act_p_dev), "keep": dict(host)}
         self._lib.call("macjd_env_step_host", self._ctx(), self._ctab, c["io"], c["host"])
 
