@@ -127,7 +127,7 @@ MACJD_API int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab,
  * ctx->stream, launches the step, copies the requested outputs back and returns after the
  * stream has drained.  Host pointers may be pageable or page-locked; page-locked buffers are
  * handed to the kernel in place when that is faster than a copy-engine transfer (outputs up to
- * 8 MB, inputs up to 256 KB; csrc/macjd_api.cu: direct_host_limit), so the io staging buffers
+ * 8 MB, inputs up to 1 MB; csrc/macjd_api.cu: direct_host_limit), so the io staging buffers
  * may go unused.  NULL outputs are skipped. */
 /* flags of the host-buffer structs.  MACJD_HOST_PINNED: the caller vouches that every host pointer in
  * the struct is page-locked memory of the unified address space (cudaHostAlloc / torch pin_memory), so

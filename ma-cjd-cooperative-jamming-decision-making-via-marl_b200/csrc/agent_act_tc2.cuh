@@ -205,6 +205,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   // the TMEM allocation instead of following them.
   float4 h_in[kT2Upt / 4];
   float x_in[32 / kT2Parts];
+  // Observation block: 64 rows x 8 float4 slots, two slots per epilogue thread.  When rows are 16-byte
+  // multiples the slots are numbered in MEMORY order (a warp reads 512 contiguous bytes -- full lines
+  // from HBM, full-size reads over PCIe when the observations sit in page-locked host memory); the
+  // zero padding of k >= obs_dim takes the slots behind the data.  Otherwise thread = (row, 8 k) scalars.
+  const bool x_vec = (O & 3) == 0;
+  const int O4 = O >> 2;
+  auto x_slot = [&](int s_, int xc_, int& r_, int& k4_) -> bool {
+    const int w4 = min(8, O4 - 8 * xc_), nd = kTcRows * w4;
+    if (s_ < nd) { r_ = s_ / w4; k4_ = s_ - r_ * w4; return true; }
+    const int p_ = s_ - nd, wz = 8 - w4;
+    r_ = p_ / wz; k4_ = w4 + (p_ - r_ * wz);
+    return false;
+  };
+  float4 x4_in[2];
+  if (warp < kT2EpiWarps && x_vec) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int r_, k4_;
+      const bool data = x_slot(tid + i * kT2EpiThreads, 0, r_, k4_);
+      x4_in[i] = (data && r_ < valid && mode != 4)
+                     ? __ldg(reinterpret_cast<const float4*>(io.obs + (size_t)(row0 + r_) * O) + k4_) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   if (warp < kT2EpiWarps) {
     const int q4 = warp & 3, ch = warp >> 2, half = q4 >> 1;
     const int r = (q4 & 1) * 32 + lane, ub = half * 64 + ch * kT2Upt, part = half * kT2ColSplit + ch;
@@ -216,7 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #pragma unroll
     for (int j = 0; j < 32 / kT2Parts; ++j) {
       const int kk = part * (32 / kT2Parts) + j;
-      x_in[j] = (live && kk < O && mode != 4) ? __ldg(io.obs + (size_t)(row0 + r) * O + kk) : 0.f;
+      x_in[j] = (live && kk < O && mode != 4 && !x_vec) ? __ldg(io.obs + (size_t)(row0 + r) * O + kk) : 0.f;
     }
   }
 
@@ -416,6 +439,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
         const float* obs = io.obs + (tM + row0 + r) * O;
         const bool pre = (t == 0 && xc == 0);      // already in registers (requested at kernel entry)
+        if (x_vec) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            int r_, k4_;
+            const bool data = x_slot(tid + i * kT2EpiThreads, xc, r_, k4_);
+            float4 q = x4_in[i];
+            if (!pre)
+              q = (data && r_ < valid) ? __ldg(reinterpret_cast<const float4*>(io.obs + (tM + row0 + r_) * O + 32 * xc) + k4_)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float v[4] = {q.x, q.y, q.z, q.w};
+            store_split4(xhi, xlo, r_, 4 * k4_, 32, v);
+          }
+        } else
 #pragma unroll
         for (int g = 0; g < 32 / kT2Parts / 4; ++g) {
           const int k = part * (32 / kT2Parts) + 4 * g;

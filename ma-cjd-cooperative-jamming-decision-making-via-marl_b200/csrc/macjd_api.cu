@@ -151,12 +151,14 @@ int drain(const macjd_ctx* ctx) {
 // Host buffers in page-locked memory can be handed to the kernels as they are (the SMs read / write them
 // over PCIe: no separate copy operation and none of its launch latency).  Measured on B200 / PCIe 5
 // (tools/e2e_host.py, 4096 envs): kernel WRITES to host memory beat a copy-engine transfer even at 786 KB
-// (env step + D2H 62 -> 50 us); kernel READS win only for small buffers (786 KB of observations read in
-// place cost the agent step +10 us, its first phase waits for them).  Larger buffers and pageable memory
-// go through the copy engines.  MACJD_DIRECT_HOST_READ_BYTES / _WRITE_BYTES override the limits (0 = never).
+// (env step + D2H 62 -> 50 us); kernel READS of the 786 KB of observations lost 8 us against the copy
+// engine while every thread fetched its own row with 4-byte loads, and win 4 us since the pair kernel
+// reads the block in memory order (512 contiguous bytes per warp, requested at kernel entry).  The read
+// limit is set just above that size; larger inputs and pageable memory go through the copy engines.
+// MACJD_DIRECT_HOST_READ_BYTES / _WRITE_BYTES override the limits (0 = never).
 size_t direct_host_limit(bool write) {
   static const size_t lim[2] = {
-      [] { const char* e = getenv("MACJD_DIRECT_HOST_READ_BYTES"); return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)256 << 10; }(),
+      [] { const char* e = getenv("MACJD_DIRECT_HOST_READ_BYTES"); return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)1 << 20; }(),
       [] { const char* e = getenv("MACJD_DIRECT_HOST_WRITE_BYTES"); return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)8 << 20; }()};
   return lim[write ? 1 : 0];
 }

@@ -145,3 +145,23 @@ def test_split_unroll_is_bit_identical_to_fused_unroll(M, T):
     top2 = q.topk(2, dim=-1).values
     decidable = (top2[..., 0] - top2[..., 1]) > 1e-5
     assert torch.equal(d["actions"][decidable], a["actions"][decidable])
+
+
+@pytest.mark.parametrize("O", [30, 40, 68])
+def test_pair_kernel_observation_widths(O):
+    """Observation widths that are not one 16-byte-aligned 32-float block: O = 30 takes the scalar
+    observation path, O = 40 / 68 two / three blocks (the vector path with zero padding behind the data)."""
+    mac, args = AC.random_agent(3, O, 5, 128, 128, 2, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    M, T = 200, 2
+    obs = torch.randn(T, M, O, device="cuda", generator=g) * 2
+    h0 = torch.randn(M, 128, device="cuda", generator=g) * 0.5
+    res = {}
+    for path in (1, 3):
+        h = h0.clone()
+        res[path] = mac.agent.run(obs, h, n_steps=T, select=True, test_mode=True, want_q=True, want_params=True,
+                                  want_hidden_seq=True, path=path, split_unroll=False)
+    a, b = res[1], res[3]
+    torch.testing.assert_close(b["params_all"], a["params_all"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(b["hidden_seq"], a["hidden_seq"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(b["q_all"], a["q_all"], rtol=1e-4, atol=2e-5)
