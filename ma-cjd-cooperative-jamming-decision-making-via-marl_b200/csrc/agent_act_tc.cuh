@@ -19,11 +19,15 @@
 //   warp 5     lane 0 issues the tcgen05.mma's: M = 64, N = 128, K = 8, kind::tf32, three split
 //              products per k-step, accumulators in 512 TMEM columns.
 //   mbarriers carry weights-landed / stage-free / accumulator-ready / operand-ready events.
-// Measured on B200 (tools/tc_mma_rate.py): one M x N x 8 TF32 SS MMA costs ~52 / 69 / 133 cycles
-// for N = 64 / 128 / 256 regardless of M in {64, 128}; a single thread that both waits on
-// barriers and issues copies needs ~800 cycles per chunk, hence the separate stream warp.
-// One CTA-step takes ~32 us alone and ~48 us with 128 CTAs resident (1.09 MB of weight chunks
-// per CTA-step from L2: 2.9 TB/s aggregate).
+// Measured on B200 (tools/tc_mma_rate.py): one cta_group::1 M x N x 8 TF32 SS MMA costs 68 cycles at
+// N = 128 for M = 64 and for M = 128 -- a 64-row CTA wastes half of every instruction -- and a single
+// thread that both waits on barriers and issues copies needs ~800 cycles per chunk, hence the separate
+// stream warp.  One CTA-step takes ~32 us.
+//
+// This is the first tensor-core version (io->path = 2).  The default tensor-core kernel is the
+// CTA-pair one in agent_act_tc2.cuh (path 3 / auto): cta_group::2 MMAs (M = 128 per pair at 37 cycles),
+// half the weight bytes per CTA, warp-uniform issue, 22 us per step even for <= 64 rows.  This file
+// also holds what both share: chunk geometry, TcConst, the operand-tile helpers.
 #pragma once
 #include "agent_act.cuh"
 #include "tc05.cuh"
