@@ -131,6 +131,31 @@ class PackedAgentWeights:
         self.versions = versions
         return self
 
+    @torch.no_grad()
+    def refresh_qhead(self, agent):
+        """Re-pack only what the learner trains (fc2_q_head, core/qmix.py:178): six small fields and the
+        last four tensor-core chunks, in place.  The full re-pack is ~60 tensor ops per train step."""
+        if self.buffer is None or self.buffer.device != agent.fc1.weight.device:
+            return self.refresh(agent, force=True)
+        H, A = self.H, self.A
+        w1 = agent.fc2_q_head[0].weight.detach().float()             # [H, H + A + 1]
+        self.view("wqt").copy_(w1[:, :H].t())
+        self.view("bq1").copy_(agent.fc2_q_head[0].bias.detach())
+        self.view("w1a").copy_(w1[:, H:H + A].t())
+        self.view("w1p").copy_(w1[:, H + A])
+        self.view("w2").copy_(agent.fc2_q_head[2].weight.detach().reshape(-1))
+        self.view("bq2").copy_(agent.fc2_q_head[2].bias.detach())
+        if self.tc_buffer is not None:
+            kc = self.tc_buffer.shape[-1] // 128
+            full = self._umma_chunks(w1[:, :H].contiguous(), kc)     # [H / kc, 128 * kc]: the chunks the buffer ends with
+            hi = (full.view(torch.int32) & -8192).view(torch.float32)
+            self.tc_buffer[-full.shape[0]:, 0].copy_(hi)
+            self.tc_buffer[-full.shape[0]:, 1].copy_(full - hi)
+        slots = self.__dict__.get("_slots")
+        if slots is not None:
+            self.versions = tuple([(m._parameters[k]._version, m._parameters[k].data_ptr()) for m, k in slots])
+        return self
+
     @staticmethod
     def _umma_chunks(w, kc=16):
         """[128, K] (out, in) -> [K / kc] chunks in the K-major no-swizzle UMMA layout
@@ -213,6 +238,10 @@ class RNNAgent(nn.Module):
 
     def packed(self, force=False):
         return self._packed.refresh(self, force=force)
+
+    def packed_qhead(self):
+        """After an in-place update of fc2_q_head alone (the learner's Adam step)."""
+        return self._packed.refresh_qhead(self)
 
     def _ctx(self):
         dev = self.fc1.weight.device

@@ -263,7 +263,7 @@ class QMixLearner:
         L.callv("macjd_clip_adam", ctx, tensors, grad, opt["m"], opt["v"], sums, float(self.args.grad_norm_clip),
                 float(self.args.lr), BETA1, BETA2, ADAM_EPS, int(opt["step"]), opt["scal"], opt["scratch"],
                 opt["scratch"].numel())
-        agent.packed(force=True)          # the Q-head changed under the packed copy
+        agent.packed_qhead()              # the Q-head changed under the packed copy (nothing else is trained)
 
         # 11. hard target sync (qmix.py:203-205)
         if (self.train_step - self.last_target_update_step) >= self.args.target_update_interval:
