@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) gather_q_kernel(const float* __restrict__
 // ---------------------------------------------------------------- column reductions
 // part[chunk][c] = sum over the chunk's rows of X[r][c] (* Y[r][c]);  then a fixed-order
 // second pass.  Used for bias gradients and LayerNorm dgamma / dbeta.
-constexpr int kColsumRows = 256;
+constexpr int kColsumRows = 64;     // rows per partial block: each thread walks them serially, so short chunks, many blocks
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y,
                                                              int R, int Cn, int ldx, float* __restrict__ part) {
   grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)

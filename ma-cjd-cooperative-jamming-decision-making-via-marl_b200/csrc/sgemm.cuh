@@ -127,7 +127,9 @@ inline int gemm_splits(int M, int N, int K) {
   const int tiles = ((M + kGM - 1) / kGM) * ((N + kGN - 1) / kGN);
   if (K < 2048 || tiles >= kNumSMs) return 1;
   int s = (2 * kNumSMs + tiles - 1) / tiles;
-  const int maxs = (K + 511) / 512;
+  // slices of >= 128 rows: the learner's weight gradients reduce a few thousand rows into one to four
+  // tiles -- with 512-row slices that was 7 to 28 CTAs walking 28 k-steps each (54 us per GEMM)
+  const int maxs = (K + 127) / 128;
   if (s > maxs) s = maxs;
   return s < 1 ? 1 : s;
 }
