@@ -239,6 +239,9 @@ typedef struct macjd_agent_io {
                                  Other kernels return MACJD_ERR_UNSUPPORTED for part != 0.   */
   int32_t reserved2;
   float* gate_x;              /* [T][M][3][H] part 3 output / part 4 input, else unused  */
+  const float* epsilon_dev;   /* optional DEVICE scalars that override `epsilon` / `rng_step`: kernel      */
+  const uint32_t* rng_step_dev; /* parameters are frozen when a launch is replayed from a CUDA graph, these
+                                 are not (BatchedEpisodeRunner replays a whole episode as one graph) */
 } macjd_agent_io;
 
 /* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);

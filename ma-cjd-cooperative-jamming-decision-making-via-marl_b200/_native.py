@@ -54,7 +54,7 @@ class AgentIO(C.Structure):
                 ("sel_actions", c_void_p), ("q_sel", c_void_p), ("avail", c_void_p), ("u_eps", c_void_p),
                 ("rand_actions", c_void_p), ("epsilon", c_float), ("rng_step", C.c_uint32), ("seed", c_uint64),
                 ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p), ("part", c_int32), ("reserved2", c_int32),
-                ("gate_x", c_void_p)]
+                ("gate_x", c_void_p), ("epsilon_dev", c_void_p), ("rng_step_dev", c_void_p)]
 
 
 HOST_PINNED = 1       # include/macjd.h: MACJD_HOST_PINNED

@@ -187,7 +187,11 @@ class PackedAgentWeights:
         full = torch.cat(seq, dim=0).contiguous()               # [n_chunks, 128 * kc]
         hi = (full.view(torch.int32) & -8192).view(torch.float32)
         lo = full - hi
-        self.tc_buffer = torch.stack([hi, lo], dim=1).contiguous()   # [n_chunks, 2, 2048]
+        new = torch.stack([hi, lo], dim=1)                            # [n_chunks, 2, 128 * kc]
+        if self.tc_buffer is not None and self.tc_buffer.shape == new.shape and self.tc_buffer.device == new.device:
+            self.tc_buffer.copy_(new)                                 # same address: captured launches stay valid
+        else:
+            self.tc_buffer = new.contiguous()
 
     def cstruct(self):
         if self._cstruct is not None and self._cstruct_for == (self.buffer.data_ptr(), id(self.tc_buffer)):

@@ -551,12 +551,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
           int chosen = bim;
           if (!io.test_mode) {
             const uint32_t row_id = (uint32_t)(row0 + r);
-            const float u = io.u_eps ? io.u_eps[m] : philox_uniform(io.seed, kStreamEpsilon, row_id, io.rng_step + t, 0);
-            if (u < io.epsilon) {
+            const float u = io.u_eps ? io.u_eps[m] : philox_uniform(io.seed, kStreamEpsilon, row_id, (io.rng_step_dev ? __ldg(io.rng_step_dev) : io.rng_step) + t, 0);
+            if (u < (io.epsilon_dev ? __ldg(io.epsilon_dev) : io.epsilon)) {
               if (io.rand_actions) {
                 chosen = io.rand_actions[m];
               } else {
-                const float u2 = philox_uniform(io.seed, kStreamRandomAction, row_id, io.rng_step + t, 0);
+                const float u2 = philox_uniform(io.seed, kStreamRandomAction, row_id, (io.rng_step_dev ? __ldg(io.rng_step_dev) : io.rng_step) + t, 0);
                 const int navl = n_avail > 0 ? n_avail : A;
                 int kth = (int)(u2 * (float)navl);
                 kth = kth >= navl ? navl - 1 : kth;

@@ -365,7 +365,8 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const int no_pdl = getenv("MACJD_NO_PDL") ? atoi(getenv("MACJD_NO_PDL")) : 0;   // experiments
+    attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
     cfg.gridDim = dim3(grid); cfg.stream = (cudaStream_t)ctx->stream; cfg.attrs = attr; cfg.numAttrs = 1;
     cudaError_t err;
     if (tab->n_radars >= 2 && smem2 <= 48 * 1024) {

@@ -170,3 +170,33 @@ def check_host_buffer_api(device, lib, n_envs=7, steps=5, pinned=True):
         obs_h = hb["obs"]
     with pytest.raises(ValueError):
         env_h.step_host({"act_d": hb["act_d"]})
+
+
+def check_episode_graph_equals_stepwise(device, n_envs=64):
+    """BatchedEpisodeRunner.run replays a whole episode as one CUDA graph (epsilon and the Philox counter
+    come from device memory); twin runners, one stepping launch by launch, must produce identical
+    trajectories over consecutive episodes -- exploration draws included."""
+    import copy
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import hetero_spec
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
+    args = rl_args(device, buffer_size=4 * n_envs, rnn_hidden_dim=128, actor_hidden_dim=128, agent_kernel_path=0,
+                   epsilon_anneal_time=40)
+    spec = hetero_spec(n_envs, seed=2, active=True, episode_limit=args.episode_limit)
+    torch.manual_seed(8)
+    mac0 = BasicMAC(24, args)
+    mac0.cuda()
+    runners = []
+    for _ in range(2):
+        env = ElectromagneticEnvironment(args, spec=spec, device=device, seed=21)
+        runners.append(BatchedEpisodeRunner(env, copy.deepcopy(mac0), EpisodeReplayBuffer(args, device=device), args))
+    for ep in range(3):
+        info_s = runners[0].run(use_graph=False)
+        info_g = runners[1].run(use_graph=True)
+        assert not getattr(runners[1], "_graph_failed", False)
+        for k, v in runners[0].traj.items():
+            assert torch.equal(v, runners[1].traj[k]), (ep, k)
+        assert info_s["episode_return"] == info_g["episode_return"]
+    assert runners[0].t_env == runners[1].t_env and runners[0].mac._rng_step == runners[1].mac._rng_step
