@@ -93,6 +93,7 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   if (st != MACJD_OK) return st;
   if (!w || !io) return MACJD_ERR_INVALID_ARG;
   if (io->path < 0 || io->path > 3 || io->part < 0 || io->part > 4) return MACJD_ERR_INVALID_ARG;
+  if (io->n_rows == 0 && io->n_steps >= 1) return MACJD_OK;      // an empty batch is a no-op (its buffers have no address)
   if (io->part == 2 && (io->n_steps != 1 || !io->hidden)) return MACJD_ERR_INVALID_ARG;
   if (io->part == 3 && (io->n_steps != 1 || !io->gate_x)) return MACJD_ERR_INVALID_ARG;
   if (io->part == 4 && !io->gate_x) return MACJD_ERR_INVALID_ARG;

@@ -58,6 +58,10 @@ def make_spec(kind, n):
         return scaled_spec(n, seed=23)
     if kind == "scaled_small":
         return scaled_spec(n, n_jammers=3, n_radars=5, n_targets=2, seed=24)
+    if kind == "odd_radars":            # small-batch kernel with two physics workers, radars 0 and 2 / radar 1; S % 4 != 0
+        return scaled_spec(n, n_jammers=2, n_radars=3, n_targets=1, seed=25)
+    if kind == "one_radar":             # nothing to share between the physics workers
+        return scaled_spec(n, n_jammers=2, n_radars=1, n_targets=2, seed=26)
     raise KeyError(kind)
 
 

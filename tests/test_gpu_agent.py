@@ -165,3 +165,38 @@ def test_pair_kernel_observation_widths(O):
     torch.testing.assert_close(b["params_all"], a["params_all"], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(b["hidden_seq"], a["hidden_seq"], rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(b["q_all"], a["q_all"], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("A,M", [(8, 70), (2, 1), (1, 129)])
+def test_pair_kernel_action_counts_and_tiny_batches(A, M):
+    """The widest and narrowest action sets the tensor-core kernel takes (1..8) and batches smaller than one
+    row tile (one live row in a 128-row pair; one row spilling into a second pair)."""
+    mac, args = AC.random_agent(4, 24, A, 128, 128, 2, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    obs = torch.randn(1, M, 24, device="cuda", generator=g) * 3
+    h0 = torch.randn(M, 128, device="cuda", generator=g) * 0.5
+    avail = torch.rand(1, M, A, device="cuda", generator=g) < 0.6
+    avail[..., 0] = True
+    res = {}
+    for path in (1, 3):
+        h = h0.clone()
+        res[path] = mac.agent.run(obs, h, avail=avail, select=True, test_mode=True, want_q=True, want_params=True, path=path)
+    a, b = res[1], res[3]
+    torch.testing.assert_close(b["params_all"], a["params_all"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(b["q_all"], a["q_all"], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(b["hidden"], a["hidden"], rtol=1e-4, atol=2e-5)
+    q = a["q_all"].masked_fill(~avail, -float("inf"))
+    if A > 1:
+        top2 = q.topk(2, dim=-1).values
+        decidable = (top2[..., 0] - top2[..., 1]) > 1e-4
+    else:
+        decidable = torch.ones_like(a["actions"], dtype=torch.bool)
+    assert torch.equal(a["actions"][decidable], b["actions"][decidable])
+
+
+def test_zero_rows_is_a_no_op():
+    mac, args = AC.random_agent(4, 24, 5, 128, 128, 2, "cuda")
+    for path in (1, 2, 3):
+        out = mac.agent.run(torch.zeros(1, 0, 24, device="cuda"), torch.zeros(0, 128, device="cuda"), select=True,
+                            test_mode=True, want_q=True, path=path)
+        assert out["actions"].shape == (1, 0) and out["q_all"].shape == (1, 0, 5)

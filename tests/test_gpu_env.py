@@ -21,7 +21,8 @@ def test_env_kernel_vs_reference_golden(name):
     check_env_against_golden(make_env, name)
 
 
-@pytest.mark.parametrize("kind,n", [("hetero", 4096), ("active", 5000), ("scaled", 1111), ("scaled_small", 777)])
+@pytest.mark.parametrize("kind,n", [("hetero", 4096), ("active", 5000), ("scaled", 1111), ("scaled_small", 777),
+                                    ("odd_radars", 1000), ("one_radar", 333), ("active", 20000)])
 def test_env_kernel_vs_oracle(kind, n):
     check_env_against_oracle(make_env, kind, n, steps=5)
 
