@@ -103,6 +103,31 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
     }
   }
 
+  // Small-batch kernels: this env's whole scenario column goes to shared memory BEFORE the dependency wait
+  // (the tables are read-only, and while the agent kernel runs this costs nothing); after the wait every
+  // table lookup of the physics is a shared-memory read instead of an L2 round trip on the dependent chain
+  // (jammer loop 4.7 -> us, tools/env_phase_profile.py).  16 loads in flight per thread; the workers of an
+  // env take alternate rows and meet at a named barrier.
+  const int n_tab_rows = 16 * R + 8 * J + 3 * K;
+  double* tabs = pdv + (size_t)RK * BS;                  // [n_tab_rows][BS], kMode 1 / 2 only
+  if (kMode != 0 && a.physics && do_phys) {
+    if (live) {
+#pragma unroll 1
+      for (int row0 = wk * 16; row0 < n_tab_rows; row0 += 16 * NW) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (row0 + i < n_tab_rows) ? env_tab(col, rs, row0 + i) : 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (row0 + i < n_tab_rows) tabs[(row0 + i) * BS + tid] = v[i];
+      }
+    }
+#ifndef MACJD_TEST_HOST_EMULATION
+    asm volatile("bar.sync 2, %0;\n" ::"r"(NW * BS) : "memory");
+#endif
+  }
+  auto tab = [&](int row) -> double { return kMode != 0 ? tabs[row * BS + tid] : env_tab(col, rs, row); };
+
   const bool phys = live && a.physics && do_phys;
   int step = 0;
   double r_p = 0.0, r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
@@ -123,7 +148,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
       const int Ti = io.act_d[(int64_t)e * J + j];
       double P = (double)io.act_p[(int64_t)e * J + j];
       P = P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
-      const double pmin = env_tab(col, rs, jr + 6), pmax = env_tab(col, rs, jr + 7);
+      const double pmin = tab(jr + 6), pmax = tab(jr + 7);
       const double range = pmax - pmin;
       const double power = pmin + P * range;
       const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
@@ -132,21 +157,21 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
       if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
         const int tgt = (Ti + 1) / 2 - 1;
         const int rr = rbase + 16 * tgt;
-        const double dx = env_tab(col, rs, jr + 4) - env_tab(col, rs, rr + 10);
-        const double dy = env_tab(col, rs, jr + 5) - env_tab(col, rs, rr + 11);
+        const double dx = tab(jr + 4) - tab(rr + 10);
+        const double dy = tab(jr + 5) - tab(rr + 11);
         const double dist = sqrt(dx * dx + dy * dy);
         if (dist > 1e-6) {
           // core/jammer.py:73-98
           const double dsq = fmax(1e-9, dist * dist);
-          const double den = dsq * env_tab(col, rs, jr + 1) * env_tab(col, rs, jr + 2) * fmax(1e-9, env_tab(col, rs, jr + 3));
+          const double den = dsq * tab(jr + 1) * tab(jr + 2) * fmax(1e-9, tab(jr + 3));
           double prj = 0.0;
-          if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * env_tab(col, rs, jr + 0) * env_tab(col, rs, rr + 2)) / den);
+          if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * tab(jr + 0) * tab(rr + 2)) / den);
           if (Ti & 1) {  // suppression
             prjs[tgt * BS + tid] += prj;
             supp_mask |= (1ull << tgt);
           } else {       // deception: false target (environment.py:408-437)
-            const double pn = env_tab(col, rs, rr + 6);
-            double snr_f = pn > 1e-18 ? (env_tab(col, rs, rr + 8) * prj) / pn : 0.0;
+            const double pn = tab(rr + 6);
+            double snr_f = pn > 1e-18 ? (tab(rr + 8) * prj) / pn : 0.0;
             snr_f = fmax(0.0, snr_f);
             const double pd_f = albersheim(T, snr_f);
             const float u = io.noise ? io.noise[(int64_t)e * (RK + J) + RK + j]
@@ -164,10 +189,10 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
     const double four_pi3 = (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793);
     for (int r = wk; r < R; r += NW) {
       const int rr = rbase + 16 * r;
-      const double pt = env_tab(col, rs, rr + 0), gt = env_tab(col, rs, rr + 1), gr = env_tab(col, rs, rr + 2);
-      const double lam = env_tab(col, rs, rr + 3), loss = env_tab(col, rs, rr + 4), latm = env_tab(col, rs, rr + 5);
-      const double pn = env_tab(col, rs, rr + 6), Ga = env_tab(col, rs, rr + 7), D = env_tab(col, rs, rr + 8);
-      const double rx = env_tab(col, rs, rr + 10), ry = env_tab(col, rs, rr + 11);
+      const double pt = tab(rr + 0), gt = tab(rr + 1), gr = tab(rr + 2);
+      const double lam = tab(rr + 3), loss = tab(rr + 4), latm = tab(rr + 5);
+      const double pn = tab(rr + 6), Ga = tab(rr + 7), D = tab(rr + 8);
+      const double rx = tab(rr + 10), ry = tab(rr + 11);
       const double jam = D * prjs[r * BS + tid];
       const double den1 = jam + pn;
       const double num0 = pt * gt * gr * (lam * lam);
@@ -175,9 +200,9 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
       double red = 0.0;
       for (int k = 0; k < K; ++k) {
         const int tr = tbase + 3 * k;
-        const double dx = rx - env_tab(col, rs, tr + 0), dy = ry - env_tab(col, rs, tr + 1);
+        const double dx = rx - tab(tr + 0), dy = ry - tab(tr + 1);
         const double d = fmax(sqrt(dx * dx + dy * dy), 1e-6);
-        const double num = num0 * env_tab(col, rs, tr + 2);
+        const double num = num0 * tab(tr + 2);
         const double d2 = d * d;
         const double den = four_pi3 * (d2 * d2) * loss * latm;
         const double ps = den > 1e-18 ? num / den : 0.0;
@@ -203,7 +228,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
       }
       if (io.tracking) io.tracking[(int64_t)r * n + e] = tracked ? 1 : 0;
       // memoryless TRACK state (core/radar.py:90-117) -> r_d; suppression / deception terms of r_j
-      const double rd_term = tracked ? fmin(fmax(-env_tab(col, rs, rr + 9), T.rd_min), T.rd_max) : 0.0;
+      const double rd_term = tracked ? fmin(fmax(-tab(rr + 9), T.rd_min), T.rd_max) : 0.0;
       const bool supp = (supp_mask >> r) & 1ull, hit = (hit_mask >> r) & 1ull;
       if (kMode == 2) {
         rad[(0 * R + r) * BS + tid] = rd_term;
@@ -314,9 +339,11 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
   }
 }
 
-inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1) {
+// tab_rows > 0: the small-batch kernels (kMode 1 / 2), which also hold the handed-over per-radar terms
+// (laid out for both modes) and a copy of the scenario columns
+inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1, int tab_rows = 0) {
   return (size_t)(workers * 2 * R + K) * bs * sizeof(double) + (((size_t)bs * stage_ld + 1) / 2) * sizeof(double) +
-         (workers > 1 ? (size_t)(3 * R + R * K) * bs * sizeof(double) : 0);
+         (tab_rows > 0 ? (size_t)(3 * R + R * K + tab_rows) * bs * sizeof(double) : 0);
 }
 
 inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
@@ -357,25 +384,32 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
 #ifndef MACJD_TEST_HOST_EMULATION
   // latency-bound regime: physics and views as concurrent chains (measured at 4 096 envs: 22.5 -> 18.4 us),
   // and the radar loop over two workers
-  a.split_views = physics && tab->n_envs <= 16384 && bs == 128 && smem <= 48 * 1024 && (io->state || io->obs || io->avail);
+  const int tab_rows = 16 * tab->n_radars + 8 * tab->n_jammers + 3 * tab->n_targets;
+  const size_t smem1 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 1, tab_rows);
+  const size_t smem2 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 2, tab_rows);
+  constexpr size_t kSmallBatchSmem = 110 * 1024;           // two blocks per SM: the grid then fits on the SMs an agent kernel leaves idle
+  a.split_views = physics && tab->n_envs <= 16384 && bs == 128 && smem1 <= kSmallBatchSmem && (io->state || io->obs || io->avail);
   if (a.split_views) {
-    const size_t smem2 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 2);
-    // allowed to start while the preceding kernel (the agent step) drains: launch latency, table loads and
-    // view staging overlap its tail; the kernel waits (grid_dependency_wait) before the first dependent access
+    // allowed to start while the preceding kernel (the agent step) drains: launch latency, table staging and
+    // view staging overlap it; the kernel waits (grid_dependency_wait) before the first dependent access
+    const bool two = tab->n_radars >= 2 && smem2 <= kSmallBatchSmem;
+    const size_t need = two ? smem2 : smem1;
+    static size_t opted[2][64] = {};
+    const int dev = ctx->device & 63;
+    if (need > 48 * 1024 && need > opted[two][dev]) {
+      const cudaError_t e = two ? cudaFuncSetAttribute(env_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)
+                                : cudaFuncSetAttribute(env_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+      if (e != cudaSuccess) return MACJD_ERR_CUDA;
+      opted[two][dev] = need;
+    }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     static const int no_pdl = getenv("MACJD_NO_PDL") ? atoi(getenv("MACJD_NO_PDL")) : 0;   // experiments
     attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
     cfg.gridDim = dim3(grid); cfg.stream = (cudaStream_t)ctx->stream; cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t err;
-    if (tab->n_radars >= 2 && smem2 <= 48 * 1024) {
-      cfg.blockDim = dim3(3 * bs); cfg.dynamicSmemBytes = smem2;
-      err = cudaLaunchKernelEx(&cfg, env_step_kernel<2>, a);
-    } else {
-      cfg.blockDim = dim3(2 * bs); cfg.dynamicSmemBytes = smem;
-      err = cudaLaunchKernelEx(&cfg, env_step_kernel<1>, a);
-    }
+    cfg.blockDim = dim3((two ? 3 : 2) * bs); cfg.dynamicSmemBytes = need;
+    const cudaError_t err = two ? cudaLaunchKernelEx(&cfg, env_step_kernel<2>, a) : cudaLaunchKernelEx(&cfg, env_step_kernel<1>, a);
     return err == cudaSuccess ? MACJD_OK : MACJD_ERR_CUDA;
   }
 #else
