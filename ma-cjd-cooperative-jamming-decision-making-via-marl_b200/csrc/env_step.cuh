@@ -60,7 +60,7 @@ __device__ __forceinline__ double albersheim(const macjd_env_tables& t, double s
 //          radars; set 0 adds the per-radar terms up in radar order (so every sum has the sequential
 //          kernel's order and value); set 2 writes the views.
 template <int kMode>
-__global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env_step_kernel(const EnvKernelArgs a) {
+__global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMode == 0 ? 5 : 2) env_step_kernel(const EnvKernelArgs a) {
   const macjd_env_tables& T = a.tab;
   const macjd_env_io& io = a.io;
   const int n = T.n_envs, J = T.n_jammers, R = T.n_radars, K = T.n_targets;
@@ -135,55 +135,82 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
   // writes outputs: wait for the preceding kernel of the stream (normally the agent step that chose
   // the actions) -- a no-op unless this launch was allowed to start early (env_launch).
   if (do_phys) grid_dependency_wait();
+  uint64_t supp_mask = 0, hit_mask = 0;
+  // One jammer (environment.py:248-302, core/jammer.py:73-98): its power-penalty term and what it does to
+  // its target radar -- code = (target << 2) | {0 nothing, 1 suppression: val = received power,
+  // 2 detected false target: val = 1 - min(pd_f, 0.999999)}.
+  auto jammer_eval = [&](int j, double& rp_term, int& code, double& val) {
+    const int jr = jbase + 8 * j;
+    const int Ti = io.act_d[(int64_t)e * J + j];
+    double P = (double)io.act_p[(int64_t)e * J + j];
+    P = P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
+    const double pmin = tab(jr + 6), pmax = tab(jr + 7);
+    const double range = pmax - pmin;
+    const double power = pmin + P * range;
+    const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
+    rp_term = T.rp_max + (T.rp_min - T.rp_max) * norm;   // charged even when idle
+    code = 0; val = 0.0;
+    if (io.jam_power) io.jam_power[(int64_t)j * n + e] = (float)power;
+    if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
+      const int tgt = (Ti + 1) / 2 - 1;
+      const int rr = rbase + 16 * tgt;
+      const double dx = tab(jr + 4) - tab(rr + 10);
+      const double dy = tab(jr + 5) - tab(rr + 11);
+      const double dist = sqrt(dx * dx + dy * dy);
+      if (dist > 1e-6) {
+        const double dsq = fmax(1e-9, dist * dist);
+        const double den = dsq * tab(jr + 1) * tab(jr + 2) * fmax(1e-9, tab(jr + 3));
+        double prj = 0.0;
+        if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * tab(jr + 0) * tab(rr + 2)) / den);
+        if (Ti & 1) {  // suppression
+          code = (tgt << 2) | 1; val = prj;
+        } else {       // deception: false target (environment.py:408-437)
+          const double pn = tab(rr + 6);
+          double snr_f = pn > 1e-18 ? (tab(rr + 8) * prj) / pn : 0.0;
+          snr_f = fmax(0.0, snr_f);
+          const double pd_f = albersheim(T, snr_f);
+          const float u = io.noise ? io.noise[(int64_t)e * (RK + J) + RK + j]
+                                   : philox_uniform(io.seed, kStreamEnvNoise, (uint32_t)e, (uint32_t)step, (uint32_t)(RK + j));
+          if ((double)u <= pd_f) { code = (tgt << 2) | 2; val = 1.0 - fmin(pd_f, 0.999999); }
+        }
+      }
+    }
+  };
+  // ... applied in jammer order (the sums and products of the sequential code, term for term)
+  auto jammer_apply = [&](double rp_term, int code, double val) {
+    r_p += rp_term;
+    const int tgt = code >> 2;
+    if ((code & 3) == 1) { prjs[tgt * BS + tid] += val; supp_mask |= (1ull << tgt); }
+    else if ((code & 3) == 2) { prod[tgt * BS + tid] *= val; hit_mask |= (1ull << tgt); }
+  };
+  double* jr_rp = tabs + (size_t)(kMode != 0 ? n_tab_rows : 0) * BS;     // kMode 2: [J][BS] records handed between the workers
+  double* jr_val = jr_rp + (size_t)J * BS;
+  int* jr_code = reinterpret_cast<int*>(jr_val + (size_t)J * BS);
   if (phys) {
     for (int r = 0; r < R; ++r) { prjs[r * BS + tid] = 0.0; prod[r * BS + tid] = 1.0; }
     if (wk == 0)
       for (int k = 0; k < K; ++k) pnet[k * BS + tid] = 1.0;
     step = io.step_count[e] + 1;  // environment.py:235
-    uint64_t supp_mask = 0, hit_mask = 0;
-
-    // ---- jammer loop (environment.py:248-302)
-    for (int j = 0; j < J; ++j) {
-      const int jr = jbase + 8 * j;
-      const int Ti = io.act_d[(int64_t)e * J + j];
-      double P = (double)io.act_p[(int64_t)e * J + j];
-      P = P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
-      const double pmin = tab(jr + 6), pmax = tab(jr + 7);
-      const double range = pmax - pmin;
-      const double power = pmin + P * range;
-      const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
-      r_p += T.rp_max + (T.rp_min - T.rp_max) * norm;   // charged even when idle
-      if (io.jam_power && wk == 0) io.jam_power[(int64_t)j * n + e] = (float)power;
-      if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
-        const int tgt = (Ti + 1) / 2 - 1;
-        const int rr = rbase + 16 * tgt;
-        const double dx = tab(jr + 4) - tab(rr + 10);
-        const double dy = tab(jr + 5) - tab(rr + 11);
-        const double dist = sqrt(dx * dx + dy * dy);
-        if (dist > 1e-6) {
-          // core/jammer.py:73-98
-          const double dsq = fmax(1e-9, dist * dist);
-          const double den = dsq * tab(jr + 1) * tab(jr + 2) * fmax(1e-9, tab(jr + 3));
-          double prj = 0.0;
-          if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * tab(jr + 0) * tab(rr + 2)) / den);
-          if (Ti & 1) {  // suppression
-            prjs[tgt * BS + tid] += prj;
-            supp_mask |= (1ull << tgt);
-          } else {       // deception: false target (environment.py:408-437)
-            const double pn = tab(rr + 6);
-            double snr_f = pn > 1e-18 ? (tab(rr + 8) * prj) / pn : 0.0;
-            snr_f = fmax(0.0, snr_f);
-            const double pd_f = albersheim(T, snr_f);
-            const float u = io.noise ? io.noise[(int64_t)e * (RK + J) + RK + j]
-                                     : philox_uniform(io.seed, kStreamEnvNoise, (uint32_t)e, (uint32_t)step, (uint32_t)(RK + j));
-            if ((double)u <= pd_f) {
-              prod[tgt * BS + tid] *= (1.0 - fmin(pd_f, 0.999999));
-              hit_mask |= (1ull << tgt);
-            }
-          }
-        }
+    if (kMode == 2) {               // each worker evaluates every other jammer
+      for (int j = wk; j < J; j += NW) {
+        double rp_term, val; int code;
+        jammer_eval(j, rp_term, code, val);
+        jr_rp[j * BS + tid] = rp_term; jr_val[j * BS + tid] = val; jr_code[j * BS + tid] = code;
+      }
+    } else {
+      for (int j = 0; j < J; ++j) {
+        double rp_term, val; int code;
+        jammer_eval(j, rp_term, code, val);
+        jammer_apply(rp_term, code, val);
       }
     }
+  }
+#ifndef MACJD_TEST_HOST_EMULATION
+  if (kMode == 2 && a.physics && do_phys) asm volatile("bar.sync 2, %0;\n" ::"r"(2 * BS) : "memory");   // jammer records complete
+#endif
+  if (phys) {
+    if (kMode == 2)
+      for (int j = 0; j < J; ++j) jammer_apply(jr_rp[j * BS + tid], jr_code[j * BS + tid], jr_val[j * BS + tid]);
 
     // ---- radar x target loop (environment.py:316-349, 359-366, 385-398)
     const double four_pi3 = (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793);
@@ -339,11 +366,13 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128) env
   }
 }
 
+constexpr int kMaxJammersRec = 16;   // jammer records of the two-worker kernel (more jammers: one-worker kernel)
 // tab_rows > 0: the small-batch kernels (kMode 1 / 2), which also hold the handed-over per-radar terms
 // (laid out for both modes) and a copy of the scenario columns
 inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1, int tab_rows = 0) {
   return (size_t)(workers * 2 * R + K) * bs * sizeof(double) + (((size_t)bs * stage_ld + 1) / 2) * sizeof(double) +
-         (tab_rows > 0 ? (size_t)(3 * R + R * K + tab_rows) * bs * sizeof(double) : 0);
+         (tab_rows > 0 ? (size_t)(3 * R + R * K + tab_rows) * bs * sizeof(double) : 0) +
+         (workers > 1 ? (size_t)3 * kMaxJammersRec * bs * sizeof(double) : 0);
 }
 
 inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
@@ -392,7 +421,7 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   if (a.split_views) {
     // allowed to start while the preceding kernel (the agent step) drains: launch latency, table staging and
     // view staging overlap it; the kernel waits (grid_dependency_wait) before the first dependent access
-    const bool two = tab->n_radars >= 2 && smem2 <= kSmallBatchSmem;
+    const bool two = tab->n_radars >= 2 && tab->n_jammers <= kMaxJammersRec && smem2 <= kSmallBatchSmem;
     const size_t need = two ? smem2 : smem1;
     static size_t opted[2][64] = {};
     const int dev = ctx->device & 63;
