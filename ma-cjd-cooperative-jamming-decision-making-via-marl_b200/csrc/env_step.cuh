@@ -52,6 +52,14 @@ __device__ __forceinline__ double albersheim(const macjd_env_tables& t, double s
   return 1.0 / (1.0 + exp(-b));
 }
 
+// Optional %globaltimer stamps of block 0 / thread 0 (-DMACJD_TC_PROFILE; tools/env_phase_profile.py)
+#if defined(MACJD_TC_PROFILE) && !defined(MACJD_TEST_HOST_EMULATION)
+__device__ unsigned long long g_env_prof[16];
+#define ENV_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_env_prof[k] = t_; } } while (0)
+#else
+#define ENV_STAMP(k) do { } while (0)
+#endif
+
 // kMode 0: one thread per env does everything.  Small batches are one long dependent FP64 chain per
 // thread (the time for 32 envs equals the time for 4 096), so they split it over concurrent warp sets:
 // kMode 1: the block has 2 BS threads -- set 0 runs the physics, set 1 writes the static views of the
@@ -134,7 +142,9 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
   // Everything above reads the scenario tables only.  From here on the kernel reads the actions and
   // writes outputs: wait for the preceding kernel of the stream (normally the agent step that chose
   // the actions) -- a no-op unless this launch was allowed to start early (env_launch).
+  ENV_STAMP(0);
   if (do_phys) grid_dependency_wait();
+  ENV_STAMP(1);
   uint64_t supp_mask = 0, hit_mask = 0;
   // One jammer (environment.py:248-302, core/jammer.py:73-98): its power-penalty term and what it does to
   // its target radar -- code = (target << 2) | {0 nothing, 1 suppression: val = received power,
@@ -191,6 +201,8 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
     if (wk == 0)
       for (int k = 0; k < K; ++k) pnet[k * BS + tid] = 1.0;
     step = io.step_count[e] + 1;  // environment.py:235
+    if (step == -12345) prjs[tid] = 1.0;   // (keeps the load ahead of the stamp)
+    ENV_STAMP(2);
     if (kMode == 2) {               // each worker evaluates every other jammer
       for (int j = wk; j < J; j += NW) {
         double rp_term, val; int code;
@@ -212,6 +224,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
     if (kMode == 2)
       for (int j = 0; j < J; ++j) jammer_apply(jr_rp[j * BS + tid], jr_code[j * BS + tid], jr_val[j * BS + tid]);
 
+    ENV_STAMP(3);
     // ---- radar x target loop (environment.py:316-349, 359-366, 385-398)
     const double four_pi3 = (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793);
     for (int r = wk; r < R; r += NW) {
@@ -269,8 +282,10 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
     }
   }
 #ifndef MACJD_TEST_HOST_EMULATION
+  ENV_STAMP(4);
   if (kMode == 2 && a.physics && do_phys) asm volatile("bar.sync 2, %0;\n" ::"r"(2 * BS) : "memory");   // both physics sets
 #endif
+  ENV_STAMP(5);
   if (phys && wk == 0) {
     if (kMode == 2) {
       // the sequential kernel's sums, in its order (a term that kernel skips is an exact + 0.0 here)
@@ -294,6 +309,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
     if (io.r_j) io.r_j[e] = (float)r_j;
     if (io.terminated) io.terminated[e] = term ? 1 : 0;
     io.step_count[e] = (term && io.auto_reset) ? 0 : step;
+    ENV_STAMP(6);
   } else if (live && !a.physics && do_phys) {
     io.step_count[e] = 0;                                  // environment.py:203
   }

@@ -383,6 +383,13 @@ __attribute__((visibility("default"))) int macjd_debug_tc_profile(unsigned long 
 #endif
 }
 
+#if defined(MACJD_TC_PROFILE) && !defined(MACJD_TEST_HOST_EMULATION)
+// Debug aid: the env kernel's phase stamps (tools/env_phase_profile.py)
+__attribute__((visibility("default"))) int macjd_debug_env_profile(unsigned long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, macjd::g_env_prof, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -3;
+}
+#endif
+
 // Debug aid: tcgen05.mma issue / completion rate (cycles) for n back-to-back M x N x 8 TF32 MMAs.
 __attribute__((visibility("default"))) int macjd_debug_tc_mma_rate(const macjd_ctx* ctx, int M, int N, int n,
                                                                   unsigned long long* out_dev) {
