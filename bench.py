@@ -295,10 +295,12 @@ def main():
     aio.epsilon, aio.rng_step, aio.test_mode = 0.3, 1, 0
     aio_simt = type(aio).from_buffer_copy(aio)
     aio_simt.path = 1
+    eio_alone = type(eio).from_buffer_copy(eio)
+    eio_alone.flags = 0                          # timed on its own: not behind an agent kernel (include/macjd.h)
     wts = mac.agent.packed().cstruct()
     kn = 30
     dt_agent = timed_steps(lambda i: lib.call("macjd_agent_forward", ctx, wts, aio), kn) / kn
-    dt_env = timed_steps(lambda i: lib.call("macjd_env_step", ctx, env._ctab, eio), kn) / kn
+    dt_env = timed_steps(lambda i: lib.call("macjd_env_step", ctx, env._ctab, eio_alone), kn) / kn
     clocks = None
     peaks = {}
     try:

@@ -84,6 +84,13 @@ typedef struct macjd_env_tables {
   double alb_den;           /* 1.7 + 0.12 A                        (core/radar.py:74)   */
 } macjd_env_tables;
 
+/* macjd_env_io.flags.  MACJD_ENV_FOLLOWS_AGENT: the caller launches this step directly behind the kernel
+ * that produces its actions (same stream, normally macjd_agent_forward).  The step kernel is scheduled
+ * early in any case (programmatic dependent launch); with the flag it uses the time it waits for the
+ * agent kernel to copy the scenario columns into shared memory.  Results are identical; launched on its
+ * own the copy would only add latency, so leave the flag unset then. */
+#define MACJD_ENV_FOLLOWS_AGENT 1
+
 typedef struct macjd_env_io {
   /* inputs of step() -- environment.py:221 `actions` as two arrays */
   const int32_t* act_d;     /* [n_envs][J] discrete T_i                              */
@@ -91,7 +98,7 @@ typedef struct macjd_env_io {
   const float* noise;       /* [n_envs][R*K + J] injected uniforms, or NULL -> Philox */
   uint64_t seed;            /* Philox key when noise == NULL                          */
   int32_t auto_reset;       /* != 0: step_count <- 0 after a terminated step (opt-in) */
-  int32_t reserved;
+  int32_t flags;            /* MACJD_ENV_FOLLOWS_AGENT or 0                             */
   /* per-episode state */
   int32_t* step_count;      /* [n_envs] in/out                   (environment.py:235) */
   /* outputs of step() */

@@ -30,7 +30,7 @@ class EnvTables(C.Structure):
 
 class EnvIO(C.Structure):
     _fields_ = [("act_d", c_void_p), ("act_p", c_void_p), ("noise", c_void_p), ("seed", c_uint64),
-                ("auto_reset", c_int32), ("reserved", c_int32),
+                ("auto_reset", c_int32), ("flags", c_int32),
                 ("step_count", c_void_p),
                 ("reward", c_void_p), ("r_d", c_void_p), ("r_p", c_void_p), ("r_j", c_void_p),
                 ("reward64", c_void_p), ("terminated", c_void_p),
@@ -58,6 +58,7 @@ class AgentIO(C.Structure):
 
 
 HOST_PINNED = 1       # include/macjd.h: MACJD_HOST_PINNED
+ENV_FOLLOWS_AGENT = 1 # include/macjd.h: MACJD_ENV_FOLLOWS_AGENT
 
 
 class ActHost(C.Structure):

@@ -30,6 +30,8 @@ struct EnvKernelArgs {
   int stage_ld;       // padded row length of the smem state stage (odd -> no bank conflicts)
   int physics;        // 0: reset (views only, step_count <- 0), 1: full step
   int prefetch;       // issue L2 prefetches for the env's table column first (small batches)
+  int stage_tab;      // small batches, launched right behind the kernel that produces the actions (io.flags):
+                      // copy the scenario column to shared memory while waiting for it
   int split_views;    // small batches: a second set of warps writes the static views while the first runs
                       // the physics (the block is launched with 2 x the env count; one dependent chain
                       // instead of two in sequence)
@@ -118,7 +120,8 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
   // env take alternate rows and meet at a named barrier.
   const int n_tab_rows = 16 * R + 8 * J + 3 * K;
   double* tabs = pdv + (size_t)RK * BS;                  // [n_tab_rows][BS], kMode 1 / 2 only
-  if (kMode != 0 && a.physics && do_phys) {
+  const bool staged = kMode != 0 && a.stage_tab;
+  if (staged && a.physics && do_phys) {
     if (live) {
 #pragma unroll 1
       for (int row0 = wk * 16; row0 < n_tab_rows; row0 += 16 * NW) {
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
     asm volatile("bar.sync 2, %0;\n" ::"r"(NW * BS) : "memory");
 #endif
   }
-  auto tab = [&](int row) -> double { return kMode != 0 ? tabs[row * BS + tid] : env_tab(col, rs, row); };
+  auto tab = [&](int row) -> double { return staged ? tabs[row * BS + tid] : env_tab(col, rs, row); };
 
   const bool phys = live && a.physics && do_phys;
   int step = 0;
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
     if ((code & 3) == 1) { prjs[tgt * BS + tid] += val; supp_mask |= (1ull << tgt); }
     else if ((code & 3) == 2) { prod[tgt * BS + tid] *= val; hit_mask |= (1ull << tgt); }
   };
-  double* jr_rp = tabs + (size_t)(kMode != 0 ? n_tab_rows : 0) * BS;     // kMode 2: [J][BS] records handed between the workers
+  double* jr_rp = tabs + (size_t)(staged ? n_tab_rows : 0) * BS;     // kMode 2: [J][BS] records handed between the workers
   double* jr_val = jr_rp + (size_t)J * BS;
   int* jr_code = reinterpret_cast<int*>(jr_val + (size_t)J * BS);
   if (phys) {
@@ -383,11 +386,11 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
 }
 
 constexpr int kMaxJammersRec = 16;   // jammer records of the two-worker kernel (more jammers: one-worker kernel)
-// tab_rows > 0: the small-batch kernels (kMode 1 / 2), which also hold the handed-over per-radar terms
-// (laid out for both modes) and a copy of the scenario columns
-inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1, int tab_rows = 0) {
+// tab_rows >= 0: the small-batch kernels (kMode 1 / 2), which also hold the handed-over per-radar terms
+// (laid out for both modes) and, when launched behind the agent step, a copy of the scenario columns
+inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1, int tab_rows = -1) {
   return (size_t)(workers * 2 * R + K) * bs * sizeof(double) + (((size_t)bs * stage_ld + 1) / 2) * sizeof(double) +
-         (tab_rows > 0 ? (size_t)(3 * R + R * K + tab_rows) * bs * sizeof(double) : 0) +
+         (tab_rows >= 0 ? (size_t)(3 * R + R * K + tab_rows) * bs * sizeof(double) : 0) +
          (workers > 1 ? (size_t)3 * kMaxJammersRec * bs * sizeof(double) : 0);
 }
 
@@ -429,7 +432,10 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
 #ifndef MACJD_TEST_HOST_EMULATION
   // latency-bound regime: physics and views as concurrent chains (measured at 4 096 envs: 22.5 -> 18.4 us),
   // and the radar loop over two workers
-  const int tab_rows = 16 * tab->n_radars + 8 * tab->n_jammers + 3 * tab->n_targets;
+  // MACJD_ENV_FOLLOWS_AGENT: the caller launches this step right behind the kernel that writes its actions;
+  // only then is there a wait to fill with the table staging (alone, the staging is 6 us of extra latency)
+  a.stage_tab = (io->flags & MACJD_ENV_FOLLOWS_AGENT) ? 1 : 0;
+  const int tab_rows = a.stage_tab ? 16 * tab->n_radars + 8 * tab->n_jammers + 3 * tab->n_targets : 0;
   const size_t smem1 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 1, tab_rows);
   const size_t smem2 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 2, tab_rows);
   constexpr size_t kSmallBatchSmem = 110 * 1024;           // two blocks per SM: the grid then fits on the SMs an agent kernel leaves idle

@@ -184,6 +184,7 @@ class BatchedEpisodeRunner:
                 "reward": tr["reward"][t], "terminated": tr["terminated"][t], "r_d": self.r_parts[0, t],
                 "r_p": self.r_parts[1, t], "r_j": self.r_parts[2, t], "state": tr["state"][t + 1],
                 "obs": tr["obs"][t + 1], "avail": tr["avail_actions"][t + 1]}))
+            self._env_io[-1].flags = N.ENV_FOLLOWS_AGENT      # step() launches it right behind the agent kernel
         self._structs_for = (mac.hidden_states.data_ptr(), mac.agent.path)
 
     def step(self, t, test_mode=False, noise=None, u_eps=None, rand_actions=None):

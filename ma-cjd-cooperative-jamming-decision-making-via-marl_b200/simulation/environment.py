@@ -124,7 +124,7 @@ class ElectromagneticEnvironment:
         p = N.ptr
         io = N.EnvIO(
             act_d=p(act_d), act_p=p(act_p), noise=p(noise), seed=self.seed,
-            auto_reset=int(self.auto_reset), reserved=0, step_count=p(self.step_count),
+            auto_reset=int(self.auto_reset), flags=0, step_count=p(self.step_count),
             reward=p(self.reward), r_d=p(self.r_d), r_p=p(self.r_p), r_j=p(self.r_j),
             reward64=p(self.reward64), terminated=p(self.terminated),
             pd=p(self.pd), detected=p(self.detected), tracking=p(self.tracking),
