@@ -69,7 +69,9 @@ __device__ unsigned long long g_env_prof[16];
 // kMode 2: 3 BS threads -- sets 0 and 1 both run the (short) jammer loop, then take the even / odd
 //          radars; set 0 adds the per-radar terms up in radar order (so every sum has the sequential
 //          kernel's order and value); set 2 writes the views.
-template <int kMode>
+// kStaged (kMode 1 / 2 only): the launch follows the agent step; the scenario column is copied to shared
+// memory ahead of the dependency wait (compile-time, so that the physics carries no second lookup path).
+template <int kMode, bool kStaged = false>
 __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMode == 0 ? 5 : 2) env_step_kernel(const EnvKernelArgs a) {
   const macjd_env_tables& T = a.tab;
   const macjd_env_io& io = a.io;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
   // env take alternate rows and meet at a named barrier.
   const int n_tab_rows = 16 * R + 8 * J + 3 * K;
   double* tabs = pdv + (size_t)RK * BS;                  // [n_tab_rows][BS], kMode 1 / 2 only
-  const bool staged = kMode != 0 && a.stage_tab;
+  constexpr bool staged = kMode != 0 && kStaged;
   if (staged && a.physics && do_phys) {
     if (live) {
 #pragma unroll 1
@@ -425,7 +427,7 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   const size_t smem = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs);
   if (smem > 200 * 1024) return MACJD_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(env_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(env_step_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return MACJD_ERR_CUDA;
   }
   const int grid = (tab->n_envs + bs - 1) / bs;
@@ -445,13 +447,14 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
     // view staging overlap it; the kernel waits (grid_dependency_wait) before the first dependent access
     const bool two = tab->n_radars >= 2 && tab->n_jammers <= kMaxJammersRec && smem2 <= kSmallBatchSmem;
     const size_t need = two ? smem2 : smem1;
-    static size_t opted[2][64] = {};
-    const int dev = ctx->device & 63;
-    if (need > 48 * 1024 && need > opted[two][dev]) {
-      const cudaError_t e = two ? cudaFuncSetAttribute(env_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)
-                                : cudaFuncSetAttribute(env_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    static size_t opted[4][64] = {};
+    const int dev = ctx->device & 63, which = (two ? 2 : 0) + (a.stage_tab ? 1 : 0);
+    if (need > 48 * 1024 && need > opted[which][dev]) {
+      const void* fn = two ? (a.stage_tab ? (const void*)env_step_kernel<2, true> : (const void*)env_step_kernel<2, false>)
+                           : (a.stage_tab ? (const void*)env_step_kernel<1, true> : (const void*)env_step_kernel<1, false>);
+      const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
       if (e != cudaSuccess) return MACJD_ERR_CUDA;
-      opted[two][dev] = need;
+      opted[which][dev] = need;
     }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -460,13 +463,14 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
     attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
     cfg.gridDim = dim3(grid); cfg.stream = (cudaStream_t)ctx->stream; cfg.attrs = attr; cfg.numAttrs = 1;
     cfg.blockDim = dim3((two ? 3 : 2) * bs); cfg.dynamicSmemBytes = need;
-    const cudaError_t err = two ? cudaLaunchKernelEx(&cfg, env_step_kernel<2>, a) : cudaLaunchKernelEx(&cfg, env_step_kernel<1>, a);
+    const cudaError_t err = two ? (a.stage_tab ? cudaLaunchKernelEx(&cfg, env_step_kernel<2, true>, a) : cudaLaunchKernelEx(&cfg, env_step_kernel<2, false>, a))
+                                : (a.stage_tab ? cudaLaunchKernelEx(&cfg, env_step_kernel<1, true>, a) : cudaLaunchKernelEx(&cfg, env_step_kernel<1, false>, a));
     return err == cudaSuccess ? MACJD_OK : MACJD_ERR_CUDA;
   }
 #else
   a.split_views = 0;
 #endif
-  MACJD_LAUNCH(env_step_kernel<0>, grid, bs, smem, (cudaStream_t)ctx->stream, a);
+  MACJD_LAUNCH((env_step_kernel<0, false>), grid, bs, smem, (cudaStream_t)ctx->stream, a);
   return MACJD_OK;
 }
 
