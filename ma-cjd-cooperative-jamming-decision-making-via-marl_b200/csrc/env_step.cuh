@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
     if (wk == 0)
       for (int k = 0; k < K; ++k) pnet[k * BS + tid] = 1.0;
     step = io.step_count[e] + 1;  // environment.py:235
+#if defined(MACJD_TC_PROFILE) && !defined(MACJD_TEST_HOST_EMULATION)
     if (step == -12345) prjs[tid] = 1.0;   // (keeps the load ahead of the stamp)
+#endif
     ENV_STAMP(2);
     if (kMode == 2) {               // each worker evaluates every other jammer
       for (int j = wk; j < J; j += NW) {
