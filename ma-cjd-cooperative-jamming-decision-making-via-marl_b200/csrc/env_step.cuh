@@ -389,13 +389,12 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
   }
 }
 
-constexpr int kMaxJammersRec = 16;   // jammer records of the two-worker kernel (more jammers: one-worker kernel)
 // tab_rows >= 0: the small-batch kernels (kMode 1 / 2), which also hold the handed-over per-radar terms
 // (laid out for both modes) and, when launched behind the agent step, a copy of the scenario columns
-inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1, int tab_rows = -1) {
+inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1, int tab_rows = -1, int n_jammers = 0) {
   return (size_t)(workers * 2 * R + K) * bs * sizeof(double) + (((size_t)bs * stage_ld + 1) / 2) * sizeof(double) +
          (tab_rows >= 0 ? (size_t)(3 * R + R * K + tab_rows) * bs * sizeof(double) : 0) +
-         (workers > 1 ? (size_t)3 * kMaxJammersRec * bs * sizeof(double) : 0);
+         (workers > 1 ? (size_t)3 * n_jammers * bs * sizeof(double) : 0);     // jammer records handed between the workers
 }
 
 inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
@@ -441,13 +440,15 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   a.stage_tab = (io->flags & MACJD_ENV_FOLLOWS_AGENT) ? 1 : 0;
   const int tab_rows = a.stage_tab ? 16 * tab->n_radars + 8 * tab->n_jammers + 3 * tab->n_targets : 0;
   const size_t smem1 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 1, tab_rows);
-  const size_t smem2 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 2, tab_rows);
+  const size_t smem2 = env_smem_bytes(tab->n_radars, tab->n_targets, a.stage_ld, bs, 2, tab_rows, tab->n_jammers);
   constexpr size_t kSmallBatchSmem = 110 * 1024;           // two blocks per SM: the grid then fits on the SMs an agent kernel leaves idle
   a.split_views = physics && tab->n_envs <= 16384 && bs == 128 && smem1 <= kSmallBatchSmem && (io->state || io->obs || io->avail);
   if (a.split_views) {
     // allowed to start while the preceding kernel (the agent step) drains: launch latency, table staging and
     // view staging overlap it; the kernel waits (grid_dependency_wait) before the first dependent access
-    const bool two = tab->n_radars >= 2 && tab->n_jammers <= kMaxJammersRec && smem2 <= kSmallBatchSmem;
+    // two physics workers pay off when the lookups go to L2 (a launch on its own: 16.4 -> 15.0 us); with the
+    // columns staged in shared memory one worker is faster (48.0 vs 48.6 us per flushed step: no hand-over barriers)
+    const bool two = !a.stage_tab && tab->n_radars >= 2 && smem2 <= kSmallBatchSmem;
     const size_t need = two ? smem2 : smem1;
     static size_t opted[4][64] = {};
     const int dev = ctx->device & 63, which = (two ? 2 : 0) + (a.stage_tab ? 1 : 0);
