@@ -172,7 +172,8 @@ typedef struct macjd_agent_weights {
   int32_t hidden;         /* H  = rnn_hidden_dim,   multiple of 64, <= 256             */
   int32_t actor_hidden;   /* AH = actor_hidden_dim, multiple of 64, <= 256             */
   int32_t n_actions;      /* A <= 64                                                   */
-  int32_t reserved;
+  int32_t tc_format;      /* layout of tc_chunks: 0 = weight chunks only (path 2), 1 = weight
+                             chunks followed by the per-layer constant block (needed by path 3) */
   const float* wa1t;      /* [obs_pad][AH]  actor.0.weight^T                           */
   const float* ba1;       /* [AH]                                                      */
   const float* wa2t;      /* [AH][AH]       actor.2.weight^T                           */
@@ -197,7 +198,10 @@ typedef struct macjd_agent_weights {
   const float* tc_chunks; /* optional: the dense layers again, packed for the tcgen05 path
                              (csrc/agent_act_tc.cuh): 128 x 16 weight chunks in consumption order,
                              UMMA K-major layout, TF32 hi part then lo part (16 KB per chunk);
-                             NULL = FP32 SIMT kernel only                              */
+                             with tc_format 1 the 13 856-byte constant block (biases, actor
+                             output layer, Q-head vectors; csrc/agent_act_tc.cuh: TcConst) follows
+                             the last chunk so that the CTA-pair kernel fetches it with one bulk
+                             copy; NULL = FP32 SIMT kernel only                        */
 } macjd_agent_weights;
 
 typedef struct macjd_agent_io {

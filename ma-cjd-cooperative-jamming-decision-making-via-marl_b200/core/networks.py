@@ -51,6 +51,7 @@ class PackedAgentWeights:
         # tensor-core copy (csrc/agent_act_tc.cuh): reference width only
         self.tc_ok = (self.H == 128 and self.AH == 128)
         self.tc_buffer = None
+        self.tc_flat = None
         self._cstruct = None
         self._cstruct_for = None
 
@@ -58,8 +59,8 @@ class PackedAgentWeights:
         # target networks deep-copy the agent: the copy re-packs from its own parameters
         new = PackedAgentWeights.__new__(PackedAgentWeights)
         new.__dict__.update({k: v for k, v in self.__dict__.items()
-                             if k not in ("buffer", "tc_buffer", "versions", "_cstruct", "_cstruct_for", "_slots")})
-        new.buffer = new.tc_buffer = new.versions = new._cstruct = new._cstruct_for = None
+                             if k not in ("buffer", "tc_buffer", "tc_flat", "versions", "_cstruct", "_cstruct_for", "_slots")})
+        new.buffer = new.tc_buffer = new.tc_flat = new.versions = new._cstruct = new._cstruct_for = None
         return new
 
     def view(self, f):
@@ -151,6 +152,7 @@ class PackedAgentWeights:
             hi = (full.view(torch.int32) & -8192).view(torch.float32)
             self.tc_buffer[-full.shape[0]:, 0].copy_(hi)
             self.tc_buffer[-full.shape[0]:, 1].copy_(full - hi)
+            self._pack_tc_const(qhead_only=True)
         slots = self.__dict__.get("_slots")
         if slots is not None:
             self.versions = tuple([(m._parameters[k]._version, m._parameters[k].data_ptr()) for m, k in slots])
@@ -188,10 +190,33 @@ class PackedAgentWeights:
         hi = (full.view(torch.int32) & -8192).view(torch.float32)
         lo = full - hi
         new = torch.stack([hi, lo], dim=1)                            # [n_chunks, 2, 128 * kc]
-        if self.tc_buffer is not None and self.tc_buffer.shape == new.shape and self.tc_buffer.device == new.device:
-            self.tc_buffer.copy_(new)                                 # same address: captured launches stay valid
-        else:
-            self.tc_buffer = new.contiguous()
+        n = new.numel()
+        if self.tc_flat is None or self.tc_flat.numel() != n + self.TC_CONST_FLOATS or self.tc_flat.device != new.device:
+            self.tc_flat = torch.zeros(n + self.TC_CONST_FLOATS, dtype=torch.float32, device=new.device)
+        self.tc_buffer = self.tc_flat[:n].view(new.shape)             # same address on every re-pack: captured launches stay valid
+        self.tc_buffer.copy_(new)
+        self._pack_tc_const()
+
+    # Per-layer vectors in the layout of csrc/agent_act_tc.cuh: TcConst, appended to the chunk buffer; the
+    # CTA-pair kernel fetches the block with one bulk copy instead of ~26 scalar loads per thread.
+    TC_CONST_FLOATS = 4 * 128 + 4 * 128 + 3 * 128 + 8 * 128 + 8 * 128 + 8
+
+    def _pack_tc_const(self, qhead_only=False):
+        H, A = self.H, self.A
+        if A > 8:                      # the tensor-core kernels take at most 8 actions (csrc: agent_tc_supported)
+            return
+        c = self.tc_flat[-self.TC_CONST_FLOATS:]
+        gate_b, q_c = c[:512].view(128, 4), c[512:1024].view(128, 4)
+        w3, w1a = c[1408:2432].view(128, 8), c[2432:3456].view(128, 8)
+        q_c[:, 0].copy_(self.view("bq1")); q_c[:, 1].copy_(self.view("w1p")); q_c[:, 2].copy_(self.view("w2"))
+        w1a[:, :A].copy_(self.view("w1a").t())                        # [unit][action] = fc2_q_head.0.weight[unit, H + action]
+        if qhead_only:
+            return
+        brz = self.view("brz")
+        gate_b[:, 0].copy_(brz[:H]); gate_b[:, 1].copy_(brz[H:]); gate_b[:, 2].copy_(self.view("bin")); gate_b[:, 3].copy_(self.view("bhn"))
+        c[1024:1152].copy_(self.view("ba1")); c[1152:1280].copy_(self.view("ba2")); c[1280:1408].copy_(self.view("bfc1"))
+        w3[:, :A].copy_(self.view("wa3t"))                            # [unit][action] = actor.4.weight^T
+        c[3456:3456 + A].copy_(self.view("ba3"))
 
     def cstruct(self):
         if self._cstruct is not None and self._cstruct_for == (self.buffer.data_ptr(), id(self.tc_buffer)):
@@ -205,7 +230,7 @@ class PackedAgentWeights:
         kw = {f: base + 4 * self.offsets[f] for f in self.FIELDS}
         tc = self.tc_buffer.data_ptr() if self.tc_buffer is not None else None
         return N.AgentWeights(obs_dim=self.O, obs_pad=self.Op, hidden=self.H, actor_hidden=self.AH,
-                              n_actions=self.A, reserved=0, tc_chunks=tc, **kw)
+                              n_actions=self.A, tc_format=1 if (tc and self.A <= 8) else 0, tc_chunks=tc, **kw)
 
 
 class RNNAgent(nn.Module):

@@ -34,6 +34,7 @@ for k in range(32, 40):
 
 
 print("CTA 0 kernel entry .. exit (cycles rel. step start):", [v[k] - t0 for k in range(20, 26)])
+print("prologue (rel. entry): loads issued", v[26] - v[20], "weights prefetched", v[27] - v[20], "barriers initialised", v[28] - v[20], "constants staged", v[21] - v[20], "cluster barrier", v[22] - v[20], "step start", t0 - v[20])
 n_cta = min(512, (M + 63) // 64)
 ent = [v[64 + 2 * b] for b in range(n_cta)]
 ext = [v[65 + 2 * b] for b in range(n_cta)]
