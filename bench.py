@@ -355,31 +355,57 @@ def main():
     mac.init_hidden(n_envs)
     t_env = [0]
 
-    def host_step():
+    def host_step_two_calls():
         # H2D obs + avail, fused agent step, D2H actions + power (written straight into the env's action buffers)
         mac.select_actions_host(hb["obs"], avail_h, t_env[0], actions_out=hb["act_d"], power_out=hb["act_p"])
         # H2D actions + power, fused env step, D2H reward + terminated + next obs
         env.step_host(hb)
-        t_env[0] += 1
-        if t_env[0] % T == 0:
-            env.reset()
-            hb["obs"].copy_(env.get_obs())
-            mac.init_hidden(n_envs)
 
-    for _ in range(W):
-        host_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        host_step()
-    torch.cuda.synchronize()
-    dt_e2e = reduce_max(time.perf_counter() - t0)
-    h2d = hb["obs"].numel() * 4 + avail_h.numel() + hb["act_d"].numel() * 4 + hb["act_p"].numel() * 4
-    d2h = hb["act_d"].numel() * 4 + hb["act_p"].numel() * 4 + hb["obs"].numel() * 4 + hb["reward"].numel() * 4 + hb["terminated"].numel()
-    e2e = {"value": world * M * K / dt_e2e, "unit": "env-agent steps/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": dt_e2e / K * 1e3,
-           "api": "BasicMAC.select_actions_host + ElectromagneticEnvironment.step_host (C-ABI macjd_agent_act_host + "
-                  "macjd_env_step_host): pinned host buffers in and out, two stream drains per step"}
+    def host_step_fused():
+        # the same iteration as ONE call and one stream drain (BatchedEpisodeRunner.step_host ->
+        # macjd_rollout_step_host): H2D obs + avail, agent step, env step on the device-resident actions,
+        # D2H actions + power + reward + terminated + next obs
+        runner.t_env = t_env[0]
+        runner.step_host(hb["obs"], avail_h, hb)
+
+    def time_host(step_fn):
+        env.reset()
+        hb["obs"].copy_(env.get_obs())
+        mac.init_hidden(n_envs)
+        t_env[0] = 0
+
+        def one():
+            step_fn()
+            t_env[0] += 1
+            if t_env[0] % T == 0:
+                env.reset()
+                hb["obs"].copy_(env.get_obs())
+                mac.init_hidden(n_envs)
+        for _ in range(W):
+            one()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            one()
+        torch.cuda.synchronize()
+        return reduce_max(time.perf_counter() - t0)
+
+    t_env_saved = runner.t_env
+    dt_two = time_host(host_step_two_calls)
+    dt_e2e = time_host(host_step_fused)
+    runner.t_env = t_env_saved
+    obs_b, act_b = hb["obs"].numel() * 4, hb["act_d"].numel() * 4 + hb["act_p"].numel() * 4
+    out_b = hb["reward"].numel() * 4 + hb["terminated"].numel()
+    e2e = {"value": world * M * K / dt_e2e, "unit": "env-agent steps/s", "h2d_bytes_per_step": int(obs_b + avail_h.numel()),
+           "d2h_bytes_per_step": int(act_b + obs_b + out_b), "ms_per_step": dt_e2e / K * 1e3,
+           "api": "BatchedEpisodeRunner.step_host (C-ABI macjd_rollout_step_host): pinned host observations / masks in; "
+                  "actions, power, reward, terminated and next observations out to pinned host buffers; one stream "
+                  "drain per step",
+           "two_calls": {"value": world * M * K / dt_two, "ms_per_step": dt_two / K * 1e3,
+                         "h2d_bytes_per_step": int(obs_b + avail_h.numel() + act_b), "d2h_bytes_per_step": int(act_b + obs_b + out_b),
+                         "api": "BasicMAC.select_actions_host + ElectromagneticEnvironment.step_host (macjd_agent_act_host + "
+                                "macjd_env_step_host): the reference's two calls, two stream drains per step"}}
 
     # ---- learner: sample + train (B=32 episodes x T=100), all-reduce of the gradient bucket when N > 1
     np.random.seed(1 + rank)

@@ -120,6 +120,8 @@ typedef struct macjd_env_io {
   float* state;             /* [n_envs][S]                       (environment.py:479) */
   float* obs;               /* [n_envs][J][S]                    (environment.py:512) */
   uint8_t* avail;           /* [n_envs][J][A] all ones           (environment.py:539) */
+  int32_t env_begin;        /* step only envs [env_begin, env_begin + env_count): every pointer above still */
+  int32_t env_count;        /* names the whole batch (0, 0 = all; groups of one batch on separate streams)  */
 } macjd_env_io;
 
 /* environment.py:221-477  step(actions) for all envs. */
@@ -248,11 +250,16 @@ typedef struct macjd_agent_io {
                                      differ by FP32 rounding (x and h products are summed in the
                                      epilogue instead of in the accumulator).
                                  Other kernels return MACJD_ERR_UNSUPPORTED for part != 0.   */
-  int32_t reserved2;
+  int32_t rng_row_offset;     /* added to the row index in the Philox counters: a launch over rows
+                                 [k, k + n_rows) of a larger batch (pointers offset by the caller) draws
+                                 what the whole-batch launch draws for those rows                    */
   float* gate_x;              /* [T][M][3][H] part 3 output / part 4 input, else unused  */
   const float* epsilon_dev;   /* optional DEVICE scalars that override `epsilon` / `rng_step`: kernel      */
   const uint32_t* rng_step_dev; /* parameters are frozen when a launch is replayed from a CUDA graph, these
                                  are not (BatchedEpisodeRunner replays a whole episode as one graph) */
+  int32_t* actions_mirror;    /* [T][M] optional second destinations of actions / power (same values):   */
+  float* power_mirror;        /* the host-step call points them at the caller's page-locked buffers while
+                                 the primary copies stay in HBM for the env kernel                       */
 } macjd_agent_io;
 
 /* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);
@@ -279,6 +286,20 @@ typedef struct macjd_act_host {
 } macjd_act_host;
 MACJD_API int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io,
                                    const macjd_act_host* host);
+
+/* One iteration of the reference's rollout loop for a host-side caller
+ * (runners/episode_runner.py:119-165: mac.select_actions(obs, avail) followed by env.step(actions)) as ONE
+ * call with ONE stream drain: host observations / masks in, the fused agent step, the fused env step on
+ * the actions just chosen (they never leave the device: the env kernel reads aio->actions / aio->power,
+ * eio->act_d / act_p and ehost->act_d / act_p are ignored and may be NULL), then the chosen actions
+ * (ahost->actions / power) and the env outputs (ehost->reward / terminated / obs / state) back to the
+ * host.  The env kernel is launched as a programmatic dependent of the agent kernel.  Requirements and
+ * buffer rules are those of macjd_agent_act_host and macjd_env_step_host, plus
+ * aio->n_rows == n_envs * n_jammers (rows ordered env-major, as BasicMAC flattens them).
+ * Results are bit-identical to the two calls made one after the other. */
+MACJD_API int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
+                                      const macjd_act_host* ahost, const macjd_env_tables* tab,
+                                      const macjd_env_io* eio, const macjd_env_host* ehost);
 
 /* ===================================================================== replay ring
  * Replaces the data movement of utils/replay_buffer.py:78-214 (store_episode / sample) and

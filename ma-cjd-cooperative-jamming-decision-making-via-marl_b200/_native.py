@@ -37,7 +37,7 @@ class EnvIO(C.Structure):
                 ("pd", c_void_p), ("detected", c_void_p), ("tracking", c_void_p),
                 ("snr0", c_void_p), ("snr1", c_void_p), ("jsr_db", c_void_p), ("pd_net", c_void_p),
                 ("jam_power", c_void_p),
-                ("state", c_void_p), ("obs", c_void_p), ("avail", c_void_p)]
+                ("state", c_void_p), ("obs", c_void_p), ("avail", c_void_p), ("env_begin", c_int32), ("env_count", c_int32)]
 
 
 class AgentWeights(C.Structure):
@@ -53,8 +53,9 @@ class AgentIO(C.Structure):
                 ("hidden_seq", c_void_p), ("q_all", c_void_p), ("params_all", c_void_p), ("greedy", c_void_p),
                 ("sel_actions", c_void_p), ("q_sel", c_void_p), ("avail", c_void_p), ("u_eps", c_void_p),
                 ("rand_actions", c_void_p), ("epsilon", c_float), ("rng_step", C.c_uint32), ("seed", c_uint64),
-                ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p), ("part", c_int32), ("reserved2", c_int32),
-                ("gate_x", c_void_p), ("epsilon_dev", c_void_p), ("rng_step_dev", c_void_p)]
+                ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p), ("part", c_int32), ("rng_row_offset", c_int32),
+                ("gate_x", c_void_p), ("epsilon_dev", c_void_p), ("rng_step_dev", c_void_p),
+                ("actions_mirror", c_void_p), ("power_mirror", c_void_p)]
 
 
 HOST_PINNED = 1       # include/macjd.h: MACJD_HOST_PINNED
@@ -176,6 +177,7 @@ class NativeLib:
         "macjd_agent_forward": (Ctx, AgentWeights, AgentIO),
         "macjd_agent_act_host": (Ctx, AgentWeights, AgentIO, ActHost),
         "macjd_env_step_host": (Ctx, EnvTables, EnvIO, EnvHost),
+        "macjd_rollout_step_host": (Ctx, AgentWeights, AgentIO, ActHost, EnvTables, EnvIO, EnvHost),
     }
 
     def _check_abi(self):

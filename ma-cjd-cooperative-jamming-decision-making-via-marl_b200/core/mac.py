@@ -95,13 +95,9 @@ class BasicMAC:
         self.last_q_chosen = out["q_chosen"]
         return out["actions"].to(torch.int64).view(B, self.n_agents, 1), out["power"].clone().view(B, self.n_agents, 1)
 
-    def select_actions_host(self, obs, avail, t_env, test_mode=False, *, actions_out=None, power_out=None):
-        """mac.py:59-166 for callers that live on the host, as the reference's runner does: ``obs``
-        float32 [B, N, obs] and ``avail`` uint8 [B, N, A] are contiguous CPU tensors / numpy arrays
-        (page-locked memory makes the copies asynchronous); returns the chosen discrete actions int32
-        [B, N] and power float32 [B, N] in host memory (``actions_out`` / ``power_out`` when given).
-        One C call: copies in, fused step, copies out, stream drained on return
-        (include/macjd.h: macjd_agent_act_host).  The recurrent state stays on the device."""
+    def _host_launch(self, obs, avail, actions_out=None, power_out=None):
+        """Launch struct + host-pointer struct for the host-buffer calls, cached on the identity of the
+        caller's buffers (a rollout loop hands in the same objects every step)."""
         from .. import _native as N
         # steady state: the caller hands in the same buffer objects every step -> identity checks only
         c = self._host_cache
@@ -133,6 +129,16 @@ class BasicMAC:
                            flags=N.HOST_PINNED if pinned else 0)
             c = self._host_cache = {"io": io, "host": hs, "stage": st, "keep": (obs, avail, actions_out, power_out),
                                     "hid": self.hidden_states, "path": self.agent.path}
+        return c
+
+    def select_actions_host(self, obs, avail, t_env, test_mode=False, *, actions_out=None, power_out=None):
+        """mac.py:59-166 for callers that live on the host, as the reference's runner does: ``obs``
+        float32 [B, N, obs] and ``avail`` uint8 [B, N, A] are contiguous CPU tensors / numpy arrays
+        (page-locked memory makes the copies asynchronous); returns the chosen discrete actions int32
+        [B, N] and power float32 [B, N] in host memory (``actions_out`` / ``power_out`` when given).
+        One C call: copies in, fused step, copies out, stream drained on return
+        (include/macjd.h: macjd_agent_act_host).  The recurrent state stays on the device."""
+        c = self._host_launch(obs, avail, actions_out, power_out)
         eps = self.action_selector.anneal(t_env, test_mode)
         self._rng_step += 1
         io = c["io"]
@@ -140,6 +146,18 @@ class BasicMAC:
         self.agent.lib().call("macjd_agent_act_host", self.agent._ctx(), self.agent.packed().cstruct(), io, c["host"])
         self.last_q_chosen = c["stage"]["q_chosen"]
         return c["keep"][2], c["keep"][3]
+
+    def host_step_args(self, obs, avail, t_env, test_mode=False, *, actions_out=None, power_out=None):
+        """The (weights, io, host) structs of one ``select_actions_host`` call without making it: the
+        runner's fused act + env step (BatchedEpisodeRunner.step_host) passes them to
+        macjd_rollout_step_host.  Advances epsilon / the Philox step exactly as the call would."""
+        c = self._host_launch(obs, avail, actions_out, power_out)
+        eps = self.action_selector.anneal(t_env, test_mode)
+        self._rng_step += 1
+        io = c["io"]
+        io.epsilon, io.rng_step, io.test_mode = float(eps), self._rng_step & 0xFFFFFFFF, int(test_mode)
+        self.last_q_chosen = c["stage"]["q_chosen"]
+        return self.agent.packed().cstruct(), io, c["host"], c["keep"][2], c["keep"][3]
 
     def forward(self, agent_inputs_reshaped, hidden_states):
         """mac.py:168-187 -> (h_out [M, H], continuous_params_all [M, A])."""

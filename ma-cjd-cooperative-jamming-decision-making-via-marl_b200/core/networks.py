@@ -338,7 +338,7 @@ class RNNAgent(nn.Module):
         p = N.ptr
         path = int(self.path if path is None else path)
         common = dict(test_mode=int(test_mode), tile_rows=int(tile_rows), path=path, epsilon=float(epsilon),
-                      rng_step=int(rng_step) & 0xFFFFFFFF, seed=int(seed) & 0xFFFFFFFFFFFFFFFF, reserved2=0)
+                      rng_step=int(rng_step) & 0xFFFFFFFF, seed=int(seed) & 0xFFFFFFFFFFFFFFFF, rng_row_offset=0)
         heads = dict(q_all=p(out.get("q_all")), params_all=p(out.get("params_all")), greedy=p(out.get("greedy")),
                      sel_actions=p(sel_actions), q_sel=p(out.get("q_sel")), avail=p(avail), u_eps=p(u_eps),
                      rand_actions=p(rand_actions), actions=p(out.get("actions")), power=p(out.get("power")),

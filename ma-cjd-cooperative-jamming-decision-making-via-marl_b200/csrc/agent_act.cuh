@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(NT, 1) agent_forward_kernel(const AgentArgs a)
       if (io.actions) {
         int chosen = bim;
         if (!io.test_mode) {                                   // action_selectors.py:39-57
-          const uint32_t row_id = (uint32_t)(row0 + r);
+          const uint32_t row_id = (uint32_t)(io.rng_row_offset + row0 + r);
           const float u = io.u_eps ? io.u_eps[m] : philox_uniform(io.seed, kStreamEpsilon, row_id, (io.rng_step_dev ? __ldg(io.rng_step_dev) : io.rng_step) + t, 0);
           if (u < (io.epsilon_dev ? __ldg(io.epsilon_dev) : io.epsilon)) {
             if (io.rand_actions) {
@@ -404,7 +404,10 @@ __global__ void __launch_bounds__(NT, 1) agent_forward_kernel(const AgentArgs a)
           }
         }
         io.actions[m] = chosen;
-        if (io.power) io.power[m] = Ps[chosen * TM + r];
+        const float pw = Ps[chosen * TM + r];
+        if (io.power) io.power[m] = pw;
+        if (io.actions_mirror) io.actions_mirror[m] = chosen;      // e.g. the caller's page-locked host copy
+        if (io.power_mirror) io.power_mirror[m] = pw;
         if (io.q_chosen) io.q_chosen[m] = Qs[chosen * TM + r];
       }
     }

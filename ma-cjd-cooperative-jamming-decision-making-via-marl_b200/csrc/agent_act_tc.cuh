@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
         if (io.actions) {
           int chosen = bim;
           if (!io.test_mode) {
-            const uint32_t row_id = (uint32_t)(row0 + r);
+            const uint32_t row_id = (uint32_t)(io.rng_row_offset + row0 + r);
             const float u = io.u_eps ? io.u_eps[m] : philox_uniform(io.seed, kStreamEpsilon, row_id, (io.rng_step_dev ? __ldg(io.rng_step_dev) : io.rng_step) + t, 0);
             if (u < (io.epsilon_dev ? __ldg(io.epsilon_dev) : io.epsilon)) {
               if (io.rand_actions) {
@@ -570,7 +570,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
             }
           }
           io.actions[m] = chosen;
-          if (io.power) io.power[m] = Ps[chosen * kTcRows + r];
+          const float pw = Ps[chosen * kTcRows + r];
+          if (io.power) io.power[m] = pw;
+          if (io.actions_mirror) io.actions_mirror[m] = chosen;      // e.g. the caller's page-locked host copy
+          if (io.power_mirror) io.power_mirror[m] = pw;
           if (io.q_chosen) io.q_chosen[m] = Qs[chosen * kTcRows + r];
         }
       }

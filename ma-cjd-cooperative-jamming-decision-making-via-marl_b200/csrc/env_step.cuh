@@ -37,6 +37,7 @@ struct EnvKernelArgs {
                       // instead of two in sequence)
   uint32_t magic_s4;  // ceil(2^32 / (S/4)), ceil(2^32 / (J*S/4)): exact v / d for the view write-back loops
   uint32_t magic_js4;
+  int env_begin, env_end;   // this launch steps envs [env_begin, env_end) (io.env_begin / env_count; default all)
 };
 
 // element `row` of one env's table column (col = data + env * env_stride; row stride fits 32 bits)
@@ -85,9 +86,9 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
   const bool do_views = kMode == 0 || set_id == NW;
   const int wk = (kMode == 2 && do_phys) ? set_id : 0;       // which physics worker
   const int tid = (int)threadIdx.x - set_id * BS;
-  const int e0 = blockIdx.x * BS;
+  const int e0 = a.env_begin + blockIdx.x * BS;
   const int e = e0 + tid;
-  const bool live = e < n;
+  const bool live = e < a.env_end;
   const int rbase = 0, jbase = 16 * R, tbase = 16 * R + 8 * J;
 
   MACJD_DYNAMIC_SMEM(double, smem);
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
     __syncthreads();
 #endif
     if (kMode != 0) grid_dependency_wait();      // view warps: staged from the tables, nothing written yet
-    const int valid = min(BS, n - e0);
+    const int valid = min(BS, a.env_end - e0);
     if ((S & 3) == 0 && (a.stage_ld & 3) == 0) {
       // rows are 16-byte multiples: coalesced float4 stores
       const int S4 = S >> 2, ld4 = a.stage_ld >> 2;
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(kMode == 2 ? 384 : kMode == 1 ? 256 : 128, kMo
   }
   if (kMode != 0 && do_views && !want_views) grid_dependency_wait();
   if (io.avail && do_views) {  // all actions always available (environment.py:539-551)
-    const int valid = min(BS, n - e0);
+    const int valid = min(BS, a.env_end - e0);
     const int64_t base = (int64_t)e0 * J * A;
     const int total = valid * J * A;
     for (int v = tid; v < total; v += BS) io.avail[base + v] = 1;
@@ -404,8 +405,12 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   if (tab->n_radars > 64 || tab->row_stride > 0x7fffffffll || tab->row_stride < 0) return MACJD_ERR_UNSUPPORTED;
   if (!tab->data || !io->step_count) return MACJD_ERR_INVALID_ARG;
   if (physics && (!io->act_d || !io->act_p || !io->reward)) return MACJD_ERR_INVALID_ARG;
-  if (tab->n_envs == 0) return MACJD_OK;
+  if (io->env_begin < 0 || io->env_count < 0 || (int64_t)io->env_begin + io->env_count > tab->n_envs) return MACJD_ERR_INVALID_ARG;
+  const int n_step = io->env_count > 0 ? io->env_count : tab->n_envs - io->env_begin;
+  if (n_step == 0) return MACJD_OK;
   EnvKernelArgs a;
+  a.env_begin = io->env_begin;
+  a.env_end = io->env_begin + n_step;
   a.tab = *tab;
   a.io = *io;
   a.state_dim = tab->n_radars * (6 + tab->n_types) + 2 * tab->n_jammers;
@@ -431,7 +436,7 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
     if (cudaFuncSetAttribute(env_step_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return MACJD_ERR_CUDA;
   }
-  const int grid = (tab->n_envs + bs - 1) / bs;
+  const int grid = (n_step + bs - 1) / bs;
 #ifndef MACJD_TEST_HOST_EMULATION
   // latency-bound regime: physics and views as concurrent chains (measured at 4 096 envs: 22.5 -> 18.4 us),
   // and the radar loop over two workers

@@ -258,6 +258,157 @@ int macjd_env_step_host(const macjd_ctx* ctx, const macjd_env_tables* tab, const
   return drain(ctx);
 }
 
+namespace {
+// Second stream + fork / join events of the grouped host step, one set per device, created on first use.
+struct HostGroupStreams { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool failed = false; };
+HostGroupStreams* host_group_streams(int dev) {
+  static HostGroupStreams all[64];
+  HostGroupStreams& h = all[dev & 63];
+  if (!h.side && !h.failed) {
+    if (cudaStreamCreateWithFlags(&h.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      h.failed = true;
+    }
+  }
+  return h.failed ? nullptr : &h;
+}
+// A batch of at least 2 x this many envs is stepped as two groups on two streams (MACJD_HOST_GROUP_ENVS; 0 = never, the default)
+size_t host_group_envs() {
+  const char* e = getenv("MACJD_HOST_GROUP_ENVS");      // read per call (tens of ns): tests switch it
+  return e ? (size_t)strtoull(e, nullptr, 10) : (size_t)0;
+}
+extern "C++" {
+template <typename T>
+T* offset_ptr(T* p, size_t elems) { return p ? p + elems : nullptr; }
+}
+}  // namespace
+
+// Optional grouping (MACJD_HOST_GROUP_ENVS = g > 0: batches of >= 2 g envs are stepped as two groups of envs on
+// two streams, group B's chain issued behind group A's, so that B's observations come in over PCIe while A's
+// agent kernel runs and A's results go out while B computes).  Rows, envs and Philox counters keep their
+// whole-batch indices (io.rng_row_offset, io.env_begin / env_count): results do not depend on the grouping
+// (tests/runner_checks.py: check_fused_host_step).  OFF by default -- measured on B200, 4 096 envs x 2 jammers
+// (tools/e2e_host.py): one group 87.0 us per step, two groups 93.6 us: the second pair of launches and the
+// fork / join cost more than the overlap returns at this size.
+int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
+                            const macjd_act_host* ahost, const macjd_env_tables* tab, const macjd_env_io* eio,
+                            const macjd_env_host* ehost) {
+  int st = enter(ctx);
+  if (st != MACJD_OK) return st;
+  if (!w || !aio || !ahost || !tab || !eio || !ehost) return MACJD_ERR_INVALID_ARG;
+  if (aio->n_steps != 1 || aio->n_rows < 0 || tab->n_envs < 0 || tab->n_jammers < 1) return MACJD_ERR_INVALID_ARG;
+  if ((int64_t)aio->n_rows != (int64_t)tab->n_envs * tab->n_jammers) return MACJD_ERR_INVALID_ARG;
+  if (eio->env_begin != 0 || eio->env_count != 0) return MACJD_ERR_INVALID_ARG;
+  if (!ahost->obs || !aio->obs || !aio->actions || !aio->power) return MACJD_ERR_INVALID_ARG;
+  if (ahost->avail && !aio->avail) return MACJD_ERR_INVALID_ARG;
+  if ((ehost->reward && !eio->reward) || (ehost->terminated && !eio->terminated) || (ehost->obs && !eio->obs) ||
+      (ehost->state && !eio->state))
+    return MACJD_ERR_INVALID_ARG;
+  const size_t M = (size_t)aio->n_rows;
+  if (M == 0) return MACJD_OK;
+  const size_t n = (size_t)tab->n_envs, J = (size_t)tab->n_jammers;
+  const size_t S = (size_t)tab->n_radars * (6 + tab->n_types) + 2 * J;
+  const size_t O = (size_t)w->obs_dim, A = (size_t)w->n_actions, H = (size_t)w->hidden;
+  // in-place or copy-engine: decided on the whole buffers, so that grouping does not change the transfer mode
+  const float* a_obs = device_alias(ahost->obs, M * O * sizeof(float), false, ahost->flags);
+  const uint8_t* a_avail = ahost->avail ? device_alias(ahost->avail, M * A, false, ahost->flags) : nullptr;
+  float* a_q = (ahost->q_chosen && aio->q_chosen) ? device_alias(ahost->q_chosen, M * sizeof(float), true, ahost->flags) : nullptr;
+  int32_t* a_act = device_alias(ahost->actions, M * sizeof(int32_t), true, ahost->flags);
+  float* a_pow = device_alias(ahost->power, M * sizeof(float), true, ahost->flags);
+  float* e_rew = device_alias(ehost->reward, n * sizeof(float), true, ehost->flags);
+  uint8_t* e_term = device_alias(ehost->terminated, n, true, ehost->flags);
+  float* e_obs = device_alias(ehost->obs, n * J * S * sizeof(float), true, ehost->flags);
+  float* e_state = device_alias(ehost->state, n * S * sizeof(float), true, ehost->flags);
+
+  // groups of envs: [0, n0) on the caller's stream, [n0, n) on the side stream
+  size_t n0 = n;
+  HostGroupStreams* gs = nullptr;
+  if (host_group_envs() > 0 && n >= 2 * host_group_envs() && (gs = host_group_streams(ctx->device)) != nullptr)
+    n0 = ((n / 2 + 63) / 64) * 64;
+  const int n_groups = n0 < n ? 2 : 1;
+  macjd_ctx gctx[2] = {*ctx, *ctx};
+  if (n_groups == 2) {
+    gctx[1].stream = gs->side;
+    if (cudaEventRecord(gs->fork, (cudaStream_t)ctx->stream) != cudaSuccess ||
+        cudaStreamWaitEvent(gs->side, gs->fork, 0) != cudaSuccess) {
+      snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s", cudaGetErrorString(cudaGetLastError()));
+      return MACJD_ERR_CUDA;
+    }
+  }
+  // a failure after the fork still joins and drains both streams before returning
+  for (int g = 0; g < n_groups && st == MACJD_OK; ++g) {
+    const macjd_ctx* c = &gctx[g];
+    const size_t eb = g == 0 ? 0 : n0, ec = g == 0 ? n0 : n - n0;   // envs of this group
+    const size_t rb = eb * J, rc = ec * J;                           // agent rows of this group
+    // ---- agent: host observations in; the actions stay in the device staging buffers for the env kernel
+    macjd_agent_io ka = *aio;
+    ka.n_rows = (int32_t)rc;
+    ka.rng_row_offset = aio->rng_row_offset + (int32_t)rb;
+    ka.obs = a_obs ? a_obs + rb * O : aio->obs + rb * O;
+    ka.avail = (ahost->avail && a_avail) ? a_avail + rb * A : offset_ptr(aio->avail, rb * A);
+    ka.hidden = offset_ptr(aio->hidden, rb * H);
+    ka.hidden_seq = offset_ptr(aio->hidden_seq, rb * H);
+    ka.q_all = offset_ptr(aio->q_all, rb * A);
+    ka.params_all = offset_ptr(aio->params_all, rb * A);
+    ka.greedy = offset_ptr(aio->greedy, rb);
+    ka.sel_actions = offset_ptr(aio->sel_actions, rb);
+    ka.q_sel = offset_ptr(aio->q_sel, rb);
+    ka.u_eps = offset_ptr(aio->u_eps, rb);
+    ka.rand_actions = offset_ptr(aio->rand_actions, rb);
+    ka.actions = aio->actions + rb;
+    ka.power = aio->power + rb;
+    ka.q_chosen = a_q ? a_q + rb : offset_ptr(aio->q_chosen, rb);
+    // page-locked action buffers: the agent kernel writes them as well (no copy-engine operation behind the env kernel)
+    ka.actions_mirror = a_act ? a_act + rb : nullptr;
+    ka.power_mirror = a_pow ? a_pow + rb : nullptr;
+    if (!a_obs) st = copy_async(const_cast<float*>(ka.obs), ahost->obs + rb * O, rc * O * sizeof(float), cudaMemcpyHostToDevice, c);
+    if (st == MACJD_OK && ahost->avail && !a_avail)
+      st = copy_async(const_cast<uint8_t*>(ka.avail), ahost->avail + rb * A, rc * A, cudaMemcpyHostToDevice, c);
+    if (st == MACJD_OK) st = macjd_agent_forward(c, w, &ka);
+    if (st != MACJD_OK) break;
+    // ---- env: reads the chosen actions where the agent kernel left them
+    macjd_env_io ke = *eio;
+    ke.act_d = aio->actions;
+    ke.act_p = aio->power;
+    ke.flags |= MACJD_ENV_FOLLOWS_AGENT;
+    ke.env_begin = (int32_t)eb;
+    ke.env_count = (int32_t)ec;
+    if (e_rew) ke.reward = e_rew;
+    if (e_term) ke.terminated = e_term;
+    if (e_obs) ke.obs = e_obs;
+    if (e_state) ke.state = e_state;
+    st = macjd_env_step(c, tab, &ke);
+  }
+  // ---- what the kernels did not write in place (after both chains are issued: copies queue behind their group)
+  for (int g = 0; g < n_groups && st == MACJD_OK; ++g) {
+    const macjd_ctx* c = &gctx[g];
+    const size_t eb = g == 0 ? 0 : n0, ec = g == 0 ? n0 : n - n0, rb = eb * J, rc = ec * J;
+    if (ahost->actions && !a_act) st = copy_async(ahost->actions + rb, aio->actions + rb, rc * sizeof(int32_t), cudaMemcpyDeviceToHost, c);
+    if (st == MACJD_OK && ahost->power && !a_pow) st = copy_async(ahost->power + rb, aio->power + rb, rc * sizeof(float), cudaMemcpyDeviceToHost, c);
+    if (st == MACJD_OK && !a_q && ahost->q_chosen && aio->q_chosen)
+      st = copy_async(ahost->q_chosen + rb, aio->q_chosen + rb, rc * sizeof(float), cudaMemcpyDeviceToHost, c);
+    if (st == MACJD_OK && ehost->reward && !e_rew) st = copy_async(ehost->reward + eb, eio->reward + eb, ec * sizeof(float), cudaMemcpyDeviceToHost, c);
+    if (st == MACJD_OK && ehost->terminated && !e_term) st = copy_async(ehost->terminated + eb, eio->terminated + eb, ec, cudaMemcpyDeviceToHost, c);
+    if (st == MACJD_OK && ehost->obs && !e_obs)
+      st = copy_async(ehost->obs + eb * J * S, eio->obs + eb * J * S, ec * J * S * sizeof(float), cudaMemcpyDeviceToHost, c);
+    if (st == MACJD_OK && ehost->state && !e_state)
+      st = copy_async(ehost->state + eb * S, eio->state + eb * S, ec * S * sizeof(float), cudaMemcpyDeviceToHost, c);
+  }
+  if (n_groups == 2) {
+    if (cudaEventRecord(gs->join, gs->side) != cudaSuccess || cudaStreamWaitEvent((cudaStream_t)ctx->stream, gs->join, 0) != cudaSuccess) {
+      cudaStreamSynchronize(gs->side);
+      if (st == MACJD_OK) {
+        snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s", cudaGetErrorString(cudaGetLastError()));
+        st = MACJD_ERR_CUDA;
+      }
+    }
+  }
+  const int dr = drain(ctx);
+  return st != MACJD_OK ? st : dr;
+}
+
 int macjd_replay_copy(const macjd_ctx* ctx, const macjd_copy_desc* descs_host, int32_t n_keys, const int32_t* idx,
                       int32_t n_eps, int32_t index_on_src) {
   int st = enter(ctx);

@@ -215,6 +215,20 @@ class BatchedEpisodeRunner:
                              "state": tr["state"][t + 1], "obs": tr["obs"][t + 1], "avail": tr["avail_actions"][t + 1]})
         self.t_env += 1
 
+    def step_host(self, obs, avail, host, test_mode=False):
+        """One iteration of the reference's loop (episode_runner.py:119-165: select_actions, env.step) for a
+        caller whose buffers live on the HOST: ``obs`` [n, N, obs] float32 and ``avail`` [n, N, A] uint8 in;
+        ``host`` as for ``ElectromagneticEnvironment.step_host`` -- its act_d / act_p receive the chosen
+        actions, reward / terminated / obs / state the env outputs.  One C call and one stream drain
+        (include/macjd.h: macjd_rollout_step_host); the actions reach the env kernel without leaving the
+        device.  Same results as ``mac.select_actions_host`` followed by ``env.step_host``."""
+        mac, env = self.mac, self.env
+        w, aio, ahost, _, _ = mac.host_step_args(obs, avail, self.t_env, test_mode, actions_out=host["act_d"],
+                                                 power_out=host["act_p"])
+        eio, ehost = env.host_step_args(host)
+        mac.agent.lib().call("macjd_rollout_step_host", mac.agent._ctx(), w, aio, ahost, env._ctab, eio, ehost)
+        self.t_env += 1
+
     def reset(self):
         tr, mac = self.traj, self.mac
         hs = mac.hidden_states

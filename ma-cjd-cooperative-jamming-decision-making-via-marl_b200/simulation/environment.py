@@ -161,6 +161,10 @@ class ElectromagneticEnvironment:
         ``host`` maps act_d / act_p (in) and any of reward / terminated / obs / state (out) to contiguous
         CPU tensors or numpy arrays (see ``host_buffers``).  One C call: copies in, fused step, copies
         out, stream drained on return (include/macjd.h: macjd_env_step_host)."""
+        self._lib.call("macjd_env_step_host", self._ctx(), self._ctab, *self.host_step_args(host))
+
+    def host_step_args(self, host):
+        """The (io, host) structs of one ``step_host`` call, cached on the caller's buffers."""
         key = (tuple(host), tuple([v.data_ptr() if hasattr(v, "data_ptr") else N.ptr(v) for v in host.values()]))
         c = getattr(self, "_host_cache", None)
         if c is None or c["key"] != key:
@@ -174,7 +178,7 @@ class ElectromagneticEnvironment:
             pinned = all(torch.is_tensor(v) and v.is_pinned() for v in host.values()) and self.device.type == "cuda"
             hs = N.EnvHost(flags=N.HOST_PINNED if pinned else 0, **{k: N.ptr(v) for k, v in host.items()})
             c = self._host_cache = {"key": key, "host": hs, "io": self._io(self._act_d_dev, self._act_p_dev), "keep": dict(host)}
-        self._lib.call("macjd_env_step_host", self._ctx(), self._ctab, c["io"], c["host"])
+        return c["io"], c["host"]
 
     # ------------------------------------------------------------------ reference API
     def reset(self):

@@ -172,6 +172,45 @@ def check_host_buffer_api(device, lib, n_envs=7, steps=5, pinned=True):
         env_h.step_host({"act_d": hb["act_d"]})
 
 
+def check_fused_host_step(device, lib, n_envs=9, steps=6, pinned=True):
+    """BatchedEpisodeRunner.step_host (macjd_rollout_step_host: one call, one drain) against
+    select_actions_host + step_host on twin envs / controllers, exploration draws included."""
+    import copy
+    import types
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import hetero_spec
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
+    args = rl_args(device, epsilon_anneal_time=20)
+    spec = hetero_spec(n_envs, seed=6, active=True, episode_limit=steps - 2)
+    envs = [ElectromagneticEnvironment(args, spec=spec, device=device, seed=13, _lib=lib) for _ in range(2)]
+    torch.manual_seed(9)
+    mac_a = BasicMAC(24, args, _lib=lib)
+    if args.use_cuda:
+        mac_a.cuda()
+    mac_b = copy.deepcopy(mac_a)
+    for m in (mac_a, mac_b):
+        m.init_hidden(n_envs)
+    runner = types.SimpleNamespace(mac=mac_b, env=envs[1], t_env=0)
+    hbs = [e.host_buffers(pinned=pinned) for e in envs]
+    for hb, e in zip(hbs, envs):
+        hb["state"] = torch.zeros(n_envs, e.state_dim)
+        if pinned and torch.device(device).type == "cuda":
+            hb["state"] = hb["state"].pin_memory()
+        e.reset()
+    obs = [e.get_obs().cpu().contiguous() for e in envs]
+    avail = [e.get_avail_actions().cpu().contiguous() for e in envs]
+    for t in range(steps):
+        mac_a.select_actions_host(obs[0], avail[0], t, actions_out=hbs[0]["act_d"], power_out=hbs[0]["act_p"])
+        envs[0].step_host(hbs[0])
+        BatchedEpisodeRunner.step_host(runner, obs[1], avail[1], hbs[1])
+        for k in hbs[0]:
+            np.testing.assert_array_equal(hbs[1][k].numpy(), hbs[0][k].numpy(), err_msg=f"{k} t={t}")
+        assert torch.equal(mac_a.hidden_states, mac_b.hidden_states)
+        obs = [hbs[0]["obs"], hbs[1]["obs"]]
+    assert runner.t_env == steps
+
+
 def check_episode_graph_equals_stepwise(device, n_envs=64):
     """BatchedEpisodeRunner.run replays a whole episode as one CUDA graph (epsilon and the Philox counter
     come from device memory); twin runners, one stepping launch by launch, must produce identical

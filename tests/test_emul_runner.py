@@ -1,4 +1,6 @@
 """Runners + training loop on the CPU through the host-emulation build (tests/emul)."""
+import pytest
+
 from tests import runner_checks as RC
 from tests.helpers import emul_lib
 
@@ -17,3 +19,10 @@ def test_reference_protocol_runner():
 
 def test_host_buffer_api():
     RC.check_host_buffer_api("cpu", emul_lib())
+
+
+@pytest.mark.parametrize("group_envs", ["0", "64", "100"])
+def test_fused_host_step(monkeypatch, group_envs):
+    # 0: never grouped; 64: 150 envs -> two groups, envs [0, 128) and [128, 150); 100: batch too small, one group
+    monkeypatch.setenv("MACJD_HOST_GROUP_ENVS", group_envs)
+    RC.check_fused_host_step("cpu", emul_lib(), n_envs=150)

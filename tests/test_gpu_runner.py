@@ -23,5 +23,10 @@ def test_host_buffer_api(n_envs, pinned):
     RC.check_host_buffer_api("cuda", None, n_envs=n_envs, pinned=pinned)
 
 
+@pytest.mark.parametrize("n_envs,pinned", [(300, True), (300, False), (6000, True)])
+def test_fused_host_step(n_envs, pinned):
+    RC.check_fused_host_step("cuda", None, n_envs=n_envs, pinned=pinned)
+
+
 def test_episode_graph_equals_stepwise():
     RC.check_episode_graph_equals_stepwise("cuda")

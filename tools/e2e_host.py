@@ -27,3 +27,21 @@ for name, fn in (("act_host", act), ("env_step_host", envs), ("both", both)):
     for t in range(K): fn(t)
     torch.cuda.synchronize()
     print(f"{name:>14}: {(time.perf_counter() - t0) / K * 1e6:7.1f} us/call", flush=True)
+
+# ---- the fused call (BatchedEpisodeRunner.step_host -> macjd_rollout_step_host), with and without the
+# observation write-back and with / without env groups (MACJD_HOST_GROUP_ENVS is read per call)
+import os
+from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
+runner = types.SimpleNamespace(mac=mac, env=env, t_env=0)
+hb_noobs = {k: v for k, v in hb.items() if k != "obs"}
+obs_in = hb["obs"].clone().pin_memory()
+for groups in ("0", "2048", "1024"):
+    os.environ["MACJD_HOST_GROUP_ENVS"] = groups
+    for name, host in (("fused", hb), ("fused, no obs out", hb_noobs)):
+        fn = lambda t: BatchedEpisodeRunner.step_host(runner, obs_in, avail_h, host)
+        for t in range(20): fn(t)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(K): fn(t)
+        torch.cuda.synchronize()
+        print(f"groups {groups:>5} {name:>18}: {(time.perf_counter() - t0) / K * 1e6:7.1f} us/call", flush=True)
