@@ -58,6 +58,7 @@ class AgentIO(C.Structure):
                 ("actions_mirror", c_void_p), ("power_mirror", c_void_p)]
 
 
+MAX_COPY_KEYS = 12    # include/macjd.h: MACJD_MAX_COPY_KEYS
 HOST_PINNED = 1       # include/macjd.h: MACJD_HOST_PINNED
 ENV_FOLLOWS_AGENT = 1 # include/macjd.h: MACJD_ENV_FOLLOWS_AGENT
 

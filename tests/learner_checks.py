@@ -4,6 +4,7 @@ import os
 import types
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import agent_oracle as AO
@@ -175,3 +176,51 @@ def check_rollout_store_roundtrip(device, lib, n=7, seed=0):
         for b, (tr, e) in enumerate(src):
             assert torch.equal(out[k][b].cpu(), tr[k][:, e]), (k, b)
     assert bool(out["filled"].all())
+
+
+def check_shared_obs_replay(device, lib, n_agents=2, seed=1):
+    """shared_obs=True (the ring keeps no obs; sample() rebuilds it from the state inside the gather launch)
+    returns exactly what the full-format ring returns when obs is the replicated state -- both layouts,
+    both store paths, more agents than one launch has descriptors for."""
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    T, Nn, S, A, H = 5, n_agents, 12, 5, 64
+    args = types.SimpleNamespace(buffer_size=9, episode_limit=T, n_actions=A, n_agents=Nn, state_shape=S, obs_shape=S,
+                                 rnn_hidden_dim=H, use_cuda=True, device=device)
+    full = EpisodeReplayBuffer(args, device=device, _lib=lib)
+    lean = EpisodeReplayBuffer(args, device=device, _lib=lib, shared_obs=True)
+    assert "obs" not in lean.buffers and full.bytes_per_episode() - lean.bytes_per_episode() == (T + 1) * Nn * S * 4
+    gen = torch.Generator().manual_seed(seed)
+    def mk(n_eps):
+        st = torch.randn(T + 1, n_eps, S, generator=gen)
+        return {"state": st, "obs": st[:, :, None, :].expand(T + 1, n_eps, Nn, S).contiguous(),
+                "actions_discrete": torch.randint(0, A, (T, n_eps, Nn, 1), generator=gen, dtype=torch.int32),
+                "actions_continuous": torch.rand(T, n_eps, Nn, 1, generator=gen),
+                "avail_actions": torch.randint(0, 2, (T + 1, n_eps, Nn, A), generator=gen, dtype=torch.uint8),
+                "reward": torch.randn(T, n_eps, 1, generator=gen),
+                "terminated": torch.randint(0, 2, (T, n_eps, 1), generator=gen, dtype=torch.uint8),
+                "hidden_state": torch.randn(T + 1, n_eps, Nn, H, generator=gen)}
+    for n_eps in (6, 5):                                   # the second store wraps the ring
+        tr = {k: v.to(device) for k, v in mk(n_eps).items()}
+        full.store_rollout(tr)
+        lean.store_rollout(tr)
+    # one short host-side episode through the reference's store path (padding rules)
+    L = 3
+    ep = mk(1)
+    host = {k: [v[: (L + 1 if k in ("state", "obs", "avail_actions", "hidden_state") else L), 0].numpy()] for k, v in ep.items()}
+    full.store_episode(host)
+    lean.store_episode(host)
+    assert (full.current_index, full.current_size) == (lean.current_index, lean.current_size)
+    for time_major in (False, True):
+        for idx in (np.array([2, 0, 8, 3]), np.array([3])):      # slot 3 holds the short episode
+            a, b = full.gather(idx, time_major=time_major), lean.gather(idx, time_major=time_major)
+            assert list(a) == list(b)
+            for k in a:
+                assert (a[k] == b[k]) if k == "max_seq_len" else (a[k].shape == b[k].shape and torch.equal(a[k], b[k])), k
+    np.random.seed(4)
+    sa = full.sample(4)
+    np.random.seed(4)
+    sb = lean.sample(4)
+    assert sb["obs"].dtype == torch.float32 and torch.equal(sa["obs"], sb["obs"]) and sb["avail_actions"].dtype == torch.int64
+    bad = types.SimpleNamespace(**{**vars(args), "obs_shape": S + 1})
+    with pytest.raises(ValueError):
+        EpisodeReplayBuffer(bad, device=device, _lib=lib, shared_obs=True)

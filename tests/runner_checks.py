@@ -239,3 +239,42 @@ def check_episode_graph_equals_stepwise(device, n_envs=64):
             assert torch.equal(v, runners[1].traj[k]), (ep, k)
         assert info_s["episode_return"] == info_g["episode_return"]
     assert runners[0].t_env == runners[1].t_env and runners[0].mac._rng_step == runners[1].mac._rng_step
+
+
+def check_main_loop(device, lib, tmp_path):
+    """macjd_b200.main.run (main.py:72-289 on the batched path): counters with the reference's meaning,
+    training starts after start_training_steps, greedy evaluation leaves the exploration schedule alone,
+    the reference's console lines / TensorBoard tags, and checkpoints that load back."""
+    from macjd_b200 import main as M
+    from macjd_b200.simulation.scenario import hetero_spec
+    n_envs, T = 6, 5
+    args = rl_args(device, episode_limit=T, batch_size=4, buffer_size=8, total_env_steps=4 * n_envs * T,
+                   start_training_steps=n_envs * T, train_interval=2, log_interval=10, log_interval_seconds=0,
+                   save_model=True, save_model_dir=str(tmp_path / "models"), save_interval=2 * n_envs, test_name="t",
+                   test_interval=2 * n_envs * T, test_nepisodes=7, device_request=device)
+    lines, scalars = [], []
+    writer = types.SimpleNamespace(add_scalar=lambda tag, v, step: scalars.append((tag, float(v), step)), close=lambda: None)
+    out = M.run(args, spec=hetero_spec(n_envs, seed=3, active=True, episode_limit=T), writer=writer, log=lines.append, _lib=lib)
+    assert out["episodes"] == 4 * n_envs and out["total_steps"] == 4 * n_envs * T
+    assert out["train_steps"] == 3 * (T // 2)                    # rollouts 2, 3 and 4 train, T // train_interval steps each
+    assert out["buffer"].buffer_size == 8 and len(out["buffer"]) == 8
+    assert out["runner"].t_env == 4 * T                          # two evaluations did not advance the schedule
+    assert out["last_eval"]["n_episodes"] == 2 * n_envs and np.isfinite(out["last_eval"]["episode_return"])
+    assert abs(out["last_logged"]["action_dist"].sum() - 1) < 1e-6 and np.isfinite(out["last_logged"]["avg_loss"])
+    tags = {t for t, _, _ in scalars}
+    assert {"Perf/Avg_Return", "Perf/Avg_Length", "Perf/Avg_Step_Reward", "Loss/train_avg", "Loss/train_episode_avg",
+            "Params/Epsilon", "Params/Buffer_Size", "Stats/grad_norm", "QValues/eval_qtot_avg", "QValues/target_qtot_avg",
+            "Rewards/r_d_avg", "Rewards/r_p_avg", "Rewards/r_j_avg", "Perf/Avg_Power", "ActionDist/Action_0",
+            "Test/Avg_Return"} <= tags
+    assert lines[0] == "Starting training..." and lines[-1] == "Training finished."
+    assert any(l.startswith(f"Steps: {4 * n_envs * T}/{4 * n_envs * T} | Episodes: {4 * n_envs}") for l in lines)
+    assert set(os.listdir(tmp_path / "models" / "t")) == {f"step_{k * n_envs * T}" for k in (2, 4)}
+    d = tmp_path / "models" / "t" / f"step_{4 * n_envs * T}"
+    assert sorted(os.listdir(d)) == ["agent.pth", "optimizer.pth", "qmix_net.pth"]
+    sd = torch.load(d / "agent.pth", map_location="cpu")
+    for k, v in out["learner"].mac.agent.state_dict().items():
+        assert torch.equal(sd[k], v.cpu()), k
+    with pytest.raises(FileNotFoundError):
+        M.load_config("nope", str(tmp_path))
+    cfg = M.default_config(lr=1e-4)
+    assert cfg.lr == 1e-4 and cfg.batch_size == 32 and cfg.target_update_interval == 200

@@ -22,3 +22,8 @@ def test_replay_store_sample():
 
 def test_replay_rollout_roundtrip():
     LC.check_rollout_store_roundtrip("cpu", emul_lib())
+
+
+@pytest.mark.parametrize("n_agents", [2, 8])
+def test_shared_obs_replay(n_agents):
+    LC.check_shared_obs_replay("cpu", emul_lib(), n_agents=n_agents)

@@ -26,3 +26,7 @@ def test_fused_host_step(monkeypatch, group_envs):
     # 0: never grouped; 64: 150 envs -> two groups, envs [0, 128) and [128, 150); 100: batch too small, one group
     monkeypatch.setenv("MACJD_HOST_GROUP_ENVS", group_envs)
     RC.check_fused_host_step("cpu", emul_lib(), n_envs=150)
+
+
+def test_main_loop(tmp_path):
+    RC.check_main_loop("cpu", emul_lib(), tmp_path)

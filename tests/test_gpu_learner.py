@@ -124,3 +124,8 @@ def test_qhead_repack_equals_full_repack():
     part = (pk.buffer.clone(), pk.tc_buffer.clone())
     mac.agent.packed(force=True)
     assert torch.equal(part[0], pk.buffer) and torch.equal(part[1], pk.tc_buffer)
+
+
+@pytest.mark.parametrize("n_agents", [2, 8])
+def test_shared_obs_replay(n_agents):
+    LC.check_shared_obs_replay("cuda", lib(), n_agents=n_agents)

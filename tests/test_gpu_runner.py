@@ -30,3 +30,7 @@ def test_fused_host_step(n_envs, pinned):
 
 def test_episode_graph_equals_stepwise():
     RC.check_episode_graph_equals_stepwise("cuda")
+
+
+def test_main_loop(tmp_path):
+    RC.check_main_loop("cuda", None, tmp_path)
