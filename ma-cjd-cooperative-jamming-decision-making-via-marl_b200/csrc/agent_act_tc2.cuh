@@ -88,6 +88,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 // bounded wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1   // (nvcc unrolls this spin loop 32x otherwise: a third of the pair kernel's code)
   for (uint32_t it = 0; it < (1u << 22); ++it) {
     uint32_t done;
     asm volatile(

@@ -99,6 +99,7 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // Bounded wait: a wrong descriptor must fail loudly (trap), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1   // (nvcc unrolls this spin loop 32x otherwise: a third of the pair kernel's code)
   for (uint32_t it = 0; it < (1u << 22); ++it) {
     uint32_t done;
     asm volatile(
