@@ -23,8 +23,11 @@ def test_host_buffer_api(n_envs, pinned):
     RC.check_host_buffer_api("cuda", None, n_envs=n_envs, pinned=pinned)
 
 
-@pytest.mark.parametrize("n_envs,pinned", [(300, True), (300, False), (6000, True)])
-def test_fused_host_step(n_envs, pinned):
+@pytest.mark.parametrize("n_envs,pinned,group_envs", [(300, True, "0"), (300, False, "0"), (6000, True, "0"),
+                                                      (6000, True, "2048"), (6000, False, "1000"), (300, True, "100")])
+def test_fused_host_step(monkeypatch, n_envs, pinned, group_envs):
+    # group_envs > 0: batches of >= 2 x that many envs are stepped as two groups on two streams (opt-in)
+    monkeypatch.setenv("MACJD_HOST_GROUP_ENVS", group_envs)
     RC.check_fused_host_step("cuda", None, n_envs=n_envs, pinned=pinned)
 
 
