@@ -203,7 +203,10 @@ class NativeLib:
             raise MacjdError(f"macjd call failed ({status}): {msg}")
 
     def call(self, name, *structs):
-        self.check(getattr(self.lib, name)(*[C.byref(s) for s in structs]))
+        # argtypes are POINTER(struct): ctypes passes the instances by reference itself
+        status = getattr(self.lib, name)(*structs)
+        if status != 0:
+            self.check(status)
 
     def callv(self, name, *args):
         """Entry points with scalar / raw-pointer arguments: structures are passed by
@@ -243,4 +246,11 @@ def torch_ctx(device=None):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
     raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)      # same handle, without building a Stream object
-    return Ctx(device=idx, reserved=0, stream=raw(idx) if raw is not None else torch.cuda.current_stream(idx).cuda_stream)
+    stream = raw(idx) if raw is not None else torch.cuda.current_stream(idx).cuda_stream
+    c = _ctx_cache.get((idx, stream))                                # one struct per (device, stream): ~1 us per act call
+    if c is None:
+        c = _ctx_cache[(idx, stream)] = Ctx(device=idx, reserved=0, stream=stream)
+    return c
+
+
+_ctx_cache = {}
