@@ -200,3 +200,33 @@ def test_zero_rows_is_a_no_op():
         out = mac.agent.run(torch.zeros(1, 0, 24, device="cuda"), torch.zeros(0, 128, device="cuda"), select=True,
                             test_mode=True, want_q=True, path=path)
         assert out["actions"].shape == (1, 0) and out["q_all"].shape == (1, 0, 5)
+
+
+def test_pair_kernel_needs_the_constant_block():
+    """tc_format = 0 (weight chunks without the per-layer constant block behind them): the CTA-pair kernel must
+    refuse instead of reading past the chunks; auto falls back to the single-CTA tensor-core kernel."""
+    from macjd_b200 import _native as N
+    mac, args = AC.random_agent(6, 24, 5, 128, 128, 2, "cuda")
+    M = 256
+    obs = torch.randn(M, 24, device="cuda")
+    w = mac.agent.packed().cstruct()
+    assert w.tc_format == 1 and N.get_lib().lib.macjd_agent_pair_supported(N.C.byref(w)) == 1
+    w0 = type(w).from_buffer_copy(w)
+    w0.tc_format = 0
+    assert N.get_lib().lib.macjd_agent_pair_supported(N.C.byref(w0)) == 0
+    outs = {}
+    for name, ww, path in (("pair", w, 3), ("auto_without_block", w0, 0)):
+        h = torch.zeros(M, 128, device="cuda")
+        act = torch.empty(M, dtype=torch.int32, device="cuda")
+        pw = torch.empty(M, dtype=torch.float32, device="cuda")
+        io = N.AgentIO(n_rows=M, n_steps=1, obs=obs.data_ptr(), hidden=h.data_ptr(), test_mode=1, path=path,
+                       actions=act.data_ptr(), power=pw.data_ptr())
+        N.get_lib().call("macjd_agent_forward", N.torch_ctx(torch.device("cuda", 0)), ww, io)
+        torch.cuda.synchronize()
+        outs[name] = (act.clone(), pw.clone(), h.clone())
+    assert torch.equal(outs["pair"][0], outs["auto_without_block"][0])
+    torch.testing.assert_close(outs["pair"][2], outs["auto_without_block"][2], rtol=1e-5, atol=1e-6)
+    io = N.AgentIO(n_rows=M, n_steps=1, obs=obs.data_ptr(), hidden=outs["pair"][2].data_ptr(), test_mode=1, path=3,
+                   actions=outs["pair"][0].data_ptr(), power=outs["pair"][1].data_ptr())
+    with pytest.raises(N.MacjdError):
+        N.get_lib().call("macjd_agent_forward", N.torch_ctx(torch.device("cuda", 0)), w0, io)
