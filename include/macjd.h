@@ -260,6 +260,10 @@ typedef struct macjd_agent_io {
   int32_t* actions_mirror;    /* [T][M] optional second destinations of actions / power (same values):   */
   float* power_mirror;        /* the host-step call points them at the caller's page-locked buffers while
                                  the primary copies stay in HBM for the env kernel                       */
+  const float* hidden_in;     /* optional [M][H]: the initial recurrent state is read from here instead of
+                                 `hidden`, which is then only written (or NULL).  A rollout that records
+                                 h_t per step (hidden_seq) chains the steps through those records and
+                                 saves the second 4 MB store per step (runners/episode_runner.py)     */
 } macjd_agent_io;
 
 /* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);

@@ -147,11 +147,12 @@ __global__ void __launch_bounds__(NT, 1) agent_forward_kernel(const AgentArgs a)
   // ---- recurrent state tile (row-major): 16-byte async copies, zero rows past the end
   {
     const int vec = H >> 2;
-    const bool have = io.hidden && !io.hidden_zero_init;
+    const float* hsrc = io.hidden_in ? io.hidden_in : io.hidden;      // initial state: a separate read-only source, or in place
+    const bool have = hsrc && !io.hidden_zero_init;
     for (int idx = tid; idx < TM * vec; idx += NT) {
       const int r = idx / vec, k4 = (idx - r * vec) << 2;
       float* dst = B2 + (size_t)r * LDB + k4;
-      if (have && r < valid) cp_async16(dst, io.hidden + (size_t)(row0 + r) * H + k4);
+      if (have && r < valid) cp_async16(dst, hsrc + (size_t)(row0 + r) * H + k4);
       else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     cp_async_commit();

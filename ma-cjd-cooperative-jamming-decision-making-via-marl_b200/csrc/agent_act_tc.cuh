@@ -315,11 +315,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) agent_forward_tc_kernel(const A
 
     // recurrent state -> hi / lo operand tiles (each thread: its half of the row)
     {
-      const bool have = io.hidden && !io.hidden_zero_init && live;
+      const float* hsrc = io.hidden_in ? io.hidden_in : io.hidden;
+      const bool have = hsrc && !io.hidden_zero_init && live;
       for (int k = ub; k < ub + 64; k += 4) {
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (have) {
-          const float4 x = *reinterpret_cast<const float4*>(io.hidden + (size_t)(row0 + r) * H + k);
+          const float4 x = *reinterpret_cast<const float4*>(hsrc + (size_t)(row0 + r) * H + k);
           v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
         }
         store_split4(S.hhi, S.hlo, r, k, H, v);

@@ -237,10 +237,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
     const int q4 = warp & 3, ch = warp >> 2, half = q4 >> 1;
     const int r = (q4 & 1) * 32 + lane, ub = half * 64 + ch * kT2Upt, part = half * kT2ColSplit + ch;
     const bool live = r < valid;
-    const bool have = io.hidden && !io.hidden_zero_init && live;
+    const float* hsrc = io.hidden_in ? io.hidden_in : io.hidden;      // initial state: a separate read-only source, or in place
+    const bool have = hsrc && !io.hidden_zero_init && live;
 #pragma unroll
     for (int i = 0; i < kT2Upt / 4; ++i)
-      h_in[i] = have ? __ldg(reinterpret_cast<const float4*>(io.hidden + (size_t)(row0 + r) * H + ub) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      h_in[i] = have ? __ldg(reinterpret_cast<const float4*>(hsrc + (size_t)(row0 + r) * H + ub) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 32 / kT2Parts; ++j) {
       const int kk = part * (32 / kT2Parts) + j;

@@ -349,6 +349,7 @@ int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, 
     ka.obs = a_obs ? a_obs + rb * O : aio->obs + rb * O;
     ka.avail = (ahost->avail && a_avail) ? a_avail + rb * A : offset_ptr(aio->avail, rb * A);
     ka.hidden = offset_ptr(aio->hidden, rb * H);
+    ka.hidden_in = offset_ptr(aio->hidden_in, rb * H);
     ka.hidden_seq = offset_ptr(aio->hidden_seq, rb * H);
     ka.q_all = offset_ptr(aio->q_all, rb * A);
     ka.params_all = offset_ptr(aio->params_all, rb * A);

@@ -174,9 +174,16 @@ class BatchedEpisodeRunner:
         n, Nn = self.n_envs, self.n_agents
         p = N.ptr
         self._agent_io, self._env_io = [], []
-        for t in range(self.episode_limit):
+        T = self.episode_limit
+        for t in range(T):
+            # The recurrent state is chained through the trajectory's own h_t records: step t reads slot t - 1
+            # (step 0 starts from zeros, reset()) and writes slot t; only the last step also updates
+            # mac.hidden_states.  One 4 MB store per step instead of two: 41.7 -> 39.9 us per flushed step
+            # at 4 096 envs (tools/step_hidden_seq.py).  Steps of one episode must therefore all take this path
+            # (or all the injected-draws path below), in order -- which is how run() and the graph use them.
             self._agent_io.append(N.AgentIO(
-                n_rows=n * Nn, n_steps=1, obs=p(tr["obs"][t]), hidden=p(mac.hidden_states), hidden_zero_init=0,
+                n_rows=n * Nn, n_steps=1, obs=p(tr["obs"][t]), hidden=p(mac.hidden_states) if t == T - 1 else None,
+                hidden_in=p(tr["hidden_state"][t - 1]) if t > 0 else None, hidden_zero_init=1 if t == 0 else 0,
                 test_mode=0, tile_rows=0, path=mac.agent.path, hidden_seq=p(tr["hidden_state"][t]),
                 avail=p(tr["avail_actions"][t]), epsilon=0.0, rng_step=0, seed=mac.seed & 0xFFFFFFFFFFFFFFFF,
                 actions=p(tr["actions_discrete"][t]), power=p(tr["actions_continuous"][t])))

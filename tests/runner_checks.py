@@ -241,6 +241,36 @@ def check_episode_graph_equals_stepwise(device, n_envs=64):
     assert runners[0].t_env == runners[1].t_env and runners[0].mac._rng_step == runners[1].mac._rng_step
 
 
+def check_fast_path_chains_hidden_state(device, lib, n_envs=10):
+    """The cached-struct path of BatchedEpisodeRunner chains the recurrent state through the trajectory's h_t
+    records (hidden_in = slot t - 1, only the last step writes mac.hidden_states); a twin runner that takes the
+    general path (in-place mac.hidden_states every step) must produce the same episode, twice in a row."""
+    import copy
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import hetero_spec
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
+    args = rl_args(device)
+    spec = hetero_spec(n_envs, seed=12, active=True, episode_limit=args.episode_limit)
+    torch.manual_seed(2)
+    mac0 = BasicMAC(24, args, _lib=lib)
+    if args.use_cuda:
+        mac0.cuda()
+    runners = [BatchedEpisodeRunner(ElectromagneticEnvironment(args, spec=spec, device=device, seed=5, _lib=lib),
+                                    copy.deepcopy(mac0), None, args) for _ in range(2)]
+    T = args.episode_limit
+    never = torch.ones(n_envs * args.n_agents, device=device)          # u >= epsilon: no exploration, general path
+    for ep in range(2):
+        runners[0].run(test_mode=True, store=False)
+        runners[1].reset()
+        for t in range(T):
+            runners[1].step(t, test_mode=True, u_eps=never)
+        for k, v in runners[0].traj.items():
+            assert torch.equal(v, runners[1].traj[k]), (ep, k)
+        for r in runners:
+            assert torch.equal(r.mac.hidden_states.view(-1), r.traj["hidden_state"][T - 1].reshape(-1))
+
+
 def check_main_loop(device, lib, tmp_path):
     """macjd_b200.main.run (main.py:72-289 on the batched path): counters with the reference's meaning,
     training starts after start_training_steps, greedy evaluation leaves the exploration schedule alone,

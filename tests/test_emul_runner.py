@@ -30,3 +30,7 @@ def test_fused_host_step(monkeypatch, group_envs):
 
 def test_main_loop(tmp_path):
     RC.check_main_loop("cpu", emul_lib(), tmp_path)
+
+
+def test_fast_path_chains_hidden_state():
+    RC.check_fast_path_chains_hidden_state("cpu", emul_lib())

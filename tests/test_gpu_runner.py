@@ -37,3 +37,7 @@ def test_episode_graph_equals_stepwise():
 
 def test_main_loop(tmp_path):
     RC.check_main_loop("cuda", None, tmp_path)
+
+
+def test_fast_path_chains_hidden_state():
+    RC.check_fast_path_chains_hidden_state("cuda", None)
