@@ -285,13 +285,14 @@ def main():
     value = world * M * K / dt
 
     # ---- roofline of the dominant kernel (agent_forward) and of the env-step kernel, each alone
-    # the two launches of timestep 0 exactly as the timed rollout issues them (cached C structs: the
+    # the two launches of one timestep exactly as the timed rollout issues them (cached C structs: the
     # host side is one ctypes call, so the CUDA events bracket the kernel and not Python)
     import copy as _copy
     if getattr(runner, "_structs_for", None) != (mac.hidden_states.data_ptr(), mac.agent.path):
         runner._build_step_structs()
     lib, ctx = mac.agent.lib(), mac.agent._ctx()
-    aio, eio = runner._agent_io[0], runner._env_io[0]
+    # timestep 1: a typical step (timestep 0 starts from zeros and does not read a recurrent state)
+    aio, eio = runner._agent_io[1], runner._env_io[1]
     aio.epsilon, aio.rng_step, aio.test_mode = 0.3, 1, 0
     aio_simt = type(aio).from_buffer_copy(aio)
     aio_simt.path = 1
