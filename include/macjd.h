@@ -11,8 +11,10 @@
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
  *     name ends in _host; buffers are owned by the caller, kernels never allocate
  *   - all work is enqueued on ctx->stream of device ctx->device and returns
- *     immediately (stream-ordered); no global mutable state, re-entrant for
- *     disjoint buffers
+ *     immediately (stream-ordered); the calling thread's current CUDA device is
+ *     the same on return as on entry; entry points may be called from several
+ *     threads on disjoint buffers (process-wide state is limited to lock-free /
+ *     mutex-protected caches of idempotent per-device driver settings)
  *   - return value: 0 = MACJD_OK, negative = error (macjd_status_string()); the
  *     library never throws, aborts or prints
  *   - optional outputs may be NULL
@@ -215,10 +217,10 @@ typedef struct macjd_agent_io {
   int32_t test_mode;          /* != 0: greedy only (action_selectors.py:59-61)          */
   int32_t tile_rows;          /* rows per CTA: 0 = auto, or 8/16/32/64 (tuning knob)     */
   int32_t path;               /* 0 = auto (tensor cores when tc_chunks is given and the dims
-                                 allow), 1 = FP32 SIMT, 2 = tcgen05 3xTF32 with one CTA per 64 rows,
-                                 3 = tcgen05 3xTF32 with CTA pairs (cta_group::2, 128 rows per
-                                 pair); 2 and 3 return MACJD_ERR_UNSUPPORTED if the dims do
-                                 not fit */
+                                 allow), 1 = FP32 SIMT, 3 = tcgen05 3xTF32 with CTA pairs
+                                 (cta_group::2, 128 rows per pair; MACJD_ERR_UNSUPPORTED if the
+                                 dims do not fit).  2 named round 1's single-CTA tensor-core
+                                 kernel, since removed: MACJD_ERR_UNSUPPORTED */
   float* hidden_seq;          /* [T][M][H] h_t after every step, optional               */
   float* q_all;               /* [T][M][A] Q(s, a, P_a) for every action, optional      */
   float* params_all;          /* [T][M][A] actor outputs P_a, optional                  */
@@ -271,6 +273,9 @@ typedef struct macjd_agent_io {
 MACJD_API int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io);
 /* 1 if the CTA-pair tensor-core kernel (io->path 3 / auto, io->part 1 and 2) can run these weights. */
 MACJD_API int macjd_agent_pair_supported(const macjd_agent_weights* w);
+/* k-extent of one packed weight chunk in macjd_agent_weights.tc_chunks as this build of the library
+ * expects it (core/networks.py packs accordingly); 0 = built without the tensor-core kernel. */
+MACJD_API int macjd_agent_tc_chunk_k(void);
 
 /* Host-buffer form of BasicMAC.select_actions (core/mac.py:59-187: numpy observations and
  * availability masks in, chosen discrete actions and their power levels out).  `io` is a
@@ -419,6 +424,12 @@ MACJD_API size_t macjd_opt_scratch_floats(void);
 MACJD_API int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, const float* grad, float* m,
                               float* v, const float* sums, float max_norm, float lr, float beta1, float beta2,
                               float eps, int64_t step, float* scal, float* scratch, size_t scratch_floats);
+
+/* A tensor-core kernel waits on its pipeline barriers with a bound; if a wait ever runs out (a peer CTA
+ * that never arrives), the launch finishes with invalid outputs instead of trapping, and every LATER entry
+ * point returns MACJD_ERR_CUDA ("tcgen05 pipeline wait timed out ...", macjd_last_cuda_error) until
+ * macjd_clear_pipeline_fault() is called. */
+MACJD_API int macjd_clear_pipeline_fault(void);
 
 /* ===================================================================== tensor-core self-test
  * D[M][N] = A[M][K] B[N][K]^T on the tcgen05 TF32 pipe with the 3xTF32 operand split

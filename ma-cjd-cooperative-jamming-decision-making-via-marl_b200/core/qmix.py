@@ -149,8 +149,12 @@ class QMixLearner:
 
     # ------------------------------------------------------------------ the train step
     @torch.no_grad()
-    def train(self, batch, train_info=None, *, lazy_stats=False, return_debug=False):
-        """core/qmix.py:76-215.  Returns {loss, grad_norm, eval_qtot_avg, target_qtot_avg}."""
+    def train(self, batch, train_info=None, *, lazy_stats=False, return_debug=False, check_actions=True):
+        """core/qmix.py:76-215.  Returns {loss, grad_norm, eval_qtot_avg, target_qtot_avg}.
+        ``lazy_stats=True`` returns the four statistics as one device tensor (``stats_tensor``) instead of
+        reading them back, and ``check_actions=False`` skips the action-range read-back (for batches whose
+        actions this library's own selection kernel produced): together they leave the step without any
+        host synchronisation, which is what the pipelined training loop (main.py) needs."""
         self.train_step += 1
         L, ctx, dev = self.lib(), self._ctx(), self.device
         tb = self._time_major(batch)
@@ -165,7 +169,7 @@ class QMixLearner:
         # networks.py:157-158 raises on an action index outside [0, A).  Checked here, before the long
         # unrolls are queued: the read-back then only waits for the batch preparation (checked later it
         # would block the host until both unrolls finish and serialise the rest of the step behind them).
-        if int(tb["a_d"].numel()):
+        if check_actions and int(tb["a_d"].numel()):
             lo_hi = torch.stack([tb["a_d"].min(), tb["a_d"].max()]).tolist()
             if lo_hi[0] < 0 or lo_hi[1] >= A:
                 raise IndexError(f"Action index out of bounds, n_actions: {A}")
@@ -175,6 +179,11 @@ class QMixLearner:
         # STORED hidden states, eval mixer), so both unrolls go to side streams -- each occupies one
         # CTA pair -- and the main stream computes 4-5 underneath them.
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        # (re-)pack both networks' weights on THIS stream before the fork: a stale pack (first step, after
+        # load_models / load_state_dict) would otherwise be rebuilt on a side stream while the main stream's
+        # Q-head launch below reads the same buffer
+        agent.packed()
+        tgt_agent.packed()
         if dev.type == "cuda":
             cur = torch.cuda.current_stream(dev)
             if self._side_stream is None:

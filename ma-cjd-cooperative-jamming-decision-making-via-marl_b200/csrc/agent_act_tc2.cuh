@@ -1,7 +1,7 @@
 // Fused agent step on tcgen05 with CTA pairs (cta_group::2): 128 agent rows per 2-CTA cluster.
 //
-// Same computation as agent_forward_tc_kernel (agent_act_tc.cuh); what changes is how the
-// tensor cores are driven.  Measurements on the B200 (tools/tc_mma_rate.py) show that one
+// Same computation as agent_forward_kernel (agent_act.cuh) with the dense layers on the tensor cores.
+// Measurements on the B200 (tools/tc_mma_rate.py) show that one
 // tcgen05.mma costs the same cycles for M = 64 and M = 128, so a CTA that owns 64 rows wastes
 // half the pipe -- but 128 rows of TF32 hi + lo operand tiles do not fit one SM's shared
 // memory.  A CTA pair solves both: each CTA keeps its own 64 rows of operands and only HALF of
@@ -23,7 +23,7 @@
 //   issuer:   [actor.0 | fc1] x  ->  W_hr h, W_hz h, W_hn h  ->  actor.2 a1  ->  W_ir xf, W_iz xf, W_in xf  ->  q.0 h'
 //   epilogue: x tile -> E1 (a1) .............. -> E3 (xf), E2 (actor head P) ....... -> E4 (gates, h') -> E5 (Q, selection)
 #pragma once
-#include "agent_act_tc.cuh"
+#include "agent_tc_common.cuh"
 #ifndef MACJD_TEST_HOST_EMULATION
 #include <cuda.h>            // CUtensorMap (type and enums only; the encoder is fetched through the runtime)
 #endif
@@ -102,7 +102,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "memory");
     if (done) return;
   }
-  __trap();
+  watchdog_raise();
 }
 __device__ __forceinline__ void mma_tf32_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                 uint32_t accumulate) {
@@ -755,14 +755,14 @@ inline bool agent_tc2_supported(const macjd_agent_weights& w) {
 inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
   const size_t smem = agent_tc2_smem_bytes(a.w);
   // the opt-in is per device and sticky: ask once per device and size (an act call is latency-critical)
-  static size_t opted[64] = {};
-  const int dev = ctx->device & 63;
-  if (smem > opted[dev]) {
+  static PerDeviceMax opted;
+  if (!opted.covers(ctx->device, smem)) {
     if (cudaFuncSetAttribute(agent_forward_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(agent_forward_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return MACJD_ERR_CUDA;
-    opted[dev] = smem;
+    opted.record(ctx->device, smem);
   }
+  if (watchdog_arm(ctx->device) != MACJD_OK) return MACJD_ERR_CUDA;
   // TMA descriptor of the chunk buffer (a pure host-side encode; the driver entry point is looked up once)
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -792,6 +792,7 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
   return MACJD_OK;
 }
 
+#if defined(MACJD_TC_PROFILE) || defined(MACJD_DEBUG_TOOLS)   // tooling build only (tools/tc_mma_rate.py)
 // Micro-benchmark: like tc_mma_rate_kernel, for tcgen05.mma.cta_group::2 issued by the leader of a CTA pair.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tc2_mma_rate_kernel(int M, int N, int n, unsigned long long* out) {
   extern __shared__ __align__(128) unsigned char tc_smem[];
@@ -847,6 +848,8 @@ inline int tc2_mma_rate(const macjd_ctx* ctx, int M, int N, int n, unsigned long
   tc2_mma_rate_kernel<<<2, 128, 64 * 1024, (cudaStream_t)ctx->stream>>>(M, N, n, out_dev);
   return MACJD_OK;
 }
+
+#endif  // tooling build
 
 }  // namespace tc
 }  // namespace macjd

@@ -455,20 +455,19 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
     // columns staged in shared memory one worker is faster (48.0 vs 48.6 us per flushed step: no hand-over barriers)
     const bool two = !a.stage_tab && tab->n_radars >= 2 && smem2 <= kSmallBatchSmem;
     const size_t need = two ? smem2 : smem1;
-    static size_t opted[4][64] = {};
-    const int dev = ctx->device & 63, which = (two ? 2 : 0) + (a.stage_tab ? 1 : 0);
-    if (need > 48 * 1024 && need > opted[which][dev]) {
+    static PerDeviceMax opted[4];
+    const int dev = ctx->device, which = (two ? 2 : 0) + (a.stage_tab ? 1 : 0);
+    if (need > 48 * 1024 && !opted[which].covers(dev, need)) {
       const void* fn = two ? (a.stage_tab ? (const void*)env_step_kernel<2, true> : (const void*)env_step_kernel<2, false>)
                            : (a.stage_tab ? (const void*)env_step_kernel<1, true> : (const void*)env_step_kernel<1, false>);
       const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
       if (e != cudaSuccess) return MACJD_ERR_CUDA;
-      opted[which][dev] = need;
+      opted[which].record(dev, need);
     }
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    static const int no_pdl = getenv("MACJD_NO_PDL") ? atoi(getenv("MACJD_NO_PDL")) : 0;   // experiments
-    attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.gridDim = dim3(grid); cfg.stream = (cudaStream_t)ctx->stream; cfg.attrs = attr; cfg.numAttrs = 1;
     cfg.blockDim = dim3((two ? 3 : 2) * bs); cfg.dynamicSmemBytes = need;
     const cudaError_t err = two ? (a.stage_tab ? cudaLaunchKernelEx(&cfg, env_step_kernel<2, true>, a) : cudaLaunchKernelEx(&cfg, env_step_kernel<2, false>, a))

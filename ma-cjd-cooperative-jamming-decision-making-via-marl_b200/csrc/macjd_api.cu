@@ -1,16 +1,21 @@
 // C ABI of libmacjd_b200.so (declared in include/macjd.h).  Thin: validate, pick the
-// device, enqueue the kernels on the caller's stream, translate CUDA errors to status
-// codes.  No allocation, no synchronisation, no global mutable state.
+// device (and put the caller's current device back on return), enqueue the kernels on the
+// caller's stream, translate CUDA errors to status codes.  No allocation, no synchronisation.
+// Process-wide state is limited to caches of idempotent driver settings (the per-device
+// "shared-memory opt-in already requested" sizes: atomics, a lost race repeats a harmless
+// call), the lazily created side stream of the grouped host step (mutex) and the pipeline
+// watchdog word (macjd_common.cuh: a pinned host int the tensor-core kernels raise instead of
+// trapping); entry points are safe to call from several threads on disjoint buffers.
 #include "macjd_common.cuh"
 #include "env_step.cuh"
 #include "agent_act.cuh"
-#include "agent_act_tc.cuh"
 #include "agent_act_tc2.cuh"
 #include "replay.cuh"
 #include "learner.cuh"
 #include "tc05.cuh"
 
 #include <stdio.h>
+#include <mutex>
 #include <stdlib.h>
 #include <string.h>
 
@@ -29,15 +34,39 @@ int finish(const macjd_ctx* ctx, int status) {
   return MACJD_OK;
 }
 
-int enter(const macjd_ctx* ctx) {
-  if (!ctx) return MACJD_ERR_INVALID_ARG;
-  const cudaError_t err = cudaSetDevice(ctx->device);
-  if (err != cudaSuccess) {
-    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s", cudaGetErrorString(err));
-    return MACJD_ERR_CUDA;
+// Makes ctx->device current for the duration of one entry point and restores the caller's
+// device on every return path (the library must not move a PyTorch thread to another GPU).
+struct DeviceScope {
+  int prev = -1;
+  bool switched = false;
+  int status = MACJD_OK;
+  explicit DeviceScope(const macjd_ctx* ctx) {
+    if (!ctx) { status = MACJD_ERR_INVALID_ARG; return; }
+    cudaError_t err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != ctx->device) {
+      err = cudaSetDevice(ctx->device);
+      switched = err == cudaSuccess;
+    }
+    if (err != cudaSuccess) {
+      snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s", cudaGetErrorString(err));
+      status = MACJD_ERR_CUDA;
+      return;
+    }
+    // a tensor-core kernel of an EARLIER call gave up waiting on its pipeline (see macjd_common.cuh)
+    if (macjd::watchdog_tripped()) {
+      snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "tcgen05 pipeline wait timed out in an earlier launch; its outputs are invalid");
+      status = MACJD_ERR_CUDA;
+    }
   }
-  return MACJD_OK;
-}
+  ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+// (nested entry points -- the host-buffer calls invoke macjd_agent_forward / macjd_env_step -- find the
+// device already current and switch nothing)
+#define MACJD_ENTER(ctx)            \
+  DeviceScope macjd_scope_(ctx);    \
+  if (macjd_scope_.status != MACJD_OK) return macjd_scope_.status
 
 }  // namespace
 
@@ -77,20 +106,17 @@ size_t macjd_abi_sizeof(int which) {
 }
 
 int macjd_env_step(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   return finish(ctx, macjd::env_launch(ctx, tab, io, /*physics=*/1));
 }
 
 int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   return finish(ctx, macjd::env_launch(ctx, tab, io, /*physics=*/0));
 }
 
 int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   if (!w || !io) return MACJD_ERR_INVALID_ARG;
   if (io->path < 0 || io->path > 3 || io->part < 0 || io->part > 4) return MACJD_ERR_INVALID_ARG;
   if (io->n_rows == 0 && io->n_steps >= 1) return MACJD_OK;      // an empty batch is a no-op (its buffers have no address)
@@ -104,16 +130,14 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
     macjd::AgentArgs a;
     a.w = *w;
     a.io = *io;
-    // path 2: one CTA per 64 rows; path 3: CTA pairs (cta_group::2), 128 rows per pair;
-    // path 0 picks the pair kernel whenever it fits -- even for <= 64 rows (a pair MMA of M = 128,
-    // N = 128 takes 37 cycles against 68 for the single-CTA M = 64 one, and each CTA streams half
-    // the weights: 22 vs 33 us per step on the learner's 64-row unroll, tools/tc_small_m.py)
+    // path 3 / auto: the CTA-pair kernel (cta_group::2, 128 rows per pair) -- also for <= 64 rows (a pair MMA
+    // of M = 128, N = 128 takes 37 cycles against 68 for a single-CTA M = 64 one, and each CTA streams half
+    // the weights).  path 2 named round 1's single-CTA kernel, which the pair kernel superseded: unsupported.
+    if (io->path == 2) return MACJD_ERR_UNSUPPORTED;
     const bool pair_ok = macjd::tc::agent_tc2_supported(*w);
-    if ((io->path == 3 || io->part != 0) && !pair_ok) return MACJD_ERR_UNSUPPORTED;
-    if (io->part != 0 && io->path == 2) return MACJD_ERR_UNSUPPORTED;
-    if (io->path == 3 || (io->path == 0 && pair_ok))
-      return finish(ctx, macjd::tc::agent_tc2_launch(ctx, a));
-    return finish(ctx, macjd::tc::agent_tc_launch(ctx, a));
+    if (pair_ok) return finish(ctx, macjd::tc::agent_tc2_launch(ctx, a));
+    if (io->path == 3 || io->part != 0) return MACJD_ERR_UNSUPPORTED;
+    // (auto with dims the pair kernel does not take: the FP32 SIMT kernel below)
   }
 #endif
   if (io->path >= 2 || io->part != 0) return MACJD_ERR_UNSUPPORTED;
@@ -187,8 +211,8 @@ T* device_alias(T* host_ptr, size_t bytes, bool write, uint32_t flags) {
 
 int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io,
                          const macjd_act_host* host) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
+  int st = MACJD_OK;
   if (!w || !io || !host) return MACJD_ERR_INVALID_ARG;
   if (io->n_steps != 1 || io->n_rows < 0) return MACJD_ERR_INVALID_ARG;
   if (!host->obs || !host->actions || !host->power || !io->obs || !io->actions || !io->power) return MACJD_ERR_INVALID_ARG;
@@ -222,8 +246,8 @@ int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, con
 
 int macjd_env_step_host(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io,
                         const macjd_env_host* host) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
+  int st = MACJD_OK;
   if (!tab || !io || !host) return MACJD_ERR_INVALID_ARG;
   if (!host->act_d || !host->act_p || !io->act_d || !io->act_p) return MACJD_ERR_INVALID_ARG;
   if ((host->reward && !io->reward) || (host->terminated && !io->terminated) || (host->obs && !io->obs) ||
@@ -263,7 +287,10 @@ namespace {
 struct HostGroupStreams { cudaStream_t side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool failed = false; };
 HostGroupStreams* host_group_streams(int dev) {
   static HostGroupStreams all[64];
-  HostGroupStreams& h = all[dev & 63];
+  static std::mutex mu;
+  if (dev < 0 || dev >= 64) return nullptr;         // (no grouping on devices beyond the table)
+  std::lock_guard<std::mutex> lock(mu);
+  HostGroupStreams& h = all[dev];
   if (!h.side && !h.failed) {
     if (cudaStreamCreateWithFlags(&h.side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -295,8 +322,8 @@ T* offset_ptr(T* p, size_t elems) { return p ? p + elems : nullptr; }
 int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
                             const macjd_act_host* ahost, const macjd_env_tables* tab, const macjd_env_io* eio,
                             const macjd_env_host* ehost) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
+  int st = MACJD_OK;
   if (!w || !aio || !ahost || !tab || !eio || !ehost) return MACJD_ERR_INVALID_ARG;
   if (aio->n_steps != 1 || aio->n_rows < 0 || tab->n_envs < 0 || tab->n_jammers < 1) return MACJD_ERR_INVALID_ARG;
   if ((int64_t)aio->n_rows != (int64_t)tab->n_envs * tab->n_jammers) return MACJD_ERR_INVALID_ARG;
@@ -412,8 +439,7 @@ int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, 
 
 int macjd_replay_copy(const macjd_ctx* ctx, const macjd_copy_desc* descs_host, int32_t n_keys, const int32_t* idx,
                       int32_t n_eps, int32_t index_on_src) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   return finish(ctx, macjd::replay_copy(ctx, descs_host, n_keys, idx, n_eps, index_on_src));
 }
 
@@ -428,8 +454,7 @@ size_t macjd_mixer_workspace_floats(const macjd_mixer_dims* dims) {
 
 int macjd_mixer_forward(const macjd_ctx* ctx, const macjd_mixer_dims* dims, const macjd_mixer_params* w, const float* q,
                         const float* states, float* q_tot, float* workspace, size_t workspace_floats) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   if (!mixer_dims_ok(dims) || !w || !q || !states || !q_tot) return MACJD_ERR_INVALID_ARG;
   return finish(ctx, macjd::mixer_forward((cudaStream_t)ctx->stream, *dims, *w, q, states, q_tot, workspace, workspace_floats));
 }
@@ -437,8 +462,7 @@ int macjd_mixer_forward(const macjd_ctx* ctx, const macjd_mixer_dims* dims, cons
 int macjd_mixer_backward(const macjd_ctx* ctx, const macjd_mixer_dims* dims, const macjd_mixer_params* w, const float* q,
                          const float* dq_tot, float* workspace, size_t workspace_floats, const macjd_mixer_params* grads,
                          float* dq) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   if (!mixer_dims_ok(dims) || !w || !q || !dq_tot || !grads) return MACJD_ERR_INVALID_ARG;
   return finish(ctx, macjd::mixer_backward((cudaStream_t)ctx->stream, *dims, *w, q, dq_tot, workspace, workspace_floats, *grads, dq));
 }
@@ -450,8 +474,7 @@ size_t macjd_qhead_scratch_floats(const macjd_qhead_dims* dims) {
 
 int macjd_qhead_forward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
                         const float* hidden, const int32_t* a_d, const float* a_c, float* q, float* hid) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   if (!dims || !w || !hidden || !a_d || !a_c || !q || !hid || dims->n_rows < 0) return MACJD_ERR_INVALID_ARG;
   if (dims->hidden != w->hidden || dims->n_actions != w->n_actions) return MACJD_ERR_INVALID_ARG;
   return finish(ctx, macjd::qhead_forward((cudaStream_t)ctx->stream, *dims, *w, hidden, a_d, a_c, q, hid));
@@ -460,8 +483,7 @@ int macjd_qhead_forward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, cons
 int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
                          const float* hidden, const int32_t* a_d, const float* a_c, float* hid, const float* dq,
                          float* g_w1, float* g_b1, float* g_w2, float* g_b2, float* scratch, size_t scratch_floats) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   if (!dims || !w || !hidden || !a_d || !a_c || !hid || !dq || !g_w1 || !g_b1 || !g_w2 || !g_b2) return MACJD_ERR_INVALID_ARG;
   if (dims->hidden != w->hidden || dims->n_actions != w->n_actions) return MACJD_ERR_INVALID_ARG;
   return finish(ctx, macjd::qhead_backward((cudaStream_t)ctx->stream, *dims, *w, hidden, a_d, a_c, hid, dq, g_w1, g_b1,
@@ -469,8 +491,7 @@ int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, con
 }
 
 int macjd_gather_q(const macjd_ctx* ctx, int32_t n, int32_t n_actions, const float* q_all, const int32_t* idx, float* out) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   if (n < 0 || n_actions < 1 || !q_all || !idx || !out) return MACJD_ERR_INVALID_ARG;
   if (n == 0) return MACJD_OK;
   MACJD_LAUNCH(macjd::gather_q_kernel, dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)ctx->stream, q_all,
@@ -483,8 +504,7 @@ size_t macjd_td_scratch_floats(int32_t n_rows) { return n_rows > 0 ? macjd::td_s
 int macjd_td_loss(const macjd_ctx* ctx, int32_t n_rows, const float* q_tot, const float* tq_tot, const float* reward,
                   const uint8_t* terminated, const uint8_t* filled, float gamma, float* dq_tot, float* targets,
                   float* sums, float* scratch, size_t scratch_floats) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   if (!q_tot || !tq_tot || !reward || !terminated || !filled || !dq_tot || !sums) return MACJD_ERR_INVALID_ARG;
   return finish(ctx, macjd::td_loss((cudaStream_t)ctx->stream, n_rows, q_tot, tq_tot, reward, terminated, filled, gamma,
                                     dq_tot, targets, sums, scratch, scratch_floats));
@@ -495,8 +515,7 @@ size_t macjd_opt_scratch_floats(void) { return macjd::opt_scratch_floats(); }
 int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, const float* grad, float* m, float* v,
                     const float* sums, float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
                     float* scal, float* scratch, size_t scratch_floats) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
   if (!tensors || !grad || !m || !v || !sums || !scal) return MACJD_ERR_INVALID_ARG;
   return finish(ctx, macjd::clip_adam((cudaStream_t)ctx->stream, *tensors, grad, m, v, sums, max_norm, lr, beta1, beta2,
                                       eps, step, scal, scratch, scratch_floats));
@@ -504,8 +523,7 @@ int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, cons
 
 int macjd_tc_gemm_selftest(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
                            float* D) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
 #ifdef MACJD_TEST_HOST_EMULATION
   (void)M; (void)N; (void)K; (void)A; (void)B; (void)D;
   return MACJD_ERR_UNSUPPORTED;   // tensor cores cannot be emulated on the host
@@ -515,8 +533,15 @@ int macjd_tc_gemm_selftest(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K
 #endif
 }
 
+int macjd_clear_pipeline_fault(void) {
+#ifndef MACJD_TEST_HOST_EMULATION
+  if (macjd::g_watchdog_seen) *reinterpret_cast<volatile int*>(macjd::g_watchdog_seen) = 0;
+#endif
+  return MACJD_OK;
+}
+
 // k-extent of one packed weight chunk the tcgen05 agent kernel was built for (0: no tensor-core path).
-__attribute__((visibility("default"))) int macjd_agent_tc_chunk_k(void) {
+int macjd_agent_tc_chunk_k(void) {
 #ifdef MACJD_TEST_HOST_EMULATION
   return 0;
 #else
@@ -524,6 +549,10 @@ __attribute__((visibility("default"))) int macjd_agent_tc_chunk_k(void) {
 #endif
 }
 
+// ---- development aids (tools/*.py): phase timestamps and tensor-pipe micro-benchmarks.  Not part of the ABI and
+// not in the product library: compiled only into the tooling build (-DMACJD_TC_PROFILE or -DMACJD_DEBUG_TOOLS,
+// tools/_prof/build_prof.py).
+#if defined(MACJD_TC_PROFILE) || defined(MACJD_DEBUG_TOOLS)
 // Debug aid (not part of the documented ABI): phase timestamps of the tcgen05 agent kernel when
 // the library was compiled with -DMACJD_TC_PROFILE; zeros otherwise.
 __attribute__((visibility("default"))) int macjd_debug_tc_profile(unsigned long long* out_host, int n) {
@@ -545,8 +574,7 @@ __attribute__((visibility("default"))) int macjd_debug_env_profile(unsigned long
 // Debug aid: tcgen05.mma issue / completion rate (cycles) for n back-to-back M x N x 8 TF32 MMAs.
 __attribute__((visibility("default"))) int macjd_debug_tc_mma_rate(const macjd_ctx* ctx, int M, int N, int n,
                                                                   unsigned long long* out_dev) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
 #ifdef MACJD_TEST_HOST_EMULATION
   (void)M; (void)N; (void)n; (void)out_dev;
   return MACJD_ERR_UNSUPPORTED;
@@ -557,8 +585,7 @@ __attribute__((visibility("default"))) int macjd_debug_tc_mma_rate(const macjd_c
 
 __attribute__((visibility("default"))) int macjd_debug_tc_mma_rate_multi(const macjd_ctx* ctx, int M, int N, int n, int issuers,
                                                                         unsigned long long* out_dev) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
 #ifdef MACJD_TEST_HOST_EMULATION
   (void)M; (void)N; (void)n; (void)issuers; (void)out_dev;
   return MACJD_ERR_UNSUPPORTED;
@@ -570,8 +597,7 @@ __attribute__((visibility("default"))) int macjd_debug_tc_mma_rate_multi(const m
 // Same, for tcgen05.mma.cta_group::2 issued by the leader of a 2-CTA cluster (M = pair rows: 128 or 256).
 __attribute__((visibility("default"))) int macjd_debug_tc2_mma_rate(const macjd_ctx* ctx, int M, int N, int n,
                                                                    unsigned long long* out_dev) {
-  int st = enter(ctx);
-  if (st != MACJD_OK) return st;
+  MACJD_ENTER(ctx);
 #ifdef MACJD_TEST_HOST_EMULATION
   (void)M; (void)N; (void)n; (void)out_dev;
   return MACJD_ERR_UNSUPPORTED;
@@ -579,5 +605,7 @@ __attribute__((visibility("default"))) int macjd_debug_tc2_mma_rate(const macjd_
   return finish(ctx, macjd::tc::tc2_mma_rate(ctx, M, N, n, out_dev));
 #endif
 }
+
+#endif  // tooling build
 
 }  // extern "C"

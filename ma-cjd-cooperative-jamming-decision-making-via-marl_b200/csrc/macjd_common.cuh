@@ -6,6 +6,7 @@
 #include "cuda_emul.h"
 #else
 #include <cuda_runtime.h>
+#include <atomic>
 // Every kernel launched through MACJD_LAUNCH starts with grid_dependency_wait() (below), so it may be
 // launched as a programmatic dependent of its predecessor in the stream: its blocks are scheduled while
 // the predecessor drains, the launch latency of the learner's ~60 short kernels overlaps, and stream
@@ -95,5 +96,73 @@ __device__ __forceinline__ void grid_launch_dependents() {
 }
 
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------- pipeline watchdog
+// The tensor-core kernels wait on mbarriers with a bound.  A wait that runs out (a peer CTA
+// that never arrives: preemption, a debugger, a bug) must not kill the CUDA context -- the
+// library's contract is status codes -- so instead of trapping the thread raises one word of
+// page-locked host memory and carries on (every later wait is bounded too, so the kernel
+// ends; its outputs are garbage).  The next entry point sees the word and returns
+// MACJD_ERR_CUDA (macjd_api.cu: DeviceScope).  One word per process, created on first use.
+#ifndef MACJD_TEST_HOST_EMULATION
+inline int* watchdog_host_word() {
+  static int* word = [] {
+    int* p = nullptr;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&p), sizeof(int), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+      cudaGetLastError();
+      return static_cast<int*>(nullptr);
+    }
+    *p = 0;
+    return p;
+  }();                       // (thread-safe: C++11 static initialisation)
+  return word;
+}
+inline int* g_watchdog_seen = nullptr;       // set once some launch has asked for the word (no allocation on plain calls)
+inline bool watchdog_tripped() {
+  int* w = g_watchdog_seen;
+  return w && *reinterpret_cast<volatile int*>(w) != 0;
+}
+inline int* watchdog_device_word() {       // page-locked + unified addressing: the host pointer is the device pointer
+  int* w = watchdog_host_word();
+  g_watchdog_seen = w;
+  return w;
+}
+// set on a device the first time one of its tensor-core kernels is launched (watchdog_arm)
+__device__ int* g_watchdog_dev = nullptr;
+__device__ __forceinline__ void watchdog_raise() {
+  int* word = g_watchdog_dev;
+  if (word) { *reinterpret_cast<volatile int*>(word) = 1; __threadfence_system(); }
+}
+#else
+inline bool watchdog_tripped() { return false; }
+#endif
+
+// ---------------------------------------------------------------- per-device launch caches
+// "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) was already requested for >= n bytes on device d":
+// the attribute is sticky per device and asking costs microseconds on a latency-critical call.  Lock-free;
+// two threads racing on the first call both make the (idempotent) request.
+#ifndef MACJD_TEST_HOST_EMULATION
+constexpr int kMaxCachedDevices = 64;
+struct PerDeviceMax {
+  std::atomic<size_t> v[kMaxCachedDevices];
+  bool covers(int dev, size_t need) const {
+    return dev >= 0 && dev < kMaxCachedDevices && v[dev].load(std::memory_order_relaxed) >= need;
+  }
+  void record(int dev, size_t need) {
+    if (dev < 0 || dev >= kMaxCachedDevices) return;       // (uncached devices ask every time)
+    size_t cur = v[dev].load(std::memory_order_relaxed);
+    while (cur < need && !v[dev].compare_exchange_weak(cur, need, std::memory_order_relaxed)) {}
+  }
+};
+// the pipeline watchdog word is published to a device once (a synchronous 8-byte symbol copy)
+inline int watchdog_arm(int dev) {
+  static PerDeviceMax armed;
+  if (armed.covers(dev, 1)) return MACJD_OK;
+  int* w = watchdog_device_word();
+  if (w && cudaMemcpyToSymbol(g_watchdog_dev, &w, sizeof(w)) != cudaSuccess) return MACJD_ERR_CUDA;
+  armed.record(dev, 1);
+  return MACJD_OK;
+}
+#endif
 
 }  // namespace macjd

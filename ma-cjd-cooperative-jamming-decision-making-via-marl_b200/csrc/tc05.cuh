@@ -96,7 +96,9 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// Bounded wait: a wrong descriptor must fail loudly (trap), never hang the GPU.
+// Bounded wait: a wrong descriptor or a peer that never arrives must neither hang the GPU nor kill the
+// context: the thread raises the watchdog word (macjd_common.cuh) and carries on; the next library call
+// reports MACJD_ERR_CUDA.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
 #pragma unroll 1   // (nvcc unrolls this spin loop 32x otherwise: a third of the pair kernel's code)
@@ -113,7 +115,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     if (done) return;
   }
-  __trap();
+  watchdog_raise();
 }
 
 // ---- TMEM -> registers: 8 consecutive columns of this thread's lane
@@ -291,6 +293,7 @@ inline int tc_gemm_selftest(const macjd_ctx* ctx, int M, int N, int K, const flo
   return MACJD_OK;
 }
 
+#if defined(MACJD_TC_PROFILE) || defined(MACJD_DEBUG_TOOLS)   // tooling build only (tools/tc_mma_rate.py)
 // ---------------------------------------------------------------------------------------
 // Micro-benchmark: issue `n` back-to-back tcgen05.mma (kind::tf32, SS) of shape M x N x 8 on
 // garbage operands; out[0] = cycles to issue them, out[1] = cycles until the commit fires.
@@ -384,6 +387,8 @@ inline int tc_mma_rate(const macjd_ctx* ctx, int M, int N, int n, unsigned long 
   tc_mma_rate_kernel<<<1, 128, 64 * 1024, (cudaStream_t)ctx->stream>>>(M, N, n, out_dev);
   return MACJD_OK;
 }
+
+#endif  // tooling build
 
 }  // namespace tc
 }  // namespace macjd

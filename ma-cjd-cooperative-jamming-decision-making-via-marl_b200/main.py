@@ -3,24 +3,39 @@
 The reference's loop is  run one episode -> store -> (sample -> train) x episode_length // train_interval ->
 log -> checkpoint  on one environment.  Here one iteration advances ``n_envs`` episodes together
 (``BatchedEpisodeRunner``: two fused kernels per timestep, trajectories written straight into the replay
-layout) and stores them in the HBM replay ring; the learner part of the iteration is the reference's:
-``episode_length // train_interval`` train steps on uniformly sampled batches once the buffer holds
-``batch_size`` episodes and ``total_steps > start_training_steps``.  Counters keep the reference's meaning --
-``episode`` counts episodes, ``total_steps`` counts single-environment steps (main.py:196-198) -- so
-schedules written for the reference (``total_env_steps``, ``start_training_steps``, ``save_interval``) carry
-over; the exploration schedule advances one tick per batched timestep, ``BatchedEpisodeRunner.t_env``
-(mac.py:96 reads the runner's counter there too).  Console lines and TensorBoard tags are the reference's
-(main.py:232-277); checkpoints are ``learner.save_models`` directories (agent.pth / qmix_net.pth /
-optimizer.pth, interchangeable with the reference's, main.py:280-286).
+layout) and stores them in the HBM replay ring.
+
+Schedules keep the reference's meaning, per unit of EXPERIENCE:
+  * ``episode`` counts episodes and ``total_steps`` single-environment steps (main.py:196-198), so
+    ``total_env_steps``, ``start_training_steps``, ``save_interval`` carry over;
+  * the exploration schedule is annealed on ``runner.t_env`` = total single-environment steps, as in the
+    reference (mac.py:96): a batched timestep advances it by ``n_envs``;
+  * the update-to-data ratio is the reference's: one train step per ``train_interval`` environment steps
+    (main.py:216: ``episode_length // train_interval`` per episode), i.e. ``n_envs * (T // train_interval)``
+    train steps per rollout.  ``args.updates_per_env_step`` (float) overrides the ratio and
+    ``args.train_steps_per_rollout`` (int) fixes the count -- at thousands of envs the reference's ratio makes
+    the loop learner-bound by three orders of magnitude, and a user may not want that.
+Console lines and TensorBoard tags are the reference's (main.py:232-277); checkpoints are
+``learner.save_models`` directories (agent.pth / qmix_net.pth / optimizer.pth, interchangeable with the
+reference's, main.py:280-286).
+
+``pipeline=True``: rollout k runs on one stream with a frozen ACTING copy of the agent
+while the learner trains on another stream from the ring as it stood after rollout k - 1; the copy is
+refreshed (a device copy) and the ring slots are handed over between rollouts with events, statistics are
+read back once per log line (``lazy_stats``), and no train step synchronises with the host.  The acting
+policy therefore lags the learner by one rollout -- the usual actor / learner split; ``pipeline=False`` is
+the reference's strict alternation (act with the latest weights, then train).
 
 Not in the reference: ``evaluate`` (greedy episodes with ``test_mode=True``; the reference's
 ``test_interval`` / ``test_nepisodes`` keys of config/default.yaml:81-83 are never read by its loop) and
-``n_envs`` / ``spec`` for the batched environment.
+``n_envs`` / ``spec`` for the batched environment.  The reference's command line is not rebuilt
+(out of scope); ``tools/train_cli.py`` is a development convenience.
 
 Everything on the device goes through the CUDA library; there is no CPU fallback behind this loop.
 """
 from __future__ import annotations
 
+import copy
 import os
 import time
 from collections import deque
@@ -32,7 +47,7 @@ import torch
 import yaml
 
 from .core.mac import BasicMAC
-from .core.qmix import QMixLearner
+from .core.qmix import QMixLearner, TRAINED_AGENT_KEYS
 from .runners.episode_runner import BatchedEpisodeRunner
 from .simulation.environment import ElectromagneticEnvironment
 from .utils.replay_buffer import EpisodeReplayBuffer
@@ -77,13 +92,26 @@ def _mean(q):
     return float(np.mean(q)) if len(q) else 0.0
 
 
-def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=print, use_graph=False, _lib=None):
+def train_steps_for_rollout(args, n_envs, episode_steps):
+    """How many train steps follow a rollout of ``n_envs`` episodes of ``episode_steps`` steps: the
+    reference's update-to-data ratio (main.py:216) unless the config overrides it."""
+    fixed = getattr(args, "train_steps_per_rollout", None)
+    if fixed is not None:
+        return max(0, int(fixed))
+    ratio = getattr(args, "updates_per_env_step", None)
+    if ratio is not None:
+        return max(0, int(round(float(ratio) * n_envs * episode_steps)))
+    return n_envs * (episode_steps // max(1, args.train_interval))
+
+
+def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=print, use_graph=False, pipeline=False,
+        _lib=None):
     """main.py:72-289 on the batched path.  ``args`` is the reference's config namespace (missing keys take
     ``DEFAULTS``); ``n_envs`` (or ``args.n_envs``) episodes advance per iteration, from ``sim_config_path``
     (the reference's scenario YAML replicated) or a ``ScenarioSpec``.  ``writer``: a TensorBoard
     ``SummaryWriter``-like object, ``None`` = create one under logs/<test_name>/ as the reference does,
-    ``False`` = no TensorBoard.  Returns the final counters and the last logged averages.
-    (``_lib``: the host-emulation build of the kernels, tests only.)"""
+    ``False`` = no TensorBoard.  ``pipeline``: see the module docstring.  Returns the final counters and the
+    last logged averages.  (``_lib``: the host-emulation build of the kernels, tests only.)"""
     for k, v in DEFAULTS.items():
         if not hasattr(args, k):
             setattr(args, k, v)
@@ -91,6 +119,7 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
     requested = str(getattr(args, "device_request", getattr(args, "device", "cuda"))).lower()
     if _lib is not None:
         args.device, args.use_cuda = "cpu", False                 # kernels compiled for the host (tests/emul)
+        pipeline = False
     else:
         if not requested.startswith("cuda"):
             raise RuntimeError("macjd_b200.main.run needs a CUDA device (no CPU path behind it)")
@@ -114,7 +143,10 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
         writer = None
 
     # main.py:133-160: components
-    n_envs = int(n_envs or getattr(args, "n_envs", 1024))
+    if n_envs is None and getattr(args, "n_envs", None) is None and spec is None:
+        # a rollout should be a small part of the step budget (the loop checks the budget between rollouts)
+        n_envs = int(min(1024, max(1, args.total_env_steps // (8 * max(1, getattr(args, "episode_limit", 100))))))
+    n_envs = int(n_envs or getattr(args, "n_envs", None) or 1)
     if spec is not None:
         env = ElectromagneticEnvironment(args, spec=spec, device=args.device, seed=args.seed, _lib=_lib)
     else:
@@ -131,32 +163,113 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
     mac = BasicMAC(input_shape=args.obs_shape, args=args, _lib=_lib)
     if args.use_cuda:
         mac.cuda()
-    # every agent observes the global state (environment.py:512-522): the ring keeps the state only
-    buffer = EpisodeReplayBuffer(args=args, device=args.device, _lib=_lib,
-                                 shared_obs=getattr(args, "replay_shared_obs", args.obs_shape == args.state_shape))
+    # The ring drops `obs` only when the ENVIRONMENT says every agent observes the replicated global state
+    # (environment.py:512-522; ElectromagneticEnvironment.obs_is_replicated_state) or the config asks for it:
+    # equal widths alone do not prove equal contents.
+    shared = getattr(args, "replay_shared_obs", None)
+    if shared is None:
+        shared = bool(getattr(env, "obs_is_replicated_state", False)) and args.obs_shape == args.state_shape
+    buffer = EpisodeReplayBuffer(args=args, device=args.device, _lib=_lib, shared_obs=bool(shared))
     learner = QMixLearner(mac, args=args, _lib=_lib)
-    runner = BatchedEpisodeRunner(env=env, mac=mac, buffer=buffer, args=args)
+    pipeline = bool(pipeline) and args.use_cuda
+    # pipelined: the rollout acts with a frozen copy of the agent, refreshed between rollouts
+    act_mac = copy.deepcopy(mac) if pipeline else mac
+    runner = BatchedEpisodeRunner(env=env, mac=act_mac, buffer=buffer, args=args)
+    if pipeline:
+        dev = torch.device(args.device)
+        roll_stream, learn_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        ev_weights, ev_gathered, ev_stored = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        main_stream = torch.cuda.current_stream(dev)
+        roll_stream.wait_stream(main_stream)
+        learn_stream.wait_stream(main_stream)
+        ev_weights.record(learn_stream)
+        ev_gathered.record(learn_stream)
+
+    def sync_acting_copy():
+        """Acting copy <- learner's agent: only fc2_q_head is ever trained (core/qmix.py:178), so four raw
+        device copies and the Q-head re-pack (no full re-pack, no version bump on the acting parameters)."""
+        src = dict(mac.agent.named_parameters())
+        with torch.no_grad():
+            for k, p_ in act_mac.agent.named_parameters():
+                if k in TRAINED_AGENT_KEYS:
+                    p_.data.copy_(src[k].data)
+        act_mac.agent.packed()
+        act_mac.agent.packed_qhead()
 
     start_time = last_log_time = time.time()
     episode = total_steps = train_steps = 0
     last_test_steps = 0
-    n_train = args.episode_limit // max(1, args.train_interval)
+    n_train_nominal = train_steps_for_rollout(args, n_envs, args.episode_limit)
     stats = {k: deque(maxlen=args.log_interval) for k in
              ("episode_return", "episode_length", "avg_step_reward", "reward_r_d", "reward_r_p", "reward_r_j",
               "avg_power", "action_dist")}
-    stats.update({k: deque(maxlen=args.log_interval * max(1, n_train)) for k in
-                  ("loss", "grad_norm", "eval_qtot_avg", "target_qtot_avg")})
+    stat_keys = ("loss", "grad_norm", "eval_qtot_avg", "target_qtot_avg")
+    stats.update({k: deque(maxlen=args.log_interval * max(1, n_train_nominal)) for k in stat_keys})
+    pending_stats = []                 # lazily read train statistics: (device tensor [4], total_steps at that time)
     last_logged, last_eval = {}, None
 
     def scalar(tag, value, step):
         if writer is not None:
             writer.add_scalar(tag, value, step)
 
+    def flush_train_stats():
+        """One read-back for every train step since the last flush (pipelined mode)."""
+        if not pending_stats:
+            return
+        rows = torch.stack([t for t, _ in pending_stats]).tolist()
+        by_step = {}
+        for (_, at), r in zip(pending_stats, rows):
+            for k, v in zip(stat_keys, r):
+                stats[k].append(v)
+            by_step.setdefault(at, []).append(r[0])
+        for at, losses in by_step.items():
+            scalar("Loss/train_episode_avg", float(np.mean(losses)), at)
+        pending_stats.clear()
+
+    def train_phase(n_steps, at_steps):
+        count, loss_sum = 0, 0.0
+        for _ in range(n_steps):
+            batch = buffer.sample(args.batch_size, time_major=True)
+            if batch is None:
+                continue
+            if pipeline:
+                ts = learner.train(batch, {"total_steps": at_steps}, lazy_stats=True, check_actions=False)
+                pending_stats.append((ts["stats_tensor"], at_steps))
+            else:
+                ts = learner.train(batch, {"total_steps": at_steps})
+                for k in stat_keys:
+                    stats[k].append(ts[k])
+                loss_sum += ts["loss"]
+            count += 1
+        if count and not pipeline:
+            scalar("Loss/train_episode_avg", loss_sum / count, at_steps)
+        return count
+
     log("Starting training...")
     while total_steps < args.total_env_steps:
-        # ---- one rollout: n_envs episodes (main.py:193-198)
-        run_info = runner.run(test_mode=False, use_graph=use_graph)
         episodes_before = episode
+        will_train = buffer.current_size >= args.batch_size and total_steps > args.start_training_steps
+        if pipeline:
+            # ---- rollout k on roll_stream with the acting copy, train on learn_stream from the ring as of k - 1
+            with torch.cuda.stream(roll_stream):
+                roll_stream.wait_event(ev_weights)              # the learner's weights of the previous phase are final
+                sync_acting_copy()
+                runner.reset()
+                for t in range(args.episode_limit):
+                    runner.step(t)
+            if will_train:
+                with torch.cuda.stream(learn_stream):
+                    learn_stream.wait_event(ev_stored)          # ring slots written by the previous store
+                    train_steps += train_phase(train_steps_for_rollout(args, n_envs, args.episode_limit), total_steps)
+                    ev_gathered.record(learn_stream)            # (every gather of this phase is enqueued before this)
+                    ev_weights.record(learn_stream)
+            with torch.cuda.stream(roll_stream):
+                roll_stream.wait_event(ev_gathered)             # the store may overwrite slots the learner sampled
+                run_info = runner.finish_run(store=True)
+                ev_stored.record(roll_stream)
+        else:
+            # ---- one rollout: n_envs episodes (main.py:193-198)
+            run_info = runner.run(test_mode=False, use_graph=use_graph)
         episode += n_envs
         current_episode_steps = run_info["episode_length"]
         total_steps += current_episode_steps * n_envs
@@ -169,27 +282,20 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
         stats["avg_power"].append(run_info.get("avg_power_overall", 0))
         stats["action_dist"].append(run_info["action_distribution"])
 
-        # ---- learner (main.py:212-228)
-        if buffer.current_size >= args.batch_size and total_steps > args.start_training_steps:
-            loss_sum, count = 0.0, 0
-            for _ in range(current_episode_steps // max(1, args.train_interval)):
-                batch = buffer.sample(args.batch_size, time_major=True)
-                if batch is None:
-                    continue
-                ts = learner.train(batch, {"total_steps": total_steps})
-                for k in ("loss", "grad_norm", "eval_qtot_avg", "target_qtot_avg"):
-                    stats[k].append(ts[k])
-                loss_sum += ts["loss"]
-                count += 1
-            train_steps += count
-            if count:
-                scalar("Loss/train_episode_avg", loss_sum / count, total_steps)
+        # ---- learner (main.py:212-228), strict alternation
+        if not pipeline and buffer.current_size >= args.batch_size and total_steps > args.start_training_steps:
+            train_steps += train_phase(train_steps_for_rollout(args, n_envs, current_episode_steps), total_steps)
 
         # ---- greedy evaluation (not in the reference's loop; its config names the two keys)
         if getattr(args, "test_nepisodes", 0) and getattr(args, "test_interval", 0) and \
                 total_steps - last_test_steps >= args.test_interval:
             last_test_steps = total_steps
+            if pipeline:
+                torch.cuda.synchronize(dev)
+                sync_acting_copy()
             last_eval = evaluate(runner, args.test_nepisodes)
+            if pipeline:                                          # the evaluation ran on the caller's stream
+                roll_stream.wait_stream(main_stream)
             log(f"  Test ({last_eval['n_episodes']} greedy eps): Return {last_eval['episode_return']:.2f} | "
                 f"r_d/r_p/r_j {last_eval['avg_r_d']:.4f} / {last_eval['avg_r_p']:.4f} / {last_eval['avg_r_j']:.4f}")
             scalar("Test/Avg_Return", last_eval["episode_return"], total_steps)
@@ -199,6 +305,7 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
         # ---- logging (main.py:231-277): same lines, same tags
         now = time.time()
         if now - last_log_time >= args.log_interval_seconds or total_steps >= args.total_env_steps:
+            flush_train_stats()
             dist = np.mean(np.array(stats["action_dist"]), axis=0) if stats["action_dist"] else np.zeros(args.n_actions)
             L = last_logged = {
                 "avg_return": _mean(stats["episode_return"]), "avg_length": _mean(stats["episode_length"]),
@@ -217,14 +324,14 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
             log(f"  Avg Power: {L['avg_power']:.3f} | Action Dist: [{' / '.join(f'{p:.2f}' for p in dist)}] "
                 f"(0=Idle, 1=S0, 2=D0, ...)")
             log(f"  Buffer Size: {len(buffer)}")
-            log(f"  Epsilon: {mac.action_selector.epsilon:.3f}")
+            log(f"  Epsilon: {act_mac.action_selector.epsilon:.3f}")
             for tag, key in (("Perf/Avg_Return", "avg_return"), ("Perf/Avg_Length", "avg_length"),
                              ("Perf/Avg_Step_Reward", "avg_step_reward"), ("Loss/train_avg", "avg_loss"),
                              ("Stats/grad_norm", "avg_grad_norm"), ("QValues/eval_qtot_avg", "avg_eval_qtot"),
                              ("QValues/target_qtot_avg", "avg_target_qtot"), ("Rewards/r_d_avg", "avg_r_d"),
                              ("Rewards/r_p_avg", "avg_r_p"), ("Rewards/r_j_avg", "avg_r_j"), ("Perf/Avg_Power", "avg_power")):
                 scalar(tag, L[key], total_steps)
-            scalar("Params/Epsilon", mac.action_selector.epsilon, total_steps)
+            scalar("Params/Epsilon", act_mac.action_selector.epsilon, total_steps)
             scalar("Params/Buffer_Size", len(buffer), total_steps)
             for a, p in enumerate(dist):
                 scalar(f"ActionDist/Action_{a}", p, total_steps)
@@ -236,31 +343,19 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
             save_dir = os.path.join(args.save_model_dir, test_name, f"step_{total_steps}")
             os.makedirs(save_dir, exist_ok=True)
             log(f"Saving model to {save_dir}")
+            if pipeline:
+                learn_stream.synchronize()
             learner.save_models(save_dir)
 
+    if pipeline:
+        torch.cuda.synchronize(dev)
+        main_stream.wait_stream(roll_stream)
+        main_stream.wait_stream(learn_stream)
+        flush_train_stats()
     runner.close_env()
     if own_writer:
         writer.close()
     log("Training finished.")
     return {"episodes": episode, "total_steps": total_steps, "train_steps": train_steps, "time_s": time.time() - start_time,
-            "last_logged": last_logged, "last_eval": last_eval, "learner": learner, "runner": runner, "buffer": buffer}
-
-
-if __name__ == "__main__":
-    import argparse
-    ap = argparse.ArgumentParser(description="QMix / MP-DQN training on the batched device-resident path")
-    ap.add_argument("--config", default=None, help="name of a YAML file under --config-dir (reference format); default: built-in defaults")
-    ap.add_argument("--config-dir", default="config")
-    ap.add_argument("--sim-config", default=None, help="scenario YAML (reference format); default: the reference's default scenario")
-    ap.add_argument("--n-envs", type=int, default=1024)
-    ap.add_argument("--total-env-steps", type=int, default=None)
-    ap.add_argument("--no-tensorboard", action="store_true")
-    a = ap.parse_args()
-    cfg = load_config(a.config, a.config_dir) if a.config else default_config()
-    if a.total_env_steps is not None:
-        cfg.total_env_steps = a.total_env_steps
-    if a.sim_config is None:
-        from .simulation.scenario import default_spec
-        run(cfg, spec=default_spec(a.n_envs), writer=False if a.no_tensorboard else None)
-    else:
-        run(cfg, n_envs=a.n_envs, sim_config_path=a.sim_config, writer=False if a.no_tensorboard else None)
+            "last_logged": last_logged, "last_eval": last_eval, "learner": learner, "runner": runner, "buffer": buffer,
+            "pipeline": pipeline}

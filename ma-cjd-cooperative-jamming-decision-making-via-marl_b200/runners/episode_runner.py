@@ -155,6 +155,9 @@ class BatchedEpisodeRunner:
         info = env.get_env_info()
         self.episode_limit, self.n_agents = info["episode_limit"], info["n_agents"]
         self.n_envs = env.n_envs
+        # total single-environment steps, the reference's meaning of t_env (episode_runner.py:117: one tick per
+        # env.step of ONE env; mac.py:96 anneals epsilon on it): a batched timestep advances it by n_envs, so
+        # an exploration schedule written for the reference decays over the same amount of experience
         self.t_env = 0
         dev = env.device
         n, T, Nn, S, A, H = self.n_envs, self.episode_limit, self.n_agents, info["state_shape"], info["n_actions"], args.rnn_hidden_dim
@@ -209,7 +212,7 @@ class BatchedEpisodeRunner:
             lib, ctx = mac.agent.lib(), mac.agent._ctx()
             lib.call("macjd_agent_forward", ctx, mac.agent.packed().cstruct(), aio)
             lib.call("macjd_env_step", ctx, env._ctab, self._env_io[t])
-            self.t_env += 1
+            self.t_env += self.n_envs
             return
         mac.agent.run(tr["obs"][t].view(1, n * Nn, -1), mac.hidden_states, avail=tr["avail_actions"][t],
                       epsilon=eps, test_mode=test_mode, u_eps=u_eps, rand_actions=rand_actions, seed=mac.seed,
@@ -220,7 +223,7 @@ class BatchedEpisodeRunner:
                         out={"reward": tr["reward"][t], "terminated": tr["terminated"][t],
                              "r_d": self.r_parts[0, t], "r_p": self.r_parts[1, t], "r_j": self.r_parts[2, t],
                              "state": tr["state"][t + 1], "obs": tr["obs"][t + 1], "avail": tr["avail_actions"][t + 1]})
-        self.t_env += 1
+        self.t_env += self.n_envs
 
     def step_host(self, obs, avail, host, test_mode=False):
         """One iteration of the reference's loop (episode_runner.py:119-165: select_actions, env.step) for a
@@ -247,7 +250,7 @@ class BatchedEpisodeRunner:
             self._host_step_cache = (obs, avail, host, mac.hidden_states, mac.agent.path, tuple(map(id, host.values())),
                                      (aio, ahost, eio, ehost))
         mac.agent.lib().call("macjd_rollout_step_host", mac.agent._ctx(), w, aio, ahost, env._ctab, eio, ehost)
-        self.t_env += 1
+        self.t_env += env.n_envs
 
     def reset(self):
         tr, mac = self.traj, self.mac
@@ -303,11 +306,11 @@ class BatchedEpisodeRunner:
         g = self._episode_graph(test_mode)
         eh, rh = g["eps_host"], g["rng_host"]
         for t in range(T):                                 # the same schedule and counters step() would use
-            eh[t] = mac.action_selector.anneal(self.t_env + t, test_mode)
+            eh[t] = mac.action_selector.anneal(self.t_env + t * self.n_envs, test_mode)
             v = (mac._rng_step + 1 + t) & 0xFFFFFFFF
             rh[t] = v - (1 << 32) if v >= (1 << 31) else v       # uint32 bit pattern in an int32 tensor
         mac._rng_step += T
-        self.t_env += T
+        self.t_env += T * self.n_envs
         g["eps_dev"].copy_(eh, non_blocking=True)
         g["rng_dev"].copy_(rh, non_blocking=True)
         g["graph"].replay()
@@ -325,6 +328,11 @@ class BatchedEpisodeRunner:
         if not use_graph:
             for t in range(self.episode_limit):
                 self.step(t, test_mode=test_mode)
+        return self.finish_run(store=store, test_mode=test_mode)
+
+    def finish_run(self, store=True, test_mode=False):
+        """Second half of ``run`` (the pipelined training loop issues the timesteps itself): episodes into the
+        replay ring, then the reference's ``run_info`` statistics (one read-back)."""
         if store and not test_mode and self.buffer is not None:
             self.buffer.store_rollout(self.traj)
         tr = self.traj

@@ -35,6 +35,10 @@ _ALB_DEN = float(1.7 + 0.12 * _ALB_A)
 
 
 class ElectromagneticEnvironment:
+    # every agent's observation IS the global state (environment.py:512-522: get_obs returns get_state once per
+    # jammer); a replay ring may therefore keep the state only (utils/replay_buffer.py: shared_obs)
+    obs_is_replicated_state = True
+
     def __init__(self, config, sim_config_path=DEFAULT_SIM_CONFIG_PATH, *, n_envs=None, spec=None,
                  device=None, seed=None, auto_reset=False, share_scenario=False, _lib=None):
         """config: RL config namespace (reads num_jammers / num_radars / episode_limit with

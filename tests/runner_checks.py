@@ -201,14 +201,14 @@ def check_fused_host_step(device, lib, n_envs=9, steps=6, pinned=True):
     obs = [e.get_obs().cpu().contiguous() for e in envs]
     avail = [e.get_avail_actions().cpu().contiguous() for e in envs]
     for t in range(steps):
-        mac_a.select_actions_host(obs[0], avail[0], t, actions_out=hbs[0]["act_d"], power_out=hbs[0]["act_p"])
+        mac_a.select_actions_host(obs[0], avail[0], t * n_envs, actions_out=hbs[0]["act_d"], power_out=hbs[0]["act_p"])
         envs[0].step_host(hbs[0])
         BatchedEpisodeRunner.step_host(runner, obs[1], avail[1], hbs[1])
         for k in hbs[0]:
             np.testing.assert_array_equal(hbs[1][k].numpy(), hbs[0][k].numpy(), err_msg=f"{k} t={t}")
         assert torch.equal(mac_a.hidden_states, mac_b.hidden_states)
         obs = [hbs[0]["obs"], hbs[1]["obs"]]
-    assert runner.t_env == steps
+    assert runner.t_env == steps * n_envs       # the reference's unit: single-environment steps
 
 
 def check_episode_graph_equals_stepwise(device, n_envs=64):
@@ -286,9 +286,17 @@ def check_main_loop(device, lib, tmp_path):
     writer = types.SimpleNamespace(add_scalar=lambda tag, v, step: scalars.append((tag, float(v), step)), close=lambda: None)
     out = M.run(args, spec=hetero_spec(n_envs, seed=3, active=True, episode_limit=T), writer=writer, log=lines.append, _lib=lib)
     assert out["episodes"] == 4 * n_envs and out["total_steps"] == 4 * n_envs * T
-    assert out["train_steps"] == 3 * (T // 2)                    # rollouts 2, 3 and 4 train, T // train_interval steps each
+    # rollouts 2, 3 and 4 train; the reference's update-to-data ratio: one train step per train_interval
+    # single-environment steps (main.py:216), i.e. n_envs * (T // train_interval) per rollout
+    assert out["train_steps"] == 3 * n_envs * (T // 2)
+    ref_ratio = (T // 2) / T                                     # reference: T // train_interval train steps per T env steps
+    assert abs(out["train_steps"] / (3 * n_envs * T) - ref_ratio) < 1e-12
     assert out["buffer"].buffer_size == 8 and len(out["buffer"]) == 8
-    assert out["runner"].t_env == 4 * T                          # two evaluations did not advance the schedule
+    assert out["runner"].t_env == 4 * n_envs * T                 # single-env steps; two evaluations did not advance the schedule
+    # epsilon(total_steps) is the reference's schedule (action_selectors.py:30-32) evaluated on single-env steps
+    last_tick = 4 * n_envs * T - n_envs                          # t_env of the last batched timestep that acted
+    want_eps = max(args.epsilon_finish, args.epsilon_start - (args.epsilon_start - args.epsilon_finish) / args.epsilon_anneal_time * last_tick)
+    assert abs(out["runner"].mac.action_selector.epsilon - want_eps) < 1e-9
     assert out["last_eval"]["n_episodes"] == 2 * n_envs and np.isfinite(out["last_eval"]["episode_return"])
     assert abs(out["last_logged"]["action_dist"].sum() - 1) < 1e-6 and np.isfinite(out["last_logged"]["avg_loss"])
     tags = {t for t, _, _ in scalars}
