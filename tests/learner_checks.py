@@ -70,10 +70,16 @@ def make_learner(args, agent_sd, mixer_sd, device, lib):
     return learner
 
 
-def check_learner_against_golden(name, device, lib):
+def check_learner_against_golden(name, device, lib, path=1):
     """Whole train steps against the unmodified reference learner: stats, (clipped) gradients
-    of every trained tensor, post-Adam weights, target sync; untrained tensors stay frozen."""
+    of every trained tensor, post-Adam weights, target sync; untrained tensors stay frozen.
+    path = agent_kernel_path of the unrolls: 1 FP32 SIMT (bounds: stats 5e-5, gradients 5e-4, Adam deltas 5e-3),
+    0 the benchmarked tcgen05 3xTF32 pair kernel with split unrolls where the dims allow it (stated looser
+    bounds: stats 2e-4, gradients 2e-3, Adam deltas 1e-2 -- the tensor-core Q's only enter through the
+    double-DQN arg-max and the target network's Q at it)."""
     g, args = _load("learner_" + name)
+    args.agent_kernel_path = path
+    k_stats, k_grad, k_adam = (1.0, 1.0, 1.0) if path == 1 else (4.0, 4.0, 2.0)
     agent0, mixer0 = _sd(g, "agent0."), _sd(g, "mixer0.")
     L = make_learner(args, agent0, mixer0, device, lib)
     for step in range(int(g["n_steps"])):
@@ -87,7 +93,7 @@ def check_learner_against_golden(name, device, lib):
         dbg = stats.pop("debug")
         ref = g[pre + "stats"]
         np.testing.assert_allclose([stats["loss"], stats["grad_norm"], stats["eval_qtot_avg"], stats["target_qtot_avg"]],
-                                   ref, rtol=5e-5, err_msg=f"stats step {step}")
+                                   ref, rtol=5e-5 * k_stats, err_msg=f"stats step {step}")
         coef = min(1.0, args.grad_norm_clip / (stats["grad_norm"] + 1e-6))
         scale = coef / float(dbg["sums"][1])
         off = 0
@@ -95,14 +101,15 @@ def check_learner_against_golden(name, device, lib):
             kind, key = nm.split(".", 1)
             ref_g = g[pre + ("agent_grad." if kind == "agent" else "mixer_grad.") + key]
             mine = dbg["grad"][off:off + n].cpu().numpy().reshape(ref_g.shape) * scale
-            np.testing.assert_allclose(mine, ref_g, rtol=5e-4, atol=5e-6 * max(1e-3, np.abs(ref_g).max()), err_msg=f"{nm} step {step}")
+            np.testing.assert_allclose(mine, ref_g, rtol=5e-4 * k_grad, atol=5e-6 * k_grad * max(1e-3, np.abs(ref_g).max()),
+                                       err_msg=f"{nm} step {step}")
             off += n
         sd_now = {k: v.detach().cpu().numpy() for k, v in L.mac.agent.state_dict().items()}
         for k in agent0:
             if k in AO.TRAINED_AGENT_KEYS:
                 w0 = agent0[k].numpy()
-                np.testing.assert_allclose(sd_now[k] - w0, g[pre + "agent." + k] - w0, rtol=5e-3,
-                                           atol=args.lr * 5e-3 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+                np.testing.assert_allclose(sd_now[k] - w0, g[pre + "agent." + k] - w0, rtol=5e-3 * k_adam,
+                                           atol=args.lr * 5e-3 * k_adam + 2.4e-7 * np.abs(w0).max(), err_msg=k)
             else:
                 np.testing.assert_array_equal(sd_now[k], agent0[k].numpy(), err_msg=f"{k} must stay frozen")
         tgt_now = L.target_mac.agent.state_dict()
@@ -112,8 +119,8 @@ def check_learner_against_golden(name, device, lib):
         tmix_now = L.target_qmix_net.state_dict()
         for k in mixer0:
             w0 = mixer0[k].numpy()
-            np.testing.assert_allclose(mix_now[k].cpu().numpy() - w0, g[pre + "mixer." + k] - w0, rtol=5e-3,
-                                       atol=args.lr * 5e-3 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+            np.testing.assert_allclose(mix_now[k].cpu().numpy() - w0, g[pre + "mixer." + k] - w0, rtol=5e-3 * k_adam,
+                                       atol=args.lr * 5e-3 * k_adam + 2.4e-7 * np.abs(w0).max(), err_msg=k)
             np.testing.assert_allclose(tmix_now[k].cpu().numpy(), g[pre + "tgt_mixer." + k], rtol=1e-5, atol=1e-6)
     return L
 

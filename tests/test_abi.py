@@ -51,3 +51,21 @@ def test_product_classes_refuse_cpu():
     from macjd_b200.simulation.scenario import default_spec
     with pytest.raises(N.MacjdError, match="CUDA only"):
         ElectromagneticEnvironment(types.SimpleNamespace(), spec=default_spec(2), device="cpu")
+
+
+def test_product_library_exports_nothing_undeclared():
+    """Development aids (phase stamps, tensor-pipe micro-benchmarks) live in the tooling build only."""
+    import subprocess
+    import __graft_entry__ as ge
+    out = subprocess.run(["nm", "-D", "--defined-only", ge.build()], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("macjd_")}
+    assert exported == set(declared_symbols()), exported ^ set(declared_symbols())
+
+
+def test_build_records_what_it_compiled():
+    import json
+    import __graft_entry__ as ge
+    lib = ge.build()
+    with open(lib + ".build_info.json") as f:
+        info = json.load(f)
+    assert info["compiled"] is True and "arch=compute_100a,code=sm_100a" in info["flags"]

@@ -57,7 +57,7 @@ def test_full_size_properties():
     assert torch.equal(q.argmax(1), chosen)
 
 
-@pytest.mark.parametrize("tc_path", [2, 3])
+@pytest.mark.parametrize("tc_path", [3])
 @pytest.mark.parametrize("M,T", [(8192, 1), (100, 3), (64, 5), (8200, 2)])
 def test_tensor_core_path_matches_simt_path(M, T, tc_path):
     """tcgen05 3xTF32 kernel against the FP32 SIMT kernel on the same inputs: Q, P, hidden within
@@ -86,7 +86,7 @@ def test_tensor_core_path_matches_simt_path(M, T, tc_path):
     torch.testing.assert_close(b["power"][decidable], a["power"][decidable], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("tc_path", [2, 3])
+@pytest.mark.parametrize("tc_path", [3])
 @pytest.mark.parametrize("name", ["c1"])
 def test_tensor_core_path_vs_reference_golden(name, tc_path):
     """The tcgen05 path against the reference's recorded outputs, with its stated looser bound:
@@ -196,7 +196,7 @@ def test_pair_kernel_action_counts_and_tiny_batches(A, M):
 
 def test_zero_rows_is_a_no_op():
     mac, args = AC.random_agent(4, 24, 5, 128, 128, 2, "cuda")
-    for path in (1, 2, 3):
+    for path in (1, 3):
         out = mac.agent.run(torch.zeros(1, 0, 24, device="cuda"), torch.zeros(0, 128, device="cuda"), select=True,
                             test_mode=True, want_q=True, path=path)
         assert out["actions"].shape == (1, 0) and out["q_all"].shape == (1, 0, 5)
@@ -204,7 +204,8 @@ def test_zero_rows_is_a_no_op():
 
 def test_pair_kernel_needs_the_constant_block():
     """tc_format = 0 (weight chunks without the per-layer constant block behind them): the CTA-pair kernel must
-    refuse instead of reading past the chunks; auto falls back to the single-CTA tensor-core kernel."""
+    refuse instead of reading past the chunks; auto falls back to the FP32 SIMT kernel.  path 2 (round 1's
+    single-CTA tensor-core kernel, removed) is refused."""
     from macjd_b200 import _native as N
     mac, args = AC.random_agent(6, 24, 5, 128, 128, 2, "cuda")
     M = 256
@@ -224,8 +225,12 @@ def test_pair_kernel_needs_the_constant_block():
         N.get_lib().call("macjd_agent_forward", N.torch_ctx(torch.device("cuda", 0)), ww, io)
         torch.cuda.synchronize()
         outs[name] = (act.clone(), pw.clone(), h.clone())
-    assert torch.equal(outs["pair"][0], outs["auto_without_block"][0])
-    torch.testing.assert_close(outs["pair"][2], outs["auto_without_block"][2], rtol=1e-5, atol=1e-6)
+    assert float((outs["pair"][0] == outs["auto_without_block"][0]).float().mean()) > 0.99     # (ties aside)
+    torch.testing.assert_close(outs["pair"][2], outs["auto_without_block"][2], rtol=1e-4, atol=2e-5)
+    io2 = N.AgentIO(n_rows=M, n_steps=1, obs=obs.data_ptr(), hidden=outs["pair"][2].data_ptr(), test_mode=1, path=2,
+                    actions=outs["pair"][0].data_ptr(), power=outs["pair"][1].data_ptr())
+    with pytest.raises(N.MacjdError):
+        N.get_lib().call("macjd_agent_forward", N.torch_ctx(torch.device("cuda", 0)), w, io2)
     io = N.AgentIO(n_rows=M, n_steps=1, obs=obs.data_ptr(), hidden=outs["pair"][2].data_ptr(), test_mode=1, path=3,
                    actions=outs["pair"][0].data_ptr(), power=outs["pair"][1].data_ptr())
     with pytest.raises(N.MacjdError):

@@ -20,9 +20,11 @@ def test_mixer_forward_backward(name):
     LC.check_mixer_against_golden(name, "cuda", lib())
 
 
+@pytest.mark.parametrize("path", [1, 0])
 @pytest.mark.parametrize("name", ["c1", "small_fastlr"])
-def test_learner_train_steps(name):
-    LC.check_learner_against_golden(name, "cuda", lib())
+def test_learner_train_steps(name, path):
+    """path 0 = what bench.py runs (tcgen05 pair kernel, split unrolls on side streams)."""
+    LC.check_learner_against_golden(name, "cuda", lib(), path=path)
 
 
 def test_replay_store_sample():

@@ -14,7 +14,7 @@ if which == "agent":
     h = torch.zeros(M, 128, device="cuda")
     for _ in range(4):
         if len(sys.argv) > 2 and sys.argv[2] in ("tc", "tc2"):
-            mac.agent.run(obs, h, select=True, test_mode=True, path=2 if sys.argv[2] == "tc" else 3)
+            mac.agent.run(obs, h, select=True, test_mode=True, path=3)
         else:
             mac.agent.run(obs, h, select=True, test_mode=True, tile_rows=int(sys.argv[2]) if len(sys.argv) > 2 else 0, path=1)
 elif which == "env":
