@@ -200,12 +200,15 @@ typedef struct macjd_agent_weights {
   const float* w2;        /* [H]    fc2_q_head.2.weight                                */
   const float* bq2;       /* [1]    fc2_q_head.2.bias                                  */
   const float* tc_chunks; /* optional: the dense layers again, packed for the tcgen05 path
-                             (csrc/agent_act_tc.cuh): 128 x 16 weight chunks in consumption order,
+                             (csrc/agent_act_tc2.cuh): 128 x 32 weight chunks in consumption order,
                              UMMA K-major layout, TF32 hi part then lo part (16 KB per chunk);
                              with tc_format 1 the 13 856-byte constant block (biases, actor
-                             output layer, Q-head vectors; csrc/agent_act_tc.cuh: TcConst) follows
+                             output layer, Q-head vectors; csrc/agent_tc_common.cuh: TcConst) follows
                              the last chunk so that the CTA-pair kernel fetches it with one bulk
-                             copy; NULL = FP32 SIMT kernel only                        */
+                             copy, and for A > 8 the per-action tables follow that block:
+                             [H][A8] actor.4.weight^T, [H][A8] fc2_q_head.0.weight[:, H + a],
+                             [A8] actor.4.bias (A8 = A rounded up to 8, zero padded);
+                             NULL = FP32 SIMT kernel only                              */
 } macjd_agent_weights;
 
 typedef struct macjd_agent_io {

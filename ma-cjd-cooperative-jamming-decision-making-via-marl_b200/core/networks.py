@@ -191,8 +191,9 @@ class PackedAgentWeights:
         lo = full - hi
         new = torch.stack([hi, lo], dim=1)                            # [n_chunks, 2, 128 * kc]
         n = new.numel()
-        if self.tc_flat is None or self.tc_flat.numel() != n + self.TC_CONST_FLOATS or self.tc_flat.device != new.device:
-            self.tc_flat = torch.zeros(n + self.TC_CONST_FLOATS, dtype=torch.float32, device=new.device)
+        tail = self.TC_CONST_FLOATS + self._tc_big_floats()
+        if self.tc_flat is None or self.tc_flat.numel() != n + tail or self.tc_flat.device != new.device:
+            self.tc_flat = torch.zeros(n + tail, dtype=torch.float32, device=new.device)
         self.tc_buffer = self.tc_flat[:n].view(new.shape)             # same address on every re-pack: captured launches stay valid
         self.tc_buffer.copy_(new)
         self._pack_tc_const()
@@ -201,14 +202,27 @@ class PackedAgentWeights:
     # CTA-pair kernel fetches the block with one bulk copy instead of ~26 scalar loads per thread.
     TC_CONST_FLOATS = 4 * 128 + 4 * 128 + 3 * 128 + 8 * 128 + 8 * 128 + 8
 
+    def _tc_big_floats(self):
+        """More than 8 actions: the per-action tables do not fit the fixed block; they follow it as
+        [unit][A8] actor.4.weight^T, [unit][A8] fc2_q_head.0.weight[:, H + a], [A8] actor.4.bias (A8 = A rounded up
+        to a multiple of 8, zero padded) and the kernel reads them through L1 (csrc/agent_act_tc2.cuh, kBigA)."""
+        if self.A <= 8:
+            return 0
+        a8 = _ceil_to(self.A, 8)
+        return 2 * 128 * a8 + a8
+
     def _pack_tc_const(self, qhead_only=False):
         H, A = self.H, self.A
-        if A > 8:                      # the tensor-core kernels take at most 8 actions (csrc: agent_tc_supported)
-            return
-        c = self.tc_flat[-self.TC_CONST_FLOATS:]
+        nb = self._tc_big_floats()
+        c = self.tc_flat[-(self.TC_CONST_FLOATS + nb):]
         gate_b, q_c = c[:512].view(128, 4), c[512:1024].view(128, 4)
-        w3, w1a = c[1408:2432].view(128, 8), c[2432:3456].view(128, 8)
         q_c[:, 0].copy_(self.view("bq1")); q_c[:, 1].copy_(self.view("w1p")); q_c[:, 2].copy_(self.view("w2"))
+        if nb:
+            a8 = _ceil_to(A, 8)
+            big = c[self.TC_CONST_FLOATS:]
+            w3, w1a, b3 = big[:128 * a8].view(128, a8), big[128 * a8:2 * 128 * a8].view(128, a8), big[2 * 128 * a8:]
+        else:
+            w3, w1a, b3 = c[1408:2432].view(128, 8), c[2432:3456].view(128, 8), c[3456:3464]
         w1a[:, :A].copy_(self.view("w1a").t())                        # [unit][action] = fc2_q_head.0.weight[unit, H + action]
         if qhead_only:
             return
@@ -216,7 +230,7 @@ class PackedAgentWeights:
         gate_b[:, 0].copy_(brz[:H]); gate_b[:, 1].copy_(brz[H:]); gate_b[:, 2].copy_(self.view("bin")); gate_b[:, 3].copy_(self.view("bhn"))
         c[1024:1152].copy_(self.view("ba1")); c[1152:1280].copy_(self.view("ba2")); c[1280:1408].copy_(self.view("bfc1"))
         w3[:, :A].copy_(self.view("wa3t"))                            # [unit][action] = actor.4.weight^T
-        c[3456:3456 + A].copy_(self.view("ba3"))
+        b3[:A].copy_(self.view("ba3"))
 
     def cstruct(self):
         if self._cstruct is not None and self._cstruct_for == (self.buffer.data_ptr(), id(self.tc_buffer)):
@@ -230,7 +244,7 @@ class PackedAgentWeights:
         kw = {f: base + 4 * self.offsets[f] for f in self.FIELDS}
         tc = self.tc_buffer.data_ptr() if self.tc_buffer is not None else None
         return N.AgentWeights(obs_dim=self.O, obs_pad=self.Op, hidden=self.H, actor_hidden=self.AH,
-                              n_actions=self.A, tc_format=1 if (tc and self.A <= 8) else 0, tc_chunks=tc, **kw)
+                              n_actions=self.A, tc_format=1 if tc else 0, tc_chunks=tc, **kw)
 
 
 class RNNAgent(nn.Module):

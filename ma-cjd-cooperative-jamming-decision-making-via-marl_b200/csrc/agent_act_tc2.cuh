@@ -178,7 +178,11 @@ struct T2Smem {
 
 // kWholeStep: the acting launch (io.part == 0) gets its own instance with the other parts compiled out -- less
 // code to fetch on a cold start (the instruction fetches after an L2 flush are visible in the phase profile)
-template <bool kWholeStep>
+// kBigA: more than 8 discrete actions (BASELINE config 3: 2 x 16 radars + 1 = 33).  The per-action tables of the actor head
+// and of the Q tail ([unit][A8] each, 20 KB at A = 33) then do not fit beside the operand tiles: they are read from global
+// memory through L1 (warp-uniform 16-byte loads), the head / tail run in groups of 8 actions on register-resident
+// activations, and the Q staging buffer borrows the xf operand tile, which is dead by then.
+template <bool kWholeStep, bool kBigA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   T2Smem& S = *reinterpret_cast<T2Smem*>(tc_raw);
@@ -194,8 +198,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   TC_STAMP_ONCE(20);
   const int row0 = blockIdx.x * kTcRows;
   const int valid = max(0, min(kTcRows, M - row0));
+  const int A8 = (A + 7) & ~7;
   float* Ps = reinterpret_cast<float*>(tc_raw + sizeof(T2Smem));     // [A][64]
-  float* Qs = Ps + (size_t)A * kTcRows;
+  // kBigA: the Q staging [A][64] borrows the xf tile (b0lo): every MMA that reads b0 has completed before E4, and
+  // the next step's observation block is written only after E5
+  float* Qs = kBigA ? S.b0lo : Ps + (size_t)A * kTcRows;
   const int nxc = Op / 32;
   const int chunks_per_step = 2 * kTcChunksPerX * nxc + 8 * kTcChunksPerH;
   const int mode = kWholeStep ? 0 : io.part;   // 0 whole step, 1 recurrence only, 2 heads only, 3 input pre-pass, 4 recurrence on gate_x
@@ -250,6 +257,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   }
 
   const float bq2 = __ldg(W.bq2);   // used at the very end (E5): requested here so that a cold line is not a stall there
+  // kBigA: per-action tables behind the constant block: [H][A8] actor.4.weight^T, [H][A8] q.0 one-hot columns, [A8] actor.4.bias
+  const float* const big_w3 = W.tc_chunks + (size_t)chunks_per_step * kTcChunkFloats + sizeof(TcConst) / 4;
+  const float* const big_w1a = big_w3 + (size_t)H * A8;
+  const float* const big_b3 = big_w1a + (size_t)H * A8;
   TC_STAMP_ONCE(26);
   warm_weights_l2(W.tc_chunks, chunks_per_step, kT2Threads);
   TC_STAMP_ONCE(27);
@@ -427,10 +438,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       EP_STAMP(0);
       // this step's availability mask, requested now and used in E5 (a cold load at the end of the
       // step would sit on the critical path)
-      uint8_t av_in[8];
+      uint64_t av_mask = ~0ull;
+      if (part == 0 && live && io.avail) {
+        const uint8_t* ap = io.avail + (tM + row0 + r) * A;
+        av_mask = 0;
+        if (kBigA) {
+#pragma unroll 4
+          for (int act = 0; act < A; ++act) av_mask |= (uint64_t)(__ldg(ap + act) != 0 ? 1u : 0u) << act;
+        } else {
 #pragma unroll
-      for (int act = 0; act < 8; ++act)
-        av_in[act] = (part == 0 && live && io.avail && act < A) ? __ldg(io.avail + (tM + row0 + r) * A + act) : (uint8_t)1;
+          for (int act = 0; act < 8; ++act)
+            if (act < A) av_mask |= (uint64_t)(__ldg(ap + act) != 0 ? 1u : 0u) << act;
+        }
+      }
       for (int xc = 0; xc < nx; ++xc) {
         if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
         const float* obs = io.obs + (tM + row0 + r) * O;
@@ -513,7 +533,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       mbar_arrive_cluster(&S.a_ready, 0);
       }
       EP_STAMP(5);
-      if (mode == 0 || mode == 2)
+      if ((mode == 0 || mode == 2) && !kBigA)
       {
         float acc[8];
 #pragma unroll
@@ -546,6 +566,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
               for (int pp = 0; pp < kT2Parts; ++pp) sum += S.red[pp][j][r];
               Ps[j * kTcRows + r] = sigmoid_fast(sum);
             }
+      }
+      if ((mode == 0 || mode == 2) && kBigA)
+      {
+        // this thread's 32 units of a2 stay in registers; 8 actions per pass over them
+        float a2v[kT2Upt];
+#pragma unroll
+        for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
+          float v[16];
+          tmem_ld16_nowait(tl + kT2ColA2 + (uint32_t)c0, v);
+          tmem_ld_wait();
+          reg_fence(v);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) a2v[c0 + n] = fmaxf(v[n] + S.c.ba2[ub + c0 + n], 0.f);
+        }
+        const float4* w3 = reinterpret_cast<const float4*>(big_w3 + (size_t)ub * A8);
+        const int a84 = A8 >> 2;
+#pragma unroll 1
+        for (int g = 0; g < A8; g += 8) {
+          float acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+          for (int n = 0; n < kT2Upt; ++n) {
+            const float4 wl = __ldg(w3 + n * a84 + (g >> 2)), wh = __ldg(w3 + n * a84 + (g >> 2) + 1);
+            const float a2 = a2v[n];
+            acc[0] = fmaf(a2, wl.x, acc[0]); acc[1] = fmaf(a2, wl.y, acc[1]);
+            acc[2] = fmaf(a2, wl.z, acc[2]); acc[3] = fmaf(a2, wl.w, acc[3]);
+            acc[4] = fmaf(a2, wh.x, acc[4]); acc[5] = fmaf(a2, wh.y, acc[5]);
+            acc[6] = fmaf(a2, wh.z, acc[6]); acc[7] = fmaf(a2, wh.w, acc[7]);
+          }
+          if (g > 0) epi_bar_sync();         // the previous group's partial sums have been consumed
+#pragma unroll
+          for (int j = 0; j < 8; ++j) S.red[part][j][r] = acc[j];
+          epi_bar_sync();
+          // the row's four threads finish two actions each
+#pragma unroll
+          for (int jj = 0; jj < 8 / kT2Parts; ++jj) {
+            const int j = part * (8 / kT2Parts) + jj;
+            if (g + j < A) {
+              float sum = __ldg(big_b3 + g + j);
+#pragma unroll
+              for (int pp = 0; pp < kT2Parts; ++pp) sum += S.red[pp][j][r];
+              Ps[(g + j) * kTcRows + r] = sigmoid_fast(sum);
+            }
+          }
+        }
       }
       EP_STAMP(6);
 
@@ -641,7 +707,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       else epi_bar_sync();                                                  // ... but P (written by E2's last stage) must be visible
       fence_after_sync();
       EP_STAMP(9);
-      {
+      if (!kBigA) {
         float acc[8], pa[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc[j] = 0.f; pa[j] = (j < A) ? Ps[j * kTcRows + r] : 0.f; }
@@ -674,13 +740,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
               for (int pp = 0; pp < kT2Parts; ++pp) sum += S.red[pp][j][r];
               Qs[j * kTcRows + r] = sum;
             }
+      } else {
+        // this thread's 32 units of the shared hidden product stay in registers; 8 actions per pass over them
+        float prev[kT2Upt];
+#pragma unroll
+        for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
+          float v[16];
+          tmem_ld16_nowait(tl + (mode == 2 ? kT2ColHn : kT2ColQ) + (uint32_t)c0, v);
+          tmem_ld_wait();
+          reg_fence(v);
+#pragma unroll
+          for (int n = 0; n < 16; ++n) prev[c0 + n] = v[n] + S.c.q_c[ub + c0 + n].x;
+        }
+        const float4* w1 = reinterpret_cast<const float4*>(big_w1a + (size_t)ub * A8);
+        const int a84 = A8 >> 2;
+#pragma unroll 1
+        for (int g = 0; g < A8; g += 8) {
+          float acc[8], pa[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc[j] = 0.f; pa[j] = (g + j < A) ? Ps[(g + j) * kTcRows + r] : 0.f; }
+#pragma unroll
+          for (int n = 0; n < kT2Upt; ++n) {
+            const float4 qc = S.c.q_c[ub + n];
+            const float4 wl = __ldg(w1 + n * a84 + (g >> 2)), wh = __ldg(w1 + n * a84 + (g >> 2) + 1);
+            const float wa[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(qc.z, fmaxf(fmaf(pa[j], qc.y, prev[n] + wa[j]), 0.f), acc[j]);
+          }
+          epi_bar_sync();               // red is free (first group: E2's last use; later groups: the previous reduction)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) S.red[part][j][r] = acc[j];
+          epi_bar_sync();
+#pragma unroll
+          for (int jj = 0; jj < 8 / kT2Parts; ++jj) {
+            const int j = part * (8 / kT2Parts) + jj;
+            if (g + j < A) {
+              float sum = bq2;
+#pragma unroll
+              for (int pp = 0; pp < kT2Parts; ++pp) sum += S.red[pp][j][r];
+              Qs[(g + j) * kTcRows + r] = sum;
+            }
+          }
+        }
+        epi_bar_sync();                 // every action's Q is staged before the selection reads them
       }
       fence_before_sync();
       if (part == 0 && live) {
         const size_t m = tM + row0 + r;
-        uint32_t av_mask = 0;
-#pragma unroll
-        for (int act = 0; act < 8; ++act) av_mask |= (av_in[act] != 0 ? 1u : 0u) << act;
         float best = -INFINITY, bestm = -INFINITY;
         int bi = 0, bim = 0, n_avail = 0;
         for (int act = 0; act < A; ++act) {
@@ -689,7 +795,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           if (io.q_all) io.q_all[m * A + act] = q;
           if (io.params_all) io.params_all[m * A + act] = p;
           if (q > best) { best = q; bi = act; }
-          const bool ok = (av_mask >> act) & 1u;
+          const bool ok = (av_mask >> act) & 1ull;
           n_avail += ok ? 1 : 0;
           const float qm = ok ? q : -INFINITY;
           if (qm > bestm) { bestm = qm; bim = act; }
@@ -715,7 +821,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
                 kth = kth >= navl ? navl - 1 : kth;
                 chosen = 0;
                 for (int act = 0, seen = 0; act < A; ++act) {
-                  const bool ok = (n_avail == 0) || ((av_mask >> act) & 1u);
+                  const bool ok = (n_avail == 0) || ((av_mask >> act) & 1ull);
                   if (ok) { if (seen == kth) { chosen = act; break; } ++seen; }
                 }
               }
@@ -745,7 +851,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 }
 
 inline size_t agent_tc2_smem_bytes(const macjd_agent_weights& w) {
-  return sizeof(T2Smem) + sizeof(float) * 2 * (size_t)w.n_actions * kTcRows + 1024;
+  // Ps [A][64] and, up to 8 actions, Qs [A][64] behind it (kBigA: Qs borrows the xf tile)
+  return sizeof(T2Smem) + sizeof(float) * (w.n_actions > 8 ? 1 : 2) * (size_t)w.n_actions * kTcRows + 1024;
 }
 
 inline bool agent_tc2_supported(const macjd_agent_weights& w) {
@@ -757,8 +864,10 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
   // the opt-in is per device and sticky: ask once per device and size (an act call is latency-critical)
   static PerDeviceMax opted;
   if (!opted.covers(ctx->device, smem)) {
-    if (cudaFuncSetAttribute(agent_forward_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(agent_forward_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(agent_forward_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(agent_forward_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(agent_forward_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(agent_forward_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return MACJD_ERR_CUDA;
     opted.record(ctx->device, smem);
   }
@@ -787,8 +896,15 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return MACJD_ERR_CUDA;
   const int pairs = (a.io.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
-  if (a.io.part == 0) agent_forward_tc2_kernel<true><<<2 * pairs, kT2Threads, smem, (cudaStream_t)ctx->stream>>>(p);
-  else agent_forward_tc2_kernel<false><<<2 * pairs, kT2Threads, smem, (cudaStream_t)ctx->stream>>>(p);
+  const bool big = a.w.n_actions > 8;
+  const cudaStream_t st = (cudaStream_t)ctx->stream;
+  if (a.io.part == 0) {
+    if (big) agent_forward_tc2_kernel<true, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
+    else agent_forward_tc2_kernel<true, false><<<2 * pairs, kT2Threads, smem, st>>>(p);
+  } else {
+    if (big) agent_forward_tc2_kernel<false, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
+    else agent_forward_tc2_kernel<false, false><<<2 * pairs, kT2Threads, smem, st>>>(p);
+  }
   return MACJD_OK;
 }
 

@@ -121,7 +121,7 @@ inline int agent_tc_chunk_k() { return kTcKc; }
 
 // dims the packed tensor-core weights exist for (core/networks.py: PackedAgentWeights._pack_tc)
 inline bool agent_tc_supported(const macjd_agent_weights& w) {
-  return w.tc_chunks != nullptr && w.hidden == kTcH && w.actor_hidden == kTcH && w.obs_pad % 32 == 0 && w.n_actions <= 8;
+  return w.tc_chunks != nullptr && w.hidden == kTcH && w.actor_hidden == kTcH && w.obs_pad % 32 == 0 && w.n_actions <= 64;
 }
 
 inline int tc_profile_read(unsigned long long* out_host, int n) {

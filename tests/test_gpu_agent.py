@@ -235,3 +235,48 @@ def test_pair_kernel_needs_the_constant_block():
                    actions=outs["pair"][0].data_ptr(), power=outs["pair"][1].data_ptr())
     with pytest.raises(N.MacjdError):
         N.get_lib().call("macjd_agent_forward", N.torch_ctx(torch.device("cuda", 0)), w0, io)
+
+
+@pytest.mark.parametrize("O,A,M,T", [(176, 33, 520, 1), (176, 33, 8192, 2), (24, 9, 70, 3), (40, 40, 129, 1), (176, 33, 300, 4)])
+def test_pair_kernel_many_actions(O, A, M, T):
+    """More than 8 discrete actions (BASELINE config 3: 16 radars -> 33 actions, observations 176 wide): the
+    CTA-pair kernel runs the actor head and the Q tail in groups of 8 actions with the per-action tables read
+    through L1.  Against the FP32 SIMT kernel: Q, P, hidden within the tensor-core path's stated bound, chosen
+    actions (masked arg-max), greedy actions and gathers identical where the margin is decidable -- for the fused
+    step and for the split 3 + 4 + 2 unroll the learner uses."""
+    from macjd_b200 import _native as N
+    mac, args = AC.random_agent(11, O, A, 128, 128, 2, "cuda")
+    w = mac.agent.packed().cstruct()
+    assert N.get_lib().lib.macjd_agent_pair_supported(N.C.byref(w)) == 1
+    g = torch.Generator(device="cuda").manual_seed(5)
+    obs = torch.randn(T, M, O, device="cuda", generator=g) * 2
+    h0 = torch.randn(M, 128, device="cuda", generator=g) * 0.5
+    avail = torch.rand(T, M, A, device="cuda", generator=g) < 0.7
+    avail[..., A - 1] = True
+    sel = torch.randint(0, A, (T, M), device="cuda", generator=g, dtype=torch.int32)
+    res = {}
+    for name, kw in (("simt", dict(path=1)), ("pair", dict(path=3, split_unroll=False)), ("split", dict(path=3))):
+        res[name] = mac.agent.run(obs, h0.clone(), n_steps=T, avail=avail, select=True, test_mode=True, want_q=True,
+                                  want_params=True, want_greedy=True, want_hidden_seq=True, sel_actions=sel, **kw)
+    a = res["simt"]
+    q = a["q_all"].masked_fill(~avail, -float("inf"))
+    top2 = q.topk(2, dim=-1).values
+    decidable = (top2[..., 0] - top2[..., 1]) > 1e-4
+    top2g = a["q_all"].topk(2, dim=-1).values
+    decidable_g = (top2g[..., 0] - top2g[..., 1]) > 1e-4
+    assert decidable.float().mean() > 0.9
+    for name in ("pair", "split"):
+        b = res[name]
+        torch.testing.assert_close(b["params_all"], a["params_all"], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(b["hidden_seq"], a["hidden_seq"], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(b["q_all"], a["q_all"], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(b["q_sel"], a["q_sel"], rtol=1e-4, atol=2e-5)
+        assert torch.equal(a["actions"][decidable], b["actions"][decidable]), name
+        assert torch.equal(a["greedy"][decidable_g], b["greedy"][decidable_g]), name
+        same = a["actions"] == b["actions"]
+        torch.testing.assert_close(b["power"][same], a["power"][same], rtol=1e-5, atol=1e-6)
+    # twice the same launch: bit-reproducible (a race on the borrowed staging tile would show here)
+    again = mac.agent.run(obs, h0.clone(), n_steps=T, avail=avail, select=True, test_mode=True, want_q=True,
+                          want_params=True, want_greedy=True, want_hidden_seq=True, sel_actions=sel, path=3, split_unroll=False)
+    for k in ("q_all", "params_all", "actions", "hidden_seq", "power"):
+        assert torch.equal(again[k], res["pair"][k]), k
