@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MACJD_ABI_VERSION 1
+#define MACJD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MACJD_API __attribute__((visibility("default")))
@@ -84,6 +84,11 @@ typedef struct macjd_env_tables {
   double alb_a;             /* ln(0.62/prfa)                       (core/radar.py:70)   */
   double alb_zoff;          /* 5 log10(m)/(6.2+4.54/sqrt(m)+0.44)  (core/radar.py:73)   */
   double alb_den;           /* 1.7 + 0.12 A                        (core/radar.py:74)   */
+  /* optional: everything of a step that depends on the scenario alone, evaluated once by
+   * macjd_env_prepare() into a caller-owned buffer of macjd_env_derived_bytes() bytes (same
+   * per-env / shared convention as `data`).  NULL: the step kernel derives it from `data` on
+   * every step (round 1's kernel); results are the same. */
+  const double* derived;
 } macjd_env_tables;
 
 /* macjd_env_io.flags.  MACJD_ENV_FOLLOWS_AGENT: the caller launches this step directly behind the kernel
@@ -125,6 +130,13 @@ typedef struct macjd_env_io {
   int32_t env_begin;        /* step only envs [env_begin, env_begin + env_count): every pointer above still */
   int32_t env_count;        /* names the whole batch (0, 0 = all; groups of one batch on separate streams)  */
 } macjd_env_io;
+
+/* Scenario-only terms of the step (environment.py:316-349 echo power and no-jamming Pd per radar-target pair,
+ * core/jammer.py:73-98 link denominators, environment.py:365 clipped tracking penalties, environment.py:479-510
+ * state rows), which the reference recomputes every step although the scenario never changes within a run:
+ * computed once here.  `tab->derived` is ignored; point it at `derived` afterwards.  Stream-ordered. */
+MACJD_API size_t macjd_env_derived_bytes(const macjd_env_tables* tab);
+MACJD_API int macjd_env_prepare(const macjd_ctx* ctx, const macjd_env_tables* tab, void* derived);
 
 /* environment.py:221-477  step(actions) for all envs. */
 MACJD_API int macjd_env_step(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io);

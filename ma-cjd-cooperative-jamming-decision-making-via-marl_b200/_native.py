@@ -25,7 +25,7 @@ class EnvTables(C.Structure):
                 ("n_types", c_int32), ("episode_limit", c_int32),
                 ("data", c_void_p), ("row_stride", c_int64), ("env_stride", c_int64),
                 ("rd_min", c_double), ("rd_max", c_double), ("rp_min", c_double), ("rp_max", c_double),
-                ("alb_a", c_double), ("alb_zoff", c_double), ("alb_den", c_double)]
+                ("alb_a", c_double), ("alb_zoff", c_double), ("alb_den", c_double), ("derived", c_void_p)]
 
 
 class EnvIO(C.Structure):
@@ -154,6 +154,8 @@ class NativeLib:
         vp, sz, i32, i64, f32 = c_void_p, C.c_size_t, c_int32, c_int64, c_float
         for name, restype, argtypes in (
             ("macjd_replay_copy", C.c_int, [P(Ctx), P(CopyDesc), i32, vp, i32, i32]),
+            ("macjd_env_derived_bytes", sz, [P(EnvTables)]),
+            ("macjd_env_prepare", C.c_int, [P(Ctx), P(EnvTables), vp]),
             ("macjd_mixer_workspace_floats", sz, [P(MixerDims)]),
             ("macjd_mixer_forward", C.c_int, [P(Ctx), P(MixerDims), P(MixerParams), vp, vp, vp, vp, sz]),
             ("macjd_mixer_backward", C.c_int, [P(Ctx), P(MixerDims), P(MixerParams), vp, vp, vp, sz, P(MixerParams), vp]),
@@ -182,7 +184,7 @@ class NativeLib:
     }
 
     def _check_abi(self):
-        if self.lib.macjd_abi_version() != 1:
+        if self.lib.macjd_abi_version() != 2:
             raise MacjdError("macjd ABI version mismatch")
         for i, st in enumerate(ABI_STRUCTS):
             got = self.lib.macjd_abi_sizeof(i)

@@ -398,7 +398,8 @@ inline size_t env_smem_bytes(int R, int K, int stage_ld, int bs, int workers = 1
          (workers > 1 ? (size_t)3 * n_jammers * bs * sizeof(double) : 0);     // jammer records handed between the workers
 }
 
-inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
+// argument checks shared by both step kernels
+inline int env_check_args(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
   if (!ctx || !tab || !io) return MACJD_ERR_INVALID_ARG;
   if (tab->n_envs < 0 || tab->n_jammers < 1 || tab->n_radars < 1 || tab->n_targets < 1 || tab->n_types < 1)
     return MACJD_ERR_INVALID_ARG;
@@ -406,6 +407,11 @@ inline int env_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const m
   if (!tab->data || !io->step_count) return MACJD_ERR_INVALID_ARG;
   if (physics && (!io->act_d || !io->act_p || !io->reward)) return MACJD_ERR_INVALID_ARG;
   if (io->env_begin < 0 || io->env_count < 0 || (int64_t)io->env_begin + io->env_count > tab->n_envs) return MACJD_ERR_INVALID_ARG;
+  return MACJD_OK;
+}
+
+// the kernel on the RAW scenario tables (callers that did not run macjd_env_prepare)
+inline int env_launch_raw(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
   const int n_step = io->env_count > 0 ? io->env_count : tab->n_envs - io->env_begin;
   if (n_step == 0) return MACJD_OK;
   EnvKernelArgs a;

@@ -7,7 +7,7 @@
 // watchdog word (macjd_common.cuh: a pinned host int the tensor-core kernels raise instead of
 // trapping); entry points are safe to call from several threads on disjoint buffers.
 #include "macjd_common.cuh"
-#include "env_step.cuh"
+#include "env_step2.cuh"
 #include "agent_act.cuh"
 #include "agent_act_tc2.cuh"
 #include "replay.cuh"
@@ -113,6 +113,16 @@ int macjd_env_step(const macjd_ctx* ctx, const macjd_env_tables* tab, const macj
 int macjd_env_reset(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io) {
   MACJD_ENTER(ctx);
   return finish(ctx, macjd::env_launch(ctx, tab, io, /*physics=*/0));
+}
+
+size_t macjd_env_derived_bytes(const macjd_env_tables* tab) {
+  if (!tab || tab->n_envs < 0 || tab->n_jammers < 1 || tab->n_radars < 1 || tab->n_targets < 1 || tab->n_types < 1) return 0;
+  return macjd::env_derived_bytes(*tab);
+}
+
+int macjd_env_prepare(const macjd_ctx* ctx, const macjd_env_tables* tab, void* derived) {
+  MACJD_ENTER(ctx);
+  return finish(ctx, macjd::env_prepare_launch(ctx, tab, derived));
 }
 
 int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io) {

@@ -40,7 +40,7 @@ class ElectromagneticEnvironment:
     obs_is_replicated_state = True
 
     def __init__(self, config, sim_config_path=DEFAULT_SIM_CONFIG_PATH, *, n_envs=None, spec=None,
-                 device=None, seed=None, auto_reset=False, share_scenario=False, _lib=None):
+                 device=None, seed=None, auto_reset=False, share_scenario=False, derive_tables=True, _lib=None):
         """config: RL config namespace (reads num_jammers / num_radars / episode_limit with
         the reference's fallbacks, environment.py:82-84).  ``spec`` (a raw scenario spec,
         see scenario.py) replaces the YAML for heterogeneous / synthetic scenarios."""
@@ -88,7 +88,15 @@ class ElectromagneticEnvironment:
             episode_limit=tabs.episode_limit, data=self._tab_dev.data_ptr(),
             row_stride=row_stride, env_stride=env_stride,
             rd_min=tabs.rd_min, rd_max=tabs.rd_max, rp_min=tabs.rp_min, rp_max=tabs.rp_max,
-            alb_a=_ALB_A, alb_zoff=_ALB_ZOFF, alb_den=_ALB_DEN)
+            alb_a=_ALB_A, alb_zoff=_ALB_ZOFF, alb_den=_ALB_DEN, derived=None)
+        # Scenario-only terms of the step (echo power and no-jamming Pd per radar-target pair, link denominators,
+        # state rows): derived once here, read by every step (csrc/env_step2.cuh).  derive_tables=False keeps the
+        # kernel that works from the raw tables on every step (round 1's; same results).
+        if derive_tables:
+            nbytes = int(self._lib.lib.macjd_env_derived_bytes(N.C.byref(self._ctab)))
+            self._derived_dev = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            self._lib.callv("macjd_env_prepare", self._ctx_for(dev), self._ctab, self._derived_dev)
+            self._ctab.derived = self._derived_dev.data_ptr()
 
         f32 = dict(dtype=torch.float32, device=dev)
         u8 = dict(dtype=torch.uint8, device=dev)
@@ -120,8 +128,12 @@ class ElectromagneticEnvironment:
 
     # ------------------------------------------------------------------ native calls
     def _ctx(self):
-        if self.device.type == "cuda":
-            return N.torch_ctx(self.device)
+        return self._ctx_for(self.device)
+
+    @staticmethod
+    def _ctx_for(device):
+        if device.type == "cuda":
+            return N.torch_ctx(device)
         return N.Ctx(device=0, reserved=0, stream=None)
 
     def _io(self, act_d=None, act_p=None, noise=None, out=None):

@@ -85,3 +85,9 @@ def test_invalid_arguments_are_status_codes():
         lib.call("macjd_env_step", N.Ctx(), N.EnvTables(n_envs=4, n_jammers=2, n_radars=2, n_targets=1, n_types=4), N.EnvIO())
     with pytest.raises(N.MacjdError, match="unsupported"):
         lib.call("macjd_env_step", N.Ctx(), N.EnvTables(n_envs=4, n_jammers=2, n_radars=65, n_targets=1, n_types=4), N.EnvIO())
+
+
+@pytest.mark.parametrize("kind,n", [("active", 70), ("scaled_small", 45), ("odd_radars", 33)])
+def test_raw_and_derived_table_kernels_agree(kind, n):
+    from tests.env_checks import check_raw_and_derived_kernels_agree
+    check_raw_and_derived_kernels_agree(make_env, kind, n)

@@ -53,3 +53,11 @@ def test_full_size_properties():
         noise.zero_()                                                 # u = 0: everything is detected
         _, _, _, info = env.step((z, p), noise=noise)
         assert bool(info["radar_tracking"].all())
+
+
+@pytest.mark.parametrize("kind,n", [("active", 5000), ("scaled", 1111), ("scaled_small", 777), ("odd_radars", 1000),
+                                    ("one_radar", 333), ("hetero", 40000)])
+def test_raw_and_derived_table_kernels_agree(kind, n):
+    """The step kernel on derived scenario tables (csrc/env_step2.cuh) against the raw-table kernel (csrc/env_step.cuh)."""
+    from tests.env_checks import check_raw_and_derived_kernels_agree
+    check_raw_and_derived_kernels_agree(make_env, kind, n)
