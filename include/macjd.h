@@ -292,6 +292,19 @@ MACJD_API int macjd_agent_pair_supported(const macjd_agent_weights* w);
  * expects it (core/networks.py packs accordingly); 0 = built without the tensor-core kernel. */
 MACJD_API int macjd_agent_tc_chunk_k(void);
 
+/* One timestep of the reference's rollout loop on the device (runners/episode_runner.py:119-165:
+ * mac.select_actions(obs, avail) then env.step(actions)): the fused agent step (aio, n_steps = 1, part 0,
+ * actions / power set) followed by the env step on the actions it chose (eio->act_d / act_p are ignored: the
+ * step reads aio->actions / aio->power).  When the CTA-pair tensor-core kernel takes the agent dims, a CTA's 64
+ * rows are whole envs (64 % n_jammers == 0) and `tab->derived` is set, this is ONE launch: the CTA that
+ * selected an env's actions also evaluates that env's step (actions handed over in shared memory) and copies
+ * its next state / obs / avail.  Otherwise the two kernels run back to back.  Results are identical to
+ * macjd_agent_forward followed by macjd_env_step.  Requires aio->n_rows == n_envs * n_jammers (env-major). */
+MACJD_API int macjd_rollout_step(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
+                                 const macjd_env_tables* tab, const macjd_env_io* eio);
+/* 1 if macjd_rollout_step runs these weights / tables as one launch. */
+MACJD_API int macjd_rollout_fused_supported(const macjd_agent_weights* w, const macjd_env_tables* tab);
+
 /* Host-buffer form of BasicMAC.select_actions (core/mac.py:59-187: numpy observations and
  * availability masks in, chosen discrete actions and their power levels out).  `io` is a
  * single-step (n_steps = 1) macjd_agent_io whose obs / avail / actions / power name DEVICE

@@ -24,6 +24,7 @@
 //   epilogue: x tile -> E1 (a1) .............. -> E3 (xf), E2 (actor head P) ....... -> E4 (gates, h') -> E5 (Q, selection)
 #pragma once
 #include "agent_tc_common.cuh"
+#include "env_step2.cuh"
 #ifndef MACJD_TEST_HOST_EMULATION
 #include <cuda.h>            // CUtensorMap (type and enums only; the encoder is fetched through the runtime)
 #endif
@@ -147,6 +148,7 @@ __device__ __forceinline__ void epi_wait(uint64_t* bar, uint32_t parity, int war
 struct T2Args {
   AgentArgs a;
   alignas(64) CUtensorMap wmap;
+  Env2Args env;        // kFuseEnv launches: the environment step of the same timestep (macjd_rollout_step)
 };
 
 // 8 KB half-chunk -> this CTA's shared memory; the bytes are counted on the LEADER's mbarrier
@@ -174,6 +176,8 @@ struct T2Smem {
   uint64_t x_full, x_empty, d_ready, a_ready;
   uint64_t c_full;                          // the constant block has landed
   uint32_t tmem_base;
+  int32_t act_s[kTcRows];                   // kFuseEnv: the actions just chosen, handed to the env step in place
+  float pow_s[kTcRows];
 };
 
 // kWholeStep: the acting launch (io.part == 0) gets its own instance with the other parts compiled out -- less
@@ -182,7 +186,13 @@ struct T2Smem {
 // and of the Q tail ([unit][A8] each, 20 KB at A = 33) then do not fit beside the operand tiles: they are read from global
 // memory through L1 (warp-uniform 16-byte loads), the head / tail run in groups of 8 actions on register-resident
 // activations, and the Q staging buffer borrows the xf operand tile, which is dead by then.
-template <bool kWholeStep, bool kBigA>
+// kFuseEnv (acting launches only): the CTA also runs the environment step of its rows' envs -- a CTA's 64 rows are
+// 64 / J whole envs -- right behind the selection: the actions go from the selecting threads to the physics threads
+// through shared memory (no second launch, no dependency hand-over, no global round trip), one thread per env
+// evaluates the step on the derived scenario tables (env_step2.cuh: env2_physics, the code of the stand-alone
+// kernel), and the static views of the next timestep are copied by all epilogue threads while they would
+// otherwise wait for the Q-head product.
+template <bool kWholeStep, bool kBigA, bool kFuseEnv = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   T2Smem& S = *reinterpret_cast<T2Smem*>(tc_raw);
@@ -703,6 +713,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 
       if (mode == 0 || mode == 2) {
       // ---- E5: Q tail, outputs, selection
+      if (kFuseEnv) {
+        // the next timestep's state / obs / avail of this CTA's envs, while the Q-head product runs
+        const int Je = p.env.tab.n_jammers;
+        env2_views(p.env, p.env.io, row0 / Je, valid / Je, tid, kT2EpiThreads);
+      }
       if (mode == 0) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }   // heads only: q.0 finished with actor.2
       else epi_bar_sync();                                                  // ... but P (written by E2's last stage) must be visible
       fence_after_sync();
@@ -830,12 +845,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           }
           io.actions[m] = chosen;
           const float pw = Ps[chosen * kTcRows + r];
+          if (kFuseEnv) { S.act_s[r] = chosen; S.pow_s[r] = pw; }
           if (io.power) io.power[m] = pw;
           if (io.actions_mirror) io.actions_mirror[m] = chosen;      // e.g. the caller's page-locked host copy
           if (io.power_mirror) io.power_mirror[m] = pw;
           if (io.q_chosen) io.q_chosen[m] = Qs[chosen * kTcRows + r];
         }
       }
+      }
+      if (kFuseEnv) {
+        // ---- the environment step of this CTA's envs on the actions just chosen (environment.py:221-477)
+        epi_bar_sync();                 // actions staged; red (the scratch below) is free
+        const Env2Args& E = p.env;
+        const int Je = E.tab.n_jammers, epc = kTcRows / Je;
+        if (part == 0 && live && (r % Je) == 0) {
+          const int e = (row0 + r) / Je;
+          const bool shared_scn = E.tab.env_stride == 0;
+          const int64_t drs = shared_scn ? 1 : (int64_t)E.tab.n_envs;
+          const double* dcol = E.tab.derived + (shared_scn ? 0 : e);
+          auto dv = [&](int row) -> double { return __ldg(dcol + (int64_t)row * drs); };
+          double* rec_val = reinterpret_cast<double*>(S.red);                          // [J][epc]
+          int* rec_code = reinterpret_cast<int*>(rec_val + kTcRows);                   // [J][epc]
+          double* pnet = rec_val + kTcRows + kTcRows / 2;                              // [K][epc]
+          env2_physics(E, E.io, e, dv, S.act_s + r, S.pow_s + r, rec_val, rec_code, pnet, epc, r / Je);
+        }
       }
       epi_bar_sync();                   // Ps / Qs / red are free for the next step
       EP_STAMP(10);
@@ -859,7 +892,14 @@ inline bool agent_tc2_supported(const macjd_agent_weights& w) {
   return agent_tc_supported(w) && w.tc_format == 1 && kTcKc == 32 && kTcChunksPerX == 1 && agent_tc2_smem_bytes(w) <= 227 * 1024;
 }
 
-inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
+// The fused rollout step needs whole envs per CTA (64 % J == 0), derived scenario tables and room for the physics
+// scratch in the 8 KB reduction buffer.
+inline bool agent_tc2_fuse_supported(const macjd_agent_weights& w, const macjd_env_tables& t) {
+  return agent_tc2_supported(w) && t.derived != nullptr && t.n_jammers >= 1 && kTcRows % t.n_jammers == 0 &&
+         (size_t)t.n_targets * (kTcRows / t.n_jammers) * sizeof(double) + 1024 <= sizeof(float) * kT2Parts * 8 * kTcRows;
+}
+
+inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a, const Env2Args* env = nullptr) {
   const size_t smem = agent_tc2_smem_bytes(a.w);
   // the opt-in is per device and sticky: ask once per device and size (an act call is latency-critical)
   static PerDeviceMax opted;
@@ -867,7 +907,9 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
     if (cudaFuncSetAttribute(agent_forward_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(agent_forward_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(agent_forward_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(agent_forward_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        cudaFuncSetAttribute(agent_forward_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(agent_forward_tc2_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(agent_forward_tc2_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return MACJD_ERR_CUDA;
     opted.record(ctx->device, smem);
   }
@@ -886,6 +928,7 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
   if (!encode) return MACJD_ERR_CUDA;
   T2Args p;
   p.a = a;
+  if (env) p.env = *env;
   const size_t chunk_bytes = (size_t)(2 * kTcChunksPerX * (a.w.obs_pad / 32) + 8 * kTcChunksPerH) * kTcChunkBytes;
   const cuuint64_t gdim[2] = {32, chunk_bytes / 128};
   const cuuint64_t gstride[1] = {128};
@@ -898,7 +941,11 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a) {
   const int pairs = (a.io.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
   const bool big = a.w.n_actions > 8;
   const cudaStream_t st = (cudaStream_t)ctx->stream;
-  if (a.io.part == 0) {
+  if (env) {
+    if (a.io.part != 0 || a.io.n_steps != 1) return MACJD_ERR_INVALID_ARG;
+    if (big) agent_forward_tc2_kernel<true, true, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
+    else agent_forward_tc2_kernel<true, false, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
+  } else if (a.io.part == 0) {
     if (big) agent_forward_tc2_kernel<true, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
     else agent_forward_tc2_kernel<true, false><<<2 * pairs, kT2Threads, smem, st>>>(p);
   } else {

@@ -163,167 +163,134 @@ struct Env2Args {
   int env_begin, env_end;
 };
 
-template <bool kStaged>
-__global__ void __launch_bounds__(kEnv2Threads) env_step2_kernel(const Env2Args a) {
+// One env's step on the derived tables.  `dv(row)` reads this env's derived value; act_d / act_p point at this env's
+// J actions (global memory, or shared memory when the agent kernel runs the step itself); scratch is per-thread
+// [slot * sstride + sidx]: rec_val [J], rec_code [J] (ints), pnet [K] (only touched when pd_net is wanted).
+template <typename DV>
+__device__ __forceinline__ void env2_physics(const Env2Args& a, const macjd_env_io& io, int e, DV dv, const int32_t* act_d,
+                                             const float* act_p, double* rec_val, int* rec_code, double* pnet, int sstride, int sidx) {
   const macjd_env_tables& T = a.tab;
-  const macjd_env_io& io = a.io;
   const DerivedRows& D = a.rows;
-  const int n = T.n_envs, J = T.n_jammers, R = T.n_radars, K = T.n_targets;
-  const int RK = R * K, S = a.state_dim, A = a.n_actions;
-  const int tid = (int)threadIdx.x;
-  const int e0 = a.env_begin + blockIdx.x * kEnv2Envs;
-  const int valid = min(kEnv2Envs, a.env_end - e0);
-  const bool shared_scn = T.env_stride == 0;
-  MACJD_DYNAMIC_SMEM(double, smem);
-
-  if (tid < kEnv2Envs) {
-    // =========================================================================== physics: thread = env
-    const int e = e0 + tid;
-    const bool live = tid < valid;
-    const int64_t drs = shared_scn ? 1 : (int64_t)n;                   // derived row stride
-    const double* dcol = T.derived + (shared_scn ? 0 : (live ? e : e0));
-    // per-thread scratch [slot][32]: jammer records (value, code), networked-Pd products
-    double* rec_val = smem;                                            // [J][32]
-    int* rec_code = reinterpret_cast<int*>(rec_val + (size_t)J * kEnv2Envs);   // [J][32]
-    double* pnet = rec_val + (size_t)J * kEnv2Envs + ((size_t)J * kEnv2Envs + 1) / 2;   // [K][32]
-    double* srows = pnet + (size_t)K * kEnv2Envs;                      // [rows][32] when kStaged
-    if (kStaged && a.physics && live) {
-#pragma unroll 1
-      for (int row0 = 0; row0 < D.total; row0 += 16) {
-        double v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (row0 + i < D.total) ? __ldg(dcol + (int64_t)(row0 + i) * drs) : 0.0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (row0 + i < D.total) srows[(row0 + i) * kEnv2Envs + tid] = v[i];
+  const int n = T.n_envs, J = T.n_jammers, R = T.n_radars, K = T.n_targets, RK = R * K;
+  const int step = io.step_count[e] + 1;                             // environment.py:235
+  double r_p = 0.0, r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
+  uint64_t supp_mask = 0, hit_mask = 0;
+  // Philox yields four uniforms per call: slots 4q .. 4q + 3 share one
+  Philox4 px = {0u, 0u, 0u, 0u};
+  int px_q = -1;
+  auto uniform = [&](int slot) -> float {
+    if (io.noise) return io.noise[(int64_t)e * (RK + J) + slot];
+    if ((slot >> 2) != px_q) {
+      px_q = slot >> 2;
+      px = philox4x32_10((uint32_t)px_q, (uint32_t)step, (uint32_t)e, kStreamEnvNoise, (uint32_t)io.seed, (uint32_t)(io.seed >> 32));
+    }
+    const int q = slot & 3;
+    return u01(q == 0 ? px.x : q == 1 ? px.y : q == 2 ? px.z : px.w);
+  };
+  // ---- jammers (environment.py:248-302, core/jammer.py:73-98), in jammer order
+  for (int j = 0; j < J; ++j) {
+    const int Ti = act_d[j];
+    double P = (double)act_p[j];
+    P = P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
+    const double pmin = dv(D.pmin + j), pmax = dv(D.pmax + j);
+    const double range = pmax - pmin;
+    const double power = pmin + P * range;
+    const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
+    r_p += T.rp_max + (T.rp_min - T.rp_max) * norm;                // charged even when idle
+    if (io.jam_power) io.jam_power[(int64_t)j * n + e] = (float)power;
+    int code = 0;
+    double val = 0.0;
+    if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
+      const int tgt = (Ti + 1) / 2 - 1;
+      const double den = dv(D.den + j * R + tgt);
+      if (den >= 0.0) {                                              // farther than 1e-6 from the radar
+        double prj = 0.0;
+        if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * dv(D.gj + j) * dv(D.gr + tgt)) / den);
+        if (Ti & 1) {                                                // suppression
+          code = (tgt << 2) | 1; val = prj;
+          supp_mask |= 1ull << tgt;
+        } else {                                                     // deception: false target (environment.py:408-437)
+          const double pn = dv(D.pn + tgt);
+          double snr_f = pn > 1e-18 ? (dv(D.dd + tgt) * prj) / pn : 0.0;
+          snr_f = fmax(0.0, snr_f);
+          const double pd_f = albersheim(T, snr_f);
+          if ((double)uniform(RK + j) <= pd_f) {
+            code = (tgt << 2) | 2; val = 1.0 - fmin(pd_f, 0.999999);
+            hit_mask |= 1ull << tgt;
+          }
+        }
       }
     }
-    auto dv = [&](int row) -> double { return kStaged ? srows[row * kEnv2Envs + tid] : __ldg(dcol + (int64_t)row * drs); };
-    // from here on the kernel reads the actions and writes outputs: wait for the preceding kernel of the stream
-    grid_dependency_wait();
-    if (live && !a.physics) io.step_count[e] = 0;                      // environment.py:203
-    if (live && a.physics) {
-      const int step = io.step_count[e] + 1;                           // environment.py:235
-      double r_p = 0.0, r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
-      uint64_t supp_mask = 0, hit_mask = 0;
-      // Philox yields four uniforms per call: slots 4q .. 4q + 3 share one
-      Philox4 px = {0u, 0u, 0u, 0u};
-      int px_q = -1;
-      auto uniform = [&](int slot) -> float {
-        if (io.noise) return io.noise[(int64_t)e * (RK + J) + slot];
-        if ((slot >> 2) != px_q) {
-          px_q = slot >> 2;
-          px = philox4x32_10((uint32_t)px_q, (uint32_t)step, (uint32_t)e, kStreamEnvNoise, (uint32_t)io.seed, (uint32_t)(io.seed >> 32));
-        }
-        const int q = slot & 3;
-        return u01(q == 0 ? px.x : q == 1 ? px.y : q == 2 ? px.z : px.w);
-      };
-      // ---- jammers (environment.py:248-302, core/jammer.py:73-98), in jammer order
-      for (int j = 0; j < J; ++j) {
-        const int Ti = io.act_d[(int64_t)e * J + j];
-        double P = (double)io.act_p[(int64_t)e * J + j];
-        P = P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
-        const double pmin = dv(D.pmin + j), pmax = dv(D.pmax + j);
-        const double range = pmax - pmin;
-        const double power = pmin + P * range;
-        const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
-        r_p += T.rp_max + (T.rp_min - T.rp_max) * norm;              // charged even when idle
-        if (io.jam_power) io.jam_power[(int64_t)j * n + e] = (float)power;
-        int code = 0;
-        double val = 0.0;
-        if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
-          const int tgt = (Ti + 1) / 2 - 1;
-          const double den = dv(D.den + j * R + tgt);
-          if (den >= 0.0) {                                            // farther than 1e-6 from the radar
-            double prj = 0.0;
-            if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * dv(D.gj + j) * dv(D.gr + tgt)) / den);
-            if (Ti & 1) {                                              // suppression
-              code = (tgt << 2) | 1; val = prj;
-              supp_mask |= 1ull << tgt;
-            } else {                                                   // deception: false target (environment.py:408-437)
-              const double pn = dv(D.pn + tgt);
-              double snr_f = pn > 1e-18 ? (dv(D.dd + tgt) * prj) / pn : 0.0;
-              snr_f = fmax(0.0, snr_f);
-              const double pd_f = albersheim(T, snr_f);
-              if ((double)uniform(RK + j) <= pd_f) {
-                code = (tgt << 2) | 2; val = 1.0 - fmin(pd_f, 0.999999);
-                hit_mask |= 1ull << tgt;
-              }
-            }
-          }
-        }
-        rec_val[j * kEnv2Envs + tid] = val;
-        rec_code[j * kEnv2Envs + tid] = code;
-      }
-      const bool want_net = io.pd_net != nullptr;
-      if (want_net)
-        for (int k = 0; k < K; ++k) pnet[k * kEnv2Envs + tid] = 1.0;
-      // ---- radars x targets (environment.py:316-349, 359-366, 385-398), in radar order
-      for (int r = 0; r < R; ++r) {
-        const bool supp = (supp_mask >> r) & 1ull, hit = (hit_mask >> r) & 1ull;
-        double prjs = 0.0, prod = 1.0;
-        if (supp || hit)
-          for (int j = 0; j < J; ++j) {                                // this radar's jammers, in jammer order
-            const int code = rec_code[j * kEnv2Envs + tid];
-            if ((code >> 2) == r) {
-              if ((code & 3) == 1) prjs += rec_val[j * kEnv2Envs + tid];
-              else if ((code & 3) == 2) prod *= rec_val[j * kEnv2Envs + tid];
-            }
-          }
-        double jam = 0.0, den1 = 0.0;
-        if (supp) { jam = dv(D.dd + r) * prjs; den1 = jam + dv(D.pn + r); }
-        bool tracked = false;
-        double red = 0.0;
-        for (int k = 0; k < K; ++k) {
-          const int slot = r * K + k;
-          const double pd0 = dv(D.pd0 + slot);
-          double pd = pd0, sig = 0.0, snr1 = 0.0;
-          const bool need_sig = supp || io.jsr_db != nullptr;
-          if (need_sig) sig = dv(D.sig + slot);
-          if (supp) {
-            snr1 = den1 > 1e-18 ? sig / den1 : 0.0;
-            pd = albersheim(T, snr1);
-            red += fmax(0.0, pd0 - pd);                                // P_d without jamming only matters here (r_j)
-          }
-          const bool det = (double)uniform(slot) <= pd;
-          tracked |= det;
-          if (want_net) pnet[k * kEnv2Envs + tid] *= (1.0 - pd);
-          const int64_t o = (int64_t)slot * n + e;
-          if (io.pd) io.pd[o] = (float)pd;
-          if (io.detected) io.detected[o] = det ? 1 : 0;
-          if (io.snr0 || io.snr1) {
-            const float s0 = (float)dv(D.snr0 + slot);
-            if (io.snr0) io.snr0[o] = s0;
-            if (io.snr1) io.snr1[o] = supp ? (float)fmax(0.0, snr1) : s0;
-          }
-          if (io.jsr_db) io.jsr_db[o] = 10.0f * log10f((float)(jam / sig));   // float32 output of an extension: float log
-        }
-        if (io.tracking) io.tracking[(int64_t)r * n + e] = tracked ? 1 : 0;
-        if (tracked) r_d += dv(D.rdt + r);
-        if (supp) r_j_supp += red;
-        if (hit) r_j_dec += 1.0 - prod;
-      }
-      if (want_net)
-        for (int k = 0; k < K; ++k) io.pd_net[(int64_t)k * n + e] = (float)(1.0 - pnet[k * kEnv2Envs + tid]);
-      const double r_j = r_j_supp + r_j_dec;
-      const double reward = r_d + r_p + r_j;                           // environment.py:457
-      const bool term = step >= T.episode_limit;                       // environment.py:460
-      io.reward[e] = (float)reward;
-      if (io.reward64) io.reward64[e] = reward;
-      if (io.r_d) io.r_d[e] = (float)r_d;
-      if (io.r_p) io.r_p[e] = (float)r_p;
-      if (io.r_j) io.r_j[e] = (float)r_j;
-      if (io.terminated) io.terminated[e] = term ? 1 : 0;
-      io.step_count[e] = (term && io.auto_reset) ? 0 : step;
-    }
-    return;
+    rec_val[j * sstride + sidx] = val;
+    rec_code[j * sstride + sidx] = code;
   }
+  const bool want_net = io.pd_net != nullptr;
+  if (want_net)
+    for (int k = 0; k < K; ++k) pnet[k * sstride + sidx] = 1.0;
+  // ---- radars x targets (environment.py:316-349, 359-366, 385-398), in radar order
+  for (int r = 0; r < R; ++r) {
+    const bool supp = (supp_mask >> r) & 1ull, hit = (hit_mask >> r) & 1ull;
+    double prjs = 0.0, prod = 1.0;
+    if (supp || hit)
+      for (int j = 0; j < J; ++j) {                                  // this radar's jammers, in jammer order
+        const int code = rec_code[j * sstride + sidx];
+        if ((code >> 2) == r) {
+          if ((code & 3) == 1) prjs += rec_val[j * sstride + sidx];
+          else if ((code & 3) == 2) prod *= rec_val[j * sstride + sidx];
+        }
+      }
+    double jam = 0.0, den1 = 0.0;
+    if (supp) { jam = dv(D.dd + r) * prjs; den1 = jam + dv(D.pn + r); }
+    bool tracked = false;
+    double red = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const int slot = r * K + k;
+      const double pd0 = dv(D.pd0 + slot);
+      double pd = pd0, sig = 0.0, snr1 = 0.0;
+      const bool need_sig = supp || io.jsr_db != nullptr;
+      if (need_sig) sig = dv(D.sig + slot);
+      if (supp) {
+        snr1 = den1 > 1e-18 ? sig / den1 : 0.0;
+        pd = albersheim(T, snr1);
+        red += fmax(0.0, pd0 - pd);                                  // P_d without jamming only matters here (r_j)
+      }
+      const bool det = (double)uniform(slot) <= pd;
+      tracked |= det;
+      if (want_net) pnet[k * sstride + sidx] *= (1.0 - pd);
+      const int64_t o = (int64_t)slot * n + e;
+      if (io.pd) io.pd[o] = (float)pd;
+      if (io.detected) io.detected[o] = det ? 1 : 0;
+      if (io.snr0 || io.snr1) {
+        const float s0 = (float)dv(D.snr0 + slot);
+        if (io.snr0) io.snr0[o] = s0;
+        if (io.snr1) io.snr1[o] = supp ? (float)fmax(0.0, snr1) : s0;
+      }
+      if (io.jsr_db) io.jsr_db[o] = 10.0f * log10f((float)(jam / sig));   // float32 output of an extension: float log
+    }
+    if (io.tracking) io.tracking[(int64_t)r * n + e] = tracked ? 1 : 0;
+    if (tracked) r_d += dv(D.rdt + r);
+    if (supp) r_j_supp += red;
+    if (hit) r_j_dec += 1.0 - prod;
+  }
+  if (want_net)
+    for (int k = 0; k < K; ++k) io.pd_net[(int64_t)k * n + e] = (float)(1.0 - pnet[k * sstride + sidx]);
+  const double r_j = r_j_supp + r_j_dec;
+  const double reward = r_d + r_p + r_j;                             // environment.py:457
+  const bool term = step >= T.episode_limit;                         // environment.py:460
+  io.reward[e] = (float)reward;
+  if (io.reward64) io.reward64[e] = reward;
+  if (io.r_d) io.r_d[e] = (float)r_d;
+  if (io.r_p) io.r_p[e] = (float)r_p;
+  if (io.r_j) io.r_j[e] = (float)r_j;
+  if (io.terminated) io.terminated[e] = term ? 1 : 0;
+  io.step_count[e] = (term && io.auto_reset) ? 0 : step;
+}
 
-  // ============================================================================= views: warps 1-3, 32 envs
-  // (environment.py:479-551; nothing here depends on the actions, but the destinations may be read by the
-  // preceding kernel: wait before the first store)
-  const int vt = tid - kEnv2Envs, VT = kEnv2Threads - kEnv2Envs;
-  grid_dependency_wait();
+// The static views (environment.py:479-551) of envs [e0, e0 + valid): thread vt of VT cooperating threads.
+__device__ __forceinline__ void env2_views(const Env2Args& a, const macjd_env_io& io, int e0, int valid, int vt, int VT) {
+  const macjd_env_tables& T = a.tab;
+  const int J = T.n_jammers, S = a.state_dim, A = a.n_actions;
+  const bool shared_scn = T.env_stride == 0;
   if (valid <= 0) return;
   const float* src_rows = a.state_rows + (shared_scn ? 0 : (int64_t)e0 * S);
   if ((S & 3) == 0) {
@@ -384,13 +351,81 @@ __global__ void __launch_bounds__(kEnv2Threads) env_step2_kernel(const Env2Args 
   }
 }
 
+template <bool kStaged>
+__global__ void __launch_bounds__(kEnv2Threads) env_step2_kernel(const Env2Args a) {
+  const macjd_env_tables& T = a.tab;
+  const macjd_env_io& io = a.io;
+  const DerivedRows& D = a.rows;
+  const int n = T.n_envs, J = T.n_jammers, K = T.n_targets;
+  const int tid = (int)threadIdx.x;
+  const int e0 = a.env_begin + blockIdx.x * kEnv2Envs;
+  const int valid = min(kEnv2Envs, a.env_end - e0);
+  const bool shared_scn = T.env_stride == 0;
+  MACJD_DYNAMIC_SMEM(double, smem);
+
+  if (tid < kEnv2Envs) {
+    // =========================================================================== physics: thread = env
+    const int e = e0 + tid;
+    const bool live = tid < valid;
+    const int64_t drs = shared_scn ? 1 : (int64_t)n;                   // derived row stride
+    const double* dcol = T.derived + (shared_scn ? 0 : (live ? e : e0));
+    // per-thread scratch [slot][32]: jammer records (value, code), networked-Pd products
+    double* rec_val = smem;                                            // [J][32]
+    int* rec_code = reinterpret_cast<int*>(rec_val + (size_t)J * kEnv2Envs);   // [J][32]
+    double* pnet = rec_val + (size_t)J * kEnv2Envs + ((size_t)J * kEnv2Envs + 1) / 2;   // [K][32]
+    double* srows = pnet + (size_t)K * kEnv2Envs;                      // [rows][32] when kStaged
+    if (kStaged && a.physics && live) {
+#pragma unroll 1
+      for (int row0 = 0; row0 < D.total; row0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (row0 + i < D.total) ? __ldg(dcol + (int64_t)(row0 + i) * drs) : 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (row0 + i < D.total) srows[(row0 + i) * kEnv2Envs + tid] = v[i];
+      }
+    }
+    auto dv = [&](int row) -> double { return kStaged ? srows[row * kEnv2Envs + tid] : __ldg(dcol + (int64_t)row * drs); };
+    // from here on the kernel reads the actions and writes outputs: wait for the preceding kernel of the stream
+    grid_dependency_wait();
+    if (live && !a.physics) io.step_count[e] = 0;                      // environment.py:203
+    if (live && a.physics)
+      env2_physics(a, io, e, dv, io.act_d + (int64_t)e * J, io.act_p + (int64_t)e * J, rec_val, rec_code, pnet, kEnv2Envs, tid);
+    return;
+  }
+
+  // ============================================================================= views: warps 1-3, 32 envs
+  // (nothing here depends on the actions, but the destinations may be read by the preceding kernel: wait before
+  // the first store)
+  grid_dependency_wait();
+  env2_views(a, io, e0, valid, tid - kEnv2Envs, kEnv2Threads - kEnv2Envs);
+}
+
 inline size_t env2_smem_bytes(int J, int K, int staged_rows) {
   return ((size_t)J * kEnv2Envs + ((size_t)J * kEnv2Envs + 1) / 2 + (size_t)K * kEnv2Envs + (size_t)staged_rows * kEnv2Envs) * sizeof(double);
 }
 
+// kernel arguments of one step (also used by the agent kernel when it runs the step itself)
+inline Env2Args env2_args(const macjd_env_tables* tab, const macjd_env_io* io, int physics);
+
 inline int env2_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
   const int n_step = io->env_count > 0 ? io->env_count : tab->n_envs - io->env_begin;
   if (n_step == 0) return MACJD_OK;
+  Env2Args a = env2_args(tab, io, physics);
+  // Small scenarios: the physics warp parks its envs' derived rows in shared memory ahead of the dependency wait
+  // (behind the agent kernel that wait is long and the copy free; every later lookup is a shared-memory read on the
+  // dependent chain).  Large scenarios read the few rows a step needs straight from L2.
+  a.stage_rows = (physics && (io->flags & MACJD_ENV_FOLLOWS_AGENT) && a.rows.total <= 96 && tab->env_stride != 0) ? 1 : 0;
+  const size_t smem = env2_smem_bytes(tab->n_jammers, tab->n_targets, a.stage_rows ? a.rows.total : 0);
+  if (smem > 48 * 1024) return MACJD_ERR_UNSUPPORTED;
+  const int grid = (n_step + kEnv2Envs - 1) / kEnv2Envs;
+  if (a.stage_rows) MACJD_LAUNCH(env_step2_kernel<true>, grid, kEnv2Threads, smem, (cudaStream_t)ctx->stream, a);
+  else MACJD_LAUNCH(env_step2_kernel<false>, grid, kEnv2Threads, smem, (cudaStream_t)ctx->stream, a);
+  return MACJD_OK;
+}
+
+inline Env2Args env2_args(const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
+  const int n_step = io->env_count > 0 ? io->env_count : tab->n_envs - io->env_begin;
   Env2Args a;
   a.tab = *tab;
   a.io = *io;
@@ -403,20 +438,12 @@ inline int env2_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const 
   a.env_end = io->env_begin + n_step;
   {
     const uint64_t s4 = (uint64_t)a.state_dim / 4, js4 = (uint64_t)tab->n_jammers * s4;
-    const bool ok = (a.state_dim % 4 == 0) && s4 >= 2 && (uint64_t)kEnv2Envs * js4 * js4 < 0x100000000ull;
+    const bool ok = (a.state_dim % 4 == 0) && s4 >= 2 && 64ull * js4 * js4 < 0x100000000ull;   // (<= 64 envs per copying block)
     a.magic_s4 = ok ? (uint32_t)((0x100000000ull + s4 - 1) / s4) : 0;
     a.magic_js4 = ok ? (uint32_t)((0x100000000ull + js4 - 1) / js4) : 0;
   }
-  // Small scenarios: the physics warp parks its envs' derived rows in shared memory ahead of the dependency wait
-  // (behind the agent kernel that wait is long and the copy free; every later lookup is a shared-memory read on the
-  // dependent chain).  Large scenarios read the few rows a step needs straight from L2.
-  a.stage_rows = (physics && (io->flags & MACJD_ENV_FOLLOWS_AGENT) && a.rows.total <= 96 && tab->env_stride != 0) ? 1 : 0;
-  const size_t smem = env2_smem_bytes(tab->n_jammers, tab->n_targets, a.stage_rows ? a.rows.total : 0);
-  if (smem > 48 * 1024) return MACJD_ERR_UNSUPPORTED;
-  const int grid = (n_step + kEnv2Envs - 1) / kEnv2Envs;
-  if (a.stage_rows) MACJD_LAUNCH(env_step2_kernel<true>, grid, kEnv2Threads, smem, (cudaStream_t)ctx->stream, a);
-  else MACJD_LAUNCH(env_step2_kernel<false>, grid, kEnv2Threads, smem, (cudaStream_t)ctx->stream, a);
-  return MACJD_OK;
+  a.stage_rows = 0;
+  return a;
 }
 
 // environment.py:221-477 / :208-219 for the whole batch: on the derived tables when the caller prepared them

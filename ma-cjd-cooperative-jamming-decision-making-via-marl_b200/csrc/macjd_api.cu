@@ -154,6 +154,47 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   return finish(ctx, macjd::agent_launch(ctx, w, io));
 }
 
+// One timestep on the device: agent step, then the env step on the actions it chose.  One launch when the CTA-pair
+// kernel can run both (macjd_rollout_fused_supported), else the two kernels back to back (the env step as a
+// programmatic dependent of the agent step).  Same results either way.
+int macjd_rollout_step(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
+                       const macjd_env_tables* tab, const macjd_env_io* eio) {
+  MACJD_ENTER(ctx);
+  if (!w || !aio || !tab || !eio) return MACJD_ERR_INVALID_ARG;
+  if (aio->n_steps != 1 || aio->part != 0 || !aio->actions || !aio->power) return MACJD_ERR_INVALID_ARG;
+  if ((int64_t)aio->n_rows != (int64_t)tab->n_envs * tab->n_jammers) return MACJD_ERR_INVALID_ARG;
+  macjd_env_io ke = *eio;
+  ke.act_d = aio->actions;
+  ke.act_p = aio->power;
+  int st = macjd::env_check_args(ctx, tab, &ke, /*physics=*/1);
+  if (st != MACJD_OK) return st;
+  if (aio->n_rows == 0) return MACJD_OK;
+#ifndef MACJD_TEST_HOST_EMULATION
+  if (aio->path != 1 && ke.env_begin == 0 && ke.env_count == 0 && macjd::tc::agent_tc_supported(*w) &&
+      macjd::tc::agent_tc2_fuse_supported(*w, *tab)) {
+    if (aio->n_rows < 0 || !aio->obs) return MACJD_ERR_INVALID_ARG;
+    macjd::AgentArgs a;
+    a.w = *w;
+    a.io = *aio;
+    const macjd::Env2Args e = macjd::env2_args(tab, &ke, 1);
+    return finish(ctx, macjd::tc::agent_tc2_launch(ctx, a, &e));
+  }
+#endif
+  st = macjd_agent_forward(ctx, w, aio);
+  if (st != MACJD_OK) return st;
+  ke.flags |= MACJD_ENV_FOLLOWS_AGENT;
+  return macjd_env_step(ctx, tab, &ke);
+}
+
+int macjd_rollout_fused_supported(const macjd_agent_weights* w, const macjd_env_tables* tab) {
+#ifndef MACJD_TEST_HOST_EMULATION
+  return (w && tab && macjd::tc::agent_tc_supported(*w) && macjd::tc::agent_tc2_fuse_supported(*w, *tab)) ? 1 : 0;
+#else
+  (void)w; (void)tab;
+  return 0;
+#endif
+}
+
 int macjd_agent_pair_supported(const macjd_agent_weights* w) {
 #ifndef MACJD_TEST_HOST_EMULATION
   return (w && macjd::tc::agent_tc2_supported(*w)) ? 1 : 0;
@@ -404,7 +445,6 @@ int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, 
     if (!a_obs) st = copy_async(const_cast<float*>(ka.obs), ahost->obs + rb * O, rc * O * sizeof(float), cudaMemcpyHostToDevice, c);
     if (st == MACJD_OK && ahost->avail && !a_avail)
       st = copy_async(const_cast<uint8_t*>(ka.avail), ahost->avail + rb * A, rc * A, cudaMemcpyHostToDevice, c);
-    if (st == MACJD_OK) st = macjd_agent_forward(c, w, &ka);
     if (st != MACJD_OK) break;
     // ---- env: reads the chosen actions where the agent kernel left them
     macjd_env_io ke = *eio;
@@ -417,7 +457,13 @@ int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, 
     if (e_term) ke.terminated = e_term;
     if (e_obs) ke.obs = e_obs;
     if (e_state) ke.state = e_state;
-    st = macjd_env_step(c, tab, &ke);
+    if (n_groups == 1) {
+      ke.env_begin = ke.env_count = 0;
+      st = macjd_rollout_step(c, w, &ka, tab, &ke);      // one launch when the pair kernel can run both
+    } else {
+      st = macjd_agent_forward(c, w, &ka);
+      if (st == MACJD_OK) st = macjd_env_step(c, tab, &ke);
+    }
   }
   // ---- what the kernels did not write in place (after both chains are issued: copies queue behind their group)
   for (int g = 0; g < n_groups && st == MACJD_OK; ++g) {

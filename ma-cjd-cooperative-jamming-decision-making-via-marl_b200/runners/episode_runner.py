@@ -167,6 +167,9 @@ class BatchedEpisodeRunner:
                      "avail_actions": z((T + 1, n, Nn, A), torch.uint8), "reward": z((T, n, 1), torch.float32),
                      "terminated": z((T, n, 1), torch.uint8), "hidden_state": z((T + 1, n, Nn, H), torch.float32)}
         self.r_parts = z((3, T, n), torch.float32)
+        # True: a timestep is one macjd_rollout_step call (the library fuses agent step and env step into one launch
+        # when it can, include/macjd.h); False: macjd_agent_forward + macjd_env_step.  Same results.
+        self.fused_step = bool(getattr(args, "fused_rollout_step", True))
 
     def _build_step_structs(self):
         """All pointers of a timestep are fixed (persistent trajectory buffers), so the C structs
@@ -210,8 +213,12 @@ class BatchedEpisodeRunner:
             aio = self._agent_io[t]
             aio.epsilon, aio.rng_step, aio.test_mode = float(eps), mac._rng_step & 0xFFFFFFFF, int(test_mode)
             lib, ctx = mac.agent.lib(), mac.agent._ctx()
-            lib.call("macjd_agent_forward", ctx, mac.agent.packed().cstruct(), aio)
-            lib.call("macjd_env_step", ctx, env._ctab, self._env_io[t])
+            if self.fused_step:
+                # one call; ONE launch when the CTA-pair kernel can run the env step of its rows' envs itself
+                lib.call("macjd_rollout_step", ctx, mac.agent.packed().cstruct(), aio, env._ctab, self._env_io[t])
+            else:
+                lib.call("macjd_agent_forward", ctx, mac.agent.packed().cstruct(), aio)
+                lib.call("macjd_env_step", ctx, env._ctab, self._env_io[t])
             self.t_env += self.n_envs
             return
         mac.agent.run(tr["obs"][t].view(1, n * Nn, -1), mac.hidden_states, avail=tr["avail_actions"][t],
@@ -294,8 +301,11 @@ class BatchedEpisodeRunner:
         with torch.cuda.graph(graph):
             ctx = mac.agent._ctx()                         # the capture stream
             for t in range(T):
-                lib.call("macjd_agent_forward", ctx, wts, aios[t])
-                lib.call("macjd_env_step", ctx, env._ctab, self._env_io[t])
+                if self.fused_step:
+                    lib.call("macjd_rollout_step", ctx, wts, aios[t], env._ctab, self._env_io[t])
+                else:
+                    lib.call("macjd_agent_forward", ctx, wts, aios[t])
+                    lib.call("macjd_env_step", ctx, env._ctab, self._env_io[t])
         self._graph = {"key": key, "graph": graph, "eps_dev": eps_dev, "rng_dev": rng_dev, "keep": (aios, wts),
                        "eps_host": torch.zeros(T, dtype=torch.float32).pin_memory(),
                        "rng_host": torch.zeros(T, dtype=torch.int32).pin_memory()}

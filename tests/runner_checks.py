@@ -316,3 +316,54 @@ def check_main_loop(device, lib, tmp_path):
         M.load_config("nope", str(tmp_path))
     cfg = M.default_config(lr=1e-4)
     assert cfg.lr == 1e-4 and cfg.batch_size == 32 and cfg.target_update_interval == 200
+
+
+def check_fused_rollout_step(device, lib, n_envs=300, kind="c2", path=0, expect_fused=None):
+    """macjd_rollout_step (one launch when the CTA-pair kernel can run the env step of its rows' envs itself)
+    against macjd_agent_forward + macjd_env_step: whole episodes with device Philox draws on twin runners must be
+    bit-identical in every trajectory tensor, reward part and step counter."""
+    import copy
+    from macjd_b200 import _native as N
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import hetero_spec, scaled_spec
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
+    if kind == "c2":
+        spec, dims = hetero_spec(n_envs, seed=31, active=True, episode_limit=5), dict()
+        J, S, A = 2, 24, 5
+    elif kind == "c3":
+        J, R, K = 8, 16, 4
+        spec = scaled_spec(n_envs, n_jammers=J, n_radars=R, n_targets=K, seed=32, episode_limit=5)
+        S, A = R * 10 + 2 * J, 2 * R + 1
+    else:                       # 3 jammers: a CTA's 64 rows are not whole envs -> two launches
+        J, R, K = 3, 2, 2
+        spec = scaled_spec(n_envs, n_jammers=J, n_radars=R, n_targets=K, seed=33, episode_limit=5)
+        S, A = R * 10 + 2 * J, 2 * R + 1
+    args = rl_args(device, episode_limit=5, n_agents=J, n_actions=A, state_shape=S, obs_shape=S, rnn_hidden_dim=128,
+                   actor_hidden_dim=128, agent_kernel_path=path, epsilon_anneal_time=10 * n_envs)
+    torch.manual_seed(4)
+    mac0 = BasicMAC(S, args, _lib=lib)
+    if args.use_cuda:
+        mac0.cuda()
+    runners = []
+    for fused in (True, False):
+        env = ElectromagneticEnvironment(args, spec=spec, device=device, seed=17, _lib=lib)
+        r = BatchedEpisodeRunner(env, copy.deepcopy(mac0), None, args)
+        r.fused_step = fused
+        runners.append(r)
+    if expect_fused is not None and lib is None:
+        fn = N.get_lib().lib.macjd_rollout_fused_supported
+        fn.restype = N.C.c_int
+        got = fn(N.C.byref(runners[0].mac.agent.packed().cstruct()), N.C.byref(runners[0].env._ctab))
+        assert bool(got) == expect_fused
+    for ep in range(2):
+        for r in runners:
+            r.run(store=False)
+        a, b = runners
+        for k in a.traj:
+            assert torch.equal(a.traj[k], b.traj[k]), (ep, k)
+        assert torch.equal(a.r_parts, b.r_parts)
+        assert torch.equal(a.env.step_count, b.env.step_count)
+        for k in ("pd", "detected", "tracking", "snr1", "jam_power", "pd_net", "reward64"):
+            assert torch.equal(getattr(a.env, k), getattr(b.env, k)), (ep, k)
+        assert bool(a.traj["terminated"][-1].all()) and not bool(a.traj["terminated"][0].any())

@@ -34,3 +34,8 @@ def test_main_loop(tmp_path):
 
 def test_fast_path_chains_hidden_state():
     RC.check_fast_path_chains_hidden_state("cpu", emul_lib())
+
+
+def test_rollout_step_call_equals_two_calls():
+    """macjd_rollout_step without the tensor-core kernel (host emulation): the two kernels behind one call."""
+    RC.check_fused_rollout_step("cpu", emul_lib(), n_envs=9, kind="c2", path=1)

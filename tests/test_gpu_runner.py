@@ -41,3 +41,9 @@ def test_main_loop(tmp_path):
 
 def test_fast_path_chains_hidden_state():
     RC.check_fast_path_chains_hidden_state("cuda", None)
+
+
+@pytest.mark.parametrize("kind,n_envs,path,fused", [("c2", 300, 0, True), ("c2", 4096, 0, True), ("c2", 33, 1, None),
+                                                    ("c3", 100, 0, True), ("c3", 1030, 0, True), ("j3", 200, 0, False)])
+def test_fused_rollout_step_equals_two_kernels(kind, n_envs, path, fused):
+    RC.check_fused_rollout_step("cuda", None, n_envs=n_envs, kind=kind, path=path, expect_fused=fused)
