@@ -415,6 +415,10 @@ def main():
         barrier()
         dt = reduce_max(dt)
         res = {"value": world * M * K_ / dt, "ms_per_step": dt / K_ * 1e3, "M": M}
+        from macjd_b200 import _native as N_
+        fn = N_.get_lib().lib.macjd_rollout_fused_supported
+        fn.restype = N_.C.c_int
+        res["fused"] = bool(runner.fused_step and fn(N_.C.byref(mac.agent.packed().cstruct()), N_.C.byref(env._ctab)))
 
         # ---- the two launches of one timestep, each alone (cached C structs: one ctypes call per launch)
         if getattr(runner, "_structs_for", None) != (mac.hidden_states.data_ptr(), mac.agent.path):
@@ -554,7 +558,9 @@ def main():
     learner = QMixLearner(mac, rl)
     r2 = rollout_bench(env, mac, runner, K, W, with_e2e=True)
     M = r2["M"]
-    line.update({"value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e": r2["e2e"], "gpu_launches": 2 * K,
+    line["config"]["launches_per_step"] = ("1: macjd_rollout_step, the CTA-pair agent kernel also runs the env step of its rows' envs"
+                                           if r2["fused"] else "2: agent_forward kernel + env_step kernel (programmatic dependent launch)")
+    line.update({"value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e": r2["e2e"], "gpu_launches": (1 if r2["fused"] else 2) * K,
                  "roofline": agent_roofline(mac, M, r2["dt_agent"], r2["dt_simt"], OBS, N_ACTIONS, HID),
                  "roofline_env": env_roofline(n_envs, r2["dt_env"], ENV_BYTES_PER_STEP, "dram_bytes_per_launch_at_bench_size"),
                  "parity": r2.get("parity"),
@@ -627,6 +633,7 @@ def main():
                            f"({n3 * world} over {world} GPU{'s' if world > 1 else ''}; BASELINE.json configs[2] = 65 536 over 8), "
                            "per-env scenario tables; L2 flushed between steps",
                "value": r3["value"], "unit": "env-agent steps/s", "ms_per_step": r3["ms_per_step"], "steps": k3, "scaling": "weak",
+               "launches_per_step": 1 if r3["fused"] else 2,
                "env_only": {"value": world * M3 / r3["dt_env"], "us_per_launch": r3["dt_env"] * 1e6},
                "act_only": {"value": world * M3 / r3["dt_agent"], "us_per_launch": r3["dt_agent"] * 1e6},
                "roofline": agent_roofline(mac3, M3, r3["dt_agent"], r3["dt_simt"], S3, A3, HID),

@@ -714,9 +714,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       if (mode == 0 || mode == 2) {
       // ---- E5: Q tail, outputs, selection
       if (kFuseEnv) {
-        // the next timestep's state / obs / avail of this CTA's envs, while the Q-head product runs
-        const int Je = p.env.tab.n_jammers;
-        env2_views(p.env, p.env.io, row0 / Je, valid / Je, tid, kT2EpiThreads);
+        // while the Q-head product runs: this CTA's envs' derived scenario rows -> the xf tile's hi half (dead since
+        // the input products completed; the physics below reads them from shared memory), and the next timestep's
+        // state / obs / avail of those envs
+        const int Je = p.env.tab.n_jammers, ne = valid / Je;
+        if (p.env.tab.env_stride != 0) {                 // (a shared scenario is one block: read in place)
+          const double2* src = reinterpret_cast<const double2*>(p.env.tab.derived + (int64_t)(row0 / Je) * p.env.rows.total);
+          double2* dst = reinterpret_cast<double2*>(S.b0hi);
+          const int n2 = ne * p.env.rows.total / 2;
+#pragma unroll 4
+          for (int i = tid; i < n2; i += kT2EpiThreads) dst[i] = __ldg(src + i);
+        }
+        env2_views(p.env, p.env.io, row0 / Je, ne, tid, kT2EpiThreads);
       }
       if (mode == 0) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }   // heads only: q.0 finished with actor.2
       else epi_bar_sync();                                                  // ... but P (written by E2's last stage) must be visible
@@ -855,19 +864,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       }
       if (kFuseEnv) {
         // ---- the environment step of this CTA's envs on the actions just chosen (environment.py:221-477)
-        epi_bar_sync();                 // actions staged; red (the scratch below) is free
+        epi_bar_sync();                 // actions staged
         const Env2Args& E = p.env;
-        const int Je = E.tab.n_jammers, epc = kTcRows / Je;
-        if (part == 0 && live && (r % Je) == 0) {
-          const int e = (row0 + r) / Je;
-          const bool shared_scn = E.tab.env_stride == 0;
-          const int64_t drs = shared_scn ? 1 : (int64_t)E.tab.n_envs;
-          const double* dcol = E.tab.derived + (shared_scn ? 0 : e);
-          auto dv = [&](int row) -> double { return __ldg(dcol + (int64_t)row * drs); };
-          double* rec_val = reinterpret_cast<double*>(S.red);                          // [J][epc]
-          int* rec_code = reinterpret_cast<int*>(rec_val + kTcRows);                   // [J][epc]
-          double* pnet = rec_val + kTcRows + kTcRows / 2;                              // [K][epc]
-          env2_physics(E, E.io, e, dv, S.act_s + r, S.pow_s + r, rec_val, rec_code, pnet, epc, r / Je);
+        const int Je = E.tab.n_jammers, epc = kTcRows / Je, G = E.group;
+        // groups of G lanes, one env each: the first epc * G epilogue threads (whole warps: epc * G is a multiple of 32)
+        if (tid < epc * G) {
+          const int slot = tid / G, g = tid - slot * G;
+          const bool env_live = slot < valid / Je;
+          const int e = row0 / Je + (env_live ? slot : 0);
+          const double* d = E.tab.env_stride == 0 ? E.tab.derived
+                                                  : reinterpret_cast<const double*>(S.b0hi) + (size_t)(env_live ? slot : 0) * E.rows.total;
+          env2_physics_group(E, E.io, e, env_live, g, G, d, S.act_s + slot * Je, S.pow_s + slot * Je);
         }
       }
       epi_bar_sync();                   // Ps / Qs / red are free for the next step
@@ -895,8 +902,11 @@ inline bool agent_tc2_supported(const macjd_agent_weights& w) {
 // The fused rollout step needs whole envs per CTA (64 % J == 0), derived scenario tables and room for the physics
 // scratch in the 8 KB reduction buffer.
 inline bool agent_tc2_fuse_supported(const macjd_agent_weights& w, const macjd_env_tables& t) {
-  return agent_tc2_supported(w) && t.derived != nullptr && t.n_jammers >= 1 && kTcRows % t.n_jammers == 0 &&
-         (size_t)t.n_targets * (kTcRows / t.n_jammers) * sizeof(double) + 1024 <= sizeof(float) * kT2Parts * 8 * kTcRows;
+  if (!agent_tc2_supported(w) || t.derived == nullptr || t.n_jammers < 1 || kTcRows % t.n_jammers != 0 || !env2_supported(t)) return false;
+  const int epc = kTcRows / t.n_jammers, G = env2_group(t.n_jammers, t.n_radars);
+  // one group of G lanes per env among the epilogue threads; the envs' derived blocks are staged in the xf tile's hi half
+  return epc * G <= kT2EpiThreads && (epc * G) % 32 == 0 &&
+         (size_t)derived_rows(t.n_jammers, t.n_radars, t.n_targets).total * epc * sizeof(double) <= sizeof(float) * kTcRows * kTcH;
 }
 
 inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a, const Env2Args* env = nullptr) {

@@ -9,38 +9,41 @@
 //   per radar               noise power, D, receive gain, the clipped tracking penalty (environment.py:365)
 //   per jammer-radar link   the Friis denominator d^2 L L_atm B_j (core/jammer.py:73-98)
 //   per env                 the float32 state row (environment.py:479-510), row-major
-// The step itself then costs one division per acting jammer, one Albersheim evaluation per deception attempt
-// and per target of a SUPPRESSED radar, and the Bernoulli draws: ~20 exponentials per env-step instead of 84
-// at 8 jammers x 16 radars x 4 targets, and a short dependent chain at the default scenario.  Sums and products
-// keep the reference's order (jammers in jammer order into each radar, radars in radar order), so the
-// outputs are those of env_step_kernel (env_step.cuh, kept for callers without derived tables).
+// stored as one contiguous block of doubles PER ENV (array of structures: a group of lanes working on one env reads
+// neighbouring addresses).  The step itself then costs one division per acting jammer, one Albersheim evaluation
+// per deception attempt and per target of a SUPPRESSED radar, and the Bernoulli draws.
 //
-// A block is 128 threads = 32 envs: warp 0 runs the physics (thread = env; outputs are [field][env], coalesced),
-// warps 1-3 copy the static views of the same 32 envs (state, obs = the state once per jammer, all-ones
-// availability: 6.3 KB per env-step at 8 x 16 x 4, the bulk of the kernel's traffic) with 16-byte stores,
-// concurrently.  Launched behind the agent kernel (programmatic dependent launch) the physics warp has the env's
-// derived rows in shared memory before it waits for the actions.
+// Mapping (north_star: "warp-shuffle reductions over radars and jammers"): a GROUP of G = 2^k >= max(J, R) lanes
+// steps one env -- lane j evaluates jammer j, then lane r evaluates radar r and its K targets; the jammer records
+// travel to the radar lanes by shuffles and are applied in jammer order, the per-radar terms are summed by
+// shuffles in radar order, so every sum and product has the reference's (sequential) order and value.
+// The stand-alone kernel runs 128 physics threads (128 / G envs, at most 32) and 128 view threads per block: the
+// view warps copy the static views of the same envs (state, obs = the state once per jammer, all-ones availability:
+// 6.3 KB per env-step at 8 x 16 x 4, the bulk of the kernel's traffic) with 16-byte loads and stores.  Scenario
+// values that do not depend on the actions are fetched before the dependency wait (programmatic dependent launch
+// behind the agent kernel).  The CTA-pair agent kernel calls the same device functions when it runs the env step
+// of its own rows' envs (agent_act_tc2.cuh, kFuseEnv).
 #pragma once
 #include "env_step.cuh"
 
 namespace macjd {
 
-// row indices of the derived table (doubles, [row][env] like the raw tables)
+// offsets (in doubles) inside one env's derived block
 struct DerivedRows {
-  int sig, pd0, snr0;      // [R*K] each
-  int pn, dd, rdt, gr;     // [R] each
-  int den;                 // [J*R]
-  int gj, pmin, pmax;      // [J] each
-  int total;
+  int pd0, sig, snr0;      // [R*K] each, slot = r * K + k
+  int rad;                 // [R][4]: pn, D, clipped tracking penalty, receive gain
+  int den;                 // [J][R] link denominators (-1: jammer closer than 1e-6 to the radar, no effect)
+  int jam;                 // [J][4]: gj, power_min, power_max, 0
+  int total;               // doubles per env (a multiple of 2: blocks stay 16-byte aligned)
 };
 __host__ __device__ inline DerivedRows derived_rows(int J, int R, int K) {
   DerivedRows d;
   int o = 0;
-  d.sig = o; o += R * K; d.pd0 = o; o += R * K; d.snr0 = o; o += R * K;
-  d.pn = o; o += R; d.dd = o; o += R; d.rdt = o; o += R; d.gr = o; o += R;
+  d.pd0 = o; o += R * K; d.sig = o; o += R * K; d.snr0 = o; o += R * K;
+  d.rad = o; o += 4 * R;
   d.den = o; o += J * R;
-  d.gj = o; o += J; d.pmin = o; o += J; d.pmax = o; o += J;
-  d.total = o;
+  d.jam = o; o += 4 * J;
+  d.total = (o + 1) & ~1;
   return d;
 }
 inline size_t env_derived_bytes(const macjd_env_tables& t) {
@@ -49,12 +52,19 @@ inline size_t env_derived_bytes(const macjd_env_tables& t) {
   const size_t dbl = (size_t)derived_rows(t.n_jammers, t.n_radars, t.n_targets).total * cols * sizeof(double);
   return ((dbl + 15) & ~(size_t)15) + ((cols * S * sizeof(float) + 15) & ~(size_t)15);
 }
-// the float32 state rows sit behind the double rows
+// the float32 state rows sit behind the double blocks
 __host__ __device__ inline const float* derived_state_rows(const macjd_env_tables& t) {
   const size_t cols = t.env_stride == 0 ? 1 : (size_t)t.n_envs;
   const size_t dbl = (size_t)derived_rows(t.n_jammers, t.n_radars, t.n_targets).total * cols * sizeof(double);
   return reinterpret_cast<const float*>(reinterpret_cast<const char*>(t.derived) + ((dbl + 15) & ~(size_t)15));
 }
+// lanes per env: the power of two that covers jammers and radars (<= 32)
+__host__ __device__ inline int env2_group(int J, int R) {
+  int g = 1;
+  while (g < J || g < R) g <<= 1;
+  return g;
+}
+inline bool env2_supported(const macjd_env_tables& t) { return t.n_jammers <= 32 && t.n_radars <= 32; }
 
 // ------------------------------------------------------------------------------------------ prepare
 __global__ void __launch_bounds__(128) env_prepare_kernel(const macjd_env_tables T, double* out, float* state_rows, int n_cols) {
@@ -67,8 +77,8 @@ __global__ void __launch_bounds__(128) env_prepare_kernel(const macjd_env_tables
   const int rs = (int)T.row_stride;
   auto tab = [&](int row) -> double { return env_tab(col, rs, row); };
   const DerivedRows D = derived_rows(J, R, K);
-  const int64_t ors = T.env_stride == 0 ? 1 : (int64_t)T.n_envs;       // same [row][env] convention as the raw table
-  auto put = [&](int row, double v) { out[(int64_t)row * ors + (T.env_stride == 0 ? 0 : e)] = v; };
+  double* blk = out + (int64_t)e * D.total;                            // this env's block
+  auto put = [&](int off, double v) { blk[off] = v; };
   const double four_pi3 = (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793) * (4.0 * 3.141592653589793);
   for (int r = 0; r < R; ++r) {
     const int rr = 16 * r;
@@ -92,10 +102,10 @@ __global__ void __launch_bounds__(128) env_prepare_kernel(const macjd_env_tables
       put(D.snr0 + r * K + k, snr0);
       put(D.pd0 + r * K + k, albersheim(T, snr0));
     }
-    put(D.pn + r, pn);
-    put(D.dd + r, Dd);
-    put(D.gr + r, gr);
-    put(D.rdt + r, fmin(fmax(-tab(rr + 9), T.rd_min), T.rd_max));
+    put(D.rad + 4 * r + 0, pn);
+    put(D.rad + 4 * r + 1, Dd);
+    put(D.rad + 4 * r + 2, fmin(fmax(-tab(rr + 9), T.rd_min), T.rd_max));
+    put(D.rad + 4 * r + 3, gr);
     for (int j = 0; j < J; ++j) {
       const int jr = jbase + 8 * j;
       const double dx = tab(jr + 4) - rx, dy = tab(jr + 5) - ry;
@@ -110,9 +120,10 @@ __global__ void __launch_bounds__(128) env_prepare_kernel(const macjd_env_tables
   }
   for (int j = 0; j < J; ++j) {
     const int jr = jbase + 8 * j;
-    put(D.gj + j, tab(jr + 0));
-    put(D.pmin + j, tab(jr + 6));
-    put(D.pmax + j, tab(jr + 7));
+    put(D.jam + 4 * j + 0, tab(jr + 0));
+    put(D.jam + 4 * j + 1, tab(jr + 6));
+    put(D.jam + 4 * j + 2, tab(jr + 7));
+    put(D.jam + 4 * j + 3, 0.0);
   }
   // float32 state row (environment.py:479-510)
   const int per = 6 + T.n_types, S = R * per + 2 * J;
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(128) env_prepare_kernel(const macjd_env_tables
 inline int env_prepare_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, void* derived) {
   if (!ctx || !tab || !derived || !tab->data) return MACJD_ERR_INVALID_ARG;
   if (tab->n_envs < 0 || tab->n_jammers < 1 || tab->n_radars < 1 || tab->n_targets < 1 || tab->n_types < 1) return MACJD_ERR_INVALID_ARG;
-  if (tab->n_radars > 64 || tab->row_stride > 0x7fffffffll || tab->row_stride < 0) return MACJD_ERR_UNSUPPORTED;
+  if (tab->n_radars > 64 || tab->row_stride > 0x7fffffffll || tab->row_stride < 0 || !env2_supported(*tab)) return MACJD_ERR_UNSUPPORTED;
   const int n_cols = tab->env_stride == 0 ? 1 : tab->n_envs;
   if (n_cols == 0) return MACJD_OK;
   macjd_env_tables t = *tab;
@@ -148,8 +159,8 @@ inline int env_prepare_launch(const macjd_ctx* ctx, const macjd_env_tables* tab,
 }
 
 // ------------------------------------------------------------------------------------------ step
-constexpr int kEnv2Envs = 32;        // envs per block (the physics warp)
-constexpr int kEnv2Threads = 128;    // + three view warps
+constexpr int kEnv2Phys = 128;       // physics threads per block (128 / G envs, at most 32)
+constexpr int kEnv2Threads = 256;    // + four view warps
 
 struct Env2Args {
   macjd_env_tables tab;
@@ -158,23 +169,23 @@ struct Env2Args {
   const float* state_rows;
   int state_dim, n_actions;
   int physics;               // 0: reset (views only, step_count <- 0)
-  int stage_rows;            // physics warp copies its envs' derived rows to shared memory before the dependency wait
+  int group;                 // lanes per env (env2_group)
+  int envs_per_block;        // stand-alone kernel: min(32, 128 / group)
   uint32_t magic_s4, magic_js4;
   int env_begin, env_end;
 };
 
-// One env's step on the derived tables.  `dv(row)` reads this env's derived value; act_d / act_p point at this env's
-// J actions (global memory, or shared memory when the agent kernel runs the step itself); scratch is per-thread
-// [slot * sstride + sidx]: rec_val [J], rec_code [J] (ints), pnet [K] (only touched when pd_net is wanted).
-template <typename DV>
-__device__ __forceinline__ void env2_physics(const Env2Args& a, const macjd_env_io& io, int e, DV dv, const int32_t* act_d,
-                                             const float* act_p, double* rec_val, int* rec_code, double* pnet, int sstride, int sidx) {
+// One env's step by a group of G lanes (lane g of the group; the groups of a warp run in lockstep: every lane of
+// the warp must call this, `live` says whether its env exists).  d: this env's derived block (global or shared
+// memory); act_d / act_p: this env's J actions.  Lane 0 of the group writes the per-env outputs.
+__device__ __forceinline__ void env2_physics_group(const Env2Args& a, const macjd_env_io& io, int e, bool live, int g, int G,
+                                                   const double* d, const int32_t* act_d, const float* act_p) {
   const macjd_env_tables& T = a.tab;
   const DerivedRows& D = a.rows;
   const int n = T.n_envs, J = T.n_jammers, R = T.n_radars, K = T.n_targets, RK = R * K;
-  const int step = io.step_count[e] + 1;                             // environment.py:235
-  double r_p = 0.0, r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
-  uint64_t supp_mask = 0, hit_mask = 0;
+  const unsigned full = 0xffffffffu;
+  const int lane = (int)(threadIdx.x & 31), base = lane & ~(G - 1);    // first lane of this group inside the warp
+  const int step = live ? io.step_count[e] + 1 : 1;                    // environment.py:235
   // Philox yields four uniforms per call: slots 4q .. 4q + 3 share one
   Philox4 px = {0u, 0u, 0u, 0u};
   int px_q = -1;
@@ -187,103 +198,113 @@ __device__ __forceinline__ void env2_physics(const Env2Args& a, const macjd_env_
     const int q = slot & 3;
     return u01(q == 0 ? px.x : q == 1 ? px.y : q == 2 ? px.z : px.w);
   };
-  // ---- jammers (environment.py:248-302, core/jammer.py:73-98), in jammer order
-  for (int j = 0; j < J; ++j) {
-    const int Ti = act_d[j];
-    double P = (double)act_p[j];
+  // ---- jammer g (environment.py:248-302, core/jammer.py:73-98)
+  double rp_term = 0.0, val = 0.0;
+  int code = 0;                                                        // (target << 2) | {0 nothing, 1 suppression, 2 detected false target}
+  if (live && g < J) {
+    const int Ti = act_d[g];
+    double P = (double)act_p[g];
     P = P < 0.0 ? 0.0 : (P > 1.0 ? 1.0 : P);
-    const double pmin = dv(D.pmin + j), pmax = dv(D.pmax + j);
+    const double gj = d[D.jam + 4 * g], pmin = d[D.jam + 4 * g + 1], pmax = d[D.jam + 4 * g + 2];
     const double range = pmax - pmin;
     const double power = pmin + P * range;
     const double norm = range > 1e-6 ? (power - pmin) / range : 0.0;
-    r_p += T.rp_max + (T.rp_min - T.rp_max) * norm;                // charged even when idle
-    if (io.jam_power) io.jam_power[(int64_t)j * n + e] = (float)power;
-    int code = 0;
-    double val = 0.0;
+    rp_term = T.rp_max + (T.rp_min - T.rp_max) * norm;               // charged even when idle
+    if (io.jam_power) io.jam_power[(int64_t)g * n + e] = (float)power;
     if (Ti >= 1 && Ti <= 2 * R && power > 0.0) {
       const int tgt = (Ti + 1) / 2 - 1;
-      const double den = dv(D.den + j * R + tgt);
-      if (den >= 0.0) {                                              // farther than 1e-6 from the radar
+      const double den = d[D.den + g * R + tgt];
+      if (den >= 0.0) {                                                // farther than 1e-6 from the radar
         double prj = 0.0;
-        if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * dv(D.gj + j) * dv(D.gr + tgt)) / den);
-        if (Ti & 1) {                                                // suppression
+        if (den > 1e-18) prj = fmax(0.0, (fmax(0.0, power) * gj * d[D.rad + 4 * tgt + 3]) / den);
+        if (Ti & 1) {                                                  // suppression
           code = (tgt << 2) | 1; val = prj;
-          supp_mask |= 1ull << tgt;
-        } else {                                                     // deception: false target (environment.py:408-437)
-          const double pn = dv(D.pn + tgt);
-          double snr_f = pn > 1e-18 ? (dv(D.dd + tgt) * prj) / pn : 0.0;
+        } else {                                                       // deception: false target (environment.py:408-437)
+          const double pn = d[D.rad + 4 * tgt];
+          double snr_f = pn > 1e-18 ? (d[D.rad + 4 * tgt + 1] * prj) / pn : 0.0;
           snr_f = fmax(0.0, snr_f);
           const double pd_f = albersheim(T, snr_f);
-          if ((double)uniform(RK + j) <= pd_f) {
-            code = (tgt << 2) | 2; val = 1.0 - fmin(pd_f, 0.999999);
-            hit_mask |= 1ull << tgt;
-          }
+          if ((double)uniform(RK + g) <= pd_f) { code = (tgt << 2) | 2; val = 1.0 - fmin(pd_f, 0.999999); }
         }
       }
     }
-    rec_val[j * sstride + sidx] = val;
-    rec_code[j * sstride + sidx] = code;
   }
+  // ---- the jammers' records reach every lane in jammer order: r_p, and what hits radar g
+  double r_p = 0.0, prjs = 0.0, prod = 1.0;
+  bool supp = false, hit = false;
+  for (int j = 0; j < J; ++j) {
+    const double rp_j = __shfl_sync(full, rp_term, base + j);
+    const double v_j = __shfl_sync(full, val, base + j);
+    const int c_j = __shfl_sync(full, code, base + j);
+    r_p += rp_j;
+    if ((c_j >> 2) == g) {
+      if ((c_j & 3) == 1) { prjs += v_j; supp = true; }
+      else if ((c_j & 3) == 2) { prod *= v_j; hit = true; }
+    }
+  }
+  // ---- radar g and its K targets (environment.py:316-349, 359-366, 385-398)
+  const bool radar = live && g < R;
+  double pn = 0.0, jam = 0.0, den1 = 0.0, rdt = 0.0, red = 0.0;
+  if (radar) {
+    pn = d[D.rad + 4 * g];
+    rdt = d[D.rad + 4 * g + 2];
+    if (supp) { jam = d[D.rad + 4 * g + 1] * prjs; den1 = jam + pn; }
+  }
+  bool tracked = false;
   const bool want_net = io.pd_net != nullptr;
-  if (want_net)
-    for (int k = 0; k < K; ++k) pnet[k * sstride + sidx] = 1.0;
-  // ---- radars x targets (environment.py:316-349, 359-366, 385-398), in radar order
-  for (int r = 0; r < R; ++r) {
-    const bool supp = (supp_mask >> r) & 1ull, hit = (hit_mask >> r) & 1ull;
-    double prjs = 0.0, prod = 1.0;
-    if (supp || hit)
-      for (int j = 0; j < J; ++j) {                                  // this radar's jammers, in jammer order
-        const int code = rec_code[j * sstride + sidx];
-        if ((code >> 2) == r) {
-          if ((code & 3) == 1) prjs += rec_val[j * sstride + sidx];
-          else if ((code & 3) == 2) prod *= rec_val[j * sstride + sidx];
-        }
-      }
-    double jam = 0.0, den1 = 0.0;
-    if (supp) { jam = dv(D.dd + r) * prjs; den1 = jam + dv(D.pn + r); }
-    bool tracked = false;
-    double red = 0.0;
-    for (int k = 0; k < K; ++k) {
-      const int slot = r * K + k;
-      const double pd0 = dv(D.pd0 + slot);
-      double pd = pd0, sig = 0.0, snr1 = 0.0;
-      const bool need_sig = supp || io.jsr_db != nullptr;
-      if (need_sig) sig = dv(D.sig + slot);
+  for (int k = 0; k < K; ++k) {
+    double pd = 0.0;
+    if (radar) {
+      const int slot = g * K + k;
+      const double pd0 = d[D.pd0 + slot];
+      double sig = 0.0, snr1 = 0.0;
+      pd = pd0;
+      if (supp || io.jsr_db != nullptr) sig = d[D.sig + slot];
       if (supp) {
         snr1 = den1 > 1e-18 ? sig / den1 : 0.0;
         pd = albersheim(T, snr1);
-        red += fmax(0.0, pd0 - pd);                                  // P_d without jamming only matters here (r_j)
+        red += fmax(0.0, pd0 - pd);                                    // P_d without jamming only matters here (r_j)
       }
       const bool det = (double)uniform(slot) <= pd;
       tracked |= det;
-      if (want_net) pnet[k * sstride + sidx] *= (1.0 - pd);
       const int64_t o = (int64_t)slot * n + e;
       if (io.pd) io.pd[o] = (float)pd;
       if (io.detected) io.detected[o] = det ? 1 : 0;
       if (io.snr0 || io.snr1) {
-        const float s0 = (float)dv(D.snr0 + slot);
+        const float s0 = (float)d[D.snr0 + slot];
         if (io.snr0) io.snr0[o] = s0;
         if (io.snr1) io.snr1[o] = supp ? (float)fmax(0.0, snr1) : s0;
       }
       if (io.jsr_db) io.jsr_db[o] = 10.0f * log10f((float)(jam / sig));   // float32 output of an extension: float log
     }
-    if (io.tracking) io.tracking[(int64_t)r * n + e] = tracked ? 1 : 0;
-    if (tracked) r_d += dv(D.rdt + r);
-    if (supp) r_j_supp += red;
-    if (hit) r_j_dec += 1.0 - prod;
+    if (want_net) {                                                    // prod_r (1 - pd[r][k]) in radar order
+      double pn_k = 1.0;
+      const double mine = 1.0 - pd;
+      for (int r = 0; r < R; ++r) pn_k *= __shfl_sync(full, mine, base + r);
+      if (live && g == 0) io.pd_net[(int64_t)k * n + e] = (float)(1.0 - pn_k);
+    }
   }
-  if (want_net)
-    for (int k = 0; k < K; ++k) io.pd_net[(int64_t)k * n + e] = (float)(1.0 - pnet[k * sstride + sidx]);
-  const double r_j = r_j_supp + r_j_dec;
-  const double reward = r_d + r_p + r_j;                             // environment.py:457
-  const bool term = step >= T.episode_limit;                         // environment.py:460
-  io.reward[e] = (float)reward;
-  if (io.reward64) io.reward64[e] = reward;
-  if (io.r_d) io.r_d[e] = (float)r_d;
-  if (io.r_p) io.r_p[e] = (float)r_p;
-  if (io.r_j) io.r_j[e] = (float)r_j;
-  if (io.terminated) io.terminated[e] = term ? 1 : 0;
-  io.step_count[e] = (term && io.auto_reset) ? 0 : step;
+  if (radar && io.tracking) io.tracking[(int64_t)g * n + e] = tracked ? 1 : 0;
+  // ---- the per-radar terms, summed in radar order (a term the sequential code skips is an exact + 0.0 here)
+  const double t_d = (radar && tracked) ? rdt : 0.0, t_s = (radar && supp) ? red : 0.0, t_h = (radar && hit) ? 1.0 - prod : 0.0;
+  double r_d = 0.0, r_j_supp = 0.0, r_j_dec = 0.0;
+  for (int r = 0; r < R; ++r) {
+    r_d += __shfl_sync(full, t_d, base + r);
+    r_j_supp += __shfl_sync(full, t_s, base + r);
+    r_j_dec += __shfl_sync(full, t_h, base + r);
+  }
+  if (live && g == 0) {
+    const double r_j = r_j_supp + r_j_dec;
+    const double reward = r_d + r_p + r_j;                             // environment.py:457
+    const bool term = step >= T.episode_limit;                         // environment.py:460
+    io.reward[e] = (float)reward;
+    if (io.reward64) io.reward64[e] = reward;
+    if (io.r_d) io.r_d[e] = (float)r_d;
+    if (io.r_p) io.r_p[e] = (float)r_p;
+    if (io.r_j) io.r_j[e] = (float)r_j;
+    if (io.terminated) io.terminated[e] = term ? 1 : 0;
+    io.step_count[e] = (term && io.auto_reset) ? 0 : step;
+  }
 }
 
 // The static views (environment.py:479-551) of envs [e0, e0 + valid): thread vt of VT cooperating threads.
@@ -351,79 +372,40 @@ __device__ __forceinline__ void env2_views(const Env2Args& a, const macjd_env_io
   }
 }
 
-template <bool kStaged>
 __global__ void __launch_bounds__(kEnv2Threads) env_step2_kernel(const Env2Args a) {
   const macjd_env_tables& T = a.tab;
   const macjd_env_io& io = a.io;
-  const DerivedRows& D = a.rows;
-  const int n = T.n_envs, J = T.n_jammers, K = T.n_targets;
+  const int J = T.n_jammers;
   const int tid = (int)threadIdx.x;
-  const int e0 = a.env_begin + blockIdx.x * kEnv2Envs;
-  const int valid = min(kEnv2Envs, a.env_end - e0);
-  const bool shared_scn = T.env_stride == 0;
-  MACJD_DYNAMIC_SMEM(double, smem);
-
-  if (tid < kEnv2Envs) {
-    // =========================================================================== physics: thread = env
-    const int e = e0 + tid;
-    const bool live = tid < valid;
-    const int64_t drs = shared_scn ? 1 : (int64_t)n;                   // derived row stride
-    const double* dcol = T.derived + (shared_scn ? 0 : (live ? e : e0));
-    // per-thread scratch [slot][32]: jammer records (value, code), networked-Pd products
-    double* rec_val = smem;                                            // [J][32]
-    int* rec_code = reinterpret_cast<int*>(rec_val + (size_t)J * kEnv2Envs);   // [J][32]
-    double* pnet = rec_val + (size_t)J * kEnv2Envs + ((size_t)J * kEnv2Envs + 1) / 2;   // [K][32]
-    double* srows = pnet + (size_t)K * kEnv2Envs;                      // [rows][32] when kStaged
-    if (kStaged && a.physics && live) {
-#pragma unroll 1
-      for (int row0 = 0; row0 < D.total; row0 += 16) {
-        double v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (row0 + i < D.total) ? __ldg(dcol + (int64_t)(row0 + i) * drs) : 0.0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (row0 + i < D.total) srows[(row0 + i) * kEnv2Envs + tid] = v[i];
-      }
-    }
-    auto dv = [&](int row) -> double { return kStaged ? srows[row * kEnv2Envs + tid] : __ldg(dcol + (int64_t)row * drs); };
+  const int G = a.group, eb = a.envs_per_block;
+  const int e0 = a.env_begin + blockIdx.x * eb;
+  const int valid = min(eb, a.env_end - e0);
+  if (tid < kEnv2Phys) {
+    // =========================================================================== physics: G lanes per env
+    if (tid >= eb * G) return;                                         // (whole warps: eb * G is a multiple of 32)
+    const int slot = tid / G, g = tid - slot * G;
+    const bool live = slot < valid;
+    const int e = e0 + (live ? slot : 0);
+    const double* d = T.derived + (T.env_stride == 0 ? 0 : (int64_t)e * a.rows.total);
+    // pull this env's block towards the SM before waiting for the actions (the table is read-only)
+    if (a.physics && live)
+      for (int off = g * 16; off < a.rows.total; off += G * 16) prefetch_l2(d + off);
     // from here on the kernel reads the actions and writes outputs: wait for the preceding kernel of the stream
     grid_dependency_wait();
-    if (live && !a.physics) io.step_count[e] = 0;                      // environment.py:203
-    if (live && a.physics)
-      env2_physics(a, io, e, dv, io.act_d + (int64_t)e * J, io.act_p + (int64_t)e * J, rec_val, rec_code, pnet, kEnv2Envs, tid);
+    if (!a.physics) {
+      if (live && g == 0) io.step_count[e] = 0;                        // environment.py:203
+      return;
+    }
+    env2_physics_group(a, io, e, live, g, G, d, io.act_d + (int64_t)e * J, io.act_p + (int64_t)e * J);
     return;
   }
-
-  // ============================================================================= views: warps 1-3, 32 envs
-  // (nothing here depends on the actions, but the destinations may be read by the preceding kernel: wait before
-  // the first store)
+  // ============================================================================= views: warps 4-7
+  // (nothing here depends on the actions, but the destinations may be read by the preceding kernel)
   grid_dependency_wait();
-  env2_views(a, io, e0, valid, tid - kEnv2Envs, kEnv2Threads - kEnv2Envs);
-}
-
-inline size_t env2_smem_bytes(int J, int K, int staged_rows) {
-  return ((size_t)J * kEnv2Envs + ((size_t)J * kEnv2Envs + 1) / 2 + (size_t)K * kEnv2Envs + (size_t)staged_rows * kEnv2Envs) * sizeof(double);
+  env2_views(a, io, e0, valid, tid - kEnv2Phys, kEnv2Threads - kEnv2Phys);
 }
 
 // kernel arguments of one step (also used by the agent kernel when it runs the step itself)
-inline Env2Args env2_args(const macjd_env_tables* tab, const macjd_env_io* io, int physics);
-
-inline int env2_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
-  const int n_step = io->env_count > 0 ? io->env_count : tab->n_envs - io->env_begin;
-  if (n_step == 0) return MACJD_OK;
-  Env2Args a = env2_args(tab, io, physics);
-  // Small scenarios: the physics warp parks its envs' derived rows in shared memory ahead of the dependency wait
-  // (behind the agent kernel that wait is long and the copy free; every later lookup is a shared-memory read on the
-  // dependent chain).  Large scenarios read the few rows a step needs straight from L2.
-  a.stage_rows = (physics && (io->flags & MACJD_ENV_FOLLOWS_AGENT) && a.rows.total <= 96 && tab->env_stride != 0) ? 1 : 0;
-  const size_t smem = env2_smem_bytes(tab->n_jammers, tab->n_targets, a.stage_rows ? a.rows.total : 0);
-  if (smem > 48 * 1024) return MACJD_ERR_UNSUPPORTED;
-  const int grid = (n_step + kEnv2Envs - 1) / kEnv2Envs;
-  if (a.stage_rows) MACJD_LAUNCH(env_step2_kernel<true>, grid, kEnv2Threads, smem, (cudaStream_t)ctx->stream, a);
-  else MACJD_LAUNCH(env_step2_kernel<false>, grid, kEnv2Threads, smem, (cudaStream_t)ctx->stream, a);
-  return MACJD_OK;
-}
-
 inline Env2Args env2_args(const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
   const int n_step = io->env_count > 0 ? io->env_count : tab->n_envs - io->env_begin;
   Env2Args a;
@@ -434,6 +416,8 @@ inline Env2Args env2_args(const macjd_env_tables* tab, const macjd_env_io* io, i
   a.state_dim = tab->n_radars * (6 + tab->n_types) + 2 * tab->n_jammers;
   a.n_actions = 2 * tab->n_radars + 1;
   a.physics = physics;
+  a.group = env2_group(tab->n_jammers, tab->n_radars);
+  a.envs_per_block = kEnv2Phys / a.group < 32 ? kEnv2Phys / a.group : 32;
   a.env_begin = io->env_begin;
   a.env_end = io->env_begin + n_step;
   {
@@ -442,8 +426,17 @@ inline Env2Args env2_args(const macjd_env_tables* tab, const macjd_env_io* io, i
     a.magic_s4 = ok ? (uint32_t)((0x100000000ull + s4 - 1) / s4) : 0;
     a.magic_js4 = ok ? (uint32_t)((0x100000000ull + js4 - 1) / js4) : 0;
   }
-  a.stage_rows = 0;
   return a;
+}
+
+inline int env2_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
+  if (!env2_supported(*tab)) return MACJD_ERR_UNSUPPORTED;
+  const int n_step = io->env_count > 0 ? io->env_count : tab->n_envs - io->env_begin;
+  if (n_step == 0) return MACJD_OK;
+  const Env2Args a = env2_args(tab, io, physics);
+  const int grid = (n_step + a.envs_per_block - 1) / a.envs_per_block;
+  MACJD_LAUNCH(env_step2_kernel, grid, kEnv2Threads, 0, (cudaStream_t)ctx->stream, a);
+  return MACJD_OK;
 }
 
 // environment.py:221-477 / :208-219 for the whole batch: on the derived tables when the caller prepared them

@@ -92,7 +92,7 @@ class ElectromagneticEnvironment:
         # Scenario-only terms of the step (echo power and no-jamming Pd per radar-target pair, link denominators,
         # state rows): derived once here, read by every step (csrc/env_step2.cuh).  derive_tables=False keeps the
         # kernel that works from the raw tables on every step (round 1's; same results).
-        if derive_tables:
+        if derive_tables and R <= 32 and J <= 32:       # (the group-per-env kernel covers up to 32 jammers / radars)
             nbytes = int(self._lib.lib.macjd_env_derived_bytes(N.C.byref(self._ctab)))
             self._derived_dev = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
             self._lib.callv("macjd_env_prepare", self._ctx_for(dev), self._ctab, self._derived_dev)
