@@ -302,7 +302,8 @@ MACJD_API int macjd_agent_tc_chunk_k(void);
  * macjd_agent_forward followed by macjd_env_step.  Requires aio->n_rows == n_envs * n_jammers (env-major). */
 MACJD_API int macjd_rollout_step(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
                                  const macjd_env_tables* tab, const macjd_env_io* eio);
-/* 1 if macjd_rollout_step runs these weights / tables as one launch. */
+/* 1 if macjd_rollout_step runs these weights / tables as one launch (it can, and the env work a CTA would take
+ * on is small next to its agent step: at most 16 KB of next-step views per CTA). */
 MACJD_API int macjd_rollout_fused_supported(const macjd_agent_weights* w, const macjd_env_tables* tab);
 
 /* Host-buffer form of BasicMAC.select_actions (core/mac.py:59-187: numpy observations and

@@ -26,6 +26,7 @@
 #include "agent_tc_common.cuh"
 #include "env_step2.cuh"
 #ifndef MACJD_TEST_HOST_EMULATION
+#include <stdlib.h>
 #include <cuda.h>            // CUtensorMap (type and enums only; the encoder is fetched through the runtime)
 #endif
 
@@ -907,6 +908,18 @@ inline bool agent_tc2_fuse_supported(const macjd_agent_weights& w, const macjd_e
   // one group of G lanes per env among the epilogue threads; the envs' derived blocks are staged in the xf tile's hi half
   return epc * G <= kT2EpiThreads && (epc * G) % 32 == 0 &&
          (size_t)derived_rows(t.n_jammers, t.n_radars, t.n_targets).total * epc * sizeof(double) <= sizeof(float) * kTcRows * kTcH;
+}
+
+// ... and it pays off while the env work a CTA takes on is small next to its agent step: the views a CTA copies per
+// step (state + J observation rows + availability of 64 / J envs) stay within 16 KB.  Measured on B200: default
+// scenario (9 KB per CTA-step) 37.1 -> 35.5 us per step fused; 8 x 16 x 4 scenario (50 KB) 521 us fused against
+// the two kernels overlapping (MACJD_FUSE_MAX_VIEW_BYTES overrides the limit, for experiments).
+inline bool agent_tc2_fuse_profitable(const macjd_env_tables& t) {
+  const char* ev = getenv("MACJD_FUSE_MAX_VIEW_BYTES");            // read per call (tens of ns): tests switch it
+  const size_t limit = ev ? (size_t)strtoull(ev, nullptr, 10) : (size_t)16384;
+  const size_t S = (size_t)t.n_radars * (6 + t.n_types) + 2 * (size_t)t.n_jammers, J = (size_t)t.n_jammers;
+  const size_t per_env = S * 4 * (1 + J) + J * (2 * (size_t)t.n_radars + 1);
+  return per_env * (kTcRows / J) <= limit;
 }
 
 inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a, const Env2Args* env = nullptr) {

@@ -171,7 +171,7 @@ int macjd_rollout_step(const macjd_ctx* ctx, const macjd_agent_weights* w, const
   if (aio->n_rows == 0) return MACJD_OK;
 #ifndef MACJD_TEST_HOST_EMULATION
   if (aio->path != 1 && ke.env_begin == 0 && ke.env_count == 0 && macjd::tc::agent_tc_supported(*w) &&
-      macjd::tc::agent_tc2_fuse_supported(*w, *tab)) {
+      macjd::tc::agent_tc2_fuse_supported(*w, *tab) && macjd::tc::agent_tc2_fuse_profitable(*tab)) {
     if (aio->n_rows < 0 || !aio->obs) return MACJD_ERR_INVALID_ARG;
     macjd::AgentArgs a;
     a.w = *w;
@@ -188,7 +188,8 @@ int macjd_rollout_step(const macjd_ctx* ctx, const macjd_agent_weights* w, const
 
 int macjd_rollout_fused_supported(const macjd_agent_weights* w, const macjd_env_tables* tab) {
 #ifndef MACJD_TEST_HOST_EMULATION
-  return (w && tab && macjd::tc::agent_tc_supported(*w) && macjd::tc::agent_tc2_fuse_supported(*w, *tab)) ? 1 : 0;
+  return (w && tab && macjd::tc::agent_tc_supported(*w) && macjd::tc::agent_tc2_fuse_supported(*w, *tab) &&
+          macjd::tc::agent_tc2_fuse_profitable(*tab)) ? 1 : 0;
 #else
   (void)w; (void)tab;
   return 0;

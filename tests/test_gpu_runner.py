@@ -44,6 +44,8 @@ def test_fast_path_chains_hidden_state():
 
 
 @pytest.mark.parametrize("kind,n_envs,path,fused", [("c2", 300, 0, True), ("c2", 4096, 0, True), ("c2", 33, 1, None),
-                                                    ("c3", 100, 0, True), ("c3", 1030, 0, True), ("j3", 200, 0, False)])
-def test_fused_rollout_step_equals_two_kernels(kind, n_envs, path, fused):
+                                                    ("c3", 100, 0, None), ("c3", 1030, 0, None), ("j3", 200, 0, False)])
+def test_fused_rollout_step_equals_two_kernels(monkeypatch, kind, n_envs, path, fused):
+    # (the library fuses the 8 x 16 x 4 scenario only when asked to: 50 KB of views per CTA-step; ask)
+    monkeypatch.setenv("MACJD_FUSE_MAX_VIEW_BYTES", "1000000")
     RC.check_fused_rollout_step("cuda", None, n_envs=n_envs, kind=kind, path=path, expect_fused=fused)
