@@ -414,11 +414,46 @@ def main():
         dt = timed_steps(rollout_step, K_, pre=pre_step)
         barrier()
         dt = reduce_max(dt)
-        res = {"value": world * M * K_ / dt, "ms_per_step": dt / K_ * 1e3, "M": M}
+        res = {"value": world * M * K_ / dt, "ms_per_step": dt / K_ * 1e3, "M": M, "launch": "one library call per timestep"}
         from macjd_b200 import _native as N_
         fn = N_.get_lib().lib.macjd_rollout_fused_supported
         fn.restype = N_.C.c_int
         res["fused"] = bool(runner.fused_step and fn(N_.C.byref(mac.agent.packed().cstruct()), N_.C.byref(env._ctab)))
+        if res["fused"]:
+            # The same K timesteps as launches of up to one episode each (macjd_rollout_steps: the CTA pairs loop over the
+            # timesteps, recurrent state in shared memory, their envs' steps inline): K steps = ceil(K / T) launches, L2
+            # flushed before each launch, CUDA events around each launch.
+            def chunks(total):
+                out, t = [], 0
+                while total > 0:
+                    n_ = min(total, T - t)
+                    out.append((t, n_))
+                    total -= n_
+                    t = (t + n_) % T
+                return out
+            runner.reset()
+            for t0, n_ in chunks(max(W_, 3)):
+                if t0 == 0:
+                    runner.reset()
+                runner.rollout(t0, n_)
+            plan = chunks(K_)
+            runner.reset()
+            barrier()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in plan]
+            for i, (t0, n_) in enumerate(plan):
+                if t0 == 0:
+                    runner.reset()                         # episode boundary: outside the timed region
+                flush.fill_(i & 0xFF)
+                ev[i][0].record()
+                runner.rollout(t0, n_)
+                ev[i][1].record()
+            torch.cuda.synchronize()
+            barrier()
+            dt_m = reduce_max(sum(a.elapsed_time(b) for a, b in ev) * 1e-3)
+            res["per_step_launch"] = {"value": res["value"], "ms_per_step": res["ms_per_step"],
+                                      "what": "the same K timesteps as one macjd_rollout_step launch each, L2 flushed before every step"}
+            res.update({"value": world * M * K_ / dt_m, "ms_per_step": dt_m / K_ * 1e3, "launches": len(plan),
+                        "launch": f"macjd_rollout_steps: {len(plan)} launch(es) of up to {T} timesteps (one episode) each; L2 flushed before each launch"})
 
         # ---- the two launches of one timestep, each alone (cached C structs: one ctypes call per launch)
         if getattr(runner, "_structs_for", None) != (mac.hidden_states.data_ptr(), mac.agent.path):
@@ -558,9 +593,12 @@ def main():
     learner = QMixLearner(mac, rl)
     r2 = rollout_bench(env, mac, runner, K, W, with_e2e=True)
     M = r2["M"]
-    line["config"]["launches_per_step"] = ("1: macjd_rollout_step, the CTA-pair agent kernel also runs the env step of its rows' envs"
+    line["config"]["launches_per_step"] = ("<= 1: the CTA-pair agent kernel also runs the env step of its rows' envs, and loops over the timesteps of an episode"
                                            if r2["fused"] else "2: agent_forward kernel + env_step kernel (programmatic dependent launch)")
-    line.update({"value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e": r2["e2e"], "gpu_launches": (1 if r2["fused"] else 2) * K,
+    line["config"]["timed_as"] = r2["launch"]
+    line["per_step_launch"] = r2.get("per_step_launch")
+    line.update({"value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e": r2["e2e"],
+                 "gpu_launches": r2.get("launches", (1 if r2["fused"] else 2) * K),
                  "roofline": agent_roofline(mac, M, r2["dt_agent"], r2["dt_simt"], OBS, N_ACTIONS, HID),
                  "roofline_env": env_roofline(n_envs, r2["dt_env"], ENV_BYTES_PER_STEP, "dram_bytes_per_launch_at_bench_size"),
                  "parity": r2.get("parity"),

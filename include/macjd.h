@@ -271,7 +271,8 @@ typedef struct macjd_agent_io {
                                  [k, k + n_rows) of a larger batch (pointers offset by the caller) draws
                                  what the whole-batch launch draws for those rows                    */
   float* gate_x;              /* [T][M][3][H] part 3 output / part 4 input, else unused  */
-  const float* epsilon_dev;   /* optional DEVICE scalars that override `epsilon` / `rng_step`: kernel      */
+  const float* epsilon_dev;   /* optional DEVICE values that override `epsilon` (n_steps floats, one per step) and
+                                 `rng_step` (one scalar; step t uses it + t): kernel                       */
   const uint32_t* rng_step_dev; /* parameters are frozen when a launch is replayed from a CUDA graph, these
                                  are not (BatchedEpisodeRunner replays a whole episode as one graph) */
   int32_t* actions_mirror;    /* [T][M] optional second destinations of actions / power (same values):   */
@@ -302,6 +303,19 @@ MACJD_API int macjd_agent_tc_chunk_k(void);
  * macjd_agent_forward followed by macjd_env_step.  Requires aio->n_rows == n_envs * n_jammers (env-major). */
 MACJD_API int macjd_rollout_step(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
                                  const macjd_env_tables* tab, const macjd_env_io* eio);
+/* aio->n_steps = T timesteps of that loop (runners/episode_runner.py:49-119).  The buffers are the time-major
+ * rollout trajectory: aio's obs / avail / actions / power / hidden_seq ... are [T][M]... as documented in
+ * macjd_agent_io, and the env outputs of step t go t steps behind eio's addresses (reward, r_d, r_p, r_j,
+ * terminated: [T][n]; state [T][n][S], obs [T][n][J][S], avail [T][n][J][A]); because the agent of step t + 1
+ * reads what the env of step t wrote, eio->obs must be aio->obs + M * O (the next slot of the same trajectory)
+ * and eio->avail likewise (MACJD_ERR_INVALID_ARG otherwise).  aio->epsilon_dev, when given, holds T values (one
+ * per step); the Philox step counter of step t is aio->rng_step + t.  The info-only env outputs (pd, detected,
+ * ...) keep the last step's values.  Fused (macjd_rollout_fused_supported) this is ONE launch: each CTA pair
+ * keeps its rows' recurrent state in shared memory across the steps and runs its own envs' steps; otherwise the
+ * steps are issued one by one.  Results are identical to T calls of macjd_rollout_step.  Injected draws
+ * (u_eps, rand_actions, noise) are not supported here: MACJD_ERR_UNSUPPORTED. */
+MACJD_API int macjd_rollout_steps(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
+                                  const macjd_env_tables* tab, const macjd_env_io* eio);
 /* 1 if macjd_rollout_step runs these weights / tables as one launch (it can, and the env work a CTA would take
  * on is small next to its agent step: at most 16 KB of next-step views per CTA). */
 MACJD_API int macjd_rollout_fused_supported(const macjd_agent_weights* w, const macjd_env_tables* tab);

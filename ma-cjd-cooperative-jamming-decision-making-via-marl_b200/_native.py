@@ -179,6 +179,7 @@ class NativeLib:
         "macjd_env_reset": (Ctx, EnvTables, EnvIO),
         "macjd_agent_forward": (Ctx, AgentWeights, AgentIO),
         "macjd_rollout_step": (Ctx, AgentWeights, AgentIO, EnvTables, EnvIO),
+        "macjd_rollout_steps": (Ctx, AgentWeights, AgentIO, EnvTables, EnvIO),
         "macjd_agent_act_host": (Ctx, AgentWeights, AgentIO, ActHost),
         "macjd_env_step_host": (Ctx, EnvTables, EnvIO, EnvHost),
         "macjd_rollout_step_host": (Ctx, AgentWeights, AgentIO, ActHost, EnvTables, EnvIO, EnvHost),

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(NT, 1) agent_forward_kernel(const AgentArgs a)
         if (!io.test_mode) {                                   // action_selectors.py:39-57
           const uint32_t row_id = (uint32_t)(io.rng_row_offset + row0 + r);
           const float u = io.u_eps ? io.u_eps[m] : philox_uniform(io.seed, kStreamEpsilon, row_id, (io.rng_step_dev ? __ldg(io.rng_step_dev) : io.rng_step) + t, 0);
-          if (u < (io.epsilon_dev ? __ldg(io.epsilon_dev) : io.epsilon)) {
+          if (u < (io.epsilon_dev ? __ldg(io.epsilon_dev + t) : io.epsilon)) {
             if (io.rand_actions) {
               chosen = io.rand_actions[m];
             } else {

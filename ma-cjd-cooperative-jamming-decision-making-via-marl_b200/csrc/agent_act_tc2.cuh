@@ -241,6 +241,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
     r_ = p_ / wz; k4_ = w4 + (p_ - r_ * wz);
     return false;
   };
+  // Observations of later steps of a kFuseEnv launch were written by this CTA's own view threads one step earlier:
+  // they must not come through the non-coherent (read-only) path -- L2 loads (ld.global.cg) instead
+  auto ld_obs4 = [](const float4* q_) -> float4 { return kFuseEnv ? __ldcg(q_) : __ldg(q_); };
+  auto ld_obs1 = [](const float* q_) -> float { return kFuseEnv ? __ldcg(q_) : __ldg(q_); };
   float4 x4_in[2];
   if (warp < kT2EpiWarps && x_vec) {
 #pragma unroll
@@ -455,11 +459,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         av_mask = 0;
         if (kBigA) {
 #pragma unroll 4
-          for (int act = 0; act < A; ++act) av_mask |= (uint64_t)(__ldg(ap + act) != 0 ? 1u : 0u) << act;
+          for (int act = 0; act < A; ++act) av_mask |= (uint64_t)((kFuseEnv ? __ldcg(ap + act) : __ldg(ap + act)) != 0 ? 1u : 0u) << act;
         } else {
 #pragma unroll
           for (int act = 0; act < 8; ++act)
-            if (act < A) av_mask |= (uint64_t)(__ldg(ap + act) != 0 ? 1u : 0u) << act;
+            if (act < A) av_mask |= (uint64_t)((kFuseEnv ? __ldcg(ap + act) : __ldg(ap + act)) != 0 ? 1u : 0u) << act;
         }
       }
       for (int xc = 0; xc < nx; ++xc) {
@@ -473,7 +477,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
             const bool data = x_slot(tid + i * kT2EpiThreads, xc, r_, k4_);
             float4 q = x4_in[i];
             if (!pre)
-              q = (data && r_ < valid) ? __ldg(reinterpret_cast<const float4*>(io.obs + (tM + row0 + r_) * O + 32 * xc) + k4_)
+              q = (data && r_ < valid) ? ld_obs4(reinterpret_cast<const float4*>(io.obs + (tM + row0 + r_) * O + 32 * xc) + k4_)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
             const float v[4] = {q.x, q.y, q.z, q.w};
             store_split4(xhi, xlo, r_, 4 * k4_, 32, v);
@@ -486,7 +490,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int kk = xc * 32 + k + j;
-            v[j] = pre ? x_in[4 * g + j] : ((live && kk < O) ? __ldg(obs + kk) : 0.f);
+            v[j] = pre ? x_in[4 * g + j] : ((live && kk < O) ? ld_obs1(obs + kk) : 0.f);
           }
           store_split4(xhi, xlo, r, k, 32, v);
         }
@@ -726,7 +730,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #pragma unroll 4
           for (int i = tid; i < n2; i += kT2EpiThreads) dst[i] = __ldg(src + i);
         }
-        env2_views(p.env, p.env.io, row0 / Je, ne, tid, kT2EpiThreads);
+        env2_views(p.env, env2_io_at(p.env, t), row0 / Je, ne, tid, kT2EpiThreads);
       }
       if (mode == 0) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }   // heads only: q.0 finished with actor.2
       else epi_bar_sync();                                                  // ... but P (written by E2's last stage) must be visible
@@ -836,7 +840,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           if (!io.test_mode) {
             const uint32_t row_id = (uint32_t)(io.rng_row_offset + row0 + r);
             const float u = io.u_eps ? io.u_eps[m] : philox_uniform(io.seed, kStreamEpsilon, row_id, (io.rng_step_dev ? __ldg(io.rng_step_dev) : io.rng_step) + t, 0);
-            if (u < (io.epsilon_dev ? __ldg(io.epsilon_dev) : io.epsilon)) {
+            if (u < (io.epsilon_dev ? __ldg(io.epsilon_dev + t) : io.epsilon)) {
               if (io.rand_actions) {
                 chosen = io.rand_actions[m];
               } else {
@@ -875,7 +879,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           const int e = row0 / Je + (env_live ? slot : 0);
           const double* d = E.tab.env_stride == 0 ? E.tab.derived
                                                   : reinterpret_cast<const double*>(S.b0hi) + (size_t)(env_live ? slot : 0) * E.rows.total;
-          env2_physics_group(E, E.io, e, env_live, g, G, d, S.act_s + slot * Je, S.pow_s + slot * Je);
+          env2_physics_group(E, env2_io_at(E, t), e, env_live, g, G, d, S.act_s + slot * Je, S.pow_s + slot * Je);
         }
       }
       epi_bar_sync();                   // Ps / Qs / red are free for the next step
@@ -965,7 +969,7 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a, const Env2
   const bool big = a.w.n_actions > 8;
   const cudaStream_t st = (cudaStream_t)ctx->stream;
   if (env) {
-    if (a.io.part != 0 || a.io.n_steps != 1) return MACJD_ERR_INVALID_ARG;
+    if (a.io.part != 0 || a.io.n_steps < 1) return MACJD_ERR_INVALID_ARG;
     if (big) agent_forward_tc2_kernel<true, true, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
     else agent_forward_tc2_kernel<true, false, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
   } else if (a.io.part == 0) {

@@ -175,6 +175,24 @@ struct Env2Args {
   int env_begin, env_end;
 };
 
+// A launch that runs several timesteps (macjd_rollout_steps) writes the per-step outputs time-major: step t of the
+// launch lands t x (size of one step's output) behind step 0's address.  The info-only outputs (pd, detected, ...)
+// and the step counters are per-env state and stay where they are.
+__device__ __forceinline__ macjd_env_io env2_io_at(const Env2Args& a, int t) {
+  macjd_env_io io = a.io;
+  if (t == 0) return io;
+  const int64_t n = a.tab.n_envs, J = a.tab.n_jammers, S = a.state_dim, A = a.n_actions;
+  io.reward += t * n;
+  if (io.r_d) io.r_d += t * n;
+  if (io.r_p) io.r_p += t * n;
+  if (io.r_j) io.r_j += t * n;
+  if (io.terminated) io.terminated += t * n;
+  if (io.state) io.state += t * n * S;
+  if (io.obs) io.obs += t * n * J * S;
+  if (io.avail) io.avail += t * n * J * A;
+  return io;
+}
+
 // One env's step by a group of G lanes (lane g of the group; the groups of a warp run in lockstep: every lane of
 // the warp must call this, `live` says whether its env exists).  d: this env's derived block (global or shared
 // memory); act_d / act_p: this env's J actions.  Lane 0 of the group writes the per-env outputs.

@@ -186,6 +186,78 @@ int macjd_rollout_step(const macjd_ctx* ctx, const macjd_agent_weights* w, const
   return macjd_env_step(ctx, tab, &ke);
 }
 
+// Several timesteps of the rollout loop.  Fused: ONE launch (each CTA pair keeps its rows' recurrent state in shared
+// memory, loops over the timesteps and runs its envs' steps itself).  Otherwise: macjd_rollout_step per timestep.
+int macjd_rollout_steps(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* aio,
+                        const macjd_env_tables* tab, const macjd_env_io* eio) {
+  MACJD_ENTER(ctx);
+  if (!w || !aio || !tab || !eio) return MACJD_ERR_INVALID_ARG;
+  const int T = aio->n_steps;
+  if (T < 1 || aio->part != 0 || !aio->actions || !aio->power || !aio->obs) return MACJD_ERR_INVALID_ARG;
+  if ((int64_t)aio->n_rows != (int64_t)tab->n_envs * tab->n_jammers) return MACJD_ERR_INVALID_ARG;
+  if (T == 1) return macjd_rollout_step(ctx, w, aio, tab, eio);
+  const int64_t M = aio->n_rows, n = tab->n_envs, J = tab->n_jammers, O = w->obs_dim, A = w->n_actions, H = w->hidden;
+  const int64_t S = (int64_t)tab->n_radars * (6 + tab->n_types) + 2 * J;
+  // the agent of step t + 1 reads what the env of step t wrote: the buffers must be the time-major trajectory
+  if (O != S || eio->obs != aio->obs + M * O) return MACJD_ERR_INVALID_ARG;
+  if (aio->avail && eio->avail != aio->avail + M * A) return MACJD_ERR_INVALID_ARG;
+  if (aio->u_eps || aio->rand_actions || eio->noise || aio->rng_step_dev) return MACJD_ERR_UNSUPPORTED;   // (injected draws: step by step)
+  macjd_env_io ke = *eio;
+  ke.act_d = aio->actions;
+  ke.act_p = aio->power;
+  int st = macjd::env_check_args(ctx, tab, &ke, /*physics=*/1);
+  if (st != MACJD_OK) return st;
+  if (M == 0) return MACJD_OK;
+#ifndef MACJD_TEST_HOST_EMULATION
+  if (aio->path != 1 && ke.env_begin == 0 && ke.env_count == 0 && macjd::tc::agent_tc_supported(*w) &&
+      macjd::tc::agent_tc2_fuse_supported(*w, *tab) && macjd::tc::agent_tc2_fuse_profitable(*tab)) {
+    macjd::AgentArgs a;
+    a.w = *w;
+    a.io = *aio;
+    const macjd::Env2Args e = macjd::env2_args(tab, &ke, 1);
+    return finish(ctx, macjd::tc::agent_tc2_launch(ctx, a, &e));
+  }
+#endif
+  // step by step: the same pointers advanced by one timestep each
+  for (int t = 0; t < T && st == MACJD_OK; ++t) {
+    macjd_agent_io ka = *aio;
+    ka.n_steps = 1;
+    ka.obs = aio->obs + t * M * O;
+    if (aio->avail) ka.avail = aio->avail + t * M * A;
+    ka.actions = aio->actions + t * M;
+    ka.power = aio->power + t * M;
+    if (aio->q_chosen) ka.q_chosen = aio->q_chosen + t * M;
+    if (aio->hidden_seq) ka.hidden_seq = aio->hidden_seq + t * M * H;
+    if (aio->q_all) ka.q_all = aio->q_all + t * M * A;
+    if (aio->params_all) ka.params_all = aio->params_all + t * M * A;
+    if (aio->greedy) ka.greedy = aio->greedy + t * M;
+    if (aio->sel_actions) ka.sel_actions = aio->sel_actions + t * M;
+    if (aio->q_sel) ka.q_sel = aio->q_sel + t * M;
+    if (aio->actions_mirror) ka.actions_mirror = aio->actions_mirror + t * M;
+    if (aio->power_mirror) ka.power_mirror = aio->power_mirror + t * M;
+    if (aio->epsilon_dev) ka.epsilon_dev = aio->epsilon_dev + t;
+    ka.rng_step = aio->rng_step + (uint32_t)t;
+    // the recurrent state: step 0 as given; later steps continue from the previous step's record (or in place)
+    if (t > 0) {
+      ka.hidden_zero_init = 0;
+      ka.hidden_in = aio->hidden_seq ? aio->hidden_seq + (t - 1) * M * H : nullptr;
+    }
+    if (aio->hidden_seq && aio->hidden && t < T - 1) ka.hidden = nullptr;      // only the last step updates it
+    if (!aio->hidden_seq && !aio->hidden) return MACJD_ERR_INVALID_ARG;
+    macjd_env_io kt = ke;
+    kt.reward = ke.reward + t * n;
+    if (ke.r_d) kt.r_d = ke.r_d + t * n;
+    if (ke.r_p) kt.r_p = ke.r_p + t * n;
+    if (ke.r_j) kt.r_j = ke.r_j + t * n;
+    if (ke.terminated) kt.terminated = ke.terminated + t * n;
+    if (ke.state) kt.state = ke.state + t * n * S;
+    if (ke.obs) kt.obs = ke.obs + t * n * J * S;
+    if (ke.avail) kt.avail = ke.avail + t * n * J * A;
+    st = macjd_rollout_step(ctx, w, &ka, tab, &kt);
+  }
+  return st;
+}
+
 int macjd_rollout_fused_supported(const macjd_agent_weights* w, const macjd_env_tables* tab) {
 #ifndef MACJD_TEST_HOST_EMULATION
   return (w && tab && macjd::tc::agent_tc_supported(*w) && macjd::tc::agent_tc2_fuse_supported(*w, *tab) &&

@@ -170,6 +170,8 @@ class BatchedEpisodeRunner:
         # True: a timestep is one macjd_rollout_step call (the library fuses agent step and env step into one launch
         # when it can, include/macjd.h); False: macjd_agent_forward + macjd_env_step.  Same results.
         self.fused_step = bool(getattr(args, "fused_rollout_step", True))
+        # run(): the whole episode as one macjd_rollout_steps call (one launch when fused) instead of one call per step
+        self.whole_episode_launch = bool(getattr(args, "whole_episode_launch", True))
 
     def _build_step_structs(self):
         """All pointers of a timestep are fixed (persistent trajectory buffers), so the C structs
@@ -231,6 +233,42 @@ class BatchedEpisodeRunner:
                              "r_d": self.r_parts[0, t], "r_p": self.r_parts[1, t], "r_j": self.r_parts[2, t],
                              "state": tr["state"][t + 1], "obs": tr["obs"][t + 1], "avail": tr["avail_actions"][t + 1]})
         self.t_env += self.n_envs
+
+    def rollout(self, t0, n_steps, test_mode=False):
+        """Timesteps t0 .. t0 + n_steps - 1 of the current episodes as ONE library call (include/macjd.h:
+        macjd_rollout_steps) -- one launch when the CTA-pair kernel can run its rows' env steps itself: the recurrent
+        state then stays in shared memory across the steps and there is no per-step launch, prologue or hand-over.
+        Same trajectory as ``step(t)`` for each t (the exploration schedule is evaluated per step on the host and
+        handed over as an array; the Philox counters advance by one per step)."""
+        from .. import _native as N
+        tr, mac, env = self.traj, self.mac, self.env
+        n, Nn, T = self.n_envs, self.n_agents, self.episode_limit
+        assert 0 <= t0 and n_steps >= 1 and t0 + n_steps <= T
+        if getattr(self, "_structs_for", None) != (mac.hidden_states.data_ptr(), mac.agent.path):
+            self._build_step_structs()
+        if self.__dict__.get("_eps_dev") is None or self._eps_dev.device != env.device:
+            self._eps_dev = torch.zeros(T, dtype=torch.float32, device=env.device)
+            self._eps_host = torch.zeros(T, dtype=torch.float32, pin_memory=env.device.type == "cuda")
+            self._multi_io = {}
+        for i in range(n_steps):
+            self._eps_host[t0 + i] = mac.action_selector.anneal(self.t_env + i * n, test_mode)
+        self._eps_dev[t0:t0 + n_steps].copy_(self._eps_host[t0:t0 + n_steps], non_blocking=True)
+        key = (t0, n_steps, mac.hidden_states.data_ptr(), mac.agent.path)
+        aio = self._multi_io.get(key)
+        if aio is None:
+            p = N.ptr
+            last = t0 + n_steps == T
+            aio = self._multi_io[key] = N.AgentIO(
+                n_rows=n * Nn, n_steps=n_steps, obs=p(tr["obs"][t0]), hidden=p(mac.hidden_states) if last else None,
+                hidden_in=p(tr["hidden_state"][t0 - 1]) if t0 > 0 else None, hidden_zero_init=1 if t0 == 0 else 0,
+                test_mode=0, tile_rows=0, path=mac.agent.path, hidden_seq=p(tr["hidden_state"][t0]),
+                avail=p(tr["avail_actions"][t0]), epsilon=0.0, rng_step=0, seed=mac.seed & 0xFFFFFFFFFFFFFFFF,
+                actions=p(tr["actions_discrete"][t0]), power=p(tr["actions_continuous"][t0]),
+                epsilon_dev=self._eps_dev.data_ptr() + 4 * t0)
+        aio.rng_step, aio.test_mode = (mac._rng_step + 1) & 0xFFFFFFFF, int(test_mode)
+        mac.agent.lib().call("macjd_rollout_steps", mac.agent._ctx(), mac.agent.packed().cstruct(), aio, env._ctab, self._env_io[t0])
+        mac._rng_step += n_steps
+        self.t_env += n_steps * n
 
     def step_host(self, obs, avail, host, test_mode=False):
         """One iteration of the reference's loop (episode_runner.py:119-165: select_actions, env.step) for a
@@ -336,8 +374,11 @@ class BatchedEpisodeRunner:
         else:
             use_graph = False
         if not use_graph:
-            for t in range(self.episode_limit):
-                self.step(t, test_mode=test_mode)
+            if self.fused_step and self.whole_episode_launch:
+                self.rollout(0, self.episode_limit, test_mode=test_mode)
+            else:
+                for t in range(self.episode_limit):
+                    self.step(t, test_mode=test_mode)
         return self.finish_run(store=store, test_mode=test_mode)
 
     def finish_run(self, store=True, test_mode=False):

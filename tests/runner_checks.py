@@ -346,10 +346,12 @@ def check_fused_rollout_step(device, lib, n_envs=300, kind="c2", path=0, expect_
     if args.use_cuda:
         mac0.cuda()
     runners = []
-    for fused in (True, False):
+    # whole episode as one call (one launch when fused) / the same in two chunks / one fused call per step / two kernels per step
+    for fused, whole in ((True, True), (True, "chunks"), (True, False), (False, False)):
         env = ElectromagneticEnvironment(args, spec=spec, device=device, seed=17, _lib=lib)
         r = BatchedEpisodeRunner(env, copy.deepcopy(mac0), None, args)
-        r.fused_step = fused
+        r.fused_step, r.whole_episode_launch = fused, whole is True
+        r.chunks = whole == "chunks"
         runners.append(r)
     if expect_fused is not None and lib is None:
         fn = N.get_lib().lib.macjd_rollout_fused_supported
@@ -358,12 +360,20 @@ def check_fused_rollout_step(device, lib, n_envs=300, kind="c2", path=0, expect_
         assert bool(got) == expect_fused
     for ep in range(2):
         for r in runners:
-            r.run(store=False)
-        a, b = runners
-        for k in a.traj:
-            assert torch.equal(a.traj[k], b.traj[k]), (ep, k)
-        assert torch.equal(a.r_parts, b.r_parts)
-        assert torch.equal(a.env.step_count, b.env.step_count)
-        for k in ("pd", "detected", "tracking", "snr1", "jam_power", "pd_net", "reward64"):
-            assert torch.equal(getattr(a.env, k), getattr(b.env, k)), (ep, k)
-        assert bool(a.traj["terminated"][-1].all()) and not bool(a.traj["terminated"][0].any())
+            if r.chunks:
+                r.reset()
+                r.rollout(0, 2)
+                r.rollout(2, args.episode_limit - 2)
+            else:
+                r.run(store=False)
+        b = runners[-1]
+        for i, a in enumerate(runners[:-1]):
+            for k in a.traj:
+                assert torch.equal(a.traj[k], b.traj[k]), (ep, i, k)
+            assert torch.equal(a.r_parts, b.r_parts), (ep, i)
+            assert torch.equal(a.env.step_count, b.env.step_count), (ep, i)
+            assert torch.equal(a.mac.hidden_states, b.mac.hidden_states), (ep, i)
+            assert a.t_env == b.t_env and a.mac._rng_step == b.mac._rng_step
+            for k in ("pd", "detected", "tracking", "snr1", "jam_power", "pd_net", "reward64"):
+                assert torch.equal(getattr(a.env, k), getattr(b.env, k)), (ep, i, k)
+        assert bool(b.traj["terminated"][-1].all()) and not bool(b.traj["terminated"][0].any())
