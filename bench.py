@@ -507,19 +507,30 @@ def main():
             runner.t_env = t_env[0]
             runner.step_host(hb["obs"], avail_h, hb)
 
+        # the same call with ONE observation row per env: in this environment every jammer observes the global state
+        # (environment.py:512-522: get_obs() returns the get_state() array once per jammer), so a host-side caller need
+        # not ship J copies of it: state [n, S] in, next state [n, S] out
+        hb_s = {k: v for k, v in hb.items() if k != "obs"}
+        hb_s["state"] = torch.zeros(n, env.state_dim, dtype=torch.float32).pin_memory()
+
+        def host_step_state():
+            runner.t_env = t_env[0]
+            runner.step_host(hb_s["state"], avail_h, hb_s)
+
         def time_host(step_fn):
-            env.reset()
-            hb["obs"].copy_(env.get_obs())
-            mac.init_hidden(n)
+            def restart():
+                env.reset()
+                hb["obs"].copy_(env.get_obs())
+                hb_s["state"].copy_(env.get_state())
+                mac.init_hidden(n)
+            restart()
             t_env[0] = 0
 
             def one():
                 step_fn()
                 t_env[0] += n
                 if (t_env[0] // n) % T == 0:
-                    env.reset()
-                    hb["obs"].copy_(env.get_obs())
-                    mac.init_hidden(n)
+                    restart()
             for _ in range(W_):
                 one()
             torch.cuda.synchronize()
@@ -532,15 +543,21 @@ def main():
 
         t_env_saved = runner.t_env
         dt_two = time_host(host_step_two_calls)
-        dt_e2e = time_host(host_step_fused)
+        dt_rep = time_host(host_step_fused)
+        dt_e2e = time_host(host_step_state)
         runner.t_env = t_env_saved
         obs_b, act_b = hb["obs"].numel() * 4, hb["act_d"].numel() * 4 + hb["act_p"].numel() * 4
+        st_b = hb_s["state"].numel() * 4
         out_b = hb["reward"].numel() * 4 + hb["terminated"].numel()
-        res["e2e"] = {"value": world * M * K_ / dt_e2e, "unit": "env-agent steps/s", "h2d_bytes_per_step": int(obs_b + avail_h.numel()),
-                      "d2h_bytes_per_step": int(act_b + obs_b + out_b), "ms_per_step": dt_e2e / K_ * 1e3,
-                      "api": "BatchedEpisodeRunner.step_host (C-ABI macjd_rollout_step_host): pinned host observations / masks in; "
-                             "actions, power, reward, terminated and next observations out to pinned host buffers; one stream "
-                             "drain per step",
+        res["e2e"] = {"value": world * M * K_ / dt_e2e, "unit": "env-agent steps/s", "h2d_bytes_per_step": int(st_b + avail_h.numel()),
+                      "d2h_bytes_per_step": int(act_b + st_b + out_b), "ms_per_step": dt_e2e / K_ * 1e3,
+                      "api": "BatchedEpisodeRunner.step_host (C-ABI macjd_rollout_step_host, one launch): pinned host state [n, S] (the one "
+                             "observation every jammer of an env shares, environment.py:512-522) and masks in; actions, power, reward, "
+                             "terminated and the next state out to pinned host buffers; one stream drain per step",
+                      "replicated_obs": {"value": world * M * K_ / dt_rep, "ms_per_step": dt_rep / K_ * 1e3,
+                                         "h2d_bytes_per_step": int(obs_b + avail_h.numel()), "d2h_bytes_per_step": int(act_b + obs_b + out_b),
+                                         "api": "the same call with the reference's per-jammer copies of the observation "
+                                                "([n, J, S] in and out)"},
                       "two_calls": {"value": world * M * K_ / dt_two, "ms_per_step": dt_two / K_ * 1e3,
                                     "h2d_bytes_per_step": int(obs_b + avail_h.numel() + act_b), "d2h_bytes_per_step": int(act_b + obs_b + out_b),
                                     "api": "BasicMAC.select_actions_host + ElectromagneticEnvironment.step_host (macjd_agent_act_host + "

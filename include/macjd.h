@@ -282,6 +282,11 @@ typedef struct macjd_agent_io {
                                  `hidden`, which is then only written (or NULL).  A rollout that records
                                  h_t per step (hidden_seq) chains the steps through those records and
                                  saves the second 4 MB store per step (runners/episode_runner.py)     */
+  int32_t obs_group;          /* 0 / 1: `obs` holds one row per agent row ([T][M][O]).  G > 1: rows [k G, (k + 1) G)
+                                 share observation row k and `obs` is [T][M / G][O] -- with G = n_agents, the
+                                 env's global state once per env instead of once per jammer (in this environment
+                                 every agent observes the state, environment.py:512-522).  M must be a multiple of G */
+  int32_t reserved2;
 } macjd_agent_io;
 
 /* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);
@@ -328,7 +333,9 @@ MACJD_API int macjd_rollout_fused_supported(const macjd_agent_weights* w, const 
  * after the stream has drained (small page-locked buffers are read / written in place by the
  * kernel, see macjd_env_step_host).  The recurrent state stays on the device (io->hidden). */
 typedef struct macjd_act_host {
-  const float* obs;         /* host [M][O]                                            */
+  const float* obs;         /* host [M][O]; with io->obs_group = G > 1: [M / G][O] (one row per env: the
+                               global state instead of the reference's per-jammer copies -- half the
+                               bytes over PCIe at two jammers; ask macjd_env_host for `state`, not `obs`) */
   const uint8_t* avail;     /* host [M][A], optional (NULL: io->avail is used as is)  */
   int32_t* actions;         /* host [M]                                               */
   float* power;             /* host [M]                                               */

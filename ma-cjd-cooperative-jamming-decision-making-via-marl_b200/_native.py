@@ -55,7 +55,8 @@ class AgentIO(C.Structure):
                 ("rand_actions", c_void_p), ("epsilon", c_float), ("rng_step", C.c_uint32), ("seed", c_uint64),
                 ("actions", c_void_p), ("power", c_void_p), ("q_chosen", c_void_p), ("part", c_int32), ("rng_row_offset", c_int32),
                 ("gate_x", c_void_p), ("epsilon_dev", c_void_p), ("rng_step_dev", c_void_p),
-                ("actions_mirror", c_void_p), ("power_mirror", c_void_p), ("hidden_in", c_void_p)]
+                ("actions_mirror", c_void_p), ("power_mirror", c_void_p), ("hidden_in", c_void_p),
+                ("obs_group", c_int32), ("reserved2", c_int32)]
 
 
 MAX_COPY_KEYS = 12    # include/macjd.h: MACJD_MAX_COPY_KEYS

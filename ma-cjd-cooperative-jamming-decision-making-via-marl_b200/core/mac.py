@@ -106,6 +106,10 @@ class BasicMAC:
             B = obs.shape[0]
             M = B * self.n_agents
             dev = self.device
+            # obs [B, obs]: ONE row per env -- the global state, which every agent of the env observes in this
+            # environment (environment.py:512-522 returns get_state() once per jammer); the launch then runs with
+            # obs_group = n_agents and half as many bytes cross PCIe at two jammers.  obs [B, N, obs]: the reference's layout.
+            shared = obs.dim() == 2 if torch.is_tensor(obs) else np.ndim(obs) == 2
             if self.hidden_states is None or self.hidden_states.shape[0] != M:
                 self.init_hidden(batch_size=B)
             if self.hidden_states.device != dev:
@@ -116,14 +120,15 @@ class BasicMAC:
                 actions_out = torch.zeros(B, self.n_agents, dtype=torch.int32, pin_memory=pin)
             if power_out is None:
                 power_out = torch.zeros(B, self.n_agents, dtype=torch.float32, pin_memory=pin)
-            st = {"obs": torch.empty(M, self.input_shape, dtype=torch.float32, device=dev),
+            st = {"obs": torch.empty(B if shared else M, self.input_shape, dtype=torch.float32, device=dev),
                   "avail": torch.ones(M, A, dtype=torch.uint8, device=dev),
                   "actions": torch.empty(M, dtype=torch.int32, device=dev), "power": torch.empty(M, dtype=torch.float32, device=dev),
                   "q_chosen": torch.empty(M, dtype=torch.float32, device=dev)}
             io = N.AgentIO(n_rows=M, n_steps=1, obs=st["obs"].data_ptr(), hidden=self.hidden_states.data_ptr(), hidden_zero_init=0,
                            test_mode=0, tile_rows=0, path=self.agent.path, avail=st["avail"].data_ptr(), epsilon=0.0, rng_step=0,
                            seed=self.seed & 0xFFFFFFFFFFFFFFFF, actions=st["actions"].data_ptr(),
-                           power=st["power"].data_ptr(), q_chosen=st["q_chosen"].data_ptr())
+                           power=st["power"].data_ptr(), q_chosen=st["q_chosen"].data_ptr(),
+                           obs_group=self.n_agents if shared else 0)
             pinned = dev.type == "cuda" and all(torch.is_tensor(v) and v.is_pinned() for v in (obs, avail, actions_out, power_out))
             hs = N.ActHost(obs=N.ptr(obs), avail=N.ptr(avail), actions=N.ptr(actions_out), power=N.ptr(power_out), q_chosen=None,
                            flags=N.HOST_PINNED if pinned else 0)

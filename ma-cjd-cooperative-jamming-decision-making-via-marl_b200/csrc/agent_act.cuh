@@ -167,12 +167,12 @@ __global__ void __launch_bounds__(NT, 1) agent_forward_kernel(const AgentArgs a)
     float* Hnew = B1;
     // ---- observation tile, zero padded to [TM][Op]; init the two small-head accumulators
     {
-      const float* obs = io.obs + (tM + row0) * O;
+      const size_t og = io.obs_group > 1 ? (size_t)io.obs_group : 1;     // rows [k og, (k + 1) og) share observation row k
 #pragma unroll 4
       for (int idx = tid; idx < TM * Op; idx += NT) {
         const int r = idx / Op, k = idx - r * Op;
         float v = 0.f;
-        if (r < valid && k < O) v = __ldg(obs + (size_t)r * O + k);
+        if (r < valid && k < O) v = __ldg(io.obs + ((tM + row0 + r) / og) * O + k);
         Xs[(size_t)r * LDX + k] = v;
       }
       const float bq2 = __ldg(W.bq2);

@@ -34,7 +34,8 @@
 namespace macjd {
 namespace tc {
 
-constexpr int kT2Stages = 2;
+constexpr int kT2Stages = 2;                                // ring stages in their own buffer ...
+constexpr int kT2MaxStages = 4;                             // ... plus, where the xf tile is unused (io.part 4), its two halves
 constexpr int kT2HalfBytes = kTcH * kTcKc * 4 / 2;        // this CTA's 64 weight rows of one hi (or lo) chunk
 constexpr int kT2SubBytes = 2 * kT2HalfBytes;              // hi half + lo half of one chunk
 constexpr int kT2StageBytes = 2 * kT2SubBytes;             // a stage holds two consecutive chunks: one barrier round trip per 64 k
@@ -173,7 +174,7 @@ struct T2Smem {
   unsigned char wst[kT2Stages][kT2StageBytes];
   TcConst c;
   float red[kT2Parts][8][kTcRows];          // partial row sums of the threads that share a row
-  uint64_t w_full[kT2Stages], w_empty[kT2Stages];
+  uint64_t w_full[kT2MaxStages], w_empty[kT2MaxStages];
   uint64_t x_full, x_empty, d_ready, a_ready;
   uint64_t c_full;                          // the constant block has landed
   uint32_t tmem_base;
@@ -220,6 +221,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   const uint32_t slot_seq = t2_slot_seq(mode);
   const int nx = mode == 4 ? 0 : nxc;                            // observation stages per step
   const int supers_per_step = nx + 2 * t2_slot_count(mode);      // ring stages this launch runs per step
+  // The recurrence on pre-computed input products (part 4) never touches the xf tile: its 64 KB become two more ring
+  // stages.  A stage is refilled only after its MMAs have completed (commit -> TMA from L2, ~1.5 k cycles against
+  // 0.9 k of MMA work per stage), so with two stages the tensor pipe waits for every refill; with four the stream
+  // warp runs far enough ahead -- also across timesteps, the weights of step t + 1 being those of step t.
+  const int nstages = (!kWholeStep && mode == 4) ? kT2MaxStages : kT2Stages;
+  auto stage_base = [&](int s_) -> unsigned char* {
+    return s_ < kT2Stages ? S.wst[s_] : (s_ == kT2Stages ? reinterpret_cast<unsigned char*>(S.b0hi) : reinterpret_cast<unsigned char*>(S.b0lo));
+  };
   float* const xhi = S.b0hi;   // the observation block lives in b0 until E1 overwrites it with a1
   float* const xlo = S.b0lo;
 
@@ -232,6 +241,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   // multiples the slots are numbered in MEMORY order (a warp reads 512 contiguous bytes -- full lines
   // from HBM, full-size reads over PCIe when the observations sit in page-locked host memory); the
   // zero padding of k >= obs_dim takes the slots behind the data.  Otherwise thread = (row, 8 k) scalars.
+  const size_t og = io.obs_group > 1 ? (size_t)io.obs_group : 1;   // rows [k og, (k + 1) og) share observation row k
   const bool x_vec = (O & 3) == 0;
   const int O4 = O >> 2;
   auto x_slot = [&](int s_, int xc_, int& r_, int& k4_) -> bool {
@@ -252,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       int r_, k4_;
       const bool data = x_slot(tid + i * kT2EpiThreads, 0, r_, k4_);
       x4_in[i] = (data && r_ < valid && mode != 4)
-                     ? __ldg(reinterpret_cast<const float4*>(io.obs + (size_t)(row0 + r_) * O) + k4_) : make_float4(0.f, 0.f, 0.f, 0.f);
+                     ? __ldg(reinterpret_cast<const float4*>(io.obs + ((size_t)(row0 + r_) / og) * O) + k4_) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   if (warp < kT2EpiWarps) {
@@ -267,7 +277,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #pragma unroll
     for (int j = 0; j < 32 / kT2Parts; ++j) {
       const int kk = part * (32 / kT2Parts) + j;
-      x_in[j] = (live && kk < O && mode != 4 && !x_vec) ? __ldg(io.obs + (size_t)(row0 + r) * O + kk) : 0.f;
+      x_in[j] = (live && kk < O && mode != 4 && !x_vec) ? __ldg(io.obs + ((size_t)(row0 + r) / og) * O + kk) : 0.f;
     }
   }
 
@@ -282,7 +292,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 
   if (tid == 0) {
     // "full" lives in the leader: armed by its stream thread for both CTAs' bytes of a stage
-    for (int s = 0; s < kT2Stages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
+    for (int s = 0; s < kT2MaxStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
     mbar_init(&S.x_full, 2 * kT2EpiThreads); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 2 * kT2EpiThreads);
     mbar_init(&S.c_full, 1);
     fence_mbar_init();
@@ -316,7 +326,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       int s = 0;
       for (int t = 0; t < T; ++t) {
         for (int L = 0; L < supers_per_step; ++L) {
-          if (t > 0 || L >= kT2Stages) { mbar_wait_cluster(&S.w_empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
+          if (t > 0 || L >= nstages) { mbar_wait_cluster(&S.w_empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
           // stages follow the issue order; the packed buffer keeps the single-CTA kernel's layer order
           const int slot = L < nx ? 0 : (int)((slot_seq >> (4 * ((L - nx) >> 1))) & 0xFu);
           const int Lsrc = L < nx ? L : nxc + 2 * (int)((kT2LayerSrc >> (4 * slot)) & 0xFu) + ((L - nx) & 1);
@@ -325,11 +335,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           if (rank == 0) mbar_expect_tx(&S.w_full[s], 2 * kT2StageBytes);       // both CTAs' halves
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
-            tma_half_chunk_2sm(S.wst[s] + sub * kT2SubBytes, &p.wmap, row + sub * (kTcChunkBytes / 128), &S.w_full[s], 0);                        // hi
-            tma_half_chunk_2sm(S.wst[s] + sub * kT2SubBytes + kT2HalfBytes, &p.wmap, row + sub * (kTcChunkBytes / 128) + kTcChunkBytes / 256,
+            tma_half_chunk_2sm(stage_base(s) + sub * kT2SubBytes, &p.wmap, row + sub * (kTcChunkBytes / 128), &S.w_full[s], 0);                   // hi
+            tma_half_chunk_2sm(stage_base(s) + sub * kT2SubBytes + kT2HalfBytes, &p.wmap, row + sub * (kTcChunkBytes / 128) + kTcChunkBytes / 256,
                                &S.w_full[s], 0);                                                                                                      // lo
           }
-          s ^= 1;
+          s = (s + 1 == nstages) ? 0 : s + 1;
         }
       }
     }
@@ -348,7 +358,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t idesc = umma_idesc_tf32(2 * kTcRows, H);
       const uint32_t bh = smem_u32(S.b0hi), bl = smem_u32(S.b0lo), hh = smem_u32(S.hhi), hl = smem_u32(S.hlo);
-      const uint32_t w0 = smem_u32(S.wst[0]);
+      const uint32_t wb[kT2MaxStages] = {smem_u32(stage_base(0)), smem_u32(stage_base(1)), smem_u32(stage_base(2)), smem_u32(stage_base(3))};
       uint32_t full_par = 0, x_full_par = 0, a_ready_par = 0;
       int s = 0;
       for (int t = 0; t < T; ++t) {
@@ -393,7 +403,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
           mbar_wait_cluster(&S.w_full[s], (full_par >> s) & 1u);
           full_par ^= 1u << s;
           fence_after_sync();
-          const uint32_t wbase = w0 + (uint32_t)s * kT2StageBytes;
+          const uint32_t wbase = s == 0 ? wb[0] : s == 1 ? wb[1] : s == 2 ? wb[2] : wb[3];
           if (elect_one()) {
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) {
@@ -420,7 +430,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #ifdef MACJD_TC_PROFILE
           if (post & 2u) { if (lane == 0) TC_STAMP(stamp); ++stamp; }
 #endif
-          s ^= 1;
+          s = (s + 1 == nstages) ? 0 : s + 1;
         }
       }
     }
@@ -468,7 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       }
       for (int xc = 0; xc < nx; ++xc) {
         if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
-        const float* obs = io.obs + (tM + row0 + r) * O;
+        const float* obs = io.obs + ((tM + row0 + r) / og) * O;
         const bool pre = (t == 0 && xc == 0);      // already in registers (requested at kernel entry)
         if (x_vec) {
 #pragma unroll
@@ -477,7 +487,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
             const bool data = x_slot(tid + i * kT2EpiThreads, xc, r_, k4_);
             float4 q = x4_in[i];
             if (!pre)
-              q = (data && r_ < valid) ? ld_obs4(reinterpret_cast<const float4*>(io.obs + (tM + row0 + r_) * O + 32 * xc) + k4_)
+              q = (data && r_ < valid) ? ld_obs4(reinterpret_cast<const float4*>(io.obs + ((tM + row0 + r_) / og) * O + 32 * xc) + k4_)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
             const float v[4] = {q.x, q.y, q.z, q.w};
             store_split4(xhi, xlo, r_, 4 * k4_, 32, v);

@@ -199,7 +199,9 @@ int macjd_rollout_steps(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   const int64_t M = aio->n_rows, n = tab->n_envs, J = tab->n_jammers, O = w->obs_dim, A = w->n_actions, H = w->hidden;
   const int64_t S = (int64_t)tab->n_radars * (6 + tab->n_types) + 2 * J;
   // the agent of step t + 1 reads what the env of step t wrote: the buffers must be the time-major trajectory
-  if (O != S || eio->obs != aio->obs + M * O) return MACJD_ERR_INVALID_ARG;
+  const int64_t og = aio->obs_group > 1 ? aio->obs_group : 1;
+  if (M % og != 0 || O != S) return MACJD_ERR_INVALID_ARG;
+  if (og == 1 ? eio->obs != aio->obs + M * O : (og != J || eio->state != aio->obs + n * O)) return MACJD_ERR_INVALID_ARG;
   if (aio->avail && eio->avail != aio->avail + M * A) return MACJD_ERR_INVALID_ARG;
   if (aio->u_eps || aio->rand_actions || eio->noise || aio->rng_step_dev) return MACJD_ERR_UNSUPPORTED;   // (injected draws: step by step)
   macjd_env_io ke = *eio;
@@ -222,7 +224,7 @@ int macjd_rollout_steps(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   for (int t = 0; t < T && st == MACJD_OK; ++t) {
     macjd_agent_io ka = *aio;
     ka.n_steps = 1;
-    ka.obs = aio->obs + t * M * O;
+    ka.obs = aio->obs + t * (M / og) * O;
     if (aio->avail) ka.avail = aio->avail + t * M * A;
     ka.actions = aio->actions + t * M;
     ka.power = aio->power + t * M;
@@ -344,7 +346,9 @@ int macjd_agent_act_host(const macjd_ctx* ctx, const macjd_agent_weights* w, con
   const size_t M = (size_t)io->n_rows;
   if (M == 0) return MACJD_OK;
   macjd_agent_io k = *io;
-  const size_t obs_bytes = M * w->obs_dim * sizeof(float), avail_bytes = M * w->n_actions;
+  const size_t og = io->obs_group > 1 ? (size_t)io->obs_group : 1;
+  if (M % og != 0) return MACJD_ERR_INVALID_ARG;
+  const size_t obs_bytes = (M / og) * w->obs_dim * sizeof(float), avail_bytes = M * w->n_actions;
   if (const float* d = device_alias(host->obs, obs_bytes, false, host->flags)) k.obs = d;
   else st = copy_async(const_cast<float*>(io->obs), host->obs, obs_bytes, cudaMemcpyHostToDevice, ctx);
   if (st == MACJD_OK && host->avail) {
@@ -463,7 +467,9 @@ int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, 
   const size_t S = (size_t)tab->n_radars * (6 + tab->n_types) + 2 * J;
   const size_t O = (size_t)w->obs_dim, A = (size_t)w->n_actions, H = (size_t)w->hidden;
   // in-place or copy-engine: decided on the whole buffers, so that grouping does not change the transfer mode
-  const float* a_obs = device_alias(ahost->obs, M * O * sizeof(float), false, ahost->flags);
+  const size_t og = aio->obs_group > 1 ? (size_t)aio->obs_group : 1;
+  if (og > 1 && og != J) return MACJD_ERR_INVALID_ARG;         // (one observation row per env, or one per agent)
+  const float* a_obs = device_alias(ahost->obs, (M / og) * O * sizeof(float), false, ahost->flags);
   const uint8_t* a_avail = ahost->avail ? device_alias(ahost->avail, M * A, false, ahost->flags) : nullptr;
   float* a_q = (ahost->q_chosen && aio->q_chosen) ? device_alias(ahost->q_chosen, M * sizeof(float), true, ahost->flags) : nullptr;
   int32_t* a_act = device_alias(ahost->actions, M * sizeof(int32_t), true, ahost->flags);
@@ -497,7 +503,7 @@ int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, 
     macjd_agent_io ka = *aio;
     ka.n_rows = (int32_t)rc;
     ka.rng_row_offset = aio->rng_row_offset + (int32_t)rb;
-    ka.obs = a_obs ? a_obs + rb * O : aio->obs + rb * O;
+    ka.obs = a_obs ? a_obs + (rb / og) * O : aio->obs + (rb / og) * O;
     ka.avail = (ahost->avail && a_avail) ? a_avail + rb * A : offset_ptr(aio->avail, rb * A);
     ka.hidden = offset_ptr(aio->hidden, rb * H);
     ka.hidden_in = offset_ptr(aio->hidden_in, rb * H);
@@ -515,7 +521,7 @@ int macjd_rollout_step_host(const macjd_ctx* ctx, const macjd_agent_weights* w, 
     // page-locked action buffers: the agent kernel writes them as well (no copy-engine operation behind the env kernel)
     ka.actions_mirror = a_act ? a_act + rb : nullptr;
     ka.power_mirror = a_pow ? a_pow + rb : nullptr;
-    if (!a_obs) st = copy_async(const_cast<float*>(ka.obs), ahost->obs + rb * O, rc * O * sizeof(float), cudaMemcpyHostToDevice, c);
+    if (!a_obs) st = copy_async(const_cast<float*>(ka.obs), ahost->obs + (rb / og) * O, (rc / og) * O * sizeof(float), cudaMemcpyHostToDevice, c);
     if (st == MACJD_OK && ahost->avail && !a_avail)
       st = copy_async(const_cast<uint8_t*>(ka.avail), ahost->avail + rb * A, rc * A, cudaMemcpyHostToDevice, c);
     if (st != MACJD_OK) break;

@@ -193,7 +193,9 @@ class ElectromagneticEnvironment:
                 raise ValueError(f"step_host: need act_d and act_p, unknown keys {sorted(unknown)}")
             pinned = all(torch.is_tensor(v) and v.is_pinned() for v in host.values()) and self.device.type == "cuda"
             hs = N.EnvHost(flags=N.HOST_PINNED if pinned else 0, **{k: N.ptr(v) for k, v in host.items()})
-            c = self._host_cache = {"key": key, "host": hs, "io": self._io(self._act_d_dev, self._act_p_dev), "keep": dict(host)}
+            # a caller that keeps the state only (one observation row per env) does not get the per-jammer copies written
+            io = self._io(self._act_d_dev, self._act_p_dev, out=None if "obs" in host else {"obs": None})
+            c = self._host_cache = {"key": key, "host": hs, "io": io, "keep": dict(host)}
         return c["io"], c["host"]
 
     # ------------------------------------------------------------------ reference API

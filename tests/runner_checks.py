@@ -183,15 +183,17 @@ def check_fused_host_step(device, lib, n_envs=9, steps=6, pinned=True):
     from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
     args = rl_args(device, epsilon_anneal_time=20)
     spec = hetero_spec(n_envs, seed=6, active=True, episode_limit=steps - 2)
-    envs = [ElectromagneticEnvironment(args, spec=spec, device=device, seed=13, _lib=lib) for _ in range(2)]
+    envs = [ElectromagneticEnvironment(args, spec=spec, device=device, seed=13, _lib=lib) for _ in range(3)]
     torch.manual_seed(9)
     mac_a = BasicMAC(24, args, _lib=lib)
     if args.use_cuda:
         mac_a.cuda()
-    mac_b = copy.deepcopy(mac_a)
-    for m in (mac_a, mac_b):
+    mac_b, mac_c = copy.deepcopy(mac_a), copy.deepcopy(mac_a)
+    for m in (mac_a, mac_b, mac_c):
         m.init_hidden(n_envs)
     runner = types.SimpleNamespace(mac=mac_b, env=envs[1], t_env=0)
+    # third twin: the host keeps ONE observation row per env (the state) instead of the per-jammer copies
+    runner_s = types.SimpleNamespace(mac=mac_c, env=envs[2], t_env=0)
     hbs = [e.host_buffers(pinned=pinned) for e in envs]
     for hb, e in zip(hbs, envs):
         hb["state"] = torch.zeros(n_envs, e.state_dim)
@@ -200,13 +202,18 @@ def check_fused_host_step(device, lib, n_envs=9, steps=6, pinned=True):
         e.reset()
     obs = [e.get_obs().cpu().contiguous() for e in envs]
     avail = [e.get_avail_actions().cpu().contiguous() for e in envs]
+    hb_s = {k: v for k, v in hbs[2].items() if k != "obs"}
+    hb_s["state"].copy_(envs[2].get_state().cpu())
     for t in range(steps):
         mac_a.select_actions_host(obs[0], avail[0], t * n_envs, actions_out=hbs[0]["act_d"], power_out=hbs[0]["act_p"])
         envs[0].step_host(hbs[0])
         BatchedEpisodeRunner.step_host(runner, obs[1], avail[1], hbs[1])
+        BatchedEpisodeRunner.step_host(runner_s, hb_s["state"], avail[2], hb_s)
         for k in hbs[0]:
             np.testing.assert_array_equal(hbs[1][k].numpy(), hbs[0][k].numpy(), err_msg=f"{k} t={t}")
-        assert torch.equal(mac_a.hidden_states, mac_b.hidden_states)
+            if k != "obs":
+                np.testing.assert_array_equal(hb_s[k].numpy(), hbs[0][k].numpy(), err_msg=f"state-only {k} t={t}")
+        assert torch.equal(mac_a.hidden_states, mac_b.hidden_states) and torch.equal(mac_a.hidden_states, mac_c.hidden_states)
         obs = [hbs[0]["obs"], hbs[1]["obs"]]
     assert runner.t_env == steps * n_envs       # the reference's unit: single-environment steps
 
