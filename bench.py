@@ -452,6 +452,7 @@ def main():
             dt_m = reduce_max(sum(a.elapsed_time(b) for a, b in ev) * 1e-3)
             res["per_step_launch"] = {"value": res["value"], "ms_per_step": res["ms_per_step"],
                                       "what": "the same K timesteps as one macjd_rollout_step launch each, L2 flushed before every step"}
+            res["dt_persistent_per_step"] = dt_m / K_
             res.update({"value": world * M * K_ / dt_m, "ms_per_step": dt_m / K_ * 1e3, "launches": len(plan),
                         "launch": f"macjd_rollout_steps: {len(plan)} launch(es) of up to {T} timesteps (one episode) each; L2 flushed before each launch"})
 
@@ -564,8 +565,17 @@ def main():
                                            "macjd_env_step_host): the reference's two calls, two stream drains per step"}}
         return res
 
-    def agent_roofline(mac, M, dt_agent, dt_simt, O, A, H):
+    def agent_roofline(mac, M, dt_agent, dt_simt, O, A, H, dt_persistent=None):
+        """dt_agent: one single-step launch of the agent kernel alone.  dt_persistent: per-timestep time of the multi-step
+        launches the timed region consists of (the same kernel looping over an episode, env steps inline): when given,
+        `achieved` / `frac` describe THAT launch (algorithmic FLOPs of its timesteps / its duration; the env work adds
+        time but no FLOPs) and the single-step figures move to `single_step_launch`."""
         fpr, fpr_coded = flop_per_row(O, A, H), flop_per_row_as_coded(O, A, H)
+        single = None
+        if dt_persistent is not None:
+            single = {"us_per_launch": dt_agent * 1e6, "achieved": M * fpr / dt_agent / 1e12,
+                      "what": "one single-timestep launch of the agent kernel alone (no env step), L2 flushed"}
+            dt_agent = dt_persistent
         name = agent_kernel_name(mac)
         tc = name.startswith("agent_forward_tc2")
         peak = tf32_peak if tc else fp32_peak
@@ -578,6 +588,12 @@ def main():
              "simt_kernel": {"kernel": "agent_forward_kernel<256>", "bound": "fp32", "us_per_launch": dt_simt * 1e6,
                              "achieved": M * fpr / dt_simt / 1e12, "peak": fp32_peak, "frac": M * fpr / dt_simt / 1e12 / fp32_peak,
                              "peak_source": fp32_src}}
+        if single is not None:
+            single["frac"] = single["achieved"] / peak
+            r["single_step_launch"] = single
+            r["us_per_launch"] = "see us_per_timestep_in_launch x timesteps per launch (config.timed_as)"
+            r["us_per_timestep_in_launch"] = dt_agent * 1e6
+            r["kernel"] = name + "<whole step, env fused> looping over the timesteps of an episode (macjd_rollout_steps)"
         if tc:
             r["executed_tensor_tflops"] = 3 * M * fpr / dt_agent / 1e12
             r["note"] = ("achieved counts algorithmic FLOPs once; the 3xTF32 split executes 3x that on the tensor pipe. CTA pairs issue "
@@ -616,7 +632,7 @@ def main():
     line["per_step_launch"] = r2.get("per_step_launch")
     line.update({"value": r2["value"], "ms_per_step": r2["ms_per_step"], "e2e": r2["e2e"],
                  "gpu_launches": r2.get("launches", (1 if r2["fused"] else 2) * K),
-                 "roofline": agent_roofline(mac, M, r2["dt_agent"], r2["dt_simt"], OBS, N_ACTIONS, HID),
+                 "roofline": agent_roofline(mac, M, r2["dt_agent"], r2["dt_simt"], OBS, N_ACTIONS, HID, r2.get("dt_persistent_per_step")),
                  "roofline_env": env_roofline(n_envs, r2["dt_env"], ENV_BYTES_PER_STEP, "dram_bytes_per_launch_at_bench_size"),
                  "parity": r2.get("parity"),
                  # the metric for the env step alone and the agent act alone (same launches, timed apart)
@@ -691,7 +707,7 @@ def main():
                "launches_per_step": 1 if r3["fused"] else 2,
                "env_only": {"value": world * M3 / r3["dt_env"], "us_per_launch": r3["dt_env"] * 1e6},
                "act_only": {"value": world * M3 / r3["dt_agent"], "us_per_launch": r3["dt_agent"] * 1e6},
-               "roofline": agent_roofline(mac3, M3, r3["dt_agent"], r3["dt_simt"], S3, A3, HID),
+               "roofline": agent_roofline(mac3, M3, r3["dt_agent"], r3["dt_simt"], S3, A3, HID, r3.get("dt_persistent_per_step")),
                "roofline_env": env_roofline(n3, r3["dt_env"], C3["env_bytes"], "dram_bytes_per_launch_c3"),
                "parity": r3.get("parity"), "cpu_baseline": None}
         if want_cpu:
