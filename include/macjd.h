@@ -292,6 +292,17 @@ typedef struct macjd_agent_io {
 /* One launch: for t in 0..T-1: h <- GRU(relu(fc1 obs_t), h); P <- actor(obs_t);
  * Q_a <- Qhead(h, a, P_a) for all a; masked epsilon-greedy / argmax / gathers. */
 MACJD_API int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io);
+/* The time-unrolled forward of core/qmix.py:217-280 (the learner's eval / target unrolls: T steps from `hidden`
+ * or zeros, h_t / Q for all actions / arg-max / gathers out, no action selection) as batched layers: every layer
+ * but the recurrence h_t -> h_t+1 runs as ONE dense product over all T x M rows, the recurrence as per-step
+ * products, all on the tensor cores (3xTF32) where they fill its tiles.  For network widths the fused CTA-pair
+ * kernel does not take (macjd_agent_pair_supported == 0, e.g. rnn_hidden_dim 256); same outputs as
+ * macjd_agent_forward with n_steps = T up to FP32 summation order.  `io` as for macjd_agent_forward (actions /
+ * power / obs_group must be unset); workspace: macjd_agent_unroll_workspace_floats() floats, caller-owned. */
+MACJD_API size_t macjd_agent_unroll_workspace_floats(const macjd_agent_weights* w, int32_t n_rows, int32_t n_steps);
+MACJD_API int macjd_agent_unroll(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io, float* workspace,
+                                 size_t workspace_floats);
+
 /* 1 if the CTA-pair tensor-core kernel (io->path 3 / auto, io->part 1 and 2) can run these weights. */
 MACJD_API int macjd_agent_pair_supported(const macjd_agent_weights* w);
 /* k-extent of one packed weight chunk in macjd_agent_weights.tc_chunks as this build of the library

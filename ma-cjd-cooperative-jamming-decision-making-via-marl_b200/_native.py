@@ -156,6 +156,8 @@ class NativeLib:
         for name, restype, argtypes in (
             ("macjd_replay_copy", C.c_int, [P(Ctx), P(CopyDesc), i32, vp, i32, i32]),
             ("macjd_env_derived_bytes", sz, [P(EnvTables)]),
+            ("macjd_agent_unroll_workspace_floats", sz, [P(AgentWeights), i32, i32]),
+            ("macjd_agent_unroll", C.c_int, [P(Ctx), P(AgentWeights), P(AgentIO), vp, sz]),
             ("macjd_env_prepare", C.c_int, [P(Ctx), P(EnvTables), vp]),
             ("macjd_mixer_workspace_floats", sz, [P(MixerDims)]),
             ("macjd_mixer_forward", C.c_int, [P(Ctx), P(MixerDims), P(MixerParams), vp, vp, vp, vp, sz]),

@@ -383,6 +383,17 @@ class RNNAgent(nn.Module):
             return out
         io = N.AgentIO(n_rows=M, n_steps=T, obs=p(obs), hidden=p(hidden), hidden_zero_init=int(zero_init),
                        hidden_seq=p(out.get("hidden_seq")), part=0, **common, **heads)
+        if split_unroll and T > 1 and path in (0, 3) and not select and not self._pair_kernel_ok(pk):
+            # Widths the fused CTA-pair kernel does not take (rnn_hidden_dim = 256): the time-unrolled pass as batched
+            # layers -- every layer but the recurrence is one dense product over all T x M rows -- on the tensor
+            # cores where they fill its tiles (include/macjd.h: macjd_agent_unroll).  FP32-level accuracy (3xTF32).
+            L = self.lib()
+            n_ws = int(L.lib.macjd_agent_unroll_workspace_floats(N.C.byref(pk.cstruct()), M, T))
+            ws = self.__dict__.get("_unroll_ws")
+            if ws is None or ws.numel() < n_ws or ws.device != dev:
+                ws = self.__dict__["_unroll_ws"] = torch.empty(max(n_ws, 4), dtype=torch.float32, device=dev)
+            L.callv("macjd_agent_unroll", self._ctx(), pk.cstruct(), io, ws, ws.numel())
+            return out
         self.lib().call("macjd_agent_forward", self._ctx(), pk.cstruct(), io)
         return out
 

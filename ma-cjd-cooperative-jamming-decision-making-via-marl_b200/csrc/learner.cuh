@@ -5,7 +5,7 @@
 //   grad norm, clip, Adam       core/qmix.py:197-200
 #pragma once
 #include "learner_kernels.cuh"
-#include "sgemm.cuh"
+#include "tc_gemm.cuh"
 
 namespace macjd {
 

@@ -166,11 +166,11 @@ __global__ void __launch_bounds__(256) gather_q_kernel(const float* __restrict__
 // second pass.  Used for bias gradients and LayerNorm dgamma / dbeta.
 constexpr int kColsumRows = 64;     // rows per partial block: each thread walks them serially, so short chunks, many blocks
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y,
-                                                             int R, int Cn, int ldx, float* __restrict__ part) {
+                                                             int R, int Cn, int ldx, float* __restrict__ part, int rows_per_chunk) {
   grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
-  const int r0 = blockIdx.y * kColsumRows, r1 = min(R, r0 + kColsumRows);
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
   float s = 0.f;
   for (int r = r0; r < r1; ++r) {
     const float x = X[(size_t)r * ldx + c];
@@ -190,9 +190,13 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 inline size_t colsum_ws_floats(int R, int Cn) { return (size_t)((R + kColsumRows - 1) / kColsumRows) * Cn; }
 inline void colsum(cudaStream_t st, const float* X, const float* Y, int R, int Cn, int ldx, float* out, float* ws) {
   if (Cn <= 0) return;
-  const int chunks = (R + kColsumRows - 1) / kColsumRows;
+  // at most 256 chunks (the second pass walks them serially in one block per 256 columns: 1 584 chunks of 64 rows at
+  // 101 376 rows made it 93 us), at least 64 rows each
+  int rows = (R + 255) / 256;
+  if (rows < kColsumRows) rows = kColsumRows;
+  const int chunks = (R + rows - 1) / rows;
   if (chunks == 0) { cudaMemsetAsync(out, 0, sizeof(float) * Cn, st); return; }
-  MACJD_LAUNCH(colsum_partial_kernel, dim3((Cn + 255) / 256, chunks), dim3(256), 0, st, X, Y, R, Cn, ldx, ws);
+  MACJD_LAUNCH(colsum_partial_kernel, dim3((Cn + 255) / 256, chunks), dim3(256), 0, st, X, Y, R, Cn, ldx, ws, rows);
   MACJD_LAUNCH(colsum_final_kernel, dim3((Cn + 255) / 256), dim3(256), 0, st, (const float*)ws, chunks, Cn, out);
 }
 

@@ -12,6 +12,7 @@
 #include "agent_act_tc2.cuh"
 #include "replay.cuh"
 #include "learner.cuh"
+#include "agent_unroll.cuh"
 #include "tc05.cuh"
 
 #include <stdio.h>
@@ -268,6 +269,18 @@ int macjd_rollout_fused_supported(const macjd_agent_weights* w, const macjd_env_
   (void)w; (void)tab;
   return 0;
 #endif
+}
+
+size_t macjd_agent_unroll_workspace_floats(const macjd_agent_weights* w, int32_t n_rows, int32_t n_steps) {
+  if (!w || n_rows < 0 || n_steps < 1) return 0;
+  return macjd::unroll_ws_layout(*w, n_rows, n_steps, nullptr).total;
+}
+
+int macjd_agent_unroll(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io, float* workspace,
+                       size_t workspace_floats) {
+  MACJD_ENTER(ctx);
+  if (!w || !io) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::agent_unroll_gemm(ctx, *w, *io, workspace, workspace_floats));
 }
 
 int macjd_agent_pair_supported(const macjd_agent_weights* w) {

@@ -15,7 +15,7 @@
 
 namespace macjd {
 
-enum GemmAct : int { kActNone = 0, kActRelu = 1, kActClamp = 2 };
+enum GemmAct : int { kActNone = 0, kActRelu = 1, kActClamp = 2, kActSigmoid = 3 };
 
 struct GemmArgs {
   const float* A; const float* B; float* C;
@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
       if (g.bias) v += g.bias[n];
       if (g.act == kActRelu) v = fmaxf(v, 0.f);
       else if (g.act == kActClamp) v = fminf(fmaxf(v, g.lo), g.hi);
+      else if (g.act == kActSigmoid) v = 1.0f / (1.0f + expf(-v));
       if (g.mask) v = g.mask[(size_t)m * g.ldmask + n] > 0.f ? v : 0.f;
       float* c = g.C + (size_t)m * g.ldc + n;
       *c = g.accumulate ? *c + v : v;
@@ -139,13 +140,21 @@ inline size_t gemm_splitk_ws_floats(int M, int N, int K) {
   return s > 1 ? (size_t)s * M * N : 0;
 }
 
-inline void gemm(cudaStream_t st, const float* A, int lda, bool ta, const float* B, int ldb, bool tb, float* C,
-                 int ldc, int M, int N, int K, const GemmOpts& o = GemmOpts()) {
-  if (M <= 0 || N <= 0) return;
+inline GemmArgs gemm_args(const float* A, int lda, bool ta, const float* B, int ldb, bool tb, float* C, int ldc, int M, int N,
+                          int K, const GemmOpts& o) {
   GemmArgs g;
   g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
   g.ta = ta; g.tb = tb; g.bias = o.bias; g.act = o.act; g.lo = o.lo; g.hi = o.hi;
   g.mask = o.mask; g.ldmask = o.ldmask; g.accumulate = o.accumulate;
+  g.k_per_split = K; g.partial = nullptr;
+  return g;
+}
+
+// the FP32 SIMT kernel (small problems, host emulation)
+inline void gemm_simt(cudaStream_t st, const float* A, int lda, bool ta, const float* B, int ldb, bool tb, float* C,
+                      int ldc, int M, int N, int K, const GemmOpts& o = GemmOpts()) {
+  if (M <= 0 || N <= 0) return;
+  GemmArgs g = gemm_args(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, o);
   int splits = 1;
   if (o.splitk_ws && !o.bias && o.act == kActNone && !o.mask) {
     splits = gemm_splits(M, N, K);

@@ -1,0 +1,301 @@
+// General GEMM of the learner on the tcgen05 tensor cores (3xTF32: FP32-level accuracy), same contract as
+// sgemm_kernel (sgemm.cuh: GemmArgs -- operand orientations ta / tb, bias, ReLU / clamp / sigmoid, mask, accumulate,
+// deterministic split-K partials).  ncu on the FP32 SIMT GEMM at the stress shapes (BASELINE config 4: 101 376 mixer
+// rows, 202 752 Q-head rows, K = 128 / 256) shows it FMA-issue bound at ~15 TFLOP/s -- dense contractions, which is
+// where north_star sends the work to the tensor cores.
+//
+// One CTA = one 128 x 128 output tile (cta_group::1, M = 128, N = 128 MMAs, accumulator = 128 TMEM columns).
+//   warps 0-7  stage the operands: global FP32 -> registers -> TF32 hi / lo split -> shared memory in the K-major
+//              no-swizzle UMMA layout (tc05.cuh), 16 k per stage, three stages (32 KB each: two CTAs share an SM, one
+//              loads while the other computes); the next chunk's global loads are in flight while the current one is
+//              split and stored; either operand may be
+//              k-contiguous in memory (16-byte loads along k) or row-contiguous (16-byte loads along the rows: the
+//              transposed forms of the weight-gradient products, whose contraction runs over the batch rows);
+//              afterwards they are the epilogue (thread = row; warps w and w + 4 split the 128 columns)
+//   warp 8     issues the MMAs (whole warp converged, one elected lane: operands in uniform registers) and commits
+//              each stage back to the loaders
+#pragma once
+#include <stdlib.h>
+#include "sgemm.cuh"
+#include "tc05.cuh"
+
+#ifndef MACJD_TEST_HOST_EMULATION
+namespace macjd {
+namespace tc {
+
+constexpr int kGtM = 128, kGtN = 128, kGtK = 16, kGtStages = 3;     // 96 KB of stages: two CTAs per SM
+constexpr int kGtLoadThreads = 256, kGtThreads = kGtLoadThreads + 32;
+constexpr int kGtTileFloats = kGtM * kGtK;                       // one hi (or lo) operand tile of a stage
+
+struct GtSmem {
+  float a[kGtStages][2][kGtTileFloats];                          // [stage][hi / lo]
+  float b[kGtStages][2][kGtTileFloats];
+  uint64_t full[kGtStages], empty[kGtStages], done;
+  uint32_t tmem_base;
+};
+
+// write 4 consecutive k of one row (hi and lo parts) into a [128][kGtK] operand tile
+__device__ __forceinline__ void store_split4_tile(float* hi, float* lo, int r, int k, const float (&v)[4]) {
+  const uint32_t off = umma_off_bytes(r, k, kGtK) >> 2;
+  float4 h, l;
+  h.x = tf32_hi(v[0]); h.y = tf32_hi(v[1]); h.z = tf32_hi(v[2]); h.w = tf32_hi(v[3]);
+  l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+  *reinterpret_cast<float4*>(hi + off) = h;
+  *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+__device__ __forceinline__ void gt_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One 128 x 16 operand tile, element (row, k) = src(row0 + row, k0 + k), zero outside the matrix, in two halves so
+// that the global loads of the NEXT chunk are in flight while this chunk is split and stored:
+//   gt_load : global -> registers (kGtVec 16-byte vectors per thread)
+//   gt_store: registers -> TF32 hi / lo -> shared memory (UMMA K-major layout)
+// kContigK: src(r, k) = p[r * ld + k] (vectors along k); else src(r, k) = p[k * ld + r] (vectors along the rows).
+constexpr int kGtVec = kGtTileFloats / 4 / kGtLoadThreads;      // 2
+
+template <bool kContigK>
+__device__ __forceinline__ void gt_load(float4 (&x)[kGtVec], const float* p, int ld, int row0, int n_rows, int k0, int kend, int tid,
+                                        bool vec_ok) {
+#pragma unroll
+  for (int q = 0; q < kGtVec; ++q) {
+    const int idx = tid + q * kGtLoadThreads;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kContigK) {
+      const int r = idx >> 2, k = (idx & 3) << 2;
+      const int gr = row0 + r, gk = k0 + k;
+      if (gr < n_rows) {
+        const float* s = p + (size_t)gr * ld + gk;
+        if (vec_ok && gk + 3 < kend) {
+          x[q] = __ldg(reinterpret_cast<const float4*>(s));
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gk + j < kend) v[j] = __ldg(s + j);
+      }
+    } else {
+      const int k = idx >> 5, r = (idx & 31) << 2;
+      const int gr = row0 + r, gk = k0 + k;
+      if (gk < kend) {
+        const float* s = p + (size_t)gk * ld + gr;
+        if (vec_ok && gr + 3 < n_rows) {
+          x[q] = __ldg(reinterpret_cast<const float4*>(s));
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gr + j < n_rows) v[j] = __ldg(s + j);
+      }
+    }
+    x[q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+template <bool kContigK>
+__device__ __forceinline__ void gt_store(float* hi, float* lo, const float4 (&x)[kGtVec], int tid) {
+#pragma unroll
+  for (int q = 0; q < kGtVec; ++q) {
+    const int idx = tid + q * kGtLoadThreads;
+    const float v[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+    if (kContigK) {
+      store_split4_tile(hi, lo, idx >> 2, (idx & 3) << 2, v);
+    } else {
+      const int k = idx >> 5, r = (idx & 31) << 2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = umma_off_bytes(r + j, k, kGtK) >> 2;
+        const float h = tf32_hi(v[j]);
+        hi[off] = h;
+        lo[off] = v[j] - h;
+      }
+    }
+  }
+}
+
+template <bool kAContigK, bool kBContigK>
+__global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g) {
+  extern __shared__ __align__(1024) unsigned char gt_raw[];
+  GtSmem& S = *reinterpret_cast<GtSmem*>(gt_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * kGtM, n0 = blockIdx.x * kGtN;
+  const int kbeg = blockIdx.z * g.k_per_split;
+  const int kend = min(g.K, kbeg + g.k_per_split);
+  const int n_chunks = (kend - kbeg + kGtK - 1) / kGtK;
+  if (tid == 0) {
+    for (int s = 0; s < kGtStages; ++s) { mbar_init(&S.full[s], kGtLoadThreads); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.done, 1);
+    fence_mbar_init();
+  }
+  if (warp == kGtLoadThreads / 32) tmem_alloc(&S.tmem_base, kGtN);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+  grid_dependency_wait();               // (operands may come from the preceding kernel of the stream)
+
+  if (warp < kGtLoadThreads / 32) {
+    // ================================================================== loaders, then epilogue
+    // 16-byte loads need aligned rows: base pointer and leading dimension multiples of four floats
+    const bool a_vec = ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && (g.lda & 3) == 0 && (!kAContigK || (kbeg & 3) == 0);
+    const bool b_vec = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && (g.ldb & 3) == 0 && (!kBContigK || (kbeg & 3) == 0);
+    uint32_t empty_par = 0;
+    float4 xa[kGtVec], xb[kGtVec], ya[kGtVec], yb[kGtVec];
+    gt_load<kAContigK>(xa, g.A, g.lda, m0, g.M, kbeg, kend, tid, a_vec);
+    gt_load<kBContigK>(xb, g.B, g.ldb, n0, g.N, kbeg, kend, tid, b_vec);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c % kGtStages;
+      // the next chunk's loads go out before this chunk is converted and stored
+      if (c + 1 < n_chunks) {
+        gt_load<kAContigK>(ya, g.A, g.lda, m0, g.M, kbeg + (c + 1) * kGtK, kend, tid, a_vec);
+        gt_load<kBContigK>(yb, g.B, g.ldb, n0, g.N, kbeg + (c + 1) * kGtK, kend, tid, b_vec);
+      }
+      if (c >= kGtStages) { mbar_wait(&S.empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
+      gt_store<kAContigK>(S.a[s][0], S.a[s][1], xa, tid);
+      gt_store<kBContigK>(S.b[s][0], S.b[s][1], xb, tid);
+      fence_async_smem();
+      gt_mbar_arrive(&S.full[s]);
+#pragma unroll
+      for (int q = 0; q < kGtVec; ++q) { xa[q] = ya[q]; xb[q] = yb[q]; }
+    }
+    mbar_wait(&S.done, 0);
+    fence_after_sync();
+    const int q4 = warp & 3, half = warp >> 2;
+    const int m = m0 + q4 * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 64);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      float v[16];
+      tmem_ld16_nowait(tl + (uint32_t)c0, v);
+      tmem_ld_wait();
+      reg_fence(v);
+      if (m < g.M) {
+        const int nb = n0 + half * 64 + c0;
+        if (gridDim.z > 1) {
+          float* dst = g.partial + ((size_t)blockIdx.z * g.M + m) * g.N + nb;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < g.N) dst[j] = v[j];
+        } else {
+          float* c = g.C + (size_t)m * g.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (nb + j >= g.N) continue;
+            float x = v[j];
+            if (g.bias) x += __ldg(g.bias + nb + j);
+            if (g.act == kActRelu) x = fmaxf(x, 0.f);
+            else if (g.act == kActClamp) x = fminf(fmaxf(x, g.lo), g.hi);
+            else if (g.act == kActSigmoid) x = 1.0f / (1.0f + expf(-x));
+            if (g.mask) x = g.mask[(size_t)m * g.ldmask + nb + j] > 0.f ? x : 0.f;
+            c[j] = g.accumulate ? c[j] + x : x;
+          }
+        }
+      }
+    }
+  } else {
+    // ================================================================== MMA issue (warp-uniform, one elected lane)
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t idesc = umma_idesc_tf32(kGtM, kGtN);
+    uint32_t full_par = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c % kGtStages;
+      mbar_wait(&S.full[s], (full_par >> s) & 1u);
+      full_par ^= 1u << s;
+      fence_after_sync();
+      if (elect_one()) {
+        const uint64_t dah = umma_smem_desc(smem_u32(S.a[s][0]), 128, kGtK * 32), dal = umma_smem_desc(smem_u32(S.a[s][1]), 128, kGtK * 32);
+        const uint64_t dbh = umma_smem_desc(smem_u32(S.b[s][0]), 128, kGtK * 32), dbl = umma_smem_desc(smem_u32(S.b[s][1]), 128, kGtK * 32);
+#pragma unroll
+        for (int ks = 0; ks < kGtK / 8; ++ks) {
+          const uint64_t adv = (uint64_t)((ks * 256) >> 4);
+          mma_tf32_ss(tmem_u, dah + adv, dbh + adv, idesc, (c == 0 && ks == 0) ? 0u : 1u);
+          mma_tf32_ss(tmem_u, dal + adv, dbh + adv, idesc, 1u);
+          mma_tf32_ss(tmem_u, dah + adv, dbl + adv, idesc, 1u);
+        }
+        mma_commit(&S.empty[s]);
+        if (c == n_chunks - 1) mma_commit(&S.done);
+      }
+      __syncwarp();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == kGtLoadThreads / 32) tmem_dealloc(tmem, kGtN);
+}
+
+inline size_t tc_gemm_smem_bytes() { return sizeof(GtSmem) + 1024; }
+
+// K splits for the tensor-core kernel: enough CTAs to fill the chip, slices of at least 256 rows
+inline int tc_gemm_splits(int M, int N, int K, size_t ws_floats) {
+  const int tiles = ((M + kGtM - 1) / kGtM) * ((N + kGtN - 1) / kGtN);
+  if (K < 2048 || tiles >= kNumSMs) return 1;
+  int s = (kNumSMs + tiles - 1) / tiles;
+  const int maxs = (K + 255) / 256;
+  if (s > maxs) s = maxs;
+  const size_t fit = ws_floats / ((size_t)M * N);
+  if ((size_t)s > fit) s = (int)fit;
+  return s < 1 ? 1 : s;
+}
+
+// Worth the tensor cores: enough work to fill 128 x 128 tiles.  (MACJD_TC_GEMM=0 keeps every GEMM on the FP32 kernel.)
+inline bool tc_gemm_wanted(int M, int N, int K) {
+  static const bool on = [] { const char* e = getenv("MACJD_TC_GEMM"); return !(e && e[0] == '0'); }();
+  return on && N >= 32 && M >= 64 && (double)M * N * K >= (double)(1 << 24);
+}
+
+// returns false if the launch could not be set up (caller falls back to the FP32 kernel)
+inline bool tc_gemm_launch(cudaStream_t st, int device, GemmArgs g, const GemmOpts& o) {
+  static PerDeviceMax opted;
+  const size_t smem = tc_gemm_smem_bytes();
+  if (!opted.covers(device, smem)) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    opted.record(device, smem);
+  }
+  if (watchdog_arm(device) != MACJD_OK) return false;
+  int splits = 1;
+  if (o.splitk_ws && !o.bias && o.act == kActNone && !o.mask) splits = tc_gemm_splits(g.M, g.N, g.K, o.splitk_ws_floats);
+  g.k_per_split = ((g.K + splits - 1) / splits + kGtK - 1) / kGtK * kGtK;
+  if (g.k_per_split < kGtK) g.k_per_split = kGtK;
+  splits = (g.K + g.k_per_split - 1) / g.k_per_split;
+  if (splits < 1) splits = 1;
+  g.partial = o.splitk_ws;
+  const dim3 grid((g.N + kGtN - 1) / kGtN, (g.M + kGtM - 1) / kGtM, splits);
+  // A(m,k) is k-contiguous unless ta; B(k,n) is k-contiguous (per output column n) when tb
+  const bool ak = !g.ta, bk = g.tb != 0;
+  if (ak && bk) MACJD_LAUNCH((tc_gemm_kernel<true, true>), grid, dim3(kGtThreads), smem, st, g);
+  else if (ak) MACJD_LAUNCH((tc_gemm_kernel<true, false>), grid, dim3(kGtThreads), smem, st, g);
+  else if (bk) MACJD_LAUNCH((tc_gemm_kernel<false, true>), grid, dim3(kGtThreads), smem, st, g);
+  else MACJD_LAUNCH((tc_gemm_kernel<false, false>), grid, dim3(kGtThreads), smem, st, g);
+  if (splits > 1) {
+    const int total = g.M * g.N;
+    MACJD_LAUNCH(splitk_reduce_kernel, dim3((total + 255) / 256), dim3(256), 0, st, (const float*)o.splitk_ws, splits, g.M, g.N,
+                 g.C, g.ldc, o.accumulate);
+  }
+  return true;
+}
+
+}  // namespace tc
+}  // namespace macjd
+#endif  // !MACJD_TEST_HOST_EMULATION
+
+namespace macjd {
+// C = epi(A B): the tensor-core kernel where the problem fills its tiles, else the FP32 SIMT kernel
+inline void gemm(cudaStream_t st, const float* A, int lda, bool ta, const float* B, int ldb, bool tb, float* C,
+                 int ldc, int M, int N, int K, const GemmOpts& o = GemmOpts()) {
+  if (M <= 0 || N <= 0) return;
+#ifndef MACJD_TEST_HOST_EMULATION
+  if (tc::tc_gemm_wanted(M, N, K)) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && tc::tc_gemm_launch(st, dev, gemm_args(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, o), o)) return;
+  }
+#endif
+  gemm_simt(st, A, lda, ta, B, ldb, tb, C, ldc, M, N, K, o);
+}
+}  // namespace macjd

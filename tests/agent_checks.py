@@ -115,7 +115,7 @@ def random_agent(seed, O, A, H, AH, Nn, device, lib=None):
     return mac, args
 
 
-def check_unroll_against_oracle(device, lib=None, O=24, A=5, H=128, AH=128, Nn=2, B=19, T=5, seed=3, tile_rows=0):
+def check_unroll_against_oracle(device, lib=None, O=24, A=5, H=128, AH=128, Nn=2, B=19, T=5, seed=3, tile_rows=0, path=None):
     """T-step unroll inside one launch (learner mode): all-action Q, unmasked argmax, gather of
     given actions and hidden sequence against the eager oracle; ragged row count."""
     mac, args = random_agent(seed, O, A, H, AH, Nn, device, lib)
@@ -126,7 +126,7 @@ def check_unroll_against_oracle(device, lib=None, O=24, A=5, H=128, AH=128, Nn=2
     sel = rng.integers(0, A, size=(T, M)).astype(np.int32)
     sd = {k: v.detach().cpu() for k, v in mac.agent.state_dict().items()}
     out = mac.agent.run(torch.from_numpy(obs).to(dev), None, n_steps=T, zero_init=True, want_q=True, want_greedy=True,
-                        sel_actions=torch.from_numpy(sel), want_hidden_seq=True, want_params=True, tile_rows=tile_rows)
+                        sel_actions=torch.from_numpy(sel), want_hidden_seq=True, want_params=True, tile_rows=tile_rows, path=path)
     sd64 = AO.cast_sd(sd, torch.float64)
     h = torch.zeros(M, H)
     h64 = torch.zeros(M, H, dtype=torch.float64)

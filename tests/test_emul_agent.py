@@ -32,3 +32,10 @@ def test_unroll_vs_oracle_small_tiles(tile):
 
 def test_device_rng_selection():
     AC.check_device_rng_selection("cpu", emul_lib())
+
+
+@pytest.mark.parametrize("H,AH,A,O,B,T", [(256, 128, 5, 24, 20, 4), (64, 64, 7, 39, 15, 3), (128, 128, 33, 176, 12, 2)])
+def test_gemm_unroll_vs_oracle(H, AH, A, O, B, T):
+    """macjd_agent_unroll (the time-unrolled pass as batched layers; here on the FP32 GEMM of the host build): the
+    path widths like rnn_hidden_dim = 256 take on the GPU (path 0 without the CTA-pair kernel)."""
+    AC.check_unroll_against_oracle("cpu", emul_lib(), O=O, A=A, H=H, AH=AH, Nn=2, B=B, T=T, path=0)

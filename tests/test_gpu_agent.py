@@ -280,3 +280,13 @@ def test_pair_kernel_many_actions(O, A, M, T):
                           want_params=True, want_greedy=True, want_hidden_seq=True, sel_actions=sel, path=3, split_unroll=False)
     for k in ("q_all", "params_all", "actions", "hidden_seq", "power"):
         assert torch.equal(again[k], res["pair"][k]), k
+
+
+@pytest.mark.parametrize("H,AH,A,O,B,T", [(256, 128, 5, 24, 700, 5), (256, 128, 5, 24, 19, 3), (192, 64, 9, 40, 130, 2)])
+def test_gemm_unroll_vs_oracle(H, AH, A, O, B, T):
+    """Widths the CTA-pair kernel does not take (BASELINE config 4: rnn_hidden_dim 256): macjd_agent_unroll -- the
+    unrolled pass as batched layers on the tcgen05 3xTF32 GEMM -- against the eager oracle / float64 truth."""
+    from macjd_b200 import _native as N
+    mac, _ = AC.random_agent(3, O, A, H, AH, 2, "cuda")
+    assert N.get_lib().lib.macjd_agent_pair_supported(N.C.byref(mac.agent.packed().cstruct())) == 0
+    AC.check_unroll_against_oracle("cuda", None, O=O, A=A, H=H, AH=AH, Nn=2, B=B, T=T, path=0)
