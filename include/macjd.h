@@ -492,6 +492,17 @@ MACJD_API int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* ten
  * macjd_clear_pipeline_fault() is called. */
 MACJD_API int macjd_clear_pipeline_fault(void);
 
+/* The dense-layer primitive every learner entry point above is built from (nn.Linear of core/networks.py:54-79,
+ * 215-248 and its two backward products):  C[m][n] (ldc) = act(sum_k A(m,k) B(k,n) + bias[n]) (+ C if accumulate),
+ *   A(m,k) = ta ? A[k lda + m] : A[m lda + k],   B(k,n) = tb ? B[n ldb + k] : B[k ldb + n]  (tb = 1: a PyTorch weight)
+ *   act: 0 none, 1 ReLU, 3 sigmoid.  splitk_ws (optional, >= splits x M x N floats): lets a product with few output
+ * tiles and a long contraction (weight gradients: K = batch rows) be split over K, reduced in a fixed order.
+ * Runs on the tcgen05 tensor cores (3xTF32 operand split, FP32-level accuracy; csrc/tc_gemm.cuh) when the problem
+ * fills its 128 x 128 tiles, else on the FP32 SIMT kernel (csrc/sgemm.cuh). */
+MACJD_API int macjd_gemm(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t ta,
+                         const float* B, int32_t ldb, int32_t tb, float* C, int32_t ldc, const float* bias, int32_t act,
+                         int32_t accumulate, float* splitk_ws, size_t splitk_ws_floats);
+
 /* ===================================================================== tensor-core self-test
  * D[M][N] = A[M][K] B[N][K]^T on the tcgen05 TF32 pipe with the 3xTF32 operand split
  * (csrc/tc05.cuh).  M in {64, 128}, N multiple of 16 <= 256, K multiple of 8.  Exercises the

@@ -156,6 +156,7 @@ class NativeLib:
         for name, restype, argtypes in (
             ("macjd_replay_copy", C.c_int, [P(Ctx), P(CopyDesc), i32, vp, i32, i32]),
             ("macjd_env_derived_bytes", sz, [P(EnvTables)]),
+            ("macjd_gemm", C.c_int, [P(Ctx), i32, i32, i32, vp, i32, i32, vp, i32, i32, vp, i32, vp, i32, i32, vp, sz]),
             ("macjd_agent_unroll_workspace_floats", sz, [P(AgentWeights), i32, i32]),
             ("macjd_agent_unroll", C.c_int, [P(Ctx), P(AgentWeights), P(AgentIO), vp, sz]),
             ("macjd_env_prepare", C.c_int, [P(Ctx), P(EnvTables), vp]),

@@ -669,6 +669,17 @@ int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, cons
                                       eps, step, scal, scratch, scratch_floats));
 }
 
+int macjd_gemm(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t ta, const float* B,
+               int32_t ldb, int32_t tb, float* C, int32_t ldc, const float* bias, int32_t act, int32_t accumulate, float* splitk_ws,
+               size_t splitk_ws_floats) {
+  MACJD_ENTER(ctx);
+  if (M < 0 || N < 0 || K < 1 || !A || !B || !C || act < 0 || act > 3 || act == 2) return MACJD_ERR_INVALID_ARG;
+  macjd::GemmOpts o;
+  o.bias = bias; o.act = act; o.accumulate = accumulate; o.splitk_ws = splitk_ws; o.splitk_ws_floats = splitk_ws_floats;
+  macjd::gemm((cudaStream_t)ctx->stream, A, lda, ta != 0, B, ldb, tb != 0, C, ldc, M, N, K, o);
+  return finish(ctx, MACJD_OK);
+}
+
 int macjd_tc_gemm_selftest(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
                            float* D) {
   MACJD_ENTER(ctx);

@@ -26,6 +26,7 @@ namespace tc {
 constexpr int kGtM = 128, kGtN = 128, kGtK = 16, kGtStages = 3;     // 96 KB of stages: two CTAs per SM
 constexpr int kGtLoadThreads = 256, kGtThreads = kGtLoadThreads + 32;
 constexpr int kGtTileFloats = kGtM * kGtK;                       // one hi (or lo) operand tile of a stage
+constexpr int kGtTileLd = kGtN + 4;                              // epilogue staging tile: padded rows (bank spread, 16-byte aligned)
 
 struct GtSmem {
   float a[kGtStages][2][kGtTileFloats];                          // [stage][hi / lo]
@@ -161,37 +162,59 @@ __global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g
     }
     mbar_wait(&S.done, 0);
     fence_after_sync();
-    const int q4 = warp & 3, half = warp >> 2;
-    const int m = m0 + q4 * 32 + lane;
-    const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 64);
-#pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 16) {
-      float v[16];
-      tmem_ld16_nowait(tl + (uint32_t)c0, v);
-      tmem_ld_wait();
-      reg_fence(v);
-      if (m < g.M) {
-        const int nb = n0 + half * 64 + c0;
-        if (gridDim.z > 1) {
-          float* dst = g.partial + ((size_t)blockIdx.z * g.M + m) * g.N + nb;
+    // ---- epilogue.  The accumulator is read thread = row (a TMEM lane); written that way every store instruction
+    // of a warp would touch 32 different rows, 4 bytes each.  So the tile goes through shared memory (the operand
+    // stages are free now: every MMA has completed) and leaves in row order: a warp writes 512 contiguous bytes.
+    float* tile = reinterpret_cast<float*>(gt_raw);                     // [128][kGtTileLd]
+    {
+      const int q4 = warp & 3, half = warp >> 2;
+      const int r = q4 * 32 + lane;
+      const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(half * 64);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < g.N) dst[j] = v[j];
-        } else {
-          float* c = g.C + (size_t)m * g.ldc + nb;
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        float v[16];
+        tmem_ld16_nowait(tl + (uint32_t)c0, v);
+        tmem_ld_wait();
+        reg_fence(v);
+        float4* dst = reinterpret_cast<float4*>(tile + (size_t)r * kGtTileLd + half * 64 + c0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (nb + j >= g.N) continue;
-            float x = v[j];
-            if (g.bias) x += __ldg(g.bias + nb + j);
-            if (g.act == kActRelu) x = fmaxf(x, 0.f);
-            else if (g.act == kActClamp) x = fminf(fmaxf(x, g.lo), g.hi);
-            else if (g.act == kActSigmoid) x = 1.0f / (1.0f + expf(-x));
-            if (g.mask) x = g.mask[(size_t)m * g.ldmask + nb + j] > 0.f ? x : 0.f;
-            c[j] = g.accumulate ? c[j] + x : x;
-          }
+        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+    fence_before_sync();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(kGtLoadThreads) : "memory");
+    const bool part = gridDim.z > 1;
+    float* out = part ? g.partial + (size_t)blockIdx.z * g.M * g.N : g.C;
+    const int ldo = part ? g.N : g.ldc;
+    const bool o_vec = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (ldo & 3) == 0 &&
+                       (!g.mask || (((reinterpret_cast<uintptr_t>(g.mask) & 15) == 0) && (g.ldmask & 3) == 0)) &&
+                       (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+#pragma unroll 2
+    for (int idx = tid; idx < kGtM * (kGtN / 4); idx += kGtLoadThreads) {
+      const int r = idx >> 5, c = (idx & 31) << 2;
+      const int m = m0 + r, n = n0 + c;
+      if (m >= g.M || n >= g.N) continue;
+      const float4 t4 = *reinterpret_cast<const float4*>(tile + (size_t)r * kGtTileLd + c);
+      float x[4] = {t4.x, t4.y, t4.z, t4.w};
+      float* dst = out + (size_t)m * ldo + n;
+      const bool full4 = o_vec && n + 3 < g.N;
+      if (!part) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n + j >= g.N) break;
+          if (g.bias) x[j] += __ldg(g.bias + n + j);
+          if (g.act == kActRelu) x[j] = fmaxf(x[j], 0.f);
+          else if (g.act == kActClamp) x[j] = fminf(fmaxf(x[j], g.lo), g.hi);
+          else if (g.act == kActSigmoid) x[j] = 1.0f / (1.0f + expf(-x[j]));
+          if (g.mask) x[j] = g.mask[(size_t)m * g.ldmask + n + j] > 0.f ? x[j] : 0.f;
+          if (g.accumulate) x[j] += dst[j];
         }
       }
+      if (full4) *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+      else
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < g.N) dst[j] = x[j];
     }
   } else {
     // ================================================================== MMA issue (warp-uniform, one elected lane)
@@ -224,7 +247,10 @@ __global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g
   if (warp == kGtLoadThreads / 32) tmem_dealloc(tmem, kGtN);
 }
 
-inline size_t tc_gemm_smem_bytes() { return sizeof(GtSmem) + 1024; }
+inline size_t tc_gemm_smem_bytes() {
+  static_assert(sizeof(float) * kGtM * kGtTileLd <= sizeof(float) * 4 * kGtStages * kGtTileFloats, "the epilogue tile borrows the operand stages");
+  return sizeof(GtSmem) + 1024;
+}
 
 // K splits for the tensor-core kernel: enough CTAs to fill the chip, slices of at least 256 rows
 inline int tc_gemm_splits(int M, int N, int K, size_t ws_floats) {

@@ -289,4 +289,6 @@ def test_gemm_unroll_vs_oracle(H, AH, A, O, B, T):
     from macjd_b200 import _native as N
     mac, _ = AC.random_agent(3, O, A, H, AH, 2, "cuda")
     assert N.get_lib().lib.macjd_agent_pair_supported(N.C.byref(mac.agent.packed().cstruct())) == 0
-    AC.check_unroll_against_oracle("cuda", None, O=O, A=A, H=H, AH=AH, Nn=2, B=B, T=T, path=0)
+    # the tensor-core path's stated bound: within 1e-4 of the float64 truth (3xTF32: ~2^-21 per product), or within
+    # 16x the eager-FP32 oracle's own rounding error where the pre-activations are large
+    AC.check_unroll_against_oracle("cuda", None, O=O, A=A, H=H, AH=AH, Nn=2, B=B, T=T, path=0, k=16.0, rtol=1e-4)
