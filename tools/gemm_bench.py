@@ -9,7 +9,10 @@ ctx = N.torch_ctx(torch.device("cuda", 0))
 shapes = [("mixer layer  ", 101376, 128, 128, 0, 1), ("qhead fwd    ", 202752, 256, 256, 0, 0), ("gx r|z       ", 204800, 512, 256, 0, 0),
           ("step gh      ", 2048, 512, 256, 0, 0), ("fc1 K=24     ", 204800, 256, 24, 0, 0), ("dW 256x256   ", 256, 256, 202752, 1, 0),
           ("dX           ", 101376, 128, 128, 0, 0)]
+only = sys.argv[1] if len(sys.argv) > 1 else None
 for name, M, Nn, K, ta, tb in shapes:
+    if only and only not in name:
+        continue
     A = torch.randn((K, M) if ta else (M, K), device="cuda")
     B = torch.randn((Nn, K) if tb else (K, Nn), device="cuda")
     C = torch.empty(M, Nn, device="cuda")
