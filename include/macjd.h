@@ -221,6 +221,9 @@ typedef struct macjd_agent_weights {
                              [H][A8] actor.4.weight^T, [H][A8] fc2_q_head.0.weight[:, H + a],
                              [A8] actor.4.bias (A8 = A rounded up to 8, zero padded);
                              NULL = FP32 SIMT kernel only                              */
+  const float* wiht;      /* optional [H][3H] rnn.weight_ih^T (gates r | z | n side by side) and ...           */
+  const float* whht;      /* ... [H][3H] rnn.weight_hh^T: let macjd_agent_unroll form a GRU side with ONE
+                             product instead of two (NULL: it uses wrzt / wint / whnt)                  */
 } macjd_agent_weights;
 
 typedef struct macjd_agent_io {

@@ -98,8 +98,12 @@ inline int agent_unroll_gemm(const macjd_ctx* ctx, const macjd_agent_weights& W,
   // ---- input side of the GRU for all rows
   relu.bias = W.bfc1;
   gemm(st, io.obs, O, false, W.wfc1t, H, false, u.xf, H, rows, H, O, relu);
-  gemm(st, u.xf, H, false, W.wrzt, 2 * H, false, u.gx, 3 * H, rows, 2 * H, H);
-  gemm(st, u.xf, H, false, W.wint, H, false, u.gx + 2 * H, 3 * H, rows, H, H);
+  if (W.wiht) {
+    gemm(st, u.xf, H, false, W.wiht, 3 * H, false, u.gx, 3 * H, rows, 3 * H, H);
+  } else {
+    gemm(st, u.xf, H, false, W.wrzt, 2 * H, false, u.gx, 3 * H, rows, 2 * H, H);
+    gemm(st, u.xf, H, false, W.wint, H, false, u.gx + 2 * H, 3 * H, rows, H, H);
+  }
   // ---- the recurrence
   const float* h_first = (io.hidden_zero_init || !(io.hidden_in || io.hidden)) ? nullptr : (io.hidden_in ? io.hidden_in : io.hidden);
   const int gblocks = (M * H + 255) / 256;
@@ -107,8 +111,12 @@ inline int agent_unroll_gemm(const macjd_ctx* ctx, const macjd_agent_weights& W,
     const float* h_prev = t == 0 ? h_first : hs + (size_t)(t - 1) * M * H;
     const float* gh = nullptr;
     if (h_prev) {
-      gemm(st, h_prev, H, false, W.wrzt + (size_t)H * 2 * H, 2 * H, false, u.gh, 3 * H, M, 2 * H, H);
-      gemm(st, h_prev, H, false, W.whnt, H, false, u.gh + 2 * H, 3 * H, M, H, H);
+      if (W.whht) {
+        gemm(st, h_prev, H, false, W.whht, 3 * H, false, u.gh, 3 * H, M, 3 * H, H);
+      } else {
+        gemm(st, h_prev, H, false, W.wrzt + (size_t)H * 2 * H, 2 * H, false, u.gh, 3 * H, M, 2 * H, H);
+        gemm(st, h_prev, H, false, W.whnt, H, false, u.gh + 2 * H, 3 * H, M, H, H);
+      }
       gh = u.gh;
     }
     MACJD_LAUNCH(gru_gates_kernel, dim3(gblocks), dim3(256), 0, st, (const float*)(u.gx + (size_t)t * M * 3 * H), gh, h_prev, W.brz,
