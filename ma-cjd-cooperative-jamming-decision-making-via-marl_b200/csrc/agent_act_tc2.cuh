@@ -43,6 +43,9 @@ constexpr int kT2ColSplit = 2;                             // epilogue warps per
 constexpr int kT2EpiWarps = 4 * kT2ColSplit;
 constexpr int kT2EpiThreads = 32 * kT2EpiWarps;
 constexpr int kT2Threads = kT2EpiThreads + 64;             // + weight-stream warp + MMA / relay warp
+constexpr int kT2EnvWarps = 4;                             // kFuseEnv launches: + the env-step warps (one group of lanes per env)
+constexpr int kT2EnvThreads = 32 * kT2EnvWarps;
+constexpr int kT2BarActions = 2, kT2BarEnvDone = 3;        // named barriers between the epilogue warps and the env warps
 constexpr int kT2Upt = 64 / kT2ColSplit;                   // output units per epilogue thread
 constexpr int kT2Parts = 2 * kT2ColSplit;                  // threads that share one row
 // Accumulator columns (2-SM layout: 64 columns per 128-unit accumulator).  All seven layer
@@ -189,13 +192,16 @@ struct T2Smem {
 // memory through L1 (warp-uniform 16-byte loads), the head / tail run in groups of 8 actions on register-resident
 // activations, and the Q staging buffer borrows the xf operand tile, which is dead by then.
 // kFuseEnv (acting launches only): the CTA also runs the environment step of its rows' envs -- a CTA's 64 rows are
-// 64 / J whole envs -- right behind the selection: the actions go from the selecting threads to the physics threads
-// through shared memory (no second launch, no dependency hand-over, no global round trip), one thread per env
-// evaluates the step on the derived scenario tables (env_step2.cuh: env2_physics, the code of the stand-alone
-// kernel), and the static views of the next timestep are copied by all epilogue threads while they would
-// otherwise wait for the Q-head product.
+// 64 / J whole envs.  The actions go from the selecting threads to the physics threads through shared memory (no
+// second launch, no dependency hand-over, no global round trip); kT2EnvWarps extra warps, a group of lanes per env,
+// evaluate the step on the derived scenario tables (env_step2.cuh: env2_physics_group, the code of the stand-alone
+// kernel).  Nothing the agent reads at timestep t + 1 comes out of the physics of timestep t -- the views are the
+// scenario's static rows (environment.py:479-551), copied by the epilogue threads while they would otherwise wait
+// for the Q-head product -- so in a launch that loops over the timesteps the physics of step t (a dependent FP64
+// chain of ~7 us) runs UNDER the agent's step t + 1 instead of between the two.
 template <bool kWholeStep, bool kBigA, bool kFuseEnv = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads + (kFuseEnv ? kT2EnvThreads : 0), 1)
+agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   T2Smem& S = *reinterpret_cast<T2Smem*>(tc_raw);
   const AgentArgs& a = p.a;
@@ -287,7 +293,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
   const float* const big_w1a = big_w3 + (size_t)H * A8;
   const float* const big_b3 = big_w1a + (size_t)H * A8;
   TC_STAMP_ONCE(26);
-  warm_weights_l2(W.tc_chunks, chunks_per_step, kT2Threads);
+  if (tid < kT2Threads) warm_weights_l2(W.tc_chunks, chunks_per_step, kT2Threads);
   TC_STAMP_ONCE(27);
 
   if (tid == 0) {
@@ -432,6 +438,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
 #endif
           s = (s + 1 == nstages) ? 0 : s + 1;
         }
+      }
+    }
+  } else if (kFuseEnv && warp >= kT2EpiWarps + 2) {
+    // =========================================================== env warps: the step of this CTA's envs, one timestep
+    // behind the agent (environment.py:221-477).  Group `slot` of G lanes owns env row0 / J + slot for the whole launch.
+    const Env2Args& E = p.env;
+    const int Je = E.tab.n_jammers, epc = kTcRows / Je, G = E.group;
+    const int passes = (epc * G + kT2EnvThreads - 1) / kT2EnvThreads;   // (whole warps: epc * G is a multiple of 32)
+    // pull the envs' derived blocks into L1 / L2 while the agent's first step runs (read-only for the whole launch)
+    if (E.tab.env_stride != 0) {
+      const double* blk = E.tab.derived + (int64_t)(row0 / Je) * E.rows.total;
+      double warm = 0.0;
+      for (int off = (tid - kT2Threads) * 4; off < (valid / Je) * E.rows.total; off += kT2EnvThreads * 4) warm += __ldg(blk + off);
+      asm volatile("" ::"d"(warm));
+    }
+    for (int t = 0; t < T; ++t) {
+      asm volatile("bar.sync %0, %1;\n" ::"n"(kT2BarActions), "n"(kT2EpiThreads + kT2EnvThreads) : "memory");   // step t's actions are staged
+      const macjd_env_io eio = env2_io_at(E, t);
+      if (tid == kT2Threads) TC_STAMP(40);
+      for (int ps = 0; ps < passes; ++ps) {
+        const int et = tid - kT2Threads + ps * kT2EnvThreads;
+        if (et - (et & 31) >= epc * G) break;         // warp-uniform
+        const int slot = et / G, g = et - slot * G;
+        const bool env_live = slot < valid / Je;
+        const int e = row0 / Je + (env_live ? slot : 0);
+        const double* d = E.tab.derived + (E.tab.env_stride == 0 ? (int64_t)0 : (int64_t)e * E.rows.total);
+        env2_physics_group(E, eio, e, env_live, g, G, d, S.act_s + slot * Je, S.pow_s + slot * Je);
+      }
+      if (tid == kT2Threads) TC_STAMP(41);
+      if (t + 1 < T) {                                // the staging buffers may take the next step's actions
+        __threadfence_block();
+        asm volatile("bar.arrive %0, %1;\n" ::"n"(kT2BarEnvDone), "n"(kT2EpiThreads + kT2EnvThreads) : "memory");
       }
     }
   } else {
@@ -729,17 +767,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       if (mode == 0 || mode == 2) {
       // ---- E5: Q tail, outputs, selection
       if (kFuseEnv) {
-        // while the Q-head product runs: this CTA's envs' derived scenario rows -> the xf tile's hi half (dead since
-        // the input products completed; the physics below reads them from shared memory), and the next timestep's
-        // state / obs / avail of those envs
+        // while the Q-head product runs: the next timestep's state / obs / avail of this CTA's envs
         const int Je = p.env.tab.n_jammers, ne = valid / Je;
-        if (p.env.tab.env_stride != 0) {                 // (a shared scenario is one block: read in place)
-          const double2* src = reinterpret_cast<const double2*>(p.env.tab.derived + (int64_t)(row0 / Je) * p.env.rows.total);
-          double2* dst = reinterpret_cast<double2*>(S.b0hi);
-          const int n2 = ne * p.env.rows.total / 2;
-#pragma unroll 4
-          for (int i = tid; i < n2; i += kT2EpiThreads) dst[i] = __ldg(src + i);
-        }
         env2_views(p.env, env2_io_at(p.env, t), row0 / Je, ne, tid, kT2EpiThreads);
       }
       if (mode == 0) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }   // heads only: q.0 finished with actor.2
@@ -824,6 +853,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
         epi_bar_sync();                 // every action's Q is staged before the selection reads them
       }
       fence_before_sync();
+      // (the env warps have read the previous step's actions: all but never a wait -- they had a whole agent step)
+      if (kFuseEnv && t > 0) asm volatile("bar.sync %0, %1;\n" ::"n"(kT2BarEnvDone), "n"(kT2EpiThreads + kT2EnvThreads) : "memory");
       if (part == 0 && live) {
         const size_t m = tM + row0 + r;
         float best = -INFINITY, bestm = -INFINITY;
@@ -878,19 +909,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) agent
       }
       }
       if (kFuseEnv) {
-        // ---- the environment step of this CTA's envs on the actions just chosen (environment.py:221-477)
-        epi_bar_sync();                 // actions staged
-        const Env2Args& E = p.env;
-        const int Je = E.tab.n_jammers, epc = kTcRows / Je, G = E.group;
-        // groups of G lanes, one env each: the first epc * G epilogue threads (whole warps: epc * G is a multiple of 32)
-        if (tid < epc * G) {
-          const int slot = tid / G, g = tid - slot * G;
-          const bool env_live = slot < valid / Je;
-          const int e = row0 / Je + (env_live ? slot : 0);
-          const double* d = E.tab.env_stride == 0 ? E.tab.derived
-                                                  : reinterpret_cast<const double*>(S.b0hi) + (size_t)(env_live ? slot : 0) * E.rows.total;
-          env2_physics_group(E, env2_io_at(E, t), e, env_live, g, G, d, S.act_s + slot * Je, S.pow_s + slot * Je);
-        }
+        // ---- the actions just chosen go to the env warps, which run the step of this CTA's envs from here on
+        EP_STAMP(11);
+        __threadfence_block();
+        asm volatile("bar.arrive %0, %1;\n" ::"n"(kT2BarActions), "n"(kT2EpiThreads + kT2EnvThreads) : "memory");
       }
       epi_bar_sync();                   // Ps / Qs / red are free for the next step
       EP_STAMP(10);
@@ -914,14 +936,12 @@ inline bool agent_tc2_supported(const macjd_agent_weights& w) {
   return agent_tc_supported(w) && w.tc_format == 1 && kTcKc == 32 && kTcChunksPerX == 1 && agent_tc2_smem_bytes(w) <= 227 * 1024;
 }
 
-// The fused rollout step needs whole envs per CTA (64 % J == 0), derived scenario tables and room for the physics
-// scratch in the 8 KB reduction buffer.
+// The fused rollout step needs whole envs per CTA (64 % J == 0), derived scenario tables and whole warps of lane groups
+// (one group of G lanes per env; the env warps take them in passes of kT2EnvThreads lanes).
 inline bool agent_tc2_fuse_supported(const macjd_agent_weights& w, const macjd_env_tables& t) {
   if (!agent_tc2_supported(w) || t.derived == nullptr || t.n_jammers < 1 || kTcRows % t.n_jammers != 0 || !env2_supported(t)) return false;
   const int epc = kTcRows / t.n_jammers, G = env2_group(t.n_jammers, t.n_radars);
-  // one group of G lanes per env among the epilogue threads; the envs' derived blocks are staged in the xf tile's hi half
-  return epc * G <= kT2EpiThreads && (epc * G) % 32 == 0 &&
-         (size_t)derived_rows(t.n_jammers, t.n_radars, t.n_targets).total * epc * sizeof(double) <= sizeof(float) * kTcRows * kTcH;
+  return epc * G <= 2 * kT2EnvThreads && (epc * G) % 32 == 0;
 }
 
 // ... and it pays off while the env work a CTA takes on is small next to its agent step: the views a CTA copies per
@@ -980,8 +1000,8 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a, const Env2
   const cudaStream_t st = (cudaStream_t)ctx->stream;
   if (env) {
     if (a.io.part != 0 || a.io.n_steps < 1) return MACJD_ERR_INVALID_ARG;
-    if (big) agent_forward_tc2_kernel<true, true, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
-    else agent_forward_tc2_kernel<true, false, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
+    if (big) agent_forward_tc2_kernel<true, true, true><<<2 * pairs, kT2Threads + kT2EnvThreads, smem, st>>>(p);
+    else agent_forward_tc2_kernel<true, false, true><<<2 * pairs, kT2Threads + kT2EnvThreads, smem, st>>>(p);
   } else if (a.io.part == 0) {
     if (big) agent_forward_tc2_kernel<true, true><<<2 * pairs, kT2Threads, smem, st>>>(p);
     else agent_forward_tc2_kernel<true, false><<<2 * pairs, kT2Threads, smem, st>>>(p);
