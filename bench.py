@@ -565,7 +565,7 @@ def main():
                                            "macjd_env_step_host): the reference's two calls, two stream drains per step"}}
         return res
 
-    def agent_roofline(mac, M, dt_agent, dt_simt, O, A, H, dt_persistent=None):
+    def agent_roofline(mac, M, dt_agent, dt_simt, O, A, H, dt_persistent=None, traffic_key="agent_forward_tc2_kernel"):
         """dt_agent: one single-step launch of the agent kernel alone.  dt_persistent: per-timestep time of the multi-step
         launches the timed region consists of (the same kernel looping over an episode, env steps inline): when given,
         `achieved` / `frac` describe THAT launch (algorithmic FLOPs of its timesteps / its duration; the env work adds
@@ -579,7 +579,7 @@ def main():
         name = agent_kernel_name(mac)
         tc = name.startswith("agent_forward_tc2")
         peak = tf32_peak if tc else fp32_peak
-        tr = traffic.get("agent_forward_tc2_kernel") or {}
+        tr = traffic.get(traffic_key) or {}
         r = {"kernel": name, "bound": "tensor" if tc else "fp32", "achieved": M * fpr / dt_agent / 1e12, "peak": peak,
              "unit": "TFLOP/s", "frac": M * fpr / dt_agent / 1e12 / peak, "traffic": tr.get("dram_bytes_per_launch") if tc else None,
              "flop_per_agent_step": fpr, "flop_convention": "minimal work (Q-head hidden product shared by the actions)",
@@ -656,8 +656,13 @@ def main():
         N_, O_, A_, H_, S_, E_, HH_ = dims
         ftr, ftr_coded = flop_per_transition(N_, O_, A_, H_, 128, S_, E_, HH_), flop_per_transition(N_, O_, A_, H_, 128, S_, E_, HH_, False)
         tflops = B * (T - 1) * ftr / dt_l / 1e12
-        tc = learner.mac.agent._pair_kernel_ok(learner.mac.agent.packed()) and learner.mac.agent.path in (0, 3)
+        ag = learner.mac.agent
+        pair = ag._pair_kernel_ok(ag.packed()) and ag.path in (0, 3)
+        tc = ag.path in (0, 3)                   # pair kernel, or batched layers on the tcgen05 GEMM (macjd_agent_unroll)
         peak = tf32_peak if tc else fp32_peak
+        unroll_kernel = ("agent_forward_tc2_kernel (parts 3 + 4 + 2)" if pair else
+                         "macjd_agent_unroll: batched layers on tc_gemm_kernel (tcgen05 3xTF32) + gru_gates_kernel per timestep" if tc else
+                         "agent_forward_kernel (FP32 SIMT)")
         return {"train_episodes_per_sec": world * B / dt_l, "train_transitions_per_sec": world * B * (T - 1) / dt_l,
                 "ms_per_train_step": dt_l * 1e3, "batch_episodes_per_gpu": B, "episode_len": T, "last_loss": last_loss,
                 "includes": "replay sample (gather kernel) + 2 unrolls + mixers + TD + backward + clip/Adam"
@@ -666,7 +671,8 @@ def main():
                              "frac": tflops / peak, "flop_per_transition": ftr, "flop_convention": "minimal work",
                              "flop_per_transition_as_coded": ftr_coded, "achieved_as_coded": B * (T - 1) * ftr_coded / dt_l / 1e12,
                              "peak_source": tf32_src if tc else fp32_src,
-                             "agent_unroll_kernel": "agent_forward_tc2_kernel (parts 3 + 4 + 2)" if tc else "agent_forward_kernel (FP32 SIMT)",
+                             "agent_unroll_kernel": unroll_kernel,
+                             "executed_tensor_tflops": 3 * tflops if tc else None,
                              "note": label}}
 
     line["learner"] = learner_bench(
@@ -707,7 +713,8 @@ def main():
                "launches_per_step": 1 if r3["fused"] else 2,
                "env_only": {"value": world * M3 / r3["dt_env"], "us_per_launch": r3["dt_env"] * 1e6},
                "act_only": {"value": world * M3 / r3["dt_agent"], "us_per_launch": r3["dt_agent"] * 1e6},
-               "roofline": agent_roofline(mac3, M3, r3["dt_agent"], r3["dt_simt"], S3, A3, HID, r3.get("dt_persistent_per_step")),
+               "roofline": agent_roofline(mac3, M3, r3["dt_agent"], r3["dt_simt"], S3, A3, HID, r3.get("dt_persistent_per_step"),
+                                          traffic_key="agent_forward_tc2_kernel_c3"),
                "roofline_env": env_roofline(n3, r3["dt_env"], C3["env_bytes"], "dram_bytes_per_launch_c3"),
                "parity": r3.get("parity"), "cpu_baseline": None}
         if want_cpu:

@@ -1,5 +1,5 @@
 """Driver for ncu captures (round 2): runs ONE configuration a few times so that `ncu -k regex:... -s ... -c ...`
-can pick the launches.    python tools/prof_cases.py {learner_c1|learner_c4|agent_c3|agent_c2|env_c3|env_c3_64k|env_c2_1m}"""
+can pick the launches.    python tools/prof_cases.py {learner_c1|learner_c4|agent_c3|agent_c2|env_c3|env_c3_64k|env_c2_1m|rollout_c2}"""
 import os
 import sys
 import types
@@ -60,5 +60,20 @@ elif which.startswith("env"):
     act_p = torch.rand(n, J, device=dev)
     for _ in range(3):
         env.step_device(act_d, act_p)
+elif which == "rollout_c2":
+    # the bench's timed launch: macjd_rollout_steps over one episode (100 timesteps, env steps inline), 4 096 envs
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import default_spec
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
+    rl = B.rl_args(dev, B.N_ENVS)
+    torch.manual_seed(42)
+    env = ElectromagneticEnvironment(rl, spec=default_spec(B.N_ENVS), device=dev, seed=1000)
+    mac = BasicMAC(B.OBS, rl)
+    mac.cuda()
+    runner = BatchedEpisodeRunner(env, mac, None, rl)
+    for _ in range(3):
+        runner.reset()
+        runner.rollout(0, 100)
 torch.cuda.synchronize()
 print("done", which)
