@@ -661,7 +661,7 @@ def main():
         tc = ag.path in (0, 3)                   # pair kernel, or batched layers on the tcgen05 GEMM (macjd_agent_unroll)
         peak = tf32_peak if tc else fp32_peak
         unroll_kernel = ("agent_forward_tc2_kernel (parts 3 + 4 + 2)" if pair else
-                         "macjd_agent_unroll: batched layers on tc_gemm_kernel (tcgen05 3xTF32) + gru_gates_kernel per timestep" if tc else
+                         "macjd_agent_unroll: batched layers on tc_gemm_kernel (tcgen05 3xTF32) + the recurrence as one gru_recurrence_tc2_kernel launch (CTA pairs, h in shared memory)" if tc else
                          "agent_forward_kernel (FP32 SIMT)")
         return {"train_episodes_per_sec": world * B / dt_l, "train_transitions_per_sec": world * B * (T - 1) / dt_l,
                 "ms_per_train_step": dt_l * 1e3, "batch_episodes_per_gpu": B, "episode_len": T, "last_loss": last_loss,

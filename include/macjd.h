@@ -224,6 +224,11 @@ typedef struct macjd_agent_weights {
   const float* wiht;      /* optional [H][3H] rnn.weight_ih^T (gates r | z | n side by side) and ...           */
   const float* whht;      /* ... [H][3H] rnn.weight_hh^T: let macjd_agent_unroll form a GRU side with ONE
                              product instead of two (NULL: it uses wrzt / wint / whnt)                  */
+  const float* rec_chunks;/* optional, H = 128 or 256: rnn.weight_hh packed for the tcgen05 recurrence launch of
+                             macjd_agent_unroll (csrc/gru_rec_tc2.cuh): for every 128-unit block b of the hidden
+                             state, for every gate g (r, z, n), the H / 32 chunks of rows [g H + 128 b, + 128) x
+                             32 k in the tc_chunks chunk format (UMMA K-major, TF32 hi part then lo part, 32 KB
+                             per chunk); NULL: the recurrence runs as one GEMM + one gate launch per timestep  */
 } macjd_agent_weights;
 
 typedef struct macjd_agent_io {

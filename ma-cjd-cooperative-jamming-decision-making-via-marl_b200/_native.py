@@ -44,7 +44,8 @@ class AgentWeights(C.Structure):
     _fields_ = [("obs_dim", c_int32), ("obs_pad", c_int32), ("hidden", c_int32), ("actor_hidden", c_int32),
                 ("n_actions", c_int32), ("tc_format", c_int32)] + [
         (n, c_void_p) for n in ("wa1t", "ba1", "wa2t", "ba2", "wa3t", "ba3", "wfc1t", "bfc1", "wrzt", "brz",
-                                "wint", "bin", "whnt", "bhn", "wqt", "bq1", "w1a", "w1p", "w2", "bq2", "tc_chunks", "wiht", "whht")]
+                                "wint", "bin", "whnt", "bhn", "wqt", "bq1", "w1a", "w1p", "w2", "bq2", "tc_chunks", "wiht", "whht",
+                                "rec_chunks")]
 
 
 class AgentIO(C.Structure):

@@ -52,6 +52,10 @@ class PackedAgentWeights:
         self.tc_ok = (self.H == 128 and self.AH == 128)
         self.tc_buffer = None
         self.tc_flat = None
+        # rnn.weight_hh packed for the one-launch recurrence of macjd_agent_unroll (csrc/gru_rec_tc2.cuh): the widths
+        # the fused CTA-pair kernel does not take (rnn_hidden_dim = 256, BASELINE config 4)
+        self.rec_ok = self.H in (128, 256) and not self.tc_ok
+        self.rec_buffer = None
         self._cstruct = None
         self._cstruct_for = None
 
@@ -59,8 +63,8 @@ class PackedAgentWeights:
         # target networks deep-copy the agent: the copy re-packs from its own parameters
         new = PackedAgentWeights.__new__(PackedAgentWeights)
         new.__dict__.update({k: v for k, v in self.__dict__.items()
-                             if k not in ("buffer", "tc_buffer", "tc_flat", "versions", "_cstruct", "_cstruct_for", "_slots")})
-        new.buffer = new.tc_buffer = new.tc_flat = new.versions = new._cstruct = new._cstruct_for = None
+                             if k not in ("buffer", "tc_buffer", "tc_flat", "rec_buffer", "versions", "_cstruct", "_cstruct_for", "_slots")})
+        new.buffer = new.tc_buffer = new.tc_flat = new.rec_buffer = new.versions = new._cstruct = new._cstruct_for = None
         return new
 
     def view(self, f):
@@ -131,8 +135,23 @@ class PackedAgentWeights:
             kc = int(agent.lib().lib.macjd_agent_tc_chunk_k())
             if kc > 0:
                 self._pack_tc(sd, kc)
+        if self.rec_ok and dev.type == "cuda":
+            self._pack_rec(sd["rnn.weight_hh"])
         self.versions = versions
         return self
+
+    def _pack_rec(self, whh, kc=32):
+        """include/macjd.h: macjd_agent_weights.rec_chunks -- per 128-unit block of the hidden state, per gate (r, z, n),
+        the H / 32 chunks of weight_hh rows [g H + 128 b, + 128), each as its TF32 hi part then its lo part."""
+        H = self.H
+        blocks = [self._umma_chunks(whh[g * H + 128 * b:g * H + 128 * (b + 1)].contiguous(), kc)
+                  for b in range(H // 128) for g in range(3)]
+        full = torch.cat(blocks, dim=0).contiguous()                  # [3 (H / 128) (H / kc), 128 * kc]
+        hi = (full.view(torch.int32) & -8192).view(torch.float32)
+        new = torch.stack([hi, full - hi], dim=1)
+        if self.rec_buffer is None or self.rec_buffer.shape != new.shape or self.rec_buffer.device != new.device:
+            self.rec_buffer = torch.empty_like(new)                   # same address on later re-packs
+        self.rec_buffer.copy_(new)
 
     @torch.no_grad()
     def refresh_qhead(self, agent):
@@ -235,18 +254,20 @@ class PackedAgentWeights:
         b3[:A].copy_(self.view("ba3"))
 
     def cstruct(self):
-        if self._cstruct is not None and self._cstruct_for == (self.buffer.data_ptr(), id(self.tc_buffer)):
+        key = (self.buffer.data_ptr(), id(self.tc_buffer), id(self.rec_buffer))
+        if self._cstruct is not None and self._cstruct_for == key:
             return self._cstruct
         self._cstruct = self._make_cstruct()
-        self._cstruct_for = (self.buffer.data_ptr(), id(self.tc_buffer))
+        self._cstruct_for = key
         return self._cstruct
 
     def _make_cstruct(self):
         base = self.buffer.data_ptr()
         kw = {f: base + 4 * self.offsets[f] for f in self.FIELDS}
         tc = self.tc_buffer.data_ptr() if self.tc_buffer is not None else None
+        rec = self.rec_buffer.data_ptr() if self.rec_buffer is not None else None
         return N.AgentWeights(obs_dim=self.O, obs_pad=self.Op, hidden=self.H, actor_hidden=self.AH,
-                              n_actions=self.A, tc_format=1 if tc else 0, tc_chunks=tc, **kw)
+                              n_actions=self.A, tc_format=1 if tc else 0, tc_chunks=tc, rec_chunks=rec, **kw)
 
 
 class RNNAgent(nn.Module):

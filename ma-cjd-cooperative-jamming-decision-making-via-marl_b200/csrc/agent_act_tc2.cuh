@@ -956,6 +956,29 @@ inline bool agent_tc2_fuse_profitable(const macjd_env_tables& t) {
   return per_env * (kTcRows / J) <= limit;
 }
 
+// TMA descriptor of a packed chunk buffer, seen as [bytes / 128][32 floats]: one box of 64 rows is one contiguous 8 KB
+// half-chunk (a pure host-side encode; the driver entry point is looked up once)
+inline bool encode_chunk_map(CUtensorMap* map, const float* chunks, size_t chunk_bytes) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return false;
+  const cuuint64_t gdim[2] = {32, chunk_bytes / 128};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {32, kT2HalfBytes / 128};
+  const cuuint32_t estride[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(chunks), gdim, gstride, box, estride,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a, const Env2Args* env = nullptr) {
   const size_t smem = agent_tc2_smem_bytes(a.w);
   // the opt-in is per device and sticky: ask once per device and size (an act call is latency-critical)
@@ -971,30 +994,11 @@ inline int agent_tc2_launch(const macjd_ctx* ctx, const AgentArgs& a, const Env2
     opted.record(ctx->device, smem);
   }
   if (watchdog_arm(ctx->device) != MACJD_OK) return MACJD_ERR_CUDA;
-  // TMA descriptor of the chunk buffer (a pure host-side encode; the driver entry point is looked up once)
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = [] {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      fn = nullptr;
-    return reinterpret_cast<EncodeFn>(fn);
-  }();
-  if (!encode) return MACJD_ERR_CUDA;
   T2Args p;
   p.a = a;
   if (env) p.env = *env;
   const size_t chunk_bytes = (size_t)(2 * kTcChunksPerX * (a.w.obs_pad / 32) + 8 * kTcChunksPerH) * kTcChunkBytes;
-  const cuuint64_t gdim[2] = {32, chunk_bytes / 128};
-  const cuuint64_t gstride[1] = {128};
-  const cuuint32_t box[2] = {32, kT2HalfBytes / 128};
-  const cuuint32_t estride[2] = {1, 1};
-  if (encode(&p.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.w.tc_chunks), gdim, gstride, box, estride,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return MACJD_ERR_CUDA;
+  if (!encode_chunk_map(&p.wmap, a.w.tc_chunks, chunk_bytes)) return MACJD_ERR_CUDA;
   const int pairs = (a.io.n_rows + 2 * kTcRows - 1) / (2 * kTcRows);
   const bool big = a.w.n_actions > 8;
   const cudaStream_t st = (cudaStream_t)ctx->stream;

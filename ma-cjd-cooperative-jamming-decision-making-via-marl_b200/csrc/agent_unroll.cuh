@@ -12,6 +12,7 @@
 #pragma once
 #include "agent_act.cuh"
 #include "tc_gemm.cuh"
+#include "gru_rec_tc2.cuh"
 
 namespace macjd {
 
@@ -67,6 +68,12 @@ __global__ void __launch_bounds__(256) qhead_all_kernel(const float* __restrict_
   }
 }
 
+// MACJD_REC_KERNEL=0 keeps the recurrence on the per-timestep GEMM + gate launches (comparison runs, tests)
+inline bool rec_kernel_wanted() {
+  const char* e = getenv("MACJD_REC_KERNEL");      // read per call (tens of ns): tests switch it
+  return !(e && e[0] == '0');
+}
+
 struct UnrollWs {
   float *xf, *gx, *gh, *a1, *a2, *qh, *P, *hs;
   size_t total;
@@ -107,7 +114,19 @@ inline int agent_unroll_gemm(const macjd_ctx* ctx, const macjd_agent_weights& W,
   // ---- the recurrence
   const float* h_first = (io.hidden_zero_init || !(io.hidden_in || io.hidden)) ? nullptr : (io.hidden_in ? io.hidden_in : io.hidden);
   const int gblocks = (M * H + 255) / 256;
-  for (int t = 0; t < T; ++t) {
+  bool rec_done = false;
+#ifndef MACJD_TEST_HOST_EMULATION
+  if (W.rec_chunks && tc::gru_rec_supported(H) && rec_kernel_wanted()) {
+    // the whole recurrence as one launch: CTA pairs keep their rows' h in shared memory and stream W_hh (gru_rec_tc2.cuh)
+    tc::RecArgs ra;
+    ra.gate_x = u.gx; ra.h0 = h_first; ra.hidden_seq = hs; ra.hidden_out = nullptr;
+    ra.brz = W.brz; ra.bin = W.bin; ra.bhn = W.bhn; ra.M = M; ra.T = T;
+    const int rc = tc::gru_rec_launch(ctx, H, ra, W.rec_chunks);
+    if (rc != MACJD_OK) return rc;
+    rec_done = true;
+  }
+#endif
+  for (int t = 0; t < T && !rec_done; ++t) {
     const float* h_prev = t == 0 ? h_first : hs + (size_t)(t - 1) * M * H;
     const float* gh = nullptr;
     if (h_prev) {

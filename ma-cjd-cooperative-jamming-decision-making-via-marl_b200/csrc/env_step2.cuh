@@ -24,6 +24,7 @@
 // behind the agent kernel).  The CTA-pair agent kernel calls the same device functions when it runs the env step
 // of its own rows' envs (agent_act_tc2.cuh, kFuseEnv).
 #pragma once
+#include <stdlib.h>
 #include "env_step.cuh"
 
 namespace macjd {
@@ -39,10 +40,11 @@ struct DerivedRows {
 __host__ __device__ inline DerivedRows derived_rows(int J, int R, int K) {
   DerivedRows d;
   int o = 0;
-  d.pd0 = o; o += R * K; d.sig = o; o += R * K; d.snr0 = o; o += R * K;
+  d.pd0 = o; o += R * K; d.sig = o; o += R * K;
   d.rad = o; o += 4 * R;
   d.den = o; o += J * R;
   d.jam = o; o += 4 * J;
+  d.snr0 = o; o += R * K;          // last: only the optional snr0 / snr1 outputs read it (a step without them never fetches it)
   d.total = (o + 1) & ~1;
   return d;
 }
@@ -390,6 +392,13 @@ __device__ __forceinline__ void env2_views(const Env2Args& a, const macjd_env_io
   }
 }
 
+// kUniform (large batches): every thread of the block is a physics lane AND a view thread -- 256 / G envs per block,
+// each warp first copies its share of the block's static views (independent loads and stores, fire and forget) and
+// then runs its envs' physics (a dependent FP64 chain).  With the split roles a block keeps 2-4 physics warps alive
+// for the length of that chain and the SM holds 128 envs in flight: at 1 M envs the kernel was bound by
+// latency x occupancy (ncu r2s: warps active 30 %, long_scoreboard + wait), not by HBM.  The split form stays for
+// small batches, where the step is one chain long and the views should not sit in front of it.
+template <bool kUniform>
 __global__ void __launch_bounds__(kEnv2Threads) env_step2_kernel(const Env2Args a) {
   const macjd_env_tables& T = a.tab;
   const macjd_env_io& io = a.io;
@@ -398,6 +407,23 @@ __global__ void __launch_bounds__(kEnv2Threads) env_step2_kernel(const Env2Args 
   const int G = a.group, eb = a.envs_per_block;
   const int e0 = a.env_begin + blockIdx.x * eb;
   const int valid = min(eb, a.env_end - e0);
+  const int pf_end = (io.snr0 || io.snr1) ? a.rows.total : a.rows.snr0;   // what a step reads of an env's block
+  if (kUniform) {
+    const int slot = tid / G, g = tid - slot * G;                          // (eb * G == kEnv2Threads)
+    const bool live = slot < valid;
+    const int e = e0 + (live ? slot : 0);
+    const double* d = T.derived + (T.env_stride == 0 ? 0 : (int64_t)e * a.rows.total);
+    if (a.physics && live)
+      for (int off = g * 16; off < pf_end; off += G * 16) prefetch_l2(d + off);
+    grid_dependency_wait();
+    env2_views(a, io, e0, valid, tid, kEnv2Threads);
+    if (!a.physics) {
+      if (live && g == 0) io.step_count[e] = 0;                            // environment.py:203
+      return;
+    }
+    env2_physics_group(a, io, e, live, g, G, d, io.act_d + (int64_t)e * J, io.act_p + (int64_t)e * J);
+    return;
+  }
   if (tid < kEnv2Phys) {
     // =========================================================================== physics: G lanes per env
     if (tid >= eb * G) return;                                         // (whole warps: eb * G is a multiple of 32)
@@ -407,7 +433,7 @@ __global__ void __launch_bounds__(kEnv2Threads) env_step2_kernel(const Env2Args 
     const double* d = T.derived + (T.env_stride == 0 ? 0 : (int64_t)e * a.rows.total);
     // pull this env's block towards the SM before waiting for the actions (the table is read-only)
     if (a.physics && live)
-      for (int off = g * 16; off < a.rows.total; off += G * 16) prefetch_l2(d + off);
+      for (int off = g * 16; off < pf_end; off += G * 16) prefetch_l2(d + off);
     // from here on the kernel reads the actions and writes outputs: wait for the preceding kernel of the stream
     grid_dependency_wait();
     if (!a.physics) {
@@ -440,20 +466,31 @@ inline Env2Args env2_args(const macjd_env_tables* tab, const macjd_env_io* io, i
   a.env_end = io->env_begin + n_step;
   {
     const uint64_t s4 = (uint64_t)a.state_dim / 4, js4 = (uint64_t)tab->n_jammers * s4;
-    const bool ok = (a.state_dim % 4 == 0) && s4 >= 2 && 64ull * js4 * js4 < 0x100000000ull;   // (<= 64 envs per copying block)
+    const bool ok = (a.state_dim % 4 == 0) && s4 >= 2 && 128ull * js4 * js4 < 0x100000000ull;   // (<= 128 envs per copying block)
     a.magic_s4 = ok ? (uint32_t)((0x100000000ull + s4 - 1) / s4) : 0;
     a.magic_js4 = ok ? (uint32_t)((0x100000000ull + js4 - 1) / js4) : 0;
   }
   return a;
 }
 
+// batch size from which the stand-alone kernel runs in its uniform form (MACJD_ENV_UNIFORM_MIN overrides: tests, experiments)
+inline int env2_uniform_min() {
+  const char* e = getenv("MACJD_ENV_UNIFORM_MIN");          // read per call (tens of ns): tests switch it
+  return e ? atoi(e) : 16384;
+}
+
 inline int env2_launch(const macjd_ctx* ctx, const macjd_env_tables* tab, const macjd_env_io* io, int physics) {
   if (!env2_supported(*tab)) return MACJD_ERR_UNSUPPORTED;
   const int n_step = io->env_count > 0 ? io->env_count : tab->n_envs - io->env_begin;
   if (n_step == 0) return MACJD_OK;
-  const Env2Args a = env2_args(tab, io, physics);
+  Env2Args a = env2_args(tab, io, physics);
+  if (n_step >= env2_uniform_min()) {
+    a.envs_per_block = kEnv2Threads / a.group;
+    MACJD_LAUNCH(env_step2_kernel<true>, (n_step + a.envs_per_block - 1) / a.envs_per_block, kEnv2Threads, 0, (cudaStream_t)ctx->stream, a);
+    return MACJD_OK;
+  }
   const int grid = (n_step + a.envs_per_block - 1) / a.envs_per_block;
-  MACJD_LAUNCH(env_step2_kernel, grid, kEnv2Threads, 0, (cudaStream_t)ctx->stream, a);
+  MACJD_LAUNCH(env_step2_kernel<false>, grid, kEnv2Threads, 0, (cudaStream_t)ctx->stream, a);
   return MACJD_OK;
 }
 

@@ -88,6 +88,9 @@ def test_invalid_arguments_are_status_codes():
 
 
 @pytest.mark.parametrize("kind,n", [("active", 70), ("scaled_small", 45), ("odd_radars", 33)])
-def test_raw_and_derived_table_kernels_agree(kind, n):
+@pytest.mark.parametrize("uniform_min", [1, 1 << 30])
+def test_raw_and_derived_table_kernels_agree(kind, n, uniform_min, monkeypatch):
+    # both block forms of the derived-table kernel: split roles (small batches) and uniform roles (>= 16 384 envs)
+    monkeypatch.setenv("MACJD_ENV_UNIFORM_MIN", str(uniform_min))
     from tests.env_checks import check_raw_and_derived_kernels_agree
     check_raw_and_derived_kernels_agree(make_env, kind, n)

@@ -292,3 +292,43 @@ def test_gemm_unroll_vs_oracle(H, AH, A, O, B, T):
     # the tensor-core path's stated bound: within 1e-4 of the float64 truth (3xTF32: ~2^-21 per product), or within
     # 16x the eager-FP32 oracle's own rounding error where the pre-activations are large
     AC.check_unroll_against_oracle("cuda", None, O=O, A=A, H=H, AH=AH, Nn=2, B=B, T=T, path=0, k=16.0, rtol=1e-4)
+
+
+@pytest.mark.parametrize("H,AH,B,T", [(256, 128, 700, 7), (256, 128, 33, 4), (128, 64, 130, 5), (256, 128, 1024, 100)])
+def test_recurrence_launch_matches_per_step_launches(H, AH, B, T, monkeypatch):
+    """macjd_agent_unroll runs the GRU recurrence as ONE tcgen05 launch (csrc/gru_rec_tc2.cuh: rows of h stay in shared
+    memory, W_hh streamed per step) where rec_chunks is packed (H = 256, or 128 without the pair kernel).  Against the
+    same call with MACJD_REC_KERNEL=0 (one GEMM + one gate launch per timestep): both are 3xTF32 products of the same
+    operands, they differ by summation order and the fast sigmoid / tanh forms -- stated bound 2e-5 absolute on h in
+    [-1, 1] after T steps, Q within 1e-4 of scale, identical greedy actions where the margin exceeds 1e-4."""
+    from macjd_b200 import _native as N
+    O, A, Nn = 24, 5, 2
+    mac, _ = AC.random_agent(5, O, A, H, AH, Nn, "cuda")
+    pk = mac.agent.packed()
+    assert pk.rec_buffer is not None and pk.cstruct().rec_chunks
+    assert N.get_lib().lib.macjd_agent_pair_supported(N.C.byref(pk.cstruct())) == 0
+    M = B * Nn
+    g = torch.Generator(device="cuda").manual_seed(7)
+    obs = torch.randn(T, M, O, device="cuda", generator=g)
+    h0 = torch.randn(M, H, device="cuda", generator=g) * 0.4
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MACJD_REC_KERNEL", mode)
+        for init in ("zero", "given"):
+            kw = dict(zero_init=True) if init == "zero" else {}
+            h = None if init == "zero" else h0.clone()
+            outs[mode, init] = mac.agent.run(obs, h, n_steps=T, want_q=True, want_greedy=True, want_hidden_seq=True, path=0, **kw)
+    torch.cuda.synchronize()
+    for init in ("zero", "given"):
+        a, b = outs["1", init], outs["0", init]
+        dh = (a["hidden_seq"] - b["hidden_seq"]).abs().max().item()
+        scale = max(1.0, b["q_all"].abs().max().item())
+        dq = (a["q_all"] - b["q_all"]).abs().max().item() / scale
+        assert dh < 2e-5, (init, dh)
+        assert dq < 1e-4, (init, dq)
+        srt = torch.sort(b["q_all"], dim=-1).values
+        decidable = (srt[..., -1] - srt[..., -2]) > 1e-4 * scale
+        assert torch.equal(a["greedy"][decidable], b["greedy"][decidable])
+        assert decidable.float().mean() > 0.9
+        if init == "given" and "hidden" in a and a["hidden"] is not None:
+            assert (a["hidden"] - b["hidden"]).abs().max().item() < 2e-5

@@ -57,7 +57,10 @@ def test_full_size_properties():
 
 @pytest.mark.parametrize("kind,n", [("active", 5000), ("scaled", 1111), ("scaled_small", 777), ("odd_radars", 1000),
                                     ("one_radar", 333), ("hetero", 40000)])
-def test_raw_and_derived_table_kernels_agree(kind, n):
+@pytest.mark.parametrize("uniform_min", [1, 1 << 30])
+def test_raw_and_derived_table_kernels_agree(kind, n, uniform_min, monkeypatch):
     """The step kernel on derived scenario tables (csrc/env_step2.cuh) against the raw-table kernel (csrc/env_step.cuh)."""
+    # both block forms of the derived-table kernel: split roles (small batches) and uniform roles (>= 16 384 envs)
+    monkeypatch.setenv("MACJD_ENV_UNIFORM_MIN", str(uniform_min))
     from tests.env_checks import check_raw_and_derived_kernels_agree
     check_raw_and_derived_kernels_agree(make_env, kind, n)
