@@ -229,6 +229,8 @@ typedef struct macjd_agent_weights {
                              state, for every gate g (r, z, n), the H / 32 chunks of rows [g H + 128 b, + 128) x
                              32 k in the tc_chunks chunk format (UMMA K-major, TF32 hi part then lo part, 32 KB
                              per chunk); NULL: the recurrence runs as one GEMM + one gate launch per timestep  */
+  const float* bgx;       /* [3H] (brz | bin): the biases of the GRU's input side as one vector, added by the
+                             input-product GEMM when the recurrence launch is used (needed with rec_chunks)   */
 } macjd_agent_weights;
 
 typedef struct macjd_agent_io {

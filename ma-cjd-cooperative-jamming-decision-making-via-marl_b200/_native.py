@@ -45,7 +45,7 @@ class AgentWeights(C.Structure):
                 ("n_actions", c_int32), ("tc_format", c_int32)] + [
         (n, c_void_p) for n in ("wa1t", "ba1", "wa2t", "ba2", "wa3t", "ba3", "wfc1t", "bfc1", "wrzt", "brz",
                                 "wint", "bin", "whnt", "bhn", "wqt", "bq1", "w1a", "w1p", "w2", "bq2", "tc_chunks", "wiht", "whht",
-                                "rec_chunks")]
+                                "rec_chunks", "bgx")]
 
 
 class AgentIO(C.Structure):

@@ -28,7 +28,7 @@ class PackedAgentWeights:
     macjd_agent_weights).  One flat float32 buffer; every segment starts 16-byte aligned."""
 
     FIELDS = ("wa1t", "ba1", "wa2t", "ba2", "wa3t", "ba3", "wfc1t", "bfc1", "wrzt", "brz", "wint", "bin",
-              "whnt", "bhn", "wqt", "bq1", "w1a", "w1p", "w2", "bq2", "wiht", "whht")
+              "whnt", "bhn", "wqt", "bq1", "w1a", "w1p", "w2", "bq2", "wiht", "whht", "bgx")
 
     def __init__(self, agent: "RNNAgent"):
         self.O, self.H, self.AH, self.A = agent.input_shape, agent.rnn_hidden_dim, agent.actor_hidden_dim, agent.n_actions
@@ -40,7 +40,7 @@ class PackedAgentWeights:
         self.shapes = {"wa1t": (Op, AH), "ba1": (AH,), "wa2t": (AH, AH), "ba2": (AH,), "wa3t": (AH, A), "ba3": (A,),
                        "wfc1t": (Op, H), "bfc1": (H,), "wrzt": (2 * H, 2 * H), "brz": (2 * H,), "wint": (H, H),
                        "bin": (H,), "whnt": (H, H), "bhn": (H,), "wqt": (H, H), "bq1": (H,), "w1a": (A, H),
-                       "w1p": (H,), "w2": (H,), "bq2": (1,), "wiht": (H, 3 * H), "whht": (H, 3 * H)}
+                       "w1p": (H,), "w2": (H,), "bq2": (1,), "wiht": (H, 3 * H), "whht": (H, 3 * H), "bgx": (3 * H,)}
         self.offsets, off = {}, 0
         for f in self.FIELDS:
             self.offsets[f] = off
@@ -124,6 +124,8 @@ class PackedAgentWeights:
         self.view("wiht").copy_(wih.t())                             # [H][3H]: one product per GRU side (macjd_agent_unroll)
         self.view("whht").copy_(whh.t())
         self.view("bhn").copy_(sd["rnn.bias_hh"][2 * H:])
+        self.view("bgx")[:2 * H].copy_(self.view("brz"))             # input-side biases as one vector (macjd_agent_unroll)
+        self.view("bgx")[2 * H:].copy_(self.view("bin"))
         w1 = sd["fc2_q_head.0.weight"]                               # [H, H + A + 1]
         self.view("wqt").copy_(w1[:, :H].t())
         self.view("bq1").copy_(sd["fc2_q_head.0.bias"])

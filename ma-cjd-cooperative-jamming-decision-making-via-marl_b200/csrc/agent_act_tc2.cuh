@@ -51,9 +51,10 @@ constexpr int kT2Parts = 2 * kT2ColSplit;                  // threads that share
 // Accumulator columns (2-SM layout: 64 columns per 128-unit accumulator).  All seven layer
 // accumulators of a step are live at once -- the recurrent products are issued before the
 // actor's second layer and the actor head is evaluated while the input products run -- so none
-// of them share columns; only Q reuses actor.0's.
+// of them share columns, and Q has its own as well (448-511): in a launch that loops over the timesteps the issuer
+// starts the NEXT step's observation and recurrent products while the epilogue still reads this step's Q.
 constexpr uint32_t kT2ColA1 = 0, kT2ColFc1 = 64, kT2ColA2 = 128;
-constexpr uint32_t kT2ColR = 192, kT2ColZ = 256, kT2ColIn = 320, kT2ColHn = 384, kT2ColQ = 0;
+constexpr uint32_t kT2ColR = 192, kT2ColZ = 256, kT2ColIn = 320, kT2ColHn = 384, kT2ColQ = 448;
 constexpr uint32_t kT2TmemCols = 512;
 // Issue order of the eight K = 128 layers of a step, and where each sits in the packed weights
 // (order there: 0 actor.2, 1 W_ir, 2 W_hr, 3 W_iz, 4 W_hz, 5 W_in, 6 W_hn, 7 q.0[:, :H]):
@@ -179,6 +180,7 @@ struct T2Smem {
   float red[kT2Parts][8][kTcRows];          // partial row sums of the threads that share a row
   uint64_t w_full[kT2MaxStages], w_empty[kT2MaxStages];
   uint64_t x_full, x_empty, d_ready, a_ready;
+  uint64_t dx_ready;                        // acting launches: the observation products have completed (E1's wait)
   uint64_t c_full;                          // the constant block has landed
   uint32_t tmem_base;
   int32_t act_s[kTcRows];                   // kFuseEnv: the actions just chosen, handed to the env step in place
@@ -300,6 +302,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
     // "full" lives in the leader: armed by its stream thread for both CTAs' bytes of a stage
     for (int s = 0; s < kT2MaxStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
     mbar_init(&S.x_full, 2 * kT2EpiThreads); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 2 * kT2EpiThreads);
+    mbar_init(&S.dx_ready, 1);
     mbar_init(&S.c_full, 1);
     fence_mbar_init();
     // the per-layer vectors (TcConst, packed by the host behind the weight chunks): one 13.9 KB bulk copy
@@ -376,16 +379,16 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
           if (L < nx) {                        // [actor.0 | fc1] chunk pair of observation block L
             ahi = bh; alo = bl; sbo = 32 * 32; koff0 = koff1 = 0;
             d0 = kT2ColA1; d1 = kT2ColFc1; first0 = first1 = (L == 0);
-            pre = 1; post = 1u | (L == nx - 1 ? 2u : 0u);
+            pre = 1; post = 1u | (L == nx - 1 ? (kWholeStep ? 4u : 2u) : 0u);
           } else {                             // K = 128 layers: 4 chunks = 2 stages each
             //  slot j:  0 W_hr (h)  1 W_hz (h)  2 W_hn (h)  3 actor.2 (b0)  4 W_ir (b0)  5 W_iz (b0)  6 W_in (b0)  7 q.0 (h)
             const uint32_t j = (slot_seq >> (4 * ((uint32_t)(L - nx) >> 1))) & 0xFu, hf = (uint32_t)(L - nx) & 1u;
             const bool use_h = (0x87u >> j) & 1u;          // slots 0, 1, 2, 7 read h
             ahi = use_h ? hh : bh; alo = use_h ? hl : bl; sbo = H * 32;
             koff0 = (2 * hf) * kTcAStep; koff1 = (2 * hf + 1) * kTcAStep;
-            // accumulator column / 64 per slot: R 3, Z 4, Hn 6, A2 2, R 3, Z 4, In 5, Q 0
+            // accumulator column / 64 per slot: R 3, Z 4, Hn 6, A2 2, R 3, Z 4, In 5, Q 7
             // (heads only: q.0 is issued before actor.0's accumulator has been read, so it takes W_hn's columns)
-            d0 = d1 = 64u * (((mode == 2 ? 0x65432643u : 0x05432643u) >> (4 * j)) & 0xFu);
+            d0 = d1 = 64u * (((mode == 2 ? 0x65432643u : 0x75432643u) >> (4 * j)) & 0xFu);
             // W_ir, W_iz accumulate onto the recurrent product (pre-pass: they stand alone)
             first0 = (((mode == 3 ? 0xFFu : 0xCFu) >> j) & 1u) & (hf == 0 ? 1u : 0u);
             first1 = 0;
@@ -431,10 +434,11 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
             mma_commit_2sm(&S.w_empty[s]);
             if (post & 1u) mma_commit_2sm(&S.x_empty);
             if (post & 2u) mma_commit_2sm(&S.d_ready);
+            if (post & 4u) mma_commit_2sm(&S.dx_ready);
           }
           __syncwarp();
 #ifdef MACJD_TC_PROFILE
-          if (post & 2u) { if (lane == 0) TC_STAMP(stamp); ++stamp; }
+          if (post & 6u) { if (lane == 0) TC_STAMP(stamp); ++stamp; }
 #endif
           s = (s + 1 == nstages) ? 0 : s + 1;
         }
@@ -483,7 +487,10 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
     const int part = half * kT2ColSplit + ch;        // which of the row's kT2Parts threads
     const bool live = r < valid;
     const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * kT2Upt);
-    uint32_t d_par = 0, x_empty_par = 0;
+    uint32_t d_par = 0, x_empty_par = 0, dx_par = 0;
+    // kFuseEnv launches whose observation is one 32-wide block: the next step's observation tile is staged during THIS
+    // step's E5 (below), so the issuer runs the next step's observation and recurrent products under E5 / E1
+    const bool early_x = kFuseEnv && !kBigA && nx == 1 && x_vec;
 
 #pragma unroll
     for (int i = 0; i < kT2Upt / 4; ++i) {
@@ -515,6 +522,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
         }
       }
       for (int xc = 0; xc < nx; ++xc) {
+        if (early_x && t > 0) break;             // staged one step ahead
         if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
         const float* obs = io.obs + ((tM + row0 + r) / og) * O;
         const bool pre = (t == 0 && xc == 0);      // already in registers (requested at kernel entry)
@@ -550,7 +558,8 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
       if (mode == 0 || mode == 2) {   // (recurrence / pre-pass launches have no actor)
       // ---- E1: a1 = relu(D1 + b) -> B0
       EP_STAMP(1);
-      epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
+      if (kWholeStep) { epi_wait(&S.dx_ready, dx_par, warp); dx_par ^= 1u; }
+      else { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }
       fence_after_sync();
       EP_STAMP(2);
       for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
@@ -677,6 +686,26 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
         }
       }
       EP_STAMP(6);
+      float4 x4_next[2];
+      if (kFuseEnv) {
+        // While the input products run (this wait used to be idle): the next timestep's state / obs / avail of this
+        // CTA's envs -- nothing of them depends on the actions (environment.py:479-551: static views) -- and the loads
+        // of the next step's observation tile.  What the agent observes at t + 1 is what env2_views writes: the env's
+        // static state row, once per jammer (environment.py:512-522); the tile is filled from the same source rows.
+        const int Je = p.env.tab.n_jammers, ne = valid / Je;
+        if (early_x && t + 1 < T) {
+          const bool shared_scn = p.env.tab.env_stride == 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            int r_, k4_;
+            const bool data = x_slot(tid + i * kT2EpiThreads, 0, r_, k4_);
+            x4_next[i] = (data && r_ < valid)
+                             ? __ldg(reinterpret_cast<const float4*>(p.env.state_rows + (shared_scn ? (size_t)0 : (size_t)((row0 + r_) / Je) * O)) + k4_)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        env2_views(p.env, env2_io_at(p.env, t), row0 / Je, ne, tid, kT2EpiThreads);
+      }
 
       if (mode == 3) {
       // ---- pre-pass: the three input products of every row -> gate_x [row][3][H]
@@ -763,14 +792,26 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
       if (mode == 0 || mode == 4) mbar_arrive_cluster(&S.a_ready, 0);     // (mode 1: the next step's x_full covers h')
       }
       EP_STAMP(8);
+      if (kFuseEnv && early_x && t + 1 < T) {
+        // The next step's observation tile, one step ahead: the tile (the first 8 KB of b0) is free -- the input products,
+        // its last readers, completed before E4 -- and so are the accumulators the issuer will overwrite (actor.0 / fc1
+        // were read by E1 / E3, R / Z / Hn by E4; Q has its own columns).  Behind q.0 the issuer then runs the next
+        // step's observation and recurrent products under E5.
+        epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u;       // (this step's observation products: long done)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          int r_, k4_;
+          x_slot(tid + i * kT2EpiThreads, 0, r_, k4_);
+          const float v[4] = {x4_next[i].x, x4_next[i].y, x4_next[i].z, x4_next[i].w};
+          store_split4(xhi, xlo, r_, 4 * k4_, 32, v);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        mbar_arrive_cluster(&S.x_full, 0);
+      }
 
       if (mode == 0 || mode == 2) {
       // ---- E5: Q tail, outputs, selection
-      if (kFuseEnv) {
-        // while the Q-head product runs: the next timestep's state / obs / avail of this CTA's envs
-        const int Je = p.env.tab.n_jammers, ne = valid / Je;
-        env2_views(p.env, env2_io_at(p.env, t), row0 / Je, ne, tid, kT2EpiThreads);
-      }
       if (mode == 0) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }   // heads only: q.0 finished with actor.2
       else epi_bar_sync();                                                  // ... but P (written by E2's last stage) must be visible
       fence_after_sync();

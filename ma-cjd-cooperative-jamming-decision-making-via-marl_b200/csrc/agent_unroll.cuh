@@ -105,7 +105,15 @@ inline int agent_unroll_gemm(const macjd_ctx* ctx, const macjd_agent_weights& W,
   // ---- input side of the GRU for all rows
   relu.bias = W.bfc1;
   gemm(st, io.obs, O, false, W.wfc1t, H, false, u.xf, H, rows, H, O, relu);
-  if (W.wiht) {
+  bool use_rec = false;
+#ifndef MACJD_TEST_HOST_EMULATION
+  use_rec = W.rec_chunks && W.bgx && W.wiht && tc::gru_rec_supported(H) && rec_kernel_wanted();
+#endif
+  if (use_rec) {                      // the recurrence launch expects the input-side biases inside gate_x
+    GemmOpts gb;
+    gb.bias = W.bgx;
+    gemm(st, u.xf, H, false, W.wiht, 3 * H, false, u.gx, 3 * H, rows, 3 * H, H, gb);
+  } else if (W.wiht) {
     gemm(st, u.xf, H, false, W.wiht, 3 * H, false, u.gx, 3 * H, rows, 3 * H, H);
   } else {
     gemm(st, u.xf, H, false, W.wrzt, 2 * H, false, u.gx, 3 * H, rows, 2 * H, H);
@@ -116,11 +124,11 @@ inline int agent_unroll_gemm(const macjd_ctx* ctx, const macjd_agent_weights& W,
   const int gblocks = (M * H + 255) / 256;
   bool rec_done = false;
 #ifndef MACJD_TEST_HOST_EMULATION
-  if (W.rec_chunks && tc::gru_rec_supported(H) && rec_kernel_wanted()) {
+  if (use_rec) {
     // the whole recurrence as one launch: CTA pairs keep their rows' h in shared memory and stream W_hh (gru_rec_tc2.cuh)
     tc::RecArgs ra;
     ra.gate_x = u.gx; ra.h0 = h_first; ra.hidden_seq = hs; ra.hidden_out = nullptr;
-    ra.brz = W.brz; ra.bin = W.bin; ra.bhn = W.bhn; ra.M = M; ra.T = T;
+    ra.bhn = W.bhn; ra.M = M; ra.T = T;
     const int rc = tc::gru_rec_launch(ctx, H, ra, W.rec_chunks);
     if (rc != MACJD_OK) return rc;
     rec_done = true;

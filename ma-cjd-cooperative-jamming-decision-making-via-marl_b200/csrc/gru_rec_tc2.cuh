@@ -23,13 +23,11 @@ namespace macjd {
 namespace tc {
 
 struct RecArgs {
-  const float* gate_x;      // [T][M][3H] input products (r | z | n), no biases
+  const float* gate_x;      // [T][M][3H] input products (r | z | n) INCLUDING the biases b_ir + b_hr | b_iz + b_hz | b_in
   const float* h0;          // [M][H] or NULL (zeros)
   float* hidden_seq;        // [T][M][H]
   float* hidden_out;        // [M][H] or NULL: h_T
-  const float* brz;         // [2H] (b_ir + b_hr | b_iz + b_hz)
-  const float* bin;         // [H]
-  const float* bhn;         // [H]
+  const float* bhn;         // [H] b_hn (inside the reset gate's product: core/networks.py:88-114 -> nn.GRUCell)
   int M, T;
   alignas(64) CUtensorMap wmap;   // rec_chunks as [bytes / 128][32]
 };
@@ -50,6 +48,7 @@ struct RecSmem {
   uint64_t w_full[4], w_empty[4];
   uint64_t a_ready, d_ready[2];
   uint32_t tmem_base;
+  alignas(16) float bhn[128 * NB];
 };
 
 // number of 32 KB chunks (hi + lo) of the packed recurrent weights: per 128-unit block, per gate, H / 32 chunks
@@ -75,6 +74,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
     fence_mbar_init();
   }
   if (warp == kT2EpiWarps + 1) tmem_alloc_2sm(&S.tmem_base, Cfg::kTmemCols);
+  for (int i = tid; i < H; i += kT2Threads) S.bhn[i] = __ldg(p.bhn + i);
   fence_before_sync();
   cluster_sync_all();
   fence_after_sync();
@@ -111,6 +111,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
       for (int t = 0; t < T; ++t) {
         mbar_wait_cluster(&S.a_ready, a_par);          // h_{t-1} is in the operand tiles of both CTAs
         a_par ^= 1u;
+        if (lane == 0) TC_STAMP(32);
         for (int L = 0; L < Cfg::kStagesPerStep; ++L) {
           const uint32_t layer = (uint32_t)L / Cfg::kStagesPerLayer, hf = (uint32_t)L % Cfg::kStagesPerLayer;   // layer = 3 block + gate
           mbar_wait_cluster(&S.w_full[s], (full_par >> s) & 1u);
@@ -138,6 +139,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
             if (hf == Cfg::kStagesPerLayer - 1 && layer % 3 == 2) mma_commit_2sm(&S.d_ready[layer / 3]);   // block done
           }
           __syncwarp();
+          if (lane == 0 && hf == Cfg::kStagesPerLayer - 1 && layer % 3 == 2) TC_STAMP(33 + (int)layer / 3);   // block issued
+          if (lane == 0 && L == 0) TC_STAMP(36);                                                              // first stage issued
           s = (s + 1 == Cfg::kStages) ? 0 : s + 1;
         }
       }
@@ -165,6 +168,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
 
     for (int t = 0; t < T; ++t) {
       const size_t tM = (size_t)t * M;
+      EP_STAMP(0);
       const float* gx_row = p.gate_x + (tM + row0 + (live ? r : 0)) * 3 * H + ub;
       // next step's input products: ask L2 for them a whole step ahead (gate_x is streamed from HBM once)
       if (live && t + 1 < T) {
@@ -178,11 +182,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
       for (int b = 0; b < NB; ++b) {
         const float4* gx = reinterpret_cast<const float4*>(gx_row + b * 128);
         const uint32_t tb = tl + 64u * 3u * (uint32_t)b;
-        float4 gq[6];
+        // this block's input products (3 gates x 32 units per thread), all requested before the wait: they arrive from L2
+        // (prefetched a step ahead) while the block's MMAs finish
+        float4 gq[3][kT2Upt / 4];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) gq[i] = live ? __ldg(gx + (i >> 1) * (H / 4) + (i & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+          for (int i = 0; i < kT2Upt / 4; ++i) gq[g][i] = live ? __ldg(gx + g * (H / 4) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         epi_wait(&S.d_ready[b], d_par, warp);
         fence_after_sync();
+        EP_STAMP(1 + 2 * b);
 #pragma unroll
         for (int c0 = 0; c0 < kT2Upt; c0 += 8) {
           float vr[8], vz[8], vh[8];
@@ -191,14 +200,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
           tmem_ld8_nowait(tb + 128u + (uint32_t)c0, vh);
           tmem_ld_wait();
           reg_fence(vr); reg_fence(vz); reg_fence(vh);
-          const float gr_[8] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w};
-          const float gz_[8] = {gq[2].x, gq[2].y, gq[2].z, gq[2].w, gq[3].x, gq[3].y, gq[3].z, gq[3].w};
-          const float gn_[8] = {gq[4].x, gq[4].y, gq[4].z, gq[4].w, gq[5].x, gq[5].y, gq[5].z, gq[5].w};
-          if (c0 + 8 < kT2Upt) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-              gq[i] = live ? __ldg(gx + (i >> 1) * (H / 4) + (c0 + 8) / 4 + (i & 1)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          const float4 r0 = gq[0][c0 / 4], r1 = gq[0][c0 / 4 + 1], z0 = gq[1][c0 / 4], z1 = gq[1][c0 / 4 + 1], n0 = gq[2][c0 / 4], n1 = gq[2][c0 / 4 + 1];
+          const float gr_[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          const float gz_[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+          const float gn_[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int c = b * 128 + ub + c0 + 4 * q;       // unit index in [0, H)
@@ -206,19 +211,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
             const float4 oh = *reinterpret_cast<const float4*>(S.hhi + off);
             const float4 ol = *reinterpret_cast<const float4*>(S.hlo + off);
             const float hold[4] = {oh.x + ol.x, oh.y + ol.y, oh.z + ol.z, oh.w + ol.w};
-            const float4 brv = __ldg(reinterpret_cast<const float4*>(p.brz + c));
-            const float4 bzv = __ldg(reinterpret_cast<const float4*>(p.brz + H + c));
-            const float4 biv = __ldg(reinterpret_cast<const float4*>(p.bin + c));
-            const float4 bhv = __ldg(reinterpret_cast<const float4*>(p.bhn + c));
-            const float br_[4] = {brv.x, brv.y, brv.z, brv.w}, bz_[4] = {bzv.x, bzv.y, bzv.z, bzv.w};
-            const float bi_[4] = {biv.x, biv.y, biv.z, biv.w}, bh_[4] = {bhv.x, bhv.y, bhv.z, bhv.w};
+            const float4 bhv = *reinterpret_cast<const float4*>(S.bhn + c);
+            const float bh_[4] = {bhv.x, bhv.y, bhv.z, bhv.w};
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int jj = 4 * q + j;
-              const float rg = sigmoid_fast(vr[jj] + gr_[jj] + br_[j]);
-              const float zg = sigmoid_fast(vz[jj] + gz_[jj] + bz_[j]);
-              const float n = tanh_fast(gn_[jj] + bi_[j] + rg * (vh[jj] + bh_[j]));
+              const float rg = sigmoid_fast(vr[jj] + gr_[jj]);
+              const float zg = sigmoid_fast(vz[jj] + gz_[jj]);
+              const float n = tanh_fast(gn_[jj] + rg * (vh[jj] + bh_[j]));
               o[j] = (1.0f - zg) * n + zg * hold[j];
             }
             if (b == NB - 1) {
@@ -235,6 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
             }
           }
         }
+        EP_STAMP(2 + 2 * b);
       }
       d_par ^= 1u;
       // the earlier blocks' h' go into the operand tile now that no MMA reads it any more
@@ -248,6 +250,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kT2Threads, 1) gru_r
       fence_async_smem();
       fence_before_sync();
       if (t + 1 < T) mbar_arrive_cluster(&S.a_ready, 0);
+      EP_STAMP(5);
     }
   }
   fence_before_sync();

@@ -53,3 +53,14 @@ print("issuer:")
 for k in range(32, 40):
     print(f"  {inames[k]:>24}: {v[k] - t0:8d}" + (f"  (+{v[k] - v[k - 1]})" if k > 32 else ""))
 print(f"env warps: actions seen {v[40] - t0}, physics done {v[41] - t0}  (+{v[41] - v[40]})")
+# CTA lifetimes (%globaltimer ns at entry / exit of every CTA): is the launch as long as its slowest CTA, and how
+# far apart are the CTAs?
+n_cta = 2 * ((n * 2 + 127) // 128)
+ent = [v[64 + 2 * b] for b in range(min(n_cta, 512))]
+ext = [v[65 + 2 * b] for b in range(min(n_cta, 512))]
+t_first = min(ent)
+life = sorted((x - e) / 1e3 for e, x in zip(ent, ext))
+print(f"{len(ent)} CTAs: entry spread {(max(ent) - t_first) / 1e3:.1f} us, last exit {(max(ext) - t_first) / 1e3:.1f} us after the first entry")
+print(f"CTA lifetime us: min {life[0]:.1f}  median {life[len(life) // 2]:.1f}  max {life[-1]:.1f}   (per timestep: "
+      f"{life[0] / T:.2f} / {life[len(life) // 2] / T:.2f} / {life[-1] / T:.2f})")
+print("CTA 0 lifetime us:", (ext[0] - ent[0]) / 1e3, " slowest CTAs:", sorted(range(len(ent)), key=lambda b: ent[b] - ext[b])[:8])
