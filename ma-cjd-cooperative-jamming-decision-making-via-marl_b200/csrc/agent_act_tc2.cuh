@@ -56,6 +56,11 @@ constexpr int kT2Parts = 2 * kT2ColSplit;                  // threads that share
 constexpr uint32_t kT2ColA1 = 0, kT2ColFc1 = 64, kT2ColA2 = 128;
 constexpr uint32_t kT2ColR = 192, kT2ColZ = 256, kT2ColIn = 320, kT2ColHn = 384, kT2ColQ = 448;
 constexpr uint32_t kT2TmemCols = 512;
+// Observation blocks ([64 rows][32 k], 8 KB per hi / lo part) are staged in up to four slots of the b0 tile (32 KB per part,
+// free until E1 overwrites it with a1): the epilogue writes block after block and the issuer follows, instead of one
+// write -> MMA -> "tile free" round trip per block (obs 176 = 6 blocks: 26 k of the step's 95 k cycles, tools/tc_phase_profile.py).
+constexpr int kT2XSlots = 4;
+constexpr int kT2XTileFloats = kTcRows * 32;
 // Issue order of the eight K = 128 layers of a step, and where each sits in the packed weights
 // (order there: 0 actor.2, 1 W_ir, 2 W_hr, 3 W_iz, 4 W_hz, 5 W_in, 6 W_hn, 7 q.0[:, :H]):
 //   slot: 0 W_hr  1 W_hz  2 W_hn  3 actor.2  4 W_ir  5 W_iz  6 W_in  7 q.0
@@ -179,7 +184,8 @@ struct T2Smem {
   TcConst c;
   float red[kT2Parts][8][kTcRows];          // partial row sums of the threads that share a row
   uint64_t w_full[kT2MaxStages], w_empty[kT2MaxStages];
-  uint64_t x_full, x_empty, d_ready, a_ready;
+  uint64_t x_full[kT2XSlots], x_empty[kT2XSlots];   // per observation slot: an mbarrier must not run two phases ahead of its waiter
+  uint64_t d_ready, a_ready;
   uint64_t dx_ready;                        // acting launches: the observation products have completed (E1's wait)
   uint64_t c_full;                          // the constant block has landed
   uint32_t tmem_base;
@@ -301,7 +307,8 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
   if (tid == 0) {
     // "full" lives in the leader: armed by its stream thread for both CTAs' bytes of a stage
     for (int s = 0; s < kT2MaxStages; ++s) { mbar_init(&S.w_full[s], 1); mbar_init(&S.w_empty[s], 1); }
-    mbar_init(&S.x_full, 2 * kT2EpiThreads); mbar_init(&S.x_empty, 1); mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 2 * kT2EpiThreads);
+    for (int s = 0; s < kT2XSlots; ++s) { mbar_init(&S.x_full[s], 2 * kT2EpiThreads); mbar_init(&S.x_empty[s], 1); }
+    mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 2 * kT2EpiThreads);
     mbar_init(&S.dx_ready, 1);
     mbar_init(&S.c_full, 1);
     fence_mbar_init();
@@ -377,9 +384,10 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
         for (int L = 0; L < supers_per_step; ++L) {
           uint32_t ahi, alo, sbo, koff0, koff1, d0, d1, first0, first1, pre, post;
           if (L < nx) {                        // [actor.0 | fc1] chunk pair of observation block L
-            ahi = bh; alo = bl; sbo = 32 * 32; koff0 = koff1 = 0;
+            ahi = bh + (uint32_t)(L & (kT2XSlots - 1)) * (kT2XTileFloats * 4); alo = bl + (uint32_t)(L & (kT2XSlots - 1)) * (kT2XTileFloats * 4);
+            sbo = 32 * 32; koff0 = koff1 = 0;
             d0 = kT2ColA1; d1 = kT2ColFc1; first0 = first1 = (L == 0);
-            pre = 1; post = 1u | (L == nx - 1 ? (kWholeStep ? 4u : 2u) : 0u);
+            pre = 1; post = (L + kT2XSlots < nx ? 1u : 0u) | (L == nx - 1 ? (kWholeStep ? 4u : 2u) : 0u);   // (x_empty: the slot is reused)
           } else {                             // K = 128 layers: 4 chunks = 2 stages each
             //  slot j:  0 W_hr (h)  1 W_hz (h)  2 W_hn (h)  3 actor.2 (b0)  4 W_ir (b0)  5 W_iz (b0)  6 W_in (b0)  7 q.0 (h)
             const uint32_t j = (slot_seq >> (4 * ((uint32_t)(L - nx) >> 1))) & 0xFu, hf = (uint32_t)(L - nx) & 1u;
@@ -401,7 +409,8 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
             pre = (hf == 0 && ((pre_m >> j) & 1u)) ? 2u : 0u;
             post = (hf == 1 && ((post_m >> j) & 1u)) ? 2u : 0u;
           }
-          if (pre == 1) { mbar_wait_cluster(&S.x_full, x_full_par); x_full_par ^= 1u; if (lane == 0) TC_STAMP(32); }
+          const int xs = L & (kT2XSlots - 1);       // observation slot of this stage (pre == 1 only)
+          if (pre == 1) { mbar_wait_cluster(&S.x_full[xs], (x_full_par >> xs) & 1u); x_full_par ^= 1u << xs; if (lane == 0) TC_STAMP(32); }
           if (pre == 2) {
             mbar_wait_cluster(&S.a_ready, a_ready_par); a_ready_par ^= 1u;
 #ifdef MACJD_TC_PROFILE
@@ -432,7 +441,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
               }
             }
             mma_commit_2sm(&S.w_empty[s]);
-            if (post & 1u) mma_commit_2sm(&S.x_empty);
+            if (post & 1u) mma_commit_2sm(&S.x_empty[xs]);
             if (post & 2u) mma_commit_2sm(&S.d_ready);
             if (post & 4u) mma_commit_2sm(&S.dx_ready);
           }
@@ -521,9 +530,30 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
             if (act < A) av_mask |= (uint64_t)((kFuseEnv ? __ldcg(ap + act) : __ldg(ap + act)) != 0 ? 1u : 0u) << act;
         }
       }
+      // the first slots' worth of blocks: every load is requested before the first store
+      constexpr int kPre = kFuseEnv ? 1 : kT2XSlots;      // (the fused instance runs at a 128-register cap)
+      float4 x4_blk[kPre][2];
+      if (x_vec && !(early_x && t > 0)) {
+#pragma unroll
+        for (int xc = 0; xc < kPre; ++xc)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            int r_, k4_;
+            const bool data = xc < nx && x_slot(tid + i * kT2EpiThreads, xc, r_, k4_);
+            x4_blk[xc][i] = (t == 0 && xc == 0) ? x4_in[i]          // (requested at kernel entry)
+                            : (data && r_ < valid) ? ld_obs4(reinterpret_cast<const float4*>(io.obs + ((tM + row0 + r_) / og) * O + 32 * xc) + k4_)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+      }
       for (int xc = 0; xc < nx; ++xc) {
         if (early_x && t > 0) break;             // staged one step ahead
-        if (t > 0 || xc > 0) { epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u; }
+        // a slot is reused by block xc + kT2XSlots of the same step: wait for block xc's products (the issuer commits
+        // x_empty for exactly those blocks).  Across steps nothing is needed: every later wait of the epilogue is on a
+        // commit issued behind the observation products.
+        const int xs = xc & (kT2XSlots - 1);
+        if (xc >= kT2XSlots) { epi_wait(&S.x_empty[xs], (x_empty_par >> xs) & 1u, warp); x_empty_par ^= 1u << xs; }
+        float* const sxhi = xhi + (xc & (kT2XSlots - 1)) * kT2XTileFloats;
+        float* const sxlo = xlo + (xc & (kT2XSlots - 1)) * kT2XTileFloats;
         const float* obs = io.obs + ((tM + row0 + r) / og) * O;
         const bool pre = (t == 0 && xc == 0);      // already in registers (requested at kernel entry)
         if (x_vec) {
@@ -531,12 +561,17 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
           for (int i = 0; i < 2; ++i) {
             int r_, k4_;
             const bool data = x_slot(tid + i * kT2EpiThreads, xc, r_, k4_);
-            float4 q = x4_in[i];
-            if (!pre)
+            float4 q;
+            if (xc < kPre) {
+              q = x4_blk[0][i];
+#pragma unroll
+              for (int b_ = 1; b_ < kPre; ++b_) q = xc == b_ ? x4_blk[b_][i] : q;
+            } else {
               q = (data && r_ < valid) ? ld_obs4(reinterpret_cast<const float4*>(io.obs + ((tM + row0 + r_) / og) * O + 32 * xc) + k4_)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             const float v[4] = {q.x, q.y, q.z, q.w};
-            store_split4(xhi, xlo, r_, 4 * k4_, 32, v);
+            store_split4(sxhi, sxlo, r_, 4 * k4_, 32, v);
           }
         } else
 #pragma unroll
@@ -548,11 +583,11 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
             const int kk = xc * 32 + k + j;
             v[j] = pre ? x_in[4 * g + j] : ((live && kk < O) ? ld_obs1(obs + kk) : 0.f);
           }
-          store_split4(xhi, xlo, r, k, 32, v);
+          store_split4(sxhi, sxlo, r, k, 32, v);
         }
         fence_async_smem();
         fence_before_sync();
-        mbar_arrive_cluster(&S.x_full, 0);
+        mbar_arrive_cluster(&S.x_full[xs], 0);
       }
 
       if (mode == 0 || mode == 2) {   // (recurrence / pre-pass launches have no actor)
@@ -797,7 +832,6 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
         // its last readers, completed before E4 -- and so are the accumulators the issuer will overwrite (actor.0 / fc1
         // were read by E1 / E3, R / Z / Hn by E4; Q has its own columns).  Behind q.0 the issuer then runs the next
         // step's observation and recurrent products under E5.
-        epi_wait(&S.x_empty, x_empty_par, warp); x_empty_par ^= 1u;       // (this step's observation products: long done)
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           int r_, k4_;
@@ -807,7 +841,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
         }
         fence_async_smem();
         fence_before_sync();
-        mbar_arrive_cluster(&S.x_full, 0);
+        mbar_arrive_cluster(&S.x_full[0], 0);
       }
 
       if (mode == 0 || mode == 2) {

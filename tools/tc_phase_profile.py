@@ -5,11 +5,13 @@ import torch
 sys.path.insert(0, ".")
 from tests.agent_checks import random_agent
 from macjd_b200 import _native as N
-mac, _ = random_agent(0, 24, 5, 128, 128, 2, "cuda")
+import os
+O, A = int(os.environ.get("TC_O", 24)), int(os.environ.get("TC_A", 5))       # TC_O=176 TC_A=33: the C3 shape
+mac, _ = random_agent(0, O, A, 128, 128, 2, "cuda")
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 3   # T = 1 profiles the cold first step
 PATH = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-obs = torch.randn(T, M, 24, device="cuda")
+obs = torch.randn(T, M, O, device="cuda")
 h = torch.zeros(M, 128, device="cuda")
 for _ in range(3):
     mac.agent.run(obs, h, n_steps=T, select=True, test_mode=True, path=PATH)
