@@ -187,6 +187,7 @@ struct T2Smem {
   uint64_t x_full[kT2XSlots], x_empty[kT2XSlots];   // per observation slot: an mbarrier must not run two phases ahead of its waiter
   uint64_t d_ready, a_ready;
   uint64_t dx_ready;                        // acting launches: the observation products have completed (E1's wait)
+  uint64_t t_full;                          // kBigA: the per-action tables have landed in the (dead) b0 tile
   uint64_t c_full;                          // the constant block has landed
   uint32_t tmem_base;
   int32_t act_s[kTcRows];                   // kFuseEnv: the actions just chosen, handed to the env step in place
@@ -228,7 +229,13 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
   float* Ps = reinterpret_cast<float*>(tc_raw + sizeof(T2Smem));     // [A][64]
   // kBigA: the Q staging [A][64] borrows the xf tile (b0lo): every MMA that reads b0 has completed before E4, and
   // the next step's observation block is written only after E5
-  float* Qs = kBigA ? S.b0lo : Ps + (size_t)A * kTcRows;
+  // kBigA with A8 <= 48: the per-action tables ([H][A8] actor.4.weight^T, [H][A8] q.0 one-hot columns: 1 KB x A8) are copied
+  // into the b0 tile once its last readers (the input products) have completed, and the actor head moves behind E4:
+  // read through L1 they thrash it (the carve-out leaves ~30 KB of L1 beside 215 KB of shared memory; tools/tc_phase_profile.py
+  // at obs 176 / 33 actions: head 22 k + tail 25 k cycles of a 95 k-cycle step, mostly L2 latency).  Qs sits behind them.
+  const bool big_smem = kBigA && A8 <= 48;
+  float* const tabs = S.b0hi;                                        // [H][A8] w3 then [H][A8] w1a (b0hi and b0lo are contiguous)
+  float* Qs = kBigA ? (big_smem ? S.b0hi + 12288 : S.b0lo) : Ps + (size_t)A * kTcRows;
   const int nxc = Op / 32;
   const int chunks_per_step = 2 * kTcChunksPerX * nxc + 8 * kTcChunksPerH;
   const int mode = kWholeStep ? 0 : io.part;   // 0 whole step, 1 recurrence only, 2 heads only, 3 input pre-pass, 4 recurrence on gate_x
@@ -310,6 +317,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
     for (int s = 0; s < kT2XSlots; ++s) { mbar_init(&S.x_full[s], 2 * kT2EpiThreads); mbar_init(&S.x_empty[s], 1); }
     mbar_init(&S.d_ready, 1); mbar_init(&S.a_ready, 2 * kT2EpiThreads);
     mbar_init(&S.dx_ready, 1);
+    mbar_init(&S.t_full, 1);
     mbar_init(&S.c_full, 1);
     fence_mbar_init();
     // the per-layer vectors (TcConst, packed by the host behind the weight chunks): one 13.9 KB bulk copy
@@ -496,7 +504,15 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
     const int part = half * kT2ColSplit + ch;        // which of the row's kT2Parts threads
     const bool live = r < valid;
     const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * kT2Upt);
-    uint32_t d_par = 0, x_empty_par = 0, dx_par = 0;
+    uint32_t d_par = 0, x_empty_par = 0, dx_par = 0, t_par = 0;
+    // kBigA: one bulk copy brings both per-action tables into the b0 tile (call once its MMA readers have completed)
+    auto stage_tables = [&]() {
+      if (big_smem && tid == 0) {
+        fence_async_smem();
+        mbar_expect_tx(&S.t_full, (uint32_t)(1024 * A8));
+        bulk_g2s(tabs, big_w3, (uint32_t)(1024 * A8), &S.t_full);
+      }
+    };
     // kFuseEnv launches whose observation is one 32-wide block: the next step's observation tile is staged during THIS
     // step's E5 (below), so the issuer runs the next step's observation and recurrent products under E5 / E1
     const bool early_x = kFuseEnv && !kBigA && nx == 1 && x_vec;
@@ -522,8 +538,28 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
         const uint8_t* ap = io.avail + (tM + row0 + r) * A;
         av_mask = 0;
         if (kBigA) {
+          // A <= 64 bytes per row at an arbitrary alignment: the aligned 4-byte words that cover the row, all requested at
+          // once (one byte load per action was a chain of ~8 dependent memory round trips at the head of the step);
+          // the last row of the buffer is read bytewise so that no word reaches past the caller's allocation
+          const bool last_row = (tM + row0 + r + 1) == (size_t)T * M;
+          if (!last_row) {
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(ap);
+            const uint32_t* wp = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)3);
+            const int sh = (int)(a0 & 3), nw = (sh + A + 3) >> 2;
+            uint32_t wd[17];
+#pragma unroll
+            for (int i = 0; i < 17; ++i) wd[i] = i < nw ? (kFuseEnv ? __ldcg(wp + i) : __ldg(wp + i)) : 0u;
+#pragma unroll
+            for (int i = 0; i < 17; ++i)
+#pragma unroll
+              for (int b_ = 0; b_ < 4; ++b_) {
+                const int act = 4 * i + b_ - sh;
+                if (act >= 0 && act < A && ((wd[i] >> (8 * b_)) & 0xFFu) != 0) av_mask |= 1ull << act;
+              }
+          } else {
 #pragma unroll 4
-          for (int act = 0; act < A; ++act) av_mask |= (uint64_t)((kFuseEnv ? __ldcg(ap + act) : __ldg(ap + act)) != 0 ? 1u : 0u) << act;
+            for (int act = 0; act < A; ++act) av_mask |= (uint64_t)((kFuseEnv ? __ldcg(ap + act) : __ldg(ap + act)) != 0 ? 1u : 0u) << act;
+          }
         } else {
 #pragma unroll
           for (int act = 0; act < 8; ++act)
@@ -621,6 +657,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
       if (mode != 4) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }
       fence_after_sync();
       EP_STAMP(4);
+      if (kBigA && mode == 2) stage_tables();          // heads only: a1's last reader (actor.2) has completed
       if (mode != 2 && mode != 4) {
       for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
         float v[16];
@@ -674,8 +711,8 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
               Ps[j * kTcRows + r] = sigmoid_fast(sum);
             }
       }
-      if ((mode == 0 || mode == 2) && kBigA)
-      {
+      // kBigA actor head: P_a = sigmoid(a2 . actor.4.weight[a] + b) for A8 actions, from the A2 accumulator
+      auto actor_head_big = [&](const float4* w3, auto ld) {
         // this thread's 32 units of a2 stay in registers; 8 actions per pass over them
         float a2v[kT2Upt];
 #pragma unroll
@@ -687,7 +724,6 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
 #pragma unroll
           for (int n = 0; n < 16; ++n) a2v[c0 + n] = fmaxf(v[n] + S.c.ba2[ub + c0 + n], 0.f);
         }
-        const float4* w3 = reinterpret_cast<const float4*>(big_w3 + (size_t)ub * A8);
         const int a84 = A8 >> 2;
 #pragma unroll 1
         for (int g = 0; g < A8; g += 8) {
@@ -696,7 +732,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
           for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
           for (int n = 0; n < kT2Upt; ++n) {
-            const float4 wl = __ldg(w3 + n * a84 + (g >> 2)), wh = __ldg(w3 + n * a84 + (g >> 2) + 1);
+            const float4 wl = ld(w3 + n * a84 + (g >> 2)), wh = ld(w3 + n * a84 + (g >> 2) + 1);
             const float a2 = a2v[n];
             acc[0] = fmaf(a2, wl.x, acc[0]); acc[1] = fmaf(a2, wl.y, acc[1]);
             acc[2] = fmaf(a2, wl.z, acc[2]); acc[3] = fmaf(a2, wl.w, acc[3]);
@@ -719,7 +755,9 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
             }
           }
         }
-      }
+      };
+      if ((mode == 0 || mode == 2) && kBigA && !big_smem)
+        actor_head_big(reinterpret_cast<const float4*>(big_w3 + (size_t)ub * A8), [](const float4* q_) { return __ldg(q_); });
       EP_STAMP(6);
       float4 x4_next[2];
       if (kFuseEnv) {
@@ -774,6 +812,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
       epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u;
       fence_after_sync();
       EP_STAMP(7);
+      if (kBigA && mode == 0) stage_tables();          // xf's last readers (the input products) have completed
       for (int c0 = 0; c0 < kT2Upt; c0 += 8) {
         float vr[8], vz[8], vi[8], vh[8];
         tmem_ld8_nowait(tl + kT2ColR + (uint32_t)c0, vr);
@@ -844,6 +883,11 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
         mbar_arrive_cluster(&S.x_full[0], 0);
       }
 
+      if ((mode == 0 || mode == 2) && kBigA && big_smem) {
+        // ---- E2 behind E4 (kBigA): the actor head on the staged table, while the Q-head product runs
+        mbar_wait(&S.t_full, t_par); t_par ^= 1u;
+        actor_head_big(reinterpret_cast<const float4*>(tabs + (size_t)ub * A8), [](const float4* q_) { return *q_; });
+      }
       if (mode == 0 || mode == 2) {
       // ---- E5: Q tail, outputs, selection
       if (mode == 0) { epi_wait(&S.d_ready, d_par, warp); d_par ^= 1u; }   // heads only: q.0 finished with actor.2
@@ -884,6 +928,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
               Qs[j * kTcRows + r] = sum;
             }
       } else {
+        auto q_tail_big = [&](const float4* w1, auto ld) {
         // this thread's 32 units of the shared hidden product stay in registers; 8 actions per pass over them
         float prev[kT2Upt];
 #pragma unroll
@@ -895,7 +940,6 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
 #pragma unroll
           for (int n = 0; n < 16; ++n) prev[c0 + n] = v[n] + S.c.q_c[ub + c0 + n].x;
         }
-        const float4* w1 = reinterpret_cast<const float4*>(big_w1a + (size_t)ub * A8);
         const int a84 = A8 >> 2;
 #pragma unroll 1
         for (int g = 0; g < A8; g += 8) {
@@ -905,7 +949,7 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
 #pragma unroll
           for (int n = 0; n < kT2Upt; ++n) {
             const float4 qc = S.c.q_c[ub + n];
-            const float4 wl = __ldg(w1 + n * a84 + (g >> 2)), wh = __ldg(w1 + n * a84 + (g >> 2) + 1);
+            const float4 wl = ld(w1 + n * a84 + (g >> 2)), wh = ld(w1 + n * a84 + (g >> 2) + 1);
             const float wa[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = fmaf(qc.z, fmaxf(fmaf(pa[j], qc.y, prev[n] + wa[j]), 0.f), acc[j]);
@@ -925,6 +969,9 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
             }
           }
         }
+        };
+        if (big_smem) q_tail_big(reinterpret_cast<const float4*>(tabs + (size_t)(H + ub) * A8), [](const float4* q_) { return *q_; });
+        else q_tail_big(reinterpret_cast<const float4*>(big_w1a + (size_t)ub * A8), [](const float4* q_) { return __ldg(q_); });
         epi_bar_sync();                 // every action's Q is staged before the selection reads them
       }
       fence_before_sync();
