@@ -589,6 +589,11 @@ def main():
                              "achieved": M * fpr / dt_simt / 1e12, "peak": fp32_peak, "frac": M * fpr / dt_simt / 1e12 / fp32_peak,
                              "peak_source": fp32_src}}
         if single is not None:
+            tr_r = traffic.get(traffic_key + "_rollout") or {}
+            r["traffic"] = tr_r.get("dram_bytes_per_launch")
+            r["traffic_note"] = (f"DRAM bytes of one launch of {tr_r.get('timesteps_per_launch')} timesteps (ncu --set full); "
+                                 f"{tr_r.get('dram_bytes_per_timestep')} per timestep") if tr_r else None
+            single["traffic"] = tr.get("dram_bytes_per_launch")
             single["frac"] = single["achieved"] / peak
             r["single_step_launch"] = single
             r["us_per_launch"] = "see us_per_timestep_in_launch x timesteps per launch (config.timed_as)"

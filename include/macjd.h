@@ -304,8 +304,11 @@ typedef struct macjd_agent_io {
 MACJD_API int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, const macjd_agent_io* io);
 /* The time-unrolled forward of core/qmix.py:217-280 (the learner's eval / target unrolls: T steps from `hidden`
  * or zeros, h_t / Q for all actions / arg-max / gathers out, no action selection) as batched layers: every layer
- * but the recurrence h_t -> h_t+1 runs as ONE dense product over all T x M rows, the recurrence as per-step
- * products, all on the tensor cores (3xTF32) where they fill its tiles.  For network widths the fused CTA-pair
+ * but the recurrence h_t -> h_t+1 runs as ONE dense product over all T x M rows, all on the tensor cores (3xTF32)
+ * where they fill its tiles.  The recurrence itself is ONE launch when w->rec_chunks (and w->bgx, w->wiht) is given
+ * and H is 128 or 256 (csrc/gru_rec_tc2.cuh: CTA pairs keep their 128 rows of h in shared memory for all T steps
+ * and stream W_hh per step; the environment variable MACJD_REC_KERNEL=0 disables it), else one product and one gate
+ * launch per timestep.  For network widths the fused CTA-pair
  * kernel does not take (macjd_agent_pair_supported == 0, e.g. rnn_hidden_dim 256); same outputs as
  * macjd_agent_forward with n_steps = T up to FP32 summation order.  `io` as for macjd_agent_forward (actions /
  * power / obs_group must be unset); workspace: macjd_agent_unroll_workspace_floats() floats, caller-owned. */
