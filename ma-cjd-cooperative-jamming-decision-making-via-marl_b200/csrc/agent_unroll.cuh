@@ -75,8 +75,8 @@ inline bool rec_kernel_wanted() {
 }
 
 struct UnrollWs {
-  float *xf, *gx, *gh, *a1, *a2, *qh, *P, *hs;
-  size_t total;
+  float *xf, *gx, *gh, *a1, *a2, *qh, *P, *hs, *bpack;
+  size_t total, bpack_floats;
 };
 inline UnrollWs unroll_ws_layout(const macjd_agent_weights& w, int64_t M, int64_t T, float* base) {
   const int64_t rows = T * M, H = w.hidden, AH = w.actor_hidden, A = w.n_actions;
@@ -85,6 +85,20 @@ inline UnrollWs unroll_ws_layout(const macjd_agent_weights& w, int64_t M, int64_
   auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 3) & ~(size_t)3; return p; };
   u.xf = take(rows * H); u.gx = take(rows * 3 * H); u.gh = take(M * 3 * H);
   u.a1 = take(rows * AH); u.a2 = take(rows * AH); u.qh = take(rows * H); u.P = take(rows * A); u.hs = take(rows * H);
+  // the weights of the layer in flight, pre-split for the tensor-core GEMM (tc_gemm.cuh: tc_pack_b_kernel); the layers run
+  // one after the other on the stream, so one region sized for the largest of them is enough
+  u.bpack_floats = 0;
+#ifndef MACJD_TEST_HOST_EMULATION
+  {
+    const int64_t O = w.obs_dim;
+    const int64_t shapes[6][2] = {{3 * H, H}, {H, H}, {AH, AH}, {H, O}, {AH, O}, {A, AH}};     // (N, K) of every layer
+    for (auto& s_ : shapes) {
+      const size_t f = tc::tc_pack_b_floats((int)s_[0], (int)s_[1]);
+      if (f > u.bpack_floats) u.bpack_floats = f;
+    }
+  }
+#endif
+  u.bpack = take(u.bpack_floats);
   u.total = off;
   return u;
 }
@@ -102,6 +116,7 @@ inline int agent_unroll_gemm(const macjd_ctx* ctx, const macjd_agent_weights& W,
   float* hs = io.hidden_seq ? io.hidden_seq : u.hs;
   GemmOpts relu;
   relu.act = kActRelu;
+  relu.bpack_ws = u.bpack; relu.bpack_ws_floats = u.bpack_floats;
   // ---- input side of the GRU for all rows
   relu.bias = W.bfc1;
   gemm(st, io.obs, O, false, W.wfc1t, H, false, u.xf, H, rows, H, O, relu);
@@ -112,6 +127,7 @@ inline int agent_unroll_gemm(const macjd_ctx* ctx, const macjd_agent_weights& W,
   if (use_rec) {                      // the recurrence launch expects the input-side biases inside gate_x
     GemmOpts gb;
     gb.bias = W.bgx;
+    gb.bpack_ws = u.bpack; gb.bpack_ws_floats = u.bpack_floats;
     gemm(st, u.xf, H, false, W.wiht, 3 * H, false, u.gx, 3 * H, rows, 3 * H, H, gb);
   } else if (W.wiht) {
     gemm(st, u.xf, H, false, W.wiht, 3 * H, false, u.gx, 3 * H, rows, 3 * H, H);
@@ -160,12 +176,14 @@ inline int agent_unroll_gemm(const macjd_ctx* ctx, const macjd_agent_weights& W,
   relu.bias = W.ba2;
   gemm(st, u.a1, AH, false, W.wa2t, AH, false, u.a2, AH, rows, AH, AH, relu);
   GemmOpts sig;
+  sig.bpack_ws = u.bpack; sig.bpack_ws_floats = u.bpack_floats;
   sig.act = kActSigmoid;
   sig.bias = W.ba3;
   gemm(st, u.a2, AH, false, W.wa3t, A, false, P, A, rows, A, AH, sig);
   if (io.q_all || io.greedy || (io.sel_actions && io.q_sel)) {
     GemmOpts b;
     b.bias = W.bq1;
+    b.bpack_ws = u.bpack; b.bpack_ws_floats = u.bpack_floats;
     gemm(st, hs, H, false, W.wqt, H, false, u.qh, H, rows, H, H, b);
     MACJD_LAUNCH(qhead_all_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, (const float*)u.qh, (const float*)P, W.w1a, W.w1p, W.w2, W.bq2,
                  rows, H, A, io.q_all, (int*)io.greedy, (const int*)io.sel_actions, io.q_sel);

@@ -14,6 +14,7 @@ struct MixerWs {
   float *d_w1, *d_b1, *d_wf, *d_v, *d_h, *d_sn;                   // backward deltas
   float *splitk; size_t splitk_floats;
   float *colsum;
+  float *bpack; size_t bpack_floats;    // the weights of the product in flight, pre-split for the tensor-core GEMM (tc_gemm.cuh)
   size_t total;
 };
 
@@ -33,6 +34,18 @@ inline MixerWs mixer_ws_layout(const macjd_mixer_dims& d, float* base) {
   w.splitk = take(sk);
   const size_t widest = NE > HH ? NE : HH;
   w.colsum = take(colsum_ws_floats((int)R, (int)(widest > S ? widest : S)));
+  w.bpack_floats = 0;
+#ifndef MACJD_TEST_HOST_EMULATION
+  {
+    // (N, K) of every product whose B operand is a weight matrix: the forward layers and the backward data products
+    const size_t shapes[10][2] = {{HH, S}, {NE, HH}, {E, HH}, {E, S}, {1, E}, {HH, NE}, {S, HH}, {HH, E}, {S, E}, {E, 1}};
+    for (auto& s_ : shapes) {
+      const size_t f = tc::tc_pack_b_floats((int)s_[0], (int)s_[1]);
+      if (f > w.bpack_floats) w.bpack_floats = f;
+    }
+  }
+#endif
+  w.bpack = take(w.bpack_floats);
   w.total = off;
   return w;
 }
@@ -50,6 +63,8 @@ inline int mixer_forward(cudaStream_t st, const macjd_mixer_dims& d, const macjd
   GemmOpts relu; relu.act = kActRelu;
   GemmOpts c05; c05.act = kActClamp; c05.lo = 0.f; c05.hi = 5.f;
   GemmOpts c55; c55.act = kActClamp; c55.lo = -5.f; c55.hi = 5.f;
+  relu.bpack_ws = c05.bpack_ws = c55.bpack_ws = w.bpack;
+  relu.bpack_ws_floats = c05.bpack_ws_floats = c55.bpack_ws_floats = w.bpack_floats;
   relu.bias = p.w1a_b; gemm(st, w.sn, S, false, p.w1a_w, S, true, w.h1, HH, R, HH, S, relu);
   c05.bias = p.w1b_b;  gemm(st, w.h1, HH, false, p.w1b_w, HH, true, w.w1, NE, R, NE, HH, c05);
   relu.bias = p.wfa_b; gemm(st, w.sn, S, false, p.wfa_w, S, true, w.hf, HH, R, HH, S, relu);
@@ -76,17 +91,19 @@ inline int mixer_backward(cudaStream_t st, const macjd_mixer_dims& d, const macj
   GemmOpts sk; sk.splitk_ws = w.splitk; sk.splitk_ws_floats = w.splitk_floats;   // weight gradients: dY^T X
   GemmOpts acc; acc.accumulate = 1;
   GemmOpts plain;
+  acc.bpack_ws = plain.bpack_ws = w.bpack;
+  acc.bpack_ws_floats = plain.bpack_ws_floats = w.bpack_floats;
   // hyper_w_1 : sn -> relu(h1) -> w1
   gemm(st, w.d_w1, NE, true, w.h1, HH, false, g.w1b_w, HH, NE, HH, R, sk);
   colsum(st, w.d_w1, nullptr, R, NE, NE, g.w1b_b, w.colsum);
-  { GemmOpts m; m.mask = w.h1; m.ldmask = HH; gemm(st, w.d_w1, NE, false, p.w1b_w, HH, false, w.d_h, HH, R, HH, NE, m); }
+  { GemmOpts m = plain; m.mask = w.h1; m.ldmask = HH; gemm(st, w.d_w1, NE, false, p.w1b_w, HH, false, w.d_h, HH, R, HH, NE, m); }
   gemm(st, w.d_h, HH, true, w.sn, S, false, g.w1a_w, S, HH, S, R, sk);
   colsum(st, w.d_h, nullptr, R, HH, HH, g.w1a_b, w.colsum);
   gemm(st, w.d_h, HH, false, p.w1a_w, S, false, w.d_sn, S, R, S, HH, plain);
   // hyper_w_final : sn -> relu(hf) -> wf
   gemm(st, w.d_wf, E, true, w.hf, HH, false, g.wfb_w, HH, E, HH, R, sk);
   colsum(st, w.d_wf, nullptr, R, E, E, g.wfb_b, w.colsum);
-  { GemmOpts m; m.mask = w.hf; m.ldmask = HH; gemm(st, w.d_wf, E, false, p.wfb_w, HH, false, w.d_h, HH, R, HH, E, m); }
+  { GemmOpts m = plain; m.mask = w.hf; m.ldmask = HH; gemm(st, w.d_wf, E, false, p.wfb_w, HH, false, w.d_h, HH, R, HH, E, m); }
   gemm(st, w.d_h, HH, true, w.sn, S, false, g.wfa_w, S, HH, S, R, sk);
   colsum(st, w.d_h, nullptr, R, HH, HH, g.wfa_b, w.colsum);
   gemm(st, w.d_h, HH, false, p.wfa_w, S, false, w.d_sn, S, R, S, HH, acc);
@@ -97,7 +114,7 @@ inline int mixer_backward(cudaStream_t st, const macjd_mixer_dims& d, const macj
   // V : sn -> relu(hv) -> v
   gemm(st, w.d_v, 1, true, w.hv, E, false, g.vb_w, E, 1, E, R, sk);
   colsum(st, w.d_v, nullptr, R, 1, 1, g.vb_b, w.colsum);
-  { GemmOpts m; m.mask = w.hv; m.ldmask = E; gemm(st, w.d_v, 1, false, p.vb_w, E, false, w.d_h, E, R, E, 1, m); }
+  { GemmOpts m = plain; m.mask = w.hv; m.ldmask = E; gemm(st, w.d_v, 1, false, p.vb_w, E, false, w.d_h, E, R, E, 1, m); }
   gemm(st, w.d_h, E, true, w.sn, S, false, g.va_w, S, E, S, R, sk);
   colsum(st, w.d_h, nullptr, R, E, E, g.va_b, w.colsum);
   gemm(st, w.d_h, E, false, p.va_w, S, false, w.d_sn, S, R, S, E, acc);

@@ -27,6 +27,8 @@ struct GemmArgs {
   int accumulate;         // C += result
   int k_per_split;        // K range per blockIdx.z (multiple of 16)
   float* partial;         // [splits][M][N] when gridDim.z > 1
+  const float* bpack;     // tensor-core kernel only: B pre-split and pre-laid-out (tc_gemm.cuh: tc_pack_b_kernel), or null
+  int bpack_kchunks;      // 16-k chunks per 128-column tile in bpack
 };
 
 constexpr int kGM = 64, kGN = 64, kGK = 16;
@@ -121,6 +123,7 @@ struct GemmOpts {
   const float* mask = nullptr; int ldmask = 0;
   int accumulate = 0;
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0;   // enables split-K when useful
+  float* bpack_ws = nullptr; size_t bpack_ws_floats = 0;     // tensor-core kernel: room to pre-split B once per call (tall products)
 };
 
 // Number of K splits used for a reduction over `K` rows into an M x N result.
@@ -135,8 +138,21 @@ inline int gemm_splits(int M, int N, int K) {
   return s < 1 ? 1 : s;
 }
 
+// K splits of the tensor-core kernel (tc_gemm.cuh: 128 x 128 tiles, two CTAs per SM): enough CTAs for one full wave,
+// slices of at least 256 rows
+inline int gemm_splits_tc(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  if (K < 2048 || tiles >= kNumSMs) return 1;
+  int s = (2 * kNumSMs + tiles - 1) / tiles;
+  const int maxs = (K + 255) / 256;
+  if (s > maxs) s = maxs;
+  return s < 1 ? 1 : s;
+}
+
+// workspace for either kernel's partial sums
 inline size_t gemm_splitk_ws_floats(int M, int N, int K) {
-  const int s = gemm_splits(M, N, K);
+  const int a = gemm_splits(M, N, K), b = gemm_splits_tc(M, N, K);
+  const int s = a > b ? a : b;
   return s > 1 ? (size_t)s * M * N : 0;
 }
 
@@ -147,6 +163,7 @@ inline GemmArgs gemm_args(const float* A, int lda, bool ta, const float* B, int 
   g.ta = ta; g.tb = tb; g.bias = o.bias; g.act = o.act; g.lo = o.lo; g.hi = o.hi;
   g.mask = o.mask; g.ldmask = o.ldmask; g.accumulate = o.accumulate;
   g.k_per_split = K; g.partial = nullptr;
+  g.bpack = nullptr; g.bpack_kchunks = 0;
   return g;
 }
 

@@ -116,7 +116,44 @@ __device__ __forceinline__ void gt_store(float* hi, float* lo, const float4 (&x)
   }
 }
 
-template <bool kAContigK, bool kBContigK>
+__device__ __forceinline__ void gt_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;\n" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gt_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// B once per call instead of once per CTA.  In a tall product (the learner's layers over T x M rows: 1 600 row tiles) every
+// CTA of a column used to load the same FP32 weights, split them to TF32 hi / lo and lay them out for the MMA -- half of
+// the loader warps' work, and the loaders bound the kernel (ncu r2s: tensor pipe active 19 %, issue active 34 %).  This
+// kernel writes, per 128-column tile and 16-k chunk, the hi tile followed by the lo tile exactly as a stage's B buffers
+// hold them (16 KB, zero padded); the GEMM then fetches a stage's B with ONE bulk copy.
+constexpr int kGtPackFloats = 2 * kGtTileFloats;                 // hi + lo of one chunk
+inline size_t tc_pack_b_floats(int N, int K) { return (size_t)((N + kGtN - 1) / kGtN) * ((K + kGtK - 1) / kGtK) * kGtPackFloats; }
+
+__global__ void __launch_bounds__(256) tc_pack_b_kernel(const float* __restrict__ B, int ldb, int tb, int N, int K, float* __restrict__ out) {
+  grid_dependency_wait();               // (the previous GEMM of the stream may still be reading `out`)
+  const int kchunks = (K + kGtK - 1) / kGtK;
+  const int nt = blockIdx.x / kchunks, kc = blockIdx.x - nt * kchunks;
+  const int r = threadIdx.x >> 1, kh = (threadIdx.x & 1) * 8;     // column of the tile, 8 of its 16 k
+  const int n = nt * kGtN + r;
+  float* hi = out + (size_t)blockIdx.x * kGtPackFloats;
+  float* lo = hi + kGtTileFloats;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kc * kGtK + kh + 4 * q + j;
+      v[j] = (n < N && k < K) ? (tb ? __ldg(B + (size_t)n * ldb + k) : __ldg(B + (size_t)k * ldb + n)) : 0.f;
+    }
+    store_split4_tile(hi, lo, r, kh + 4 * q, v);
+  }
+}
+
+template <bool kAContigK, bool kBContigK, bool kBPacked = false>
 __global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g) {
   extern __shared__ __align__(1024) unsigned char gt_raw[];
   GtSmem& S = *reinterpret_cast<GtSmem*>(gt_raw);
@@ -126,7 +163,7 @@ __global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g
   const int kend = min(g.K, kbeg + g.k_per_split);
   const int n_chunks = (kend - kbeg + kGtK - 1) / kGtK;
   if (tid == 0) {
-    for (int s = 0; s < kGtStages; ++s) { mbar_init(&S.full[s], kGtLoadThreads); mbar_init(&S.empty[s], 1); }
+    for (int s = 0; s < kGtStages; ++s) { mbar_init(&S.full[s], kGtLoadThreads + (kBPacked ? 1 : 0)); mbar_init(&S.empty[s], 1); }
     mbar_init(&S.done, 1);
     fence_mbar_init();
   }
@@ -145,12 +182,14 @@ __global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g
     uint32_t empty_par = 0;
     // kGtAhead chunks of both operands are in flight per thread (registers) while the oldest one is converted and
     // stored: at ~1.5 us of memory latency under load a single chunk in flight left every k-step waiting for DRAM / L2
-    float4 ra[kGtAhead][kGtVec], rb[kGtAhead][kGtVec];
+    float4 ra[kGtAhead][kGtVec], rb[kBPacked ? 1 : kGtAhead][kGtVec];
+    // kBPacked: a stage's B (hi + lo tiles, 16 KB, contiguous in S.b[s]) arrives by one bulk copy from the packed buffer
+    const float* bsrc = kBPacked ? g.bpack + ((size_t)blockIdx.x * g.bpack_kchunks + kbeg / kGtK) * kGtPackFloats : nullptr;
 #pragma unroll
     for (int d = 0; d < kGtAhead; ++d)
       if (d < n_chunks) {
         gt_load<kAContigK>(ra[d], g.A, g.lda, m0, g.M, kbeg + d * kGtK, kend, tid, a_vec);
-        gt_load<kBContigK>(rb[d], g.B, g.ldb, n0, g.N, kbeg + d * kGtK, kend, tid, b_vec);
+        if (!kBPacked) gt_load<kBContigK>(rb[d < (kBPacked ? 1 : kGtAhead) ? d : 0], g.B, g.ldb, n0, g.N, kbeg + d * kGtK, kend, tid, b_vec);
       }
     for (int c0 = 0; c0 < n_chunks; c0 += kGtAhead) {
 #pragma unroll
@@ -159,13 +198,17 @@ __global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g
         if (c < n_chunks) {
           const int s = c % kGtStages;
           if (c >= kGtStages) { mbar_wait(&S.empty[s], (empty_par >> s) & 1u); empty_par ^= 1u << s; }
+          if (kBPacked && tid == 0) {
+            gt_expect_tx(&S.full[s], (uint32_t)(kGtPackFloats * 4));
+            gt_bulk_g2s(S.b[s][0], bsrc + (size_t)c * kGtPackFloats, (uint32_t)(kGtPackFloats * 4), &S.full[s]);
+          }
           gt_store<kAContigK>(S.a[s][0], S.a[s][1], ra[d], tid);
-          gt_store<kBContigK>(S.b[s][0], S.b[s][1], rb[d], tid);
+          if (!kBPacked) gt_store<kBContigK>(S.b[s][0], S.b[s][1], rb[d < (kBPacked ? 1 : kGtAhead) ? d : 0], tid);
           fence_async_smem();
           gt_mbar_arrive(&S.full[s]);
           if (c + kGtAhead < n_chunks) {           // refill the slot just consumed
             gt_load<kAContigK>(ra[d], g.A, g.lda, m0, g.M, kbeg + (c + kGtAhead) * kGtK, kend, tid, a_vec);
-            gt_load<kBContigK>(rb[d], g.B, g.ldb, n0, g.N, kbeg + (c + kGtAhead) * kGtK, kend, tid, b_vec);
+            if (!kBPacked) gt_load<kBContigK>(rb[d < (kBPacked ? 1 : kGtAhead) ? d : 0], g.B, g.ldb, n0, g.N, kbeg + (c + kGtAhead) * kGtK, kend, tid, b_vec);
           }
         }
       }
@@ -262,13 +305,9 @@ inline size_t tc_gemm_smem_bytes() {
   return sizeof(GtSmem) + 1024;
 }
 
-// K splits for the tensor-core kernel: enough CTAs to fill the chip, slices of at least 256 rows
+// K splits for the tensor-core kernel (sgemm.cuh: gemm_splits_tc), bounded by the caller's workspace
 inline int tc_gemm_splits(int M, int N, int K, size_t ws_floats) {
-  const int tiles = ((M + kGtM - 1) / kGtM) * ((N + kGtN - 1) / kGtN);
-  if (K < 2048 || tiles >= kNumSMs) return 1;
-  int s = (kNumSMs + tiles - 1) / tiles;
-  const int maxs = (K + 255) / 256;
-  if (s > maxs) s = maxs;
+  int s = gemm_splits_tc(M, N, K);          // one full wave at two CTAs per SM (19 splits of a 2 x 2-tile gradient left half the chip idle)
   const size_t fit = ws_floats / ((size_t)M * N);
   if ((size_t)s > fit) s = (int)fit;
   return s < 1 ? 1 : s;
@@ -285,7 +324,9 @@ inline bool tc_gemm_launch(cudaStream_t st, int device, GemmArgs g, const GemmOp
   static PerDeviceMax opted;
   const size_t smem = tc_gemm_smem_bytes();
   if (!opted.covers(device, smem)) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+    if (cudaFuncSetAttribute(tc_gemm_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(tc_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(tc_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(tc_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -305,6 +346,16 @@ inline bool tc_gemm_launch(cudaStream_t st, int device, GemmArgs g, const GemmOp
   const dim3 grid((g.N + kGtN - 1) / kGtN, (g.M + kGtM - 1) / kGtM, splits);
   // A(m,k) is k-contiguous unless ta; B(k,n) is k-contiguous (per output column n) when tb
   const bool ak = !g.ta, bk = g.tb != 0;
+  // tall products: split B once (tc_pack_b_kernel), then every CTA fetches its B stages with bulk copies
+  if (o.bpack_ws && g.M >= 8 * kGtM && tc_pack_b_floats(g.N, g.K) <= o.bpack_ws_floats &&
+      (reinterpret_cast<uintptr_t>(o.bpack_ws) & 15) == 0) {
+    const int kchunks = (g.K + kGtK - 1) / kGtK;
+    MACJD_LAUNCH(tc_pack_b_kernel, dim3(grid.x * kchunks), dim3(256), 0, st, g.B, g.ldb, g.tb, g.N, g.K, o.bpack_ws);
+    g.bpack = o.bpack_ws;
+    g.bpack_kchunks = kchunks;
+    if (ak) MACJD_LAUNCH((tc_gemm_kernel<true, true, true>), grid, dim3(kGtThreads), smem, st, g);
+    else MACJD_LAUNCH((tc_gemm_kernel<false, true, true>), grid, dim3(kGtThreads), smem, st, g);
+  } else
   if (ak && bk) MACJD_LAUNCH((tc_gemm_kernel<true, true>), grid, dim3(kGtThreads), smem, st, g);
   else if (ak) MACJD_LAUNCH((tc_gemm_kernel<true, false>), grid, dim3(kGtThreads), smem, st, g);
   else if (bk) MACJD_LAUNCH((tc_gemm_kernel<false, true>), grid, dim3(kGtThreads), smem, st, g);
