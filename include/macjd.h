@@ -462,6 +462,11 @@ MACJD_API size_t macjd_qhead_scratch_floats(const macjd_qhead_dims* dims);
  * (wqt, bq1, w1a, w1p, w2, bq2); hid [R][H] keeps the ReLU activations for the backward. */
 MACJD_API int macjd_qhead_forward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
                                   const float* hidden, const int32_t* a_d, const float* a_c, float* q, float* hid);
+/* The same with caller-owned scratch (any size; macjd_qhead_scratch_floats() is enough): room for the tensor-core GEMM to
+ * pre-split the weight matrix once per call instead of once per CTA (tall batches).  Same results. */
+MACJD_API int macjd_qhead_forward_ws(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
+                                     const float* hidden, const int32_t* a_d, const float* a_c, float* q, float* hid,
+                                     float* scratch, size_t scratch_floats);
 /* dq [R] -> gradients in PyTorch layout: g_w1 [H][H+A+1], g_b1 [H], g_w2 [H], g_b2 [1].
  * `hid` (from the forward) is consumed. */
 MACJD_API int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,

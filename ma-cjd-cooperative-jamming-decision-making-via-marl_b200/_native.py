@@ -166,6 +166,7 @@ class NativeLib:
             ("macjd_mixer_backward", C.c_int, [P(Ctx), P(MixerDims), P(MixerParams), vp, vp, vp, sz, P(MixerParams), vp]),
             ("macjd_qhead_scratch_floats", sz, [P(QheadDims)]),
             ("macjd_qhead_forward", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp]),
+            ("macjd_qhead_forward_ws", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp, vp, C.c_size_t]),
             ("macjd_qhead_backward", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]),
             ("macjd_gather_q", C.c_int, [P(Ctx), i32, i32, vp, vp, vp]),
             ("macjd_td_scratch_floats", sz, [i32]),

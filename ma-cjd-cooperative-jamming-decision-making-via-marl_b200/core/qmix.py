@@ -216,7 +216,8 @@ class QMixLearner:
         a_d, a_c = tb["a_d"].view(-1), tb["a_c"].view(-1)
         q_taken = f32(R * Nn)
         hid = self._workspace("qhead_hid", R * Nn * H, dev)
-        L.callv("macjd_qhead_forward", ctx, qd, pk, hidden, a_d, a_c, q_taken, hid)
+        qs = self._workspace("qhead_scratch", L.lib.macjd_qhead_scratch_floats(qd), dev)
+        L.callv("macjd_qhead_forward_ws", ctx, qd, pk, hidden, a_d, a_c, q_taken, hid, qs, qs.numel())
 
         # 5. eval mixer (qmix.py:187); leaves its intermediates in the workspace
         eval_struct = self._mixer_struct(self.eval_qmix_net)
@@ -248,7 +249,6 @@ class QMixLearner:
         L.callv("macjd_mixer_backward", ctx, dims, eval_struct, q_taken, dq_tot, ws, ws_floats,
                 self._mixer_struct(flat=grad, offset=qh), dq)
         o0, o1, o2, o3 = np.cumsum([0] + opt["sizes"][:3])
-        qs = self._workspace("qhead_scratch", L.lib.macjd_qhead_scratch_floats(qd), dev)
         L.callv("macjd_qhead_backward", ctx, qd, pk, hidden, a_d, a_c, hid, dq,
                 grad[o0:], grad[o1:], grad[o2:], grad[o3:], qs, qs.numel())
 

@@ -133,10 +133,11 @@ inline size_t qhead_scratch_floats(const macjd_qhead_dims& d) {
 }
 
 inline int qhead_forward(cudaStream_t st, const macjd_qhead_dims& d, const macjd_agent_weights& w, const float* hidden,
-                         const int32_t* a_d, const float* a_c, float* q, float* hid) {
+                         const int32_t* a_d, const float* a_c, float* q, float* hid, float* scratch, size_t scratch_floats) {
   const int R = d.n_rows, H = d.hidden, A = d.n_actions;
   if (R == 0) return MACJD_OK;
   GemmOpts o; o.bias = w.bq1;
+  o.bpack_ws = scratch; o.bpack_ws_floats = scratch ? scratch_floats : 0;     // (optional: the pre-split weight matrix)
   gemm(st, hidden, H, false, w.wqt, H, false, hid, H, R, H, H, o);          // pre = h W1[:, :H]^T + b1
   MACJD_LAUNCH(qhead_tail_fwd_kernel, dim3(rows_grid(R)), dim3(256), 0, st, hid, (const int*)a_d, a_c, w.w1a, w.w1p,
                w.w2, w.bq2, R, H, A, q);

@@ -625,7 +625,16 @@ int macjd_qhead_forward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, cons
   MACJD_ENTER(ctx);
   if (!dims || !w || !hidden || !a_d || !a_c || !q || !hid || dims->n_rows < 0) return MACJD_ERR_INVALID_ARG;
   if (dims->hidden != w->hidden || dims->n_actions != w->n_actions) return MACJD_ERR_INVALID_ARG;
-  return finish(ctx, macjd::qhead_forward((cudaStream_t)ctx->stream, *dims, *w, hidden, a_d, a_c, q, hid));
+  return finish(ctx, macjd::qhead_forward((cudaStream_t)ctx->stream, *dims, *w, hidden, a_d, a_c, q, hid, nullptr, 0));
+}
+
+int macjd_qhead_forward_ws(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,
+                           const float* hidden, const int32_t* a_d, const float* a_c, float* q, float* hid, float* scratch,
+                           size_t scratch_floats) {
+  MACJD_ENTER(ctx);
+  if (!dims || !w || !hidden || !a_d || !a_c || !q || !hid || dims->n_rows < 0) return MACJD_ERR_INVALID_ARG;
+  if (dims->hidden != w->hidden || dims->n_actions != w->n_actions) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::qhead_forward((cudaStream_t)ctx->stream, *dims, *w, hidden, a_d, a_c, q, hid, scratch, scratch_floats));
 }
 
 int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims* dims, const macjd_agent_weights* w,

@@ -316,7 +316,9 @@ inline int tc_gemm_splits(int M, int N, int K, size_t ws_floats) {
 // Worth the tensor cores: enough work to fill 128 x 128 tiles.  (MACJD_TC_GEMM=0 keeps every GEMM on the FP32 kernel.)
 inline bool tc_gemm_wanted(int M, int N, int K) {
   static const bool on = [] { const char* e = getenv("MACJD_TC_GEMM"); return !(e && e[0] == '0'); }();
-  return on && N >= 32 && M >= 64 && (double)M * N * K >= (double)(1 << 24);
+  // (narrow outputs included: a [256 x 6] weight gradient over 200 k rows or a 5-column layer over 200 k rows is bound by
+  // reading its tall operand, which the 128-row tiles with several chunks in flight do at 3-4x the FP32 kernel's rate)
+  return on && M >= 64 && (double)M * N * K >= (double)(1 << 24);
 }
 
 // returns false if the launch could not be set up (caller falls back to the FP32 kernel)
