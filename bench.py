@@ -317,8 +317,13 @@ def main():
 
     import torch
     import torch.distributed as dist
-    real_stdout = sys.stdout
-    sys.stdout = sys.stderr                     # library chatter must not pollute the one JSON line
+    # library chatter must not pollute the one JSON line -- including what C libraries write to file descriptor 1
+    # (NCCL prints its version banner there when NCCL_DEBUG is set): fd 1 points at stderr until the line is written
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(json_fd, "w")
+    sys.stdout = sys.stderr
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
