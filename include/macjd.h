@@ -514,7 +514,9 @@ MACJD_API int macjd_clear_pipeline_fault(void);
  * 215-248 and its two backward products):  C[m][n] (ldc) = act(sum_k A(m,k) B(k,n) + bias[n]) (+ C if accumulate),
  *   A(m,k) = ta ? A[k lda + m] : A[m lda + k],   B(k,n) = tb ? B[n ldb + k] : B[k ldb + n]  (tb = 1: a PyTorch weight)
  *   act: 0 none, 1 ReLU, 3 sigmoid.  splitk_ws (optional, >= splits x M x N floats): lets a product with few output
- * tiles and a long contraction (weight gradients: K = batch rows) be split over K, reduced in a fixed order.
+ * tiles and a long contraction (weight gradients: K = batch rows) be split over K, reduced in a fixed order; for
+ * K < 2048 and M >= 1024 the same workspace (>= ceil(N / 128) x ceil(K / 16) x 4096 floats) lets the tensor-core kernel
+ * split and lay out B once per call instead of once per CTA (bit-identical results).
  * Runs on the tcgen05 tensor cores (3xTF32 operand split, FP32-level accuracy; csrc/tc_gemm.cuh) when the problem
  * fills its 128 x 128 tiles, else on the FP32 SIMT kernel (csrc/sgemm.cuh). */
 MACJD_API int macjd_gemm(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t ta,

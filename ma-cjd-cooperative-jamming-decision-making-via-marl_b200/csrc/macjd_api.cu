@@ -685,6 +685,8 @@ int macjd_gemm(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const floa
   if (M < 0 || N < 0 || K < 1 || !A || !B || !C || act < 0 || act > 3 || act == 2) return MACJD_ERR_INVALID_ARG;
   macjd::GemmOpts o;
   o.bias = bias; o.act = act; o.accumulate = accumulate; o.splitk_ws = splitk_ws; o.splitk_ws_floats = splitk_ws_floats;
+  // the same workspace lets a tall product pre-split B once per call (K < 2048: split-K never applies there)
+  if (K < 2048) { o.bpack_ws = splitk_ws; o.bpack_ws_floats = splitk_ws ? splitk_ws_floats : 0; }
   macjd::gemm((cudaStream_t)ctx->stream, A, lda, ta != 0, B, ldb, tb != 0, C, ldc, M, N, K, o);
   return finish(ctx, MACJD_OK);
 }

@@ -58,3 +58,26 @@ def test_gemm_split_k_weight_gradient_shapes():
 
 def test_gemm_small_problems_stay_on_the_fp32_kernel():
     assert _gemm(64, 5, 128, 0, 0, bias=True, act=3) < 1e-6
+
+
+@pytest.mark.parametrize("tb", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(4096, 200, 100), (2048, 768, 256), (1500, 5, 128)])
+def test_gemm_presplit_weights_are_bit_identical(M, N, K, tb):
+    """Tall products: with workspace the tensor-core kernel fetches B pre-split (csrc/tc_gemm.cuh: tc_pack_b_kernel + one bulk
+    copy per stage) instead of splitting it in every CTA -- the same hi / lo values, the same MMAs in the same order."""
+    from macjd_b200 import _native as N_
+    L = N_.get_lib()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g) if tb else torch.randn(K, N, device="cuda", generator=g)
+    b = torch.randn(N, device="cuda", generator=g)
+    outs = []
+    for ws in (None, torch.empty(((N + 127) // 128) * ((K + 15) // 16) * 4096, device="cuda")):
+        C = torch.empty(M, N, device="cuda")
+        L.callv("macjd_gemm", N_.torch_ctx(torch.device("cuda", 0)), M, N, K, A, K, 0, B, B.shape[1], tb, C, N, b, 1, 0,
+                ws, ws.numel() if ws is not None else 0)
+        outs.append(C)
+    assert torch.equal(outs[0], outs[1])
+    ref = (A.double() @ (B.double().t() if tb else B.double()) + b.double()).clamp(min=0)
+    scale = (A.abs().double() @ (B.abs().double().t() if tb else B.abs().double())).clamp(min=1.0)
+    assert ((outs[1].double() - ref).abs() / scale).max().item() < 4e-6
