@@ -86,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -617,8 +617,11 @@ def main():
                 "traffic": (traffic.get("env_step_kernel") or {}).get(key), "bytes_per_env_step": bytes_per_step,
                 "us_per_launch": dt_env * 1e6, "peak_source": hbm_src}
 
+    # rank 0 samples its GPU (one nvidia-smi poller per box: every query takes driver locks that the other ranks' launch
+    # paths share, and eight pollers next to eight host-bound e2e loops are measurable)
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     line = {"metric": "env_agent_steps_per_sec", "unit": "env-agent steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 env physics + 3xTF32 tensor-core GEMMs (f32-level) + f32 epilogues", "data": "synthetic",
