@@ -62,9 +62,12 @@ runner.t_env = 0
 for _ in range(20):
     runner.step_host(hb_s["state"], avail_h, hb_s)
 torch.cuda.synchronize()
-for rep in range(3):
+hs = []
+for rep in range(8):
     t0 = time.perf_counter()
-    for _ in range(60):
+    for _ in range(200):
         runner.step_host(hb_s["state"], avail_h, hb_s)
     torch.cuda.synchronize()
-    print(f"host step (state rows): {(time.perf_counter() - t0) / 60 * 1e6:.1f} us")
+    hs.append((time.perf_counter() - t0) / 200 * 1e6)
+hs.sort()
+print(f"host step (state rows), 8 x 200 steps: min {hs[0]:.1f}  median {hs[4]:.1f}  max {hs[-1]:.1f} us")
