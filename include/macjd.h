@@ -398,9 +398,11 @@ typedef struct macjd_copy_desc {
   int64_t dst_ep_stride;
   int64_t dst_t_stride;
   int32_t n_t;             /* timesteps to copy (T or T+1)                               */
-  int32_t inner_bytes;     /* contiguous bytes per timestep                              */
+  int32_t inner_bytes;     /* contiguous bytes per timestep (on the SOURCE side when `convert` is set) */
   int32_t vec_bytes;       /* filled in by the library                                   */
-  int32_t reserved;
+  int32_t convert;         /* 0: plain bytes.  1: source float32 -> destination bfloat16 (round to nearest even),
+                              2: source bfloat16 -> destination float32: the optional BF16 storage of
+                              `hidden_state` in the ring (72 % of an episode, utils/replay_buffer.py:66) */
 } macjd_copy_desc;
 
 /* For b in [0, n_eps): slot = idx ? idx[b] : b.  index_on_src != 0: dst episode b <- src

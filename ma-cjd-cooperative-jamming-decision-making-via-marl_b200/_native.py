@@ -78,7 +78,7 @@ class EnvHost(C.Structure):
 class CopyDesc(C.Structure):
     _fields_ = [("src", c_void_p), ("dst", c_void_p), ("src_ep_stride", c_int64), ("src_t_stride", c_int64),
                 ("dst_ep_stride", c_int64), ("dst_t_stride", c_int64), ("n_t", c_int32), ("inner_bytes", c_int32),
-                ("vec_bytes", c_int32), ("reserved", c_int32)]
+                ("vec_bytes", c_int32), ("convert", c_int32)]
 
 
 class MixerDims(C.Structure):

@@ -13,7 +13,12 @@ replay_buffer.py:59); with ``shared_obs=True`` the ring does not hold ``obs`` at
 every agent observes the global state (environment.py:512-522: ``get_obs`` replicates ``get_state``), so
 ``sample`` rebuilds ``obs[b, t, i, :] = state[b, t, :]`` inside the same gather launch.  ``sample`` returns
 the reference's keys, shapes and dtypes either way; an episode shrinks from 142.8 KB to 123.4 KB at the
-default dims.
+default dims.  ``hidden_bf16=True`` (opt-in; ``args.replay_hidden_bf16``) stores ``hidden_state`` -- 72 % of an
+episode (replay_buffer.py:66) -- as bfloat16: the store and gather launches convert (round to nearest even),
+``sample`` still returns float32.  The learner computes Q of the taken actions from the stored states
+(core/qmix.py:161-184), so this option changes its numbers: every state carries a relative rounding error of up
+to 2^-9 (stated bound of the option; ``tests/learner_checks.py:check_hidden_bf16_replay``); 71.5 KB per episode
+with both options at the default dims.
 """
 from __future__ import annotations
 
@@ -31,8 +36,9 @@ class EpisodeReplayBuffer:
     KEY_ORDER = ("state", "obs", "actions_discrete", "actions_continuous", "avail_actions", "reward", "terminated",
                  "filled", "hidden_state")
 
-    def __init__(self, args, device=None, _lib=None, shared_obs=None):
+    def __init__(self, args, device=None, _lib=None, shared_obs=None, hidden_bf16=None):
         self.args = args
+        self.hidden_bf16 = bool(getattr(args, "replay_hidden_bf16", False) if hidden_bf16 is None else hidden_bf16)
         # obs is state replicated per agent: keep only the state (caller vouches; needs obs_shape == state_shape)
         self.shared_obs = bool(getattr(args, "replay_shared_obs", False) if shared_obs is None else shared_obs)
         self._lib = _lib if _lib is not None else N.get_lib()
@@ -60,7 +66,7 @@ class EpisodeReplayBuffer:
             "reward": z((C_, T, 1), torch.float32),
             "terminated": z((C_, T, 1), torch.uint8),
             "filled": z((C_, T, 1), torch.uint8),
-            "hidden_state": z((C_, T + 1, Nn, args.rnn_hidden_dim), torch.float32),
+            "hidden_state": z((C_, T + 1, Nn, args.rnn_hidden_dim), torch.bfloat16 if self.hidden_bf16 else torch.float32),
         }
         if self.shared_obs:
             if self.obs_shape != self.state_shape:
@@ -110,7 +116,7 @@ class EpisodeReplayBuffer:
             for key, buf in self.buffers.items():       # (with shared_obs the episode's "obs" entry is not kept)
                 n_t = buf.shape[1]
                 host = np.zeros(tuple(buf.shape[1:]), dtype={torch.float32: np.float32, torch.int32: np.int32,
-                                                              torch.uint8: np.uint8}[buf.dtype])
+                                                              torch.uint8: np.uint8, torch.bfloat16: np.float32}[buf.dtype])
                 if key == "filled":
                     host[:L] = 1
                 elif key == "hidden_state" and key not in ep:
@@ -121,7 +127,7 @@ class EpisodeReplayBuffer:
                     host[:n] = src.reshape((n,) + host.shape[1:])
                     if key == "terminated":
                         host[L:] = 1                      # replay_buffer.py:150
-                buf[idx].copy_(torch.from_numpy(host), non_blocking=False)
+                buf[idx].copy_(torch.from_numpy(host), non_blocking=False)      # (casts to bfloat16, round to nearest even)
             self.ep_len[idx] = L
 
     def store_rollout(self, traj, n_eps=None):
@@ -140,13 +146,15 @@ class EpisodeReplayBuffer:
                     buf[torch.from_numpy(slots).to(self.device)] = 1
                     continue
                 src = traj[key]
-                assert src.is_contiguous() and src.dtype == buf.dtype, key
-                inner = buf[0, 0].numel() * buf.element_size()
+                to_bf16 = buf.dtype == torch.bfloat16 and src.dtype == torch.float32      # converted by the copy launch
+                assert src.is_contiguous() and (src.dtype == buf.dtype or to_bf16), key
+                inner = buf[0, 0].numel() * buf.element_size()                  # ring side
+                s_inner = buf[0, 0].numel() * src.element_size()                # rollout side
                 n_t = buf.shape[1]
-                assert src.shape[0] == n_t and src.numel() * src.element_size() == n_t * src.shape[1] * inner, key
-                descs.append(N.CopyDesc(src=src.data_ptr(), dst=buf.data_ptr(), src_ep_stride=inner,
-                                        src_t_stride=src.shape[1] * inner, dst_ep_stride=n_t * inner,
-                                        dst_t_stride=inner, n_t=n_t, inner_bytes=inner))
+                assert src.shape[0] == n_t and src.numel() * src.element_size() == n_t * src.shape[1] * s_inner, key
+                descs.append(N.CopyDesc(src=src.data_ptr(), dst=buf.data_ptr(), src_ep_stride=s_inner,
+                                        src_t_stride=src.shape[1] * s_inner, dst_ep_stride=n_t * inner,
+                                        dst_t_stride=inner, n_t=n_t, inner_bytes=s_inner, convert=1 if to_bf16 else 0))
                 keep.append(src)
             self._copy(descs, idx_dev, n, index_on_src=False)
             self.ep_len[slots] = T
@@ -174,15 +182,18 @@ class EpisodeReplayBuffer:
         for key, buf in self.buffers.items():
             n_t = max_len + 1 if key in T_PLUS_1 else max_len
             inner_shape = tuple(buf.shape[2:])
-            inner = int(np.prod(inner_shape)) * buf.element_size()
+            from_bf16 = buf.dtype == torch.bfloat16                          # the gather launch converts back to float32
+            s_inner = int(np.prod(inner_shape)) * buf.element_size()         # ring side
             shape = (n_t, B) + inner_shape if time_major else (B, n_t) + inner_shape
-            dst = torch.empty(shape, dtype=buf.dtype, device=self.device)
+            dst = torch.empty(shape, dtype=torch.float32 if from_bf16 else buf.dtype, device=self.device)
+            inner = int(np.prod(inner_shape)) * dst.element_size()           # batch side
             out[key] = dst
             if B == 0 or n_t == 0:
                 continue
-            descs.append(N.CopyDesc(src=buf.data_ptr(), dst=dst.data_ptr(), src_ep_stride=buf.shape[1] * inner,
-                                    src_t_stride=inner, dst_ep_stride=inner if time_major else n_t * inner,
-                                    dst_t_stride=B * inner if time_major else inner, n_t=n_t, inner_bytes=inner))
+            descs.append(N.CopyDesc(src=buf.data_ptr(), dst=dst.data_ptr(), src_ep_stride=buf.shape[1] * s_inner,
+                                    src_t_stride=s_inner, dst_ep_stride=inner if time_major else n_t * inner,
+                                    dst_t_stride=B * inner if time_major else inner, n_t=n_t, inner_bytes=s_inner,
+                                    convert=2 if from_bf16 else 0))
         if self.shared_obs:
             # obs[b, t, i, :] <- state[b, t, :] for every agent i: one more strided copy per agent in the same launch
             n_t, Nn, sbuf = max_len + 1, self.n_agents, self.buffers["state"]

@@ -231,3 +231,53 @@ def check_shared_obs_replay(device, lib, n_agents=2, seed=1):
     bad = types.SimpleNamespace(**{**vars(args), "obs_shape": S + 1})
     with pytest.raises(ValueError):
         EpisodeReplayBuffer(bad, device=device, _lib=lib, shared_obs=True)
+
+
+def check_hidden_bf16_replay(device, lib, seed=2):
+    """hidden_bf16=True: the ring keeps hidden_state as bfloat16 (the store / gather launches convert, round to nearest
+    even); sample() still returns float32 with every other key bit-identical to the full-format ring, and the states
+    within the stated bound of the option: what torch's own float32 -> bfloat16 cast gives (relative error <= 2^-9).
+    Both store paths, both layouts, a width that is not a multiple of four (scalar conversion path)."""
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    for H in (64, 67):
+        T, Nn, S, A = 5, 2, 12, 5
+        args = types.SimpleNamespace(buffer_size=9, episode_limit=T, n_actions=A, n_agents=Nn, state_shape=S, obs_shape=S,
+                                     rnn_hidden_dim=H, use_cuda=True, device=device)
+        full = EpisodeReplayBuffer(args, device=device, _lib=lib)
+        lean = EpisodeReplayBuffer(args, device=device, _lib=lib, hidden_bf16=True, shared_obs=True)
+        assert lean.buffers["hidden_state"].dtype == torch.bfloat16
+        assert full.bytes_per_episode() - lean.bytes_per_episode() == (T + 1) * Nn * (H * 2 + S * 4)
+        gen = torch.Generator().manual_seed(seed)
+        def mk(n_eps):
+            st = torch.randn(T + 1, n_eps, S, generator=gen)
+            hs = torch.randn(T + 1, n_eps, Nn, H, generator=gen) * 3.0
+            hs[0, 0, 0, :4] = torch.tensor([0.0, -0.0, 1e-30, 65504.0])
+            return {"state": st, "obs": st[:, :, None, :].expand(T + 1, n_eps, Nn, S).contiguous(),
+                    "actions_discrete": torch.randint(0, A, (T, n_eps, Nn, 1), generator=gen, dtype=torch.int32),
+                    "actions_continuous": torch.rand(T, n_eps, Nn, 1, generator=gen),
+                    "avail_actions": torch.randint(0, 2, (T + 1, n_eps, Nn, A), generator=gen, dtype=torch.uint8),
+                    "reward": torch.randn(T, n_eps, 1, generator=gen),
+                    "terminated": torch.randint(0, 2, (T, n_eps, 1), generator=gen, dtype=torch.uint8),
+                    "hidden_state": hs}
+        for n_eps in (6, 5):                                   # the second store wraps the ring
+            tr = {k: v.to(device) for k, v in mk(n_eps).items()}
+            full.store_rollout(tr)
+            lean.store_rollout(tr)
+        L = 3
+        ep = mk(1)
+        host = {k: [v[: (L + 1 if k in ("state", "obs", "avail_actions", "hidden_state") else L), 0].numpy()] for k, v in ep.items()}
+        full.store_episode(host)
+        lean.store_episode(host)
+        for time_major in (False, True):
+            for idx in (np.array([2, 0, 8, 3]), np.array([3])):
+                a, b = full.gather(idx, time_major=time_major), lean.gather(idx, time_major=time_major)
+                assert list(a) == list(b)
+                for k in a:
+                    if k == "max_seq_len":
+                        assert a[k] == b[k]
+                    elif k == "hidden_state":
+                        assert b[k].dtype == torch.float32 and b[k].shape == a[k].shape
+                        assert torch.equal(b[k], a[k].to(torch.bfloat16).to(torch.float32)), "round to nearest even, as torch casts"
+                        assert bool(((b[k] - a[k]).abs() <= a[k].abs() * 2.0 ** -8 + 1e-37).all())
+                    else:
+                        assert torch.equal(a[k], b[k]), k

@@ -27,3 +27,7 @@ def test_replay_rollout_roundtrip():
 @pytest.mark.parametrize("n_agents", [2, 8])
 def test_shared_obs_replay(n_agents):
     LC.check_shared_obs_replay("cpu", emul_lib(), n_agents=n_agents)
+
+
+def test_hidden_bf16_replay():
+    LC.check_hidden_bf16_replay("cpu", emul_lib())

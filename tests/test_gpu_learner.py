@@ -131,3 +131,41 @@ def test_qhead_repack_equals_full_repack():
 @pytest.mark.parametrize("n_agents", [2, 8])
 def test_shared_obs_replay(n_agents):
     LC.check_shared_obs_replay("cuda", lib(), n_agents=n_agents)
+
+
+def test_hidden_bf16_replay():
+    LC.check_hidden_bf16_replay("cuda", lib())
+
+
+def test_hidden_bf16_effect_on_a_train_step():
+    """What the opt-in BF16 hidden_state ring costs the learner: one train step on the same episodes from a float32
+    ring and from a bfloat16 ring.  Stated bound of the option: loss and Q_tot means within 1 % (the stored states
+    carry up to 2^-9 relative rounding error; the double-DQN targets do not read them at all)."""
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.core.qmix import QMixLearner
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    B, T, Nn, A, S, H = 32, 100, 2, 5, 24, 128
+    args = types.SimpleNamespace(n_agents=Nn, n_actions=A, state_shape=S, obs_shape=S, rnn_hidden_dim=H, actor_hidden_dim=128,
+                                 mixing_embed_dim=64, hyper_hidden_dim=128, epsilon_start=1.0, epsilon_finish=0.05,
+                                 epsilon_anneal_time=1000, gamma=0.99, lr=5e-6, grad_norm_clip=1.0, target_update_interval=200,
+                                 use_cuda=True, device="cuda", seed=0, buffer_size=B, episode_limit=T, batch_size=B)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    traj = {"state": rn(T + 1, B, S), "obs": rn(T + 1, B, Nn, S),
+            "actions_discrete": torch.randint(0, A, (T, B, Nn, 1), device="cuda", generator=g, dtype=torch.int32),
+            "actions_continuous": torch.rand(T, B, Nn, 1, device="cuda", generator=g),
+            "avail_actions": torch.ones(T + 1, B, Nn, A, dtype=torch.uint8, device="cuda"),
+            "reward": rn(T, B, 1), "terminated": torch.zeros(T, B, 1, dtype=torch.uint8, device="cuda"),
+            "hidden_state": rn(T + 1, B, Nn, H) * 0.5}
+    stats = []
+    for bf16 in (False, True):
+        torch.manual_seed(42)
+        mac = BasicMAC(S, args)
+        learner = QMixLearner(mac, args)
+        buf = EpisodeReplayBuffer(args, device="cuda", hidden_bf16=bf16)
+        buf.store_rollout(traj)
+        stats.append(learner.train(buf.gather(np.arange(B), time_major=True), {}))
+    print("\nfloat32 ring:", stats[0], "\nbfloat16 ring:", stats[1])
+    for k in ("loss", "eval_qtot_avg", "target_qtot_avg"):
+        np.testing.assert_allclose(stats[1][k], stats[0][k], rtol=1e-2, atol=1e-3, err_msg=k)
+    assert stats[1]["target_qtot_avg"] == stats[0]["target_qtot_avg"]      # the unrolls start from zeros: no stored state involved
