@@ -164,7 +164,9 @@ def test_hidden_bf16_effect_on_a_train_step():
         learner = QMixLearner(mac, args)
         buf = EpisodeReplayBuffer(args, device="cuda", hidden_bf16=bf16)
         buf.store_rollout(traj)
-        stats.append(learner.train(buf.gather(np.arange(B), time_major=True), {}))
+        batch = buf.gather(np.arange(B), time_major=True)
+        batch["time_major"] = True
+        stats.append(learner.train(batch, {}))
     print("\nfloat32 ring:", stats[0], "\nbfloat16 ring:", stats[1])
     for k in ("loss", "eval_qtot_avg", "target_qtot_avg"):
         np.testing.assert_allclose(stats[1][k], stats[0][k], rtol=1e-2, atol=1e-3, err_msg=k)
