@@ -26,6 +26,7 @@
 #include "agent_tc_common.cuh"
 #include "env_step2.cuh"
 #ifndef MACJD_TEST_HOST_EMULATION
+#include <type_traits>
 #include <stdlib.h>
 #include <cuda.h>            // CUtensorMap (type and enums only; the encoder is fetched through the runtime)
 #endif
@@ -895,38 +896,45 @@ agent_forward_tc2_kernel(const __grid_constant__ T2Args p) {
       fence_after_sync();
       EP_STAMP(9);
       if (!kBigA) {
-        float acc[8], pa[8];
+        // NS action slots: the reference scenario has 5 actions (2 radars x {suppress, deceive} + idle), and the tail is
+        // 4 FP32 instructions per (unit, slot) -- three of eight slots were computed for nothing
+        auto q_tail = [&](auto ns_tag) {
+          constexpr int NS = decltype(ns_tag)::value;
+          float acc[NS], pa[NS];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[j] = 0.f; pa[j] = (j < A) ? Ps[j * kTcRows + r] : 0.f; }
-        for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
-          float v[16];
-          tmem_ld16_nowait(tl + (mode == 2 ? kT2ColHn : kT2ColQ) + (uint32_t)c0, v);
-          tmem_ld_wait();
-          reg_fence(v);
+          for (int j = 0; j < NS; ++j) { acc[j] = 0.f; pa[j] = (j < A) ? Ps[j * kTcRows + r] : 0.f; }
+          for (int c0 = 0; c0 < kT2Upt; c0 += 16) {
+            float v[16];
+            tmem_ld16_nowait(tl + (mode == 2 ? kT2ColHn : kT2ColQ) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            reg_fence(v);
 #pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            const int u = ub + c0 + n;
-            const float4 qc = S.c.q_c[u];
-            const float4 wl = S.c.w1a[2 * u], wh = S.c.w1a[2 * u + 1];
-            const float pre = v[n] + qc.x;
-            const float wa[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
+            for (int n = 0; n < 16; ++n) {
+              const int u = ub + c0 + n;
+              const float4 qc = S.c.q_c[u];
+              const float4 wl = S.c.w1a[2 * u], wh = NS > 4 ? S.c.w1a[2 * u + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float pre = v[n] + qc.x;
+              const float wa[8] = {wl.x, wl.y, wl.z, wl.w, wh.x, wh.y, wh.z, wh.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(qc.z, fmaxf(fmaf(pa[j], qc.y, pre + wa[j]), 0.f), acc[j]);
-          }
-        }
-        epi_bar_sync();                 // every thread has read its Ps before red is reused
-#pragma unroll
-        for (int j = 0; j < 8; ++j) S.red[part][j][r] = acc[j];
-        epi_bar_sync();
-        if (part == 0)
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < A) {
-              float sum = bq2;
-#pragma unroll
-              for (int pp = 0; pp < kT2Parts; ++pp) sum += S.red[pp][j][r];
-              Qs[j * kTcRows + r] = sum;
+              for (int j = 0; j < NS; ++j) acc[j] = fmaf(qc.z, fmaxf(fmaf(pa[j], qc.y, pre + wa[j]), 0.f), acc[j]);
             }
+          }
+          epi_bar_sync();                 // every thread has read its Ps before red is reused
+#pragma unroll
+          for (int j = 0; j < NS; ++j) S.red[part][j][r] = acc[j];
+          epi_bar_sync();
+          if (part == 0)
+#pragma unroll
+            for (int j = 0; j < NS; ++j)
+              if (j < A) {
+                float sum = bq2;
+#pragma unroll
+                for (int pp = 0; pp < kT2Parts; ++pp) sum += S.red[pp][j][r];
+                Qs[j * kTcRows + r] = sum;
+              }
+        };
+        if (A <= 5) q_tail(std::integral_constant<int, 5>());
+        else q_tail(std::integral_constant<int, 8>());
       } else {
         auto q_tail_big = [&](const float4* w1, auto ld) {
         // this thread's 32 units of the shared hidden product stay in registers; 8 actions per pass over them
