@@ -49,8 +49,8 @@ elif which.startswith("agent"):
 elif which.startswith("env"):
     from macjd_b200.simulation.environment import ElectromagneticEnvironment
     from macjd_b200.simulation.scenario import default_spec, scaled_spec
-    if which == "env_c2_1m":
-        n, J, R, K = 1 << 20, 2, 2, 1
+    if which in ("env_c2_1m", "env_c2"):
+        n, J, R, K = (1 << 20) if which == "env_c2_1m" else 4096, 2, 2, 1
         spec = default_spec(n)
     else:
         n, J, R, K = (65536 if which == "env_c3_64k" else 8192), 8, 16, 4
