@@ -249,6 +249,156 @@ def cpu_reference_classes_run(n_envs=32, steps=30):
         sys.modules.update(saved_mods)
 
 
+def _ref_env_worker(conn, RefEnv, cfg, n_local, n_agents, seed):
+    """Child of cpu_reference_parallel_run (forked: the reference modules are already imported): steps its share of
+    unmodified reference env objects on one core; an env that terminates is reset, as the reference runner does."""
+    import contextlib
+    import io
+    try:
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            envs = [RefEnv(cfg) for _ in range(n_local)]
+            for e in envs:
+                e.reset()
+        conn.send("ready")
+        while True:
+            msg = conn.recv()
+            if msg is None:
+                break
+            with contextlib.redirect_stdout(io.StringIO()):
+                if isinstance(msg, tuple):
+                    a, p = msg
+                    for i, e in enumerate(envs):
+                        _, _, terminated, _ = e.step([(int(a[i, j]), float(p[i, j])) for j in range(n_agents)])
+                        if terminated:
+                            e.reset()
+                obs = np.array([e.get_obs() for e in envs], dtype=np.float32)
+                avail = np.array([e.get_avail_actions() for e in envs], dtype=np.int64)
+            conn.send((obs, avail))
+    except Exception as e:                          # the parent reports it and falls back
+        try:
+            conn.send(RuntimeError(f"{type(e).__name__}: {e}"))
+        except Exception:
+            pass
+    finally:
+        conn.close()
+
+
+def cpu_reference_parallel_run(n_envs, steps, warmup=2):
+    """kind = "reference" on ALL host cores: n_envs unmodified reference
+    ElectromagneticEnvironment objects (baseline/_ref), split over one forked worker process per core and stepped in
+    each worker's Python loop, + the reference BasicMAC.select_actions at batch n_envs on all torch threads --
+    the loop body of the reference's runners/episode_runner.py:49-119 for the SAME workload the B200 arm steps."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "simulation")):
+        return {"unavailable": "baseline/_ref (copy of the reference sources) is not present on this box"}
+    import contextlib
+    import io
+    import multiprocessing as mp
+    import torch
+    try:
+        n_cores = max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        n_cores = max(1, os.cpu_count() or 1)
+    n_workers = max(1, min(n_cores, n_envs))
+    cwd, saved_path = os.getcwd(), list(sys.path)
+    saved_mods = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("core", "simulation", "utils", "runners")}
+    procs, conns = [], []
+    try:
+        os.chdir(ref)                               # the reference resolves config/*.yaml against the cwd
+        for k in saved_mods:
+            del sys.modules[k]
+        sys.path.insert(0, ref)
+        with contextlib.redirect_stdout(io.StringIO()):
+            import yaml
+            from simulation.environment import ElectromagneticEnvironment as RefEnv
+            from core.mac import BasicMAC as RefMAC
+            with open(os.path.join(ref, "config", "default.yaml")) as f:
+                cfg = types.SimpleNamespace(**yaml.safe_load(f))
+            cfg.device, cfg.use_cuda = "cpu", False
+            info = RefEnv(cfg).get_env_info()
+        cfg.n_agents, cfg.n_actions = info["n_agents"], info["n_actions"]
+        cfg.state_shape, cfg.obs_shape, cfg.episode_limit = info["state_shape"], info["obs_shape"], info["episode_limit"]
+        # workers first (fork), before this process runs any multi-threaded torch work
+        ctx = mp.get_context("fork")
+        share = [n_envs // n_workers + (1 if i < n_envs % n_workers else 0) for i in range(n_workers)]
+        for i, n_local in enumerate(share):
+            parent, child = ctx.Pipe()
+            pr = ctx.Process(target=_ref_env_worker, args=(child, RefEnv, cfg, n_local, cfg.n_agents, 1000 + i), daemon=True)
+            pr.start()
+            child.close()
+            procs.append(pr)
+            conns.append(parent)
+
+        def recv(c):
+            if not c.poll(300.0):
+                raise RuntimeError("a reference env worker did not answer within 300 s")
+            m = c.recv()
+            if isinstance(m, Exception):
+                raise m
+            return m
+
+        for c in conns:
+            recv(c)                                 # "ready": envs constructed and reset
+        cores = _all_threads()
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            mac = RefMAC(info["obs_shape"], cfg)
+            mac.init_hidden(n_envs)
+        offs = np.cumsum([0] + share)
+
+        def gather(send):
+            for i, c in enumerate(conns):
+                c.send(send(i))
+            parts = [recv(c) for c in conns]
+            return (torch.from_numpy(np.concatenate([p[0] for p in parts])),
+                    torch.from_numpy(np.concatenate([p[1] for p in parts])))
+
+        obs, avail = gather(lambda i: "views")
+        t_mac = 0.0
+
+        def one_step(t, obs, avail):
+            nonlocal t_mac
+            t0 = time.perf_counter()
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                a, p = mac.select_actions(obs, avail, t, test_mode=False)
+            a, p = a.squeeze(-1).numpy(), p.squeeze(-1).numpy()
+            t_mac += time.perf_counter() - t0
+            return gather(lambda i: (a[offs[i]:offs[i + 1]], p[offs[i]:offs[i + 1]]))
+
+        for t in range(warmup):
+            obs, avail = one_step(t, obs, avail)
+        t_mac = 0.0
+        t0 = time.perf_counter()
+        for t in range(steps):
+            obs, avail = one_step(warmup + t, obs, avail)
+        dt = time.perf_counter() - t0
+        return {"value": n_envs * cfg.n_agents * steps / dt, "unit": "env-agent steps/s", "cores": n_workers, "kind": "reference",
+                "ms_per_step": dt / steps * 1e3, "ms_per_step_select_actions": t_mac / steps * 1e3,
+                "sample": f"{steps} timesteps of the same workload ({n_envs} envs x {cfg.n_agents} agents): {n_envs} unmodified reference "
+                          f"ElectromagneticEnvironment objects in {n_workers} worker processes (one per host core, {share[0]} envs "
+                          f"each, stepped in the worker's Python loop; terminated envs reset) + the reference BasicMAC.select_actions "
+                          f"at batch {n_envs} ({cores} torch threads); host has {os.cpu_count()} cores"}
+    except Exception as e:                         # say why instead of failing the bench
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    finally:
+        for c in conns:
+            try:
+                c.send(None)
+                c.close()
+            except Exception:
+                pass
+        for pr in procs:
+            pr.join(timeout=5.0)
+            if pr.is_alive():
+                pr.terminate()                     # (exactly the process this function started)
+        os.chdir(cwd)
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k.split(".")[0] in ("core", "simulation", "utils", "runners")]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+
+
 def cpu_learner_run(agent_sd, mixer_sd, batch, n_agents, embed, steps, B, T, label):
     """The oracle port of QMixLearner.train (eager PyTorch autograd, all host threads)."""
     import torch
@@ -274,16 +424,24 @@ def run_reference(args):
     world = max(1, args.gpus)
     n_total = args.n_envs * world
     steps, warmup = min(args.steps, max(4, 200 // world)), max(min(args.warmup, 3), 1)
-    base = cpu_baseline_run(steps, warmup, n_envs=n_total)
-    ref = cpu_reference_classes_run()
-    line = {"impl": "reference", "metric": "env_agent_steps_per_sec", "value": base["value"], "unit": "env-agent steps/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_step"],
+    # headline: the UNMODIFIED reference classes on every host core (forked first: no torch thread pool exists yet);
+    # beside it the oracle port (a much stronger CPU baseline: the env step vectorised over the envs in NumPy) and the
+    # reference's own single-process loop
+    ref_all = cpu_reference_parallel_run(n_total, steps, warmup)
+    port = cpu_baseline_run(steps, warmup, n_envs=n_total)
+    port = {k: port[k] for k in ("value", "unit", "cores", "kind", "ms_per_step", "sample")}
+    ref_one = cpu_reference_classes_run()
+    head = ref_all if "value" in ref_all else port
+    line = {"impl": "reference", "metric": "env_agent_steps_per_sec", "value": head["value"], "unit": "env-agent steps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": head["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 env + f32 nets",
             "data": "synthetic",
             "config": bench_config(args.n_envs),
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "reference_classes": ref,
-            "e2e": {"value": base["value"], "unit": "env-agent steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {k: head[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "port": port,
+            "reference_all_cores": ref_all,
+            "reference_classes": ref_one,
+            "e2e": {"value": head["value"], "unit": "env-agent steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -701,6 +859,18 @@ def main():
         batch = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in buf.sample(LEARNER_B).items()}
         cpu["learner"] = cpu_learner_run(agent_sd, mixer_sd, batch, N_AGENTS, 64, 2, LEARNER_B, LEARNER_T, "C1 dims")
         cpu["reference_classes"] = cpu_reference_classes_run()
+        # the unmodified reference classes on every host core, in a child interpreter (its worker processes are forked,
+        # which this process -- CUDA context, NCCL, poller thread -- should not do)
+        try:
+            env_ = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+            env_["CUDA_VISIBLE_DEVICES"] = ""
+            out = subprocess.run([sys.executable, "-c", "import json, bench; print('REF_ALL ' + json.dumps("
+                                  f"bench.cpu_reference_parallel_run({n_envs}, 12, 2)))"], cwd=ROOT, env=env_,
+                                 capture_output=True, text=True, timeout=900)
+            got = [ln[8:] for ln in out.stdout.splitlines() if ln.startswith("REF_ALL ")]
+            cpu["reference_all_cores"] = json.loads(got[-1]) if got else {"unavailable": (out.stderr or "no output")[-300:]}
+        except Exception as e:
+            cpu["reference_all_cores"] = {"unavailable": f"{type(e).__name__}: {e}"}
     line["cpu_baseline"] = cpu
     del runner, learner, buf, env, mac
     torch.cuda.empty_cache()
