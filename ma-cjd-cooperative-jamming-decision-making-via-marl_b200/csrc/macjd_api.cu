@@ -13,6 +13,7 @@
 #include "replay.cuh"
 #include "learner.cuh"
 #include "agent_unroll.cuh"
+#include "gru_rec_rows.cuh"
 #include "tc05.cuh"
 
 #include <stdio.h>
@@ -134,6 +135,9 @@ int macjd_agent_forward(const macjd_ctx* ctx, const macjd_agent_weights* w, cons
   if (io->part == 2 && (io->n_steps != 1 || !io->hidden)) return MACJD_ERR_INVALID_ARG;
   if (io->part == 3 && (io->n_steps != 1 || !io->gate_x)) return MACJD_ERR_INVALID_ARG;
   if (io->part == 4 && !io->gate_x) return MACJD_ERR_INVALID_ARG;
+  // the recurrence of a time-unrolled pass over FEW rows (a learner batch): rows split over CTAs that keep
+  // rnn.weight_hh in shared memory (gru_rec_rows.cuh) instead of one CTA pair working through every step
+  if (macjd::rec_rows_supported(*w, *io)) return finish(ctx, macjd::rec_rows_launch(ctx, *w, *io));
 #ifndef MACJD_TEST_HOST_EMULATION
   if (io->path != 1 && macjd::tc::agent_tc_supported(*w)) {
     if (io->n_rows < 0 || io->n_steps < 1 || (!io->obs && io->part != 4)) return MACJD_ERR_INVALID_ARG;

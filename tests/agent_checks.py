@@ -149,6 +149,41 @@ def check_unroll_against_oracle(device, lib=None, O=24, A=5, H=128, AH=128, Nn=2
     assert_as_accurate(out["hidden"].cpu().numpy(), h.numpy(), h64.numpy(), "final hidden", k=k, rtol=rtol)
 
 
+def check_recurrence_rows_against_float64(device, lib=None, M=11, T=7, seed=5, path=0, with_initial_state=False, rtol=1e-5):
+    """The recurrence launch of a time-unrolled pass (macjd_agent_forward, io.part == 4) on given input products:
+    gate_x [T, M, 3, H] in, every step's hidden state out, against a float64 GRU (core/networks.py:101-129 unrolled
+    as core/qmix.py:129-147 does).  Few rows run on csrc/gru_rec_rows.cuh (rows split over CTAs, FP32 SIMT); the
+    bound is the FP32 one."""
+    from macjd_b200 import _native as N
+    O, A, H = 24, 5, 128
+    mac, args = random_agent(seed, O, A, H, 128, 2, device, lib)
+    agent, dev = mac.agent, mac.device
+    rng = np.random.default_rng(seed)
+    gx = (rng.standard_normal((T, M, 3, H)) * 1.5).astype(np.float32)
+    h0 = (rng.standard_normal((M, H)) * 0.5).astype(np.float32) if with_initial_state else np.zeros((M, H), np.float32)
+    gx_t = torch.from_numpy(gx).to(dev)
+    hidden = torch.from_numpy(h0.copy()).to(dev)
+    hs = torch.full((T, M, H), float("nan"), dtype=torch.float32, device=dev)
+    io = N.AgentIO(n_rows=M, n_steps=T, hidden=N.ptr(hidden), hidden_zero_init=0 if with_initial_state else 1,
+                   hidden_seq=N.ptr(hs), gate_x=N.ptr(gx_t), part=4, path=path, test_mode=1, tile_rows=0)
+    agent.lib().call("macjd_agent_forward", agent._ctx(), agent.packed().cstruct(), io)
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    sd = {k: v.detach().cpu().double().numpy() for k, v in agent.state_dict().items()}
+    w_hh, b_ih, b_hh = sd["rnn.weight_hh"], sd["rnn.bias_ih"], sd["rnn.bias_hh"]
+    h = h0.astype(np.float64)
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    for t in range(T):
+        gh = h @ w_hh.T + b_hh
+        g = gx[t].astype(np.float64)
+        r = sig(g[:, 0] + b_ih[:H] + gh[:, :H])
+        z = sig(g[:, 1] + b_ih[H:2 * H] + gh[:, H:2 * H])
+        n = np.tanh(g[:, 2] + b_ih[2 * H:] + r * gh[:, 2 * H:])
+        h = (1.0 - z) * n + z * h
+        np.testing.assert_allclose(hs[t].cpu().numpy(), h, rtol=rtol, atol=2e-6 * (t + 1), err_msg=f"h t={t}")
+    np.testing.assert_array_equal(hidden.cpu().numpy(), hs[T - 1].cpu().numpy())
+
+
 def check_device_rng_selection(device, lib=None):
     """Without injected draws the kernel's Philox stream decides: reproduce it with the
     oracle's Philox and check the epsilon test and the uniform-over-available draw."""

@@ -332,3 +332,38 @@ def test_recurrence_launch_matches_per_step_launches(H, AH, B, T, monkeypatch):
         assert decidable.float().mean() > 0.9
         if init == "given" and "hidden" in a and a["hidden"] is not None:
             assert (a["hidden"] - b["hidden"]).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("M,T,h0", [(64, 100, False), (3, 5, True), (1, 2, False), (1184, 3, True), (130, 9, False)])
+def test_recurrence_rows_kernel_vs_float64(M, T, h0):
+    """csrc/gru_rec_rows.cuh (io.part == 4 with few rows: the learner's unrolls at the reference batch, M = 64 x T = 100):
+    rows split over CTAs, rnn.weight_hh in shared memory, FP32 FMAs -- against a float64 GRU on the same input products."""
+    AC.check_recurrence_rows_against_float64("cuda", None, M=M, T=T, with_initial_state=h0)
+
+
+@pytest.mark.parametrize("M,T", [(64, 100), (37, 6), (600, 4)])
+def test_recurrence_rows_kernel_matches_pair_kernel(M, T, monkeypatch):
+    """The same time-unrolled call (input pre-pass, recurrence, heads) with the recurrence on the row-split FP32 kernel
+    (default for few rows) and on the CTA-pair tcgen05 kernel (MACJD_REC_ROWS_MAX=0): FP32 against 3xTF32 products --
+    stated bound 2e-5 absolute on h in [-1, 1] after T steps, Q within 1e-4 of scale, identical greedy actions where
+    the margin exceeds 1e-4 of scale."""
+    O, A, H = 24, 5, 128
+    mac, _ = AC.random_agent(9, O, A, H, 128, 2, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    obs = torch.randn(T, M, O, device="cuda", generator=g)
+    outs = {}
+    for limit in ("0", "100000"):
+        monkeypatch.setenv("MACJD_REC_ROWS_MAX", limit)
+        outs[limit] = mac.agent.run(obs, None, n_steps=T, zero_init=True, want_q=True, want_greedy=True, want_hidden_seq=True, path=0)
+    torch.cuda.synchronize()
+    a, b = outs["100000"], outs["0"]
+    assert not torch.equal(a["hidden_seq"], b["hidden_seq"])          # (two different kernels ran)
+    dh = (a["hidden_seq"] - b["hidden_seq"]).abs().max().item()
+    scale = max(1.0, b["q_all"].abs().max().item())
+    dq = (a["q_all"] - b["q_all"]).abs().max().item() / scale
+    assert dh < 2e-5, dh
+    assert dq < 1e-4, dq
+    srt = torch.sort(b["q_all"], dim=-1).values
+    decidable = (srt[..., -1] - srt[..., -2]) > 1e-4 * scale
+    assert decidable.float().mean().item() > 0.9
+    assert torch.equal(a["greedy"][decidable], b["greedy"][decidable])
