@@ -476,6 +476,16 @@ MACJD_API int macjd_qhead_backward(const macjd_ctx* ctx, const macjd_qhead_dims*
                                    const float* dq, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
                                    float* scratch, size_t scratch_floats);
 
+/* After the optimiser step (core/qmix.py:197-200; macjd_clip_adam updates the nn.Parameters in place) the packed copy
+ * of the one trained agent layer, fc2_q_head (core/qmix.py:178), is refreshed by ONE launch: w1 [H][H + A + 1], b1 [H],
+ * w2 [H], b2 [1] (PyTorch layout) -> w's fields wqt, bq1, w1a, w1p, w2, bq2 (written through their pointers) and,
+ * optionally (H = 128, pointers may be NULL): tc_chunks = the last H / tc_kc chunks of w->tc_chunks (q.0[:, :H];
+ * [chunk][hi | lo][128 tc_kc]), tc_q_c = the constant block's [128][4] (bq1, w1p, w2, -) rows, tc_w1a = its
+ * [128][tc_w1a_stride] one-hot-column table.  Bit-identical to re-packing everything on the host. */
+MACJD_API int macjd_qhead_repack(const macjd_ctx* ctx, const macjd_agent_weights* w, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, float* tc_chunks, int32_t tc_kc, float* tc_q_c,
+                                 float* tc_w1a, int32_t tc_w1a_stride);
+
 /* out[i] = q_all[i][idx[i]] for i < n: the target network's Q at the eval network's greedy
  * action (core/qmix.py:147 torch.gather). */
 MACJD_API int macjd_gather_q(const macjd_ctx* ctx, int32_t n, int32_t n_actions, const float* q_all,

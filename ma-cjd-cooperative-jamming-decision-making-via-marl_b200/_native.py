@@ -168,6 +168,7 @@ class NativeLib:
             ("macjd_qhead_forward", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp]),
             ("macjd_qhead_forward_ws", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp, vp, C.c_size_t]),
             ("macjd_qhead_backward", C.c_int, [P(Ctx), P(QheadDims), P(AgentWeights), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz]),
+            ("macjd_qhead_repack", C.c_int, [P(Ctx), P(AgentWeights), vp, vp, vp, vp, vp, i32, vp, vp, i32]),
             ("macjd_gather_q", C.c_int, [P(Ctx), i32, i32, vp, vp, vp]),
             ("macjd_td_scratch_floats", sz, [i32]),
             ("macjd_td_loss", C.c_int, [P(Ctx), i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, sz]),

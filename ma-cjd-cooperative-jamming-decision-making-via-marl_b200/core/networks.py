@@ -162,6 +162,34 @@ class PackedAgentWeights:
         if self.buffer is None or self.buffer.device != agent.fc1.weight.device:
             return self.refresh(agent, force=True)
         H, A = self.H, self.A
+        q0, q2 = agent.fc2_q_head[0], agent.fc2_q_head[2]
+        if all(p_.dtype == torch.float32 and p_.is_contiguous() for p_ in (q0.weight, q0.bias, q2.weight, q2.bias)):
+            # ONE launch (include/macjd.h: macjd_qhead_repack) instead of ~20 tensor operations per train step
+            tc_chunks = tc_q_c = tc_w1a = None
+            kc = stride = 0
+            if self.tc_buffer is not None:
+                kc = self.tc_buffer.shape[-1] // 128
+                tc_chunks = self.tc_buffer[self.tc_buffer.shape[0] - H // kc:]
+                nb = self._tc_big_floats()
+                c = self.tc_flat[-(self.TC_CONST_FLOATS + nb):]
+                tc_q_c = c[512:1024]
+                if nb:
+                    stride = _ceil_to(A, 8)
+                    tc_w1a = c[self.TC_CONST_FLOATS + 128 * stride:]
+                else:
+                    stride, tc_w1a = 8, c[2432:3456]
+            agent.lib().callv("macjd_qhead_repack", agent._ctx(), self.cstruct(), q0.weight.detach(), q0.bias.detach(),
+                              q2.weight.detach(), q2.bias.detach(), tc_chunks, kc, tc_q_c, tc_w1a, stride)
+        else:
+            self._refresh_qhead_host(agent)
+        slots = self.__dict__.get("_slots")
+        if slots is not None:
+            self.versions = tuple([(m._parameters[k]._version, m._parameters[k].data_ptr()) for m, k in slots])
+        return self
+
+    def _refresh_qhead_host(self, agent):
+        """The same re-layout as tensor operations (parameters that are not contiguous float32)."""
+        H, A = self.H, self.A
         w1 = agent.fc2_q_head[0].weight.detach().float()             # [H, H + A + 1]
         self.view("wqt").copy_(w1[:, :H].t())
         self.view("bq1").copy_(agent.fc2_q_head[0].bias.detach())
@@ -176,10 +204,6 @@ class PackedAgentWeights:
             self.tc_buffer[-full.shape[0]:, 0].copy_(hi)
             self.tc_buffer[-full.shape[0]:, 1].copy_(full - hi)
             self._pack_tc_const(qhead_only=True)
-        slots = self.__dict__.get("_slots")
-        if slots is not None:
-            self.versions = tuple([(m._parameters[k]._version, m._parameters[k].data_ptr()) for m, k in slots])
-        return self
 
     @staticmethod
     def _umma_chunks(w, kc=16):

@@ -73,12 +73,27 @@ class QMixLearner:
             return N.torch_ctx(self.device)
         return N.Ctx(device=0, reserved=0, stream=None)
 
+    @staticmethod
+    def _param_slots(module):
+        """(owner module, parameter key, qualified name) of every parameter: collected once -- walking
+        named_parameters() costs ~0.1 ms per call, and a train step needs the trained tensors' addresses four
+        times; looking the Parameters up through their owner modules still sees replaced ones."""
+        slots = []
+        for prefix, m in module.named_modules():
+            for k, p_ in m._parameters.items():
+                if p_ is not None:
+                    slots.append((m, k, (prefix + "." if prefix else "") + k))
+        return slots
+
     def _trainable(self):
         """(tensor, name) in flat-bucket order: the Q-head, then every mixer parameter."""
-        agent_sd = dict(self.mac.agent.named_parameters())
-        out = [(agent_sd[k], "agent." + k) for k in TRAINED_AGENT_KEYS]
-        out += [(p, "mixer." + k) for k, p in self.eval_qmix_net.named_parameters()]
-        return out
+        sl = self.__dict__.get("_train_slots")
+        if sl is None or sl[0] is not self.mac.agent or sl[1] is not self.eval_qmix_net:
+            agent_slots = {n: (m, k) for m, k, n in self._param_slots(self.mac.agent)}
+            order = [agent_slots[k] + ("agent." + k,) for k in TRAINED_AGENT_KEYS]
+            order += [(m, k, "mixer." + n) for m, k, n in self._param_slots(self.eval_qmix_net)]
+            sl = self._train_slots = (self.mac.agent, self.eval_qmix_net, order)
+        return [(m._parameters[k], n) for m, k, n in sl[2]]
 
     def _ensure_opt_state(self):
         tr = self._trainable()
@@ -89,7 +104,7 @@ class QMixLearner:
             z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
             old = self._opt_state
             self._opt_state = {"sizes": sizes, "total": total, "grad": z(total + 8), "m": z(total), "v": z(total),
-                               "step": 0, "scal": z(4),
+                               "step": 0, "scal": z(4), "qhead_offsets": [int(x) for x in np.cumsum([0] + sizes[:3])],
                                "scratch": z(self.lib().lib.macjd_opt_scratch_floats())}
             if old is not None:
                 self._opt_state["m"].copy_(old["m"]); self._opt_state["v"].copy_(old["v"]); self._opt_state["step"] = old["step"]
@@ -97,21 +112,26 @@ class QMixLearner:
 
     def _mixer_struct(self, net=None, flat=None, offset=0):
         """macjd_mixer_params over a QMixer's parameters, or over views of a flat buffer."""
-        kw = {}
+        cache = self.__dict__.setdefault("_mixer_struct_cache", {})
         if net is not None:
-            sd = dict(net.named_parameters())
-            for f, k in zip(N.MIXER_FIELDS, N.MIXER_KEYS):
-                kw[f] = sd[k].data_ptr()
-        else:
-            names = [k for k, _ in self.eval_qmix_net.named_parameters()]
-            sizes = {k: p.numel() for k, p in self.eval_qmix_net.named_parameters()}
+            ent = cache.get(id(net))
+            if ent is None or ent[0] is not net:
+                by_name = {n: (m, k) for m, k, n in self._param_slots(net)}
+                ent = cache[id(net)] = (net, [by_name[k] for k in N.MIXER_KEYS], None, None)
+            ptrs = tuple([m._parameters[k].data_ptr() for m, k in ent[1]])
+            if ptrs != ent[2]:
+                ent = cache[id(net)] = (net, ent[1], ptrs, N.MixerParams(**dict(zip(N.MIXER_FIELDS, ptrs))))
+            return ent[3]
+        key = ("flat", flat.data_ptr(), offset)
+        st = cache.get(key)
+        if st is None:
+            sizes = {n: m._parameters[k].numel() for m, k, n in self._param_slots(self.eval_qmix_net)}
             offs, o = {}, offset
-            for k in names:
+            for k in sizes:                                   # (named_parameters order: the flat bucket's order)
                 offs[k] = o
                 o += sizes[k]
-            for f, k in zip(N.MIXER_FIELDS, N.MIXER_KEYS):
-                kw[f] = flat.data_ptr() + 4 * offs[k]
-        return N.MixerParams(**kw)
+            st = cache[key] = N.MixerParams(**{f: flat.data_ptr() + 4 * offs[k] for f, k in zip(N.MIXER_FIELDS, N.MIXER_KEYS)})
+        return st
 
     def _workspace(self, name, n_floats, dev):
         t = self._ws.get(name)
@@ -248,7 +268,7 @@ class QMixLearner:
         dq = f32(R * Nn)
         L.callv("macjd_mixer_backward", ctx, dims, eval_struct, q_taken, dq_tot, ws, ws_floats,
                 self._mixer_struct(flat=grad, offset=qh), dq)
-        o0, o1, o2, o3 = np.cumsum([0] + opt["sizes"][:3])
+        o0, o1, o2, o3 = opt["qhead_offsets"]
         L.callv("macjd_qhead_backward", ctx, qd, pk, hidden, a_d, a_c, hid, dq,
                 grad[o0:], grad[o1:], grad[o2:], grad[o3:], qs, qs.numel())
 
@@ -260,10 +280,14 @@ class QMixLearner:
         # 10. clip + Adam on the Q-head and the mixer (qmix.py:197-200)
         opt["step"] += 1
         tr = self._trainable()
-        tensors = N.OptTensors(count=len(tr), reserved=0)
-        for i, (p, _) in enumerate(tr):
-            tensors.param[i] = p.data_ptr()
-            tensors.numel[i] = p.numel()
+        ptrs = tuple([p.data_ptr() for p, _ in tr])
+        if opt.get("tensors_for") != ptrs:
+            tensors = N.OptTensors(count=len(tr), reserved=0)
+            for i, (p, _) in enumerate(tr):
+                tensors.param[i] = p.data_ptr()
+                tensors.numel[i] = p.numel()
+            opt["tensors_for"], opt["tensors"] = ptrs, tensors
+        tensors = opt["tensors"]
         debug = None
         if return_debug:
             debug = {"grad": grad[:total].clone(), "names": [n for _, n in tr], "sizes": list(opt["sizes"]),

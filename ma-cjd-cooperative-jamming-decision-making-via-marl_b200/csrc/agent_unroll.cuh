@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) gru_gates_kernel(const float* __restrict_
                                                         const float* __restrict__ h_prev, const float* __restrict__ brz,
                                                         const float* __restrict__ bin, const float* __restrict__ bhn, int M, int H,
                                                         float* __restrict__ h_out) {
-  grid_dependency_wait();
+  grid_dependency_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * H) return;
   const int row = idx / H, u = idx - row * H;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) qhead_all_kernel(const float* __restrict_
                                                         const float* __restrict__ w2, const float* __restrict__ bq2, int R, int H, int A,
                                                         float* __restrict__ q_all, int* __restrict__ greedy,
                                                         const int* __restrict__ sel, float* __restrict__ q_sel) {
-  grid_dependency_wait();
+  grid_dependency_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= R) return;
   const float b2 = bq2[0];

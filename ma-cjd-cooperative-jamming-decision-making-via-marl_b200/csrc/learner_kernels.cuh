@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ y,
                                                             float* __restrict__ xhat) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;   // whole warps exit together; no block-level sync below
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) mix_fwd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ b1, const float* __restrict__ wf,
                                                       const float* __restrict__ v, int R, int N, int E,
                                                       float* __restrict__ hidden, float* __restrict__ y) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(256) mix_bwd_kernel(const float* __restrict__ 
                                                       float* __restrict__ d_w1, float* __restrict__ d_b1,
                                                       float* __restrict__ d_wf, float* __restrict__ d_v,
                                                       float* __restrict__ dq) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) qhead_tail_fwd_kernel(float* __restrict__
                                                              const float* __restrict__ w2,
                                                              const float* __restrict__ b2, int R, int H, int A,
                                                              float* __restrict__ q) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) qhead_tail_bwd_kernel(float* __restrict__
                                                              const float* __restrict__ par,
                                                              const float* __restrict__ w2, int R, int H, int A,
                                                              float* __restrict__ xaug) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) qhead_tail_bwd_kernel(float* __restrict__
 // out[i] = q_all[i][idx[i]]   (i over rows x timesteps, q_all [.., A])
 __global__ void __launch_bounds__(256) gather_q_kernel(const float* __restrict__ q_all, const int* __restrict__ idx,
                                                        int n, int A, float* __restrict__ out) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int a = idx[i];
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) gather_q_kernel(const float* __restrict__
 constexpr int kColsumRows = 64;     // rows per partial block: each thread walks them serially, so short chunks, many blocks
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ X, const float* __restrict__ Y,
                                                              int R, int Cn, int ldx, float* __restrict__ part, int rows_per_chunk) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(R, r0 + rows_per_chunk);
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
 }
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int chunks, int Cn,
                                                            float* __restrict__ out) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cn) return;
   float s = 0.f;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kTdBlock) td_partial_kernel(const float* __res
                                                               const uint8_t* __restrict__ filled, float gamma, int R,
                                                               float* __restrict__ dy, float* __restrict__ targets_out,
                                                               float* __restrict__ part) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   __shared__ float red[4][kTdBlock / 32];
   const int r = blockIdx.x * kTdBlock + threadIdx.x;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kTdBlock) td_partial_kernel(const float* __res
   }
 }
 __global__ void td_final_kernel(const float* __restrict__ part, int blocks, float* __restrict__ sums) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   if (threadIdx.x < 4) {
     float s = 0.f;
     for (int k = 0; k < blocks; ++k) s += part[(size_t)k * 4 + threadIdx.x];
@@ -264,7 +264,7 @@ struct OptTable {
 };
 
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int n, float* __restrict__ part) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   __shared__ float red[8];
   float s = 0.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s = fmaf(g[i], g[i], s);
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 // sums[1] = sum(mask) (possibly all-reduced); scale = 1 / sum(mask)
 __global__ void clip_coef_kernel(const float* __restrict__ part, int blocks, const float* __restrict__ sums,
                                  float max_norm, float* __restrict__ scal) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int k = 0; k < blocks; ++k) s += (double)part[k];
@@ -299,7 +299,7 @@ __global__ void clip_coef_kernel(const float* __restrict__ part, int blocks, con
 __global__ void __launch_bounds__(256) adam_kernel(OptTable tab, const float* __restrict__ grad, float* __restrict__ m,
                                                    float* __restrict__ v, const float* __restrict__ scal, float lr,
                                                    float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int total = tab.offset[tab.count];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;

@@ -14,6 +14,7 @@
 #include "learner.cuh"
 #include "agent_unroll.cuh"
 #include "gru_rec_rows.cuh"
+#include "qhead_repack.cuh"
 #include "tc05.cuh"
 
 #include <stdio.h>
@@ -680,6 +681,20 @@ int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, cons
   if (!tensors || !grad || !m || !v || !sums || !scal) return MACJD_ERR_INVALID_ARG;
   return finish(ctx, macjd::clip_adam((cudaStream_t)ctx->stream, *tensors, grad, m, v, sums, max_norm, lr, beta1, beta2,
                                       eps, step, scal, scratch, scratch_floats));
+}
+
+int macjd_qhead_repack(const macjd_ctx* ctx, const macjd_agent_weights* w, const float* w1, const float* b1, const float* w2,
+                       const float* b2, float* tc_chunks, int32_t tc_kc, float* tc_q_c, float* tc_w1a, int32_t tc_w1a_stride) {
+  MACJD_ENTER(ctx);
+  if (!w) return MACJD_ERR_INVALID_ARG;
+  macjd::QheadRepackArgs a;
+  a.H = w->hidden; a.A = w->n_actions;
+  a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2;
+  // (the packed fields are const for the kernels that READ them; this is the one call that writes them)
+  a.wqt = const_cast<float*>(w->wqt); a.bq1 = const_cast<float*>(w->bq1); a.w1a = const_cast<float*>(w->w1a);
+  a.w1p = const_cast<float*>(w->w1p); a.w2p = const_cast<float*>(w->w2); a.bq2 = const_cast<float*>(w->bq2);
+  a.tc_chunks = tc_chunks; a.kc = tc_kc; a.tc_q_c = tc_q_c; a.tc_w1a = tc_w1a; a.tc_w1a_stride = tc_w1a_stride;
+  return finish(ctx, macjd::qhead_repack((cudaStream_t)ctx->stream, a));
 }
 
 int macjd_gemm(const macjd_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, int32_t ta, const float* B,

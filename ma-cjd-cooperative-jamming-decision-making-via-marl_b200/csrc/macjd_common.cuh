@@ -95,6 +95,15 @@ __device__ __forceinline__ void grid_launch_dependents() {
 #endif
 }
 
+// The learner's short kernels: let the NEXT kernel of the stream be launched right away -- its blocks are scheduled as
+// this grid's blocks retire and park in their own grid_dependency_wait() until this grid has completed and flushed --
+// then wait for the predecessor.  A train step at the reference batch is ~75 dependent launches of 3-20 us each; without
+// the early trigger a dependent is only launched when the last block of its predecessor exits (~2 us per hand-over).
+__device__ __forceinline__ void grid_dependency_sync() {
+  grid_launch_dependents();
+  grid_dependency_wait();
+}
+
 __device__ __forceinline__ float sigmoidf_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---------------------------------------------------------------- pipeline watchdog

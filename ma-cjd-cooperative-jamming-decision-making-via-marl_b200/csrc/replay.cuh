@@ -73,7 +73,7 @@ __device__ __forceinline__ void convert_rows(const macjd_copy_desc& k, int64_t s
 
 // grid = (n_eps, n_keys); one CTA copies one key of one episode
 __global__ void __launch_bounds__(256) replay_copy_kernel(const CopyArgs a) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int b = blockIdx.x;
   const macjd_copy_desc& k = a.key[blockIdx.y];
   const int64_t slot = a.idx ? a.idx[b] : b;

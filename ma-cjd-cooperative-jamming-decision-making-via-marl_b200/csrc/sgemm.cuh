@@ -34,7 +34,7 @@ struct GemmArgs {
 constexpr int kGM = 64, kGN = 64, kGK = 16;
 
 __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   __shared__ float As[kGK][kGM + 4];
   __shared__ float Bs[kGK][kGN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const GemmArgs g) {
 // C[m][n] = (accumulate ? C : 0) + sum_s partial[s][m][n]   (fixed order)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* partial, int splits, int M, int N,
                                                             float* C, int ldc, int accumulate) {
-  grid_dependency_wait();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= M * N) return;
   const int m = idx / N, n = idx - m * N;

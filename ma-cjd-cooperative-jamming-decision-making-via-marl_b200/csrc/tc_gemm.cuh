@@ -134,7 +134,7 @@ constexpr int kGtPackFloats = 2 * kGtTileFloats;                 // hi + lo of o
 inline size_t tc_pack_b_floats(int N, int K) { return (size_t)((N + kGtN - 1) / kGtN) * ((K + kGtK - 1) / kGtK) * kGtPackFloats; }
 
 __global__ void __launch_bounds__(256) tc_pack_b_kernel(const float* __restrict__ B, int ldb, int tb, int N, int K, float* __restrict__ out) {
-  grid_dependency_wait();               // (the previous GEMM of the stream may still be reading `out`)
+  grid_dependency_sync();               // (the previous GEMM of the stream may still be reading `out`)
   const int kchunks = (K + kGtK - 1) / kGtK;
   const int nt = blockIdx.x / kchunks, kc = blockIdx.x - nt * kchunks;
   const int r = threadIdx.x >> 1, kh = (threadIdx.x & 1) * 8;     // column of the tile, 8 of its 16 k
@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(256) tc_pack_b_kernel(const float* __restrict_
 
 template <bool kAContigK, bool kBContigK, bool kBPacked = false>
 __global__ void __launch_bounds__(kGtThreads, 2) tc_gemm_kernel(const GemmArgs g) {
+  grid_launch_dependents();             // (the next kernel of the stream may be launched; it waits for this grid before its first access)
   extern __shared__ __align__(1024) unsigned char gt_raw[];
   GtSmem& S = *reinterpret_cast<GtSmem*>(gt_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

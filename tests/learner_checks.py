@@ -281,3 +281,36 @@ def check_hidden_bf16_replay(device, lib, seed=2):
                         assert bool(((b[k] - a[k]).abs() <= a[k].abs() * 2.0 ** -8 + 1e-37).all())
                     else:
                         assert torch.equal(a[k], b[k]), k
+
+
+def check_qhead_repack(device, lib=None, O=24, A=5, H=128, AH=128):
+    """After the learner's in-place Adam step only fc2_q_head is re-packed, by ONE launch (macjd_qhead_repack): the packed
+    FP32 buffer, the tensor-core chunk buffer and its constant block must equal a full re-pack bit for bit, and so must
+    the host-side fallback of the same re-layout."""
+    import types
+    from macjd_b200.core.mac import BasicMAC
+    args = types.SimpleNamespace(n_agents=2, n_actions=A, rnn_hidden_dim=H, actor_hidden_dim=AH, epsilon_start=1.0,
+                                 epsilon_finish=0.05, epsilon_anneal_time=1000, seed=0, agent_kernel_path=0)
+    torch.manual_seed(3)
+    mac = BasicMAC(O, args, _lib=lib)
+    if device != "cpu":
+        mac.cuda()
+    pk = mac.agent.packed()
+    snap = lambda: (pk.buffer.clone(), None if pk.tc_flat is None else pk.tc_flat.clone())
+    with torch.no_grad():                       # what the clip+Adam kernel does: raw in-place writes, no version bump
+        for p in mac.agent.fc2_q_head.parameters():
+            p.data.add_(torch.randn_like(p) * 0.01)
+    before = snap()
+    mac.agent.packed_qhead()
+    part = snap()
+    assert not torch.equal(before[0], part[0])
+    pk._refresh_qhead_host(mac.agent)
+    host = snap()
+    mac.agent.packed(force=True)
+    full = snap()
+    for got, name in ((part, "kernel"), (host, "host fallback")):
+        assert torch.equal(got[0], full[0]), name
+        assert (got[1] is None) == (full[1] is None)
+        if full[1] is not None:
+            assert torch.equal(got[1], full[1]), name
+    return pk

@@ -41,8 +41,8 @@ def test_gemm_unroll_vs_oracle(H, AH, A, O, B, T):
     AC.check_unroll_against_oracle("cpu", emul_lib(), O=O, A=A, H=H, AH=AH, Nn=2, B=B, T=T, path=0)
 
 
-@pytest.mark.parametrize("M,T,h0", [(1, 3, False), (11, 7, True), (8, 2, False)])
+@pytest.mark.parametrize("M,T,h0", [(1, 3, False), (11, 7, True), (8, 2, False), (299, 2, True)])
 def test_recurrence_rows_kernel(M, T, h0):
     """csrc/gru_rec_rows.cuh: the recurrence of a learner-sized unroll (rows split over CTAs, weight_hh in shared memory);
-    ragged last CTA, zero and given initial state."""
+    ragged last CTA, zero and given initial state, 2 and 4 rows per CTA."""
     AC.check_recurrence_rows_against_float64("cpu", emul_lib(), M=M, T=T, with_initial_state=h0)

@@ -31,3 +31,9 @@ def test_shared_obs_replay(n_agents):
 
 def test_hidden_bf16_replay():
     LC.check_hidden_bf16_replay("cpu", emul_lib())
+
+
+@pytest.mark.parametrize("O,A,H,AH", [(24, 5, 128, 128), (176, 33, 128, 128), (39, 7, 64, 64)])
+def test_qhead_repack_equals_full_repack(O, A, H, AH):
+    """macjd_qhead_repack (one launch after the optimiser step) against the full re-pack and the host fallback."""
+    LC.check_qhead_repack("cpu", emul_lib(), O=O, A=A, H=H, AH=AH)

@@ -107,25 +107,12 @@ def test_learner_stress_dims_vs_oracle():
                                    rtol=1e-2, atol=1e-4 * 1e-2 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
 
 
-def test_qhead_repack_equals_full_repack():
-    """After the learner's in-place Adam step only fc2_q_head is re-packed (six fields + the last four
-    tensor-core chunks): both packed buffers must equal a full re-pack bit for bit."""
-    import copy
-    from macjd_b200.core.mac import BasicMAC
-    args = types.SimpleNamespace(n_agents=2, n_actions=5, rnn_hidden_dim=128, actor_hidden_dim=128, epsilon_start=1.0,
-                                 epsilon_finish=0.05, epsilon_anneal_time=1000, seed=0, agent_kernel_path=0)
-    torch.manual_seed(3)
-    mac = BasicMAC(24, args)
-    mac.cuda()
-    pk = mac.agent.packed()
-    assert pk.tc_buffer is not None
-    with torch.no_grad():                       # what the clip+Adam kernel does: raw in-place writes, no version bump
-        for p in mac.agent.fc2_q_head.parameters():
-            p.data.add_(torch.randn_like(p) * 0.01)
-    mac.agent.packed_qhead()
-    part = (pk.buffer.clone(), pk.tc_buffer.clone())
-    mac.agent.packed(force=True)
-    assert torch.equal(part[0], pk.buffer) and torch.equal(part[1], pk.tc_buffer)
+@pytest.mark.parametrize("O,A,H,AH,tc", [(24, 5, 128, 128, True), (176, 33, 128, 128, True), (24, 5, 256, 128, False), (39, 7, 64, 64, False)])
+def test_qhead_repack_equals_full_repack(O, A, H, AH, tc):
+    """After the learner's in-place Adam step only fc2_q_head is re-packed (six fields, the last tensor-core chunks and
+    the Q-head entries of the constant block, one launch): every packed buffer must equal a full re-pack bit for bit."""
+    pk = LC.check_qhead_repack("cuda", None, O=O, A=A, H=H, AH=AH)
+    assert (pk.tc_buffer is not None) == tc
 
 
 @pytest.mark.parametrize("n_agents", [2, 8])
