@@ -810,16 +810,23 @@ def main():
                  "env_only": {"value": world * M / r2["dt_env"], "unit": "env-agent steps/s", "us_per_launch": r2["dt_env"] * 1e6},
                  "act_only": {"value": world * M / r2["dt_agent"], "unit": "env-agent steps/s", "us_per_launch": r2["dt_agent"] * 1e6}})
 
-    def learner_bench(learner, buf, B, T, n_steps, dims, label):
-        """sample + train, all-reduce when N > 1; B = episodes per GPU"""
+    def learner_bench(learner, buf, B, T, n_steps, dims, label, sampled=False):
+        """sample + train, all-reduce when N > 1; B = episodes per GPU.  sampled: through QMixLearner.train_sampled, the call
+        the training loop makes (one GPU: the whole step as a replayed CUDA graph; data parallel: the same eager step)."""
         np.random.seed(1 + rank)
         for _ in range(3):
             learner.train(buf.sample(B, time_major=True), {})
+        if sampled:
+            for _ in range(3):               # eager (sizes the workspaces), capture + replay, replay
+                learner.train_sampled(buf, B, {})
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(n_steps):
-            stats = learner.train(buf.sample(B, time_major=True), {}, lazy_stats=True, check_actions=False)
+            if sampled:
+                stats = learner.train_sampled(buf, B, {})
+            else:
+                stats = learner.train(buf.sample(B, time_major=True), {}, lazy_stats=True, check_actions=False)
         ev1.record()
         barrier()
         dt_l = reduce_max(ev0.elapsed_time(ev1) * 1e-3) / n_steps
@@ -831,13 +838,16 @@ def main():
         pair = ag._pair_kernel_ok(ag.packed()) and ag.path in (0, 3)
         tc = ag.path in (0, 3)                   # pair kernel, or batched layers on the tcgen05 GEMM (macjd_agent_unroll)
         peak = tf32_peak if tc else fp32_peak
-        unroll_kernel = ("agent_forward_tc2_kernel (parts 3 + 4 + 2)" if pair else
+        unroll_kernel = (("agent_forward_tc2_kernel (parts 3 + 2) around gru_rec_rows_kernel (the recurrence of few rows: FP32, weight_hh on chip)"
+                          if B * N_ <= 1184 else "agent_forward_tc2_kernel (parts 3 + 4 + 2)") if pair else
                          "macjd_agent_unroll: batched layers on tc_gemm_kernel (tcgen05 3xTF32) + the recurrence as one gru_recurrence_tc2_kernel launch (CTA pairs, h in shared memory)" if tc else
                          "agent_forward_kernel (FP32 SIMT)")
         return {"train_episodes_per_sec": world * B / dt_l, "train_transitions_per_sec": world * B * (T - 1) / dt_l,
                 "ms_per_train_step": dt_l * 1e3, "batch_episodes_per_gpu": B, "episode_len": T, "last_loss": last_loss,
                 "includes": "replay sample (gather kernel) + 2 unrolls + mixers + TD + backward + clip/Adam"
-                            + (" + NCCL all-reduce" if world > 1 else ""),
+                            + (" + NCCL all-reduce" if world > 1 else "")
+                            + ("; issued as one replayed CUDA graph per step (QMixLearner.train_sampled)"
+                               if sampled and learner._graphable() else ""),
                 "roofline": {"bound": "tensor" if tc else "fp32", "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
                              "frac": tflops / peak, "flop_per_transition": ftr, "flop_convention": "minimal work",
                              "flop_per_transition_as_coded": ftr_coded, "achieved_as_coded": B * (T - 1) * ftr_coded / dt_l / 1e12,
@@ -848,8 +858,9 @@ def main():
 
     line["learner"] = learner_bench(
         learner, buf, LEARNER_B, LEARNER_T, args.learner_steps, (N_AGENTS, OBS, N_ACTIONS, HID, OBS, 64, 128),
-        "B = 32 episodes is 64 agent rows: both 100-step unrolls run on one CTA pair each, so the step is bound by the serial "
-        "depth (2 T dependent GRU steps, SURVEY 8d), not by throughput")
+        "B = 32 episodes is 64 agent rows: the step is bound by its serial depth (2 x T dependent GRU steps, which run on the "
+        "row-split FP32 recurrence kernel with weight_hh on chip, and ~90 short dependent launches), not by throughput",
+        sampled=True)
     cpu = None
     if want_cpu:
         cpu = cpu_baseline_run(args.cpu_steps, 3)

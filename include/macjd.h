@@ -516,6 +516,13 @@ MACJD_API int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* ten
                               float* v, const float* sums, float max_norm, float lr, float beta1, float beta2,
                               float eps, int64_t step, float* scal, float* scratch, size_t scratch_floats);
 
+/* The same step with its two bias corrections read from DEVICE memory at run time -- bias_corr[0] = 1 - beta1^step,
+ * bias_corr[1] = sqrt(1 - beta2^step) -- so that ONE captured launch sequence (a CUDA graph of the whole train step,
+ * QMixLearner.train_sampled) serves every step; the caller refreshes the two floats before each replay. */
+MACJD_API int macjd_clip_adam_dev(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, const float* grad, float* m,
+                                  float* v, const float* sums, float max_norm, float lr, float beta1, float beta2,
+                                  float eps, const float* bias_corr, float* scal, float* scratch, size_t scratch_floats);
+
 /* A tensor-core kernel waits on its pipeline barriers with a bound; if a wait ever runs out (a peer CTA
  * that never arrives), the launch finishes with invalid outputs instead of trapping, and every LATER entry
  * point returns MACJD_ERR_CUDA ("tcgen05 pipeline wait timed out ...", macjd_last_cuda_error) until

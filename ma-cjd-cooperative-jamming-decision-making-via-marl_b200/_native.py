@@ -175,6 +175,7 @@ class NativeLib:
             ("macjd_opt_scratch_floats", sz, []),
             ("macjd_tc_gemm_selftest", C.c_int, [P(Ctx), i32, i32, i32, vp, vp, vp]),
             ("macjd_clip_adam", C.c_int, [P(Ctx), P(OptTensors), vp, vp, vp, vp, f32, f32, f32, f32, f32, i64, vp, vp, sz]),
+            ("macjd_clip_adam_dev", C.c_int, [P(Ctx), P(OptTensors), vp, vp, vp, vp, f32, f32, f32, f32, f32, vp, vp, vp, sz]),
         ):
             fn = getattr(L, name)
             fn.restype = restype

@@ -19,6 +19,7 @@ loss / mask sums) is all-reduced, then every rank applies the identical update.
 from __future__ import annotations
 
 import copy
+import math
 import os
 
 import numpy as np
@@ -169,7 +170,7 @@ class QMixLearner:
 
     # ------------------------------------------------------------------ the train step
     @torch.no_grad()
-    def train(self, batch, train_info=None, *, lazy_stats=False, return_debug=False, check_actions=True):
+    def train(self, batch, train_info=None, *, lazy_stats=False, return_debug=False, check_actions=True, _bias_corr=None):
         """core/qmix.py:76-215.  Returns {loss, grad_norm, eval_qtot_avg, target_qtot_avg}.
         ``lazy_stats=True`` returns the four statistics as one device tensor (``stats_tensor``) instead of
         reading them back, and ``check_actions=False`` skips the action-range read-back (for batches whose
@@ -293,13 +294,18 @@ class QMixLearner:
             debug = {"grad": grad[:total].clone(), "names": [n for _, n in tr], "sizes": list(opt["sizes"]),
                      "q_tot": q_tot.clone(), "targets": targets.clone(), "q_taken": q_taken.clone(),
                      "tq_taken": tq_taken.clone(), "next_actions": ev["greedy"][1:].clone(), "sums": sums.clone()}
-        L.callv("macjd_clip_adam", ctx, tensors, grad, opt["m"], opt["v"], sums, float(self.args.grad_norm_clip),
-                float(self.args.lr), BETA1, BETA2, ADAM_EPS, int(opt["step"]), opt["scal"], opt["scratch"],
-                opt["scratch"].numel())
+        if _bias_corr is None:
+            L.callv("macjd_clip_adam", ctx, tensors, grad, opt["m"], opt["v"], sums, float(self.args.grad_norm_clip),
+                    float(self.args.lr), BETA1, BETA2, ADAM_EPS, int(opt["step"]), opt["scal"], opt["scratch"],
+                    opt["scratch"].numel())
+        else:      # captured step (train_sampled): the step's bias corrections are read from device memory
+            L.callv("macjd_clip_adam_dev", ctx, tensors, grad, opt["m"], opt["v"], sums, float(self.args.grad_norm_clip),
+                    float(self.args.lr), BETA1, BETA2, ADAM_EPS, _bias_corr, opt["scal"], opt["scratch"],
+                    opt["scratch"].numel())
         agent.packed_qhead()              # the Q-head changed under the packed copy (nothing else is trained)
 
-        # 11. hard target sync (qmix.py:203-205)
-        if (self.train_step - self.last_target_update_step) >= self.args.target_update_interval:
+        # 11. hard target sync (qmix.py:203-205); a captured step leaves it to its replayer
+        if _bias_corr is None and (self.train_step - self.last_target_update_step) >= self.args.target_update_interval:
             self._update_targets()
             self.last_target_update_step = self.train_step
 
@@ -313,6 +319,76 @@ class QMixLearner:
         if return_debug:
             stats["debug"] = debug
         return stats
+
+    # ------------------------------------------------------------------ sample + train as one replayed graph
+    MAX_STEP_GRAPHS = 4
+
+    def _graphable(self):
+        dist = torch.distributed
+        return (self.device.type == "cuda" and self.process_group is None and os.environ.get("MACJD_TRAIN_GRAPH", "1") != "0"
+                and not (dist.is_available() and dist.is_initialized() and getattr(self.args, "data_parallel", False)))
+
+    def train_sampled(self, buffer, batch_size, train_info=None):
+        """``train(buffer.sample(batch_size, time_major=True), lazy_stats=True, check_actions=False)`` -- the learner's half
+        of main.py:212-228 -- as ONE call.  Same index draws, same kernels, same results; on a single GPU the whole step
+        (replay gather, both unrolls, mixers, TD loss, backward, clip + Adam, Q-head re-pack: ~90 launches on three
+        streams, ~0.6 ms of host work against ~0.7 ms of GPU work at the reference batch) is captured once per
+        (batch, episode length) as a CUDA graph and replayed: per step the host then draws the indices, refreshes them and
+        the two Adam bias corrections in device memory, and launches the graph.  The first step of a shape runs eagerly
+        (it sizes the workspaces), the second is captured; the hard target update stays on the host between replays.
+        Data-parallel learners (the all-reduce) and MACJD_TRAIN_GRAPH=0 take the eager path.  Returns
+        {"stats_tensor": [loss, grad_norm, eval_qtot_avg, target_qtot_avg]} or None when the ring is empty."""
+        indices = buffer._draw_indices(batch_size)
+        if indices is None:
+            return None
+        eager = lambda: self.train(dict(buffer.gather(indices, time_major=True), time_major=True), train_info,
+                                   lazy_stats=True, check_actions=False)
+        if not self._graphable():
+            return eager()
+        B, max_len = len(indices), int(buffer.ep_len[indices].max())
+        graphs = self.__dict__.setdefault("_step_graphs", {})
+        key = (id(buffer), B, max_len, self.mac.agent.path)
+        g = graphs.get(key)
+        if g is None:
+            if max_len < 2 or len(graphs) >= self.MAX_STEP_GRAPHS:
+                return eager()
+            graphs[key] = "warm"             # this step sizes every workspace; the next one of this shape is captured
+            return eager()
+        if g == "warm":
+            g = graphs[key] = self._capture_step(buffer, B, max_len)
+        return self._replay_step(g, indices)
+
+    def _capture_step(self, buffer, B, max_len):
+        dev = self.device
+        g = {"buffer": buffer, "idx": torch.zeros(B, dtype=torch.int32, device=dev),
+             "bias_corr": torch.ones(2, dtype=torch.float32, device=dev), "graph": torch.cuda.CUDAGraph(),
+             "packs": (self.mac.agent.packed().buffer.data_ptr(), self.target_mac.agent.packed().buffer.data_ptr())}
+        step0, opt_step0 = self.train_step, self._ensure_opt_state()["step"]
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(g["graph"]):
+            batch = dict(buffer.gather(None, time_major=True, idx_dev=g["idx"], max_len=max_len), time_major=True)
+            g["stats"] = self.train(batch, None, lazy_stats=True, check_actions=False, _bias_corr=g["bias_corr"])["stats_tensor"]
+        # capturing recorded the launches without running them: the counters go back, the replay below is the step
+        self.train_step, self._opt_state["step"] = step0, opt_step0
+        g["keep"] = (dict(self._ws), batch)      # a later, larger shape may replace a workspace: this graph keeps its own alive
+        return g
+
+    def _replay_step(self, g, indices):
+        self.train_step += 1
+        opt = self._opt_state
+        opt["step"] += 1
+        step = opt["step"]
+        # (copies from pageable host memory are staged by the driver before they return: the arrays may die right away)
+        g["idx"].copy_(torch.from_numpy(indices.astype(np.int32)), non_blocking=True)
+        b1, b2 = float(np.float32(BETA1)), float(np.float32(BETA2))      # (macjd_clip_adam takes them as floats)
+        g["bias_corr"].copy_(torch.tensor([1.0 - b1 ** step, math.sqrt(1.0 - b2 ** step)], dtype=torch.float64).float(),
+                             non_blocking=True)
+        g["graph"].replay()
+        if (self.train_step - self.last_target_update_step) >= self.args.target_update_interval:
+            self._update_targets()
+            self.target_mac.agent.packed()              # same buffers: the captured launches read the new weights
+            self.last_target_update_step = self.train_step
+        return {"stats_tensor": g["stats"].clone()}
 
     # ------------------------------------------------------------------ reference API
     def _update_targets(self):

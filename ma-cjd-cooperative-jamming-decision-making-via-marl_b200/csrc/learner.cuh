@@ -185,8 +185,8 @@ inline size_t opt_scratch_floats() { return kSumsqBlocks + 4; }
 
 inline int clip_adam(cudaStream_t st, const macjd_opt_tensors& t, const float* grad, float* m, float* v,
                      const float* sums, float max_norm, float lr, float beta1, float beta2, float eps, int64_t step,
-                     float* scal, float* scratch, size_t scratch_floats) {
-  if (t.count < 1 || t.count > kMaxOptTensors || step < 1) return MACJD_ERR_INVALID_ARG;
+                     float* scal, float* scratch, size_t scratch_floats, const float* bias_corr = nullptr) {
+  if (t.count < 1 || t.count > kMaxOptTensors || (step < 1 && !bias_corr)) return MACJD_ERR_INVALID_ARG;
   if (!scratch || scratch_floats < opt_scratch_floats()) return MACJD_ERR_WORKSPACE;
   OptTable tab;
   tab.count = t.count;
@@ -200,10 +200,10 @@ inline int clip_adam(cudaStream_t st, const macjd_opt_tensors& t, const float* g
   tab.offset[t.count] = off;
   MACJD_LAUNCH(sumsq_partial_kernel, dim3(kSumsqBlocks), dim3(256), 0, st, grad, off, scratch);
   MACJD_LAUNCH(clip_coef_kernel, dim3(1), dim3(32), 0, st, (const float*)scratch, kSumsqBlocks, sums, max_norm, scal);
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc1 = bias_corr ? 1.0 : 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = bias_corr ? 1.0 : 1.0 - pow((double)beta2, (double)step);
   MACJD_LAUNCH(adam_kernel, dim3((off + 255) / 256), dim3(256), 0, st, tab, grad, m, v, (const float*)scal, lr, beta1,
-               beta2, eps, (float)bc1, (float)sqrt(bc2));
+               beta2, eps, (float)bc1, (float)sqrt(bc2), bias_corr);
   return MACJD_OK;
 }
 

@@ -298,8 +298,11 @@ __global__ void clip_coef_kernel(const float* __restrict__ part, int blocks, con
 
 __global__ void __launch_bounds__(256) adam_kernel(OptTable tab, const float* __restrict__ grad, float* __restrict__ m,
                                                    float* __restrict__ v, const float* __restrict__ scal, float lr,
-                                                   float beta1, float beta2, float eps, float bc1, float bc2_sqrt) {
+                                                   float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                                                   const float* __restrict__ bias_corr) {
   grid_dependency_sync();   // no-op unless launched as a programmatic dependent (MACJD_LAUNCH)
+  // a captured launch (CUDA graph) serves every step: the step's bias corrections then come from device memory
+  if (bias_corr) { bc1 = bias_corr[0]; bc2_sqrt = bias_corr[1]; }
   const int total = tab.offset[tab.count];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;

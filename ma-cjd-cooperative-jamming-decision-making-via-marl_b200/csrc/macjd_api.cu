@@ -683,6 +683,15 @@ int macjd_clip_adam(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, cons
                                       eps, step, scal, scratch, scratch_floats));
 }
 
+int macjd_clip_adam_dev(const macjd_ctx* ctx, const macjd_opt_tensors* tensors, const float* grad, float* m, float* v,
+                        const float* sums, float max_norm, float lr, float beta1, float beta2, float eps,
+                        const float* bias_corr, float* scal, float* scratch, size_t scratch_floats) {
+  MACJD_ENTER(ctx);
+  if (!tensors || !grad || !m || !v || !sums || !scal || !bias_corr) return MACJD_ERR_INVALID_ARG;
+  return finish(ctx, macjd::clip_adam((cudaStream_t)ctx->stream, *tensors, grad, m, v, sums, max_norm, lr, beta1, beta2,
+                                      eps, 0, scal, scratch, scratch_floats, bias_corr));
+}
+
 int macjd_qhead_repack(const macjd_ctx* ctx, const macjd_agent_weights* w, const float* w1, const float* b1, const float* w2,
                        const float* b2, float* tc_chunks, int32_t tc_kc, float* tc_q_c, float* tc_w1a, int32_t tc_w1a_stride) {
   MACJD_ENTER(ctx);

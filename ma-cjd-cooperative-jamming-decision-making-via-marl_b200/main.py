@@ -229,17 +229,21 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
     def train_phase(n_steps, at_steps):
         count, loss_sum = 0, 0.0
         for _ in range(n_steps):
+            if pipeline:
+                # sample + train as one call: on one GPU the whole step is a replayed CUDA graph (QMixLearner.train_sampled)
+                ts = learner.train_sampled(buffer, args.batch_size, {"total_steps": at_steps})
+                if ts is None:
+                    continue
+                pending_stats.append((ts["stats_tensor"], at_steps))
+                count += 1
+                continue
             batch = buffer.sample(args.batch_size, time_major=True)
             if batch is None:
                 continue
-            if pipeline:
-                ts = learner.train(batch, {"total_steps": at_steps}, lazy_stats=True, check_actions=False)
-                pending_stats.append((ts["stats_tensor"], at_steps))
-            else:
-                ts = learner.train(batch, {"total_steps": at_steps})
-                for k in stat_keys:
-                    stats[k].append(ts[k])
-                loss_sum += ts["loss"]
+            ts = learner.train(batch, {"total_steps": at_steps})
+            for k in stat_keys:
+                stats[k].append(ts[k])
+            loss_sum += ts["loss"]
             count += 1
         if count and not pipeline:
             scalar("Loss/train_episode_avg", loss_sum / count, at_steps)

@@ -170,14 +170,19 @@ class EpisodeReplayBuffer:
             return None
         return np.random.choice(self.current_size, batch_size, replace=False)
 
-    def gather(self, indices, time_major=False):
+    def gather(self, indices, time_major=False, *, idx_dev=None, max_len=None):
         """Gather episodes ``indices`` (host array of ring slots) into fresh device tensors.
         Reference layout [B, T(+1), ...] or, for the learner kernels, time-major [T(+1), B, ...];
-        trimmed to the longest episode of the batch (replay_buffer.py:183-209)."""
-        indices = np.asarray(indices)
-        B = len(indices)
-        max_len = int(self.ep_len[indices].max()) if B else 0
-        idx_dev = torch.from_numpy(indices.astype(np.int32)).to(self.device)
+        trimmed to the longest episode of the batch (replay_buffer.py:183-209).
+        ``idx_dev`` (int32 device tensor) + ``max_len`` instead of ``indices``: the slots are read from device memory at
+        run time and nothing is taken from the host -- the form a captured launch (CUDA graph) needs."""
+        if idx_dev is None:
+            indices = np.asarray(indices)
+            B = len(indices)
+            max_len = int(self.ep_len[indices].max()) if B else 0
+            idx_dev = torch.from_numpy(indices.astype(np.int32)).to(self.device)
+        else:
+            B, max_len = int(idx_dev.numel()), int(max_len)
         out, descs = {}, []
         for key, buf in self.buffers.items():
             n_t = max_len + 1 if key in T_PLUS_1 else max_len

@@ -158,3 +158,55 @@ def test_hidden_bf16_effect_on_a_train_step():
     for k in ("loss", "eval_qtot_avg", "target_qtot_avg"):
         np.testing.assert_allclose(stats[1][k], stats[0][k], rtol=1e-2, atol=1e-3, err_msg=k)
     assert stats[1]["target_qtot_avg"] == stats[0]["target_qtot_avg"]      # the unrolls start from zeros: no stored state involved
+
+
+def _sampled_learner(seed=5, n_envs=64):
+    """A learner + a filled replay ring at the reference dims (the bench's C1 learner shape, fewer envs)."""
+    import bench
+    from macjd_b200.core.mac import BasicMAC
+    from macjd_b200.core.qmix import QMixLearner
+    from macjd_b200.runners.episode_runner import BatchedEpisodeRunner
+    from macjd_b200.simulation.environment import ElectromagneticEnvironment
+    from macjd_b200.simulation.scenario import default_spec
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    rl = bench.rl_args("cuda:0", n_envs)
+    rl.target_update_interval = 3                 # the hard target update falls between replays of the captured step
+    torch.manual_seed(seed)
+    env = ElectromagneticEnvironment(rl, spec=default_spec(n_envs), device="cuda:0", seed=seed)
+    mac = BasicMAC(bench.OBS, rl)
+    mac.cuda()
+    buf = EpisodeReplayBuffer(rl, device="cuda:0")
+    runner = BatchedEpisodeRunner(env, mac, buf, rl)
+    learner = QMixLearner(mac, rl)
+    runner.run()
+    return learner, buf
+
+
+def test_train_sampled_graph_equals_eager_steps(monkeypatch):
+    """QMixLearner.train_sampled replays the whole step as one CUDA graph (from its second step of a shape on): same
+    index draws, same kernels -- seven steps must leave the same statistics and the same parameters, target networks
+    and optimiser state as sample() + train() with the graph switched off (bit for bit: nothing in the step is
+    order-dependent), across two hard target updates."""
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MACJD_TRAIN_GRAPH", mode)
+        learner, buf = _sampled_learner()
+        np.random.seed(11)
+        stats = [learner.train_sampled(buf, 16, {})["stats_tensor"] for _ in range(7)]
+        torch.cuda.synchronize()
+        assert ("_step_graphs" in learner.__dict__ and any(isinstance(g, dict) for g in learner._step_graphs.values())) == (mode == "1")
+        out[mode] = (torch.stack(stats).cpu(),
+                     {k: v.detach().cpu().clone() for k, v in learner.mac.agent.state_dict().items()},
+                     {k: v.detach().cpu().clone() for k, v in learner.eval_qmix_net.state_dict().items()},
+                     {k: v.detach().cpu().clone() for k, v in learner.target_qmix_net.state_dict().items()},
+                     {k: v.detach().cpu().clone() for k, v in learner.target_mac.agent.state_dict().items()},
+                     learner._opt_state["m"].cpu().clone(), learner._opt_state["v"].cpu().clone(),
+                     learner.train_step, learner._opt_state["step"], learner.last_target_update_step)
+    g, e = out["1"], out["0"]
+    assert torch.isfinite(g[0]).all() and g[0].abs().sum() > 0
+    assert torch.equal(g[0], e[0]), (g[0], e[0])
+    for a, b in zip(g[1:5], e[1:5]):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    assert torch.equal(g[5], e[5]) and torch.equal(g[6], e[6])
+    assert g[7:] == e[7:] == (7, 7, 6)

@@ -49,3 +49,31 @@ def test_fused_rollout_step_equals_two_kernels(monkeypatch, kind, n_envs, path, 
     # (the library fuses the 8 x 16 x 4 scenario only when asked to: 50 KB of views per CTA-step; ask)
     monkeypatch.setenv("MACJD_FUSE_MAX_VIEW_BYTES", "1000000")
     RC.check_fused_rollout_step("cuda", None, n_envs=n_envs, kind=kind, path=path, expect_fused=fused)
+
+
+def test_pipelined_loop_trains_through_the_step_graph():
+    """main.run(pipeline=True): the learner's phase is QMixLearner.train_sampled on its own stream -- eager first step,
+    captured second, replayed from then on (a hetero scenario: episodes end at different lengths, so several shapes
+    occur and the cache limit is exercised) -- and the loop's counters agree with the learner's."""
+    import types
+    import numpy as np
+    from macjd_b200 import main as M
+    from macjd_b200.simulation.scenario import hetero_spec
+    n_envs, T = 16, 8
+    args = RC.rl_args("cuda", episode_limit=T, batch_size=8, buffer_size=32, total_env_steps=6 * n_envs * T,
+                      start_training_steps=n_envs * T, train_interval=2, log_interval=10, log_interval_seconds=0,
+                      save_model=False, test_interval=0, test_nepisodes=0, device_request="cuda", rnn_hidden_dim=128,
+                      actor_hidden_dim=128, target_update_interval=5)
+    scalars = []
+    writer = types.SimpleNamespace(add_scalar=lambda tag, v, step: scalars.append((tag, float(v), step)), close=lambda: None)
+    np.random.seed(4)
+    p = M.run(args, spec=hetero_spec(n_envs, seed=3, active=True, episode_limit=T), writer=writer, log=lambda s: None, pipeline=True)
+    assert p["total_steps"] == 6 * n_envs * T and p["episodes"] == 6 * n_envs
+    # rollouts 3 .. 6 train (the pipelined learner works from the ring as of the previous rollout), n_envs * (T // 2) steps each
+    assert p["train_steps"] == 4 * n_envs * (T // 2)
+    graphs = p["learner"].__dict__.get("_step_graphs", {})
+    assert any(isinstance(g, dict) for g in graphs.values()) and len(graphs) <= p["learner"].MAX_STEP_GRAPHS
+    assert p["learner"].train_step == p["train_steps"] and p["learner"]._opt_state["step"] == p["train_steps"]
+    assert p["learner"].last_target_update_step == (p["train_steps"] // 5) * 5
+    losses = [v for t, v, _ in scalars if t == "Loss/train_avg"]
+    assert losses and all(np.isfinite(losses))

@@ -62,6 +62,21 @@ for _ in range(10):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 print("isolated train step (after a sync), GPU events ms:", " ".join(f"{x:.3f}" for x in ts))
+# the call the training loop makes: sample + train as one replayed CUDA graph
+for _ in range(4):
+    learner.train_sampled(buf, bench.LEARNER_B, {})
+torch.cuda.synchronize()
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(N):
+        learner.train_sampled(buf, bench.LEARNER_B, {})
+    e1.record()
+    t_issue = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    print(f"{N} train_sampled steps (graph): host issue {t_issue / N * 1e3:.3f} ms / step, GPU events {e0.elapsed_time(e1) / N:.3f} ms / step")
+
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(N):
@@ -70,3 +85,4 @@ pr.disable()
 torch.cuda.synchronize()
 st = pstats.Stats(pr)
 st.sort_stats("cumulative").print_stats(28)
+
