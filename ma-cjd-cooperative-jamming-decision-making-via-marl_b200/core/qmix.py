@@ -324,9 +324,16 @@ class QMixLearner:
     MAX_STEP_GRAPHS = 4
 
     def _graphable(self):
+        if self.device.type != "cuda" or os.environ.get("MACJD_TRAIN_GRAPH", "1") == "0":
+            return False
         dist = torch.distributed
-        return (self.device.type == "cuda" and self.process_group is None and os.environ.get("MACJD_TRAIN_GRAPH", "1") != "0"
-                and not (dist.is_available() and dist.is_initialized() and getattr(self.args, "data_parallel", False)))
+        if self.process_group is not None or (dist.is_available() and dist.is_initialized()
+                                              and getattr(self.args, "data_parallel", False)):
+            # data-parallel: the gradient all-reduce is captured with the step (NCCL records its kernel into the graph;
+            # every rank issues one all-reduce per step whether it replays or runs eagerly, so ranks may mix the two)
+            return (dist.get_backend(self.process_group) == "nccl"
+                    and os.environ.get("MACJD_TRAIN_GRAPH_DP", "1") != "0")
+        return True
 
     def train_sampled(self, buffer, batch_size, train_info=None):
         """``train(buffer.sample(batch_size, time_major=True), lazy_stats=True, check_actions=False)`` -- the learner's half
@@ -336,7 +343,8 @@ class QMixLearner:
         (batch, episode length) as a CUDA graph and replayed: per step the host then draws the indices, refreshes them and
         the two Adam bias corrections in device memory, and launches the graph.  The first step of a shape runs eagerly
         (it sizes the workspaces), the second is captured; the hard target update stays on the host between replays.
-        Data-parallel learners (the all-reduce) and MACJD_TRAIN_GRAPH=0 take the eager path.  Returns
+        Data-parallel learners over NCCL capture the gradient all-reduce with the step (MACJD_TRAIN_GRAPH_DP=0: eager);
+        other backends and MACJD_TRAIN_GRAPH=0 take the eager path.  Returns
         {"stats_tensor": [loss, grad_norm, eval_qtot_avg, target_qtot_avg]} or None when the ring is empty."""
         indices = buffer._draw_indices(batch_size)
         if indices is None:
@@ -365,7 +373,8 @@ class QMixLearner:
              "packs": (self.mac.agent.packed().buffer.data_ptr(), self.target_mac.agent.packed().buffer.data_ptr())}
         step0, opt_step0 = self.train_step, self._ensure_opt_state()["step"]
         torch.cuda.synchronize(dev)
-        with torch.cuda.graph(g["graph"]):
+        # (thread-local capture mode: the NCCL watchdog thread polls its events while this thread captures)
+        with torch.cuda.graph(g["graph"], capture_error_mode="thread_local"):
             batch = dict(buffer.gather(None, time_major=True, idx_dev=g["idx"], max_len=max_len), time_major=True)
             g["stats"] = self.train(batch, None, lazy_stats=True, check_actions=False, _bias_corr=g["bias_corr"])["stats_tensor"]
         # capturing recorded the launches without running them: the counters go back, the replay below is the step

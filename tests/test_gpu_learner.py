@@ -160,8 +160,9 @@ def test_hidden_bf16_effect_on_a_train_step():
     assert stats[1]["target_qtot_avg"] == stats[0]["target_qtot_avg"]      # the unrolls start from zeros: no stored state involved
 
 
-def _sampled_learner(seed=5, n_envs=64):
-    """A learner + a filled replay ring at the reference dims (the bench's C1 learner shape, fewer envs)."""
+def _sampled_learner(seed=5, n_envs=64, device="cuda:0", same_init_seed=None):
+    """A learner + a filled replay ring at the reference dims (the bench's C1 learner shape, fewer envs).  same_init_seed:
+    the networks' initial weights come from this seed (data-parallel ranks start equal), the env from `seed`."""
     import bench
     from macjd_b200.core.mac import BasicMAC
     from macjd_b200.core.qmix import QMixLearner
@@ -169,13 +170,13 @@ def _sampled_learner(seed=5, n_envs=64):
     from macjd_b200.simulation.environment import ElectromagneticEnvironment
     from macjd_b200.simulation.scenario import default_spec
     from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
-    rl = bench.rl_args("cuda:0", n_envs)
+    rl = bench.rl_args(device, n_envs)
     rl.target_update_interval = 3                 # the hard target update falls between replays of the captured step
-    torch.manual_seed(seed)
-    env = ElectromagneticEnvironment(rl, spec=default_spec(n_envs), device="cuda:0", seed=seed)
+    torch.manual_seed(seed if same_init_seed is None else same_init_seed)
+    env = ElectromagneticEnvironment(rl, spec=default_spec(n_envs), device=device, seed=seed)
     mac = BasicMAC(bench.OBS, rl)
     mac.cuda()
-    buf = EpisodeReplayBuffer(rl, device="cuda:0")
+    buf = EpisodeReplayBuffer(rl, device=device)
     runner = BatchedEpisodeRunner(env, mac, buf, rl)
     learner = QMixLearner(mac, rl)
     runner.run()
@@ -210,3 +211,16 @@ def test_train_sampled_graph_equals_eager_steps(monkeypatch):
             assert torch.equal(a[k], b[k]), k
     assert torch.equal(g[5], e[5]) and torch.equal(g[6], e[6])
     assert g[7:] == e[7:] == (7, 7, 6)
+
+
+def test_dp_train_sampled_graph_equals_eager():
+    """Two ranks over NCCL (tests/dp_graph_worker.py): the data-parallel train step with its all-reduce captured in the
+    step graph equals the eager data-parallel step bit for bit on every rank, and the ranks hold the same networks."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dp_graph_worker.py")],
+                       cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "DP_GRAPH_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
