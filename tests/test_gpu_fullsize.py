@@ -164,3 +164,72 @@ def test_c3_rollout_full_size_vs_oracles(path):
           f"{undecidable}; greedy actions differing from the float64 truth: {flips}")
     assert flips <= undecidable
     assert undecidable < 2e-2 * T * n * J      # (measured on B200: 0.8 % of the rows have a margin below 1e-4 x scale; none flipped)
+
+
+def _ring_model_slots(size, index, inc):
+    """utils/replay_buffer.py:216-250 (reference `_get_storage_idx`) restated on plain integers: the slots the next
+    `inc` episodes go to, and the insertion pointer afterwards."""
+    if index + inc <= size:
+        return np.arange(index, index + inc), index + inc
+    if index < size:
+        over = inc - (size - index)
+        return np.concatenate([np.arange(index, size), np.arange(0, over)]), over
+    return np.arange(0, inc), inc
+
+
+def _episodes_of(gid, T, Nn, S, A, H, dev):
+    """Time-major trajectories whose every element is a hash of (global episode number, key, t, inner index): a slot's
+    content tells which episode was written there last."""
+    n = gid.numel()
+    g = gid.to(dev).view(1, n, 1)
+
+    def field(rows, inner, salt, mod):
+        t = torch.arange(rows, device=dev, dtype=torch.int64).view(rows, 1, 1)
+        j = torch.arange(inner, device=dev, dtype=torch.int64).view(1, 1, inner)
+        return (g * 1000003 + t * 7919 + j * 131 + salt) % mod
+
+    return {"state": (field(T + 1, S, 1, 4093).float() - 2046.0) / 64.0,
+            "obs": ((field(T + 1, Nn * S, 2, 4093).float() - 2046.0) / 64.0).view(T + 1, n, Nn, S),
+            "actions_discrete": field(T, Nn, 3, A).to(torch.int32).view(T, n, Nn, 1),
+            "actions_continuous": (field(T, Nn, 4, 1021).float() / 1021.0).view(T, n, Nn, 1),
+            "avail_actions": field(T + 1, Nn * A, 5, 2).to(torch.uint8).view(T + 1, n, Nn, A),
+            "reward": (field(T, 1, 6, 8191).float() - 4095.0) / 256.0,
+            "terminated": field(T, 1, 7, 2).to(torch.uint8),
+            "hidden_state": ((field(T + 1, Nn * H, 8, 65521).float() - 32760.0) / 32768.0).view(T + 1, n, Nn, H)}
+
+
+def test_replay_ring_at_scale_wraps_and_addresses_past_4gb():
+    """The C5 ring in the small: 30 000 episodes of the C2 shape (4.3 GB; the hidden_state key alone is 3.1 GB, so slot
+    offsets need 64 bits), filled by 9 rollouts of 4 096 episodes (36 864 > 30 000: the ring wraps inside a rollout).
+    After every store the pointer and size follow the reference's ring arithmetic (utils/replay_buffer.py:216-250);
+    at the end EVERY slot holds, bit for bit and in every key, the episode that was written there last
+    (utils/replay_buffer.py:78-156 keeps whole episodes per slot), read back through gather() in both layouts."""
+    from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
+    cap, n, T, Nn, S, A, H, dev = 30000, 4096, 100, 2, 24, 5, 128, "cuda"
+    args = types.SimpleNamespace(buffer_size=cap, episode_limit=T, n_actions=A, n_agents=Nn, state_shape=S, obs_shape=S,
+                                 rnn_hidden_dim=H, use_cuda=True, device=dev)
+    buf = EpisodeReplayBuffer(args, device=dev)
+    assert buf.buffers["hidden_state"].numel() * buf.buffers["hidden_state"].element_size() > 2 ** 31
+    owner = np.full(cap, -1, dtype=np.int64)
+    index = size = 0
+    for r in range(9):
+        gid = torch.arange(r * n, (r + 1) * n, dtype=torch.int64)
+        buf.store_rollout(_episodes_of(gid, T, Nn, S, A, H, dev))
+        slots, index = _ring_model_slots(cap, index, n)
+        size = min(cap, size + n)
+        owner[slots] = gid.numpy()
+        assert (buf.current_index, buf.current_size) == (index, size), r
+    assert (owner >= 0).all() and len(np.unique(owner)) == cap
+    rng = np.random.default_rng(0)
+    order = rng.permutation(cap)                                   # every slot once, in random order
+    for c0 in range(0, cap, 3000):
+        idx = order[c0:c0 + 3000]
+        want = _episodes_of(torch.from_numpy(owner[idx]), T, Nn, S, A, H, dev)
+        tm = (c0 // 3000) % 2 == 1
+        got = buf.gather(idx, time_major=tm)
+        for k, w in want.items():
+            g = got[k] if tm else got[k].transpose(0, 1)
+            assert g.shape == w.shape and g.dtype == w.dtype, (k, g.shape, w.shape, g.dtype, w.dtype)
+            assert torch.equal(g, w), (k, c0)
+        assert bool(got["filled"].all())
+        del want, got
