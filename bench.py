@@ -967,6 +967,7 @@ def main():
         out = loop.run(cfg, spec=default_spec(n5), writer=False, log=lambda *_: None, pipeline=True)
         torch.cuda.synchronize()
         dt5 = reduce_max(time.perf_counter() - t0)
+        loop_s = reduce_max(out["time_s"])             # main.run's own clock: the loop alone (device drained at its end)
         held = len(out["buffer"])
         bpe = out["buffer"].bytes_per_episode()
         line["configs"]["C5"] = {
@@ -981,6 +982,11 @@ def main():
             "train_transitions_per_sec": world * out["train_steps"] * 32 * 99 / dt5,
             "train_steps": out["train_steps"], "rollouts": rollouts, "wall_s": dt5, "scaling": "weak",
             "timing": "host wall clock around the whole loop incl. construction of env / ring / networks, max over ranks",
+            "loop_only": {"wall_s": loop_s, "env_agent_steps_per_sec": world * out["total_steps"] * N_AGENTS / loop_s,
+                          "train_episodes_per_sec": world * out["train_steps"] * 32 / loop_s,
+                          "what": "the same run on main.run's own clock (time_s): from the first rollout to the drained "
+                                  "device, without the construction of env / ring / networks; still includes the first "
+                                  "eager train step and the capture of the step graph"},
             "last_loss": out["last_logged"].get("avg_loss")}
         del out
         torch.cuda.empty_cache()

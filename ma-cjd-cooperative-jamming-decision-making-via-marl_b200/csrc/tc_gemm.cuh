@@ -319,7 +319,8 @@ inline bool tc_gemm_wanted(int M, int N, int K) {
   static const bool on = [] { const char* e = getenv("MACJD_TC_GEMM"); return !(e && e[0] == '0'); }();
   // (narrow outputs included: a [256 x 6] weight gradient over 200 k rows or a 5-column layer over 200 k rows is bound by
   // reading its tall operand, which the 128-row tiles with several chunks in flight do at 3-4x the FP32 kernel's rate)
-  return on && M >= 64 && (double)M * N * K >= (double)(1 << 24);
+  static const double min_macs = [] { const char* e = getenv("MACJD_TC_GEMM_MIN_LOG2"); return ldexp(1.0, e ? atoi(e) : 24); }();
+  return on && M >= 64 && (double)M * N * K >= min_macs;
 }
 
 // returns false if the launch could not be set up (caller falls back to the FP32 kernel)

@@ -178,7 +178,7 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
     if pipeline:
         dev = torch.device(args.device)
         roll_stream, learn_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        ev_weights, ev_gathered, ev_stored = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        ev_weights, ev_gathered, ev_stored, ev_copied = (torch.cuda.Event() for _ in range(4))
         main_stream = torch.cuda.current_stream(dev)
         roll_stream.wait_stream(main_stream)
         learn_stream.wait_stream(main_stream)
@@ -258,12 +258,20 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
             with torch.cuda.stream(roll_stream):
                 roll_stream.wait_event(ev_weights)              # the learner's weights of the previous phase are final
                 sync_acting_copy()
+                ev_copied.record(roll_stream)
+            # (A/B on one B200, bench C5, four runs with temporary switches: issuing the learner's phase before the
+            # rollout, or the rollout as ONE launch per episode, is slower -- 41.6 M / 38.6 M env-agent steps/s against
+            # 44.5 M, both together 32.9 M.  Likely cause: the two streams compete for the SMs' shared memory, and a 2 ms
+            # launch on 128 SMs holds up the learner's chain of short kernels for its whole length, while per-step
+            # launches interleave with it.)
+            with torch.cuda.stream(roll_stream):
                 runner.reset()
                 for t in range(args.episode_limit):
                     runner.step(t)
             if will_train:
                 with torch.cuda.stream(learn_stream):
                     learn_stream.wait_event(ev_stored)          # ring slots written by the previous store
+                    learn_stream.wait_event(ev_copied)          # the acting copy has read the weights this phase updates
                     train_steps += train_phase(train_steps_for_rollout(args, n_envs, args.episode_limit), total_steps)
                     ev_gathered.record(learn_stream)            # (every gather of this phase is enqueued before this)
                     ev_weights.record(learn_stream)
