@@ -961,7 +961,7 @@ def main():
         cfg = loop.default_config(buffer_size=cap, total_env_steps=rollouts * n5 * 100, start_training_steps=0,
                                   train_steps_per_rollout=tpr, save_model=False, test_nepisodes=0, test_interval=0,
                                   log_interval_seconds=1e9, seed=42 + rank, data_parallel=True, agent_kernel_path=0,
-                                  device=device)
+                                  device=device, replay_fast_sampling=os.environ.get("MACJD_BENCH_C5_REFERENCE_DRAWS", "0") == "0")
         barrier()
         t0 = time.perf_counter()
         out = loop.run(cfg, spec=default_spec(n5), writer=False, log=lambda *_: None, pipeline=True)
@@ -974,7 +974,9 @@ def main():
             "workload": f"end-to-end training loop (macjd_b200.main.run, pipeline=True: act with a frozen copy on one stream while the "
                         f"learner trains on another, store, sample, train, target update) with the replay ring sized for "
                         f"{C5['episodes_total']} episodes over {C5['gpus_nominal']} GPUs = {cap} per GPU (BASELINE.json configs[4]); "
-                        f"{rollouts} rollouts of {n5} episodes x 100 steps, {tpr} train steps of B = 32 per rollout",
+                        f"{rollouts} rollouts of {n5} episodes x 100 steps, {tpr} train steps of B = 32 per rollout; batches drawn with "
+                        + ("the ring's O(batch) sampler (replay_fast_sampling: uniform without replacement, Floyd)"
+                           if cfg.replay_fast_sampling else "the reference's np.random.choice (a full permutation per draw)"),
             "ring_capacity_episodes_per_gpu": cap, "ring_bytes_per_episode": bpe, "ring_gb_per_gpu": cap * bpe / 1e9,
             "episodes_held_per_gpu": held, "ring_wrapped": bool(rollouts * n5 > cap),
             "env_agent_steps_per_sec": world * out["total_steps"] * N_AGENTS / dt5,

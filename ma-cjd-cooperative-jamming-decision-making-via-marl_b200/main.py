@@ -24,7 +24,10 @@ while the learner trains on another stream from the ring as it stood after rollo
 refreshed (a device copy) and the ring slots are handed over between rollouts with events, statistics are
 read back once per log line (``lazy_stats``), and no train step synchronises with the host.  The acting
 policy therefore lags the learner by one rollout -- the usual actor / learner split; ``pipeline=False`` is
-the reference's strict alternation (act with the latest weights, then train).
+the reference's strict alternation (act with the latest weights, then train).  The pipelined loop also draws its
+batches with the ring's O(batch) sampler (``args.replay_fast_sampling``, default on here, off everywhere else: same
+distribution, different index stream than ``np.random.choice``'s full permutation, which at a 125 000-episode ring
+costs the host four train steps per draw); ``replay_fast_sampling=False`` keeps the reference's draws.
 
 Not in the reference: ``evaluate`` (greedy episodes with ``test_mode=True``; the reference's
 ``test_interval`` / ``test_nepisodes`` keys of config/default.yaml:81-83 are never read by its loop) and
@@ -169,7 +172,11 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
     shared = getattr(args, "replay_shared_obs", None)
     if shared is None:
         shared = bool(getattr(env, "obs_is_replicated_state", False)) and args.obs_shape == args.state_shape
-    buffer = EpisodeReplayBuffer(args=args, device=args.device, _lib=_lib, shared_obs=bool(shared))
+    # the pipelined loop draws its batches with the O(batch) sampler unless told otherwise: the reference's draw permutes
+    # the whole ring population per batch (2.7 ms at 125 000 episodes; utils/replay_buffer.py header)
+    fast = getattr(args, "replay_fast_sampling", None)
+    fast = (bool(pipeline) and args.use_cuda) if fast is None else bool(fast)
+    buffer = EpisodeReplayBuffer(args=args, device=args.device, _lib=_lib, shared_obs=bool(shared), fast_sampling=fast)
     learner = QMixLearner(mac, args=args, _lib=_lib)
     pipeline = bool(pipeline) and args.use_cuda
     # pipelined: the rollout acts with a frozen copy of the agent, refreshed between rollouts
@@ -184,6 +191,16 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
         learn_stream.wait_stream(main_stream)
         ev_weights.record(learn_stream)
         ev_gathered.record(learn_stream)
+
+    # MACJD_LOOP_TIMING=1: device time of each rollout / train phase / store of the pipelined loop (CUDA events on their
+    # streams; returned as out["phase_ms"]: medians over the iterations)
+    phase_events = {} if pipeline and os.environ.get("MACJD_LOOP_TIMING", "0") != "0" else None
+
+    def stamp(name, stream):
+        if phase_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            phase_events.setdefault(name, []).append(e)
 
     def sync_acting_copy():
         """Acting copy <- learner's agent: only fc2_q_head is ever trained (core/qmix.py:178), so four raw
@@ -266,18 +283,24 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
             # launches interleave with it.)
             with torch.cuda.stream(roll_stream):
                 runner.reset()
+                stamp("rollout", roll_stream)
                 for t in range(args.episode_limit):
                     runner.step(t)
+                stamp("rollout", roll_stream)
             if will_train:
                 with torch.cuda.stream(learn_stream):
                     learn_stream.wait_event(ev_stored)          # ring slots written by the previous store
                     learn_stream.wait_event(ev_copied)          # the acting copy has read the weights this phase updates
+                    stamp("train", learn_stream)
                     train_steps += train_phase(train_steps_for_rollout(args, n_envs, args.episode_limit), total_steps)
+                    stamp("train", learn_stream)
                     ev_gathered.record(learn_stream)            # (every gather of this phase is enqueued before this)
                     ev_weights.record(learn_stream)
             with torch.cuda.stream(roll_stream):
                 roll_stream.wait_event(ev_gathered)             # the store may overwrite slots the learner sampled
+                stamp("store", roll_stream)
                 run_info = runner.finish_run(store=True)
+                stamp("store", roll_stream)
                 ev_stored.record(roll_stream)
         else:
             # ---- one rollout: n_envs episodes (main.py:193-198)
@@ -368,6 +391,10 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
     if own_writer:
         writer.close()
     log("Training finished.")
+    phase_ms = None
+    if phase_events:
+        phase_ms = {k: float(np.median([a.elapsed_time(b) for a, b in zip(v[0::2], v[1::2])])) for k, v in phase_events.items()}
     return {"episodes": episode, "total_steps": total_steps, "train_steps": train_steps, "time_s": time.time() - start_time,
+            "phase_ms": phase_ms,
             "last_logged": last_logged, "last_eval": last_eval, "learner": learner, "runner": runner, "buffer": buffer,
             "pipeline": pipeline}

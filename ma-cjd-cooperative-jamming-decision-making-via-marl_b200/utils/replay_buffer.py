@@ -6,7 +6,10 @@ episode dict, ``store_rollout`` takes time-major device buffers of many episodes
 ``sample`` gathers a batch with one strided-copy kernel launch (csrc/replay.cuh).
 Indices are drawn on the host exactly like the reference does
 (``np.random.choice(current_size, B, replace=False)``, replay_buffer.py:178) so a seeded run
-samples the same episodes.
+samples the same episodes.  That draw is a full permutation of the ring's population -- 0.2 ms at 4 096 episodes, 2.7 ms at
+125 000, against a 0.7 ms train step -- so ``fast_sampling=True`` (opt-in; ``args.replay_fast_sampling``) draws the
+same distribution (uniform, without replacement) with Floyd's algorithm in ~12 us from a ``numpy.random.Generator``
+seeded off the legacy global state (``np.random.seed`` still fixes the run; the index stream differs from the reference's).
 
 Storage format: masks and ``avail_actions`` are bytes (the reference keeps int64 masks,
 replay_buffer.py:59); with ``shared_obs=True`` the ring does not hold ``obs`` at all -- in this environment
@@ -36,8 +39,10 @@ class EpisodeReplayBuffer:
     KEY_ORDER = ("state", "obs", "actions_discrete", "actions_continuous", "avail_actions", "reward", "terminated",
                  "filled", "hidden_state")
 
-    def __init__(self, args, device=None, _lib=None, shared_obs=None, hidden_bf16=None):
+    def __init__(self, args, device=None, _lib=None, shared_obs=None, hidden_bf16=None, fast_sampling=None):
         self.args = args
+        self.fast_sampling = bool(getattr(args, "replay_fast_sampling", False) if fast_sampling is None else fast_sampling)
+        self._rng = None
         self.hidden_bf16 = bool(getattr(args, "replay_hidden_bf16", False) if hidden_bf16 is None else hidden_bf16)
         # obs is state replicated per agent: keep only the state (caller vouches; needs obs_shape == state_shape)
         self.shared_obs = bool(getattr(args, "replay_shared_obs", False) if shared_obs is None else shared_obs)
@@ -168,6 +173,10 @@ class EpisodeReplayBuffer:
         if batch_size <= 0:
             print("Error: Cannot sample 0 or negative episodes.")
             return None
+        if self.fast_sampling:
+            if self._rng is None:        # seeded off the legacy global stream: np.random.seed() still determines the run
+                self._rng = np.random.Generator(np.random.PCG64(int(np.random.randint(0, 2 ** 31 - 1))))
+            return self._rng.choice(self.current_size, batch_size, replace=False)
         return np.random.choice(self.current_size, batch_size, replace=False)
 
     def gather(self, indices, time_major=False, *, idx_dev=None, max_len=None):
