@@ -964,7 +964,8 @@ def main():
                                   device=device, replay_fast_sampling=os.environ.get("MACJD_BENCH_C5_REFERENCE_DRAWS", "0") == "0")
         barrier()
         t0 = time.perf_counter()
-        out = loop.run(cfg, spec=default_spec(n5), writer=False, log=lambda *_: None, pipeline=True)
+        out = loop.run(cfg, spec=default_spec(n5), writer=False, log=lambda *_: None, pipeline=True,
+                       use_graph=os.environ.get("MACJD_BENCH_C5_ROLLOUT_GRAPH", "0") != "0")
         torch.cuda.synchronize()
         dt5 = reduce_max(time.perf_counter() - t0)
         loop_s = reduce_max(out["time_s"])             # main.run's own clock: the loop alone (device drained at its end)

@@ -284,8 +284,19 @@ def run(args, *, n_envs=None, spec=None, sim_config_path=None, writer=None, log=
             with torch.cuda.stream(roll_stream):
                 runner.reset()
                 stamp("rollout", roll_stream)
-                for t in range(args.episode_limit):
-                    runner.step(t)
+                # use_graph: the episode's launches replayed as one CUDA graph -- the same per-step launches on the device,
+                # but the host issues them in ~0.1 ms instead of ~2 ms and gets to the learner's phase that much earlier
+                graphed = False
+                if use_graph and not getattr(runner, "_graph_failed", False):
+                    try:
+                        runner._run_graph(False)
+                        graphed = True
+                    except RuntimeError:                        # capture not possible here: keep the per-step launches
+                        runner._graph_failed = True
+                        runner.reset()
+                if not graphed:
+                    for t in range(args.episode_limit):
+                        runner.step(t)
                 stamp("rollout", roll_stream)
             if will_train:
                 with torch.cuda.stream(learn_stream):

@@ -336,7 +336,8 @@ class BatchedEpisodeRunner:
             self._build_step_structs()
         lib, wts = mac.agent.lib(), pk.cstruct()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # (thread-local capture mode: under torch.distributed the NCCL watchdog thread polls its events meanwhile)
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             ctx = mac.agent._ctx()                         # the capture stream
             for t in range(T):
                 if self.fused_step:
