@@ -6,6 +6,7 @@ Runs only in the build container, where the reference is mounted read-only at
 .npz / .json files only).  Usage:
 
     python tests/golden/make_golden.py [env] [agent] [mixer] [learner] [replay] [api]
+    MAKE_GOLDEN_NAMES=c3,c4 python tests/golden/make_golden.py agent mixer learner     (only these network configs)
 
 Inputs are seeded; noise that the reference would draw from np.random / torch RNG
 is injected (FIFO patches) so that both sides see identical sequences.
@@ -222,7 +223,18 @@ NET_CONFIGS = {
     "c1": dict(),
     "small": dict(n_agents=3, n_actions=7, state_shape=39, obs_shape=39, rnn_hidden_dim=64, actor_hidden_dim=64,
                   mixing_embed_dim=32, hyper_hidden_dim=64),
+    # BASELINE.json configs[2]: 8 jammers x 16 radars x 4 target types -> 33 actions, state = 16 x (6 + 4) + 2 x 8 = 176
+    "c3": dict(n_agents=8, n_actions=33, state_shape=176, obs_shape=176),
+    # BASELINE.json configs[3]: the learner stress dims (GRU 256, mixer embed 128)
+    "c4": dict(rnn_hidden_dim=256, mixing_embed_dim=128),
 }
+AGENT_SEEDS = {"c1": (42, 100, 6), "small": (7, 101, 5), "c3": (11, 102, 4), "c4": (12, 103, 6)}      # torch seed, numpy seed, B
+MIXER_SEEDS = {"c1": 3, "small": 4, "c3": 5, "c4": 6}
+
+
+def wanted(name):
+    only = os.environ.get("MAKE_GOLDEN_NAMES")
+    return only is None or name in only.split(",")
 
 
 def realistic_obs(rng, shape):
@@ -236,13 +248,15 @@ def gen_agent():
     import torch
     from core.mac import BasicMAC
     for name, kw in NET_CONFIGS.items():
+        if not wanted(name):
+            continue
         args = rl_args(**kw)
-        torch.manual_seed(42 if name == "c1" else 7)
+        torch.manual_seed(AGENT_SEEDS[name][0])
         with quiet():
             mac = BasicMAC(args.obs_shape, args)
         sd = {k: v.detach().clone() for k, v in mac.agent.state_dict().items()}
-        rng = np.random.default_rng(100 if name == "c1" else 101)
-        B, Nn, O, A, H = (6 if name == "c1" else 5), args.n_agents, args.obs_shape, args.n_actions, args.rnn_hidden_dim
+        rng = np.random.default_rng(AGENT_SEEDS[name][1])
+        B, Nn, O, A, H = AGENT_SEEDS[name][2], args.n_agents, args.obs_shape, args.n_actions, args.rnn_hidden_dim
         steps = 4
         out = {f"sd.{k}": v.numpy() for k, v in sd.items()}
         out["n_params"] = np.array(sum(v.numel() for v in sd.values()))
@@ -294,8 +308,10 @@ def gen_mixer():
     import torch
     from core.networks import QMixer
     for name, kw in NET_CONFIGS.items():
+        if not wanted(name):
+            continue
         args = rl_args(**kw)
-        torch.manual_seed(3 if name == "c1" else 4)
+        torch.manual_seed(MIXER_SEEDS[name])
         mixer = QMixer(args)
         rng = np.random.default_rng(200)
         Rr = 37
@@ -345,6 +361,8 @@ def synthetic_batch(rng, args, B, T, ragged):
 LEARNER_CONFIGS = {
     "c1": dict(net="c1", B=4, T=7, ragged=False, lr=5e-6, interval=2, steps=3),
     "small_fastlr": dict(net="small", B=5, T=6, ragged=True, lr=1e-3, interval=2, steps=4),
+    "c3": dict(net="c3", B=3, T=5, ragged=True, lr=5e-6, interval=2, steps=2),
+    "c4": dict(net="c4", B=4, T=6, ragged=False, lr=1e-4, interval=1, steps=2),
 }
 
 
@@ -353,6 +371,8 @@ def gen_learner():
     from core.mac import BasicMAC
     from core.qmix import QMixLearner
     for name, c in LEARNER_CONFIGS.items():
+        if not wanted(name):
+            continue
         args = rl_args(**NET_CONFIGS[c["net"]], lr=c["lr"], target_update_interval=c["interval"])
         torch.manual_seed(42)
         with quiet():

@@ -70,6 +70,20 @@ def make_learner(args, agent_sd, mixer_sd, device, lib):
     return learner
 
 
+def _check_adam_delta(new, ref_new, w0, ref_grad, lr, k_adam, tiny_seen, key, step):
+    """Post-Adam weights as deltas from the initial weights, against the reference's.  Adam moves an element by
+    lr * m / (sqrt(v) + 1e-8): where the (clipped) gradient is of the order of that epsilon the move is a fraction of lr
+    that hangs on the gradient's last bits, so elements outside the bound must be such elements (|reference gradient|
+    < 1e-6 at this or an earlier step -- the deltas are cumulative), rare (<= 0.1 % of the tensor) and within one Adam
+    step per train step."""
+    tiny = tiny_seen[key] = tiny_seen.get(key, False) | (np.abs(ref_grad) < 1e-6)
+    err = np.abs((new - w0) - (ref_new - w0))
+    bad = err > lr * 5e-3 * k_adam + 2.4e-7 * np.abs(w0).max() + 5e-3 * k_adam * np.abs(ref_new - w0)
+    if bad.any():
+        assert bad.sum() <= max(2, 1e-3 * bad.size) and tiny[bad].all() and (err[bad] <= lr * (step + 1)).all(), \
+            (key, step, int(bad.sum()), bad.size, float(err.max()), int((bad & ~tiny).sum()))
+
+
 def check_learner_against_golden(name, device, lib, path=1):
     """Whole train steps against the unmodified reference learner: stats, (clipped) gradients
     of every trained tensor, post-Adam weights, target sync; untrained tensors stay frozen.
@@ -82,6 +96,7 @@ def check_learner_against_golden(name, device, lib, path=1):
     k_stats, k_grad, k_adam = (1.0, 1.0, 1.0) if path == 1 else (4.0, 4.0, 2.0)
     agent0, mixer0 = _sd(g, "agent0."), _sd(g, "mixer0.")
     L = make_learner(args, agent0, mixer0, device, lib)
+    tiny_seen = {}
     for step in range(int(g["n_steps"])):
         pre = f"step{step}."
         batch = {}
@@ -107,9 +122,8 @@ def check_learner_against_golden(name, device, lib, path=1):
         sd_now = {k: v.detach().cpu().numpy() for k, v in L.mac.agent.state_dict().items()}
         for k in agent0:
             if k in AO.TRAINED_AGENT_KEYS:
-                w0 = agent0[k].numpy()
-                np.testing.assert_allclose(sd_now[k] - w0, g[pre + "agent." + k] - w0, rtol=5e-3 * k_adam,
-                                           atol=args.lr * 5e-3 * k_adam + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+                _check_adam_delta(sd_now[k], g[pre + "agent." + k], agent0[k].numpy(), g[pre + "agent_grad." + k], args.lr, k_adam,
+                                  tiny_seen, "agent." + k, step)
             else:
                 np.testing.assert_array_equal(sd_now[k], agent0[k].numpy(), err_msg=f"{k} must stay frozen")
         tgt_now = L.target_mac.agent.state_dict()
@@ -118,9 +132,8 @@ def check_learner_against_golden(name, device, lib, path=1):
         mix_now = L.eval_qmix_net.state_dict()
         tmix_now = L.target_qmix_net.state_dict()
         for k in mixer0:
-            w0 = mixer0[k].numpy()
-            np.testing.assert_allclose(mix_now[k].cpu().numpy() - w0, g[pre + "mixer." + k] - w0, rtol=5e-3 * k_adam,
-                                       atol=args.lr * 5e-3 * k_adam + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+            _check_adam_delta(mix_now[k].cpu().numpy(), g[pre + "mixer." + k], mixer0[k].numpy(), g[pre + "mixer_grad." + k], args.lr,
+                              k_adam, tiny_seen, "mixer." + k, step)
             np.testing.assert_allclose(tmix_now[k].cpu().numpy(), g[pre + "tgt_mixer." + k], rtol=1e-5, atol=1e-6)
     return L
 

@@ -6,12 +6,12 @@ from tests import agent_checks as AC
 from tests.helpers import emul_lib
 
 
-@pytest.mark.parametrize("name", ["c1", "small"])
+@pytest.mark.parametrize("name", ["c1", "small", "c3", "c4"])
 def test_select_actions_vs_reference(name):
     AC.check_mac_against_golden(name, "cpu", emul_lib())
 
 
-@pytest.mark.parametrize("name", ["c1", "small"])
+@pytest.mark.parametrize("name", ["c1", "small", "c3", "c4"])
 def test_q_params_hidden_vs_reference(name):
     AC.check_agent_outputs_against_golden(name, "cpu", emul_lib())
 

@@ -6,12 +6,12 @@ from tests import learner_checks as LC
 from tests.helpers import emul_lib
 
 
-@pytest.mark.parametrize("name", ["c1", "small"])
+@pytest.mark.parametrize("name", ["c1", "small", "c3", "c4"])
 def test_mixer_forward_backward(name):
     LC.check_mixer_against_golden(name, "cpu", emul_lib())
 
 
-@pytest.mark.parametrize("name", ["c1", "small_fastlr"])
+@pytest.mark.parametrize("name", ["c1", "small_fastlr", "c3", "c4"])
 def test_learner_train_steps(name):
     LC.check_learner_against_golden(name, "cpu", emul_lib())
 

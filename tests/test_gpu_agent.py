@@ -8,12 +8,12 @@ from tests import agent_checks as AC
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["c1", "small"])
+@pytest.mark.parametrize("name", ["c1", "small", "c3", "c4"])
 def test_select_actions_vs_reference(name):
     AC.check_mac_against_golden(name, "cuda")
 
 
-@pytest.mark.parametrize("name", ["c1", "small"])
+@pytest.mark.parametrize("name", ["c1", "small", "c3", "c4"])
 def test_q_params_hidden_vs_reference(name):
     AC.check_agent_outputs_against_golden(name, "cuda")
 
@@ -87,7 +87,7 @@ def test_tensor_core_path_matches_simt_path(M, T, tc_path):
 
 
 @pytest.mark.parametrize("tc_path", [3])
-@pytest.mark.parametrize("name", ["c1"])
+@pytest.mark.parametrize("name", ["c1", "c3"])
 def test_tensor_core_path_vs_reference_golden(name, tc_path):
     """The tcgen05 path against the reference's recorded outputs, with its stated looser bound:
     realistic observation magnitudes (hundreds) put pre-activations near 30-100, where the 3xTF32

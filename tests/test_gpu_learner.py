@@ -15,13 +15,13 @@ def lib():
     return N.get_lib()
 
 
-@pytest.mark.parametrize("name", ["c1", "small"])
+@pytest.mark.parametrize("name", ["c1", "small", "c3", "c4"])
 def test_mixer_forward_backward(name):
     LC.check_mixer_against_golden(name, "cuda", lib())
 
 
 @pytest.mark.parametrize("path", [1, 0])
-@pytest.mark.parametrize("name", ["c1", "small_fastlr"])
+@pytest.mark.parametrize("name", ["c1", "small_fastlr", "c3", "c4"])
 def test_learner_train_steps(name, path):
     """path 0 = what bench.py runs (tcgen05 pair kernel, split unrolls on side streams)."""
     LC.check_learner_against_golden(name, "cuda", lib(), path=path)

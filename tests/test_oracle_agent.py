@@ -21,7 +21,7 @@ def sd_of(g, prefix="sd."):
     return {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
 
 
-@pytest.mark.parametrize("name", ["c1", "small"])
+@pytest.mark.parametrize("name", ["c1", "small", "c3", "c4"])
 def test_agent_and_selector(name):
     g, args = load("agent_" + name)
     sd = sd_of(g)
@@ -49,7 +49,7 @@ def test_agent_and_selector(name):
         h = torch.from_numpy(g["hidden"][t])
 
 
-@pytest.mark.parametrize("name", ["c1", "small"])
+@pytest.mark.parametrize("name", ["c1", "small", "c3", "c4"])
 def test_mixer_forward_and_gradients(name):
     g, args = load("mixer_" + name)
     msd = {k: v.clone().requires_grad_(True) for k, v in sd_of(g).items()}
@@ -65,12 +65,13 @@ def test_mixer_forward_and_gradients(name):
         np.testing.assert_allclose(v.grad.numpy(), ref, rtol=1e-4, atol=1e-5 * max(1.0, np.abs(ref).max()), err_msg=k)
 
 
-@pytest.mark.parametrize("name", ["c1", "small_fastlr"])
+@pytest.mark.parametrize("name", ["c1", "small_fastlr", "c3", "c4"])
 def test_learner_steps(name):
     g, args = load("learner_" + name)
     agent0, mixer0 = sd_of(g, "agent0."), sd_of(g, "mixer0.")
     L = AO.LearnerOracle(agent0, mixer0, args["n_agents"], args["mixing_embed_dim"], args["gamma"], args["lr"],
                          args["grad_norm_clip"], args["target_update_interval"])
+    tiny_seen = {}
     for step in range(int(g["n_steps"])):
         pre = f"step{step}."
         batch = {}
@@ -91,11 +92,19 @@ def test_learner_steps(name):
             kind, key = name_.split(".", 1)
             ref_g = g[pre + ("agent_grad." if kind == "agent" else "mixer_grad.") + key]
             np.testing.assert_allclose(gr.numpy() * coef, ref_g, rtol=2e-4, atol=2e-6 * max(1e-3, np.abs(ref_g).max()), err_msg=name_)
+        def check_delta(new, ref_new, w0, ref_grad, k):
+            # Adam moves an element by lr * m / (sqrt(v) + 1e-8): where the (clipped) gradient is of the order of that
+            # epsilon the move is a fraction of lr that hangs on the gradient's last bits.  Elements outside the tight
+            # bound must be such elements, rare (1 of 65 536 in hyper_w_1.2.weight at the C3 dims), and within one step.
+            # (deltas are cumulative over the steps, so an element stays excused once it has had such a gradient)
+            tiny = tiny_seen[k] = tiny_seen.get(k, False) | (np.abs(ref_grad) < 1e-6)
+            err = np.abs((new - w0) - (ref_new - w0))
+            bad = err > args["lr"] * 2e-3 + 2.4e-7 * np.abs(w0).max() + 2e-3 * np.abs(ref_new - w0)
+            if bad.any():
+                assert bad.sum() <= max(2, 1e-4 * bad.size) and tiny[bad].all() and (err[bad] <= args["lr"]).all(), (k, int(bad.sum()), float(err.max()))
         for k in AO.TRAINED_AGENT_KEYS:
-            w0 = agent0[k].numpy()
-            np.testing.assert_allclose(L.agent[k].numpy() - w0, g[pre + "agent." + k] - w0, rtol=2e-3, atol=args["lr"] * 2e-3 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+            check_delta(L.agent[k].numpy(), g[pre + "agent." + k], agent0[k].numpy(), g[pre + "agent_grad." + k], k)
             np.testing.assert_allclose(L.tgt_agent[k].numpy(), g[pre + "tgt_agent." + k], rtol=1e-5, atol=1e-6)
         for k in mixer0:
-            w0 = mixer0[k].numpy()
-            np.testing.assert_allclose(L.mixer[k].numpy() - w0, g[pre + "mixer." + k] - w0, rtol=2e-3, atol=args["lr"] * 2e-3 + 2.4e-7 * np.abs(w0).max(), err_msg=k)
+            check_delta(L.mixer[k].numpy(), g[pre + "mixer." + k], mixer0[k].numpy(), g[pre + "mixer_grad." + k], k)
             np.testing.assert_allclose(L.tgt_mixer[k].numpy(), g[pre + "tgt_mixer." + k], rtol=1e-5, atol=1e-6)
