@@ -21,7 +21,7 @@ def _np(t):
 def check_env_against_golden(make_env, name):
     """Drive the kernel with the exact action / noise sequences the unmodified reference
     saw: integer outputs bit-exact, float64 reward to 1e-10, float32 views to an ulp."""
-    g, cfg = load_env_golden(name)
+    g, cfg = load_env_golden(name) if isinstance(name, str) else name        # (or a recording: (arrays, config))
     n_eps, T = g["reward"].shape
     env = make_env(spec_for_golden(g, cfg, n_envs=n_eps))
     dev = env.device

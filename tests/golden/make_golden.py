@@ -22,7 +22,7 @@ import types
 
 import numpy as np
 
-REF = "/root/reference"
+REF = os.environ.get("MAKE_GOLDEN_REF", "/root/reference")     # (tests/test_oracle_live_reference.py points it at baseline/_ref)
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REF)
@@ -114,23 +114,32 @@ def f32_uniform(rng, size=None):
 
 
 def gen_env():
+    for name, fn in SCENARIOS.items():
+        cfg = fn()
+        rl = types.SimpleNamespace(episode_limit=7) if name == "active" else types.SimpleNamespace()
+        n_eps, T = (4, 60) if name != "active" else (6, 40)
+        arrs = record_env(cfg, rl, {"default": 11, "selftest": 12, "active": 13}[name], n_eps, T)
+        np.savez_compressed(os.path.join(HERE, f"env_{name}.npz"), **arrs)
+        print(f"env_{name}: {n_eps}x{T} steps, reward range [{arrs['reward'].min():.4f}, {arrs['reward'].max():.4f}], "
+              f"pd range [{arrs['pd'].min():.4f}, {arrs['pd'].max():.4f}], r_j max {arrs['r_j'].max():.4f}")
+
+
+def record_env(cfg, rl, seed, n_eps, T):
+    """Drive ONE unmodified reference environment through n_eps episodes of T steps with seeded actions and injected
+    uniform draws; returns everything the oracle / kernel checks compare against (the arrays of an env_*.npz)."""
     from simulation.environment import ElectromagneticEnvironment
     import simulation.environment as envmod  # noqa: F401
 
-    out = {}
-    for name, fn in SCENARIOS.items():
-        cfg = fn()
+    if True:
         with tempfile.TemporaryDirectory() as td:
             path = os.path.join(td, "sim.yaml")
             with open(path, "w") as f:
                 yaml.safe_dump(cfg, f)
-            rl = types.SimpleNamespace(episode_limit=7) if name == "active" else types.SimpleNamespace()
             with quiet():
                 env = ElectromagneticEnvironment(rl, sim_config_path=path)
         R, J = env.num_radars, env.num_jammers
         A = 2 * R + 1
-        rng = np.random.default_rng({"default": 11, "selftest": 12, "active": 13}[name])
-        n_eps, T = (4, 60) if name != "active" else (6, 40)
+        rng = np.random.default_rng(seed)
         info0 = env.get_env_info()
         rec = {k: [] for k in ("act_d", "act_p", "noise", "reward", "r_d", "r_p", "r_j", "pd", "snr0",
                                "snr1", "tracking", "terminated", "step_count", "n_rng_draws")}
@@ -204,9 +213,61 @@ def gen_env():
         arrs["echo_ps"] = np.array([r.calculate_echo_power(tpos, env.protected_target_config["rcs"]) for r in env.radars])
         arrs["pd_table_snr"] = np.array([0.0, 1e-5, 0.05, 0.2163, 0.5, 1.0, 2.0, 5.0, 80.0, 1e3])
         arrs["pd_table"] = np.array([env.radars[0].detection_probability(s) for s in arrs["pd_table_snr"]])
-        np.savez_compressed(os.path.join(HERE, f"env_{name}.npz"), **arrs)
-        print(f"env_{name}: {n_eps}x{T} steps, reward range [{arrs['reward'].min():.4f}, {arrs['reward'].max():.4f}], "
-              f"pd range [{arrs['pd'].min():.4f}, {arrs['pd'].max():.4f}], r_j max {arrs['r_j'].max():.4f}")
+        return arrs
+
+
+def scenario_random(seed):
+    """A random scenario for the live differential test: 1-5 radars, 1-4 jammers, random geometry, gains, losses,
+    bandwidths, power ranges, radar types and threat levels; transmit powers scaled so that the un-jammed SNR lands
+    between 0.3 and 4 (Pd between ~0.25 and ~1) and jamming powers that move it."""
+    rng = np.random.default_rng(seed)
+    R, J = int(rng.integers(1, 6)), int(rng.integers(1, 5))
+    n_types = int(rng.integers(max(2, 1), 6))
+    u = lambda lo, hi: float(np.round(rng.uniform(lo, hi), 4))
+    tpos = [u(-50, 50), u(-50, 50)]
+    radars = []
+    for _ in range(R):
+        ang, dist = rng.uniform(0, 2 * np.pi), rng.uniform(300, 3000)
+        radars.append(dict(pt=1.0, gt=u(20, 35), gr=u(20, 35), wavelength=u(0.02, 0.1), rcs=u(0.5, 2.0), loss=u(2, 10), latm=u(0.5, 3),
+                           pn=u(-95, -55), type_id=int(rng.integers(0, n_types)),
+                           position=[float(np.round(tpos[0] + dist * np.cos(ang), 3)), float(np.round(tpos[1] + dist * np.sin(ang), 3))],
+                           theta_m=u(1, 4), theta_a=u(0, 360), t_s=u(1, 8), pulse_compression_gain=u(20, 150),
+                           anti_jamming_factor=u(1, 20), threat_level=u(0.4, 1.6)))
+    jammers = []
+    for _ in range(J):
+        pmin = u(0, 2) if rng.random() < 0.5 else 0.0
+        pmax = pmin if rng.random() < 0.15 else pmin + u(0.1, 20)
+        jammers.append(dict(power=u(1, 10), gj=u(0, 25), loss=u(1, 6), latm=u(0.5, 3), bj=float(np.round(rng.uniform(0.5e6, 5e6), 0)),
+                            position=[u(-200, 200), u(-200, 200)], power_min=pmin, power_max=float(np.round(pmax, 4))))
+    cfg = {"radars": radars, "jammers": jammers, "protected_target": dict(position=tpos, rcs=u(0.5, 5.0)),
+           "environment_params": dict(max_radar_types=n_types, rewards=dict(rd_min=u(-1.5, -1.0), rd_max=u(-0.9, -0.5),
+                                                                             rp_min=u(-0.3, -0.1), rp_max=u(-0.05, -0.005)))}
+    lin = lambda d: 10 ** (d / 10.0)
+    for r in radars:
+        d = ((r["position"][0] - tpos[0]) ** 2 + (r["position"][1] - tpos[1]) ** 2) ** 0.5
+        unit = (lin(r["gt"]) * lin(r["gr"]) * r["wavelength"] ** 2 * cfg["protected_target"]["rcs"]
+                / ((4 * np.pi) ** 3 * d ** 4 * lin(r["loss"]) * lin(r["latm"])))
+        pn_w = 10 ** ((r["pn"] - 30) / 10)
+        r["pt"] = float(f"{rng.uniform(0.3, 4.0) * pn_w / (r['pulse_compression_gain'] * unit):.5g}")
+    return cfg
+
+
+def gen_env_random():
+    """Four random scenarios (seeds 300-303) committed as env_rand{0..3}.npz: they travel to the GPU box, where the live
+    differential test (tests/test_oracle_live_reference.py) cannot run."""
+    gen_live(HERE, 300, 4, prefix="env_rand")
+
+
+def gen_live(outdir, seed0, count, prefix="env_live_"):
+    """`make_golden.py live OUTDIR SEED COUNT`: COUNT random scenarios recorded from the reference into OUTDIR (not
+    committed: tests/test_oracle_live_reference.py calls this in a subprocess when a copy of the reference is present)."""
+    for i in range(count):
+        cfg = scenario_random(seed0 + i)
+        limit = int(np.random.default_rng(seed0 + i).integers(5, 30))
+        arrs = record_env(cfg, types.SimpleNamespace(episode_limit=limit), 1000 + seed0 + i, 3, limit + 3)
+        np.savez_compressed(os.path.join(outdir, f"{prefix}{i}.npz"), **arrs)
+        print(f"{prefix}{i}: R={len(cfg['radars'])} J={len(cfg['jammers'])} limit={limit} pd range [{arrs['pd'].min():.3f}, {arrs['pd'].max():.3f}] "
+              f"r_j max {arrs['r_j'].max():.3f} terminated {int(arrs['terminated'].sum())}")
 
 
 # ------------------------------------------------------------------ networks
@@ -478,11 +539,14 @@ def gen_api():
     print("api:", {k: len(v) for k, v in api.items()})
 
 
-GENERATORS = {"env": gen_env, "agent": gen_agent, "mixer": gen_mixer, "learner": gen_learner,
+GENERATORS = {"env": gen_env, "env_random": gen_env_random, "agent": gen_agent, "mixer": gen_mixer, "learner": gen_learner,
               "replay": gen_replay, "api": gen_api}
 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)
     os.chdir(REF)  # the reference resolves config/ relative to the cwd
+    if which[0] == "live":
+        gen_live(which[1], int(which[2]), int(which[3]))
+        sys.exit(0)
     for w in which:
         GENERATORS[w]()

@@ -12,7 +12,7 @@ from oracle.env_oracle import EnvOracle, device_noise
 from tests.helpers import emul_lib, load_env_golden, spec_for_golden
 from tests.env_checks import check_env_against_golden, check_env_against_oracle, check_shim_types
 
-SCEN = ["default", "selftest", "active"]
+SCEN = ["default", "selftest", "active", "rand0", "rand1", "rand2", "rand3"]      # rand*: random scenarios (make_golden.py env_random)
 
 
 def make_env(spec, **kw):

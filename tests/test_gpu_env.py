@@ -16,7 +16,7 @@ def make_env(spec, **kw):
     return ElectromagneticEnvironment(types.SimpleNamespace(), spec=spec, device="cuda", **kw)
 
 
-@pytest.mark.parametrize("name", ["default", "selftest", "active"])
+@pytest.mark.parametrize("name", ["default", "selftest", "active", "rand0", "rand1", "rand2", "rand3"])
 def test_env_kernel_vs_reference_golden(name):
     check_env_against_golden(make_env, name)
 

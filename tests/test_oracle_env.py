@@ -9,7 +9,7 @@ from oracle.env_oracle import (EnvOracle, albersheim_pd, compact_noise_for_refer
                                device_noise, philox4x32_10)
 from tests.helpers import load_env_golden, spec_for_golden
 
-SCEN = ["default", "selftest", "active"]
+SCEN = ["default", "selftest", "active", "rand0", "rand1", "rand2", "rand3"]      # rand*: random scenarios (make_golden.py env_random)
 RTOL = 1e-12  # float64 restatement vs float64 reference: operation-order noise only
 
 
@@ -41,6 +41,11 @@ def test_entity_constants(name):
 @pytest.mark.parametrize("name", SCEN)
 def test_step_sequences_match_reference(name):
     g, cfg = load_env_golden(name)
+    check_step_sequences(g, cfg)
+
+
+def check_step_sequences(g, cfg):
+    """The oracle against one recording of the reference (the arrays of tests/golden/make_golden.py:record_env)."""
     n_eps, T = g["reward"].shape
     # all golden episodes advance side by side as a batch of n_eps envs
     env = EnvOracle(spec_for_golden(g, cfg, n_envs=n_eps))
