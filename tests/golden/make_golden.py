@@ -258,6 +258,30 @@ def gen_env_random():
     gen_live(HERE, 300, 4, prefix="env_rand")
 
 
+def gen_live_nets(outdir, seed0, count):
+    """`make_golden.py live_nets OUTDIR SEED COUNT`: agent / mixer / learner recordings of the reference at COUNT random
+    sets of network dims (names live0 ..), into OUTDIR -- for tests/test_oracle_live_reference.py, not committed."""
+    global HERE
+    rng = np.random.default_rng(seed0)
+    names = []
+    for i in range(count):
+        name = f"live{i}"
+        S = int(rng.integers(5, 61))
+        NET_CONFIGS[name] = dict(n_agents=int(rng.integers(1, 7)), n_actions=int(rng.integers(2, 17)), state_shape=S, obs_shape=S,
+                                 rnn_hidden_dim=int(rng.choice([64, 128, 192])), actor_hidden_dim=int(rng.choice([64, 128])),
+                                 mixing_embed_dim=int(rng.choice([16, 32, 64])), hyper_hidden_dim=int(rng.choice([32, 64, 128])))
+        AGENT_SEEDS[name] = (int(rng.integers(1, 1 << 30)), int(rng.integers(1, 1 << 30)), int(rng.integers(2, 8)))
+        MIXER_SEEDS[name] = int(rng.integers(1, 1 << 30))
+        LEARNER_CONFIGS[name] = dict(net=name, B=int(rng.integers(2, 6)), T=int(rng.integers(3, 8)), ragged=bool(rng.random() < 0.5),
+                                     lr=float(rng.choice([5e-6, 1e-4, 1e-3])), interval=int(rng.integers(1, 4)), steps=3)
+        names.append(name)
+    os.environ["MAKE_GOLDEN_NAMES"] = ",".join(names)
+    HERE = outdir
+    gen_agent()
+    gen_mixer()
+    gen_learner()
+
+
 def gen_live(outdir, seed0, count, prefix="env_live_"):
     """`make_golden.py live OUTDIR SEED COUNT`: COUNT random scenarios recorded from the reference into OUTDIR (not
     committed: tests/test_oracle_live_reference.py calls this in a subprocess when a copy of the reference is present)."""
@@ -545,8 +569,8 @@ GENERATORS = {"env": gen_env, "env_random": gen_env_random, "agent": gen_agent, 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)
     os.chdir(REF)  # the reference resolves config/ relative to the cwd
-    if which[0] == "live":
-        gen_live(which[1], int(which[2]), int(which[3]))
+    if which[0] in ("live", "live_nets"):
+        (gen_live if which[0] == "live" else gen_live_nets)(which[1], int(which[2]), int(which[3]))
         sys.exit(0)
     for w in which:
         GENERATORS[w]()

@@ -108,7 +108,7 @@ def check_learner_against_golden(name, device, lib, path=1):
         dbg = stats.pop("debug")
         ref = g[pre + "stats"]
         np.testing.assert_allclose([stats["loss"], stats["grad_norm"], stats["eval_qtot_avg"], stats["target_qtot_avg"]],
-                                   ref, rtol=5e-5 * k_stats, err_msg=f"stats step {step}")
+                                   ref, rtol=5e-5 * k_stats, atol=5e-7 * k_stats, err_msg=f"stats step {step}")   # (atol: means that cancel)
         coef = min(1.0, args.grad_norm_clip / (stats["grad_norm"] + 1e-6))
         scale = coef / float(dbg["sums"][1])
         off = 0

@@ -82,7 +82,7 @@ def test_learner_steps(name):
         stats, grads, aux = L.train(batch)
         ref = g[pre + "stats"]
         np.testing.assert_allclose([stats["loss"], stats["grad_norm"], stats["eval_qtot_avg"], stats["target_qtot_avg"]],
-                                   ref, rtol=2e-5)
+                                   ref, rtol=2e-5, atol=2e-7)     # (atol: a Q_tot mean can cancel to ~1e-3 of its terms' scale)
         coef = min(1.0, args["grad_norm_clip"] / (stats["grad_norm"] + 1e-6))
         # the reference leaves *clipped* gradients in .grad; fc1 / rnn / actor never get one
         for k in agent0:

@@ -48,3 +48,28 @@ def test_oracle_vs_live_reference_on_random_scenarios(tmp_path, seed0):
         check_env_against_golden(make_env, (g, cfg))
         assert 0.2 < g["pd"].max() and g["terminated"].any() and (g["r_j"] > 0).any()       # the recording exercises the physics
     assert len(shapes) >= 3
+
+
+@pytest.mark.parametrize("seed0", [7, 8])
+def test_networks_vs_live_reference_at_random_dims(tmp_path, monkeypatch, seed0):
+    """Agent / selector sequences, mixer forward + backward and whole QMixLearner.train steps recorded from the live reference
+    at random network dims (1-6 agents, 2-16 actions, obs 5-60, GRU 64 / 128 / 192, actor 64 / 128, mixer embed 16-64,
+    random batch shapes, ragged episodes, learning rates, target intervals): the eager oracle (tests/test_oracle_agent.py's
+    checks) and the FP32 kernels compiled for the host (tests/agent_checks.py, tests/learner_checks.py) against them."""
+    count = 3
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden.py"), "live_nets", str(tmp_path), str(seed0), str(count)],
+                       env=dict(os.environ, MAKE_GOLDEN_REF=REF), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    from tests import agent_checks as AC, learner_checks as LC, test_oracle_agent as TOA
+    from tests.helpers import emul_lib
+    for mod in (AC, LC, TOA):
+        monkeypatch.setattr(mod, "GOLDEN", str(tmp_path))
+    for i in range(count):
+        name = f"live{i}"
+        TOA.test_agent_and_selector(name)
+        TOA.test_mixer_forward_and_gradients(name)
+        TOA.test_learner_steps(name)
+        AC.check_mac_against_golden(name, "cpu", emul_lib())
+        AC.check_agent_outputs_against_golden(name, "cpu", emul_lib())
+        LC.check_mixer_against_golden(name, "cpu", emul_lib())
+        LC.check_learner_against_golden(name, "cpu", emul_lib())
