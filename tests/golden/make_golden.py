@@ -282,6 +282,20 @@ def gen_live_nets(outdir, seed0, count):
     gen_learner()
 
 
+def gen_live_replay(outdir, seed0, count):
+    """`make_golden.py live_replay OUTDIR SEED COUNT`: random rings (capacity, dims, episode lengths, sampling points) driven
+    through the reference EpisodeReplayBuffer, the sampled indices drawn by the reference's own np.random.choice."""
+    for i in range(count):
+        rng = np.random.default_rng(seed0 + i)
+        cap, T = int(rng.integers(2, 12)), int(rng.integers(2, 10))
+        n_eps = int(rng.integers(cap, 3 * cap + 2))
+        lens = [int(T if rng.random() < 0.5 else rng.integers(1, T + 1)) for _ in range(n_eps)]
+        sample_at = sorted(set(int(x) for x in rng.integers(0, n_eps, size=4)) | {n_eps - 1})
+        gen_replay(os.path.join(outdir, f"replay_live{i}.npz"), seed=seed0 + i, cap=cap, T=T, Nn=int(rng.integers(1, 5)),
+                   A=int(rng.integers(2, 9)), S=int(rng.integers(3, 20)), H=int(rng.choice([8, 16, 64])), lens=lens, sample_at=sample_at,
+                   n_sample=int(rng.integers(1, cap + 2)), seeded_draws=True)
+
+
 def gen_live(outdir, seed0, count, prefix="env_live_"):
     """`make_golden.py live OUTDIR SEED COUNT`: COUNT random scenarios recorded from the reference into OUTDIR (not
     committed: tests/test_oracle_live_reference.py calls this in a subprocess when a copy of the reference is present)."""
@@ -496,15 +510,16 @@ def gen_learner():
         np.savez_compressed(os.path.join(HERE, f"learner_{name}.npz"), **out)
 
 
-def gen_replay():
+def gen_replay(path=None, seed=400, cap=5, T=6, Nn=2, A=5, S=8, H=16, lens=(6, 6, 3, 6, 5, 6, 6), sample_at=(2, 6), n_sample=3,
+               seeded_draws=False):
+    """Defaults: the committed replay.npz (7 episodes into a ring of 5 -> wraps; the sampled indices injected).
+    seeded_draws=True (live differential test): sample() draws its indices itself after np.random.seed(recorded seed)."""
     from utils.replay_buffer import EpisodeReplayBuffer
-    args = rl_args(buffer_size=5, episode_limit=6, n_agents=2, n_actions=5, state_shape=8, obs_shape=8, rnn_hidden_dim=16)
+    args = rl_args(buffer_size=cap, episode_limit=T, n_agents=Nn, n_actions=A, state_shape=S, obs_shape=S, rnn_hidden_dim=H)
     with quiet():
         buf = EpisodeReplayBuffer(args)
-    rng = np.random.default_rng(400)
-    T, Nn, A, S, H = 6, 2, 5, 8, 16
+    rng = np.random.default_rng(seed)
     out = {"args_json": np.array(json.dumps(vars(args)))}
-    lens = [6, 6, 3, 6, 5, 6, 6]        # 7 episodes into a ring of 5 -> wraps
     for i, L in enumerate(lens):
         ep = {
             "state": [rng.standard_normal((L + 1, S)).astype(np.float32)],
@@ -521,20 +536,32 @@ def gen_replay():
         buf.store_episode(ep)
         out[f"after{i}.current_index"] = np.array(buf.current_index)
         out[f"after{i}.current_size"] = np.array(buf.current_size)
-        if i in (2, 6):
-            idx = rng.permutation(buf.current_size)[:3]
+        if i in sample_at and seeded_draws:
+            np_seed = int(rng.integers(0, 1 << 31))
+            n_draw = min(n_sample, buf.current_size)
+            np.random.seed(np_seed)
+            idx = np.random.choice(buf.current_size, n_draw, replace=False)      # what sample() is about to draw (replay_buffer.py:178)
+            np.random.seed(np_seed)
+            with quiet():
+                b = buf.sample(n_draw)
+            out[f"sample{i}.np_seed"] = np.array(np_seed)
+            out[f"sample{i}.indices"] = idx
+            for k, v in b.items():
+                out[f"sample{i}.{k}"] = np.asarray(v)
+        elif i in sample_at:
+            idx = rng.permutation(buf.current_size)[:n_sample]
             orig = np.random.choice
             np.random.choice = lambda n, k, replace=False, _idx=idx: _idx
             try:
                 with quiet():
-                    b = buf.sample(3)
+                    b = buf.sample(n_sample)
             finally:
                 np.random.choice = orig
             out[f"sample{i}.indices"] = idx
             for k, v in b.items():
                 out[f"sample{i}.{k}"] = np.asarray(v)
     out["n_eps"] = np.array(len(lens))
-    np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
+    np.savez_compressed(path or os.path.join(HERE, "replay.npz"), **out)
     print("replay: stored", len(lens), "episodes; final index/size", buf.current_index, buf.current_size)
 
 
@@ -569,8 +596,8 @@ GENERATORS = {"env": gen_env, "env_random": gen_env_random, "agent": gen_agent, 
 if __name__ == "__main__":
     which = sys.argv[1:] or list(GENERATORS)
     os.chdir(REF)  # the reference resolves config/ relative to the cwd
-    if which[0] in ("live", "live_nets"):
-        (gen_live if which[0] == "live" else gen_live_nets)(which[1], int(which[2]), int(which[3]))
+    if which[0] in ("live", "live_nets", "live_replay"):
+        {"live": gen_live, "live_nets": gen_live_nets, "live_replay": gen_live_replay}[which[0]](which[1], int(which[2]), int(which[3]))
         sys.exit(0)
     for w in which:
         GENERATORS[w]()

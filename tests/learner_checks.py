@@ -138,11 +138,12 @@ def check_learner_against_golden(name, device, lib, path=1):
     return L
 
 
-def check_replay_against_golden(device, lib):
+def check_replay_against_golden(device, lib, name="replay"):
     """store_episode / sample against the reference ring buffer: ring index arithmetic, padding
-    rules, trimming to the longest sampled episode, dtypes of the returned dict."""
+    rules, trimming to the longest sampled episode, dtypes of the returned dict.  Recordings with a `np_seed` per sample
+    (the live differential test) also hold the public sample() to the reference's own index draws."""
     from macjd_b200.utils.replay_buffer import EpisodeReplayBuffer
-    g, args = _load("replay")
+    g, args = _load(name)
     buf = EpisodeReplayBuffer(args, device=device, _lib=lib)
     keys = ("state", "obs", "actions_discrete", "actions_continuous", "avail_actions", "reward", "terminated", "hidden_state")
     for i in range(int(g["n_eps"])):
@@ -157,11 +158,18 @@ def check_replay_against_golden(device, lib):
                 mine = out[k].cpu().numpy()
                 assert mine.shape == ref.shape, k
                 np.testing.assert_array_equal(mine.astype(ref.dtype), ref, err_msg=k)
+            if f"sample{i}.np_seed" in g.files:
+                np.random.seed(int(g[f"sample{i}.np_seed"]))
+                s = buf.sample(len(g[f"sample{i}.indices"]))
+                assert s["max_seq_len"] == int(g[f"sample{i}.max_seq_len"])
+                for k in keys + ("filled",):
+                    ref = g[f"sample{i}.{k}"]
+                    np.testing.assert_array_equal(s[k].cpu().numpy().astype(ref.dtype), ref, err_msg=f"seeded sample: {k}")
     # the public sample(): reference dtypes for masks / avail, no replacement
     np.random.seed(0)
     s = buf.sample(4)
     assert s["terminated"].dtype == torch.bool and s["filled"].dtype == torch.bool and s["avail_actions"].dtype == torch.int64
-    assert s["state"].shape[0] == 4
+    assert s["state"].shape[0] == min(4, len(buf))
     np.random.seed(0)
     s2 = buf.sample(4, time_major=True)
     assert torch.equal(s2["state"].transpose(0, 1), s["state"])

@@ -73,3 +73,19 @@ def test_networks_vs_live_reference_at_random_dims(tmp_path, monkeypatch, seed0)
         AC.check_agent_outputs_against_golden(name, "cpu", emul_lib())
         LC.check_mixer_against_golden(name, "cpu", emul_lib())
         LC.check_learner_against_golden(name, "cpu", emul_lib())
+
+
+def test_replay_ring_vs_live_reference_on_random_sequences(tmp_path, monkeypatch):
+    """Random rings (capacity 2-11, episode limit 2-9, 1-4 agents, ragged episode lengths, up to three times the capacity
+    stored, samples at random points incl. requests larger than the ring holds) through the live reference
+    EpisodeReplayBuffer (utils/replay_buffer.py:78-214) and through the product ring on the host-emulated copy kernel:
+    pointer and size after every store, gathered batches bit for bit, and sample() under the same np.random seed."""
+    count = 8
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden.py"), "live_replay", str(tmp_path), "50", str(count)],
+                       env=dict(os.environ, MAKE_GOLDEN_REF=REF), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    from tests import learner_checks as LC
+    from tests.helpers import emul_lib
+    monkeypatch.setattr(LC, "GOLDEN", str(tmp_path))
+    for i in range(count):
+        LC.check_replay_against_golden("cpu", emul_lib(), name=f"replay_live{i}")
